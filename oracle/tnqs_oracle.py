@@ -1,0 +1,639 @@
+"""CPU ORACLE — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED.
+
+NumPy complex128 (+ LAPACK through numpy.linalg: zheevd, zgeqrf/zungqr, zgesdd) restatement of the
+two hot paths of haimeng-zhang/TensorNetworkQuantumSimulator: the belief-propagation message sweep
+and the two-site gate application with SVD truncation, plus the BP expectation values, scalars,
+rescaling, symmetric gauge and BP truncation that sit on the same path.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may
+import this module, and only as the checker.  The product (`tensornetworkquantumsimulator_b200`,
+`libtnqs_cuda.so`) never imports it and has no CPU fallback.
+
+"Parity unpinned": the reference is pure Julia on ITensors; Julia is not installed here or on the GPU
+box, the numerics live in un-vendored packages (ITensors 0.9, NamedGraphs 0.7, TensorOperations 5.2,
+SimpleGraphAlgorithms 0.6; `Project.toml:30-51`, no Manifest), and the reference's tests hold no golden
+vectors.  What pins this restatement instead (tests/test_oracle_*.py):
+an independent exact statevector simulator, BP exactness on trees, the reference's own property tests
+(test/test_apply.jl:11-53, test/test_beliefpropagation.jl:26-53, test/test_constructors.jl:69-73,
+test/test_truncate.jl:16-33) and the physical invariants of the symmetric gauge.
+
+Every function cites the reference file:line it follows (paths relative to /root/reference).
+Conventions: site tensor of v = ndarray [s, b_e1 .. b_ez], incident edges ascending; message of the
+directed edge k=2e+dir = ndarray m[b, b'] (b contracts the ket leg, b' the bra leg).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from tensornetworkquantumsimulator_b200 import gates as _gates
+from tensornetworkquantumsimulator_b200 import rng as _rng
+from tensornetworkquantumsimulator_b200.graphs import Graph, forest_cover_edge_sequence, edge_color
+
+EPS = float(np.finfo(np.float64).eps)
+DEFAULT_BP_MAXITER = 25          # src/MessagePassing/beliefpropagationcache.jl:108
+DEFAULT_TOL_F64 = 1.0e-8         # src/MessagePassing/beliefpropagationcache.jl:109-112
+
+
+# ---------------------------------------------------------------------------------------------
+# containers  (src/TensorNetworks/tensornetworkstate.jl:4-18, src/MessagePassing/beliefpropagationcache.jl:9-13)
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class TensorNetworkState:
+    g: Graph
+    tensors: List[np.ndarray]
+
+    def copy(self) -> "TensorNetworkState":
+        return TensorNetworkState(self.g, [t.copy() for t in self.tensors])
+
+    def bond_dim(self, e: int) -> int:
+        v = int(self.g.esrc[e])
+        return self.tensors[v].shape[1 + self.g.leg(v, e)]
+
+    def bond_dims(self) -> np.ndarray:
+        return np.array([self.bond_dim(e) for e in range(self.g.ne)], dtype=np.int32)
+
+    def maxvirtualdim(self) -> int:
+        return int(self.bond_dims().max()) if self.g.ne else 1
+
+
+@dataclass
+class BeliefPropagationCache:
+    network: TensorNetworkState
+    messages: Dict[int, np.ndarray] = field(default_factory=dict)
+
+    def copy(self) -> "BeliefPropagationCache":
+        return BeliefPropagationCache(self.network.copy(), {k: m.copy() for k, m in self.messages.items()})
+
+    @property
+    def g(self) -> Graph:
+        return self.network.g
+
+
+def tensornetworkstate(f, g: Graph) -> TensorNetworkState:
+    """Product state, all bonds of dimension 1 (src/TensorNetworks/tensornetworkstate.jl:124-144)."""
+    ts = []
+    for v in range(g.nv):
+        vec = _gates.state_vector(f(g.names[v]))
+        ts.append(vec.reshape((vec.shape[0],) + (1,) * g.degree(v)).copy())
+    return TensorNetworkState(g, ts)
+
+
+def random_tensornetworkstate(g: Graph, bond_dimension: int = 1, seed: int = 0, d: int = 2) -> TensorNetworkState:
+    """Random N(0,1)+iN(0,1) entries (src/TensorNetworks/tensornetworkstate.jl:82-92), drawn from the
+    counter-based generator: stream = vertex id, element index = column-major offset."""
+    ts = []
+    for v in range(g.nv):
+        shape = (d,) + (bond_dimension,) * g.degree(v)
+        flat = _rng.complex_normal(seed, v, int(np.prod(shape)))
+        ts.append(flat.reshape(shape, order="F").copy())
+    return TensorNetworkState(g, ts)
+
+
+# ---------------------------------------------------------------------------------------------
+# messages
+# ---------------------------------------------------------------------------------------------
+def message(bpc: BeliefPropagationCache, k: int) -> np.ndarray:
+    """Stored message or the un-normalised identity default
+    (src/MessagePassing/abstractbeliefpropagationcache.jl:88-91, src/TensorNetworks/tensornetworkstate.jl:64-67)."""
+    m = bpc.messages.get(k)
+    if m is None:
+        chi = bpc.network.bond_dim(k // 2)
+        return np.eye(chi, dtype=np.complex128)
+    return m
+
+
+def _absorb(t: np.ndarray, axis: int, m: np.ndarray) -> np.ndarray:
+    """out[.., c, ..] = sum_b t[.., b, ..] m[b, c] on `axis`."""
+    return np.moveaxis(np.tensordot(t, m, axes=([axis], [0])), -1, axis)
+
+
+def incoming(bpc: BeliefPropagationCache, v: int, ignore: Sequence[int] = ()) -> List[Tuple[int, np.ndarray]]:
+    """(leg axis, message) for every message into v except those from vertices in `ignore`
+    (src/MessagePassing/abstractbeliefpropagationcache.jl:132-142)."""
+    g = bpc.g
+    out = []
+    for i, e in enumerate(g.incident[v]):
+        u = g.other(e, v)
+        if u in ignore:
+            continue
+        out.append((1 + i, message(bpc, g.dedge(u, v))))
+    return out
+
+
+def updated_message(bpc: BeliefPropagationCache, k: int, normalize: bool = True,
+                    enforce_hermiticity: bool = False) -> np.ndarray:
+    """src/MessagePassing/abstractbeliefpropagationcache.jl:144-168: absorb the incoming messages of
+    src(k) (all but the one from dst(k)) into the ket, close with the bra, optionally hermitise,
+    divide by the sum of ALL entries."""
+    g = bpc.g
+    v, w = g.dsrc(k), g.ddst(k)
+    t = bpc.network.tensors[v]
+    a = t
+    for axis, m in incoming(bpc, v, ignore=(w,)):
+        a = _absorb(a, axis, m)
+    ax_w = 1 + g.leg(v, k // 2)
+    others = [i for i in range(t.ndim) if i != ax_w]
+    out = np.tensordot(a, t.conj(), axes=(others, others))          # [b_w, b_w']
+    if enforce_hermiticity:                                          # beliefpropagationcache.jl:123-127
+        out = (out + out.conj().T) / 2
+    if normalize:
+        s = out.sum()
+        if s != 0:
+            out = out / s
+    return out
+
+
+def message_diff(a: np.ndarray, b: np.ndarray) -> float:
+    """1 - |<a,b>|^2 / (|a|^2 |b|^2)  (src/MessagePassing/beliefpropagationcache.jl:15-19)."""
+    na, nb = np.linalg.norm(a), np.linalg.norm(b)
+    f = abs(np.vdot(a, b) / (na * nb)) ** 2
+    return 1.0 - f
+
+
+def default_bp_update_kwargs(tns: TensorNetworkState) -> dict:
+    """src/MessagePassing/beliefpropagationcache.jl:114-119."""
+    return dict(maxiter=1 if tns.g.is_tree() else DEFAULT_BP_MAXITER, tolerance=DEFAULT_TOL_F64)
+
+
+def update(bpc: BeliefPropagationCache, maxiter: Optional[int] = None, tolerance: Optional[float] = None,
+           edge_sequence: Optional[Sequence[int]] = None, normalize: bool = True,
+           enforce_hermiticity: bool = False, info: Optional[dict] = None) -> BeliefPropagationCache:
+    """Sequential Gauss-Seidel BP (src/MessagePassing/abstractbeliefpropagationcache.jl:182-218, defaults
+    src/MessagePassing/beliefpropagationcache.jl:56-65): bare `update(bpc)` has tolerance=None and runs all
+    `maxiter` sweeps (25, or 1 on trees)."""
+    g = bpc.g
+    if maxiter is None:
+        maxiter = 1 if g.is_tree() else DEFAULT_BP_MAXITER
+    if edge_sequence is None:
+        edge_sequence = forest_cover_edge_sequence(g)
+    bpc = bpc.copy()
+    iters, mean = 0, float("nan")
+    for it in range(1, maxiter + 1):
+        iters = it
+        diff = 0.0
+        for k in edge_sequence:
+            k = int(k)
+            prev = message(bpc, k) if tolerance is not None else None
+            new = updated_message(bpc, k, normalize, enforce_hermiticity)
+            bpc.messages[k] = new
+            if tolerance is not None:
+                diff += message_diff(new, prev)
+        if tolerance is not None:
+            mean = diff / len(edge_sequence)
+            if mean <= tolerance:
+                break
+    if info is not None:
+        info["iters"] = iters
+        info["mean_diff"] = mean
+    return bpc
+
+
+# ---------------------------------------------------------------------------------------------
+# scalars, partition function, rescale
+# ---------------------------------------------------------------------------------------------
+def vertex_scalar(bpc: BeliefPropagationCache, v: int) -> complex:
+    """src/MessagePassing/abstractbeliefpropagationcache.jl:21-27."""
+    t = bpc.network.tensors[v]
+    a = t
+    for axis, m in incoming(bpc, v):
+        a = _absorb(a, axis, m)
+    return complex(np.vdot(t, a))            # sum conj(t) * a
+
+
+def edge_scalar(bpc: BeliefPropagationCache, e: int) -> complex:
+    """src/MessagePassing/beliefpropagationcache.jl:38-40: sum_{b,b'} m_e[b,b'] m_rev[b,b']."""
+    return complex(np.sum(message(bpc, 2 * e) * message(bpc, 2 * e + 1)))
+
+
+def freenergy(bpc: BeliefPropagationCache) -> complex:
+    """src/MessagePassing/abstractbeliefpropagationcache.jl:252-263."""
+    num = np.array([vertex_scalar(bpc, v) for v in range(bpc.g.nv)])
+    den = np.array([edge_scalar(bpc, e) for e in range(bpc.g.ne)])
+    if np.any(den == 0):
+        return -math.inf
+    return np.sum(np.log(num.astype(np.complex128))) - np.sum(np.log(den.astype(np.complex128)))
+
+
+def partitionfunction(bpc: BeliefPropagationCache) -> complex:
+    return complex(np.exp(freenergy(bpc)))
+
+
+def _csign(x: complex) -> complex:
+    return 0.0 if x == 0 else x / abs(x)
+
+
+def rescale_messages(bpc: BeliefPropagationCache, edges: Optional[Sequence[int]] = None) -> None:
+    """In place; src/MessagePassing/beliefpropagationcache.jl:129-142."""
+    for e in (range(bpc.g.ne) if edges is None else edges):
+        me, mer = message(bpc, 2 * e), message(bpc, 2 * e + 1)
+        me, mer = me / np.linalg.norm(me), mer / np.linalg.norm(mer)
+        n = complex(np.sum(me * mer))
+        if n.imag == 0:
+            s = _csign(n)
+            me = me * s
+            n = n * s
+        r = 1.0 / np.sqrt(n)
+        bpc.messages[2 * e] = me * r
+        bpc.messages[2 * e + 1] = mer * r
+
+
+def rescale_vertices(bpc: BeliefPropagationCache, vertices: Optional[Sequence[int]] = None) -> None:
+    """In place; src/MessagePassing/beliefpropagationcache.jl:87-106 (TensorNetworkState branch)."""
+    for v in (range(bpc.g.nv) if vertices is None else vertices):
+        vn = vertex_scalar(bpc, v)
+        s = _csign(vn) if vn.imag == 0 else 1.0
+        bpc.network.tensors[v] = bpc.network.tensors[v] * (s * (1.0 / np.sqrt(complex(vn))))
+
+
+def rescale(bpc: BeliefPropagationCache) -> BeliefPropagationCache:
+    """src/MessagePassing/abstractbeliefpropagationcache.jl:281-291."""
+    bpc = bpc.copy()
+    rescale_messages(bpc)
+    rescale_vertices(bpc)
+    return bpc
+
+
+# ---------------------------------------------------------------------------------------------
+# matrix functions and truncation
+# ---------------------------------------------------------------------------------------------
+class NegativeEigenvalueError(ValueError):
+    pass
+
+
+def pseudo_sqrt_inv_sqrt(m: np.ndarray, cutoff: float = 10 * EPS) -> Tuple[np.ndarray, np.ndarray]:
+    """src/utils.jl:18-26: Hermitian eigh, f(λ)=0 if λ==0 or |λ|<cutoff else sqrt(λ) (1/sqrt(λ));
+    a negative λ beyond the cutoff throws in the reference (sqrt of a negative real)."""
+    w, u = np.linalg.eigh(m)
+    keep = ~((w == 0) | (np.abs(w) < cutoff))
+    if np.any(w[keep] < 0):
+        raise NegativeEigenvalueError(f"message eigenvalue {w[keep].min()} < 0")
+    rs = np.zeros_like(w)
+    ri = np.zeros_like(w)
+    rs[keep] = np.sqrt(w[keep])
+    ri[keep] = 1.0 / np.sqrt(w[keep])
+    return (u * rs) @ u.conj().T, (u * ri) @ u.conj().T
+
+
+def truncate_spectrum(p: np.ndarray, maxdim: Optional[int] = None, cutoff: Optional[float] = None,
+                      mindim: int = 1) -> Tuple[int, float]:
+    """NDTensors `truncate!` as reached through `factorize_svd(...; maxdim, cutoff)` at
+    src/Apply/simple_update.jl:46-52.  p = S^2 sorted descending.  Returns
+    (kept rank, truncerr = discarded weight / total weight); sequential FP64 tail sums."""
+    p = np.asarray(p, dtype=np.float64)
+    n = p.shape[0]
+    if n == 1:
+        return 1, 0.0
+    maxdim = n if maxdim is None else min(int(maxdim), n)
+    t = 0.0
+    while n > maxdim:
+        t += float(p[n - 1])
+        n -= 1
+    scale = 0.0
+    for x in p:                     # fixed ascending order; the device kernel sums in the same order
+        scale += float(x)
+    if scale == 0.0:
+        scale = 1.0
+    if cutoff is not None:
+        while n > mindim and t + float(p[n - 1]) <= cutoff * scale:
+            t += float(p[n - 1])
+            n -= 1
+    return n, t / scale
+
+
+# ---------------------------------------------------------------------------------------------
+# gate application
+# ---------------------------------------------------------------------------------------------
+def simple_update_2site(bpc: BeliefPropagationCache, gate: np.ndarray, v1: int, v2: int,
+                        maxdim: Optional[int] = None, cutoff: Optional[float] = None,
+                        normalize_tensors: bool = True, detail: Optional[dict] = None):
+    """src/Apply/simple_update.jl:24-66 with envs from src/Apply/apply_gates.jl:101.
+    gate[s1', s2', s1, s2].  Returns (T1', T2', S, truncerr) in canonical leg order."""
+    g = bpc.g
+    e = g.edge_of[(v1, v2)]
+    t1, t2 = bpc.network.tensors[v1], bpc.network.tensors[v2]
+
+    def reduce_site(v, other, t):
+        envs = [(ax, *pseudo_sqrt_inv_sqrt(m)) for ax, m in incoming(bpc, v, ignore=(other,))]
+        a = t
+        for ax, rs, _ in envs:                                   # simple_update.jl:35-36
+            a = _absorb(a, ax, rs)
+        ax_b = 1 + g.leg(v, e)
+        outer = [i for i in range(t.ndim) if i not in (0, ax_b)]
+        am = np.transpose(a, outer + [0, ax_b])
+        oshape = am.shape[:len(outer)]
+        d, chi = am.shape[-2], am.shape[-1]
+        q, r = np.linalg.qr(am.reshape(int(np.prod(oshape, dtype=np.int64)), d * chi))   # :39-40
+        return q.reshape(oshape + (q.shape[1],)), r.reshape(r.shape[0], d, chi), envs, outer, ax_b
+
+    q1, r1, envs1, outer1, axb1 = reduce_site(v1, v2, t1)
+    q2, r2, envs2, outer2, axb2 = reduce_site(v2, v1, t2)
+    theta = np.einsum("asb,ctb->asct", r1, r2)                   # R1 * R2        (:43)
+    theta = np.einsum("xyst,asct->axcy", gate, theta)            # apply(o, .)    (:43)
+    n1, d1, n2, d2 = theta.shape
+    u, s, vh = np.linalg.svd(theta.reshape(n1 * d1, n2 * d2), full_matrices=False)    # :46-52
+    rank, err = truncate_spectrum(s * s, maxdim, cutoff)
+    u, s, vh = u[:, :rank], s[:rank], vh[:rank]
+    rs = np.sqrt(s)
+    r1n = (u * rs).reshape(n1, d1, rank)                          # ortho="none": U sqrt(S)
+    r2n = (rs[:, None] * vh).reshape(rank, n2, d2).transpose(1, 2, 0)
+
+    def rebuild(q, rn, envs, outer, ax_b, ndim):
+        # Q * dag(M^-1/2): Q'[.., b, ..] = sum_c Q[.., c, ..] conj(Minv[b, c])      (:55-56)
+        for pos, (ax, _, ri) in enumerate(envs):
+            q = _absorb(q, outer.index(ax), ri.conj().T)
+        tn = np.tensordot(q, rn, axes=([q.ndim - 1], [0]))        # [outer.., s, u]  (:57)
+        perm_src = outer + [0, ax_b]
+        inv = [perm_src.index(i) for i in range(ndim)]
+        return np.ascontiguousarray(np.transpose(tn, inv))
+
+    t1n = rebuild(q1, r1n, envs1, outer1, axb1, t1.ndim)
+    t2n = rebuild(q2, r2n, envs2, outer2, axb2, t2.ndim)
+    if normalize_tensors:                                          # :58-65
+        s = s / np.linalg.norm(s)
+        t1n = t1n / np.linalg.norm(t1n)
+        t2n = t2n / np.linalg.norm(t2n)
+    if detail is not None:
+        detail.update(rank=rank, svals=s.copy(), truncerr=err)
+    return t1n, t2n, s, err
+
+
+def apply_gate(bpc: BeliefPropagationCache, gate: np.ndarray, vs: Sequence[int], maxdim=None, cutoff=None,
+               normalize_tensors: bool = True, detail: Optional[dict] = None) -> float:
+    """In place on `bpc`; src/Apply/apply_gates.jl:95-122 (+ 1-site branch src/Apply/simple_update.jl:21-23,63-65)."""
+    if len(vs) == 1:
+        v = vs[0]
+        t = np.tensordot(gate, bpc.network.tensors[v], axes=([1], [0]))
+        if normalize_tensors:
+            t = t / np.linalg.norm(t)
+        bpc.network.tensors[v] = t
+        return 0.0
+    v1, v2 = vs
+    t1, t2, s, err = simple_update_2site(bpc, gate, v1, v2, maxdim, cutoff, normalize_tensors, detail)
+    k = bpc.g.dedge(v1, v2)
+    # message <- S * sign(S) on the diagonal (apply_gates.jl:105-115)
+    bpc.messages[k] = np.diag(s).astype(np.complex128)
+    bpc.messages[k ^ 1] = np.diag(s).astype(np.complex128)
+    bpc.network.tensors[v1] = t1
+    bpc.network.tensors[v2] = t2
+    return float(err)
+
+
+def _resolve_circuit(g: Graph, circuit: Sequence[tuple]):
+    out = []
+    for gate in circuit:
+        if isinstance(gate[0], np.ndarray):
+            arr, verts = gate[0], gate[1]
+        else:
+            arr, verts = _gates.gate_array(gate), gate[1]
+        verts = verts if isinstance(verts, list) else [verts]
+        out.append((np.asarray(arr, dtype=np.complex128), [g.v(x) if not isinstance(x, (int, np.integer)) else int(x) for x in verts]))
+    return out
+
+
+def apply_gates(circuit: Sequence[tuple], psi, apply_kwargs: Optional[dict] = None,
+                bp_update_kwargs: Optional[dict] = None, update_cache: bool = True,
+                info: Optional[dict] = None):
+    """src/Apply/apply_gates.jl:13-23 (TensorNetworkState: build cache, initial update, return the network)
+    and :42-92 (ordered loop; a BP refresh before a 2-site gate that touches a vertex touched since the last
+    refresh -- 1-site gates mark vertices too, :84; final refresh)."""
+    apply_kwargs = dict(apply_kwargs or {})
+    if isinstance(psi, TensorNetworkState):
+        kw = bp_update_kwargs if bp_update_kwargs is not None else default_bp_update_kwargs(psi)
+        bpc = update(BeliefPropagationCache(psi), **kw)
+        bpc, errs = apply_gates(circuit, bpc, apply_kwargs, kw, update_cache, info)
+        return bpc.network, errs
+    bpc = psi.copy()
+    kw = bp_update_kwargs if bp_update_kwargs is not None else default_bp_update_kwargs(bpc.network)
+    gates = _resolve_circuit(bpc.g, circuit)
+    affected: set = set()
+    errs = np.zeros(len(gates))
+    refreshes = 0
+    for i, (arr, vs) in enumerate(gates):
+        if update_cache and len(vs) >= 2 and any(v in affected for v in vs):
+            bpc = update(bpc, **kw)
+            refreshes += 1
+            affected = set()
+        errs[i] = apply_gate(bpc, arr, vs, **apply_kwargs)
+        affected |= set(vs)
+    if update_cache:
+        bpc = update(bpc, **kw)
+        refreshes += 1
+    if info is not None:
+        info["refreshes"] = refreshes
+    return bpc, errs
+
+
+# ---------------------------------------------------------------------------------------------
+# BP expectation values (src/expect.jl:58-83)
+# ---------------------------------------------------------------------------------------------
+def _tree_path(g: Graph, a: int, b: int) -> List[int]:
+    """Shortest path a..b (the Steiner tree of two vertices)."""
+    prev = {a: -1}
+    queue = [a]
+    while queue:
+        u = queue.pop(0)
+        if u == b:
+            break
+        for w in g.neighbors(u):
+            if w not in prev:
+                prev[w] = u
+                queue.append(w)
+    path = [b]
+    while path[-1] != a:
+        path.append(prev[path[-1]])
+    return path[::-1]
+
+
+def _region_contract(bpc: BeliefPropagationCache, region: List[int], ops: Dict[int, np.ndarray]) -> complex:
+    """Contract [T, conj(T) (+ op)] over a path region with all incoming messages."""
+    g = bpc.g
+    env = None            # matrix on the bond towards the next vertex of the path: env[b, b']
+    for i, v in enumerate(region):
+        t = bpc.network.tensors[v]
+        ket = t
+        if v in ops:
+            ket = np.tensordot(ops[v], t, axes=([1], [0]))       # O[s', s] T[s] -> index s' (paired with bra)
+        prev_v = region[i - 1] if i > 0 else None
+        next_v = region[i + 1] if i + 1 < len(region) else None
+        for axis, m in incoming(bpc, v, ignore=tuple(x for x in (prev_v, next_v) if x is not None)):
+            ket = _absorb(ket, axis, m)
+        if prev_v is not None:
+            ket = _absorb(ket, 1 + g.leg(v, g.edge_of[(prev_v, v)]), env)
+        if next_v is None:
+            return complex(np.vdot(t, ket))
+        ax = 1 + g.leg(v, g.edge_of[(v, next_v)])
+        others = [j for j in range(t.ndim) if j != ax]
+        env = np.tensordot(ket, t.conj(), axes=(others, others))
+    raise AssertionError
+
+
+def expect(bpc: BeliefPropagationCache, obs: tuple) -> complex:
+    """obs = (op string or list of op names, vertex names/ids[, coeff]); src/expect.jl:58-83,160-176."""
+    g = bpc.g
+    op, verts = obs[0], obs[1]
+    coeff = obs[2] if len(obs) > 2 else 1
+    verts = verts if isinstance(verts, list) else [verts]
+    vs = [g.v(x) if not isinstance(x, (int, np.integer)) else int(x) for x in verts]
+    names = list(op) if isinstance(op, str) else list(op)
+    if len(names) != len(vs):
+        raise ValueError("Invalid observable: need as many operators as vertices passed.")
+    if coeff == 0:
+        return 0
+    if len(vs) == 1:
+        region = vs
+    elif len(vs) == 2:
+        region = _tree_path(g, vs[0], vs[1])
+    else:
+        raise NotImplementedError("oracle expect handles one- and two-site observables")
+    ops = {v: _gates.PAULI[n] for v, n in zip(vs, names)}
+    denom = _region_contract(bpc, region, {})
+    numer = _region_contract(bpc, region, ops)
+    return coeff * numer / denom
+
+
+def expect_tns(psi: TensorNetworkState, obs, cache_update_kwargs: Optional[dict] = None):
+    """src/expect.jl:124-136: build a cache, update with default_bp_update_kwargs, measure."""
+    kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(psi)
+    bpc = update(BeliefPropagationCache(psi), **kw)
+    if isinstance(obs, list):
+        return [expect(bpc, o) for o in obs]
+    return expect(bpc, obs)
+
+
+def rdm_1site(bpc: BeliefPropagationCache, v: int) -> np.ndarray:
+    """BP one-site reduced density matrix rho[s, s'] (src/rdm.jl:49-70 restricted to one vertex), trace 1."""
+    t = bpc.network.tensors[v]
+    a = t
+    for axis, m in incoming(bpc, v):
+        a = _absorb(a, axis, m)
+    others = list(range(1, t.ndim))
+    rho = np.tensordot(a, t.conj(), axes=(others, others))
+    return rho / np.trace(rho)
+
+
+# ---------------------------------------------------------------------------------------------
+# symmetric gauge, entanglement, BP truncation
+# ---------------------------------------------------------------------------------------------
+def symmetric_gauge(bpc: BeliefPropagationCache, regularization: float = 10 * EPS) -> BeliefPropagationCache:
+    """src/symmetric_gauge.jl:1-56 (SURVEY.md Appendix A.8 for the index roles)."""
+    bpc = bpc.copy()
+    g = bpc.g
+    for e in range(g.ne):
+        a, c = int(g.esrc[e]), int(g.edst[e])
+        xw, xu = np.linalg.eigh(message(bpc, 2 * e))
+        yw, yu = np.linalg.eigh(message(bpc, 2 * e + 1))
+        xw, yw = xw + regularization, yw + regularization                   # :14-15 (a shift)
+        if np.any(xw < 0) or np.any(yw < 0):
+            raise NegativeEigenvalueError("negative message eigenvalue in symmetric_gauge")
+        root_x = (xu * np.sqrt(xw)) @ xu.conj().T
+        root_y = (yu * np.sqrt(yw)) @ yu.conj().T
+        inv_x = (xu / np.sqrt(xw)) @ xu.conj().T
+        inv_y = (yu / np.sqrt(yw)) @ yu.conj().T
+        ce = root_x.T @ root_y                                              # :27-28
+        u, s, vh = np.linalg.svd(ce)                                        # :30
+        rs = np.sqrt(s)
+        ax_a, ax_c = 1 + g.leg(a, e), 1 + g.leg(c, e)
+        ta = _absorb(bpc.network.tensors[a], ax_a, inv_x.T)                 # T~[.., l] = sum_b T[.., b] X^-1/2[l, b]
+        tc = _absorb(bpc.network.tensors[c], ax_c, inv_y.T)
+        bpc.network.tensors[a] = _absorb(ta, ax_a, u * rs)                  # :34, :45-46
+        bpc.network.tensors[c] = _absorb(tc, ax_c, vh.T * rs)               # :35-36, :47
+        bpc.messages[2 * e] = np.diag(s).astype(np.complex128)              # :51-52
+        bpc.messages[2 * e + 1] = np.diag(s).astype(np.complex128)
+    return bpc
+
+
+def gauge_and_scale(psi: TensorNetworkState, maxiter: int = 40, edge_sequence=None) -> TensorNetworkState:
+    """symmetrize_and_bpnormalize (src/symmetric_gauge.jl:76-83): update(maxiter=40), rescale, symmetric gauge."""
+    bpc = update(BeliefPropagationCache(psi), maxiter=maxiter, edge_sequence=edge_sequence)
+    bpc = rescale(bpc)
+    return symmetric_gauge(bpc).network
+
+
+def entanglement(bpc: BeliefPropagationCache, e: int) -> float:
+    """src/symmetric_gauge.jl:85-103."""
+    r1, _ = pseudo_sqrt_inv_sqrt(message(bpc, 2 * e))
+    r2, _ = pseudo_sqrt_inv_sqrt(message(bpc, 2 * e + 1))
+    s = np.linalg.svd(r1 @ r2.T, compute_uv=False)
+    s = s / np.linalg.norm(s)
+    ee = 0.0
+    for d in s:
+        if abs(d) >= EPS:
+            ee -= d * d * math.log(d * d)
+    return abs(ee)
+
+
+def truncate_bp(bpc: BeliefPropagationCache, maxdim: int, cutoff: Optional[float] = None,
+                normalize_tensors: bool = True, edge_groups: Optional[List[List[int]]] = None,
+                bp_update_kwargs: Optional[dict] = None) -> BeliefPropagationCache:
+    """src/truncate.jl:12-38: identity gates per colour group, a BP update after each group."""
+    bpc = bpc.copy()
+    g = bpc.g
+    kw = bp_update_kwargs if bp_update_kwargs is not None else default_bp_update_kwargs(bpc.network)
+    if edge_groups is None:
+        edge_groups = edge_color(g)
+    ident = np.eye(4, dtype=np.complex128).reshape(2, 2, 2, 2)
+    for grp in edge_groups:
+        for e in grp:
+            if bpc.network.bond_dim(e) == 1:                       # truncatable_edge, truncate.jl:5-10
+                continue
+            apply_gate(bpc, ident, [int(g.esrc[e]), int(g.edst[e])], maxdim=maxdim, cutoff=cutoff,
+                       normalize_tensors=normalize_tensors)
+        bpc = update(bpc, **kw)
+    return bpc
+
+
+def truncate_tns(psi: TensorNetworkState, **kwargs) -> TensorNetworkState:
+    """src/truncate.jl:74-79: bare update (25 sweeps / 1 on trees, no tolerance) then truncate."""
+    bpc = update(BeliefPropagationCache(psi))
+    return truncate_bp(bpc, **kwargs).network
+
+
+# ---------------------------------------------------------------------------------------------
+# exact helpers for tiny systems (independent ground truth, not part of the restatement)
+# ---------------------------------------------------------------------------------------------
+def to_statevector(psi: TensorNetworkState) -> np.ndarray:
+    """Contract all bonds; returns psi[s_0, s_1, ..] flattened with vertex 0 slowest."""
+    g = psi.g
+    done: List[int] = []
+    labels: List = []
+    big = None
+    order = list(range(g.nv))
+    for v in order:
+        t = psi.tensors[v]
+        tl = [("s", v)] + [("e", e) for e in g.incident[v]]
+        if big is None:
+            big, labels = t, tl
+        else:
+            shared = [l for l in tl if l in labels]
+            big = np.tensordot(big, t, axes=([labels.index(l) for l in shared], [tl.index(l) for l in shared]))
+            labels = [l for l in labels if l not in shared] + [l for l in tl if l not in shared]
+        done.append(v)
+    perm = [labels.index(("s", v)) for v in range(g.nv)]
+    assert len(labels) == g.nv
+    return np.transpose(big, perm).reshape(-1)
+
+
+def statevector_circuit(g: Graph, f, circuit: Sequence[tuple]) -> np.ndarray:
+    """Exact evolution of a product state; vertex 0 slowest."""
+    n = g.nv
+    psi = np.array([1.0 + 0j])
+    for v in range(n):
+        psi = np.kron(psi, _gates.state_vector(f(g.names[v])))
+    psi = psi.reshape((2,) * n)
+    for arr, vs in _resolve_circuit(g, circuit):
+        if len(vs) == 1:
+            psi = np.moveaxis(np.tensordot(arr, psi, axes=([1], [vs[0]])), 0, vs[0])
+        else:
+            psi = np.moveaxis(np.tensordot(arr, psi, axes=([2, 3], [vs[0], vs[1]])), [0, 1], [vs[0], vs[1]])
+    return psi.reshape(-1)
+
+
+def statevector_expect(psi: np.ndarray, n: int, ops: Dict[int, np.ndarray]) -> complex:
+    phi = psi.reshape((2,) * n)
+    for v, o in ops.items():
+        phi = np.moveaxis(np.tensordot(o, phi, axes=([1], [v])), 0, v)
+    return complex(np.vdot(psi, phi.reshape(-1)) / np.vdot(psi, psi))
