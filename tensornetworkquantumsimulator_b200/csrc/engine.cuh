@@ -1,0 +1,306 @@
+// Host-side engine: context, device memory, contraction plans (levels of chains), launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <stdexcept>
+
+#include "../../include/tnqs_cuda.h"
+#include "common.cuh"
+#include "kernels_gemm.cuh"
+#include "kernels_small.cuh"
+#include "kernels_misc.cuh"
+
+struct TnqsError {
+  int code; std::string msg;
+  TnqsError(int c, const std::string& m) : code(c), msg(m) {}
+};
+
+#define CU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) throw TnqsError(_e == cudaErrorMemoryAllocation ? TNQS_ERR_OOM : TNQS_ERR_CUDA, \
+  std::string(#x) + ": " + cudaGetErrorString(_e)); } while (0)
+#define REQUIRE(cond, code, msg) do { if (!(cond)) throw TnqsError(code, msg); } while (0)
+
+struct ProfEvent { cudaEvent_t a, b; int kc; };
+
+struct tnqs_ctx {
+  int device = 0;
+  int num_sms = 148;
+  size_t smem_optin = 227 * 1024;
+  cudaStream_t stream = nullptr;
+  int nv = 0, ne = 0, chi_cap = 1, dmax = 2;
+  std::vector<int> esrc, edst, d, chi;
+  std::vector<std::vector<int>> inc;               // v -> incident edge ids ascending
+  std::vector<cplx*> site;                         // device pointers
+  std::vector<long long> site_n;                   // element counts
+  cplx* msg_cur = nullptr; cplx* msg_stage = nullptr;
+  long long slot = 1;
+  int* d_chi = nullptr;                            // device copy of chi[ne]
+  int* d_status = nullptr;
+  std::vector<int> owner; int rank = 0; bool partitioned = false;
+  std::string err;
+  long long launches = 0;
+  bool profiling = false;
+  std::vector<ProfEvent> prof_events;
+  double prof_ms[TNQS_KC_COUNT] = {0};
+  long long prof_launches[TNQS_KC_COUNT] = {0};
+  std::vector<void*> temp;                         // stream-ordered temporaries of the current call
+
+  // ---- graph helpers ----
+  int other(int e, int v) const { return esrc[e] == v ? edst[e] : esrc[e]; }
+  int dsrc(int k) const { return (k & 1) ? edst[k >> 1] : esrc[k >> 1]; }
+  int ddst(int k) const { return (k & 1) ? esrc[k >> 1] : edst[k >> 1]; }
+  int dedge(int u, int e) const { return 2 * e + (esrc[e] == u ? 0 : 1); }       // u -> other(e, u)
+  int leg(int v, int e) const {
+    for (size_t i = 0; i < inc[v].size(); ++i) if (inc[v][i] == e) return (int)i;
+    return -1;
+  }
+  long long site_elems(int v) const { long long n = d[v]; for (int e : inc[v]) n *= chi[e]; return n; }
+  cplx* msg(int k) const { return msg_cur + (size_t)k * slot; }
+  cplx* msg_st(int k) const { return msg_stage + (size_t)k * slot; }
+
+  // ---- memory ----
+  void* dalloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    CU(cudaMallocAsync(&p, bytes, stream));
+    return p;
+  }
+  void dfree(void* p) { if (p) cudaFreeAsync(p, stream); }
+  template <typename T> T* talloc(size_t count) { T* p = (T*)dalloc(count * sizeof(T)); temp.push_back(p); return p; }
+  void release_temps() { for (void* p : temp) dfree(p); temp.clear(); }
+  template <typename T> T* upload(const std::vector<T>& v) {
+    T* p = talloc<T>(std::max<size_t>(v.size(), 1));
+    if (!v.empty()) CU(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+    return p;
+  }
+  void sync() { CU(cudaStreamSynchronize(stream)); }
+
+  // ---- launch accounting ----
+  void pre_launch(int kc) {
+    ++launches; ++prof_launches[kc];
+    if (profiling) {
+      ProfEvent ev; ev.kc = kc;
+      cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
+      cudaEventRecord(ev.a, stream);
+      prof_events.push_back(ev);
+    }
+  }
+  void post_launch() {
+    if (profiling) cudaEventRecord(prof_events.back().b, stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw TnqsError(TNQS_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  }
+  void collect_profile() {
+    if (prof_events.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (auto& ev : prof_events) {
+      float ms = 0; cudaEventElapsedTime(&ms, ev.a, ev.b);
+      prof_ms[ev.kc] += ms;
+      cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+    }
+    prof_events.clear();
+  }
+  int read_status() {
+    int st = 0;
+    CU(cudaMemcpyAsync(&st, d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    sync();
+    if (st) { int z = 0; CU(cudaMemcpyAsync(d_status, &z, sizeof(int), cudaMemcpyHostToDevice, stream)); }
+    return st;
+  }
+};
+
+#define LAUNCH(ctx, kc, kernel, grid, block, smem, ...) do { (ctx)->pre_launch(kc); \
+  kernel<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__); (ctx)->post_launch(); } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// Contraction plans.  A chain takes a site tensor, optionally applies a one-site operator, absorbs small matrices
+// on a list of legs, and closes against the conjugated site on one leg (or on the site index) into a small
+// matrix.  A level is a set of independent chains; levels run in order; BP levels commit staged messages.
+// ---------------------------------------------------------------------------------------------------------------
+struct Absorb { int leg; const cplx* mat; int ldm; int flags; };     // leg: 0-based bond leg of the site
+struct Chain {
+  int v = -1;
+  const cplx* op = nullptr;          // device d x d operator o[s', s] applied first, or null
+  std::vector<Absorb> absorb;
+  int close_leg = -1;                // bond leg to close on; -1 = close on the site index (RDM)
+  // output
+  cplx* dst = nullptr;               // n x n result (BP: staged message)
+  const cplx* prev = nullptr; double* diff = nullptr; int bp_mode = 0, normalize = 0, hermitize = 0;
+  int commit_k = -1;                 // BP: directed edge to commit at the end of the level
+};
+
+struct LaunchRec { size_t off; int count; dim3 grid; size_t smem; };
+struct SubLevel {
+  LaunchRec gate1{0, 0, dim3(), 0};
+  std::vector<LaunchRec> steps;
+  LaunchRec close{0, 0, dim3(), 0}, reduce{0, 0, dim3(), 0};
+};
+struct LevelPlan { std::vector<SubLevel> subs; size_t commit_off = 0; int commit_count = 0; };
+
+struct Plan {
+  std::vector<LevelPlan> levels;
+  Gate1Desc* d_gate1 = nullptr; ModeApplyDesc* d_apply = nullptr; ModeCloseDesc* d_close = nullptr;
+  CloseReduceDesc* d_reduce = nullptr; int* d_commit = nullptr;
+  double flops = 0;                  // executed flops per run of the plan (8 per complex MAC)
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Build a plan for `levels` (vector of vector of chains).  All device buffers are temporaries of the current call.
+static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& levels, size_t scratch_budget_bytes) {
+  Plan plan;
+  std::vector<Gate1Desc> g1; std::vector<ModeApplyDesc> ma; std::vector<ModeCloseDesc> mc;
+  std::vector<CloseReduceDesc> rd; std::vector<int> commit;
+  // pass 1: scratch requirement per chain, sub-level split, global scratch sizing
+  struct ChainMem { size_t buf_elems; int nbuf; int nsplit; size_t partial_elems; };
+  size_t max_scratch = 0, max_partial = 0;
+  std::vector<std::vector<std::vector<int>>> subsets(levels.size());   // level -> sub-level -> chain indices
+  std::vector<std::vector<ChainMem>> mem(levels.size());
+  for (size_t L = 0; L < levels.size(); ++L) {
+    const auto& chains = levels[L];
+    mem[L].resize(chains.size());
+    std::vector<int> cur; size_t cur_bytes = 0;
+    for (size_t i = 0; i < chains.size(); ++i) {
+      const Chain& ch = chains[i];
+      int nsteps = (ch.op ? 1 : 0) + (int)ch.absorb.size();
+      ChainMem cm; cm.buf_elems = (size_t)c->site_n[ch.v]; cm.nbuf = std::min(nsteps, 2); cm.nsplit = 1; cm.partial_elems = 0;
+      mem[L][i] = cm;
+      size_t bytes = align_up(cm.buf_elems * sizeof(cplx), 256) * cm.nbuf;
+      if (!cur.empty() && cur_bytes + bytes > scratch_budget_bytes) { subsets[L].push_back(cur); cur.clear(); cur_bytes = 0; }
+      cur.push_back((int)i); cur_bytes += bytes;
+      max_scratch = std::max(max_scratch, cur_bytes);
+    }
+    if (!cur.empty()) subsets[L].push_back(cur);
+    for (auto& sub : subsets[L]) {
+      int target = std::max(1, (4 * c->num_sms + (int)sub.size() - 1) / (int)sub.size());
+      size_t part = 0;
+      for (int i : sub) {
+        const Chain& ch = chains[i];
+        int n = ch.close_leg < 0 ? c->d[ch.v] : c->chi[c->inc[ch.v][ch.close_leg]];
+        long long rows = c->site_n[ch.v] / n;
+        int ns = (int)std::min<long long>(std::min(target, 64), std::max<long long>(1, rows / 128));
+        mem[L][i].nsplit = std::max(1, ns);
+        mem[L][i].partial_elems = (size_t)mem[L][i].nsplit * n * n;
+        part += mem[L][i].partial_elems;
+      }
+      max_partial = std::max(max_partial, part);
+    }
+  }
+  cplx* scratch = c->talloc<cplx>(max_scratch / sizeof(cplx) + 16);
+  cplx* partial = c->talloc<cplx>(max_partial + 16);
+  // pass 2: descriptors
+  for (size_t L = 0; L < levels.size(); ++L) {
+    const auto& chains = levels[L];
+    LevelPlan lp;
+    lp.commit_off = commit.size();
+    for (auto& sub : subsets[L]) {
+      SubLevel sl;
+      size_t soff = 0, poff = 0;
+      int maxsteps = 0;
+      std::vector<cplx*> buf0(sub.size()), buf1(sub.size());
+      for (size_t j = 0; j < sub.size(); ++j) {
+        const ChainMem& cm = mem[L][sub[j]];
+        size_t stride = align_up(cm.buf_elems * sizeof(cplx), 256) / sizeof(cplx);
+        buf0[j] = scratch + soff; if (cm.nbuf >= 1) soff += stride;
+        buf1[j] = scratch + soff; if (cm.nbuf >= 2) soff += stride;
+        maxsteps = std::max(maxsteps, (int)chains[sub[j]].absorb.size());
+      }
+      // current tensor of every chain and which buffer it would write next
+      std::vector<const cplx*> curp(sub.size()); std::vector<int> next(sub.size(), 0);
+      for (size_t j = 0; j < sub.size(); ++j) curp[j] = c->site[chains[sub[j]].v];
+      // one-site operators
+      sl.gate1.off = g1.size();
+      long long maxrest = 0;
+      for (size_t j = 0; j < sub.size(); ++j) {
+        const Chain& ch = chains[sub[j]];
+        if (!ch.op) continue;
+        Gate1Desc g; g.in = curp[j]; g.out = buf0[j]; g.gate = ch.op; g.d = c->d[ch.v];
+        g.rest = c->site_n[ch.v] / g.d; g.norm2_partial = nullptr;
+        g1.push_back(g); curp[j] = buf0[j]; next[j] = 1; maxrest = std::max(maxrest, g.rest);
+        plan.flops += 8.0 * g.d * g.d * g.rest;
+      }
+      sl.gate1.count = (int)(g1.size() - sl.gate1.off);
+      sl.gate1.grid = dim3((unsigned)std::min<long long>(std::max<long long>(1, (maxrest + 255) / 256), 1024), sl.gate1.count, 1);
+      // absorption steps
+      for (int s = 0; s < maxsteps; ++s) {
+        LaunchRec lr; lr.off = ma.size(); lr.smem = 0;
+        long long maxtiles = 1; int maxcol = 1;
+        for (size_t j = 0; j < sub.size(); ++j) {
+          const Chain& ch = chains[sub[j]];
+          if (s >= (int)ch.absorb.size()) continue;
+          const Absorb& ab = ch.absorb[s];
+          int v = ch.v;
+          ModeApplyDesc d;
+          long long Lp = c->d[v];
+          for (int i = 0; i < ab.leg; ++i) Lp *= c->chi[c->inc[v][i]];
+          int n = c->chi[c->inc[v][ab.leg]];
+          long long R = c->site_n[v] / (Lp * n);
+          d.in = curp[j]; d.out = next[j] == 0 ? buf0[j] : buf1[j]; d.m = ab.mat;
+          d.L = (int)Lp; d.n = n; d.np = n; d.R = (int)R;
+          d.in_sb = Lp; d.in_sr = Lp * n; d.out_sb = Lp; d.out_sr = Lp * n; d.ldm = ab.ldm; d.flags = ab.flags;
+          ma.push_back(d);
+          curp[j] = d.out; next[j] ^= 1;
+          maxtiles = std::max(maxtiles, (Lp * R + MA_BM - 1) / MA_BM);
+          maxcol = std::max(maxcol, (n + MA_BN - 1) / MA_BN);
+          plan.flops += 8.0 * (double)c->site_n[v] * n;
+        }
+        lr.count = (int)(ma.size() - lr.off);
+        lr.grid = dim3((unsigned)maxtiles, lr.count, maxcol);
+        if (lr.count) sl.steps.push_back(lr);
+      }
+      // closing + reduction
+      sl.close.off = mc.size(); sl.reduce.off = rd.size();
+      int maxsplit = 1; size_t maxnn = 1;
+      for (size_t j = 0; j < sub.size(); ++j) {
+        const Chain& ch = chains[sub[j]];
+        const ChainMem& cm = mem[L][sub[j]];
+        int v = ch.v;
+        ModeCloseDesc d;
+        long long Lp; int n;
+        if (ch.close_leg < 0) { Lp = 1; n = c->d[v]; }
+        else { Lp = c->d[v]; for (int i = 0; i < ch.close_leg; ++i) Lp *= c->chi[c->inc[v][i]]; n = c->chi[c->inc[v][ch.close_leg]]; }
+        long long R = c->site_n[v] / (Lp * n);
+        d.a = curp[j]; d.b = c->site[v]; d.partial = partial + poff;
+        d.L = (int)Lp; d.R = (int)R; d.n = n; d.np = n;
+        d.a_sb = Lp; d.a_sr = Lp * n; d.b_sb = Lp; d.b_sr = Lp * n;
+        d.nsplit = cm.nsplit; d.rows_per_split = (Lp * R + cm.nsplit - 1) / cm.nsplit;
+        mc.push_back(d);
+        CloseReduceDesc r;
+        r.partial = d.partial; r.nsplit = cm.nsplit; r.n = n; r.np = n; r.dst = ch.dst; r.prev = ch.prev; r.diff = ch.diff;
+        r.mode = ch.bp_mode; r.normalize = ch.normalize; r.hermitize = ch.hermitize;
+        rd.push_back(r);
+        poff += cm.partial_elems;
+        maxsplit = std::max(maxsplit, cm.nsplit); maxnn = std::max(maxnn, (size_t)n * n);
+        plan.flops += 8.0 * (double)c->site_n[v] * n;
+        REQUIRE(n <= 64, TNQS_ERR_UNSUPPORTED, "closing extent > 64 is not supported");
+      }
+      sl.close.count = (int)sub.size(); sl.close.grid = dim3(maxsplit, sl.close.count, 1);
+      sl.reduce.count = (int)sub.size(); sl.reduce.grid = dim3(sl.reduce.count, 1, 1); sl.reduce.smem = maxnn * sizeof(cplx);
+      lp.subs.push_back(sl);
+    }
+    for (const Chain& ch : chains) if (ch.commit_k >= 0) commit.push_back(ch.commit_k);
+    lp.commit_count = (int)(commit.size() - lp.commit_off);
+    plan.levels.push_back(lp);
+  }
+  plan.d_gate1 = c->upload(g1); plan.d_apply = c->upload(ma); plan.d_close = c->upload(mc);
+  plan.d_reduce = c->upload(rd); plan.d_commit = c->upload(commit);
+  return plan;
+}
+
+static void run_plan(tnqs_ctx* c, const Plan& p) {
+  for (const LevelPlan& lp : p.levels) {
+    for (const SubLevel& sl : lp.subs) {
+      if (sl.gate1.count) LAUNCH(c, TNQS_KC_MISC, k_gate1, sl.gate1.grid, 256, 0, p.d_gate1 + sl.gate1.off);
+      for (const LaunchRec& lr : sl.steps) LAUNCH(c, TNQS_KC_MODE_APPLY, k_mode_apply, lr.grid, 256, 0, p.d_apply + lr.off);
+      LAUNCH(c, TNQS_KC_MODE_CLOSE, k_mode_close, sl.close.grid, 256, 0, p.d_close + sl.close.off);
+      LAUNCH(c, TNQS_KC_BP_FINALIZE, k_close_reduce, sl.reduce.grid, 256, sl.reduce.smem, p.d_reduce + sl.reduce.off);
+    }
+    if (lp.commit_count)
+      LAUNCH(c, TNQS_KC_BP_FINALIZE, k_msg_commit, lp.commit_count, 128, 0, c->msg_cur, c->msg_stage, c->slot,
+             p.d_commit + lp.commit_off, c->d_chi);
+  }
+}

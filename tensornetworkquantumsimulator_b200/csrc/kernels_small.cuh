@@ -1,0 +1,394 @@
+// Small dense factorisations, one CTA per matrix (DESIGN.md "kernels"):
+//   k_eigh_sqrt  : Hermitian eigendecomposition by one-sided Jacobi -> sqrt(M), M^(-1/2)   (src/utils.jl:18-26)
+//   k_house_qr   : Householder QR of a row block held in shared memory, explicit thin Q     (TSQR building block)
+//   k_theta      : theta = R1 * R2 over the gate bond, then the two-site gate               (simple_update.jl:43)
+//   k_svd_trunc  : one-sided Jacobi SVD + ITensors-style truncation + factor outputs         (simple_update.jl:46-61)
+// All reductions have a fixed order (warp butterflies, sequential tail sums): results do not depend on scheduling.
+#pragma once
+#include "common.cuh"
+
+#define TNQS_EPS 2.220446049250313e-16
+#define TNQS_JACOBI_MAX_SWEEPS 60
+
+enum { ST_NEG_EIG = 1, ST_NO_CONV = 2, ST_RANK_CAP = 4 };
+
+// Round-robin (circle method) pairing: N even players, round s in [0, N-1), pair i in [0, N/2).
+__device__ __forceinline__ void rr_pair(int N, int s, int i, int& p, int& q) {
+  if (i == 0) { p = s % (N - 1); q = N - 1; }
+  else { p = (s + i) % (N - 1); q = (s - i + 2 * (N - 1)) % (N - 1); }
+  if (p > q) { int t = p; p = q; q = t; }
+}
+
+// One-sided Jacobi on the columns of W (m x n, leading dim ldw); the same rotations are accumulated into the
+// rows of V (nv x n, leading dim ldv) unless V is null.  On exit the columns of W are mutually orthogonal.
+// Every thread of the CTA must call.  Returns the number of sweeps used, or -1 if not converged.
+__device__ int jacobi_columns(cplx* W, int ldw, int m, cplx* V, int ldv, int nv, int n) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int N = n + (n & 1);
+  if (n < 2) return 0;
+  const double tol2 = (double)m * TNQS_EPS * TNQS_EPS;
+  for (int sweep = 0; sweep < TNQS_JACOBI_MAX_SWEEPS; ++sweep) {
+    int rotated = 0;
+    for (int s = 0; s < N - 1; ++s) {
+      for (int i = warp; i < N / 2; i += nwarps) {
+        int p, q;
+        rr_pair(N, s, i, p, q);
+        if (q >= n) continue;
+        cplx* wp = W + (size_t)p * ldw;
+        cplx* wq = W + (size_t)q * ldw;
+        double al = 0, be = 0, gr = 0, gi = 0;
+        for (int r = lane; r < m; r += 32) {
+          cplx a = wp[r], b = wq[r];
+          al += cabs2(a); be += cabs2(b);
+          gr += a.x * b.x + a.y * b.y;         // conj(a) * b
+          gi += a.x * b.y - a.y * b.x;
+        }
+        al = warp_sum(al); be = warp_sum(be); gr = warp_sum(gr); gi = warp_sum(gi);
+        double g2 = gr * gr + gi * gi;
+        if (!(g2 > tol2 * al * be) || g2 == 0.0) continue;
+        rotated = 1;
+        double ag = sqrt(g2);
+        cplx ph = cmake(gr / ag, -gi / ag);           // e^{-i phi}: makes <a_p, ph*a_q> real positive
+        double zeta = (be - al) / (2.0 * ag);
+        double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+        for (int r = lane; r < m; r += 32) {
+          cplx a = wp[r], b = cmul(ph, wq[r]);
+          wp[r] = cmake(c * a.x - sn * b.x, c * a.y - sn * b.y);
+          wq[r] = cmake(sn * a.x + c * b.x, sn * a.y + c * b.y);
+        }
+        if (V) {
+          cplx* vp = V + (size_t)p * ldv;
+          cplx* vq = V + (size_t)q * ldv;
+          for (int r = lane; r < nv; r += 32) {
+            cplx a = vp[r], b = cmul(ph, vq[r]);
+            vp[r] = cmake(c * a.x - sn * b.x, c * a.y - sn * b.y);
+            vq[r] = cmake(sn * a.x + c * b.x, sn * a.y + c * b.y);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(rotated)) return sweep + 1;
+  }
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct EighDesc {
+  const cplx* m; int n; int ldm;
+  cplx* root; cplx* invroot;      // n x n each (ld = n); either may be null
+  double cutoff;                  // mode 0: f(lambda) = 0 if lambda == 0 or |lambda| < cutoff
+  double shift;                   // mode 1: lambda <- lambda + shift, no cutoff (symmetric_gauge.jl:14-15)
+  int mode;
+};
+
+// dynamic shared memory: W[n*n] V[n*n] complex, lam[n] fr[n] fi[n] doubles
+__global__ void __launch_bounds__(1024) k_eigh_sqrt(const EighDesc* __restrict__ descs, int* status) {
+  const EighDesc d = descs[blockIdx.x];
+  extern __shared__ cplx esm[];
+  const int n = d.n;
+  cplx* W = esm;
+  cplx* V = esm + (size_t)n * n;
+  double* lam = (double*)(V + (size_t)n * n);
+  double* fr = lam + n;
+  double* fi = fr + n;
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    int i = idx % n, j = idx / n;
+    // Hermitian part: LAPACK's heev reads one triangle only; (M + M^H)/2 is the symmetric equivalent
+    cplx a = d.m[i + (size_t)j * d.ldm], b = d.m[j + (size_t)i * d.ldm];
+    W[idx] = cmake(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+    V[idx] = cmake(i == j ? 1.0 : 0.0, 0.0);
+  }
+  __syncthreads();
+  int sweeps = jacobi_columns(W, n, n, V, n, n, n);
+  if (sweeps < 0 && threadIdx.x == 0) atomicOr(status, ST_NO_CONV);
+  // W = M V  => lambda_j = Re(v_j^H w_j)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < n; j += nwarps) {
+    double s = 0;
+    for (int r = lane; r < n; r += 32) { cplx v = V[r + (size_t)j * n], w = W[r + (size_t)j * n]; s += v.x * w.x + v.y * w.y; }
+    s = warp_sum(s);
+    if (lane == 0) {
+      double f = 0, g = 0;
+      if (d.mode == 0) {
+        if (!(s == 0.0 || fabs(s) < d.cutoff)) {
+          if (s < 0) atomicOr(status, ST_NEG_EIG); else { f = sqrt(s); g = 1.0 / f; }
+        }
+      } else {
+        double l = s + d.shift;
+        if (l < 0) atomicOr(status, ST_NEG_EIG); else { f = sqrt(l); g = 1.0 / f; }
+      }
+      lam[j] = s; fr[j] = f; fi[j] = g;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    int b = idx % n, c = idx / n;
+    cplx sr = cmake(0, 0), si = cmake(0, 0);
+    for (int j = 0; j < n; ++j) {
+      cplx vb = V[b + (size_t)j * n], vc = V[c + (size_t)j * n];
+      cplx pr = cmake(vb.x * vc.x + vb.y * vc.y, vb.y * vc.x - vb.x * vc.y);   // vb * conj(vc)
+      sr.x = fma(fr[j], pr.x, sr.x); sr.y = fma(fr[j], pr.y, sr.y);
+      si.x = fma(fi[j], pr.x, si.x); si.y = fma(fi[j], pr.y, si.y);
+    }
+    if (d.root) d.root[idx] = sr;
+    if (d.invroot) d.invroot[idx] = si;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct QrDesc {
+  cplx* a; long long lda; int h, nc;     // block: h rows x nc columns, column-major
+  cplx* rout; int ldr;                   // R: min(h,nc) x nc, zeros below the diagonal
+};
+
+// Householder QR (LAPACK zgeqr2 + zung2r arithmetic) of one block in shared memory; block 256 threads.
+// dynamic shared memory: A[h*nc] complex + tau[nc] complex + 2 complex scratch
+__global__ void __launch_bounds__(256) k_house_qr(const QrDesc* __restrict__ descs) {
+  const QrDesc d = descs[blockIdx.x];
+  extern __shared__ cplx qsm[];
+  const int h = d.h, nc = d.nc, q = min(h, nc);
+  cplx* A = qsm;
+  cplx* tau = qsm + (size_t)h * nc;
+  cplx* scal = tau + nc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int idx = tid; idx < h * nc; idx += blockDim.x) {
+    int r = idx % h, c = idx / h;
+    A[idx] = d.a[r + (size_t)c * d.lda];
+  }
+  __syncthreads();
+  for (int j = 0; j < q; ++j) {
+    cplx* col = A + (size_t)j * h;
+    if (warp == 0) {                                      // zlarfg
+      double xn2 = 0;
+      for (int r = j + 1 + lane; r < h; r += 32) xn2 += cabs2(col[r]);
+      xn2 = warp_sum(xn2);
+      if (lane == 0) {
+        cplx alpha = col[j];
+        if (xn2 == 0.0 && alpha.y == 0.0) { tau[j] = cmake(0, 0); scal[0] = cmake(0, 0); }
+        else {
+          double beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xn2), alpha.x);
+          tau[j] = cmake((beta - alpha.x) / beta, -alpha.y / beta);
+          double dr = alpha.x - beta, di = alpha.y, den = dr * dr + di * di;
+          scal[0] = cmake(dr / den, -di / den);
+          col[j] = cmake(beta, 0);
+        }
+      }
+    }
+    __syncthreads();
+    {
+      cplx sc = scal[0];
+      for (int r = j + 1 + tid; r < h; r += blockDim.x) col[r] = cmul(col[r], sc);
+    }
+    __syncthreads();
+    cplx tj = tau[j];
+    if (tj.x != 0.0 || tj.y != 0.0) {                     // apply H(j)^H = I - conj(tau) v v^H to the trailing columns
+      for (int c = j + 1 + warp; c < nc; c += nwarps) {
+        cplx* cc = A + (size_t)c * h;
+        cplx w = cmake(0, 0);
+        for (int r = j + 1 + lane; r < h; r += 32) cfma_ca(w, col[r], cc[r]);
+        w.x = warp_sum(w.x); w.y = warp_sum(w.y);
+        w = cadd(w, cc[j]);                                // v_j = 1
+        cplx f = cmul(cconj(tj), w);
+        if (lane == 0) cc[j] = csub(cc[j], f);
+        for (int r = j + 1 + lane; r < h; r += 32) cc[r] = csub(cc[r], cmul(f, col[r]));
+      }
+    }
+    __syncthreads();
+  }
+  // R out
+  for (int idx = tid; idx < q * nc; idx += blockDim.x) {
+    int i = idx % q, c = idx / q;
+    d.rout[i + (size_t)c * d.ldr] = (i <= c) ? A[i + (size_t)c * h] : cmake(0, 0);
+  }
+  __syncthreads();
+  // explicit Q (h x q) in place (zung2r)
+  for (int i = q - 1; i >= 0; --i) {
+    cplx* col = A + (size_t)i * h;
+    cplx ti = tau[i];
+    if (ti.x != 0.0 || ti.y != 0.0) {
+      for (int c = i + 1 + warp; c < q; c += nwarps) {
+        cplx* cc = A + (size_t)c * h;
+        cplx w = cmake(0, 0);
+        for (int r = i + 1 + lane; r < h; r += 32) cfma_ca(w, col[r], cc[r]);
+        w.x = warp_sum(w.x); w.y = warp_sum(w.y);
+        w = cadd(w, cc[i]);
+        cplx f = cmul(ti, w);
+        if (lane == 0) cc[i] = csub(cc[i], f);
+        for (int r = i + 1 + lane; r < h; r += 32) cc[r] = csub(cc[r], cmul(f, col[r]));
+      }
+    }
+    __syncthreads();
+    for (int r = tid; r < h; r += blockDim.x) {
+      cplx v;
+      if (r < i) v = cmake(0, 0);
+      else if (r == i) v = cmake(1.0 - ti.x, -ti.y);
+      else v = cmul(cmake(-ti.x, -ti.y), col[r]);
+      col[r] = v;
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < h * q; idx += blockDim.x) {
+    int r = idx % h, c = idx / h;
+    d.a[r + (size_t)c * d.lda] = A[idx];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct ThetaDesc {
+  const cplx* r1; int q1, ld1;           // R1[q1, s1 + d*b]
+  const cplx* r2; int q2, ld2;           // R2[q2, s2 + d*b]
+  const cplx* gate;                      // o[s1', s2', s1, s2], column-major d^4
+  int d, chi;
+  cplx* theta;                           // theta'[(q1 + q1n*s1'), (q2 + q2n*s2')], ld = q1*d
+};
+
+// one CTA per gate; thread per (q1, q2) computes the d x d block over the bond, then mixes it with the gate.
+__global__ void __launch_bounds__(256) k_theta(const ThetaDesc* __restrict__ descs) {
+  const ThetaDesc t = descs[blockIdx.x];
+  const int d = t.d;
+  const int m = t.q1 * d;
+  for (int idx = threadIdx.x; idx < t.q1 * t.q2; idx += blockDim.x) {
+    int a = idx % t.q1, c = idx / t.q1;
+    cplx th[16];                                          // d <= 4
+    for (int i = 0; i < d * d; ++i) th[i] = cmake(0, 0);
+    for (int b = 0; b < t.chi; ++b)
+      for (int s2 = 0; s2 < d; ++s2) {
+        cplx y = t.r2[c + (size_t)(s2 + d * b) * t.ld2];
+        for (int s1 = 0; s1 < d; ++s1) cfma(th[s1 + d * s2], t.r1[a + (size_t)(s1 + d * b) * t.ld1], y);
+      }
+    for (int s2p = 0; s2p < d; ++s2p)
+      for (int s1p = 0; s1p < d; ++s1p) {
+        cplx acc = cmake(0, 0);
+        for (int s2 = 0; s2 < d; ++s2)
+          for (int s1 = 0; s1 < d; ++s1)
+            cfma(acc, t.gate[s1p + d * (s2p + d * (s1 + d * s2))], th[s1 + d * s2]);
+        t.theta[(a + t.q1 * s1p) + (size_t)(c + t.q2 * s2p) * m] = acc;
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct SvdDesc {
+  const cplx* theta; int m, n;           // m x n column-major, ld = m
+  cplx* work;                            // global scratch of (max(m,n)*min(m,n) + min(m,n)^2) complex, or null -> shared memory
+  cplx* r1out;                           // U sqrt(S): m x rank, ld = m
+  cplx* r2out;                           // [i, u] = sqrt(S_u) * conj(V[i, u]): n x rank, ld = n
+  double* svals;                         // [cap]
+  int* rank; double* truncerr;
+  cplx* msg_a; cplx* msg_b;              // message slots receiving diag(S) (rank x rank), may be null
+  int maxdim; double cutoff; int has_cutoff; int normalize; int cap; int mindim;
+};
+
+// dynamic shared memory: [W | V] if work == null, then sigma[nn] doubles, perm[nn] ints
+__global__ void __launch_bounds__(1024) k_svd_trunc(const SvdDesc* __restrict__ descs, int* status, size_t smem_wv_bytes) {
+  const SvdDesc d = descs[blockIdx.x];
+  extern __shared__ cplx ssm[];
+  const int m = d.m, n = d.n;
+  const bool swapped = m < n;
+  const int mm = swapped ? n : m, nn = swapped ? m : n;
+  cplx* W = d.work ? d.work : ssm;
+  cplx* V = W + (size_t)mm * nn;
+  double* sigma = (double*)((char*)ssm + smem_wv_bytes);
+  int* perm = (int*)(sigma + nn);
+  __shared__ int sh_rank;
+  __shared__ double sh_norm;
+  for (int idx = threadIdx.x; idx < mm * nn; idx += blockDim.x) {
+    int r = idx % mm, c = idx / mm;
+    cplx v;
+    if (!swapped) v = d.theta[r + (size_t)c * m];
+    else v = cconj(d.theta[c + (size_t)r * m]);        // W = theta'^H
+    W[idx] = v;
+  }
+  for (int idx = threadIdx.x; idx < nn * nn; idx += blockDim.x)
+    V[idx] = cmake((idx % nn) == (idx / nn) ? 1.0 : 0.0, 0.0);
+  __syncthreads();
+  int sweeps = jacobi_columns(W, mm, mm, V, nn, nn, nn);
+  if (sweeps < 0 && threadIdx.x == 0) atomicOr(status, ST_NO_CONV);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < nn; j += nwarps) {
+    double s = 0;
+    for (int r = lane; r < mm; r += 32) s += cabs2(W[r + (size_t)j * mm]);
+    s = warp_sum(s);
+    if (lane == 0) sigma[j] = sqrt(s);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nn; j += blockDim.x) {   // descending order, ties by index
+    double sj = sigma[j];
+    int rk = 0;
+    for (int i = 0; i < nn; ++i) { double si = sigma[i]; rk += (si > sj) || (si == sj && i < j); }
+    perm[rk] = j;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // NDTensors truncate!: P = S^2 descending, sequential tail sums
+    int k = nn;
+    double t = 0.0, err = 0.0;
+    if (k > 1) {
+      int maxdim = d.maxdim > 0 ? min(d.maxdim, k) : k;
+      while (k > maxdim) { double s = sigma[perm[k - 1]]; t += s * s; --k; }
+      double scale = 0.0;
+      for (int i = 0; i < nn; ++i) { double s = sigma[perm[i]]; scale += s * s; }
+      if (scale == 0.0) scale = 1.0;
+      if (d.has_cutoff) {
+        while (k > d.mindim) {
+          double s = sigma[perm[k - 1]];
+          if (!(t + s * s <= d.cutoff * scale)) break;
+          t += s * s; --k;
+        }
+      }
+      err = t / scale;
+    }
+    if (k > d.cap) { atomicOr(status, ST_RANK_CAP); k = d.cap; }
+    double nrm = 0.0;
+    for (int i = 0; i < k; ++i) { double s = sigma[perm[i]]; nrm += s * s; }
+    nrm = sqrt(nrm);
+    sh_rank = k; sh_norm = (d.normalize && nrm > 0.0) ? 1.0 / nrm : 1.0;
+    if (d.rank) *d.rank = k;
+    if (d.truncerr) *d.truncerr = err;
+  }
+  __syncthreads();
+  const int rank = sh_rank;
+  const double sn = sh_norm;
+  for (int u = threadIdx.x; u < d.cap; u += blockDim.x)
+    if (d.svals) d.svals[u] = u < rank ? sigma[perm[u]] * sn : 0.0;
+  for (int idx = threadIdx.x; idx < rank * rank; idx += blockDim.x) {
+    int i = idx % rank, j = idx / rank;
+    cplx v = cmake(i == j ? sigma[perm[i]] * sn : 0.0, 0.0);
+    if (d.msg_a) d.msg_a[idx] = v;
+    if (d.msg_b) d.msg_b[idx] = v;
+  }
+  // factors: not swapped: U sqrt(S) = W_j / sqrt(sigma_j), sqrt(S) conj(V);  swapped: roles exchanged
+  for (int idx = threadIdx.x; idx < m * rank; idx += blockDim.x) {
+    int i = idx % m, u = idx / m, j = perm[u];
+    double s = sigma[j];
+    cplx v;
+    if (!swapped) { double f = s > 0.0 ? 1.0 / sqrt(s) : 0.0; v = cscale(W[i + (size_t)j * mm], f); }
+    else { v = cscale(V[i + (size_t)j * nn], sqrt(s)); }
+    d.r1out[idx] = v;
+  }
+  for (int idx = threadIdx.x; idx < n * rank; idx += blockDim.x) {
+    int i = idx % n, u = idx / n, j = perm[u];
+    double s = sigma[j];
+    cplx v;
+    if (!swapped) { v = cscale(cconj(V[i + (size_t)j * nn]), sqrt(s)); }
+    else { double f = s > 0.0 ? 1.0 / sqrt(s) : 0.0; v = cscale(cconj(W[i + (size_t)j * mm]), f); }
+    d.r2out[idx] = v;
+  }
+}
+
+// C = op(A) * B for small matrices (n <= 64): C[i,j] = sum_k A'[i,k] B[k,j], A' = A^T if transA.  One CTA per item.
+struct SmallMatmulDesc { const cplx* a; const cplx* b; cplx* c; int m, k, n; int lda, ldb, ldc; int transA; };
+__global__ void __launch_bounds__(256) k_small_matmul(const SmallMatmulDesc* __restrict__ descs) {
+  const SmallMatmulDesc d = descs[blockIdx.x];
+  for (int idx = threadIdx.x; idx < d.m * d.n; idx += blockDim.x) {
+    int i = idx % d.m, j = idx / d.m;
+    cplx acc = cmake(0, 0);
+    for (int k = 0; k < d.k; ++k) {
+      cplx a = d.transA ? d.a[k + (size_t)i * d.lda] : d.a[i + (size_t)k * d.lda];
+      cfma(acc, a, d.b[k + (size_t)j * d.ldb]);
+    }
+    d.c[i + (size_t)j * d.ldc] = acc;
+  }
+}

@@ -1,0 +1,1020 @@
+// libtnqs_cuda.so — C-ABI entry points (include/tnqs_cuda.h) over the engine in engine.cuh.
+// Build: see csrc/Makefile (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -shared).
+#include "engine.cuh"
+#include <set>
+#include <map>
+
+static thread_local std::string g_create_error;
+
+#define API_BEGIN(ctx) if (!(ctx)) return TNQS_ERR_INVALID_ARG; try { CU(cudaSetDevice((ctx)->device));
+#define API_END(ctx) } catch (const TnqsError& e) { (ctx)->err = e.msg; (ctx)->release_temps(); return e.code; } \
+  catch (const std::exception& e) { (ctx)->err = e.what(); (ctx)->release_temps(); return TNQS_ERR_INVALID_ARG; } return TNQS_OK;
+
+extern "C" {
+
+const char* tnqs_version(void) { return "tnqs-cuda 0.1 (sm_100a)"; }
+
+const char* tnqs_status_string(int32_t s) {
+  switch (s) {
+    case TNQS_OK: return "ok";
+    case TNQS_ERR_INVALID_ARG: return "invalid argument";
+    case TNQS_ERR_SHAPE: return "shape mismatch";
+    case TNQS_ERR_OVERLAPPING_BATCH: return "gates of a batch overlap";
+    case TNQS_ERR_NEGATIVE_EIGENVALUE: return "message has a negative eigenvalue beyond the cutoff";
+    case TNQS_ERR_SVD_NO_CONVERGENCE: return "Jacobi iteration did not converge";
+    case TNQS_ERR_CUDA: return "CUDA error";
+    case TNQS_ERR_NCCL: return "NCCL error";
+    case TNQS_ERR_OOM: return "out of device memory";
+    case TNQS_ERR_UNSUPPORTED: return "unsupported configuration";
+  }
+  return "unknown";
+}
+
+const char* tnqs_last_error(const tnqs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+static void set_smem_attrs() {
+  static bool done = false;
+  if (done) return;
+  cudaFuncSetAttribute(k_eigh_sqrt, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_house_qr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_svd_trunc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_close_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  done = true;
+}
+
+static void alloc_site(tnqs_ctx* c, int v) {
+  long long n = c->site_elems(v);
+  c->site[v] = (cplx*)c->dalloc((size_t)n * sizeof(cplx));
+  c->site_n[v] = n;
+}
+
+static void upload_chi(tnqs_ctx* c) {
+  CU(cudaMemcpyAsync(c->d_chi, c->chi.data(), sizeof(int) * std::max(c->ne, 1), cudaMemcpyHostToDevice, c->stream));
+}
+
+static void reset_messages(tnqs_ctx* c) {
+  if (c->ne == 0) return;
+  LAUNCH(c, TNQS_KC_MISC, k_msg_identity, 2 * c->ne, 128, 0, c->msg_cur, c->slot, c->d_chi);
+}
+
+static size_t scratch_budget(tnqs_ctx* c) {
+  size_t fr = 0, tot = 0;
+  cudaMemGetInfo(&fr, &tot);
+  size_t b = fr / 4;
+  const size_t cap = (size_t)16 << 30, floor_ = (size_t)64 << 20;
+  return std::max(floor_, std::min(b, cap));
+}
+
+extern "C" int32_t tnqs_create(tnqs_ctx** out, int32_t nv, int32_t ne, const int32_t* esrc, const int32_t* edst,
+                               const int32_t* d, const int32_t* chi, int32_t chi_cap, int32_t device) {
+  if (!out || nv <= 0 || ne < 0 || !d || (ne > 0 && (!esrc || !edst || !chi)) || chi_cap < 1) {
+    g_create_error = "tnqs_create: invalid argument"; return TNQS_ERR_INVALID_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    g_create_error = "tnqs_create: no usable CUDA device (this engine has no CPU fallback)"; return TNQS_ERR_CUDA;
+  }
+  tnqs_ctx* c = new tnqs_ctx();
+  try {
+    c->device = device;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount; c->smem_optin = prop.sharedMemPerBlockOptin;
+    set_smem_attrs();
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->nv = nv; c->ne = ne; c->chi_cap = chi_cap;
+    c->esrc.assign(esrc, esrc + ne); c->edst.assign(edst, edst + ne);
+    c->d.assign(d, d + nv); c->chi.assign(chi, chi + ne);
+    c->inc.assign(nv, {});
+    std::set<std::pair<int, int>> seen;
+    for (int e = 0; e < ne; ++e) {
+      int a = esrc[e], b = edst[e];
+      REQUIRE(a >= 0 && a < nv && b >= 0 && b < nv && a != b, TNQS_ERR_INVALID_ARG, "bad edge endpoints");
+      REQUIRE(seen.insert({std::min(a, b), std::max(a, b)}).second, TNQS_ERR_INVALID_ARG, "duplicate edge");
+      REQUIRE(chi[e] >= 1 && chi[e] <= chi_cap, TNQS_ERR_SHAPE, "bond dimension outside [1, chi_cap]");
+      c->inc[a].push_back(e); c->inc[b].push_back(e);
+    }
+    c->dmax = 1;
+    for (int v = 0; v < nv; ++v) {
+      REQUIRE(d[v] >= 1 && d[v] <= 4, TNQS_ERR_UNSUPPORTED, "site dimension must be in [1, 4]");
+      REQUIRE((int)c->inc[v].size() <= TNQS_MAX_LEGS, TNQS_ERR_UNSUPPORTED, "vertex degree > 8");
+      c->dmax = std::max(c->dmax, d[v]);
+    }
+    REQUIRE(chi_cap <= 64, TNQS_ERR_UNSUPPORTED, "chi_cap > 64 is not supported");
+    c->slot = (long long)chi_cap * chi_cap;
+    c->site.assign(nv, nullptr); c->site_n.assign(nv, 0);
+    for (int v = 0; v < nv; ++v) { alloc_site(c, v); CU(cudaMemsetAsync(c->site[v], 0, c->site_n[v] * sizeof(cplx), c->stream)); }
+    size_t mbytes = (size_t)std::max(1, 2 * ne) * c->slot * sizeof(cplx);
+    c->msg_cur = (cplx*)c->dalloc(mbytes); c->msg_stage = (cplx*)c->dalloc(mbytes);
+    CU(cudaMemsetAsync(c->msg_cur, 0, mbytes, c->stream)); CU(cudaMemsetAsync(c->msg_stage, 0, mbytes, c->stream));
+    c->d_chi = (int*)c->dalloc(sizeof(int) * std::max(ne, 1));
+    c->d_status = (int*)c->dalloc(sizeof(int));
+    CU(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
+    upload_chi(c);
+    reset_messages(c);
+    c->sync();
+  } catch (const TnqsError& e) { g_create_error = e.msg; int code = e.code; delete c; return code; }
+  *out = c;
+  return TNQS_OK;
+}
+
+extern "C" int32_t tnqs_destroy(tnqs_ctx* c) {
+  if (!c) return TNQS_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->collect_profile();
+  for (cplx* p : c->site) if (p) cudaFreeAsync(p, c->stream);
+  if (c->msg_cur) cudaFreeAsync(c->msg_cur, c->stream);
+  if (c->msg_stage) cudaFreeAsync(c->msg_stage, c->stream);
+  if (c->d_chi) cudaFreeAsync(c->d_chi, c->stream);
+  if (c->d_status) cudaFreeAsync(c->d_status, c->stream);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return TNQS_OK;
+}
+
+extern "C" int32_t tnqs_clone(const tnqs_ctx* src, tnqs_ctx** out) {
+  if (!src || !out) return TNQS_ERR_INVALID_ARG;
+  tnqs_ctx* c = nullptr;
+  int32_t st = tnqs_create(&c, src->nv, src->ne, src->esrc.data(), src->edst.data(), src->d.data(), src->chi.data(),
+                           src->chi_cap, src->device);
+  if (st != TNQS_OK) return st;
+  try {
+    CU(cudaStreamSynchronize(src->stream));
+    for (int v = 0; v < c->nv; ++v)
+      CU(cudaMemcpyAsync(c->site[v], src->site[v], src->site_n[v] * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->msg_cur, src->msg_cur, (size_t)std::max(1, 2 * c->ne) * c->slot * sizeof(cplx),
+                       cudaMemcpyDeviceToDevice, c->stream));
+    c->owner = src->owner; c->rank = src->rank; c->partitioned = src->partitioned;
+    c->sync();
+  } catch (const TnqsError& e) { g_create_error = e.msg; int code = e.code; tnqs_destroy(c); return code; }
+  *out = c;
+  return TNQS_OK;
+}
+
+extern "C" int32_t tnqs_sync(tnqs_ctx* c) { API_BEGIN(c) c->sync(); API_END(c) }
+extern "C" int32_t tnqs_num_vertices(const tnqs_ctx* c) { return c ? c->nv : 0; }
+extern "C" int32_t tnqs_num_edges(const tnqs_ctx* c) { return c ? c->ne : 0; }
+extern "C" int32_t tnqs_get_bond_dims(const tnqs_ctx* c, int32_t* chi) {
+  if (!c || !chi) return TNQS_ERR_INVALID_ARG;
+  for (int e = 0; e < c->ne; ++e) chi[e] = c->chi[e];
+  return TNQS_OK;
+}
+extern "C" int64_t tnqs_site_size(const tnqs_ctx* c, int32_t v) { return (c && v >= 0 && v < c->nv) ? c->site_n[v] : -1; }
+
+extern "C" int32_t tnqs_set_site(tnqs_ctx* c, int32_t v, const double* data, int64_t n) {
+  API_BEGIN(c)
+  REQUIRE(v >= 0 && v < c->nv && data, TNQS_ERR_INVALID_ARG, "tnqs_set_site: bad vertex or null data");
+  REQUIRE(n == c->site_n[v], TNQS_ERR_SHAPE, "tnqs_set_site: element count does not match the site tensor");
+  CU(cudaMemcpyAsync(c->site[v], data, n * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  c->sync();
+  API_END(c)
+}
+extern "C" int32_t tnqs_get_site(const tnqs_ctx* cc, int32_t v, double* data, int64_t n) {
+  tnqs_ctx* c = const_cast<tnqs_ctx*>(cc);
+  API_BEGIN(c)
+  REQUIRE(v >= 0 && v < c->nv && data, TNQS_ERR_INVALID_ARG, "tnqs_get_site: bad vertex or null data");
+  REQUIRE(n == c->site_n[v], TNQS_ERR_SHAPE, "tnqs_get_site: element count does not match the site tensor");
+  CU(cudaMemcpyAsync(data, c->site[v], n * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  API_END(c)
+}
+extern "C" int32_t tnqs_fill_random(tnqs_ctx* c, uint64_t seed) {
+  API_BEGIN(c)
+  for (int v = 0; v < c->nv; ++v) {
+    long long n = c->site_n[v];
+    int blocks = (int)std::min<long long>((n + 255) / 256, 4096);
+    LAUNCH(c, TNQS_KC_MISC, k_fill_random, blocks, 256, 0, c->site[v], n, (unsigned long long)seed, (unsigned long long)v);
+  }
+  c->sync();
+  API_END(c)
+}
+extern "C" int32_t tnqs_set_message(tnqs_ctx* c, int32_t k, const double* data, int64_t n) {
+  API_BEGIN(c)
+  REQUIRE(k >= 0 && k < 2 * c->ne && data, TNQS_ERR_INVALID_ARG, "tnqs_set_message: bad edge or null data");
+  long long x = c->chi[k >> 1];
+  REQUIRE(n == x * x, TNQS_ERR_SHAPE, "tnqs_set_message: element count != chi^2");
+  CU(cudaMemcpyAsync(c->msg(k), data, n * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  c->sync();
+  API_END(c)
+}
+extern "C" int32_t tnqs_get_message(const tnqs_ctx* cc, int32_t k, double* data, int64_t n) {
+  tnqs_ctx* c = const_cast<tnqs_ctx*>(cc);
+  API_BEGIN(c)
+  REQUIRE(k >= 0 && k < 2 * c->ne && data, TNQS_ERR_INVALID_ARG, "tnqs_get_message: bad edge or null data");
+  long long x = c->chi[k >> 1];
+  REQUIRE(n == x * x, TNQS_ERR_SHAPE, "tnqs_get_message: element count != chi^2");
+  CU(cudaMemcpyAsync(data, c->msg(k), n * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  API_END(c)
+}
+extern "C" int32_t tnqs_reset_messages(tnqs_ctx* c) { API_BEGIN(c) reset_messages(c); c->sync(); API_END(c) }
+
+// ---------------------------------------------------------------------------------------------------------------
+// BP sweep
+// ---------------------------------------------------------------------------------------------------------------
+static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, const tnqs_bp_opts& o, int* iters_out,
+                           double* mean_out) {
+  REQUIRE(o.maxiter >= 1, TNQS_ERR_INVALID_ARG, "You need to specify a number of iterations for BP!");
+  std::vector<int> seq;
+  for (int i = 0; i < nseq_in; ++i) {
+    int k = seq_in[i];
+    REQUIRE(k >= 0 && k < 2 * c->ne, TNQS_ERR_INVALID_ARG, "edge sequence entry out of range");
+    if (c->partitioned && c->owner[c->dsrc(k)] != c->rank) continue;
+    seq.push_back(k);
+  }
+  const int nseq = (int)seq.size();
+  if (iters_out) *iters_out = 0;
+  if (mean_out) *mean_out = NAN;
+  if (nseq == 0) return;
+  const bool want_diff = o.tolerance >= 0;
+  // dependency levels of the sequential (Gauss-Seidel) order; reads of a level happen before its commit
+  std::vector<int> level(nseq, 0);
+  int nlevels = 1;
+  if (o.mode == TNQS_BP_REFERENCE_ORDER) {
+    std::vector<int> lastwrite(2 * c->ne, -1), lastread(2 * c->ne, -1);
+    for (int i = 0; i < nseq; ++i) {
+      int k = seq[i], v = c->dsrc(k), w = c->ddst(k), lvl = 0;
+      for (int e : c->inc[v]) {
+        int u = c->other(e, v);
+        if (u == w) continue;
+        int r = c->dedge(u, e);
+        if (lastwrite[r] >= 0) lvl = std::max(lvl, lastwrite[r] + 1);     // RAW
+      }
+      lvl = std::max(lvl, lastread[k]);                                     // WAR (same level is safe)
+      lvl = std::max(lvl, lastwrite[k] + 1);                                // WAW
+      level[i] = lvl; lastwrite[k] = lvl;
+      for (int e : c->inc[v]) {
+        int u = c->other(e, v);
+        if (u == w) continue;
+        int r = c->dedge(u, e);
+        lastread[r] = std::max(lastread[r], lvl);
+      }
+      nlevels = std::max(nlevels, lvl + 1);
+    }
+  } else {
+    std::set<int> uniq(seq.begin(), seq.end());
+    REQUIRE((int)uniq.size() == nseq, TNQS_ERR_INVALID_ARG, "JACOBI mode needs each directed edge at most once");
+  }
+  double* d_diff = c->talloc<double>(nseq + 1);
+  std::vector<std::vector<Chain>> levels(nlevels);
+  for (int i = 0; i < nseq; ++i) {
+    int k = seq[i], v = c->dsrc(k), w = c->ddst(k), e = k >> 1;
+    Chain ch; ch.v = v;
+    for (size_t j = 0; j < c->inc[v].size(); ++j) {
+      int ee = c->inc[v][j], u = c->other(ee, v);
+      if (u == w) { ch.close_leg = (int)j; continue; }
+      Absorb ab; ab.leg = (int)j; ab.mat = c->msg(c->dedge(u, ee)); ab.ldm = c->chi[ee]; ab.flags = 0;
+      ch.absorb.push_back(ab);
+    }
+    (void)e;
+    ch.dst = c->msg_st(k); ch.prev = c->msg(k); ch.diff = want_diff ? d_diff + i : nullptr;
+    ch.bp_mode = 1; ch.normalize = o.normalize; ch.hermitize = o.hermitize; ch.commit_k = k;
+    levels[level[i]].push_back(ch);
+  }
+  Plan plan = build_plan(c, levels, scratch_budget(c));
+  double* d_sum = d_diff + nseq;
+  int it = 0; double mean = NAN;
+  for (it = 1; it <= o.maxiter; ++it) {
+    run_plan(c, plan);
+    if (want_diff) {
+      LAUNCH(c, TNQS_KC_BP_FINALIZE, k_sum, 1, 1024, 0, d_diff, nseq, d_sum);
+      double s = 0;
+      CU(cudaMemcpyAsync(&s, d_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      c->sync();
+      mean = s / nseq;
+      if (mean <= o.tolerance) break;
+    }
+  }
+  if (it > o.maxiter) it = o.maxiter;
+  if (iters_out) *iters_out = it;
+  if (mean_out) *mean_out = mean;
+}
+
+extern "C" int32_t tnqs_bp_update(tnqs_ctx* c, const int32_t* edge_seq, int32_t nseq, const tnqs_bp_opts* opts,
+                                  int32_t* iters, double* mean_diff) {
+  API_BEGIN(c)
+  REQUIRE(opts && (edge_seq || nseq == 0) && nseq >= 0, TNQS_ERR_INVALID_ARG, "tnqs_bp_update: null argument");
+  bp_update_impl(c, edge_seq, nseq, *opts, iters, mean_diff);
+  c->sync();
+  c->release_temps();
+  API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// gates
+// ---------------------------------------------------------------------------------------------------------------
+static void apply_1site_impl(tnqs_ctx* c, int n, const int32_t* vs, const double* gates, int normalize) {
+  if (n == 0) return;
+  std::set<int> seen;
+  std::vector<cplx> hg; std::vector<size_t> goff(n);
+  size_t base = 0;
+  for (int i = 0; i < n; ++i) {
+    int v = vs[i];
+    REQUIRE(v >= 0 && v < c->nv, TNQS_ERR_INVALID_ARG, "tnqs_apply_1site: vertex out of range");
+    REQUIRE(seen.insert(v).second, TNQS_ERR_OVERLAPPING_BATCH, "tnqs_apply_1site: repeated vertex in batch");
+    goff[i] = hg.size();
+    int d = c->d[v];
+    const cplx* g = (const cplx*)gates + base;
+    hg.insert(hg.end(), g, g + d * d);
+    base += (size_t)d * d;
+  }
+  cplx* d_g = c->upload(hg);
+  const int NB = 64;                       // norm partials per site
+  double* d_part = c->talloc<double>((size_t)n * NB);
+  double* d_n2 = c->talloc<double>(n);
+  std::vector<Gate1Desc> g1(n); std::vector<Norm2Desc> nd(n); std::vector<ScaleDesc> sd(n);
+  std::vector<cplx*> outs(n);
+  for (int i = 0; i < n; ++i) {
+    int v = vs[i];
+    outs[i] = (cplx*)c->dalloc(c->site_n[v] * sizeof(cplx));
+    g1[i].in = c->site[v]; g1[i].out = outs[i]; g1[i].gate = d_g + goff[i]; g1[i].d = c->d[v];
+    g1[i].rest = c->site_n[v] / c->d[v]; g1[i].norm2_partial = d_part + (size_t)i * NB;
+    nd[i].x = nullptr; nd[i].n = 0; nd[i].out = d_n2 + i; nd[i].partial = d_part + (size_t)i * NB; nd[i].npartial = NB;
+    sd[i].x = outs[i]; sd[i].n = c->site_n[v]; sd[i].scalar = d_n2 + i; sd[i].mode = 0;
+  }
+  Gate1Desc* dg1 = c->upload(g1);
+  LAUNCH(c, TNQS_KC_MISC, k_gate1, dim3(NB, n), 256, 0, dg1);
+  if (normalize) {
+    Norm2Desc* dnd = c->upload(nd); ScaleDesc* dsd = c->upload(sd);
+    LAUNCH(c, TNQS_KC_MISC, k_norm2, n, 64, 0, dnd);
+    LAUNCH(c, TNQS_KC_MISC, k_scale, dim3(NB, n), 256, 0, dsd);
+  }
+  for (int i = 0; i < n; ++i) { c->dfree(c->site[vs[i]]); c->site[vs[i]] = outs[i]; }
+}
+
+extern "C" int32_t tnqs_apply_1site(tnqs_ctx* c, int32_t n, const int32_t* v, const double* gates, int32_t normalize) {
+  API_BEGIN(c)
+  REQUIRE(n >= 0 && (n == 0 || (v && gates)), TNQS_ERR_INVALID_ARG, "tnqs_apply_1site: null argument");
+  apply_1site_impl(c, n, v, gates, normalize);
+  c->sync();
+  c->release_temps();
+  API_END(c)
+}
+
+// both directed messages of edge list[i] <- diag(svals[i*cap .. i*cap + rank[i]))
+__global__ void k_msg_diag(cplx* slab, long long slot, const int* list, const double* svals, const int* rank, int cap) {
+  int i = blockIdx.x, e = list[i], r = rank[i];
+  cplx* a = slab + (size_t)(2 * e) * slot; cplx* b = a + slot;
+  for (int idx = threadIdx.x; idx < r * r; idx += blockDim.x) {
+    int x = idx % r, y = idx / r;
+    cplx v = cmake(x == y ? svals[(size_t)i * cap + x] : 0.0, 0.0);
+    a[idx] = v; b[idx] = v;
+  }
+}
+
+// Plan of the TSQR tree of one matrix (Po x nc, column-major, ld = Po), see DESIGN.md "QR".
+struct QrLevel { cplx* base; long long ld; long long rows; std::vector<long long> blk_begin; };   // blocks = row ranges
+
+static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_t* flips, const double* gates,
+                             const tnqs_apply_opts& o, int32_t* ranks_out, double* err_out, double* svals_out) {
+  if (n == 0) return;
+  const int cap = c->chi_cap;
+  std::set<int> seen;
+  struct SiteJob {
+    int v, e, jb, d, chib; long long Po; int nc, q; std::vector<int> outer;   // outer: bond leg indices ascending
+    cplx* A; cplx* Rbuf; std::vector<cplx*> root, invroot;
+  };
+  std::vector<SiteJob> jobs(2 * n);
+  for (int i = 0; i < n; ++i) {
+    int e = es[i];
+    REQUIRE(e >= 0 && e < c->ne, TNQS_ERR_INVALID_ARG, "tnqs_apply_2site: edge out of range");
+    int v1 = flips && flips[i] ? c->edst[e] : c->esrc[e], v2 = c->other(e, v1);
+    REQUIRE(seen.insert(v1).second && seen.insert(v2).second, TNQS_ERR_OVERLAPPING_BATCH,
+            "tnqs_apply_2site: gates of a batch share a vertex");
+    REQUIRE(c->d[v1] == c->d[v2], TNQS_ERR_UNSUPPORTED, "two-site gate on sites of different dimension");
+    for (int s = 0; s < 2; ++s) {
+      SiteJob& J = jobs[2 * i + s];
+      J.v = s == 0 ? v1 : v2; J.e = e; J.jb = c->leg(J.v, e); J.d = c->d[J.v]; J.chib = c->chi[e];
+      J.Po = 1;
+      for (size_t j = 0; j < c->inc[J.v].size(); ++j) if ((int)j != J.jb) { J.outer.push_back((int)j); J.Po *= c->chi[c->inc[J.v][j]]; }
+      J.nc = J.d * J.chib; J.q = (int)std::min<long long>(J.Po, J.nc);
+      REQUIRE(J.nc <= 64, TNQS_ERR_UNSUPPORTED, "d * chi > 64 is not supported by the two-site gate path");
+    }
+  }
+  const int NJ = 2 * n;
+  // ---- 1. sqrt / inverse sqrt of the incoming messages (src/utils.jl:18-26) ----
+  std::vector<EighDesc> eg;
+  int maxchi = 1;
+  for (SiteJob& J : jobs)
+    for (int j : J.outer) {
+      int ee = c->inc[J.v][j], u = c->other(ee, J.v), x = c->chi[ee];
+      EighDesc d; d.m = c->msg(c->dedge(u, ee)); d.n = x; d.ldm = x;
+      d.root = c->talloc<cplx>((size_t)x * x); d.invroot = c->talloc<cplx>((size_t)x * x);
+      d.cutoff = 10 * TNQS_EPS; d.shift = 0; d.mode = 0;
+      J.root.push_back(d.root); J.invroot.push_back(d.invroot);
+      eg.push_back(d); maxchi = std::max(maxchi, x);
+    }
+  if (!eg.empty()) {
+    EighDesc* deg = c->upload(eg);
+    int threads = 32 * std::max(1, std::min(32, (maxchi + 1) / 2));
+    size_t smem = (size_t)2 * maxchi * maxchi * sizeof(cplx) + 3 * maxchi * sizeof(double);
+    LAUNCH(c, TNQS_KC_EIGH, k_eigh_sqrt, (unsigned)eg.size(), threads, smem, deg, c->d_status);
+  }
+  // ---- 2. matricise: A[outer.., (s, b)] ----
+  std::vector<PermDesc> pd(NJ);
+  long long maxtot = 1;
+  for (int j = 0; j < NJ; ++j) {
+    SiteJob& J = jobs[j];
+    J.A = c->talloc<cplx>((size_t)c->site_n[J.v]);
+    J.Rbuf = c->talloc<cplx>((size_t)J.nc * J.nc);
+    PermDesc& p = pd[j];
+    p.src = c->site[J.v]; p.dst = J.A; p.d = J.d; p.chib = J.chib; p.nouter = (int)J.outer.size();
+    long long stride = J.d;
+    for (size_t l = 0, oi = 0; l < c->inc[J.v].size(); ++l) {
+      int x = c->chi[c->inc[J.v][l]];
+      if ((int)l == J.jb) p.bstride = stride; else { p.odim[oi] = x; p.ostride[oi] = stride; ++oi; }
+      stride *= x;
+    }
+    p.Po = J.Po; p.to_matrix = 1; p.norm2 = nullptr;
+    maxtot = std::max(maxtot, (long long)c->site_n[J.v]);
+  }
+  {
+    PermDesc* dpd = c->upload(pd);
+    unsigned gx = (unsigned)std::min<long long>((maxtot + 255) / 256, 2048);
+    LAUNCH(c, TNQS_KC_PERMUTE, k_permute, dim3(gx, NJ), 256, 0, dpd);
+  }
+  // ---- 3. absorb sqrt(M_k) on the outer legs, in place in the matrix layout (simple_update.jl:35-36) ----
+  auto absorb_outer = [&](bool inverse, std::vector<int>& ncols) {
+    size_t maxouter = 0;
+    for (SiteJob& J : jobs) maxouter = std::max(maxouter, J.outer.size());
+    for (size_t s = 0; s < maxouter; ++s) {
+      std::vector<ModeApplyDesc> ma; long long maxtiles = 1;
+      for (int j = 0; j < NJ; ++j) {
+        SiteJob& J = jobs[j];
+        if (s >= J.outer.size()) continue;
+        long long Lp = 1;
+        for (size_t i = 0; i < s; ++i) Lp *= c->chi[c->inc[J.v][J.outer[i]]];
+        int x = c->chi[c->inc[J.v][J.outer[s]]];
+        long long R = J.Po / (Lp * x) * ncols[j];
+        ModeApplyDesc d; d.in = J.A; d.out = J.A; d.m = inverse ? J.invroot[s] : J.root[s];
+        d.L = (int)Lp; d.n = x; d.np = x; d.R = (int)R; d.in_sb = Lp; d.in_sr = Lp * x; d.out_sb = Lp; d.out_sr = Lp * x;
+        d.ldm = x; d.flags = inverse ? 3 : 0;      // Q * dag(M^-1/2): element (c, b) = conj(Minv[b, c])
+        ma.push_back(d);
+        maxtiles = std::max(maxtiles, (Lp * R + MA_BM - 1) / MA_BM);
+      }
+      if (ma.empty()) continue;
+      ModeApplyDesc* dma = c->upload(ma);
+      LAUNCH(c, TNQS_KC_MODE_APPLY, k_mode_apply, dim3((unsigned)maxtiles, (unsigned)ma.size(), 1), 256, 0, dma);
+    }
+  };
+  std::vector<int> ncols(NJ);
+  for (int j = 0; j < NJ; ++j) ncols[j] = jobs[j].nc;
+  absorb_outer(false, ncols);
+  // ---- 4. TSQR with explicit thin Q, in place (simple_update.jl:39-40) ----
+  {
+    std::vector<std::vector<QrLevel>> trees(NJ);
+    size_t maxlev = 0;
+    for (int j = 0; j < NJ; ++j) {
+      SiteJob& J = jobs[j];
+      const long long hmax = std::max<long long>(8192 / J.nc, 2 * J.nc);
+      QrLevel lv; lv.base = J.A; lv.ld = J.Po; lv.rows = J.Po;
+      while (true) {
+        long long nb = lv.rows <= hmax ? 1 : (lv.rows + hmax - 1) / hmax;
+        lv.blk_begin.clear();
+        for (long long b = 0; b <= nb; ++b) lv.blk_begin.push_back(lv.rows * b / nb);
+        trees[j].push_back(lv);
+        if (nb == 1) break;
+        QrLevel nx; nx.rows = nb * J.nc; nx.ld = nx.rows; nx.base = c->talloc<cplx>((size_t)nx.rows * J.nc);
+        lv = nx;
+      }
+      maxlev = std::max(maxlev, trees[j].size());
+    }
+    // upward sweep: factor every block, R factors stack into the next level
+    for (size_t l = 0; l < maxlev; ++l) {
+      std::vector<QrDesc> qd; size_t smem = 0;
+      for (int j = 0; j < NJ; ++j) {
+        if (l >= trees[j].size()) continue;
+        SiteJob& J = jobs[j]; QrLevel& lv = trees[j][l];
+        bool top = l + 1 == trees[j].size();
+        size_t nb = lv.blk_begin.size() - 1;
+        for (size_t b = 0; b < nb; ++b) {
+          QrDesc d; d.a = lv.base + lv.blk_begin[b]; d.lda = lv.ld; d.h = (int)(lv.blk_begin[b + 1] - lv.blk_begin[b]); d.nc = J.nc;
+          if (top) { d.rout = J.Rbuf; d.ldr = std::min(d.h, J.nc); }
+          else { d.rout = trees[j][l + 1].base + (long long)b * J.nc; d.ldr = (int)trees[j][l + 1].ld; }
+          qd.push_back(d);
+          smem = std::max(smem, ((size_t)d.h * d.nc + d.nc + 2) * sizeof(cplx));
+        }
+      }
+      REQUIRE(smem <= 200 * 1024, TNQS_ERR_UNSUPPORTED, "QR block does not fit shared memory");
+      QrDesc* dqd = c->upload(qd);
+      LAUNCH(c, TNQS_KC_QR, k_house_qr, (unsigned)qd.size(), 256, smem, dqd);
+    }
+    // downward sweep: Q_block <- Q_block * (its nc x nc slice of the parent's explicit Q)
+    for (int l = (int)maxlev - 2; l >= 0; --l) {
+      std::vector<ModeApplyDesc> ma; long long maxtiles = 1;
+      for (int j = 0; j < NJ; ++j) {
+        if ((size_t)l + 1 >= trees[j].size()) continue;
+        SiteJob& J = jobs[j]; QrLevel& lv = trees[j][l]; QrLevel& up = trees[j][l + 1];
+        size_t nb = lv.blk_begin.size() - 1;
+        for (size_t b = 0; b < nb; ++b) {
+          ModeApplyDesc d; d.in = lv.base + lv.blk_begin[b]; d.out = const_cast<cplx*>(d.in);
+          d.m = up.base + (long long)b * J.nc; d.ldm = (int)up.ld; d.flags = 0;
+          d.L = (int)(lv.blk_begin[b + 1] - lv.blk_begin[b]); d.n = J.nc; d.np = J.nc; d.R = 1;
+          d.in_sb = lv.ld; d.in_sr = 0; d.out_sb = lv.ld; d.out_sr = 0;
+          ma.push_back(d);
+          maxtiles = std::max(maxtiles, ((long long)d.L + MA_BM - 1) / MA_BM);
+        }
+      }
+      if (ma.empty()) continue;
+      ModeApplyDesc* dma = c->upload(ma);
+      LAUNCH(c, TNQS_KC_QR, k_mode_apply, dim3((unsigned)maxtiles, (unsigned)ma.size(), 1), 256, 0, dma);
+    }
+  }
+  // ---- 5. theta = R1 R2 over the bond, gate (simple_update.jl:43) ----
+  std::vector<ThetaDesc> td(n); std::vector<SvdDesc> sv(n);
+  int* d_rank = c->talloc<int>(n); double* d_err = c->talloc<double>(n); double* d_sv = c->talloc<double>((size_t)n * cap);
+  cplx* d_gates = c->talloc<cplx>((size_t)n * 256);
+  std::vector<cplx*> r1n(n), r2n(n);
+  size_t svd_smem_wv = 0; int svd_maxn = 2; bool any_global = false;
+  {
+    size_t goff = 0; std::vector<cplx> hg;
+    for (int i = 0; i < n; ++i) {
+      SiteJob& A = jobs[2 * i]; SiteJob& B = jobs[2 * i + 1];
+      int d = A.d, d4 = d * d * d * d;
+      const cplx* g = (const cplx*)gates + goff; goff += d4;
+      size_t hoff = hg.size(); hg.insert(hg.end(), g, g + d4);
+      ThetaDesc& t = td[i];
+      t.r1 = A.Rbuf; t.q1 = A.q; t.ld1 = A.q; t.r2 = B.Rbuf; t.q2 = B.q; t.ld2 = B.q; t.gate = d_gates + hoff; t.d = d; t.chi = A.chib;
+      int m = A.q * d, nn = B.q * d;
+      t.theta = c->talloc<cplx>((size_t)m * nn);
+      r1n[i] = c->talloc<cplx>((size_t)m * std::min(std::min(m, nn), cap));
+      r2n[i] = c->talloc<cplx>((size_t)nn * std::min(std::min(m, nn), cap));
+      SvdDesc& s = sv[i];
+      s.theta = t.theta; s.m = m; s.n = nn; s.r1out = r1n[i]; s.r2out = r2n[i];
+      s.svals = d_sv + (size_t)i * cap; s.rank = d_rank + i; s.truncerr = d_err + i; s.msg_a = nullptr; s.msg_b = nullptr;
+      s.maxdim = o.maxdim; s.has_cutoff = !std::isnan(o.cutoff); s.cutoff = s.has_cutoff ? o.cutoff : 0.0;
+      s.normalize = o.normalize_tensors; s.cap = cap; s.mindim = 1;
+      int mm = std::max(m, nn), mn = std::min(m, nn);
+      size_t wv = ((size_t)mm * mn + (size_t)mn * mn) * sizeof(cplx);
+      if (wv + mn * 12 + 64 <= 190 * 1024) { s.work = nullptr; svd_smem_wv = std::max(svd_smem_wv, wv); }
+      else { s.work = c->talloc<cplx>(wv / sizeof(cplx)); any_global = true; }
+      svd_maxn = std::max(svd_maxn, mn);
+    }
+    CU(cudaMemcpyAsync(d_gates, hg.data(), hg.size() * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  }
+  (void)any_global;
+  {
+    ThetaDesc* dtd = c->upload(td);
+    LAUNCH(c, TNQS_KC_SVD, k_theta, n, 256, 0, dtd);
+    // ---- 6. Jacobi SVD + truncation (simple_update.jl:46-61) ----
+    SvdDesc* dsv = c->upload(sv);
+    int threads = 32 * std::max(1, std::min(32, (svd_maxn + 1) / 2));
+    size_t smem = svd_smem_wv + (size_t)svd_maxn * 12 + 64;
+    LAUNCH(c, TNQS_KC_SVD, k_svd_trunc, n, threads, smem, dsv, c->d_status, svd_smem_wv);
+  }
+  std::vector<int> ranks(n);
+  CU(cudaMemcpyAsync(ranks.data(), d_rank, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  int st = c->read_status();
+  if (st & ST_NEG_EIG) throw TnqsError(TNQS_ERR_NEGATIVE_EIGENVALUE, "message eigenvalue < -10 eps in simple update");
+  if (st & ST_NO_CONV) throw TnqsError(TNQS_ERR_SVD_NO_CONVERGENCE, "Jacobi eigen/SVD iteration did not converge");
+  if (st & ST_RANK_CAP) throw TnqsError(TNQS_ERR_SHAPE, "kept rank exceeds chi_cap (raise chi_cap or set maxdim)");
+  // ---- 7. Q <- Q * dag(M^-1/2) on the outer legs (simple_update.jl:55-56) ----
+  for (int j = 0; j < NJ; ++j) ncols[j] = jobs[j].q;
+  absorb_outer(true, ncols);
+  // ---- 8. T' = Q R' (simple_update.jl:57), normalise, back to the canonical layout ----
+  std::vector<cplx*> Tm(NJ), newsite(NJ);
+  {
+    std::vector<ModeApplyDesc> ma(NJ); long long maxtiles = 1; int maxcol = 1;
+    for (int j = 0; j < NJ; ++j) {
+      SiteJob& J = jobs[j]; int r = ranks[j / 2];
+      Tm[j] = c->talloc<cplx>((size_t)J.Po * J.d * r);
+      ModeApplyDesc& d = ma[j];
+      d.in = J.A; d.out = Tm[j]; d.m = (j & 1) ? r2n[j / 2] : r1n[j / 2];
+      d.L = (int)J.Po; d.n = J.q; d.np = J.d * r; d.R = 1; d.in_sb = J.Po; d.in_sr = 0; d.out_sb = J.Po; d.out_sr = 0;
+      d.ldm = J.q; d.flags = 0;
+      maxtiles = std::max(maxtiles, (J.Po + MA_BM - 1) / MA_BM); maxcol = std::max(maxcol, (d.np + MA_BN - 1) / MA_BN);
+    }
+    ModeApplyDesc* dma = c->upload(ma);
+    LAUNCH(c, TNQS_KC_MODE_APPLY, k_mode_apply, dim3((unsigned)maxtiles, NJ, maxcol), 256, 0, dma);
+  }
+  double* d_n2 = c->talloc<double>(NJ);
+  if (o.normalize_tensors) {
+    std::vector<Norm2Desc> nd(NJ);
+    for (int j = 0; j < NJ; ++j) { nd[j].x = Tm[j]; nd[j].n = jobs[j].Po * jobs[j].d * ranks[j / 2]; nd[j].out = d_n2 + j; nd[j].partial = nullptr; nd[j].npartial = 0; }
+    Norm2Desc* dnd = c->upload(nd);
+    LAUNCH(c, TNQS_KC_MISC, k_norm2, NJ, 1024, 0, dnd);
+  }
+  {
+    long long maxtot2 = 1;
+    for (int j = 0; j < NJ; ++j) {
+      SiteJob& J = jobs[j]; int r = ranks[j / 2];
+      long long tot = J.Po * J.d * r;
+      newsite[j] = (cplx*)c->dalloc((size_t)tot * sizeof(cplx));
+      PermDesc& p = pd[j];
+      p.src = Tm[j]; p.dst = newsite[j]; p.chib = r; p.to_matrix = 0; p.norm2 = o.normalize_tensors ? d_n2 + j : nullptr;
+      long long stride = J.d;
+      for (size_t l = 0, oi = 0; l < c->inc[J.v].size(); ++l) {
+        int x = (int)l == J.jb ? r : c->chi[c->inc[J.v][l]];
+        if ((int)l == J.jb) p.bstride = stride; else { p.odim[oi] = x; p.ostride[oi] = stride; ++oi; }
+        stride *= x;
+      }
+      maxtot2 = std::max(maxtot2, tot);
+    }
+    PermDesc* dpd = c->upload(pd);
+    unsigned gx = (unsigned)std::min<long long>((maxtot2 + 255) / 256, 2048);
+    LAUNCH(c, TNQS_KC_PERMUTE, k_permute, dim3(gx, NJ), 256, 0, dpd);
+  }
+  // ---- 9. commit: bond dimensions, site pointers, messages <- diag(S) (apply_gates.jl:105-119) ----
+  for (int i = 0; i < n; ++i) c->chi[es[i]] = ranks[i];
+  upload_chi(c);
+  for (int j = 0; j < NJ; ++j) {
+    c->dfree(c->site[jobs[j].v]); c->site[jobs[j].v] = newsite[j];
+    c->site_n[jobs[j].v] = jobs[j].Po * jobs[j].d * ranks[j / 2];
+  }
+  {
+    std::vector<int> ks(es, es + n);
+    int* dks = c->upload(ks);
+    LAUNCH(c, TNQS_KC_MISC, k_msg_diag, n, 128, 0, c->msg_cur, c->slot, dks, d_sv, d_rank, cap);
+  }
+  if (ranks_out) for (int i = 0; i < n; ++i) ranks_out[i] = ranks[i];
+  if (err_out) CU(cudaMemcpyAsync(err_out, d_err, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (svals_out) CU(cudaMemcpyAsync(svals_out, d_sv, (size_t)n * cap * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+}
+
+extern "C" int32_t tnqs_apply_2site(tnqs_ctx* c, int32_t n, const int32_t* e, const int32_t* flip, const double* gates,
+                                    const tnqs_apply_opts* opts, int32_t* ranks, double* truncerr, double* svals) {
+  API_BEGIN(c)
+  REQUIRE(n >= 0 && opts && (n == 0 || (e && gates)), TNQS_ERR_INVALID_ARG, "tnqs_apply_2site: null argument");
+  apply_2site_impl(c, n, e, flip, gates, *opts, ranks, truncerr, svals);
+  c->release_temps();
+  API_END(c)
+}
+
+extern "C" int32_t tnqs_apply_circuit(tnqs_ctx* c, int32_t ngates, const int32_t* gate_v, const int64_t* gate_off,
+                                      const double* gate_data, const tnqs_apply_opts* aopts, const int32_t* edge_seq,
+                                      int32_t nseq, const tnqs_bp_opts* bopts, int32_t update_cache, double* truncerr,
+                                      int32_t* refreshes) {
+  API_BEGIN(c)
+  REQUIRE(ngates >= 0 && aopts && bopts && (ngates == 0 || (gate_v && gate_off && gate_data)), TNQS_ERR_INVALID_ARG,
+          "tnqs_apply_circuit: null argument");
+  const cplx* gd = (const cplx*)gate_data;
+  std::vector<char> affected(c->nv, 0), inbatch(c->nv, 0);
+  std::vector<int> batch;          // gate indices of the pending batch (all 1-site or all 2-site, vertex-disjoint)
+  int batch_arity = 0, nrefresh = 0;
+  auto flush = [&]() {
+    if (batch.empty()) return;
+    if (batch_arity == 1) {
+      std::vector<int> vs; std::vector<cplx> g;
+      for (int i : batch) { int v = gate_v[2 * i], d = c->d[v]; vs.push_back(v); g.insert(g.end(), gd + gate_off[i], gd + gate_off[i] + d * d); }
+      apply_1site_impl(c, (int)vs.size(), vs.data(), (const double*)g.data(), aopts->normalize_tensors);
+    } else {
+      std::vector<int> es, fl; std::vector<cplx> g; std::vector<double> err(batch.size());
+      for (int i : batch) {
+        int v1 = gate_v[2 * i], v2 = gate_v[2 * i + 1], e = -1;
+        for (int ee : c->inc[v1]) if (c->other(ee, v1) == v2) e = ee;
+        REQUIRE(e >= 0, TNQS_ERR_INVALID_ARG, "two-site gate on vertices that do not share an edge");
+        int d = c->d[v1];
+        es.push_back(e); fl.push_back(c->esrc[e] == v1 ? 0 : 1);
+        g.insert(g.end(), gd + gate_off[i], gd + gate_off[i] + d * d * d * d);
+      }
+      apply_2site_impl(c, (int)es.size(), es.data(), fl.data(), (const double*)g.data(), *aopts, nullptr, err.data(), nullptr);
+      if (truncerr) for (size_t j = 0; j < batch.size(); ++j) truncerr[batch[j]] = err[j];
+    }
+    c->release_temps();
+    for (int i : batch) { inbatch[gate_v[2 * i]] = 0; if (gate_v[2 * i + 1] >= 0) inbatch[gate_v[2 * i + 1]] = 0; }
+    batch.clear();
+  };
+  auto refresh = [&]() {
+    int it; double md;
+    bp_update_impl(c, edge_seq, nseq, *bopts, &it, &md);
+    c->release_temps();
+    ++nrefresh;
+  };
+  for (int i = 0; i < ngates; ++i) {
+    int v1 = gate_v[2 * i], v2 = gate_v[2 * i + 1];
+    REQUIRE(v1 >= 0 && v1 < c->nv && v2 < c->nv && v1 != v2, TNQS_ERR_INVALID_ARG, "gate vertex out of range");
+    int arity = v2 >= 0 ? 2 : 1;
+    if (truncerr) truncerr[i] = 0.0;
+    bool need = update_cache && arity == 2 && (affected[v1] || affected[v2]);        // apply_gates.jl:64
+    if (need) { flush(); refresh(); std::fill(affected.begin(), affected.end(), 0); }
+    bool conflict = !batch.empty() && (arity != batch_arity || inbatch[v1] || (v2 >= 0 && inbatch[v2]));
+    if (conflict) flush();
+    batch_arity = arity; batch.push_back(i);
+    inbatch[v1] = 1; affected[v1] = 1;                                                // apply_gates.jl:84
+    if (v2 >= 0) { inbatch[v2] = 1; affected[v2] = 1; }
+  }
+  flush();
+  if (update_cache) refresh();
+  if (refreshes) *refreshes = nrefresh;
+  c->sync();
+  API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// measurements
+// ---------------------------------------------------------------------------------------------------------------
+static Chain full_env_chain(tnqs_ctx* c, int v, int skip_vertex) {
+  Chain ch; ch.v = v;
+  for (size_t j = 0; j < c->inc[v].size(); ++j) {
+    int e = c->inc[v][j], u = c->other(e, v);
+    if (u == skip_vertex) continue;
+    Absorb ab; ab.leg = (int)j; ab.mat = c->msg(c->dedge(u, e)); ab.ldm = c->chi[e]; ab.flags = 0;
+    ch.absorb.push_back(ab);
+  }
+  return ch;
+}
+
+static void rdm_impl(tnqs_ctx* c, int n, const int32_t* vs, cplx* d_out /* n * dmax^2 */) {
+  std::vector<std::vector<Chain>> levels(1);
+  const int dd = c->dmax * c->dmax;
+  cplx* tmp = c->talloc<cplx>((size_t)n * dd);
+  for (int i = 0; i < n; ++i) {
+    REQUIRE(vs[i] >= 0 && vs[i] < c->nv, TNQS_ERR_INVALID_ARG, "vertex out of range");
+    Chain ch = full_env_chain(c, vs[i], -1);
+    ch.close_leg = -1; ch.dst = tmp + (size_t)i * dd;
+    levels[0].push_back(ch);
+  }
+  Plan p = build_plan(c, levels, scratch_budget(c));
+  run_plan(c, p);
+  CU(cudaMemcpyAsync(d_out, tmp, (size_t)n * dd * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream));
+}
+
+extern "C" int32_t tnqs_rdm_1site(tnqs_ctx* c, int32_t n, const int32_t* v, double* rho) {
+  API_BEGIN(c)
+  REQUIRE(n >= 0 && (n == 0 || (v && rho)), TNQS_ERR_INVALID_ARG, "tnqs_rdm_1site: null argument");
+  if (n > 0) {
+    const int dd = c->dmax * c->dmax;
+    cplx* d_out = c->talloc<cplx>((size_t)n * dd);
+    CU(cudaMemsetAsync(d_out, 0, (size_t)n * dd * sizeof(cplx), c->stream));
+    rdm_impl(c, n, v, d_out);
+    // compact d x d blocks were written with ld = d; expand to the caller's dmax x dmax layout on the host
+    std::vector<cplx> h((size_t)n * dd);
+    CU(cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    cplx* out = (cplx*)rho;
+    for (int i = 0; i < n; ++i) {
+      int d = c->d[v[i]];
+      for (int b = 0; b < c->dmax; ++b) for (int a = 0; a < c->dmax; ++a)
+        out[(size_t)i * dd + a + b * c->dmax] = (a < d && b < d) ? h[(size_t)i * dd + a + b * d] : cmake(0, 0);
+    }
+  }
+  c->release_temps();
+  API_END(c)
+}
+
+extern "C" int32_t tnqs_expect_2site_nn(tnqs_ctx* c, int32_t n, const int32_t* es, const double* ops, double* out) {
+  API_BEGIN(c)
+  REQUIRE(n >= 0 && (n == 0 || (es && ops && out)), TNQS_ERR_INVALID_ARG, "tnqs_expect_2site_nn: null argument");
+  if (n > 0) {
+    // level 0: environments of the first vertex with and without O1, closed on the shared bond
+    // level 1: second vertex with / without O2, absorbing that environment, closed on the site index
+    std::vector<std::vector<Chain>> levels(2);
+    size_t opoff = 0; std::vector<cplx> hops;
+    std::vector<size_t> o1(n), o2(n);
+    for (int i = 0; i < n; ++i) {
+      REQUIRE(es[i] >= 0 && es[i] < c->ne, TNQS_ERR_INVALID_ARG, "edge out of range");
+      int a = c->esrc[es[i]], b = c->edst[es[i]], da = c->d[a], db = c->d[b];
+      const cplx* src = (const cplx*)ops + opoff;
+      o1[i] = hops.size(); hops.insert(hops.end(), src, src + da * da);
+      o2[i] = hops.size(); hops.insert(hops.end(), src + da * da, src + da * da + db * db);
+      opoff += da * da + db * db;
+    }
+    cplx* d_ops = c->upload(hops);
+    const int dd = c->dmax * c->dmax;
+    cplx* envs = c->talloc<cplx>((size_t)2 * n * c->slot);
+    cplx* res = c->talloc<cplx>((size_t)2 * n * dd);
+    for (int i = 0; i < n; ++i) {
+      int e = es[i], a = c->esrc[e], b = c->edst[e];
+      for (int w = 0; w < 2; ++w) {                       // w = 0: numerator (with operators), 1: denominator
+        Chain ca = full_env_chain(c, a, b);
+        ca.op = w == 0 ? d_ops + o1[i] : nullptr; ca.close_leg = c->leg(a, e); ca.dst = envs + (size_t)(2 * i + w) * c->slot;
+        levels[0].push_back(ca);
+        Chain cb = full_env_chain(c, b, a);
+        cb.op = w == 0 ? d_ops + o2[i] : nullptr;
+        Absorb ab; ab.leg = c->leg(b, e); ab.mat = ca.dst; ab.ldm = c->chi[e]; ab.flags = 0;
+        cb.absorb.push_back(ab);
+        cb.close_leg = -1; cb.dst = res + (size_t)(2 * i + w) * dd;
+        levels[1].push_back(cb);
+      }
+    }
+    Plan p = build_plan(c, levels, scratch_budget(c));
+    run_plan(c, p);
+    std::vector<cplx> h((size_t)2 * n * dd);
+    CU(cudaMemcpyAsync(h.data(), res, h.size() * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    for (int i = 0; i < n; ++i)
+      for (int w = 0; w < 2; ++w) {
+        int d = c->d[c->edst[es[i]]];
+        double re = 0, im = 0;
+        for (int s = 0; s < d; ++s) { cplx x = h[(size_t)(2 * i + w) * dd + s + s * d]; re += x.x; im += x.y; }
+        out[4 * i + 2 * w] = re; out[4 * i + 2 * w + 1] = im;
+      }
+  }
+  c->release_temps();
+  API_END(c)
+}
+
+static void vertex_scalars_impl(tnqs_ctx* c, cplx* d_vs /* [nv] device */) {
+  std::vector<int> vs(c->nv);
+  for (int v = 0; v < c->nv; ++v) vs[v] = v;
+  const int dd = c->dmax * c->dmax;
+  cplx* rho = c->talloc<cplx>((size_t)c->nv * dd);
+  rdm_impl(c, c->nv, vs.data(), rho);
+  std::vector<cplx> h((size_t)c->nv * dd), t(c->nv);
+  CU(cudaMemcpyAsync(h.data(), rho, h.size() * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  for (int v = 0; v < c->nv; ++v) {
+    int d = c->d[v]; double re = 0, im = 0;
+    for (int s = 0; s < d; ++s) { re += h[(size_t)v * dd + s + s * d].x; im += h[(size_t)v * dd + s + s * d].y; }
+    t[v] = cmake(re, im);
+  }
+  CU(cudaMemcpyAsync(d_vs, t.data(), c->nv * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+}
+
+extern "C" int32_t tnqs_vertex_scalars(tnqs_ctx* c, double* out) {
+  API_BEGIN(c)
+  REQUIRE(out, TNQS_ERR_INVALID_ARG, "null output");
+  cplx* d_vs = c->talloc<cplx>(c->nv);
+  vertex_scalars_impl(c, d_vs);
+  CU(cudaMemcpyAsync(out, d_vs, c->nv * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  c->release_temps();
+  API_END(c)
+}
+
+extern "C" int32_t tnqs_edge_scalars(tnqs_ctx* c, double* out) {
+  API_BEGIN(c)
+  REQUIRE(out || c->ne == 0, TNQS_ERR_INVALID_ARG, "null output");
+  if (c->ne) {
+    cplx* d_es = c->talloc<cplx>(c->ne);
+    LAUNCH(c, TNQS_KC_MISC, k_edge_scalar, c->ne, 256, 0, c->msg_cur, c->slot, c->d_chi, d_es);
+    CU(cudaMemcpyAsync(out, d_es, c->ne * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+  }
+  c->release_temps();
+  API_END(c)
+}
+
+extern "C" int32_t tnqs_rescale(tnqs_ctx* c) {
+  API_BEGIN(c)
+  if (c->ne) LAUNCH(c, TNQS_KC_MISC, k_rescale_messages, c->ne, 256, 0, c->msg_cur, c->slot, c->d_chi);
+  cplx* d_vs = c->talloc<cplx>(c->nv);
+  vertex_scalars_impl(c, d_vs);
+  std::vector<ScaleDesc> sd(c->nv);
+  long long maxn = 1;
+  for (int v = 0; v < c->nv; ++v) { sd[v].x = c->site[v]; sd[v].n = c->site_n[v]; sd[v].scalar = (const double*)(d_vs + v); sd[v].mode = 1; maxn = std::max(maxn, c->site_n[v]); }
+  ScaleDesc* dsd = c->upload(sd);
+  LAUNCH(c, TNQS_KC_MISC, k_scale, dim3((unsigned)std::min<long long>((maxn + 255) / 256, 1024), c->nv), 256, 0, dsd);
+  c->sync();
+  c->release_temps();
+  API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// symmetric gauge, truncation
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int32_t tnqs_symmetric_gauge(tnqs_ctx* c, double regularization) {
+  API_BEGIN(c)
+  const int ne = c->ne;
+  if (ne > 0) {
+    // per edge: roots of both messages, C = rootX^T rootY, SVD, leg matrices N_a = invX^T (U sqrtS), N_c = invY^T (conj(V) sqrtS)
+    std::vector<EighDesc> eg(2 * ne); std::vector<SmallMatmulDesc> mm(ne), mm2(2 * ne); std::vector<SvdDesc> sv(ne);
+    std::vector<cplx*> Nmat(2 * ne);
+    int* d_rank = c->talloc<int>(ne); double* d_err = c->talloc<double>(ne); double* d_sv = c->talloc<double>((size_t)ne * c->chi_cap);
+    int maxchi = 1; size_t wvmax = 0;
+    for (int e = 0; e < ne; ++e) {
+      int x = c->chi[e]; maxchi = std::max(maxchi, x);
+      for (int s = 0; s < 2; ++s) {
+        EighDesc& d = eg[2 * e + s];
+        d.m = c->msg(2 * e + s); d.n = x; d.ldm = x; d.root = c->talloc<cplx>((size_t)x * x); d.invroot = c->talloc<cplx>((size_t)x * x);
+        d.cutoff = 0; d.shift = regularization; d.mode = 1;
+      }
+      SmallMatmulDesc& m = mm[e];
+      m.a = eg[2 * e].root; m.b = eg[2 * e + 1].root; m.c = c->talloc<cplx>((size_t)x * x); m.m = x; m.k = x; m.n = x; m.lda = x; m.ldb = x; m.ldc = x; m.transA = 1;
+      SvdDesc& s = sv[e];
+      s.theta = m.c; s.m = x; s.n = x; s.work = nullptr; s.r1out = c->talloc<cplx>((size_t)x * x); s.r2out = c->talloc<cplx>((size_t)x * x);
+      s.svals = d_sv + (size_t)e * c->chi_cap; s.rank = d_rank + e; s.truncerr = d_err + e; s.msg_a = nullptr; s.msg_b = nullptr;
+      s.maxdim = 0; s.cutoff = 0; s.has_cutoff = 0; s.normalize = 0; s.cap = c->chi_cap; s.mindim = 1;
+      wvmax = std::max(wvmax, (size_t)2 * x * x * sizeof(cplx));
+      for (int side = 0; side < 2; ++side) {
+        SmallMatmulDesc& t = mm2[2 * e + side];
+        Nmat[2 * e + side] = c->talloc<cplx>((size_t)x * x);
+        t.a = eg[2 * e + side].invroot; t.b = side == 0 ? s.r1out : s.r2out; t.c = Nmat[2 * e + side];
+        t.m = x; t.k = x; t.n = x; t.lda = x; t.ldb = x; t.ldc = x; t.transA = 1;
+      }
+    }
+    EighDesc* deg = c->upload(eg);
+    int threads = 32 * std::max(1, std::min(32, (maxchi + 1) / 2));
+    LAUNCH(c, TNQS_KC_EIGH, k_eigh_sqrt, 2 * ne, threads, (size_t)2 * maxchi * maxchi * sizeof(cplx) + 3 * maxchi * sizeof(double), deg, c->d_status);
+    SmallMatmulDesc* dmm = c->upload(mm);
+    LAUNCH(c, TNQS_KC_MISC, k_small_matmul, ne, 256, 0, dmm);
+    SvdDesc* dsv = c->upload(sv);
+    LAUNCH(c, TNQS_KC_SVD, k_svd_trunc, ne, threads, wvmax + (size_t)maxchi * 12 + 64, dsv, c->d_status, wvmax);
+    SmallMatmulDesc* dmm2 = c->upload(mm2);
+    LAUNCH(c, TNQS_KC_MISC, k_small_matmul, 2 * ne, 256, 0, dmm2);
+    int st = c->read_status();
+    if (st & ST_NEG_EIG) throw TnqsError(TNQS_ERR_NEGATIVE_EIGENVALUE, "negative message eigenvalue in symmetric_gauge");
+    if (st & ST_NO_CONV) throw TnqsError(TNQS_ERR_SVD_NO_CONVERGENCE, "Jacobi iteration did not converge");
+    // apply the leg matrices: one leg per step, all vertices that have such a leg
+    size_t maxdeg = 0;
+    for (int v = 0; v < c->nv; ++v) maxdeg = std::max(maxdeg, c->inc[v].size());
+    std::vector<cplx*> other(c->nv);
+    for (int v = 0; v < c->nv; ++v) other[v] = (cplx*)c->dalloc(c->site_n[v] * sizeof(cplx));
+    for (size_t j = 0; j < maxdeg; ++j) {
+      std::vector<ModeApplyDesc> ma; long long maxtiles = 1;
+      std::vector<int> touched;
+      for (int v = 0; v < c->nv; ++v) {
+        if (j >= c->inc[v].size()) continue;
+        int e = c->inc[v][j], x = c->chi[e];
+        long long Lp = c->d[v];
+        for (size_t i = 0; i < j; ++i) Lp *= c->chi[c->inc[v][i]];
+        long long R = c->site_n[v] / (Lp * x);
+        ModeApplyDesc d; d.in = c->site[v]; d.out = other[v]; d.m = Nmat[2 * e + (c->esrc[e] == v ? 0 : 1)];
+        d.L = (int)Lp; d.n = x; d.np = x; d.R = (int)R; d.in_sb = Lp; d.in_sr = Lp * x; d.out_sb = Lp; d.out_sr = Lp * x; d.ldm = x; d.flags = 0;
+        ma.push_back(d); touched.push_back(v);
+        maxtiles = std::max(maxtiles, (Lp * R + MA_BM - 1) / MA_BM);
+      }
+      ModeApplyDesc* dma = c->upload(ma);
+      LAUNCH(c, TNQS_KC_MODE_APPLY, k_mode_apply, dim3((unsigned)maxtiles, (unsigned)ma.size(), 1), 256, 0, dma);
+      for (int v : touched) std::swap(c->site[v], other[v]);
+    }
+    for (int v = 0; v < c->nv; ++v) c->dfree(other[v]);
+    std::vector<int> ks(ne);
+    for (int e = 0; e < ne; ++e) ks[e] = e;
+    int* dks = c->upload(ks);
+    LAUNCH(c, TNQS_KC_MISC, k_msg_diag, ne, 128, 0, c->msg_cur, c->slot, dks, d_sv, d_rank, c->chi_cap);
+    c->sync();
+  }
+  c->release_temps();
+  API_END(c)
+}
+
+extern "C" int32_t tnqs_truncate(tnqs_ctx* c, int32_t ngroups, const int32_t* group_off, const int32_t* group_edges,
+                                 const tnqs_apply_opts* aopts, const int32_t* edge_seq, int32_t nseq,
+                                 const tnqs_bp_opts* bopts) {
+  API_BEGIN(c)
+  REQUIRE(ngroups >= 0 && aopts && bopts && (ngroups == 0 || (group_off && group_edges)), TNQS_ERR_INVALID_ARG,
+          "tnqs_truncate: null argument");
+  for (int g = 0; g < ngroups; ++g) {
+    std::vector<int> es; std::vector<cplx> gates;
+    for (int i = group_off[g]; i < group_off[g + 1]; ++i) {
+      int e = group_edges[i];
+      REQUIRE(e >= 0 && e < c->ne, TNQS_ERR_INVALID_ARG, "edge out of range");
+      if (c->chi[e] == 1) continue;                                   // truncatable_edge (src/truncate.jl:5-10)
+      int d = c->d[c->esrc[e]];
+      es.push_back(e);
+      for (int j = 0; j < d * d * d * d; ++j) {                      // identity o[s1',s2',s1,s2]
+        int s1p = j % d, s2p = (j / d) % d, s1 = (j / (d * d)) % d, s2 = j / (d * d * d);
+        gates.push_back(cmake((s1p == s1 && s2p == s2) ? 1.0 : 0.0, 0.0));
+      }
+    }
+    if (!es.empty()) { apply_2site_impl(c, (int)es.size(), es.data(), nullptr, (const double*)gates.data(), *aopts, nullptr, nullptr, nullptr); c->release_temps(); }
+    int it; double md;
+    bp_update_impl(c, edge_seq, nseq, *bopts, &it, &md);
+    c->release_temps();
+  }
+  c->sync();
+  API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// multi-GPU halo and instrumentation
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int32_t tnqs_message_slab(tnqs_ctx* c, void** dev_ptr, int64_t* n_complex, int64_t* slot_stride) {
+  if (!c) return TNQS_ERR_INVALID_ARG;
+  if (dev_ptr) *dev_ptr = c->msg_cur;
+  if (n_complex) *n_complex = (int64_t)std::max(1, 2 * c->ne) * c->slot;
+  if (slot_stride) *slot_stride = c->slot;
+  return TNQS_OK;
+}
+static int32_t halo(tnqs_ctx* c, int32_t n, const int32_t* k, void* buf, int pack) {
+  API_BEGIN(c)
+  REQUIRE(n >= 0 && (n == 0 || (k && buf)), TNQS_ERR_INVALID_ARG, "halo: null argument");
+  if (n > 0) {
+    std::vector<int> ks(k, k + n);
+    for (int x : ks) REQUIRE(x >= 0 && x < 2 * c->ne, TNQS_ERR_INVALID_ARG, "halo: directed edge out of range");
+    int* dks = c->upload(ks);
+    LAUNCH(c, TNQS_KC_MISC, k_halo_pack, n, 256, 0, c->msg_cur, c->slot, dks, (cplx*)buf, pack);
+    c->sync();
+  }
+  c->release_temps();
+  API_END(c)
+}
+extern "C" int32_t tnqs_halo_pack(tnqs_ctx* c, int32_t n, const int32_t* k, void* dev_buf) { return halo(c, n, k, dev_buf, 1); }
+extern "C" int32_t tnqs_halo_unpack(tnqs_ctx* c, int32_t n, const int32_t* k, const void* dev_buf) { return halo(c, n, k, const_cast<void*>(dev_buf), 0); }
+extern "C" int32_t tnqs_set_partition(tnqs_ctx* c, const int32_t* owner, int32_t rank) {
+  if (!c) return TNQS_ERR_INVALID_ARG;
+  if (!owner) { c->partitioned = false; c->owner.clear(); return TNQS_OK; }
+  c->owner.assign(owner, owner + c->nv); c->rank = rank; c->partitioned = true;
+  return TNQS_OK;
+}
+extern "C" int64_t tnqs_kernel_launches(const tnqs_ctx* c) { return c ? c->launches : 0; }
+extern "C" int32_t tnqs_profile_enable(tnqs_ctx* c, int32_t on) {
+  if (!c) return TNQS_ERR_INVALID_ARG;
+  c->collect_profile(); c->profiling = on != 0; return TNQS_OK;
+}
+extern "C" int32_t tnqs_profile_read(tnqs_ctx* c, double* ms, int64_t* launches, int32_t reset) {
+  if (!c) return TNQS_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  c->collect_profile();
+  for (int i = 0; i < TNQS_KC_COUNT; ++i) { if (ms) ms[i] = c->prof_ms[i]; if (launches) launches[i] = c->prof_launches[i]; }
+  if (reset) for (int i = 0; i < TNQS_KC_COUNT; ++i) { c->prof_ms[i] = 0; c->prof_launches[i] = 0; }
+  return TNQS_OK;
+}
+extern "C" void* tnqs_stream(tnqs_ctx* c) { return c ? (void*)c->stream : nullptr; }

@@ -1,0 +1,489 @@
+"""Host-side mirror of the reference interface for the hot path, over libtnqs_cuda.so.
+
+Same names, argument meaning and error behaviour as the Julia API it stands in for:
+`tensornetworkstate`, `random_tensornetworkstate` (src/TensorNetworks/tensornetworkstate.jl:82-144),
+`BeliefPropagationCache`, `update`, `message(s)`, `partitionfunction`, `rescale`
+(src/MessagePassing/*.jl), `apply_gates` / `apply_circuit` (src/Apply/apply_gates.jl:13-133),
+`expect(...; alg="bp")` (src/expect.jl:53-136), `truncate` (src/truncate.jl:12-38,74-79),
+`symmetric_gauge`, `gauge_and_scale`, `entanglement` (src/symmetric_gauge.jl).
+
+Non-mutating functions copy on entry and return new objects like the reference (`copy(bpc)`,
+apply_gates.jl:51, abstractbeliefpropagationcache.jl:206); pass `inplace=True` to skip the device copy.
+All arithmetic runs in the CUDA library; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import gates as _gates
+from . import lib as _lib
+from .graphs import Graph, edge_color as _edge_color, forest_cover_edge_sequence
+from .lib import ApplyOpts, BpOpts, TnqsError, check, i32, ptr_f64, ptr_i32, ptr_i64
+
+DEFAULT_BP_MAXITER = 25      # src/MessagePassing/beliefpropagationcache.jl:108
+DEFAULT_TOLERANCE = 1.0e-8   # ComplexF64, src/MessagePassing/beliefpropagationcache.jl:109-112
+
+
+class _Handle:
+    """Owns one tnqs_ctx."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.load().tnqs_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def _create(g: Graph, d: Sequence[int], chi: Sequence[int], chi_cap: int, device: int) -> _Handle:
+    lib = _lib.load()
+    out = C.c_void_p()
+    esrc, edst, dd, cc = i32(g.esrc), i32(g.edst), i32(d), i32(chi if len(chi) else [1])
+    st = lib.tnqs_create(C.byref(out), g.nv, g.ne, ptr_i32(esrc), ptr_i32(edst), ptr_i32(dd), ptr_i32(cc), int(chi_cap), int(device))
+    if st != 0:
+        raise TnqsError(st, (lib.tnqs_last_error(None) or b"").decode())
+    return _Handle(out)
+
+
+class TensorNetworkState:
+    """Site tensors on the device (struct TensorNetworkState, src/TensorNetworks/tensornetworkstate.jl:4-7)."""
+
+    def __init__(self, g: Graph, handle: _Handle, chi_cap: int, device: int = 0):
+        self.g, self._h, self.chi_cap, self.device = g, handle, chi_cap, device
+        if not hasattr(g, "_default_seq"):
+            g._default_seq = None
+
+    # ---- construction helpers ----
+    @staticmethod
+    def from_arrays(g: Graph, tensors: Sequence[np.ndarray], chi_cap: Optional[int] = None, device: int = 0) -> "TensorNetworkState":
+        chi = np.ones(max(g.ne, 1), dtype=np.int32)
+        for v, t in enumerate(tensors):
+            if t.ndim != 1 + g.degree(v):
+                raise ValueError(f"tensor of vertex {v} has rank {t.ndim}, expected {1 + g.degree(v)}")
+            for i, e in enumerate(g.incident[v]):
+                chi[e] = t.shape[1 + i]
+        cap = int(chi_cap if chi_cap is not None else max(1, chi.max()))
+        h = _create(g, [t.shape[0] for t in tensors], chi[:g.ne], cap, device)
+        psi = TensorNetworkState(g, h, cap, device)
+        for v, t in enumerate(tensors):
+            psi.set_site(v, t)
+        return psi
+
+    def set_site(self, v: int, t: np.ndarray) -> None:
+        a = np.asfortranarray(t, dtype=np.complex128)
+        flat = a.ravel(order="F").view(np.float64)
+        check(self._h.ptr, _lib.load().tnqs_set_site(self._h.ptr, int(v), ptr_f64(flat), a.size))
+
+    def __getitem__(self, v) -> np.ndarray:
+        """Site tensor as ndarray [s, b_e1..b_ez] (getindex)."""
+        v = self.g.v(v) if not isinstance(v, (int, np.integer)) else int(v)
+        lib = _lib.load()
+        n = lib.tnqs_site_size(self._h.ptr, v)
+        buf = np.empty(2 * n, dtype=np.float64)
+        check(self._h.ptr, lib.tnqs_get_site(self._h.ptr, v, ptr_f64(buf), n))
+        chi = self.bond_dims()
+        shape = (n // int(np.prod([chi[e] for e in self.g.incident[v]], dtype=np.int64)),) + tuple(int(chi[e]) for e in self.g.incident[v])
+        return buf.view(np.complex128).reshape(shape, order="F")
+
+    def tensors(self) -> List[np.ndarray]:
+        return [self[v] for v in range(self.g.nv)]
+
+    def bond_dims(self) -> np.ndarray:
+        chi = np.ones(max(self.g.ne, 1), dtype=np.int32)
+        check(self._h.ptr, _lib.load().tnqs_get_bond_dims(self._h.ptr, ptr_i32(chi)))
+        return chi[:self.g.ne]
+
+    def maxvirtualdim(self) -> int:
+        return int(self.bond_dims().max()) if self.g.ne else 1
+
+    def copy(self) -> "TensorNetworkState":
+        out = C.c_void_p()
+        st = _lib.load().tnqs_clone(self._h.ptr, C.byref(out))
+        if st != 0:
+            raise TnqsError(st, (_lib.load().tnqs_last_error(None) or b"").decode())
+        return TensorNetworkState(self.g, _Handle(out), self.chi_cap, self.device)
+
+    def kernel_launches(self) -> int:
+        return int(_lib.load().tnqs_kernel_launches(self._h.ptr))
+
+
+def maxvirtualdim(x) -> int:
+    return network(x).maxvirtualdim()
+
+
+def tensornetworkstate(f, g: Graph, chi_cap: int = 1, device: int = 0) -> TensorNetworkState:
+    """Product state with all bonds of dimension 1 (src/TensorNetworks/tensornetworkstate.jl:124-144).
+    `chi_cap` = the largest bond dimension the state may grow to (message slot size on the device)."""
+    ts = []
+    for v in range(g.nv):
+        vec = _gates.state_vector(f(g.names[v]))
+        ts.append(vec.reshape((vec.shape[0],) + (1,) * g.degree(v)))
+    return TensorNetworkState.from_arrays(g, ts, chi_cap=chi_cap, device=device)
+
+
+def random_tensornetworkstate(g: Graph, bond_dimension: int = 1, seed: int = 0, d: int = 2,
+                              chi_cap: Optional[int] = None, device: int = 0) -> TensorNetworkState:
+    """N(0,1)+iN(0,1) entries generated on the device with the counter-based generator (rng.py has the same
+    formula); src/TensorNetworks/tensornetworkstate.jl:82-92."""
+    cap = int(chi_cap if chi_cap is not None else bond_dimension)
+    h = _create(g, [d] * g.nv, [bond_dimension] * g.ne, cap, device)
+    psi = TensorNetworkState(g, h, cap, device)
+    check(h.ptr, _lib.load().tnqs_fill_random(h.ptr, int(seed)))
+    return psi
+
+
+class BeliefPropagationCache:
+    """Network + one message per directed edge (src/MessagePassing/beliefpropagationcache.jl:9-13).
+    Shares the device handle of the TensorNetworkState it wraps (the reference shares the tensors too);
+    every non-mutating function clones the handle first."""
+
+    def __init__(self, psi: TensorNetworkState, _keep_messages: bool = False):
+        self.psi = psi
+        if not _keep_messages:
+            check(psi._h.ptr, _lib.load().tnqs_reset_messages(psi._h.ptr))
+
+    @property
+    def g(self) -> Graph:
+        return self.psi.g
+
+    def copy(self) -> "BeliefPropagationCache":
+        return BeliefPropagationCache(self.psi.copy(), _keep_messages=True)
+
+
+def network(x) -> TensorNetworkState:
+    return x.psi if isinstance(x, BeliefPropagationCache) else x
+
+
+def _vid(g: Graph, x) -> int:
+    return int(x) if isinstance(x, (int, np.integer)) else g.v(x)
+
+
+def message(bpc: BeliefPropagationCache, edge) -> np.ndarray:
+    """Message of the directed edge (src => dst names, or a directed edge id) as ndarray m[b, b']."""
+    g = bpc.g
+    k = int(edge) if isinstance(edge, (int, np.integer)) else g.dedge(_vid(g, edge[0]), _vid(g, edge[1]))
+    chi = int(bpc.psi.bond_dims()[k // 2])
+    buf = np.empty(2 * chi * chi, dtype=np.float64)
+    check(bpc.psi._h.ptr, _lib.load().tnqs_get_message(bpc.psi._h.ptr, k, ptr_f64(buf), chi * chi))
+    return buf.view(np.complex128).reshape((chi, chi), order="F")
+
+
+def setmessage(bpc: BeliefPropagationCache, k: int, m: np.ndarray) -> None:
+    a = np.asfortranarray(m, dtype=np.complex128).ravel(order="F").view(np.float64)
+    check(bpc.psi._h.ptr, _lib.load().tnqs_set_message(bpc.psi._h.ptr, int(k), ptr_f64(a), m.size))
+
+
+def messages(bpc: BeliefPropagationCache) -> List[np.ndarray]:
+    return [message(bpc, k) for k in range(2 * bpc.g.ne)]
+
+
+def default_edge_sequence(g: Graph) -> np.ndarray:
+    if getattr(g, "_default_seq", None) is None:
+        g._default_seq = forest_cover_edge_sequence(g)
+    return g._default_seq
+
+
+def default_bp_update_kwargs(x) -> dict:
+    """src/MessagePassing/beliefpropagationcache.jl:114-121."""
+    g = network(x).g
+    return dict(maxiter=1 if g.is_tree() else DEFAULT_BP_MAXITER, tolerance=DEFAULT_TOLERANCE)
+
+
+def _bp_opts(g: Graph, maxiter=None, tolerance=None, normalize=True, enforce_hermiticity=False, mode="reference") -> BpOpts:
+    if maxiter is None:
+        maxiter = 1 if g.is_tree() else DEFAULT_BP_MAXITER           # default_bp_maxiter, beliefpropagationcache.jl:31
+    m = {"reference": _lib.TNQS_BP_REFERENCE_ORDER, "jacobi": _lib.TNQS_BP_JACOBI}[mode]
+    return BpOpts(int(maxiter), -1.0 if tolerance is None else float(tolerance), int(normalize), int(enforce_hermiticity), m)
+
+
+def update(bpc: BeliefPropagationCache, maxiter: Optional[int] = None, tolerance: Optional[float] = None,
+           edge_sequence: Optional[Sequence[int]] = None, normalize: bool = True, enforce_hermiticity: bool = False,
+           mode: str = "reference", verbose: bool = False, inplace: bool = False, info: Optional[dict] = None) -> BeliefPropagationCache:
+    """BP sweeps until `maxiter` or mean(1 - fidelity) <= tolerance
+    (src/MessagePassing/abstractbeliefpropagationcache.jl:201-222; a bare update has tolerance=None)."""
+    out = bpc if inplace else bpc.copy()
+    g = out.g
+    seq = i32(default_edge_sequence(g) if edge_sequence is None else edge_sequence)
+    opts = _bp_opts(g, maxiter, tolerance, normalize, enforce_hermiticity, mode)
+    iters, mean = C.c_int32(0), C.c_double(float("nan"))
+    check(out.psi._h.ptr, _lib.load().tnqs_bp_update(out.psi._h.ptr, ptr_i32(seq), len(seq), C.byref(opts), C.byref(iters), C.byref(mean)))
+    if verbose and tolerance is not None and mean.value <= tolerance:
+        print(f"BP converged to desired precision after {iters.value} iterations.")
+    if info is not None:
+        info["iters"], info["mean_diff"] = iters.value, mean.value
+    return out
+
+
+def _apply_opts(apply_kwargs: Optional[dict]) -> ApplyOpts:
+    kw = dict(apply_kwargs or {})
+    maxdim = kw.pop("maxdim", None)
+    cutoff = kw.pop("cutoff", None)
+    normalize_tensors = kw.pop("normalize_tensors", True)
+    if kw:
+        raise TypeError(f"unknown apply_kwargs {sorted(kw)}")
+    return ApplyOpts(0 if maxdim is None else int(maxdim), float("nan") if cutoff is None else float(cutoff), int(normalize_tensors))
+
+
+def _pack_circuit(g: Graph, circuit: Sequence[tuple]):
+    gv = np.full(2 * len(circuit), -1, dtype=np.int32)
+    off = np.zeros(len(circuit), dtype=np.int64)
+    chunks, pos = [], 0
+    for i, gate in enumerate(circuit):
+        arr = gate[0] if isinstance(gate[0], np.ndarray) else _gates.gate_array(gate)
+        verts = gate[1] if isinstance(gate[1], list) else [gate[1]]
+        if len(verts) not in (1, 2):
+            raise ValueError("gates act on one or two vertices")
+        for j, x in enumerate(verts):
+            gv[2 * i + j] = _vid(g, x)
+        flat = np.asarray(arr, dtype=np.complex128).ravel(order="F")
+        off[i] = pos
+        pos += flat.size
+        chunks.append(flat)
+    data = np.concatenate(chunks) if chunks else np.zeros(1, dtype=np.complex128)
+    return gv, off, data.view(np.float64)
+
+
+def apply_gates(circuit: Sequence[tuple], psi, apply_kwargs: Optional[dict] = None, bp_update_kwargs: Optional[dict] = None,
+                update_cache: bool = True, verbose: bool = False, inplace: bool = False, info: Optional[dict] = None):
+    """Apply an ordered list of one/two-site gates by simple update with lazy BP refreshes
+    (src/Apply/apply_gates.jl:13-23 for a TensorNetworkState, :42-92 for a cache).  Returns
+    (state or cache, truncation errors)."""
+    if isinstance(psi, TensorNetworkState):
+        kw = bp_update_kwargs if bp_update_kwargs is not None else default_bp_update_kwargs(psi)
+        bpc = update(BeliefPropagationCache(psi if inplace else psi.copy()), inplace=True, **kw)
+        bpc, errs = apply_gates(circuit, bpc, apply_kwargs, kw, update_cache, verbose, True, info)
+        return bpc.psi, errs
+    out = psi if inplace else psi.copy()
+    g = out.g
+    kw = dict(bp_update_kwargs if bp_update_kwargs is not None else default_bp_update_kwargs(out))
+    kw.pop("verbose", None)
+    seq = i32(kw.pop("edge_sequence", None) if kw.get("edge_sequence") is not None else default_edge_sequence(g))
+    kw.pop("edge_sequence", None)
+    bopts = _bp_opts(g, **kw)
+    aopts = _apply_opts(apply_kwargs)
+    gv, off, data = _pack_circuit(g, circuit)
+    errs = np.zeros(max(len(circuit), 1), dtype=np.float64)
+    refreshes = C.c_int32(0)
+    check(out.psi._h.ptr, _lib.load().tnqs_apply_circuit(
+        out.psi._h.ptr, len(circuit), ptr_i32(gv), ptr_i64(off), ptr_f64(data), C.byref(aopts), ptr_i32(seq), len(seq),
+        C.byref(bopts), int(update_cache), ptr_f64(errs), C.byref(refreshes)))
+    if info is not None:
+        info["refreshes"] = refreshes.value
+    return out, errs[:len(circuit)]
+
+
+apply_circuit = apply_gates      # src/Apply/apply_gates.jl:133
+
+
+def apply_2site_batch(bpc: BeliefPropagationCache, edges: Sequence[int], gates: Sequence[np.ndarray], flip: Optional[Sequence[int]] = None,
+                      apply_kwargs: Optional[dict] = None):
+    """In place: one vertex-disjoint batch of two-site gates (apply_gate!, src/Apply/apply_gates.jl:95-122).
+    Returns (ranks, truncation errors, singular values [n, chi_cap])."""
+    n = len(edges)
+    es = i32(edges)
+    fl = i32(flip if flip is not None else [0] * n)
+    data = np.concatenate([np.asarray(a, dtype=np.complex128).ravel(order="F") for a in gates]).view(np.float64)
+    ranks = np.zeros(n, dtype=np.int32)
+    errs = np.zeros(n, dtype=np.float64)
+    sv = np.zeros((n, bpc.psi.chi_cap), dtype=np.float64)
+    aopts = _apply_opts(apply_kwargs)
+    check(bpc.psi._h.ptr, _lib.load().tnqs_apply_2site(bpc.psi._h.ptr, n, ptr_i32(es), ptr_i32(fl), ptr_f64(data), C.byref(aopts),
+                                                        ptr_i32(ranks), ptr_f64(errs), ptr_f64(sv.reshape(-1))))
+    return ranks, errs, sv
+
+
+def apply_1site_batch(x, vertices: Sequence[int], gates: Sequence[np.ndarray], normalize_tensors: bool = True) -> None:
+    psi = network(x)
+    vs = i32(vertices)
+    data = np.concatenate([np.asarray(a, dtype=np.complex128).ravel(order="F") for a in gates]).view(np.float64)
+    check(psi._h.ptr, _lib.load().tnqs_apply_1site(psi._h.ptr, len(vs), ptr_i32(vs), ptr_f64(data), int(normalize_tensors)))
+
+
+# ---- measurements -------------------------------------------------------------------------------------------
+def rdm_1site(bpc: BeliefPropagationCache, vertices: Sequence[int]) -> np.ndarray:
+    """Un-normalised BP one-site reduced density matrices rho[i][s, s'] (src/rdm.jl:49-70 for single vertices)."""
+    vs = i32(vertices)
+    lib = _lib.load()
+    # dmax is the largest site dimension of the network; the library pads every block to dmax x dmax
+    dmax = _site_dmax(bpc.psi)
+    out = np.zeros(len(vs) * dmax * dmax * 2, dtype=np.float64)
+    check(bpc.psi._h.ptr, lib.tnqs_rdm_1site(bpc.psi._h.ptr, len(vs), ptr_i32(vs), ptr_f64(out)))
+    return out.view(np.complex128).reshape((len(vs), dmax, dmax)).transpose(0, 2, 1).copy()   # [i, s, s'] (column-major blocks)
+
+
+def _site_dmax(psi: TensorNetworkState) -> int:
+    if not hasattr(psi, "_dmax"):
+        lib = _lib.load()
+        chi = psi.bond_dims()
+        dm = 1
+        for v in range(psi.g.nv):
+            n = lib.tnqs_site_size(psi._h.ptr, v)
+            dm = max(dm, n // int(np.prod([chi[e] for e in psi.g.incident[v]], dtype=np.int64)))
+        psi._dmax = int(dm)
+    return psi._dmax
+
+
+def _collect_observable(g: Graph, obs: tuple):
+    """src/expect.jl:160-176."""
+    op, verts = obs[0], obs[1]
+    coeff = obs[2] if len(obs) > 2 else 1
+    verts = verts if isinstance(verts, list) else [verts]
+    names = list(op) if isinstance(op, str) else list(op)
+    if len(names) != len(verts):
+        raise ValueError("Invalid observable: need as many operators as vertices passed.")
+    return names, [_vid(g, x) for x in verts], coeff
+
+
+def expect(x, obs, alg: str = "bp", cache_update_kwargs: Optional[dict] = None):
+    """<O> by belief propagation (src/expect.jl:53-83,115-136): one-site observables and two-site observables on
+    neighbouring vertices; a TensorNetworkState input builds and updates a fresh cache first."""
+    if alg != "bp":
+        raise ValueError("Only alg='bp' is on the CUDA path (Expected BeliefPropagationCache or TensorNetworkState for 'bp' algorithm)")
+    if isinstance(x, TensorNetworkState):
+        kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(x)
+        x = update(BeliefPropagationCache(x.copy()), inplace=True, **kw)
+    single = isinstance(obs, tuple)
+    obs_list = [obs] if single else list(obs)
+    g = x.g
+    parsed = [_collect_observable(g, o) for o in obs_list]
+    out: List[complex] = [0j] * len(parsed)
+    one = [(i, p) for i, p in enumerate(parsed) if len(p[1]) == 1 and p[2] != 0]
+    two = [(i, p) for i, p in enumerate(parsed) if len(p[1]) == 2 and p[2] != 0]
+    if any(len(p[1]) > 2 for p in parsed):
+        raise NotImplementedError("the CUDA path measures one-site and nearest-neighbour two-site observables")
+    if one:
+        rho = rdm_1site(x, [p[1][0] for _, p in one])
+        for (i, (names, vs, coeff)), r in zip(one, rho):
+            o = _gates.PAULI[names[0]]
+            d = o.shape[0]
+            r = r[:d, :d]
+            out[i] = coeff * np.sum(o.T * r) / np.trace(r)        # sum_{s,s'} O[s',s] rho[s,s']
+    if two:
+        es, ops = [], []
+        for _, (names, vs, coeff) in two:
+            if (vs[0], vs[1]) not in g.edge_of:
+                raise NotImplementedError("two-site observables must sit on an edge of the network")
+            e = g.edge_of[(vs[0], vs[1])]
+            o1, o2 = _gates.PAULI[names[0]], _gates.PAULI[names[1]]
+            if int(g.esrc[e]) != vs[0]:
+                o1, o2 = o2, o1
+            es.append(e)
+            ops += [o1.ravel(order="F"), o2.ravel(order="F")]
+        es_a = i32(es)
+        ops_a = np.concatenate(ops).astype(np.complex128).view(np.float64)
+        res = np.zeros(4 * len(es), dtype=np.float64)
+        check(x.psi._h.ptr, _lib.load().tnqs_expect_2site_nn(x.psi._h.ptr, len(es), ptr_i32(es_a), ptr_f64(ops_a), ptr_f64(res)))
+        for j, (i, (names, vs, coeff)) in enumerate(two):
+            out[i] = coeff * complex(res[4 * j], res[4 * j + 1]) / complex(res[4 * j + 2], res[4 * j + 3])
+    return out[0] if single else out
+
+
+def vertex_scalars(bpc: BeliefPropagationCache) -> np.ndarray:
+    out = np.zeros(2 * bpc.g.nv, dtype=np.float64)
+    check(bpc.psi._h.ptr, _lib.load().tnqs_vertex_scalars(bpc.psi._h.ptr, ptr_f64(out)))
+    return out.view(np.complex128)
+
+
+def edge_scalars(bpc: BeliefPropagationCache) -> np.ndarray:
+    out = np.zeros(2 * max(bpc.g.ne, 1), dtype=np.float64)
+    check(bpc.psi._h.ptr, _lib.load().tnqs_edge_scalars(bpc.psi._h.ptr, ptr_f64(out)))
+    return out.view(np.complex128)[:bpc.g.ne]
+
+
+def partitionfunction(bpc: BeliefPropagationCache) -> complex:
+    """exp(sum log vertex scalars - sum log edge scalars) (src/MessagePassing/abstractbeliefpropagationcache.jl:252-267)."""
+    num, den = vertex_scalars(bpc), edge_scalars(bpc)
+    if np.any(den == 0):
+        return 0.0
+    return complex(np.exp(np.sum(np.log(num)) - np.sum(np.log(den))))
+
+
+def norm_sqr(x, alg: str = "bp", cache_update_kwargs: Optional[dict] = None) -> complex:
+    """BP norm (src/norm_sqr.jl:56-76): partition function of the updated cache."""
+    if isinstance(x, TensorNetworkState):
+        kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(x)
+        x = update(BeliefPropagationCache(x.copy()), inplace=True, **kw)
+    return partitionfunction(x)
+
+
+def rescale(bpc: BeliefPropagationCache, inplace: bool = False) -> BeliefPropagationCache:
+    """src/MessagePassing/abstractbeliefpropagationcache.jl:281-291."""
+    out = bpc if inplace else bpc.copy()
+    check(out.psi._h.ptr, _lib.load().tnqs_rescale(out.psi._h.ptr))
+    return out
+
+
+def symmetric_gauge(x, regularization: float = 10 * np.finfo(np.float64).eps, cache_update_kwargs: Optional[dict] = None,
+                    inplace: bool = False):
+    """src/symmetric_gauge.jl:1-68.  A TensorNetworkState is updated with maxiter=40 first and a state is returned."""
+    if isinstance(x, TensorNetworkState):
+        kw = cache_update_kwargs if cache_update_kwargs is not None else dict(maxiter=40)
+        bpc = update(BeliefPropagationCache(x.copy()), inplace=True, **kw)
+        return symmetric_gauge(bpc, regularization, inplace=True).psi
+    out = x if inplace else x.copy()
+    check(out.psi._h.ptr, _lib.load().tnqs_symmetric_gauge(out.psi._h.ptr, float(regularization)))
+    return out
+
+
+def gauge_and_scale(psi: TensorNetworkState, cache_update_kwargs: Optional[dict] = None) -> TensorNetworkState:
+    """symmetrize_and_bpnormalize (src/symmetric_gauge.jl:76-83)."""
+    kw = cache_update_kwargs if cache_update_kwargs is not None else dict(maxiter=40)
+    bpc = update(BeliefPropagationCache(psi.copy()), inplace=True, **kw)
+    rescale(bpc, inplace=True)
+    return symmetric_gauge(bpc, inplace=True).psi
+
+
+def truncate(x, maxdim: int, cutoff: Optional[float] = None, normalize_tensors: bool = True, alg: str = "bp",
+             edge_groups: Optional[List[List[int]]] = None, bp_update_kwargs: Optional[dict] = None, inplace: bool = False):
+    """src/truncate.jl:12-38 (cache) and :74-79 (state: bare update first)."""
+    if alg != "bp":
+        raise ValueError("Only alg='bp' is on the CUDA path")
+    if isinstance(x, TensorNetworkState):
+        bpc = update(BeliefPropagationCache(x.copy()), inplace=True)
+        return truncate(bpc, maxdim, cutoff, normalize_tensors, alg, edge_groups, bp_update_kwargs, True).psi
+    out = x if inplace else x.copy()
+    g = out.g
+    groups = edge_groups if edge_groups is not None else _edge_color(g)
+    goff = np.zeros(len(groups) + 1, dtype=np.int32)
+    goff[1:] = np.cumsum([len(grp) for grp in groups])
+    gedges = i32([e for grp in groups for e in grp])
+    kw = dict(bp_update_kwargs if bp_update_kwargs is not None else default_bp_update_kwargs(out))
+    kw.pop("verbose", None)
+    seq = i32(default_edge_sequence(g))
+    bopts = _bp_opts(g, **kw)
+    aopts = _apply_opts(dict(maxdim=maxdim, cutoff=cutoff, normalize_tensors=normalize_tensors))
+    check(out.psi._h.ptr, _lib.load().tnqs_truncate(out.psi._h.ptr, len(groups), ptr_i32(goff), ptr_i32(gedges), C.byref(aopts),
+                                                     ptr_i32(seq), len(seq), C.byref(bopts)))
+    return out
+
+
+def entanglement(x, edge, alg: str = "bp") -> float:
+    """Von Neumann entropy across a bond from its two messages (src/symmetric_gauge.jl:85-114).  The two
+    chi x chi messages are read back and the scalar is formed on the host, like the reference's own scalar
+    post-processing."""
+    if isinstance(x, TensorNetworkState):
+        x = update(BeliefPropagationCache(x.copy()), inplace=True)
+    g = x.g
+    e = int(edge) if isinstance(edge, (int, np.integer)) else g.edge_of[(_vid(g, edge[0]), _vid(g, edge[1]))]
+    roots = []
+    for k in (2 * e, 2 * e + 1):
+        w, u = np.linalg.eigh(message(x, k))
+        if np.any(w < -10 * np.finfo(np.float64).eps):
+            raise TnqsError(-4, "negative message eigenvalue")
+        w = np.where(np.abs(w) < 10 * np.finfo(np.float64).eps, 0.0, w)
+        roots.append((u * np.sqrt(np.maximum(w, 0.0))) @ u.conj().T)
+    s = np.linalg.svd(roots[0] @ roots[1].T, compute_uv=False)
+    s = s / np.linalg.norm(s)
+    ee = 0.0
+    for d in s:
+        if abs(d) >= np.finfo(np.float64).eps:
+            ee -= d * d * math.log(d * d)
+    return abs(ee)

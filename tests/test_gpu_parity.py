@@ -1,0 +1,355 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via the ctypes host layer) against the CPU oracle on the
+same seeded inputs.  Tolerances are BASELINE.json's: ranks / schedules exact, singular values and BP messages
+1e-10 relative, expectation values 1e-8 absolute."""
+import math
+import numpy as np
+import pytest
+
+from oracle import tnqs_oracle as O
+from tensornetworkquantumsimulator_b200 import graphs as G, gates
+from util import ragged_state, to_engine, rel, two_site, ising_layer, statevector_fidelity
+
+pytestmark = pytest.mark.gpu
+
+MSG_TOL = 1e-10
+EXP_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def E():
+    from tensornetworkquantumsimulator_b200 import engine
+    return engine
+
+
+GRAPHS = {
+    "grid4x4": lambda: G.named_grid((4, 4)),
+    "grid3x3x2": lambda: G.named_grid((3, 3, 2)),
+    "hex2x2": lambda: G.named_hexagonal_lattice_graph(2, 2),
+    "comb3x3": lambda: G.named_comb_tree((3, 3)),
+    "heavyhex": lambda: G.heavy_hexagonal_lattice(1, 2),
+}
+
+
+def check_messages(E, bpc_e, bpc_o, tol=MSG_TOL):
+    for k in range(2 * bpc_o.g.ne):
+        assert rel(E.message(bpc_e, k), O.message(bpc_o, k)) < tol, f"message {k}"
+
+
+@pytest.mark.parametrize("name", list(GRAPHS))
+@pytest.mark.parametrize("chi", [1, 3, 4])
+def test_bp_sweeps_match_oracle(E, name, chi):
+    g = GRAPHS[name]()
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=chi, seed=11)
+    seq = G.forest_cover_edge_sequence(g)
+    for sweeps in (1, 3):
+        bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=sweeps, edge_sequence=seq)
+        be = E.update(to_engine(psi_o), maxiter=sweeps, edge_sequence=seq)
+        check_messages(E, be, bo)
+
+
+def test_bp_ragged_bonds_and_tolerance(E):
+    g = G.named_grid((4, 3))
+    rs = np.random.default_rng(5)
+    dims = rs.integers(1, 6, size=g.ne)
+    psi_o = ragged_state(g, dims, seed=3)
+    io, ie = {}, {}
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=25, tolerance=1e-8, info=io)
+    be = E.update(to_engine(psi_o), maxiter=25, tolerance=1e-8, info=ie)
+    assert ie["iters"] == io["iters"]
+    assert ie["mean_diff"] == pytest.approx(io["mean_diff"], rel=1e-6, abs=1e-14)
+    check_messages(E, be, bo)
+    # first-sweep diffs are measured against the identity default
+    io, ie = {}, {}
+    O.update(O.BeliefPropagationCache(psi_o), maxiter=1, tolerance=0.0, info=io)
+    E.update(to_engine(psi_o), maxiter=1, tolerance=0.0, info=ie)
+    assert ie["mean_diff"] == pytest.approx(io["mean_diff"], rel=1e-10)
+
+
+def test_bp_options_hermitize_and_unnormalised(E):
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=2)
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=2, enforce_hermiticity=True)
+    be = E.update(to_engine(psi_o), maxiter=2, enforce_hermiticity=True)
+    check_messages(E, be, bo)
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=1, normalize=False)
+    be = E.update(to_engine(psi_o), maxiter=1, normalize=False)
+    check_messages(E, be, bo)
+
+
+def test_bp_jacobi_mode(E):
+    g = G.named_grid((3, 4))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=8)
+    bo = O.BeliefPropagationCache(psi_o)
+    for _ in range(2):                      # Jacobi: every message from the previous sweep's values
+        new = {k: O.updated_message(bo, k) for k in range(2 * g.ne)}
+        bo.messages = new
+    be = E.update(to_engine(psi_o), maxiter=2, edge_sequence=np.arange(2 * g.ne), mode="jacobi")
+    check_messages(E, be, bo)
+    # same fixed point as the reference order
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=200, tolerance=1e-28)
+    be = E.update(to_engine(psi_o), maxiter=400, tolerance=1e-28, edge_sequence=np.arange(2 * g.ne), mode="jacobi")
+    v = g.v((2, 2))
+    assert abs(E.expect(be, ("Z", [(2, 2)])) - O.expect(bo, ("Z", [(2, 2)]))) < EXP_TOL
+    del v
+
+
+def test_bp_exact_on_tree_and_partition_function(E):
+    # /root/reference/test/test_beliefpropagation.jl:32-54
+    g = G.named_comb_tree((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=123)
+    be = E.update(to_engine(psi_o))
+    sv = O.to_statevector(psi_o)
+    assert E.partitionfunction(be) == pytest.approx(np.vdot(sv, sv).real, rel=1e-11)
+    for v in range(g.nv):
+        assert abs(E.expect(be, ("Z", [g.names[v]])) - O.statevector_expect(sv, g.nv, {v: gates.Z})) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["grid4x4", "hex2x2", "grid3x3x2"])
+def test_expectation_values(E, name):
+    g = GRAPHS[name]()
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=21)
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=10)
+    be = E.update(to_engine(psi_o), maxiter=10)
+    obs = [(p, [g.names[v]]) for v in range(g.nv) for p in "XYZ"]
+    got, want = E.expect(be, obs), [O.expect(bo, o) for o in obs]
+    assert np.max(np.abs(np.array(got) - np.array(want))) < EXP_TOL
+    obs2 = []
+    for e in range(0, g.ne, 2):
+        a, c = g.names[int(g.esrc[e])], g.names[int(g.edst[e])]
+        obs2 += [("ZZ", [a, c]), ("XY", [c, a], 0.5)]
+    got, want = E.expect(be, obs2), [O.expect(bo, o) for o in obs2]
+    assert np.max(np.abs(np.array(got) - np.array(want))) < EXP_TOL
+
+
+def test_scalars_and_rescale(E):
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=4)
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=5)
+    be = E.update(to_engine(psi_o), maxiter=5)
+    vs = np.array([O.vertex_scalar(bo, v) for v in range(g.nv)])
+    es = np.array([O.edge_scalar(bo, e) for e in range(g.ne)])
+    assert rel(E.vertex_scalars(be), vs) < MSG_TOL
+    assert rel(E.edge_scalars(be), es) < MSG_TOL
+    ro, re_ = O.rescale(bo), E.rescale(be)
+    check_messages(E, re_, ro)
+    for v in range(g.nv):
+        assert rel(re_.psi[v], ro.network.tensors[v]) < MSG_TOL
+    assert np.allclose(E.vertex_scalars(re_), 1.0, atol=1e-10)
+    assert np.allclose(E.edge_scalars(re_), 1.0, atol=1e-10)
+
+
+def test_one_site_gates(E):
+    g = G.named_grid((3, 2))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=6)
+    bo = O.BeliefPropagationCache(psi_o.copy())
+    be = to_engine(psi_o)
+    arrs = [gates.op_matrix("Rx", 0.3 + 0.1 * v) @ gates.op_matrix("H") for v in range(g.nv)]
+    for norm in (True, False):
+        for v in range(g.nv):
+            O.apply_gate(bo, arrs[v], [v], normalize_tensors=norm)
+        E.apply_1site_batch(be, list(range(g.nv)), arrs, normalize_tensors=norm)
+        for v in range(g.nv):
+            assert rel(be.psi[v], bo.network.tensors[v]) < 1e-13
+
+
+def gate_case(E, g, psi_o, edges, gate_arrs, kw, sweeps=6, flip=None):
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=sweeps)
+    be = E.update(to_engine(psi_o, chi_cap=16), maxiter=sweeps)
+    details = []
+    for i, e in enumerate(edges):
+        a, c = int(g.esrc[e]), int(g.edst[e])
+        vs = [c, a] if flip and flip[i] else [a, c]
+        det = {}
+        O.apply_gate(bo, gate_arrs[i], vs, detail=det, **kw)
+        details.append(det)
+    ranks, errs, sv = E.apply_2site_batch(be, edges, gate_arrs, flip=flip, apply_kwargs=kw)
+    for i, e in enumerate(edges):
+        det = details[i]
+        assert ranks[i] == det["rank"], f"rank of gate {i}"
+        assert rel(sv[i, :ranks[i]], det["svals"]) < MSG_TOL
+        assert errs[i] == pytest.approx(det["truncerr"], rel=1e-8, abs=1e-16)
+        for k in (2 * e, 2 * e + 1):
+            assert rel(E.message(be, k), O.message(bo, k)) < MSG_TOL
+    te = be.psi.tensors()
+    for e in edges:
+        assert rel(two_site(g, te, e), two_site(g, bo.network.tensors, e)) < 1e-9
+    assert list(be.psi.bond_dims()) == list(bo.network.bond_dims())
+    return be, bo
+
+
+@pytest.mark.parametrize("kw", [dict(maxdim=4, cutoff=1e-10, normalize_tensors=True),
+                                dict(maxdim=None, cutoff=None, normalize_tensors=False),
+                                dict(maxdim=2, cutoff=None, normalize_tensors=True)])
+def test_two_site_gate_batch(E, kw):
+    g = G.named_grid((4, 4))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=4, seed=31)
+    groups = G.grid_edge_color(g)
+    rs = np.random.default_rng(0)
+    for grp in groups[:2]:
+        arrs = []
+        for e in grp:
+            h = rs.normal(size=(4, 4)) + 1j * rs.normal(size=(4, 4))
+            u, _ = np.linalg.qr(h)
+            arrs.append(u.reshape(2, 2, 2, 2))
+        gate_case(E, g, psi_o, grp, arrs, kw, flip=[i % 2 for i in range(len(grp))])
+
+
+def test_two_site_gate_ragged_and_degree3(E):
+    g = G.named_hexagonal_lattice_graph(2, 2)
+    dims = np.random.default_rng(9).integers(1, 5, size=g.ne)
+    psi_o = ragged_state(g, dims, seed=12)
+    grp = G.edge_color(g)[0]
+    arrs = [gates.gate_array(("Rxx", [0, 1], 0.8)) for _ in grp]
+    gate_case(E, g, psi_o, grp, arrs, dict(maxdim=8, cutoff=1e-12, normalize_tensors=True))
+
+
+def test_two_site_gate_tall_qr_tree(E):
+    # degree-4 vertices with chi=6: P_o = 216 > rows of one QR block for nc = 12 -> exercises the TSQR tree
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=6, seed=77)
+    e = g.edge_of[(g.v((2, 2)), g.v((2, 3)))]
+    gate_case(E, g, psi_o, [e], [gates.gate_array(("CNOT", [0, 1]))], dict(maxdim=6, cutoff=1e-10, normalize_tensors=True), sweeps=4)
+
+
+def test_two_site_gate_3d_chi8_deep_tree(E):
+    g = G.named_grid((3, 3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=5)
+    c = g.v((2, 2, 2))
+    e = g.incident[c][0]
+    gate_case(E, g, psi_o, [e], [gates.gate_array(("Rzz", [0, 1], 1.1))], dict(maxdim=3, cutoff=None, normalize_tensors=True), sweeps=3)
+
+
+def test_circuit_known_answer_two_qubits(E):
+    # /root/reference/test/test_apply.jl:11-20
+    circuit = [("Rx", [(1, 1)], 0.5), ("Rx", [(2, 1)], 0.2), ("CPHASE", [(1, 1), (2, 1)], -0.3)]
+    g = G.build_graph_from_circuit(circuit)
+    psi0 = E.tensornetworkstate(lambda v: "↓", g, chi_cap=2)
+    psi, errs = E.apply_circuit(circuit, psi0, apply_kwargs=dict(maxdim=2, cutoff=1e-10, normalize_tensors=False))
+    assert isinstance(psi, E.TensorNetworkState)
+    assert psi.maxvirtualdim() <= 2
+    got = O.to_statevector(O.TensorNetworkState(g, psi.tensors()))
+    assert np.vdot(got, got).real == pytest.approx(1.0, abs=1e-12)
+    assert statevector_fidelity(got, O.statevector_circuit(g, lambda v: "↓", circuit)) == pytest.approx(1.0, abs=1e-12)
+
+
+def test_ising_layer_grid_matches_oracle(E):
+    # /root/reference/test/test_apply.jl:23-53 + refresh schedule
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=1, seed=123)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    layer = ising_layer(g, groups=G.grid_edge_color(g))
+    kw = dict(cutoff=1e-10, normalize_tensors=False)
+    io, ie = {}, {}
+    bo = O.update(O.BeliefPropagationCache(psi_o), **O.default_bp_update_kwargs(psi_o))
+    bo, errs_o = O.apply_gates(layer, bo, apply_kwargs=kw, info=io)
+    be = E.update(to_engine(psi_o, chi_cap=4), **E.default_bp_update_kwargs(to_engine(psi_o)))
+    be, errs_e = E.apply_gates(layer, be, apply_kwargs=kw, info=ie)
+    assert ie["refreshes"] == io["refreshes"] == 5
+    assert be.psi.maxvirtualdim() <= 2
+    assert list(be.psi.bond_dims()) == list(bo.network.bond_dims())
+    assert np.allclose(errs_e, errs_o, atol=1e-14)
+    sv = O.to_statevector(O.TensorNetworkState(g, be.psi.tensors()))
+    assert np.vdot(sv, sv).real == pytest.approx(1.0, abs=1e-10)
+    for v in range(g.nv):
+        assert abs(E.expect(be, ("Z", [g.names[v]])) - O.expect(bo, ("Z", [g.names[v]]))) < EXP_TOL
+
+
+def test_trotter_evolution_config_c1_small(E):
+    # BASELINE config C1 scaled down: 4x4 grid, 6 Trotter layers in ONE apply_gates call, maxdim=4, cutoff=1e-10
+    g = G.named_grid((4, 4))
+    layer = ising_layer(g, dt=0.01, hx=2.5, hz=0.2, J=1.0, groups=G.grid_edge_color(g))
+    circuit = layer * 6
+    kw = dict(maxdim=4, cutoff=1e-10, normalize_tensors=True)
+    psi_o, _ = O.apply_gates(circuit, O.tensornetworkstate(lambda v: "↑", g), apply_kwargs=kw)
+    psi_e, _ = E.apply_gates(circuit, E.tensornetworkstate(lambda v: "↑", g, chi_cap=4), apply_kwargs=kw)
+    assert list(psi_e.bond_dims()) == list(psi_o.bond_dims())
+    want = O.expect_tns(psi_o, ("Z", [(2, 2)]))
+    got = E.expect(psi_e, ("Z", [(2, 2)]), alg="bp")
+    assert abs(got - want) < EXP_TOL
+    zz_w = O.expect_tns(psi_o, ("ZZ", [(2, 2), (2, 3)]))
+    zz_g = E.expect(psi_e, ("ZZ", [(2, 2), (2, 3)]))
+    assert abs(zz_g - zz_w) < EXP_TOL
+
+
+def test_tree_circuit_matches_statevector(E):
+    g = G.named_comb_tree((3, 2))
+    rs = np.random.default_rng(0)
+    layer = []
+    for _ in range(3):
+        layer += [("Rx", [g.names[v]], float(rs.uniform(0, 2))) for v in range(g.nv)]
+        layer += [("Ry", [g.names[v]], float(rs.uniform(0, 2))) for v in range(g.nv)]
+        for grp in G.edge_color(g):
+            layer += [("Rzz", [g.names[int(g.esrc[e])], g.names[int(g.edst[e])]], 0.7) for e in grp]
+    psi, _ = E.apply_gates(layer, E.tensornetworkstate(lambda v: "↑", g, chi_cap=8), apply_kwargs=dict(cutoff=1e-14, normalize_tensors=True))
+    sv = O.statevector_circuit(g, lambda v: "↑", layer)
+    got = O.to_statevector(O.TensorNetworkState(g, psi.tensors()))
+    assert statevector_fidelity(got, sv) == pytest.approx(1.0, abs=1e-11)
+
+
+def test_symmetric_gauge(E):
+    g = G.named_grid((3, 2))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=7)
+    bo = O.rescale(O.update(O.BeliefPropagationCache(psi_o), maxiter=30))
+    be = E.rescale(E.update(to_engine(psi_o), maxiter=30))
+    so, se = O.symmetric_gauge(bo), E.symmetric_gauge(be)
+    check_messages(E, se, so, tol=1e-9)
+    a = O.to_statevector(psi_o)
+    b = O.to_statevector(O.TensorNetworkState(g, se.psi.tensors()))
+    assert statevector_fidelity(a, b) == pytest.approx(1.0, abs=1e-10)
+    te = se.psi.tensors()
+    for e in range(g.ne):
+        assert rel(two_site(g, te, e), two_site(g, so.network.tensors, e)) < 1e-8
+
+
+def test_ghz_entanglement_log2(E):
+    # /root/reference/test/test_constructors.jl:69-73
+    g = G.named_hexagonal_lattice_graph(3, 3)
+    ts = []
+    for v in range(g.nv):
+        z = g.degree(v)
+        t = np.zeros((2,) + (2,) * z, dtype=np.complex128)
+        t[(0,) * (z + 1)] = 1
+        t[(1,) * (z + 1)] = 1
+        ts.append(t)
+    psi = E.TensorNetworkState.from_arrays(g, ts)
+    assert E.entanglement(psi, 0) == pytest.approx(math.log(2), abs=1e-12)
+
+
+def test_truncate_bp(E):
+    # /root/reference/test/test_truncate.jl:16-33
+    g = G.named_hexagonal_lattice_graph(2, 2)
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=123)
+    groups = G.edge_color(g)
+    bo = O.update(O.BeliefPropagationCache(psi_o))
+    bo = O.truncate_bp(bo, maxdim=2, cutoff=1e-10, normalize_tensors=False, edge_groups=groups)
+    pe = E.truncate(E.TensorNetworkState.from_arrays(g, psi_o.tensors), maxdim=2, cutoff=1e-10, normalize_tensors=False, edge_groups=groups)
+    assert pe.maxvirtualdim() <= 2
+    a = O.to_statevector(bo.network)
+    b = O.to_statevector(O.TensorNetworkState(g, pe.tensors()))
+    assert statevector_fidelity(a, b) == pytest.approx(1.0, abs=1e-8)
+
+
+def test_error_codes(E):
+    from tensornetworkquantumsimulator_b200.lib import TnqsError
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=1)
+    be = to_engine(psi_o)
+    e1, e2 = g.incident[g.v((2, 2))][:2]
+    cn = gates.gate_array(("CNOT", [0, 1]))
+    with pytest.raises(TnqsError) as ei:
+        E.apply_2site_batch(be, [e1, e2], [cn, cn])
+    assert ei.value.status == -3                     # TNQS_ERR_OVERLAPPING_BATCH
+    with pytest.raises(TnqsError) as ei:
+        be.psi.set_site(0, np.zeros((2, 3, 3)))
+    assert ei.value.status == -2                     # TNQS_ERR_SHAPE
+    # a message with a negative eigenvalue beyond the cutoff: the reference throws, the engine returns an error
+    k = g.dedge(g.v((1, 2)), g.v((2, 2)))
+    E.setmessage(be, k, np.diag([1.0, -0.5]).astype(np.complex128))
+    e = g.edge_of[(g.v((2, 2)), g.v((2, 3)))]
+    with pytest.raises(TnqsError) as ei:
+        E.apply_2site_batch(be, [e], [cn])
+    assert ei.value.status == -4                     # TNQS_ERR_NEGATIVE_EIGENVALUE
+    with pytest.raises(O.NegativeEigenvalueError):
+        bo = O.BeliefPropagationCache(psi_o.copy(), {k: np.diag([1.0, -0.5]).astype(np.complex128)})
+        O.apply_gate(bo, cn, [g.v((2, 2)), g.v((2, 3))])
