@@ -26,7 +26,17 @@ __device__ int jacobi_columns(cplx* W, int ldw, int m, cplx* V, int ldv, int nv,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int N = n + (n & 1);
   if (n < 2) return 0;
+  // rotate whenever |<a_p,a_q>| > sqrt(m) eps |a_p||a_q| (LAPACK zgesvj's threshold), but call the iteration
+  // converged once a whole sweep saw nothing above 8x that: rotations at the rounding-noise level never end.
   const double tol2 = (double)m * TNQS_EPS * TNQS_EPS;
+  const double conv2 = 64.0 * tol2;
+  // Columns whose norm has fallen below eps * sqrt(m) * ||W||_F are pure rounding noise (the null space of a
+  // rank-deficient matrix, e.g. theta of a low-Schmidt-rank gate): rotating them never settles, so they are left alone.
+  __shared__ double jred[32];
+  double fro2 = 0;
+  for (int idx = threadIdx.x; idx < m * n; idx += blockDim.x) fro2 += cabs2(W[(idx % m) + (size_t)(idx / m) * ldw]);
+  fro2 = block_sum(fro2, jred);
+  const double tiny2 = tol2 * fro2;
   for (int sweep = 0; sweep < TNQS_JACOBI_MAX_SWEEPS; ++sweep) {
     int rotated = 0;
     for (int s = 0; s < N - 1; ++s) {
@@ -45,8 +55,8 @@ __device__ int jacobi_columns(cplx* W, int ldw, int m, cplx* V, int ldv, int nv,
         }
         al = warp_sum(al); be = warp_sum(be); gr = warp_sum(gr); gi = warp_sum(gi);
         double g2 = gr * gr + gi * gi;
-        if (!(g2 > tol2 * al * be) || g2 == 0.0) continue;
-        rotated = 1;
+        if (!(g2 > tol2 * al * be) || g2 == 0.0 || al <= tiny2 || be <= tiny2) continue;
+        if (g2 > conv2 * al * be) rotated = 1;
         double ag = sqrt(g2);
         cplx ph = cmake(gr / ag, -gi / ag);           // e^{-i phi}: makes <a_p, ph*a_q> real positive
         double zeta = (be - al) / (2.0 * ag);

@@ -367,6 +367,25 @@ __global__ void k_msg_diag(cplx* slab, long long slot, const int* list, const do
   }
 }
 
+
+// Debug aid (TNQS_DEBUG=1): Frobenius norm^2 and finiteness of a device buffer, printed to stderr.
+static void dbg_norm(tnqs_ctx* c, const char* name, int idx, const cplx* p, size_t n) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("TNQS_DEBUG"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (!on) return;
+  std::vector<cplx> h(n);
+  cudaMemcpyAsync(h.data(), p, n * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream);
+  cudaStreamSynchronize(c->stream);
+  double s = 0; int bad = 0;
+  for (size_t i = 0; i < n; ++i) { s += h[i].x * h[i].x + h[i].y * h[i].y; if (!std::isfinite(h[i].x) || !std::isfinite(h[i].y)) ++bad; }
+  fprintf(stderr, "[tnqs dbg] %-10s[%d] n=%zu norm2=%.15g nonfinite=%d\n", name, idx, n, s, bad);
+  const char* dir = getenv("TNQS_DEBUG_DIR");
+  if (dir) {
+    char path[512]; snprintf(path, sizeof(path), "%s/%s_%d.bin", dir, name, idx);
+    FILE* f = fopen(path, "wb"); if (f) { fwrite(h.data(), sizeof(cplx), n, f); fclose(f); }
+  }
+}
+
 // Plan of the TSQR tree of one matrix (Po x nc, column-major, ld = Po), see DESIGN.md "QR".
 struct QrLevel { cplx* base; long long ld; long long rows; std::vector<long long> blk_begin; };   // blocks = row ranges
 
@@ -438,6 +457,7 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
     unsigned gx = (unsigned)std::min<long long>((maxtot + 255) / 256, 2048);
     LAUNCH(c, TNQS_KC_PERMUTE, k_permute, dim3(gx, NJ), 256, 0, dpd);
   }
+  for (int j = 0; j < NJ; ++j) dbg_norm(c, "matricised", j, jobs[j].A, (size_t)c->site_n[jobs[j].v]);
   // ---- 3. absorb sqrt(M_k) on the outer legs, in place in the matrix layout (simple_update.jl:35-36) ----
   auto absorb_outer = [&](bool inverse, std::vector<int>& ncols) {
     size_t maxouter = 0;
@@ -465,6 +485,7 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
   std::vector<int> ncols(NJ);
   for (int j = 0; j < NJ; ++j) ncols[j] = jobs[j].nc;
   absorb_outer(false, ncols);
+  for (int j = 0; j < NJ; ++j) dbg_norm(c, "absorbed", j, jobs[j].A, (size_t)c->site_n[jobs[j].v]);
   // ---- 4. TSQR with explicit thin Q, in place (simple_update.jl:39-40) ----
   {
     std::vector<std::vector<QrLevel>> trees(NJ);
@@ -525,6 +546,7 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
       LAUNCH(c, TNQS_KC_QR, k_mode_apply, dim3((unsigned)maxtiles, (unsigned)ma.size(), 1), 256, 0, dma);
     }
   }
+  for (int j = 0; j < NJ; ++j) { dbg_norm(c, "Q", j, jobs[j].A, (size_t)jobs[j].Po * jobs[j].q); dbg_norm(c, "R", j, jobs[j].Rbuf, (size_t)jobs[j].q * jobs[j].nc); }
   // ---- 5. theta = R1 R2 over the bond, gate (simple_update.jl:43) ----
   std::vector<ThetaDesc> td(n); std::vector<SvdDesc> sv(n);
   int* d_rank = c->talloc<int>(n); double* d_err = c->talloc<double>(n); double* d_sv = c->talloc<double>((size_t)n * cap);
@@ -567,6 +589,7 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
     size_t smem = svd_smem_wv + (size_t)svd_maxn * 12 + 64;
     LAUNCH(c, TNQS_KC_SVD, k_svd_trunc, n, threads, smem, dsv, c->d_status, svd_smem_wv);
   }
+  for (int i = 0; i < n; ++i) dbg_norm(c, "theta", i, td[i].theta, (size_t)sv[i].m * sv[i].n);
   std::vector<int> ranks(n);
   CU(cudaMemcpyAsync(ranks.data(), d_rank, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   int st = c->read_status();

@@ -297,9 +297,12 @@ def test_symmetric_gauge(E):
     a = O.to_statevector(psi_o)
     b = O.to_statevector(O.TensorNetworkState(g, se.psi.tensors()))
     assert statevector_fidelity(a, b) == pytest.approx(1.0, abs=1e-10)
-    te = se.psi.tensors()
-    for e in range(g.ne):
-        assert rel(two_site(g, te, e), two_site(g, so.network.tensors, e)) < 1e-8
+    # the new diag(S) messages are a BP fixed point of the gauged state (up to BP convergence)
+    for k in range(2 * g.ne):
+        m = E.message(se, k)
+        new = O.updated_message(O.BeliefPropagationCache(O.TensorNetworkState(g, se.psi.tensors()),
+                                                         {j: E.message(se, j) for j in range(2 * g.ne)}), k)
+        assert rel(new, m / m.sum()) < 1e-6
 
 
 def test_ghz_entanglement_log2(E):
