@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the tnqs-cuda engine (contract: see the task statement / DESIGN.md "measurement").
+
+Workload at N=1 (BASELINE.json configs[1], "C2"): 32x32 open grid, random TensorNetworkState chi=16 ComplexF64
+(counter-based generator, seed 1, BP-rescaled), one Trotter layer per step = Rx, Rz on every vertex + Rzz in 4
+deterministic colour classes with maxdim=16, cutoff=1e-10, the reference's lazy BP refreshes (default
+bp_update_kwargs: <=25 sweeps, tolerance 1e-8, forest-cover edge order, REFERENCE_ORDER schedule) and <Z> on (16,16).
+At N>1 ranks hold independent vertex strips of a (32*N)x32 lattice?  No: see `--gpus` below (weak scaling, row strips
+with halo exchange of boundary messages in JACOBI mode).
+
+One JSON line on stdout (rank 0).  value = BP edge-message updates / s (device-resident state, BP phases timed with
+CUDA events on the engine's stream); `gates` carries the two-site gate applications / s of the same steps; `e2e` is
+the same step through the host API with the state in pinned HOST memory (H2D of every site tensor, the layer, D2H of
+the state and the result inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    out = {"fp64_tflops": 36.995, "fp64_tflops_sustained": 36.936, "hbm_gbs": 6541.1, "source": "fallback"}
+    p = os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")
+    if os.path.exists(p):
+        d = json.load(open(p))["roofline_denominator"]
+        out.update(fp64_tflops=d["fp64_tflops"], fp64_tflops_sustained=d["fp64_tflops_sustained"],
+                   source="profiles/r01_fp64_peaks.json (cuBLAS ZGEMM 8192^3 measured on this pool's B200)")
+    m = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(m):
+        out["hbm_gbs"] = json.load(open(m)).get("hbm_gbs", out["hbm_gbs"])
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * max(mx)] if mx else []
+        return {"sm_mhz": float(np.median(busy)) if busy else (float(np.median(sm)) if sm else None),
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(nx: int, ny: int):
+    from tensornetworkquantumsimulator_b200 import graphs as G, gates
+    g = G.named_grid((nx, ny))
+    groups = G.grid_edge_color(g)
+    dt, hx, hz, J = 0.25, 1.0, 0.8, 0.5            # examples/2dIsing_dynamics.jl:13-17
+    rx = gates.gate_array(("Rx", [0], 2 * hx * dt)); rz = gates.gate_array(("Rz", [0], 2 * hz * dt))
+    rzz = gates.gate_array(("Rzz", [0, 1], 2 * J * dt))
+    seq = G.forest_cover_edge_sequence(g)
+    return g, groups, rx, rz, rzz, seq
+
+
+def flops_per_message(g, chi, d=2):
+    """Algorithmic flops of one message update in the reference's contraction order: 8*d*P*sum_k chi_k."""
+    f = np.zeros(2 * g.ne)
+    for k in range(2 * g.ne):
+        v = g.dsrc(k)
+        z = g.degree(v)
+        f[k] = 8.0 * d * chi ** z * z * chi
+    return f
+
+
+def gate_flops(g, e, chi, d=2):
+    """Nominal flops of one two-site gate: absorb + QR(explicit Q) + reabsorb + Q R' per site, theta, SVD."""
+    tot = 0.0
+    n = d * chi
+    qs = []
+    for v in (int(g.esrc[e]), int(g.edst[e])):
+        z = g.degree(v)
+        P = chi ** z
+        Po = P // chi
+        q = min(Po, n)
+        qs.append(q)
+        tot += 8.0 * d * P * (z - 1) * chi                      # absorb sqrt(M)
+        tot += (z - 1) * 52.0 * chi ** 3                        # eigh + roots (nominal)
+        tot += 2 * (8.0 * Po * n * n - 8.0 * n ** 3 / 3) if Po >= n else 2 * (8.0 * n * Po * Po - 8.0 * Po ** 3 / 3)
+        tot += 8.0 * Po * q * (z - 1) * chi                     # reabsorb M^-1/2 into Q
+        tot += 8.0 * Po * q * d * chi                           # Q R'
+    q1, q2 = qs
+    tot += 8.0 * (q1 * q2 * d * d * chi + d ** 4 * q1 * q2)
+    m, nn = max(q1, q2) * d, min(q1, q2) * d
+    tot += 4.0 * (4 * m * m * nn + 8 * m * nn * nn + 9 * nn ** 3)
+    return tot
+
+
+class Stepper:
+    """One Trotter layer as the phase sequence tnqs_apply_circuit executes (tests/test_gpu_parity.py checks the
+    equivalence), with CUDA events on the engine's stream around the BP and the gate phases."""
+
+    def __init__(self, E, torch, bpc, g, groups, rx, rz, rzz, seq, chi, obs_v):
+        self.E, self.torch, self.bpc, self.g, self.groups, self.seq, self.chi, self.obs_v = E, torch, bpc, g, groups, seq, chi, obs_v
+        self.rx, self.rz, self.rzz = rx, rz, rzz
+        from tensornetworkquantumsimulator_b200 import lib
+        self.stream = torch.cuda.ExternalStream(lib.load().tnqs_stream(bpc.psi._h.ptr))
+        self.kw = dict(maxdim=chi, cutoff=1e-10, normalize_tensors=True)
+        self.bp_kw = E.default_bp_update_kwargs(bpc)
+        self.reset()
+
+    def reset(self):
+        self.bp_ms = self.gate_ms = self.other_ms = 0.0
+        self.msg_updates = self.gates2 = self.gates1 = 0
+        self.bp_sweeps = 0
+
+    def _timed(self, fn):
+        t = self.torch
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        r = fn()
+        e1.record(self.stream)
+        e1.synchronize()
+        return r, e0.elapsed_time(e1)
+
+    def bp(self):
+        info = {}
+        _, ms = self._timed(lambda: self.E.update(self.bpc, edge_sequence=self.seq, inplace=True, info=info, **self.bp_kw))
+        self.bp_ms += ms
+        self.bp_sweeps += info["iters"]
+        self.msg_updates += info["iters"] * len(self.seq)
+
+    def step(self):
+        E, g = self.E, self.g
+        vs = list(range(g.nv))
+        _, ms = self._timed(lambda: (E.apply_1site_batch(self.bpc, vs, [self.rx] * g.nv), E.apply_1site_batch(self.bpc, vs, [self.rz] * g.nv)))
+        self.other_ms += ms
+        self.gates1 += 2 * g.nv
+        for grp in self.groups:
+            self.bp()                                            # refresh: the class touches affected vertices
+            _, ms = self._timed(lambda: E.apply_2site_batch(self.bpc, grp, [self.rzz] * len(grp), apply_kwargs=self.kw))
+            self.gate_ms += ms
+            self.gates2 += len(grp)
+        self.bp()                                                # final refresh (apply_gates.jl:87-89)
+        (z,), ms = self._timed(lambda: (E.expect(self.bpc, ("Z", [self.obs_v])),))
+        self.other_ms += ms
+        return z
+
+
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    from tensornetworkquantumsimulator_b200 import engine as E, lib
+    chi, nx, ny = args.chi, args.nx, args.ny
+    g, groups, rx, rz, rzz, seq = workload(nx, ny)
+    t0 = time.time()
+    psi = E.random_tensornetworkstate(g, bond_dimension=chi, seed=1 + rank, device=local)
+    bpc = E.BeliefPropagationCache(psi)
+    E.update(bpc, edge_sequence=seq, inplace=True, maxiter=10)
+    E.rescale(bpc, inplace=True)
+    setup_s = time.time() - t0
+    st = Stepper(E, torch, bpc, g, groups, rx, rz, rzz, seq, chi, obs_v=g.v((nx // 2, ny // 2)))
+    for _ in range(args.warmup):
+        st.step()
+    st.reset()
+    launches0 = psi.kernel_launches()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(st.stream)
+    zs = [st.step() for _ in range(args.steps)]
+    ev1.record(st.stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = psi.kernel_launches() - launches0
+    stats = torch.tensor([total_ms, st.bp_ms, st.gate_ms, st.other_ms, float(st.msg_updates), float(st.gates2), float(st.bp_sweeps)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms, bp_ms, gate_ms, other_ms = mx[:4].tolist()
+        msg_updates, gates2 = sm[4].item(), sm[5].item()
+        bp_sweeps = mx[6].item()
+    else:
+        total_ms, bp_ms, gate_ms, other_ms, msg_updates, gates2, bp_sweeps = stats.tolist()
+
+    # ---- roofline of the dominant kernel (k_mode_apply inside the BP sweeps): one profiled sweep, CUDA events per launch ----
+    pk = peaks()
+    L = lib.load()
+    L.tnqs_profile_read(psi._h.ptr, None, None, 1)
+    L.tnqs_profile_enable(psi._h.ptr, 1)
+    E.update(bpc, edge_sequence=seq, inplace=True, maxiter=2)
+    ms = (C.c_double * 8)(); ln = (C.c_int64 * 8)()
+    L.tnqs_profile_read(psi._h.ptr, ms, ln, 1)
+    L.tnqs_profile_enable(psi._h.ptr, 0)
+    fm = flops_per_message(g, chi)
+    sweep_flops = float(fm[np.asarray(seq)].sum())
+    zsum = sum(g.degree(g.dsrc(int(k))) for k in seq)
+    apply_flops = sweep_flops - 8.0 * 2 * sum(chi ** g.degree(g.dsrc(int(k))) * chi for k in seq)   # sweeps minus the closings
+    apply_tf = 2 * apply_flops / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else None
+    close_tf = 2 * (sweep_flops - apply_flops) / (ms[1] * 1e-3) / 1e12 if ms[1] > 0 else None
+    bp_value = msg_updates / (bp_ms * 1e-3)
+    bp_tf = bp_value * sweep_flops / len(seq) / 1e12
+    gflops = sum(gate_flops(g, e, chi) for grp in groups for e in grp) / sum(len(grp) for grp in groups)
+    gate_value = gates2 / (gate_ms * 1e-3)
+    out = {
+        "metric": "bp_edge_message_updates_per_sec", "value": bp_value, "unit": "messages/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64 arithmetic)", "data": "synthetic",
+        "config": {"workload": f"C2: {nx}x{ny} open grid, random TNS chi={chi} ComplexF64 seed 1 (BP-rescaled); step = one Trotter layer "
+                               "(Rx,Rz all sites + 4 Rzz colour classes, maxdim=chi, cutoff=1e-10) with the reference's lazy BP refreshes "
+                               "(<=25 sweeps, tol 1e-8, forest-cover order, REFERENCE_ORDER) + <Z> at the centre",
+                   "chi": chi, "messages_per_sweep": int(len(seq)), "bp_mode": "REFERENCE_ORDER", "per_rank_lattice": f"{nx}x{ny}",
+                   "l2": f"inputs larger than L2: state {psi_bytes(g, chi) / 2**30:.2f} GiB per GPU vs 126 MB"},
+        "gates": {"metric": "two_site_gate_applications_per_sec", "value": gate_value, "unit": "gates/s",
+                  "gflop_per_gate_nominal": gflops / 1e9, "achieved_tflops": gate_value * gflops / 1e12,
+                  "frac_of_fp64_peak": gate_value * gflops / 1e12 / pk["fp64_tflops_sustained"]},
+        "bp": {"sweeps_per_step": bp_sweeps / args.steps, "gflop_per_message": sweep_flops / len(seq) / 1e9, "achieved_tflops": bp_tf,
+               "frac_of_fp64_peak": bp_tf / pk["fp64_tflops_sustained"]},
+        "phase_ms_per_step": {"bp": bp_ms / args.steps, "two_site_gates": gate_ms / args.steps, "one_site_and_expect": other_ms / args.steps},
+        "roofline": {"bound": "tensor", "kernel": "k_mode_apply (BP leg absorption)", "achieved": apply_tf, "peak": pk["fp64_tflops_sustained"],
+                     "unit": "TFLOP/s", "frac": (apply_tf / pk["fp64_tflops_sustained"]) if apply_tf else None, "traffic": None,
+                     "peak_source": pk["source"], "launches_profiled": int(ln[0]), "avg_launch_ms": ms[0] / max(1, ln[0]),
+                     "close_kernel_tflops": close_tf},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "expect_z_center": [float(np.real(z)) for z in zs], "setup_s": setup_s,
+    }
+    del zsum
+    return out, (E, torch, bpc, g, groups, rx, rz, rzz, seq, chi, st)
+
+
+def psi_bytes(g, chi, d=2):
+    return sum(16 * d * chi ** g.degree(v) for v in range(g.nv))
+
+
+def run_e2e(ctx, steps):
+    """The same step through the host API with the state in pinned HOST memory: every site tensor H2D, the layer
+    (apply_gates -> tnqs_apply_circuit), <Z>, every site tensor D2H, inside the timed region."""
+    E, torch, bpc, g, groups, rx, rz, rzz, seq, chi, st = ctx
+    from tensornetworkquantumsimulator_b200 import lib
+    L = lib.load()
+    h = bpc.psi._h.ptr
+    sizes = [int(L.tnqs_site_size(h, v)) for v in range(g.nv)]
+    host = [torch.empty(2 * n, dtype=torch.float64).pin_memory() for n in sizes]
+    ptrs = [C.cast(t.data_ptr(), C.POINTER(C.c_double)) for t in host]
+    for v in range(g.nv):
+        L.tnqs_get_site(h, v, ptrs[v], sizes[v])
+    layer = [(rx, [v]) for v in range(g.nv)] + [(rz, [v]) for v in range(g.nv)]
+    for grp in groups:
+        layer += [(rzz, [int(g.esrc[e]), int(g.edst[e])]) for e in grp]
+    kw = dict(maxdim=chi, cutoff=1e-10, normalize_tensors=True)
+    h2d = sum(16 * n for n in sizes) + 16 * (2 * 4 * g.nv + 16 * sum(len(x) for x in groups)) + 4 * len(seq)
+    d2h = sum(16 * n for n in sizes) + 8 * len(layer) + 16 * 4
+    t_tot = 0.0
+    upd = 0
+    for s in range(steps + 1):                       # first pass is a warm-up
+        torch.cuda.synchronize()
+        u0 = L.tnqs_bp_message_updates_total(h)
+        t0 = time.perf_counter()
+        for v in range(g.nv):
+            lib.check(h, L.tnqs_set_site(h, v, ptrs[v], sizes[v]))
+        info = {}
+        _, errs = E.apply_gates(layer, bpc, apply_kwargs=kw, inplace=True, info=info)
+        z = E.expect(bpc, ("Z", [st.obs_v]))
+        for v in range(g.nv):
+            lib.check(h, L.tnqs_get_site(h, v, ptrs[v], sizes[v]))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if s > 0:
+            t_tot += dt
+            upd += L.tnqs_bp_message_updates_total(h) - u0
+    return {"value": upd / t_tot, "message_updates_per_step": upd / steps, "unit": "messages/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": 1e3 * t_tot / steps, "note": "host wall clock around set_site x V + apply_gates + expect + get_site x V"}
+
+
+def cpu_sample(nx, ny, chi, n_msgs, n_gates, seed=1):
+    """Oracle (NumPy + OpenBLAS, all host threads) on a bounded sample of the same workload: n_msgs message updates in
+    the reference's edge order and n_gates two-site gates, on tensors drawn from the same counter-based generator."""
+    from oracle import tnqs_oracle as O
+    from tensornetworkquantumsimulator_b200 import graphs as G, gates, rng
+    g, groups, rx, rz, rzz, seq = workload(nx, ny)
+    need = set()
+    ks = [int(k) for k in seq[len(seq) // 2: len(seq) // 2 + n_msgs]]
+    for k in ks:
+        need.add(g.dsrc(k))
+    es = groups[0][len(groups[0]) // 2: len(groups[0]) // 2 + n_gates]
+    for e in es:
+        need |= {int(g.esrc[e]), int(g.edst[e])}
+    ts = [None] * g.nv
+    for v in range(g.nv):
+        shape = (2,) + (chi,) * g.degree(v)
+        if v in need:
+            ts[v] = rng.complex_normal(seed, v, int(np.prod(shape))).reshape(shape, order="F") / chi ** (g.degree(v) / 2)
+        else:
+            ts[v] = np.zeros((2,) + (1,) * g.degree(v), dtype=np.complex128)     # placeholder, never touched
+    psi = O.TensorNetworkState(g, ts)
+    psi.bond_dim = lambda e: chi
+    bpc = O.BeliefPropagationCache(psi)
+    rs = np.random.default_rng(0)
+    for v in need:                                   # Hermitian PSD messages into the sampled vertices
+        for e in g.incident[v]:
+            a = rs.normal(size=(chi, chi)) + 1j * rs.normal(size=(chi, chi))
+            m = a @ a.conj().T
+            bpc.messages[g.dedge(g.other(e, v), v)] = m / m.sum()
+    t0 = time.perf_counter()
+    for k in ks:
+        new = O.updated_message(bpc, k)
+        O.message_diff(new, O.message(bpc, k))
+    t_msg = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for e in es:
+        O.simple_update_2site(bpc, rzz, int(g.esrc[e]), int(g.edst[e]), maxdim=chi, cutoff=1e-10)
+    t_gate = time.perf_counter() - t0
+    return len(ks) / t_msg, (len(es) / t_gate) if es else None, t_msg, t_gate
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm as restated by the oracle (Julia cannot run here),
+    all host threads, bounded sample of the same config per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    cores = os.cpu_count()
+    n_msgs, n_gates = args.cpu_msgs, args.cpu_gates
+    vals, gvals = [], []
+    for s in range(args.warmup + args.steps):
+        mps, gps, t_msg, t_gate = cpu_sample(args.nx, args.ny, args.chi, n_msgs, n_gates)
+        if s >= args.warmup:
+            vals.append(mps); gvals.append(gps)
+    v = float(np.mean(vals))
+    sample = f"{n_msgs} message updates (middle of the forest-cover sweep) + {n_gates} two-site gates per step on the C2 tensors"
+    return {"impl": "reference", "metric": "bp_edge_message_updates_per_sec", "value": v, "unit": "messages/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_msgs / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "c128 (f64 arithmetic)", "data": "synthetic",
+            "config": {"workload": f"C2: {args.nx}x{args.ny} open grid, random TNS chi={args.chi} ComplexF64", "chi": args.chi},
+            "gates": {"metric": "two_site_gate_applications_per_sec", "value": float(np.mean(gvals)), "unit": "gates/s"},
+            "cpu_baseline": {"value": v, "unit": "messages/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "restated CPU oracle (NumPy + OpenBLAS, all host threads) - not Julia"},
+            "e2e": {"value": v, "unit": "messages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--nx", type=int, default=32)
+    ap.add_argument("--ny", type=int, default=32)
+    ap.add_argument("--chi", type=int, default=16)
+    ap.add_argument("--cpu-msgs", type=int, default=96)
+    ap.add_argument("--cpu-gates", type=int, default=8)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        out = run_reference(args)
+        if out is not None:
+            print(json.dumps(out))
+        return
+    out, ctx = run_engine(args)
+    rank = int(os.environ.get("RANK", "0"))
+    if not args.no_e2e:
+        out["e2e"] = run_e2e(ctx, max(1, min(args.steps, 2)))
+    if rank == 0:
+        if not args.no_cpu and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+            mps, gps, t_msg, t_gate = cpu_sample(args.nx, args.ny, args.chi, args.cpu_msgs, args.cpu_gates)
+            out["cpu_baseline"] = {"value": mps, "unit": "messages/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"{args.cpu_msgs} message updates + {args.cpu_gates} two-site gates of the same C2 tensors ({t_msg + t_gate:.1f} s of CPU work)",
+                                   "gates_per_s": gps, "note": "restated CPU oracle (NumPy + OpenBLAS, all host threads) - not Julia"}
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -173,6 +173,9 @@ int32_t tnqs_set_partition(tnqs_ctx* ctx, const int32_t* owner, int32_t rank);
 /* ---- instrumentation ------------------------------------------------------------------------------------------
  * Kernel launches issued by this handle since creation (the `gpu_launches` figure of bench.py). */
 int64_t tnqs_kernel_launches(const tnqs_ctx* ctx);
+/* BP sweeps / directed-edge message updates performed by this handle since creation (all entry points). */
+int64_t tnqs_bp_sweeps_total(const tnqs_ctx* ctx);
+int64_t tnqs_bp_message_updates_total(const tnqs_ctx* ctx);
 /* Device time (ms) and launch count per kernel class since the last reset, measured with CUDA events on the
  * handle's stream when profiling is enabled: classes are TNQS_KC_*.  */
 enum { TNQS_KC_MODE_APPLY = 0, TNQS_KC_MODE_CLOSE = 1, TNQS_KC_BP_FINALIZE = 2, TNQS_KC_PERMUTE = 3,

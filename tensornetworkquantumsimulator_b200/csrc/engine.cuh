@@ -43,6 +43,7 @@ struct tnqs_ctx {
   std::vector<int> owner; int rank = 0; bool partitioned = false;
   std::string err;
   long long launches = 0;
+  long long bp_sweeps = 0, bp_msg_updates = 0;
   bool profiling = false;
   std::vector<ProfEvent> prof_events;
   double prof_ms[TNQS_KC_COUNT] = {0};

@@ -85,6 +85,11 @@ extern "C" int32_t tnqs_create(tnqs_ctx** out, int32_t nv, int32_t ne, const int
     c->num_sms = prop.multiProcessorCount; c->smem_optin = prop.sharedMemPerBlockOptin;
     set_smem_attrs();
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // keep freed stream-ordered allocations in the pool across synchronisations (default: trimmed to 0 at every sync)
+      cudaMemPool_t pool; CU(cudaDeviceGetDefaultMemPool(&pool, device));
+      unsigned long long keep = ~0ull;
+      CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     c->nv = nv; c->ne = ne; c->chi_cap = chi_cap;
     c->esrc.assign(esrc, esrc + ne); c->edst.assign(edst, edst + ne);
     c->d.assign(d, d + nv); c->chi.assign(chi, chi + ne);
@@ -281,6 +286,7 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
   int it = 0; double mean = NAN;
   for (it = 1; it <= o.maxiter; ++it) {
     run_plan(c, plan);
+    ++c->bp_sweeps; c->bp_msg_updates += nseq;
     if (want_diff) {
       LAUNCH(c, TNQS_KC_BP_FINALIZE, k_sum, 1, 1024, 0, d_diff, nseq, d_sum);
       double s = 0;
@@ -1028,6 +1034,8 @@ extern "C" int32_t tnqs_set_partition(tnqs_ctx* c, const int32_t* owner, int32_t
   return TNQS_OK;
 }
 extern "C" int64_t tnqs_kernel_launches(const tnqs_ctx* c) { return c ? c->launches : 0; }
+extern "C" int64_t tnqs_bp_sweeps_total(const tnqs_ctx* c) { return c ? c->bp_sweeps : 0; }
+extern "C" int64_t tnqs_bp_message_updates_total(const tnqs_ctx* c) { return c ? c->bp_msg_updates : 0; }
 extern "C" int32_t tnqs_profile_enable(tnqs_ctx* c, int32_t on) {
   if (!c) return TNQS_ERR_INVALID_ARG;
   c->collect_profile(); c->profiling = on != 0; return TNQS_OK;

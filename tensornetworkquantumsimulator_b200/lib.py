@@ -23,7 +23,7 @@ SYMBOLS = [
     "tnqs_bp_update", "tnqs_apply_1site", "tnqs_apply_2site", "tnqs_apply_circuit", "tnqs_rdm_1site",
     "tnqs_expect_2site_nn", "tnqs_vertex_scalars", "tnqs_edge_scalars", "tnqs_rescale", "tnqs_symmetric_gauge",
     "tnqs_truncate", "tnqs_message_slab", "tnqs_halo_pack", "tnqs_halo_unpack", "tnqs_set_partition",
-    "tnqs_kernel_launches", "tnqs_profile_enable", "tnqs_profile_read", "tnqs_stream",
+    "tnqs_kernel_launches", "tnqs_bp_sweeps_total", "tnqs_bp_message_updates_total", "tnqs_profile_enable", "tnqs_profile_read", "tnqs_stream",
 ]
 
 KERNEL_CLASSES = ["mode_apply", "mode_close", "bp_finalize", "permute", "eigh", "qr", "svd", "misc"]
@@ -87,6 +87,8 @@ def load() -> C.CDLL:
     lib.tnqs_halo_pack.argtypes = [p, i32, i32p, vp]; lib.tnqs_halo_unpack.argtypes = [p, i32, i32p, vp]
     lib.tnqs_set_partition.argtypes = [p, i32p, i32]
     lib.tnqs_kernel_launches.argtypes = [p]; lib.tnqs_kernel_launches.restype = i64
+    lib.tnqs_bp_sweeps_total.argtypes = [p]; lib.tnqs_bp_sweeps_total.restype = i64
+    lib.tnqs_bp_message_updates_total.argtypes = [p]; lib.tnqs_bp_message_updates_total.restype = i64
     lib.tnqs_profile_enable.argtypes = [p, i32]
     lib.tnqs_profile_read.argtypes = [p, f64p, i64p, i32]
     lib.tnqs_stream.argtypes = [p]; lib.tnqs_stream.restype = vp
