@@ -14,6 +14,7 @@
 #include "kernels_gemm.cuh"
 #include "kernels_small.cuh"
 #include "kernels_misc.cuh"
+#include "kernels_dmma.cuh"
 
 struct TnqsError {
   int code; std::string msg;
@@ -136,6 +137,8 @@ struct Chain {
 
 struct LaunchRec { size_t off; int count; dim3 grid; size_t smem; };
 struct SubLevel {
+  LaunchRec slab{0, 0, dim3(), 0}, dclose{0, 0, dim3(), 0};   // DMMA fast path (kernels_dmma.cuh)
+  int fastN = 0;
   LaunchRec gate1{0, 0, dim3(), 0};
   std::vector<LaunchRec> steps;
   LaunchRec close{0, 0, dim3(), 0}, reduce{0, 0, dim3(), 0};
@@ -146,16 +149,38 @@ struct Plan {
   std::vector<LevelPlan> levels;
   Gate1Desc* d_gate1 = nullptr; ModeApplyDesc* d_apply = nullptr; ModeCloseDesc* d_close = nullptr;
   CloseReduceDesc* d_reduce = nullptr; int* d_commit = nullptr;
+  SlabDesc* d_slab = nullptr; CloseDmmaDesc* d_dclose = nullptr;
   double flops = 0;                  // executed flops per run of the plan (8 per complex MAC)
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// DMMA fast path eligibility: BP-type chain (no operator, closes on a bond leg), site dimension 2, every leg of the
+// vertex of the same dimension N in {8, 16}, 2 or 3 absorbed legs with plain N x N matrices.  Returns N or 0.
+static int fast_path_N(const tnqs_ctx* c, const Chain& ch) {
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("TNQS_NO_DMMA"); disabled = (e && e[0] == '1') ? 1 : 0; }
+  if (disabled || ch.op || ch.close_leg < 0) return 0;
+  const int v = ch.v, z = (int)c->inc[v].size(), F = (int)ch.absorb.size();
+  if (c->d[v] != 2 || F != z - 1 || F < 2 || F > 3) return 0;
+  const int N = c->chi[c->inc[v][0]];
+  if (N != 8 && N != 16) return 0;
+  for (int e : c->inc[v]) if (c->chi[e] != N) return 0;
+  int expect_leg = 0;
+  for (const Absorb& ab : ch.absorb) {
+    if (expect_leg == ch.close_leg) ++expect_leg;
+    if (ab.leg != expect_leg || ab.flags != 0 || ab.ldm != N) return 0;
+    ++expect_leg;
+  }
+  return N;
+}
 
 // Build a plan for `levels` (vector of vector of chains).  All device buffers are temporaries of the current call.
 static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& levels, size_t scratch_budget_bytes) {
   Plan plan;
   std::vector<Gate1Desc> g1; std::vector<ModeApplyDesc> ma; std::vector<ModeCloseDesc> mc;
   std::vector<CloseReduceDesc> rd; std::vector<int> commit;
+  std::vector<SlabDesc> sd; std::vector<CloseDmmaDesc> dc;
   // pass 1: scratch requirement per chain, sub-level split, global scratch sizing
   struct ChainMem { size_t buf_elems; int nbuf; int nsplit; size_t partial_elems; };
   size_t max_scratch = 0, max_partial = 0;
@@ -169,6 +194,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
       const Chain& ch = chains[i];
       int nsteps = (ch.op ? 1 : 0) + (int)ch.absorb.size();
       ChainMem cm; cm.buf_elems = (size_t)c->site_n[ch.v]; cm.nbuf = std::min(nsteps, 2); cm.nsplit = 1; cm.partial_elems = 0;
+      if (fast_path_N(c, ch)) cm.nbuf = 1;
       mem[L][i] = cm;
       size_t bytes = align_up(cm.buf_elems * sizeof(cplx), 256) * cm.nbuf;
       if (!cur.empty() && cur_bytes + bytes > scratch_budget_bytes) { subsets[L].push_back(cur); cur.clear(); cur_bytes = 0; }
@@ -184,6 +210,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         int n = ch.close_leg < 0 ? c->d[ch.v] : c->chi[c->inc[ch.v][ch.close_leg]];
         long long rows = c->site_n[ch.v] / n;
         int ns = (int)std::min<long long>(std::min(target, 64), std::max<long long>(1, rows / 128));
+        if (fast_path_N(c, ch)) ns = (int)std::min<long long>(std::min(target, 32), std::max<long long>(1, rows / 128));   // >= 64 k-steps per CTA
         mem[L][i].nsplit = std::max(1, ns);
         mem[L][i].partial_elems = (size_t)mem[L][i].nsplit * n * n;
         part += mem[L][i].partial_elems;
@@ -213,12 +240,51 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
       // current tensor of every chain and which buffer it would write next
       std::vector<const cplx*> curp(sub.size()); std::vector<int> next(sub.size(), 0);
       for (size_t j = 0; j < sub.size(); ++j) curp[j] = c->site[chains[sub[j]].v];
+      // DMMA fast path: fused absorption into the slab-major intermediate, then the tensor-core closing
+      std::vector<char> fast(sub.size(), 0);
+      std::vector<size_t> fast_poff(sub.size(), 0);
+      sl.slab.off = sd.size(); sl.dclose.off = dc.size();
+      {
+        size_t pscan = 0; int maxsplit_f = 1;
+        for (size_t j = 0; j < sub.size(); ++j) {
+          const Chain& ch = chains[sub[j]];
+          const ChainMem& cm = mem[L][sub[j]];
+          int N = fast_path_N(c, ch);
+          fast_poff[j] = pscan; pscan += cm.partial_elems;
+          if (!N) continue;
+          REQUIRE(sl.fastN == 0 || sl.fastN == N, TNQS_ERR_UNSUPPORTED, "mixed fast-path bond dimensions in one level");
+          sl.fastN = N; fast[j] = 1;
+          const int v = ch.v, F = (int)ch.absorb.size();
+          SlabDesc a; a.t = c->site[v]; a.x = buf0[j]; a.F = F;
+          CloseDmmaDesc b; b.x = buf0[j]; b.t = c->site[v]; b.partial = partial + fast_poff[j]; b.F = F; b.nsplit = cm.nsplit;
+          long long stride = 2;
+          int ai = 0;
+          for (int l = 0; l < (int)c->inc[v].size(); ++l) {
+            if (l == ch.close_leg) { a.gw = stride; b.gw = stride; }
+            else { a.g[ai] = stride; b.g[ai] = stride; a.m[ai] = ch.absorb[ai].mat; ++ai; }
+            stride *= N;
+          }
+          for (; ai < 3; ++ai) { a.g[ai] = 0; b.g[ai] = 0; a.m[ai] = nullptr; }
+          sd.push_back(a); dc.push_back(b);
+          maxsplit_f = std::max(maxsplit_f, cm.nsplit);
+          plan.flops += 8.0 * (double)c->site_n[v] * N * (F + 1);
+        }
+        sl.slab.count = (int)(sd.size() - sl.slab.off);
+        sl.dclose.count = sl.slab.count;
+        if (sl.slab.count) {
+          int N = sl.fastN;
+          sl.slab.grid = dim3(2 * N, sl.slab.count, 1);
+          sl.slab.smem = (size_t)(N + 2) * N * N * sizeof(cplx);
+          sl.dclose.grid = dim3(maxsplit_f, sl.dclose.count, 1);
+          sl.dclose.smem = (size_t)8 * (2 * N) * (2 * N) * sizeof(double);
+        }
+      }
       // one-site operators
       sl.gate1.off = g1.size();
       long long maxrest = 0;
       for (size_t j = 0; j < sub.size(); ++j) {
         const Chain& ch = chains[sub[j]];
-        if (!ch.op) continue;
+        if (!ch.op || fast[j]) continue;
         Gate1Desc g; g.in = curp[j]; g.out = buf0[j]; g.gate = ch.op; g.d = c->d[ch.v];
         g.rest = c->site_n[ch.v] / g.d; g.norm2_partial = nullptr;
         g1.push_back(g); curp[j] = buf0[j]; next[j] = 1; maxrest = std::max(maxrest, g.rest);
@@ -232,7 +298,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         long long maxtiles = 1; int maxcol = 1;
         for (size_t j = 0; j < sub.size(); ++j) {
           const Chain& ch = chains[sub[j]];
-          if (s >= (int)ch.absorb.size()) continue;
+          if (fast[j] || s >= (int)ch.absorb.size()) continue;
           const Absorb& ab = ch.absorb[s];
           int v = ch.v;
           ModeApplyDesc d;
@@ -260,26 +326,29 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         const Chain& ch = chains[sub[j]];
         const ChainMem& cm = mem[L][sub[j]];
         int v = ch.v;
-        ModeCloseDesc d;
         long long Lp; int n;
         if (ch.close_leg < 0) { Lp = 1; n = c->d[v]; }
         else { Lp = c->d[v]; for (int i = 0; i < ch.close_leg; ++i) Lp *= c->chi[c->inc[v][i]]; n = c->chi[c->inc[v][ch.close_leg]]; }
         long long R = c->site_n[v] / (Lp * n);
-        d.a = curp[j]; d.b = c->site[v]; d.partial = partial + poff;
-        d.L = (int)Lp; d.R = (int)R; d.n = n; d.np = n;
-        d.a_sb = Lp; d.a_sr = Lp * n; d.b_sb = Lp; d.b_sr = Lp * n;
-        d.nsplit = cm.nsplit; d.rows_per_split = (Lp * R + cm.nsplit - 1) / cm.nsplit;
-        mc.push_back(d);
+        cplx* part = partial + fast_poff[j];
+        if (!fast[j]) {
+          ModeCloseDesc d;
+          d.a = curp[j]; d.b = c->site[v]; d.partial = part;
+          d.L = (int)Lp; d.R = (int)R; d.n = n; d.np = n;
+          d.a_sb = Lp; d.a_sr = Lp * n; d.b_sb = Lp; d.b_sr = Lp * n;
+          d.nsplit = cm.nsplit; d.rows_per_split = (Lp * R + cm.nsplit - 1) / cm.nsplit;
+          mc.push_back(d);
+          maxsplit = std::max(maxsplit, cm.nsplit);
+          plan.flops += 8.0 * (double)c->site_n[v] * n;
+        }
         CloseReduceDesc r;
-        r.partial = d.partial; r.nsplit = cm.nsplit; r.n = n; r.np = n; r.dst = ch.dst; r.prev = ch.prev; r.diff = ch.diff;
+        r.partial = part; r.nsplit = cm.nsplit; r.n = n; r.np = n; r.dst = ch.dst; r.prev = ch.prev; r.diff = ch.diff;
         r.mode = ch.bp_mode; r.normalize = ch.normalize; r.hermitize = ch.hermitize;
         rd.push_back(r);
-        poff += cm.partial_elems;
-        maxsplit = std::max(maxsplit, cm.nsplit); maxnn = std::max(maxnn, (size_t)n * n);
-        plan.flops += 8.0 * (double)c->site_n[v] * n;
+        maxnn = std::max(maxnn, (size_t)n * n);
         REQUIRE(n <= 64, TNQS_ERR_UNSUPPORTED, "closing extent > 64 is not supported");
       }
-      sl.close.count = (int)sub.size(); sl.close.grid = dim3(maxsplit, sl.close.count, 1);
+      sl.close.count = (int)(mc.size() - sl.close.off); sl.close.grid = dim3(maxsplit, std::max(1, sl.close.count), 1);
       sl.reduce.count = (int)sub.size(); sl.reduce.grid = dim3(sl.reduce.count, 1, 1); sl.reduce.smem = maxnn * sizeof(cplx);
       lp.subs.push_back(sl);
     }
@@ -289,15 +358,25 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
   }
   plan.d_gate1 = c->upload(g1); plan.d_apply = c->upload(ma); plan.d_close = c->upload(mc);
   plan.d_reduce = c->upload(rd); plan.d_commit = c->upload(commit);
+  plan.d_slab = c->upload(sd); plan.d_dclose = c->upload(dc);
   return plan;
 }
 
 static void run_plan(tnqs_ctx* c, const Plan& p) {
   for (const LevelPlan& lp : p.levels) {
     for (const SubLevel& sl : lp.subs) {
+      if (sl.slab.count) {
+        if (sl.fastN == 16) {
+          LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<16>, sl.slab.grid, 256, sl.slab.smem, p.d_slab + sl.slab.off);
+          LAUNCH(c, TNQS_KC_MODE_CLOSE, k_close_dmma<16>, sl.dclose.grid, 256, sl.dclose.smem, p.d_dclose + sl.dclose.off);
+        } else {
+          LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<8>, sl.slab.grid, 256, sl.slab.smem, p.d_slab + sl.slab.off);
+          LAUNCH(c, TNQS_KC_MODE_CLOSE, k_close_dmma<8>, sl.dclose.grid, 256, sl.dclose.smem, p.d_dclose + sl.dclose.off);
+        }
+      }
       if (sl.gate1.count) LAUNCH(c, TNQS_KC_MISC, k_gate1, sl.gate1.grid, 256, 0, p.d_gate1 + sl.gate1.off);
       for (const LaunchRec& lr : sl.steps) LAUNCH(c, TNQS_KC_MODE_APPLY, k_mode_apply, lr.grid, 256, 0, p.d_apply + lr.off);
-      LAUNCH(c, TNQS_KC_MODE_CLOSE, k_mode_close, sl.close.grid, 256, 0, p.d_close + sl.close.off);
+      if (sl.close.count) LAUNCH(c, TNQS_KC_MODE_CLOSE, k_mode_close, sl.close.grid, 256, 0, p.d_close + sl.close.off);
       LAUNCH(c, TNQS_KC_BP_FINALIZE, k_close_reduce, sl.reduce.grid, 256, sl.reduce.smem, p.d_reduce + sl.reduce.off);
     }
     if (lp.commit_count)

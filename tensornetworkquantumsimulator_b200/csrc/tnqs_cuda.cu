@@ -42,6 +42,10 @@ static void set_smem_attrs() {
   cudaFuncSetAttribute(k_house_qr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_svd_trunc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_close_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  cudaFuncSetAttribute(k_absorb_slab<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_absorb_slab<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_close_dmma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_close_dmma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   done = true;
 }
 

@@ -47,6 +47,24 @@ def test_bp_sweeps_match_oracle(E, name, chi):
         check_messages(E, be, bo)
 
 
+@pytest.mark.parametrize("name,chi", [("grid3x3", 8), ("grid3x3", 16), ("hex", 8), ("hex", 16), ("grid4x3", 8)])
+def test_bp_dmma_fast_path(E, name, chi):
+    # uniform chi in {8, 16}, d = 2, degree 3..4: the FP64 tensor-core kernels (kernels_dmma.cuh) carry the sweep
+    g = {"grid3x3": lambda: G.named_grid((3, 3)), "grid4x3": lambda: G.named_grid((4, 3)),
+         "hex": lambda: G.named_hexagonal_lattice_graph(2, 1)}[name]()
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=chi, seed=41)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    seq = G.forest_cover_edge_sequence(g)
+    io, ie = {}, {}
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=2, tolerance=0.0, edge_sequence=seq, info=io)
+    be = E.update(to_engine(psi_o), maxiter=2, tolerance=0.0, edge_sequence=seq, info=ie)
+    check_messages(E, be, bo)
+    assert ie["mean_diff"] == pytest.approx(io["mean_diff"], rel=1e-8)
+    v = g.nv // 2
+    assert abs(E.expect(be, ("Z", [g.names[v]])) - O.expect(bo, ("Z", [g.names[v]]))) < EXP_TOL
+
+
 def test_bp_ragged_bonds_and_tolerance(E):
     g = G.named_grid((4, 3))
     rs = np.random.default_rng(5)
