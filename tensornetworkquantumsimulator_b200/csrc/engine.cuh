@@ -135,7 +135,25 @@ struct Chain {
   int commit_k = -1;                 // BP: directed edge to commit at the end of the level
 };
 
-struct LaunchRec { size_t off; int count; dim3 grid; size_t smem; };
+struct LaunchRec { size_t off; int count; dim3 grid; size_t smem; bool dmma = false; };
+
+static bool dmma_disabled() {
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("TNQS_NO_DMMA"); disabled = (e && e[0] == '1') ? 1 : 0; }
+  return disabled == 1;
+}
+
+// Kernel choice and grid of one batched mode_apply launch: the tensor-core kernel when every item has n, np <= 32.
+struct ApplyLaunch { bool dmma; dim3 grid; };
+static ApplyLaunch plan_apply_launch(const ModeApplyDesc* d, size_t count) {
+  bool ok = !dmma_disabled(); long long maxrows = 1; int maxnp = 1;
+  for (size_t i = 0; i < count; ++i) {
+    ok = ok && d[i].n <= 32 && d[i].np <= 32;
+    maxrows = std::max(maxrows, (long long)d[i].L * d[i].R); maxnp = std::max(maxnp, d[i].np);
+  }
+  if (ok) return {true, dim3((unsigned)((maxrows + 127) / 128), (unsigned)count, 1)};
+  return {false, dim3((unsigned)((maxrows + MA_BM - 1) / MA_BM), (unsigned)count, (unsigned)((maxnp + MA_BN - 1) / MA_BN))};
+}
 struct SubLevel {
   LaunchRec slab{0, 0, dim3(), 0}, dclose{0, 0, dim3(), 0};   // DMMA fast path (kernels_dmma.cuh)
   int fastN = 0;
@@ -158,9 +176,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // DMMA fast path eligibility: BP-type chain (no operator, closes on a bond leg), site dimension 2, every leg of the
 // vertex of the same dimension N in {8, 16}, 2 or 3 absorbed legs with plain N x N matrices.  Returns N or 0.
 static int fast_path_N(const tnqs_ctx* c, const Chain& ch) {
-  static int disabled = -1;
-  if (disabled < 0) { const char* e = getenv("TNQS_NO_DMMA"); disabled = (e && e[0] == '1') ? 1 : 0; }
-  if (disabled || ch.op || ch.close_leg < 0) return 0;
+  if (dmma_disabled() || ch.op || ch.close_leg < 0) return 0;
   const int v = ch.v, z = (int)c->inc[v].size(), F = (int)ch.absorb.size();
   if (c->d[v] != 2 || F != z - 1 || F < 2 || F > 3) return 0;
   const int N = c->chi[c->inc[v][0]];
@@ -316,8 +332,12 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
           plan.flops += 8.0 * (double)c->site_n[v] * n;
         }
         lr.count = (int)(ma.size() - lr.off);
-        lr.grid = dim3((unsigned)maxtiles, lr.count, maxcol);
-        if (lr.count) sl.steps.push_back(lr);
+        if (lr.count) {
+          ApplyLaunch al = plan_apply_launch(ma.data() + lr.off, lr.count);
+          lr.grid = al.grid; lr.dmma = al.dmma;
+          sl.steps.push_back(lr);
+        }
+        (void)maxtiles; (void)maxcol;
       }
       // closing + reduction
       sl.close.off = mc.size(); sl.reduce.off = rd.size();
@@ -349,6 +369,8 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         REQUIRE(n <= 64, TNQS_ERR_UNSUPPORTED, "closing extent > 64 is not supported");
       }
       sl.close.count = (int)(mc.size() - sl.close.off); sl.close.grid = dim3(maxsplit, std::max(1, sl.close.count), 1);
+      sl.close.dmma = !dmma_disabled();
+      for (size_t i = sl.close.off; i < mc.size(); ++i) sl.close.dmma = sl.close.dmma && mc[i].n <= 32 && mc[i].np <= 32;
       sl.reduce.count = (int)sub.size(); sl.reduce.grid = dim3(sl.reduce.count, 1, 1); sl.reduce.smem = maxnn * sizeof(cplx);
       lp.subs.push_back(sl);
     }
@@ -360,6 +382,15 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
   plan.d_reduce = c->upload(rd); plan.d_commit = c->upload(commit);
   plan.d_slab = c->upload(sd); plan.d_dclose = c->upload(dc);
   return plan;
+}
+
+// Upload and launch one batched mode_apply (tensor-core kernel when eligible).
+static void launch_mode_apply(tnqs_ctx* c, int kc, const std::vector<ModeApplyDesc>& ma) {
+  if (ma.empty()) return;
+  ModeApplyDesc* dma = c->upload(ma);
+  ApplyLaunch al = plan_apply_launch(ma.data(), ma.size());
+  if (al.dmma) LAUNCH(c, kc, k_leg_dmma, al.grid, 256, 0, dma);
+  else LAUNCH(c, kc, k_mode_apply, al.grid, 256, 0, dma);
 }
 
 static void run_plan(tnqs_ctx* c, const Plan& p) {
@@ -375,8 +406,14 @@ static void run_plan(tnqs_ctx* c, const Plan& p) {
         }
       }
       if (sl.gate1.count) LAUNCH(c, TNQS_KC_MISC, k_gate1, sl.gate1.grid, 256, 0, p.d_gate1 + sl.gate1.off);
-      for (const LaunchRec& lr : sl.steps) LAUNCH(c, TNQS_KC_MODE_APPLY, k_mode_apply, lr.grid, 256, 0, p.d_apply + lr.off);
-      if (sl.close.count) LAUNCH(c, TNQS_KC_MODE_CLOSE, k_mode_close, sl.close.grid, 256, 0, p.d_close + sl.close.off);
+      for (const LaunchRec& lr : sl.steps) {
+        if (lr.dmma) LAUNCH(c, TNQS_KC_MODE_APPLY, k_leg_dmma, lr.grid, 256, 0, p.d_apply + lr.off);
+        else LAUNCH(c, TNQS_KC_MODE_APPLY, k_mode_apply, lr.grid, 256, 0, p.d_apply + lr.off);
+      }
+      if (sl.close.count) {
+        if (sl.close.dmma) LAUNCH(c, TNQS_KC_MODE_CLOSE, k_close_leg_dmma, sl.close.grid, 256, 8 * 1024 * sizeof(double), p.d_close + sl.close.off);
+        else LAUNCH(c, TNQS_KC_MODE_CLOSE, k_mode_close, sl.close.grid, 256, 0, p.d_close + sl.close.off);
+      }
       LAUNCH(c, TNQS_KC_BP_FINALIZE, k_close_reduce, sl.reduce.grid, 256, sl.reduce.smem, p.d_reduce + sl.reduce.off);
     }
     if (lp.commit_count)

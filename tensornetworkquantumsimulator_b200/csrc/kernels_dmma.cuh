@@ -13,6 +13,7 @@
 // There is no f64 kind of tcgen05, so DMMA is the FP64 tensor path on sm_100a (measured peak 37.15 TFLOP/s).
 #pragma once
 #include "common.cuh"
+#include "kernels_gemm.cuh"
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -178,4 +179,244 @@ __global__ void __launch_bounds__(256, 2) k_close_dmma(const CloseDmmaDesc* __re
     }
     out[idx] = cmake(rr + ii, ir - ri);              // X conj(T): re = rr + ii, im = ir - ri
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_leg_dmma: tensor-core version of k_mode_apply for n, np <= 32:  out[l, c, r] = sum_b in[l, b, r] * M[b, c].
+// The real 2n x 2np matrix [[Re M, Im M], [-Im M, Re M]] (interleaved) sits in shared memory; A fragments are 8-byte
+// loads straight from global memory (each input element is read by exactly one thread), C fragments are 16-byte
+// stores.  A warp owns 32 rows x 16 complex columns (4 x 4 DMMA tiles); a CTA of 8 warps covers 128 rows x 32
+// columns or 256 rows x 16 columns.  A CTA-wide barrier separates the last load from the first store, so in == out
+// is allowed.  Same descriptor and flags as k_mode_apply.
+// grid: (row tiles, items); block 256; static shared memory 64 x 72 doubles.
+// ---------------------------------------------------------------------------------------------------------------
+#define LD_LDB 72            // leading dimension (doubles) of the shared B matrix: == 8 mod 32 -> conflict-free fragments
+
+__global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __restrict__ descs) {
+  const ModeApplyDesc d = descs[blockIdx.y];
+  const int halves = d.np > 16 ? 2 : 1;
+  const int rows_per_cta = halves == 2 ? 128 : 256;
+  const long long rows = (long long)d.L * d.R;
+  const long long row0 = (long long)blockIdx.x * rows_per_cta;
+  if (row0 >= rows) return;
+  __shared__ double Bs[64 * LD_LDB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = lane >> 2, q = lane & 3, kpair = q >> 1, part = q & 1;
+  const int n = d.n, np = d.np;
+  const int K2 = 2 * ((n + 1) / 2 * 2);          // real K rounded up to whole k-steps (multiples of 4)
+  const bool conj_m = d.flags & 1, trans_m = d.flags & 2;
+  // B[(b, p), (c, p')]: p == p' -> Re m[b,c]; (im, re) -> -Im; (re, im) -> +Im; zero padding outside n x np
+  for (int idx = tid; idx < 64 * 64; idx += 256) {
+    int kk = idx >> 6, nn = idx & 63;
+    int b = kk >> 1, p = kk & 1, c = nn >> 1, pp = nn & 1;
+    double v = 0.0;
+    if (b < n && c < np) {
+      cplx m = trans_m ? d.m[c + (long long)b * d.ldm] : d.m[b + (long long)c * d.ldm];
+      if (conj_m) m.y = -m.y;
+      v = (p == pp) ? m.x : (p ? -m.y : m.y);
+    }
+    Bs[kk * LD_LDB + nn] = v;
+  }
+  __syncthreads();
+  const int half = halves == 2 ? (warp & 1) : 0;
+  const int rg = halves == 2 ? (warp >> 1) : warp;            // row group of 32 rows
+  const long long wrow0 = row0 + (long long)rg * 32;
+  const double* in = reinterpret_cast<const double*>(d.in);
+  double* out = reinterpret_cast<double*>(d.out);
+  long long soff[4], doff[4];
+  bool valid[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    long long row = wrow0 + 8 * t + r;
+    valid[t] = row < rows;
+    long long rr = valid[t] ? row / d.L : 0, l = valid[t] ? row - rr * d.L : 0;
+    soff[t] = l + rr * d.in_sr; doff[t] = l + rr * d.out_sr;
+  }
+  double acc[4][4][2];
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[t][j][0] = 0.0; acc[t][j][1] = 0.0; }
+  const int ncol0 = 32 * half;                                  // first real column of this warp's half
+  for (int ks0 = 0; ks0 < K2 / 4; ks0 += 4) {
+    double a[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int b = 2 * (ks0 + u) + kpair;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        a[u][t] = (valid[t] && b < n) ? in[2 * (soff[t] + (long long)b * d.in_sb) + part] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (4 * (ks0 + u) >= K2) break;
+      double bf[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = Bs[(4 * (ks0 + u) + q) * LD_LDB + ncol0 + 8 * j + r];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[t][j][0], acc[t][j][1], a[u][t], bf[j]);
+    }
+  }
+  __syncthreads();                                              // every load of the CTA tile precedes every store
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (!valid[t]) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 16 * half + 4 * j + q;
+      if (c < np) {
+        double2 v; v.x = acc[t][j][0]; v.y = acc[t][j][1];
+        *reinterpret_cast<double2*>(out + 2 * (doff[t] + (long long)c * d.out_sb)) = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_close_leg_dmma: tensor-core version of k_mode_close for n, np <= 32:  G[b, b'] = sum_rows A[row, b] conj(B[row, b']).
+// Real GEMM P[(b,p),(b',p')] = sum_rows A_p[row, b] B_p'[row, b'] (M = 2n, N = 2np, K = rows); both operand fragments
+// are 8-byte loads from global memory (4 consecutive rows x 4 columns per warp load).  A warp owns a 32 x 32 real
+// quadrant of P; 8 warps = quadrants x K-slices; fixed-order reduction over the K-slices in shared memory; partials
+// in the layout k_close_reduce consumes.  Same descriptor as k_mode_close.
+// grid: (max nsplit, items); block 256; dynamic shared memory 8 * 1024 doubles.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) k_close_leg_dmma(const ModeCloseDesc* __restrict__ descs) {
+  const ModeCloseDesc d = descs[blockIdx.y];
+  if ((int)blockIdx.x >= d.nsplit) return;
+  extern __shared__ double red[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = lane >> 2, q = lane & 3, wl = r >> 1, part = r & 1;
+  const int n = d.n, np = d.np;
+  const int qm = n > 16 ? 2 : 1, qn = np > 16 ? 2 : 1, nquad = qm * qn, nslice = 8 / nquad;
+  const int quad = warp % nquad, slice = warp / nquad;
+  const int mq = quad % qm, nq = quad / qm;
+  const long long rows = (long long)d.L * d.R;
+  const long long r_begin = (long long)blockIdx.x * d.rows_per_split;
+  const long long r_end = min(rows, r_begin + d.rows_per_split);
+  const double* A = reinterpret_cast<const double*>(d.a);
+  const double* B = reinterpret_cast<const double*>(d.b);
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  for (long long k0 = r_begin + 4 * slice; k0 < r_end; k0 += 4 * nslice) {
+    const long long row = k0 + q;
+    const bool ok = row < r_end;
+    long long rr = ok ? row / d.L : 0, l = ok ? row - rr * d.L : 0;
+    const long long aoff = l + rr * d.a_sr, boff = l + rr * d.b_sr;
+    double a[4], b[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int ba = 16 * mq + 4 * t + wl, bb = 16 * nq + 4 * t + wl;
+      a[t] = (ok && ba < n) ? A[2 * (aoff + (long long)ba * d.a_sb) + part] : 0.0;
+      b[t] = (ok && bb < np) ? B[2 * (boff + (long long)bb * d.b_sb) + part] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+  // this warp's 32 x 32 real quadrant -> shared memory, then a fixed-order sum over the K-slices
+  double* mine = red + (size_t)warp * 1024;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int row = 8 * i + r, col = 8 * j + 2 * q;
+      mine[row + 32 * col] = acc[i][j][0];
+      mine[row + 32 * (col + 1)] = acc[i][j][1];
+    }
+  __syncthreads();
+  cplx* out = d.partial + (size_t)blockIdx.x * n * np;
+  for (int idx = tid; idx < n * np; idx += blockDim.x) {
+    const int b = idx % n, bp = idx / n;
+    const int qd = (b >> 4) + qm * (bp >> 4);
+    const int lb = b & 15, lbp = bp & 15;
+    double rr = 0, ii = 0, ir = 0, ri = 0;
+    for (int sl = 0; sl < nslice; ++sl) {
+      const double* P = red + (size_t)(qd + nquad * sl) * 1024;
+      rr += P[(2 * lb) + 32 * (2 * lbp)];
+      ii += P[(2 * lb + 1) + 32 * (2 * lbp + 1)];
+      ir += P[(2 * lb + 1) + 32 * (2 * lbp)];
+      ri += P[(2 * lb) + 32 * (2 * lbp + 1)];
+    }
+    out[idx] = cmake(rr + ii, ir - ri);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_chol_inv: Cholesky factor and its inverse of a small Hermitian positive-definite Gram matrix (CholeskyQR2 step).
+// Input g holds sum_rows A[row, b] conj(A[row, b']) = conj(A^H A)[b, b'] (what the closing kernels produce); the
+// kernel factors A^H A = R^H R (R upper triangular, real positive diagonal), writes Rinv = R^-1 and accumulates
+// Rtot <- R * Rtot_prev.  A pivot below `tol` x the largest diagonal entry raises the per-matrix flag: the matrix
+// is too ill-conditioned for CholeskyQR2 and the caller falls back to Householder TSQR.
+// One CTA (64 threads) per matrix; dynamic shared memory: 2 * n * n complex.
+// ---------------------------------------------------------------------------------------------------------------
+struct CholDesc { const cplx* g; int n; cplx* rinv; cplx* rtot; int first; int* flag; double tol; };
+
+__global__ void __launch_bounds__(64) k_chol_inv(const CholDesc* __restrict__ descs) {
+  const CholDesc d = descs[blockIdx.x];
+  extern __shared__ cplx csm[];
+  const int n = d.n, tid = threadIdx.x;
+  cplx* R = csm;                   // upper triangular factor, column-major n x n
+  cplx* X = csm + (size_t)n * n;   // inverse
+  __shared__ double maxdiag;
+  __shared__ int bad;
+  for (int idx = tid; idx < n * n; idx += blockDim.x) R[idx] = cconj(d.g[idx]);       // A^H A
+  if (tid == 0) bad = 0;
+  __syncthreads();
+  if (tid == 0) { double m = 0; for (int j = 0; j < n; ++j) m = fmax(m, R[j + (size_t)j * n].x); maxdiag = m; }
+  __syncthreads();
+  // right-looking Cholesky on the upper triangle: row j of R, then the trailing update
+  for (int j = 0; j < n; ++j) {
+    double piv = R[j + (size_t)j * n].x;
+    if (!(piv > d.tol * maxdiag)) { if (tid == 0) bad = 1; piv = fmax(piv, d.tol * maxdiag); if (!(piv > 0)) piv = 1.0; }
+    const double rjj = sqrt(piv), inv = 1.0 / rjj;
+    __syncthreads();
+    for (int c = j + tid; c < n; c += blockDim.x) {
+      cplx v = R[j + (size_t)c * n];
+      R[j + (size_t)c * n] = (c == j) ? cmake(rjj, 0.0) : cscale(v, inv);
+    }
+    __syncthreads();
+    // G[i, c] -= conj(R[j, i]) * R[j, c] for j < i <= c
+    const int m = n - j - 1;
+    for (int idx = tid; idx < m * m; idx += blockDim.x) {
+      int i = j + 1 + idx % m, c = j + 1 + idx / m;
+      if (i <= c) {
+        cplx a = R[j + (size_t)i * n], b = R[j + (size_t)c * n];
+        cplx& t = R[i + (size_t)c * n];
+        t.x -= a.x * b.x + a.y * b.y;
+        t.y -= a.x * b.y - a.y * b.x;
+      }
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < n * n; idx += blockDim.x) { int i = idx % n, c = idx / n; if (i > c) R[idx] = cmake(0, 0); }
+  __syncthreads();
+  // X = R^-1 by back substitution, one column per thread: R X[:, c] = e_c
+  for (int c = tid; c < n; c += blockDim.x) {
+    for (int i = n - 1; i >= 0; --i) {
+      cplx s = cmake(i == c ? 1.0 : 0.0, 0.0);
+      for (int k = i + 1; k <= c; ++k) { cplx p = cmul(R[i + (size_t)k * n], X[k + (size_t)c * n]); s = csub(s, p); }
+      X[i + (size_t)c * n] = (i <= c) ? cscale(s, 1.0 / R[i + (size_t)i * n].x) : cmake(0, 0);
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * n; idx += blockDim.x) d.rinv[idx] = X[idx];
+  // Rtot = R (first pass) or R * Rtot_prev (second pass)
+  if (d.first) { for (int idx = tid; idx < n * n; idx += blockDim.x) d.rtot[idx] = R[idx]; }
+  else {
+    for (int idx = tid; idx < n * n; idx += blockDim.x) X[idx] = d.rtot[idx];
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+      int i = idx % n, c = idx / n;
+      cplx s = cmake(0, 0);
+      for (int k = i; k <= c; ++k) cfma(s, R[i + (size_t)k * n], X[k + (size_t)c * n]);
+      d.rtot[idx] = s;
+    }
+  }
+  if (tid == 0 && bad) *d.flag = 1;
 }

@@ -46,6 +46,8 @@ static void set_smem_attrs() {
   cudaFuncSetAttribute(k_absorb_slab<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_close_dmma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_close_dmma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_close_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   done = true;
 }
 
@@ -406,7 +408,7 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
   std::set<int> seen;
   struct SiteJob {
     int v, e, jb, d, chib; long long Po; int nc, q; std::vector<int> outer;   // outer: bond leg indices ascending
-    cplx* A; cplx* Rbuf; std::vector<cplx*> root, invroot;
+    cplx* A; cplx* Q; cplx* Rbuf; std::vector<cplx*> root, invroot;      // Q: where the thin Q factor lives (A or a CholeskyQR buffer)
   };
   std::vector<SiteJob> jobs(2 * n);
   for (int i = 0; i < n; ++i) {
@@ -469,7 +471,7 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
   }
   for (int j = 0; j < NJ; ++j) dbg_norm(c, "matricised", j, jobs[j].A, (size_t)c->site_n[jobs[j].v]);
   // ---- 3. absorb sqrt(M_k) on the outer legs, in place in the matrix layout (simple_update.jl:35-36) ----
-  auto absorb_outer = [&](bool inverse, std::vector<int>& ncols) {
+  auto absorb_outer = [&](bool inverse, std::vector<int>& ncols) {   // forward: on A (psi~); inverse: on the Q factor
     size_t maxouter = 0;
     for (SiteJob& J : jobs) maxouter = std::max(maxouter, J.outer.size());
     for (size_t s = 0; s < maxouter; ++s) {
@@ -481,28 +483,33 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
         for (size_t i = 0; i < s; ++i) Lp *= c->chi[c->inc[J.v][J.outer[i]]];
         int x = c->chi[c->inc[J.v][J.outer[s]]];
         long long R = J.Po / (Lp * x) * ncols[j];
-        ModeApplyDesc d; d.in = J.A; d.out = J.A; d.m = inverse ? J.invroot[s] : J.root[s];
+        cplx* buf = inverse ? J.Q : J.A;
+        ModeApplyDesc d; d.in = buf; d.out = buf; d.m = inverse ? J.invroot[s] : J.root[s];
         d.L = (int)Lp; d.n = x; d.np = x; d.R = (int)R; d.in_sb = Lp; d.in_sr = Lp * x; d.out_sb = Lp; d.out_sr = Lp * x;
         d.ldm = x; d.flags = inverse ? 3 : 0;      // Q * dag(M^-1/2): element (c, b) = conj(Minv[b, c])
         ma.push_back(d);
         maxtiles = std::max(maxtiles, (Lp * R + MA_BM - 1) / MA_BM);
       }
-      if (ma.empty()) continue;
-      ModeApplyDesc* dma = c->upload(ma);
-      LAUNCH(c, TNQS_KC_MODE_APPLY, k_mode_apply, dim3((unsigned)maxtiles, (unsigned)ma.size(), 1), 256, 0, dma);
+      (void)maxtiles;
+      launch_mode_apply(c, TNQS_KC_MODE_APPLY, ma);
     }
   };
   std::vector<int> ncols(NJ);
   for (int j = 0; j < NJ; ++j) ncols[j] = jobs[j].nc;
   absorb_outer(false, ncols);
   for (int j = 0; j < NJ; ++j) dbg_norm(c, "absorbed", j, jobs[j].A, (size_t)c->site_n[jobs[j].v]);
-  // ---- 4. TSQR with explicit thin Q, in place (simple_update.jl:39-40) ----
-  {
+  // ---- 4. thin QR with explicit Q (simple_update.jl:39-40) ----
+  // Tall, well-conditioned matrices: CholeskyQR2 on the tensor cores (Gram -> Cholesky -> Q = A R^-1, twice; as
+  // accurate as Householder while cond(A) < ~1e6, which the Cholesky pivots check on the device).  Everything else
+  // (short, wide, rank-deficient or ill-conditioned - the norm while bonds are still growing): Householder TSQR.
+  auto householder_qr = [&](const std::vector<int>& list) {
+    if (list.empty()) return;
+    for (int j : list) jobs[j].Q = jobs[j].A;
     std::vector<std::vector<QrLevel>> trees(NJ);
     size_t maxlev = 0;
-    for (int j = 0; j < NJ; ++j) {
+    for (int j : list) {
       SiteJob& J = jobs[j];
-      const long long hmax = std::max<long long>(8192 / J.nc, 2 * J.nc);
+      const long long hmax = 2 * J.nc;      // small blocks: many resident CTAs hide the latency of the column-by-column sweep
       QrLevel lv; lv.base = J.A; lv.ld = J.Po; lv.rows = J.Po;
       while (true) {
         long long nb = lv.rows <= hmax ? 1 : (lv.rows + hmax - 1) / hmax;
@@ -518,7 +525,7 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
     // upward sweep: factor every block, R factors stack into the next level
     for (size_t l = 0; l < maxlev; ++l) {
       std::vector<QrDesc> qd; size_t smem = 0;
-      for (int j = 0; j < NJ; ++j) {
+      for (int j : list) {
         if (l >= trees[j].size()) continue;
         SiteJob& J = jobs[j]; QrLevel& lv = trees[j][l];
         bool top = l + 1 == trees[j].size();
@@ -538,7 +545,7 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
     // downward sweep: Q_block <- Q_block * (its nc x nc slice of the parent's explicit Q)
     for (int l = (int)maxlev - 2; l >= 0; --l) {
       std::vector<ModeApplyDesc> ma; long long maxtiles = 1;
-      for (int j = 0; j < NJ; ++j) {
+      for (int j : list) {
         if ((size_t)l + 1 >= trees[j].size()) continue;
         SiteJob& J = jobs[j]; QrLevel& lv = trees[j][l]; QrLevel& up = trees[j][l + 1];
         size_t nb = lv.blk_begin.size() - 1;
@@ -551,12 +558,64 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
           maxtiles = std::max(maxtiles, ((long long)d.L + MA_BM - 1) / MA_BM);
         }
       }
-      if (ma.empty()) continue;
-      ModeApplyDesc* dma = c->upload(ma);
-      LAUNCH(c, TNQS_KC_QR, k_mode_apply, dim3((unsigned)maxtiles, (unsigned)ma.size(), 1), 256, 0, dma);
+      (void)maxtiles;
+      launch_mode_apply(c, TNQS_KC_QR, ma);
     }
+  };
+  {
+    std::vector<int> chol_list, house_list;
+    static int no_chol = -1;
+    if (no_chol < 0) { const char* e = getenv("TNQS_NO_CHOLQR"); no_chol = (e && e[0] == '1') ? 1 : 0; }
+    for (int j = 0; j < NJ; ++j) {
+      SiteJob& J = jobs[j];
+      if (!no_chol && !dmma_disabled() && J.nc <= 32 && J.Po >= 4 * (long long)J.nc) chol_list.push_back(j); else house_list.push_back(j);
+    }
+    if (!chol_list.empty()) {
+      const int nj = (int)chol_list.size();
+      int* d_flag = c->talloc<int>(nj);
+      CU(cudaMemsetAsync(d_flag, 0, nj * sizeof(int), c->stream));
+      std::vector<cplx*> Qb(nj), G(nj), Rinv(nj), part(nj);
+      int nsplit = std::max(1, std::min(16, (4 * c->num_sms + nj - 1) / nj));
+      for (int i = 0; i < nj; ++i) {
+        SiteJob& J = jobs[chol_list[i]];
+        Qb[i] = c->talloc<cplx>((size_t)J.Po * J.nc); G[i] = c->talloc<cplx>((size_t)J.nc * J.nc);
+        Rinv[i] = c->talloc<cplx>((size_t)J.nc * J.nc); part[i] = c->talloc<cplx>((size_t)nsplit * J.nc * J.nc);
+      }
+      for (int pass = 0; pass < 2; ++pass) {
+        std::vector<ModeCloseDesc> mc(nj); std::vector<CloseReduceDesc> rd(nj); std::vector<CholDesc> cd(nj); std::vector<ModeApplyDesc> ma(nj);
+        size_t maxnn = 1; int maxn = 1;
+        for (int i = 0; i < nj; ++i) {
+          SiteJob& J = jobs[chol_list[i]];
+          const cplx* src = pass == 0 ? J.A : Qb[i];
+          int ns = (int)std::min<long long>(nsplit, std::max<long long>(1, J.Po / 256));
+          ModeCloseDesc& m = mc[i];
+          m.a = src; m.b = src; m.partial = part[i]; m.L = (int)J.Po; m.R = 1; m.n = J.nc; m.np = J.nc;
+          m.a_sb = J.Po; m.a_sr = 0; m.b_sb = J.Po; m.b_sr = 0; m.nsplit = ns; m.rows_per_split = ((J.Po + ns - 1) / ns + 3) / 4 * 4;
+          CloseReduceDesc& r = rd[i];
+          r.partial = part[i]; r.nsplit = ns; r.n = J.nc; r.np = J.nc; r.dst = G[i]; r.prev = nullptr; r.diff = nullptr; r.mode = 0; r.normalize = 0; r.hermitize = 0;
+          CholDesc& k = cd[i];
+          k.g = G[i]; k.n = J.nc; k.rinv = Rinv[i]; k.rtot = J.Rbuf; k.first = pass == 0; k.flag = d_flag + i; k.tol = 1e-11;
+          ModeApplyDesc& a = ma[i];
+          a.in = src; a.out = Qb[i]; a.m = Rinv[i]; a.L = (int)J.Po; a.n = J.nc; a.np = J.nc; a.R = 1;
+          a.in_sb = J.Po; a.in_sr = 0; a.out_sb = J.Po; a.out_sr = 0; a.ldm = J.nc; a.flags = 0;
+          maxnn = std::max(maxnn, (size_t)J.nc * J.nc); maxn = std::max(maxn, J.nc);
+        }
+        ModeCloseDesc* dmc = c->upload(mc);
+        LAUNCH(c, TNQS_KC_QR, k_close_leg_dmma, dim3(nsplit, nj), 256, 8 * 1024 * sizeof(double), dmc);
+        CloseReduceDesc* drd = c->upload(rd);
+        LAUNCH(c, TNQS_KC_QR, k_close_reduce, nj, 256, maxnn * sizeof(cplx), drd);
+        CholDesc* dcd = c->upload(cd);
+        LAUNCH(c, TNQS_KC_QR, k_chol_inv, nj, 64, 2 * (size_t)maxn * maxn * sizeof(cplx), dcd);
+        launch_mode_apply(c, TNQS_KC_QR, ma);
+      }
+      std::vector<int> flags(nj);
+      CU(cudaMemcpyAsync(flags.data(), d_flag, nj * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      c->sync();
+      for (int i = 0; i < nj; ++i) { if (flags[i]) house_list.push_back(chol_list[i]); else jobs[chol_list[i]].Q = Qb[i]; }
+    }
+    householder_qr(house_list);
   }
-  for (int j = 0; j < NJ; ++j) { dbg_norm(c, "Q", j, jobs[j].A, (size_t)jobs[j].Po * jobs[j].q); dbg_norm(c, "R", j, jobs[j].Rbuf, (size_t)jobs[j].q * jobs[j].nc); }
+  for (int j = 0; j < NJ; ++j) { dbg_norm(c, "Q", j, jobs[j].Q, (size_t)jobs[j].Po * jobs[j].q); dbg_norm(c, "R", j, jobs[j].Rbuf, (size_t)jobs[j].q * jobs[j].nc); }
   // ---- 5. theta = R1 R2 over the bond, gate (simple_update.jl:43) ----
   std::vector<ThetaDesc> td(n); std::vector<SvdDesc> sv(n);
   int* d_rank = c->talloc<int>(n); double* d_err = c->talloc<double>(n); double* d_sv = c->talloc<double>((size_t)n * cap);
@@ -617,13 +676,13 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
       SiteJob& J = jobs[j]; int r = ranks[j / 2];
       Tm[j] = c->talloc<cplx>((size_t)J.Po * J.d * r);
       ModeApplyDesc& d = ma[j];
-      d.in = J.A; d.out = Tm[j]; d.m = (j & 1) ? r2n[j / 2] : r1n[j / 2];
+      d.in = J.Q; d.out = Tm[j]; d.m = (j & 1) ? r2n[j / 2] : r1n[j / 2];
       d.L = (int)J.Po; d.n = J.q; d.np = J.d * r; d.R = 1; d.in_sb = J.Po; d.in_sr = 0; d.out_sb = J.Po; d.out_sr = 0;
       d.ldm = J.q; d.flags = 0;
       maxtiles = std::max(maxtiles, (J.Po + MA_BM - 1) / MA_BM); maxcol = std::max(maxcol, (d.np + MA_BN - 1) / MA_BN);
     }
-    ModeApplyDesc* dma = c->upload(ma);
-    LAUNCH(c, TNQS_KC_MODE_APPLY, k_mode_apply, dim3((unsigned)maxtiles, NJ, maxcol), 256, 0, dma);
+    (void)maxtiles; (void)maxcol;
+    launch_mode_apply(c, TNQS_KC_MODE_APPLY, ma);
   }
   double* d_n2 = c->talloc<double>(NJ);
   if (o.normalize_tensors) {
@@ -963,8 +1022,8 @@ extern "C" int32_t tnqs_symmetric_gauge(tnqs_ctx* c, double regularization) {
         ma.push_back(d); touched.push_back(v);
         maxtiles = std::max(maxtiles, (Lp * R + MA_BM - 1) / MA_BM);
       }
-      ModeApplyDesc* dma = c->upload(ma);
-      LAUNCH(c, TNQS_KC_MODE_APPLY, k_mode_apply, dim3((unsigned)maxtiles, (unsigned)ma.size(), 1), 256, 0, dma);
+      (void)maxtiles;
+      launch_mode_apply(c, TNQS_KC_MODE_APPLY, ma);
       for (int v : touched) std::swap(c->site[v], other[v]);
     }
     for (int v = 0; v < c->nv; ++v) c->dfree(other[v]);
