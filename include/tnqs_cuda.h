@@ -123,6 +123,16 @@ int32_t tnqs_apply_1site(tnqs_ctx* ctx, int32_t n, const int32_t* v, const doubl
 int32_t tnqs_apply_2site(tnqs_ctx* ctx, int32_t n, const int32_t* e, const int32_t* flip,
                          const double* gates /* n*d^4 cplx */, const tnqs_apply_opts* opts,
                          int32_t* ranks, double* truncerr, double* svals);
+/* Two-stage form of tnqs_apply_2site for vertex-partitioned runs.  `remote[i]` = 0 (both vertices
+ * local), 1 (the gate's first vertex lives on another rank) or 2 (the second one does).  _begin runs everything that needs
+ * one site only (message roots, absorption, QR) and exposes a device buffer with the local R factors of the n_cut
+ * cut-crossing gates (batch order; slot_complex ComplexF64 per slot: a (q, nc) header, then R).  The host exchanges the slots
+ * with the partner ranks (NCCL) and passes the received buffer (same order and layout) to _end, which runs the identical
+ * theta / SVD / truncation on both sides and finishes the local halves.  No other call may touch the handle in between. */
+int32_t tnqs_apply_2site_begin(tnqs_ctx* ctx, int32_t n, const int32_t* e, const int32_t* flip, const double* gates,
+                               const tnqs_apply_opts* opts, const int32_t* remote, void** send_buf, int64_t* n_cut,
+                               int64_t* slot_complex);
+int32_t tnqs_apply_2site_end(tnqs_ctx* ctx, const void* recv_buf, int32_t* ranks, double* truncerr, double* svals);
 /* replaces: apply_gates(circuit, bpc; apply_kwargs, bp_update_kwargs, update_cache)
  * (src/Apply/apply_gates.jl:42-92): ordered gate list, BP refresh before a 2-site gate that touches a vertex
  * touched since the last refresh (1-site gates mark vertices too, :84), final refresh if update_cache.

@@ -50,6 +50,7 @@ struct tnqs_ctx {
   double prof_ms[TNQS_KC_COUNT] = {0};
   long long prof_launches[TNQS_KC_COUNT] = {0};
   std::vector<void*> temp;                         // stream-ordered temporaries of the current call
+  void* pending_gate = nullptr;                    // GateBatch between tnqs_apply_2site_begin and _end
 
   // ---- graph helpers ----
   int other(int e, int v) const { return esrc[e] == v ? edst[e] : esrc[e]; }
@@ -219,14 +220,14 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
     }
     if (!cur.empty()) subsets[L].push_back(cur);
     for (auto& sub : subsets[L]) {
-      int target = std::max(1, (4 * c->num_sms + (int)sub.size() - 1) / (int)sub.size());
+      // split-K factor depends on the tensor only (never on the batch), so a message is computed bit-identically whatever
+      // else shares its launch: partitioned (multi-GPU) JACOBI sweeps reproduce the single-GPU result exactly.
       size_t part = 0;
       for (int i : sub) {
         const Chain& ch = chains[i];
         int n = ch.close_leg < 0 ? c->d[ch.v] : c->chi[c->inc[ch.v][ch.close_leg]];
         long long rows = c->site_n[ch.v] / n;
-        int ns = (int)std::min<long long>(std::min(target, 64), std::max<long long>(1, rows / 128));
-        if (fast_path_N(c, ch)) ns = (int)std::min<long long>(std::min(target, 32), std::max<long long>(1, rows / 128));   // >= 64 k-steps per CTA
+        int ns = (int)std::min<long long>(16, std::max<long long>(1, rows / 512));
         mem[L][i].nsplit = std::max(1, ns);
         mem[L][i].partial_elems = (size_t)mem[L][i].nsplit * n * n;
         part += mem[L][i].partial_elems;

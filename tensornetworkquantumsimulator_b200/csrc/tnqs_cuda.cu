@@ -398,85 +398,54 @@ static void dbg_norm(tnqs_ctx* c, const char* name, int idx, const cplx* p, size
   }
 }
 
+
 // Plan of the TSQR tree of one matrix (Po x nc, column-major, ld = Po), see DESIGN.md "QR".
 struct QrLevel { cplx* base; long long ld; long long rows; std::vector<long long> blk_begin; };   // blocks = row ranges
 
-static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_t* flips, const double* gates,
-                             const tnqs_apply_opts& o, int32_t* ranks_out, double* err_out, double* svals_out) {
-  if (n == 0) return;
-  const int cap = c->chi_cap;
-  std::set<int> seen;
+// pack / unpack the R factors of cut-crossing gates: slot = [ (q, nc) header | R (q x nc, ld = q) ]
+struct XchgDesc { cplx* slot; cplx* r; int q, nc; };
+__global__ void k_xchg_pack(const XchgDesc* __restrict__ descs) {
+  const XchgDesc d = descs[blockIdx.x];
+  if (threadIdx.x == 0) d.slot[0] = cmake((double)d.q, (double)d.nc);
+  for (int i = threadIdx.x; i < d.q * d.nc; i += blockDim.x) d.slot[1 + i] = d.r[i];
+}
+__global__ void k_xchg_headers(const cplx* buf, long long slot, int n, cplx* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = buf[(size_t)i * slot];
+}
+__global__ void k_xchg_unpack(const XchgDesc* __restrict__ descs) {
+  const XchgDesc d = descs[blockIdx.x];
+  for (int i = threadIdx.x; i < d.q * d.nc; i += blockDim.x) d.r[i] = d.slot[1 + i];
+}
+
+// One vertex-disjoint batch of two-site gates (simple update).  stage1 = roots, matricise, absorb, QR (everything that
+// needs only one site); stage2 = theta, gate, SVD + truncation, reabsorb, T' = Q R', normalise, commit.  Between the two
+// a vertex-partitioned run exchanges the R factors of gates that cross a cut (`remote`), so each side finishes its own
+// half with an identical, deterministic theta/SVD.  All temporaries live until stage2 returns.
+struct GateBatch {
   struct SiteJob {
     int v, e, jb, d, chib; long long Po; int nc, q; std::vector<int> outer;   // outer: bond leg indices ascending
-    cplx* A; cplx* Q; cplx* Rbuf; std::vector<cplx*> root, invroot;      // Q: where the thin Q factor lives (A or a CholeskyQR buffer)
+    cplx* A; cplx* Q; cplx* Rbuf; std::vector<cplx*> root, invroot;             // Q: where the thin Q factor lives
+    bool remote;
   };
-  std::vector<SiteJob> jobs(2 * n);
-  for (int i = 0; i < n; ++i) {
-    int e = es[i];
-    REQUIRE(e >= 0 && e < c->ne, TNQS_ERR_INVALID_ARG, "tnqs_apply_2site: edge out of range");
-    int v1 = flips && flips[i] ? c->edst[e] : c->esrc[e], v2 = c->other(e, v1);
-    REQUIRE(seen.insert(v1).second && seen.insert(v2).second, TNQS_ERR_OVERLAPPING_BATCH,
-            "tnqs_apply_2site: gates of a batch share a vertex");
-    REQUIRE(c->d[v1] == c->d[v2], TNQS_ERR_UNSUPPORTED, "two-site gate on sites of different dimension");
-    for (int s = 0; s < 2; ++s) {
-      SiteJob& J = jobs[2 * i + s];
-      J.v = s == 0 ? v1 : v2; J.e = e; J.jb = c->leg(J.v, e); J.d = c->d[J.v]; J.chib = c->chi[e];
-      J.Po = 1;
-      for (size_t j = 0; j < c->inc[J.v].size(); ++j) if ((int)j != J.jb) { J.outer.push_back((int)j); J.Po *= c->chi[c->inc[J.v][j]]; }
-      J.nc = J.d * J.chib; J.q = (int)std::min<long long>(J.Po, J.nc);
-      REQUIRE(J.nc <= 64, TNQS_ERR_UNSUPPORTED, "d * chi > 64 is not supported by the two-site gate path");
-    }
-  }
-  const int NJ = 2 * n;
-  // ---- 1. sqrt / inverse sqrt of the incoming messages (src/utils.jl:18-26) ----
-  std::vector<EighDesc> eg;
-  int maxchi = 1;
-  for (SiteJob& J : jobs)
-    for (int j : J.outer) {
-      int ee = c->inc[J.v][j], u = c->other(ee, J.v), x = c->chi[ee];
-      EighDesc d; d.m = c->msg(c->dedge(u, ee)); d.n = x; d.ldm = x;
-      d.root = c->talloc<cplx>((size_t)x * x); d.invroot = c->talloc<cplx>((size_t)x * x);
-      d.cutoff = 10 * TNQS_EPS; d.shift = 0; d.mode = 0;
-      J.root.push_back(d.root); J.invroot.push_back(d.invroot);
-      eg.push_back(d); maxchi = std::max(maxchi, x);
-    }
-  if (!eg.empty()) {
-    EighDesc* deg = c->upload(eg);
-    int threads = 32 * std::max(1, std::min(32, (maxchi + 1) / 2));
-    size_t smem = (size_t)2 * maxchi * maxchi * sizeof(cplx) + 3 * maxchi * sizeof(double);
-    LAUNCH(c, TNQS_KC_EIGH, k_eigh_sqrt, (unsigned)eg.size(), threads, smem, deg, c->d_status);
-  }
-  // ---- 2. matricise: A[outer.., (s, b)] ----
-  std::vector<PermDesc> pd(NJ);
-  long long maxtot = 1;
-  for (int j = 0; j < NJ; ++j) {
-    SiteJob& J = jobs[j];
-    J.A = c->talloc<cplx>((size_t)c->site_n[J.v]);
-    J.Rbuf = c->talloc<cplx>((size_t)J.nc * J.nc);
-    PermDesc& p = pd[j];
-    p.src = c->site[J.v]; p.dst = J.A; p.d = J.d; p.chib = J.chib; p.nouter = (int)J.outer.size();
-    long long stride = J.d;
-    for (size_t l = 0, oi = 0; l < c->inc[J.v].size(); ++l) {
-      int x = c->chi[c->inc[J.v][l]];
-      if ((int)l == J.jb) p.bstride = stride; else { p.odim[oi] = x; p.ostride[oi] = stride; ++oi; }
-      stride *= x;
-    }
-    p.Po = J.Po; p.to_matrix = 1; p.norm2 = nullptr;
-    maxtot = std::max(maxtot, (long long)c->site_n[J.v]);
-  }
-  {
-    PermDesc* dpd = c->upload(pd);
-    unsigned gx = (unsigned)std::min<long long>((maxtot + 255) / 256, 2048);
-    LAUNCH(c, TNQS_KC_PERMUTE, k_permute, dim3(gx, NJ), 256, 0, dpd);
-  }
-  for (int j = 0; j < NJ; ++j) dbg_norm(c, "matricised", j, jobs[j].A, (size_t)c->site_n[jobs[j].v]);
-  // ---- 3. absorb sqrt(M_k) on the outer legs, in place in the matrix layout (simple_update.jl:35-36) ----
-  auto absorb_outer = [&](bool inverse, std::vector<int>& ncols) {   // forward: on A (psi~); inverse: on the Q factor
+  tnqs_ctx* c; int n = 0, NJ = 0, cap = 1; tnqs_apply_opts o;
+  std::vector<int> es; std::vector<cplx> hgates; std::vector<SiteJob> jobs; std::vector<int> LJ;
+  std::vector<PermDesc> pd; std::vector<int> ncols;
+  std::vector<ThetaDesc> td; std::vector<SvdDesc> sv;
+  int* d_rank = nullptr; double* d_err = nullptr; double* d_sv = nullptr;
+  std::vector<int> cut;                 // gate indices that have a remote vertex, in batch order
+  cplx* xsend = nullptr; long long xslot = 0;
+  void absorb_outer(bool inverse);
+  void stage1(int n_, const int32_t* es_, const int32_t* flips, const double* gates, const tnqs_apply_opts& o_, const int32_t* remote);
+  void stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, double* svals_out);
+};
+
+void GateBatch::absorb_outer(bool inverse) {   // forward: on A (psi~); inverse: on the Q factor
     size_t maxouter = 0;
-    for (SiteJob& J : jobs) maxouter = std::max(maxouter, J.outer.size());
+    for (int jj : LJ) { SiteJob& J = jobs[jj]; maxouter = std::max(maxouter, J.outer.size()); }
     for (size_t s = 0; s < maxouter; ++s) {
       std::vector<ModeApplyDesc> ma; long long maxtiles = 1;
-      for (int j = 0; j < NJ; ++j) {
+      for (int j : LJ) {
         SiteJob& J = jobs[j];
         if (s >= J.outer.size()) continue;
         long long Lp = 1;
@@ -493,11 +462,86 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
       (void)maxtiles;
       launch_mode_apply(c, TNQS_KC_MODE_APPLY, ma);
     }
-  };
-  std::vector<int> ncols(NJ);
+}
+
+void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const double* gates, const tnqs_apply_opts& o_, const int32_t* remote) {
+  n = n_; o = o_; cap = c->chi_cap; NJ = 2 * n;
+  es.assign(es_, es_ + n);
+  std::set<int> seen;
+  jobs.assign(NJ, SiteJob());
+  size_t goff = 0;
+  for (int i = 0; i < n; ++i) {
+    int e = es[i];
+    REQUIRE(e >= 0 && e < c->ne, TNQS_ERR_INVALID_ARG, "tnqs_apply_2site: edge out of range");
+    int v1 = flips && flips[i] ? c->edst[e] : c->esrc[e], v2 = c->other(e, v1);
+    REQUIRE(seen.insert(v1).second && seen.insert(v2).second, TNQS_ERR_OVERLAPPING_BATCH,
+            "tnqs_apply_2site: gates of a batch share a vertex");
+    REQUIRE(c->d[v1] == c->d[v2], TNQS_ERR_UNSUPPORTED, "two-site gate on sites of different dimension");
+    int rm = remote ? remote[i] : 0;
+    REQUIRE(rm >= 0 && rm <= 2, TNQS_ERR_INVALID_ARG, "remote flag must be 0, 1 or 2");
+    if (rm) cut.push_back(i);
+    for (int s = 0; s < 2; ++s) {
+      SiteJob& J = jobs[2 * i + s];
+      J.v = s == 0 ? v1 : v2; J.e = e; J.jb = c->leg(J.v, e); J.d = c->d[J.v]; J.chib = c->chi[e];
+      J.remote = rm == s + 1; J.A = J.Q = J.Rbuf = nullptr;
+      J.Po = 1;
+      for (size_t j = 0; j < c->inc[J.v].size(); ++j) if ((int)j != J.jb) { J.outer.push_back((int)j); J.Po *= c->chi[c->inc[J.v][j]]; }
+      J.nc = J.d * J.chib; J.q = (int)std::min<long long>(J.Po, J.nc);
+      REQUIRE(J.nc <= 64, TNQS_ERR_UNSUPPORTED, "d * chi > 64 is not supported by the two-site gate path");
+      if (J.remote) { J.outer.clear(); J.Rbuf = c->talloc<cplx>((size_t)J.nc * J.nc); } else LJ.push_back(2 * i + s);
+    }
+    int d4 = c->d[v1] * c->d[v1] * c->d[v1] * c->d[v1];
+    const cplx* g = (const cplx*)gates + goff; goff += d4;
+    hgates.insert(hgates.end(), g, g + d4);
+  }
+  // ---- 1. sqrt / inverse sqrt of the incoming messages (src/utils.jl:18-26) ----
+  std::vector<EighDesc> eg;
+  int maxchi = 1;
+  for (int jj : LJ) { SiteJob& J = jobs[jj];
+    for (int j : J.outer) {
+      int ee = c->inc[J.v][j], u = c->other(ee, J.v), x = c->chi[ee];
+      EighDesc d; d.m = c->msg(c->dedge(u, ee)); d.n = x; d.ldm = x;
+      d.root = c->talloc<cplx>((size_t)x * x); d.invroot = c->talloc<cplx>((size_t)x * x);
+      d.cutoff = 10 * TNQS_EPS; d.shift = 0; d.mode = 0;
+      J.root.push_back(d.root); J.invroot.push_back(d.invroot);
+      eg.push_back(d); maxchi = std::max(maxchi, x);
+    } }
+  if (!eg.empty()) {
+    EighDesc* deg = c->upload(eg);
+    int threads = 32 * std::max(1, std::min(32, (maxchi + 1) / 2));
+    size_t smem = (size_t)2 * maxchi * maxchi * sizeof(cplx) + 3 * maxchi * sizeof(double);
+    LAUNCH(c, TNQS_KC_EIGH, k_eigh_sqrt, (unsigned)eg.size(), threads, smem, deg, c->d_status);
+  }
+  // ---- 2. matricise: A[outer.., (s, b)] ----
+  pd.assign(NJ, PermDesc());
+  long long maxtot = 1;
+  for (int j : LJ) {
+    SiteJob& J = jobs[j];
+    J.A = c->talloc<cplx>((size_t)c->site_n[J.v]);
+    J.Rbuf = c->talloc<cplx>((size_t)J.nc * J.nc);
+    PermDesc& p = pd[j];
+    p.src = c->site[J.v]; p.dst = J.A; p.d = J.d; p.chib = J.chib; p.nouter = (int)J.outer.size();
+    long long stride = J.d;
+    for (size_t l = 0, oi = 0; l < c->inc[J.v].size(); ++l) {
+      int x = c->chi[c->inc[J.v][l]];
+      if ((int)l == J.jb) p.bstride = stride; else { p.odim[oi] = x; p.ostride[oi] = stride; ++oi; }
+      stride *= x;
+    }
+    p.Po = J.Po; p.to_matrix = 1; p.norm2 = nullptr;
+    maxtot = std::max(maxtot, (long long)c->site_n[J.v]);
+  }
+  {
+    std::vector<PermDesc> lp; for (int j : LJ) lp.push_back(pd[j]);
+    PermDesc* dpd = c->upload(lp);
+    unsigned gx = (unsigned)std::min<long long>((maxtot + 255) / 256, 2048);
+    if (!lp.empty()) LAUNCH(c, TNQS_KC_PERMUTE, k_permute, dim3(gx, (unsigned)lp.size()), 256, 0, dpd);
+  }
+  for (int j : LJ) dbg_norm(c, "matricised", j, jobs[j].A, (size_t)c->site_n[jobs[j].v]);
+  // ---- 3. absorb sqrt(M_k) on the outer legs, in place in the matrix layout (simple_update.jl:35-36) ----
+  ncols.assign(NJ, 0);
   for (int j = 0; j < NJ; ++j) ncols[j] = jobs[j].nc;
-  absorb_outer(false, ncols);
-  for (int j = 0; j < NJ; ++j) dbg_norm(c, "absorbed", j, jobs[j].A, (size_t)c->site_n[jobs[j].v]);
+  absorb_outer(false);
+  for (int j : LJ) dbg_norm(c, "absorbed", j, jobs[j].A, (size_t)c->site_n[jobs[j].v]);
   // ---- 4. thin QR with explicit Q (simple_update.jl:39-40) ----
   // Tall, well-conditioned matrices: CholeskyQR2 on the tensor cores (Gram -> Cholesky -> Q = A R^-1, twice; as
   // accurate as Householder while cond(A) < ~1e6, which the Cholesky pivots check on the device).  Everything else
@@ -566,7 +610,7 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
     std::vector<int> chol_list, house_list;
     static int no_chol = -1;
     if (no_chol < 0) { const char* e = getenv("TNQS_NO_CHOLQR"); no_chol = (e && e[0] == '1') ? 1 : 0; }
-    for (int j = 0; j < NJ; ++j) {
+    for (int j : LJ) {
       SiteJob& J = jobs[j];
       if (!no_chol && !dmma_disabled() && J.nc <= 32 && J.Po >= 4 * (long long)J.nc) chol_list.push_back(j); else house_list.push_back(j);
     }
@@ -615,10 +659,45 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
     }
     householder_qr(house_list);
   }
-  for (int j = 0; j < NJ; ++j) { dbg_norm(c, "Q", j, jobs[j].Q, (size_t)jobs[j].Po * jobs[j].q); dbg_norm(c, "R", j, jobs[j].Rbuf, (size_t)jobs[j].q * jobs[j].nc); }
+
+  for (int j : LJ) { dbg_norm(c, "Q", j, jobs[j].Q, (size_t)jobs[j].Po * jobs[j].q); dbg_norm(c, "R", j, jobs[j].Rbuf, (size_t)jobs[j].q * jobs[j].nc); }
+  // R factors of the cut-crossing gates -> exchange buffer
+  if (!cut.empty()) {
+    int ncmax = 1; for (const SiteJob& J : jobs) ncmax = std::max(ncmax, J.nc);
+    xslot = 1 + (long long)ncmax * ncmax;
+    xsend = c->talloc<cplx>((size_t)cut.size() * xslot);
+    std::vector<XchgDesc> xd;
+    for (size_t i = 0; i < cut.size(); ++i) {
+      const SiteJob& J = jobs[2 * cut[i]].remote ? jobs[2 * cut[i] + 1] : jobs[2 * cut[i]];
+      XchgDesc x; x.slot = xsend + i * xslot; x.r = J.Rbuf; x.q = J.q; x.nc = J.nc; xd.push_back(x);
+    }
+    XchgDesc* dxd = c->upload(xd);
+    LAUNCH(c, TNQS_KC_MISC, k_xchg_pack, (unsigned)xd.size(), 256, 0, dxd);
+  }
+}
+
+void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, double* svals_out) {
+  if (!cut.empty()) {
+    REQUIRE(xrecv, TNQS_ERR_INVALID_ARG, "tnqs_apply_2site_end: the batch has remote halves but no receive buffer was given");
+    std::vector<cplx> hdr(cut.size());
+    cplx* d_hdr = c->talloc<cplx>(cut.size());
+    LAUNCH(c, TNQS_KC_MISC, k_xchg_headers, (unsigned)((cut.size() + 127) / 128), 128, 0, xrecv, xslot, (int)cut.size(), d_hdr);
+    CU(cudaMemcpyAsync(hdr.data(), d_hdr, cut.size() * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    std::vector<XchgDesc> xd;
+    for (size_t i = 0; i < cut.size(); ++i) {
+      SiteJob& J = jobs[2 * cut[i]].remote ? jobs[2 * cut[i]] : jobs[2 * cut[i] + 1];
+      int q = (int)hdr[i].x, nc = (int)hdr[i].y;
+      REQUIRE(nc == J.nc && q >= 1 && q <= nc, TNQS_ERR_SHAPE, "remote R factor does not match the gate bond");
+      J.q = q;
+      XchgDesc x; x.slot = const_cast<cplx*>(xrecv) + i * xslot; x.r = J.Rbuf; x.q = q; x.nc = nc; xd.push_back(x);
+    }
+    XchgDesc* dxd = c->upload(xd);
+    LAUNCH(c, TNQS_KC_MISC, k_xchg_unpack, (unsigned)xd.size(), 256, 0, dxd);
+  }
   // ---- 5. theta = R1 R2 over the bond, gate (simple_update.jl:43) ----
-  std::vector<ThetaDesc> td(n); std::vector<SvdDesc> sv(n);
-  int* d_rank = c->talloc<int>(n); double* d_err = c->talloc<double>(n); double* d_sv = c->talloc<double>((size_t)n * cap);
+  td.assign(n, ThetaDesc()); sv.assign(n, SvdDesc());
+  d_rank = c->talloc<int>(n); d_err = c->talloc<double>(n); d_sv = c->talloc<double>((size_t)n * cap);
   cplx* d_gates = c->talloc<cplx>((size_t)n * 256);
   std::vector<cplx*> r1n(n), r2n(n);
   size_t svd_smem_wv = 0; int svd_maxn = 2; bool any_global = false;
@@ -627,7 +706,7 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
     for (int i = 0; i < n; ++i) {
       SiteJob& A = jobs[2 * i]; SiteJob& B = jobs[2 * i + 1];
       int d = A.d, d4 = d * d * d * d;
-      const cplx* g = (const cplx*)gates + goff; goff += d4;
+      const cplx* g = hgates.data() + goff; goff += d4;
       size_t hoff = hg.size(); hg.insert(hg.end(), g, g + d4);
       ThetaDesc& t = td[i];
       t.r1 = A.Rbuf; t.q1 = A.q; t.ld1 = A.q; t.r2 = B.Rbuf; t.q2 = B.q; t.ld2 = B.q; t.gate = d_gates + hoff; t.d = d; t.chi = A.chib;
@@ -667,15 +746,15 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
   if (st & ST_RANK_CAP) throw TnqsError(TNQS_ERR_SHAPE, "kept rank exceeds chi_cap (raise chi_cap or set maxdim)");
   // ---- 7. Q <- Q * dag(M^-1/2) on the outer legs (simple_update.jl:55-56) ----
   for (int j = 0; j < NJ; ++j) ncols[j] = jobs[j].q;
-  absorb_outer(true, ncols);
+  absorb_outer(true);
   // ---- 8. T' = Q R' (simple_update.jl:57), normalise, back to the canonical layout ----
   std::vector<cplx*> Tm(NJ), newsite(NJ);
   {
-    std::vector<ModeApplyDesc> ma(NJ); long long maxtiles = 1; int maxcol = 1;
-    for (int j = 0; j < NJ; ++j) {
+    std::vector<ModeApplyDesc> ma; long long maxtiles = 1; int maxcol = 1;
+    for (int j : LJ) {
       SiteJob& J = jobs[j]; int r = ranks[j / 2];
       Tm[j] = c->talloc<cplx>((size_t)J.Po * J.d * r);
-      ModeApplyDesc& d = ma[j];
+      ma.emplace_back(); ModeApplyDesc& d = ma.back();
       d.in = J.Q; d.out = Tm[j]; d.m = (j & 1) ? r2n[j / 2] : r1n[j / 2];
       d.L = (int)J.Po; d.n = J.q; d.np = J.d * r; d.R = 1; d.in_sb = J.Po; d.in_sr = 0; d.out_sb = J.Po; d.out_sr = 0;
       d.ldm = J.q; d.flags = 0;
@@ -686,14 +765,14 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
   }
   double* d_n2 = c->talloc<double>(NJ);
   if (o.normalize_tensors) {
-    std::vector<Norm2Desc> nd(NJ);
-    for (int j = 0; j < NJ; ++j) { nd[j].x = Tm[j]; nd[j].n = jobs[j].Po * jobs[j].d * ranks[j / 2]; nd[j].out = d_n2 + j; nd[j].partial = nullptr; nd[j].npartial = 0; }
+    std::vector<Norm2Desc> nd;
+    for (int j : LJ) { Norm2Desc x; x.x = Tm[j]; x.n = jobs[j].Po * jobs[j].d * ranks[j / 2]; x.out = d_n2 + j; x.partial = nullptr; x.npartial = 0; nd.push_back(x); }
     Norm2Desc* dnd = c->upload(nd);
-    LAUNCH(c, TNQS_KC_MISC, k_norm2, NJ, 1024, 0, dnd);
+    if (!nd.empty()) LAUNCH(c, TNQS_KC_MISC, k_norm2, (unsigned)nd.size(), 1024, 0, dnd);
   }
   {
     long long maxtot2 = 1;
-    for (int j = 0; j < NJ; ++j) {
+    for (int j : LJ) {
       SiteJob& J = jobs[j]; int r = ranks[j / 2];
       long long tot = J.Po * J.d * r;
       newsite[j] = (cplx*)c->dalloc((size_t)tot * sizeof(cplx));
@@ -707,26 +786,43 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
       }
       maxtot2 = std::max(maxtot2, tot);
     }
-    PermDesc* dpd = c->upload(pd);
+    std::vector<PermDesc> lp; for (int j : LJ) lp.push_back(pd[j]);
+    PermDesc* dpd = c->upload(lp);
     unsigned gx = (unsigned)std::min<long long>((maxtot2 + 255) / 256, 2048);
-    LAUNCH(c, TNQS_KC_PERMUTE, k_permute, dim3(gx, NJ), 256, 0, dpd);
+    if (!lp.empty()) LAUNCH(c, TNQS_KC_PERMUTE, k_permute, dim3(gx, (unsigned)lp.size()), 256, 0, dpd);
   }
   // ---- 9. commit: bond dimensions, site pointers, messages <- diag(S) (apply_gates.jl:105-119) ----
   for (int i = 0; i < n; ++i) c->chi[es[i]] = ranks[i];
   upload_chi(c);
-  for (int j = 0; j < NJ; ++j) {
+  for (int j : LJ) {
     c->dfree(c->site[jobs[j].v]); c->site[jobs[j].v] = newsite[j];
     c->site_n[jobs[j].v] = jobs[j].Po * jobs[j].d * ranks[j / 2];
   }
+  for (int j = 0; j < NJ; ++j) {                      // ghost placeholders follow the new bond dimension
+    if (!jobs[j].remote) continue;
+    int v = jobs[j].v;
+    c->dfree(c->site[v]); c->site_n[v] = c->site_elems(v);
+    c->site[v] = (cplx*)c->dalloc((size_t)c->site_n[v] * sizeof(cplx));
+    CU(cudaMemsetAsync(c->site[v], 0, (size_t)c->site_n[v] * sizeof(cplx), c->stream));
+  }
   {
-    std::vector<int> ks(es, es + n);
+    std::vector<int> ks(es.begin(), es.end());
     int* dks = c->upload(ks);
     LAUNCH(c, TNQS_KC_MISC, k_msg_diag, n, 128, 0, c->msg_cur, c->slot, dks, d_sv, d_rank, cap);
   }
+
   if (ranks_out) for (int i = 0; i < n; ++i) ranks_out[i] = ranks[i];
   if (err_out) CU(cudaMemcpyAsync(err_out, d_err, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (svals_out) CU(cudaMemcpyAsync(svals_out, d_sv, (size_t)n * cap * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   c->sync();
+}
+
+static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_t* flips, const double* gates,
+                             const tnqs_apply_opts& o, int32_t* ranks_out, double* err_out, double* svals_out) {
+  if (n == 0) return;
+  GateBatch gb; gb.c = c;
+  gb.stage1(n, es, flips, gates, o, nullptr);
+  gb.stage2(nullptr, ranks_out, err_out, svals_out);
 }
 
 extern "C" int32_t tnqs_apply_2site(tnqs_ctx* c, int32_t n, const int32_t* e, const int32_t* flip, const double* gates,
@@ -734,6 +830,34 @@ extern "C" int32_t tnqs_apply_2site(tnqs_ctx* c, int32_t n, const int32_t* e, co
   API_BEGIN(c)
   REQUIRE(n >= 0 && opts && (n == 0 || (e && gates)), TNQS_ERR_INVALID_ARG, "tnqs_apply_2site: null argument");
   apply_2site_impl(c, n, e, flip, gates, *opts, ranks, truncerr, svals);
+  c->release_temps();
+  API_END(c)
+}
+
+extern "C" int32_t tnqs_apply_2site_begin(tnqs_ctx* c, int32_t n, const int32_t* e, const int32_t* flip, const double* gates,
+                                          const tnqs_apply_opts* opts, const int32_t* remote, void** send_buf, int64_t* n_cut,
+                                          int64_t* slot_complex) {
+  API_BEGIN(c)
+  REQUIRE(n >= 1 && opts && e && gates, TNQS_ERR_INVALID_ARG, "tnqs_apply_2site_begin: null argument");
+  REQUIRE(!c->pending_gate, TNQS_ERR_INVALID_ARG, "tnqs_apply_2site_begin: a batch is already pending");
+  GateBatch* gb = new GateBatch(); gb->c = c;
+  c->pending_gate = gb;
+  try { gb->stage1(n, e, flip, gates, *opts, remote); c->sync(); }
+  catch (...) { delete gb; c->pending_gate = nullptr; throw; }
+  if (send_buf) *send_buf = gb->xsend;
+  if (n_cut) *n_cut = (int64_t)gb->cut.size();
+  if (slot_complex) *slot_complex = gb->xslot;
+  API_END(c)
+}
+
+extern "C" int32_t tnqs_apply_2site_end(tnqs_ctx* c, const void* recv_buf, int32_t* ranks, double* truncerr, double* svals) {
+  API_BEGIN(c)
+  REQUIRE(c->pending_gate, TNQS_ERR_INVALID_ARG, "tnqs_apply_2site_end: no pending batch");
+  GateBatch* gb = (GateBatch*)c->pending_gate;
+  c->pending_gate = nullptr;
+  try { gb->stage2((const cplx*)recv_buf, ranks, truncerr, svals); }
+  catch (...) { delete gb; throw; }
+  delete gb;
   c->release_temps();
   API_END(c)
 }

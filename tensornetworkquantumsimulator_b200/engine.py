@@ -300,6 +300,30 @@ def apply_2site_batch(bpc: BeliefPropagationCache, edges: Sequence[int], gates: 
     return ranks, errs, sv
 
 
+def apply_2site_begin(bpc: BeliefPropagationCache, edges: Sequence[int], gates: Sequence[np.ndarray], flip=None, remote=None,
+                      apply_kwargs: Optional[dict] = None):
+    """First stage of a batch with cut-crossing gates (tnqs_apply_2site_begin).  Returns (device pointer of the send buffer,
+    number of cut gates, slot size in ComplexF64)."""
+    n = len(edges)
+    es, fl = i32(edges), i32(flip if flip is not None else [0] * n)
+    rm = i32(remote if remote is not None else [0] * n)
+    data = np.concatenate([np.asarray(a, dtype=np.complex128).ravel(order="F") for a in gates]).view(np.float64)
+    aopts = _apply_opts(apply_kwargs)
+    send, ncut, slot = C.c_void_p(), C.c_int64(0), C.c_int64(0)
+    check(bpc.psi._h.ptr, _lib.load().tnqs_apply_2site_begin(bpc.psi._h.ptr, n, ptr_i32(es), ptr_i32(fl), ptr_f64(data), C.byref(aopts),
+                                                              ptr_i32(rm), C.byref(send), C.byref(ncut), C.byref(slot)))
+    return send.value, ncut.value, slot.value
+
+
+def apply_2site_end(bpc: BeliefPropagationCache, n: int, recv_ptr):
+    ranks = np.zeros(n, dtype=np.int32)
+    errs = np.zeros(n, dtype=np.float64)
+    sv = np.zeros((n, bpc.psi.chi_cap), dtype=np.float64)
+    check(bpc.psi._h.ptr, _lib.load().tnqs_apply_2site_end(bpc.psi._h.ptr, C.c_void_p(recv_ptr) if recv_ptr else None,
+                                                            ptr_i32(ranks), ptr_f64(errs), ptr_f64(sv.reshape(-1))))
+    return ranks, errs, sv
+
+
 def apply_1site_batch(x, vertices: Sequence[int], gates: Sequence[np.ndarray], normalize_tensors: bool = True) -> None:
     psi = network(x)
     vs = i32(vertices)

@@ -1,0 +1,52 @@
+"""Generates tests/golden/*.npz from the CPU oracle (run in the build container: python tests/golden/make_golden.py).
+The fixtures pin the oracle against drift and give the GPU tests reference-independent targets.  They are NOT Julia
+outputs (parity unpinned); julia/dump_golden.jl produces the same files from the real reference."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import tnqs_oracle as O
+from tensornetworkquantumsimulator_b200 import graphs as G, gates
+from util import ising_layer
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def bp_case():
+    g = G.named_grid((3, 3))
+    psi = O.random_tensornetworkstate(g, bond_dimension=3, seed=11)
+    seq = G.forest_cover_edge_sequence(g)
+    info = {}
+    bpc = O.update(O.BeliefPropagationCache(psi), maxiter=3, tolerance=0.0, edge_sequence=seq, info=info)
+    msgs = np.stack([O.message(bpc, k) for k in range(2 * g.ne)])
+    z = np.array([O.expect(bpc, ("Z", [g.names[v]])) for v in range(g.nv)])
+    np.savez(os.path.join(HERE, "bp_grid3x3_chi3.npz"), seed=11, chi=3, seq=seq, messages=msgs, expect_z=z, mean_diff=info["mean_diff"])
+
+
+def gate_case():
+    g = G.named_grid((4, 4))
+    psi = O.random_tensornetworkstate(g, bond_dimension=4, seed=31)
+    bpc = O.update(O.BeliefPropagationCache(psi), maxiter=6)
+    grp = G.grid_edge_color(g)[0]
+    arr = gates.gate_array(("Rzz", [0, 1], 0.9))
+    ranks, svals, errs = [], [], []
+    for e in grp:
+        det = {}
+        O.apply_gate(bpc, arr, [int(g.esrc[e]), int(g.edst[e])], maxdim=4, cutoff=1e-10, detail=det)
+        ranks.append(det["rank"]); errs.append(det["truncerr"]); svals.append(np.pad(det["svals"], (0, 4 - det["rank"])))
+    np.savez(os.path.join(HERE, "gates_grid4x4_chi4.npz"), seed=31, chi=4, edges=np.array(grp), gate=arr, ranks=np.array(ranks),
+             svals=np.array(svals), truncerr=np.array(errs))
+
+
+def circuit_case():
+    g = G.named_grid((4, 4))
+    layer = ising_layer(g, dt=0.01, hx=2.5, hz=0.2, J=1.0, groups=G.grid_edge_color(g))
+    psi, errs = O.apply_gates(layer * 6, O.tensornetworkstate(lambda v: "↑", g), apply_kwargs=dict(maxdim=4, cutoff=1e-10, normalize_tensors=True))
+    z = O.expect_tns(psi, ("Z", [(2, 2)]))
+    zz = O.expect_tns(psi, ("ZZ", [(2, 2), (2, 3)]))
+    np.savez(os.path.join(HERE, "circuit_c1_4x4.npz"), bond_dims=psi.bond_dims(), expect_z=z, expect_zz=zz, errs=errs)
+
+
+if __name__ == "__main__":
+    bp_case(); gate_case(); circuit_case()
+    print(sorted(os.listdir(HERE)))
