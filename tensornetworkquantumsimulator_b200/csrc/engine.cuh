@@ -50,7 +50,9 @@ struct tnqs_ctx {
   double prof_ms[TNQS_KC_COUNT] = {0};
   long long prof_launches[TNQS_KC_COUNT] = {0};
   std::vector<void*> temp;                         // stream-ordered temporaries of the current call
-  void* pending_gate = nullptr;                    // GateBatch between tnqs_apply_2site_begin and _end
+  void* pending_gate = nullptr;
+  void* bp_cache = nullptr;                        // BpPlanCache: last BP plan, reused while sites / bonds are unchanged
+  long long state_version = 0;                     // bumped whenever a site pointer or a bond dimension changes                    // GateBatch between tnqs_apply_2site_begin and _end
 
   // ---- graph helpers ----
   int other(int e, int v) const { return esrc[e] == v ? edst[e] : esrc[e]; }

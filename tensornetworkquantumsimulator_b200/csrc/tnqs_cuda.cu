@@ -5,6 +5,7 @@
 #include <map>
 
 static thread_local std::string g_create_error;
+static void bp_cache_drop(tnqs_ctx* c);
 
 #define API_BEGIN(ctx) if (!(ctx)) return TNQS_ERR_INVALID_ARG; try { CU(cudaSetDevice((ctx)->device));
 #define API_END(ctx) } catch (const TnqsError& e) { (ctx)->err = e.msg; (ctx)->release_temps(); return e.code; } \
@@ -137,6 +138,7 @@ extern "C" int32_t tnqs_destroy(tnqs_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->collect_profile();
+  bp_cache_drop(c);
   for (cplx* p : c->site) if (p) cudaFreeAsync(p, c->stream);
   if (c->msg_cur) cudaFreeAsync(c->msg_cur, c->stream);
   if (c->msg_stage) cudaFreeAsync(c->msg_stage, c->stream);
@@ -228,6 +230,20 @@ extern "C" int32_t tnqs_reset_messages(tnqs_ctx* c) { API_BEGIN(c) reset_message
 // ---------------------------------------------------------------------------------------------------------------
 // BP sweep
 // ---------------------------------------------------------------------------------------------------------------
+// The last BP plan (level schedule, descriptors, scratch) is kept on the handle and reused by later updates with the same
+// edge sequence and options as long as no site tensor or bond dimension changed: a refresh of 25 sweeps, or the
+// sweep-by-sweep calls of a partitioned run, build it once.
+struct BpPlanCache {
+  Plan plan; std::vector<int> seq; int mode = -1, normalize = -1, hermitize = -1, want_diff = -1; long long version = -1;
+  double* d_diff = nullptr; std::vector<void*> owned;
+};
+static void bp_cache_drop(tnqs_ctx* c) {
+  BpPlanCache* pc = (BpPlanCache*)c->bp_cache;
+  if (!pc) return;
+  for (void* p : pc->owned) c->dfree(p);
+  delete pc; c->bp_cache = nullptr;
+}
+
 static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, const tnqs_bp_opts& o, int* iters_out,
                            double* mean_out) {
   REQUIRE(o.maxiter >= 1, TNQS_ERR_INVALID_ARG, "You need to specify a number of iterations for BP!");
@@ -271,23 +287,37 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
     std::set<int> uniq(seq.begin(), seq.end());
     REQUIRE((int)uniq.size() == nseq, TNQS_ERR_INVALID_ARG, "JACOBI mode needs each directed edge at most once");
   }
-  double* d_diff = c->talloc<double>(nseq + 1);
-  std::vector<std::vector<Chain>> levels(nlevels);
-  for (int i = 0; i < nseq; ++i) {
-    int k = seq[i], v = c->dsrc(k), w = c->ddst(k), e = k >> 1;
-    Chain ch; ch.v = v;
-    for (size_t j = 0; j < c->inc[v].size(); ++j) {
-      int ee = c->inc[v][j], u = c->other(ee, v);
-      if (u == w) { ch.close_leg = (int)j; continue; }
-      Absorb ab; ab.leg = (int)j; ab.mat = c->msg(c->dedge(u, ee)); ab.ldm = c->chi[ee]; ab.flags = 0;
-      ch.absorb.push_back(ab);
-    }
-    (void)e;
-    ch.dst = c->msg_st(k); ch.prev = c->msg(k); ch.diff = want_diff ? d_diff + i : nullptr;
-    ch.bp_mode = 1; ch.normalize = o.normalize; ch.hermitize = o.hermitize; ch.commit_k = k;
-    levels[level[i]].push_back(ch);
+  BpPlanCache* pc = (BpPlanCache*)c->bp_cache;
+  if (!(pc && pc->version == c->state_version && pc->mode == o.mode && pc->normalize == o.normalize && pc->hermitize == o.hermitize &&
+        pc->want_diff == (int)want_diff && pc->seq == seq)) {
+    bp_cache_drop(c);
+    pc = new BpPlanCache();
+    std::vector<void*> saved; saved.swap(c->temp);            // allocations made while building belong to the cache
+    try {
+      pc->d_diff = c->talloc<double>(nseq + 1);
+      std::vector<std::vector<Chain>> levels(nlevels);
+      for (int i = 0; i < nseq; ++i) {
+        int k = seq[i], v = c->dsrc(k), w = c->ddst(k);
+        Chain ch; ch.v = v;
+        for (size_t j = 0; j < c->inc[v].size(); ++j) {
+          int ee = c->inc[v][j], u = c->other(ee, v);
+          if (u == w) { ch.close_leg = (int)j; continue; }
+          Absorb ab; ab.leg = (int)j; ab.mat = c->msg(c->dedge(u, ee)); ab.ldm = c->chi[ee]; ab.flags = 0;
+          ch.absorb.push_back(ab);
+        }
+        ch.dst = c->msg_st(k); ch.prev = c->msg(k); ch.diff = want_diff ? pc->d_diff + i : nullptr;
+        ch.bp_mode = 1; ch.normalize = o.normalize; ch.hermitize = o.hermitize; ch.commit_k = k;
+        levels[level[i]].push_back(ch);
+      }
+      pc->plan = build_plan(c, levels, scratch_budget(c));
+    } catch (...) { for (void* p : c->temp) c->dfree(p); c->temp.swap(saved); delete pc; throw; }
+    pc->owned.swap(c->temp); c->temp.swap(saved);
+    pc->seq = seq; pc->mode = o.mode; pc->normalize = o.normalize; pc->hermitize = o.hermitize; pc->want_diff = want_diff;
+    pc->version = c->state_version;
+    c->bp_cache = pc;
   }
-  Plan plan = build_plan(c, levels, scratch_budget(c));
+  const Plan& plan = pc->plan;
+  double* d_diff = pc->d_diff;
   double* d_sum = d_diff + nseq;
   int it = 0; double mean = NAN;
   for (it = 1; it <= o.maxiter; ++it) {
@@ -357,6 +387,7 @@ static void apply_1site_impl(tnqs_ctx* c, int n, const int32_t* vs, const double
     LAUNCH(c, TNQS_KC_MISC, k_scale, dim3(NB, n), 256, 0, dsd);
   }
   for (int i = 0; i < n; ++i) { c->dfree(c->site[vs[i]]); c->site[vs[i]] = outs[i]; }
+  ++c->state_version;
 }
 
 extern "C" int32_t tnqs_apply_1site(tnqs_ctx* c, int32_t n, const int32_t* v, const double* gates, int32_t normalize) {
@@ -793,6 +824,7 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
   }
   // ---- 9. commit: bond dimensions, site pointers, messages <- diag(S) (apply_gates.jl:105-119) ----
   for (int i = 0; i < n; ++i) c->chi[es[i]] = ranks[i];
+  ++c->state_version;
   upload_chi(c);
   for (int j : LJ) {
     c->dfree(c->site[jobs[j].v]); c->site[jobs[j].v] = newsite[j];
@@ -1149,6 +1181,7 @@ extern "C" int32_t tnqs_symmetric_gauge(tnqs_ctx* c, double regularization) {
       (void)maxtiles;
       launch_mode_apply(c, TNQS_KC_MODE_APPLY, ma);
       for (int v : touched) std::swap(c->site[v], other[v]);
+      ++c->state_version;
     }
     for (int v = 0; v < c->nv; ++v) c->dfree(other[v]);
     std::vector<int> ks(ne);

@@ -160,7 +160,7 @@ def class_gates_local(gg: Graph, lgraph: LocalGraph, owner: np.ndarray, rank: in
     """Split one colour class (global edge ids, first vertex = esrc) into this rank's batch: local edge ids, remote flags
     (0 both owned, 1 first vertex remote, 2 second vertex remote) and, per neighbour rank, the positions of the shared
     cut gates in batch order (both sides enumerate them by ascending global edge id)."""
-    es, rm, cut_with = [], [], {}
+    es, rm, cut_with, ncut = [], [], {}, 0
     for e in sorted(int(x) for x in edges_global):
         a, b = int(gg.esrc[e]), int(gg.edst[e])
         oa, ob = int(owner[a]), int(owner[b])
@@ -170,14 +170,17 @@ def class_gates_local(gg: Graph, lgraph: LocalGraph, owner: np.ndarray, rank: in
         flag = 0 if (oa == rank and ob == rank) else (1 if oa != rank else 2)
         rm.append(flag)
         if flag:
-            cut_with.setdefault(ob if flag == 2 else oa, []).append(len([f for f in rm if f]) - 1)
+            cut_with.setdefault(ob if flag == 2 else oa, []).append(ncut)
+            ncut += 1
     return np.array(es, dtype=np.int32), np.array(rm, dtype=np.int32), cut_with
 
 
-def apply_class_distributed(E, bpc, gg: Graph, lgraph: LocalGraph, owner, rank, edges_global, gate, apply_kwargs, dist, torch, device):
+def apply_class_distributed(E, bpc, gg: Graph, lgraph: LocalGraph, owner, rank, edges_global, gate, apply_kwargs, dist, torch, device,
+                            batch=None):
     """One colour class of identical two-site gates over the partitioned network (tnqs_apply_2site_begin / _end + one
-    grouped exchange of R factors).  Returns (ranks, truncation errors) of this rank's batch."""
-    es, rm, cut_with = class_gates_local(gg, lgraph, owner, rank, edges_global)
+    grouped exchange of R factors).  `batch` = a precomputed class_gates_local(...) result.  Returns (ranks, truncation
+    errors) of this rank's batch."""
+    es, rm, cut_with = batch if batch is not None else class_gates_local(gg, lgraph, owner, rank, edges_global)
     if len(es) == 0:
         return np.zeros(0, dtype=np.int32), np.zeros(0)
     send_ptr, ncut, slot = E.apply_2site_begin(bpc, es, [gate] * len(es), remote=rm, apply_kwargs=apply_kwargs)
