@@ -366,6 +366,8 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         }
         CloseReduceDesc r;
         r.partial = part; r.nsplit = cm.nsplit; r.n = n; r.np = n; r.dst = ch.dst; r.prev = ch.prev; r.diff = ch.diff;
+        // an un-chunked level has finished all its reads when its epilogue runs: write the message in place, no commit pass
+        if (ch.commit_k >= 0 && subsets[L].size() == 1) r.dst = c->msg(ch.commit_k);
         r.mode = ch.bp_mode; r.normalize = ch.normalize; r.hermitize = ch.hermitize;
         rd.push_back(r);
         maxnn = std::max(maxnn, (size_t)n * n);
@@ -377,7 +379,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
       sl.reduce.count = (int)sub.size(); sl.reduce.grid = dim3(sl.reduce.count, 1, 1); sl.reduce.smem = maxnn * sizeof(cplx);
       lp.subs.push_back(sl);
     }
-    for (const Chain& ch : chains) if (ch.commit_k >= 0) commit.push_back(ch.commit_k);
+    if (subsets[L].size() > 1) for (const Chain& ch : chains) if (ch.commit_k >= 0) commit.push_back(ch.commit_k);
     lp.commit_count = (int)(commit.size() - lp.commit_off);
     plan.levels.push_back(lp);
   }

@@ -36,72 +36,95 @@ template <int N> struct SlabCfg {
   static constexpr int SLAB3 = S1 * N * N;
 };
 
-// grid: (2*N, items); block 256 (8 warps); dynamic shared memory: S1*N^(F-1) complex (max SLAB3)
-template <int N>
-__global__ void __launch_bounds__(256, 2) k_absorb_slab(const SlabDesc* __restrict__ descs) {
+// One absorption phase P of F: compile-time strides, next tile's A fragments prefetched while the current tile multiplies.
+template <int N, int F, int P>
+__device__ __forceinline__ void absorb_phase(const SlabDesc& d, const double* __restrict__ gsrc, double* __restrict__ gdst,
+                                             double* __restrict__ sm, int lane, int warp, int nwarps) {
   using Cfg = SlabCfg<N>;
   constexpr int KS = Cfg::KS, NT = Cfg::NT;
-  const SlabDesc d = descs[blockIdx.y];
-  extern __shared__ cplx slab[];
+  constexpr bool from_global = P == 0, to_global = P == F - 1;
+  constexpr int O1 = P == 0 ? 1 : 0, O2 = P == 2 ? 1 : 2;              // the other slab legs, fastest first
+  constexpr long long SST[3] = {1, Cfg::S1, (long long)Cfg::S1 * N};    // shared strides
+  constexpr long long XST[3] = {1, N, (long long)N * N};                // intermediate strides
+  const int r = lane >> 2, q = lane & 3, kpair = q >> 1, part = q & 1;
+  const long long src_m = from_global ? d.g[P] : SST[P];
+  const long long src_o1 = from_global ? d.g[O1] : SST[O1];
+  const long long src_o2 = (F == 3) ? (from_global ? d.g[O2] : SST[O2]) : 0;
+  constexpr long long dst_m = to_global ? XST[P] : SST[P];
+  constexpr long long dst_o1 = to_global ? XST[O1] : SST[O1];
+  constexpr long long dst_o2 = (F == 3) ? (to_global ? XST[O2] : SST[O2]) : 0;
+  const double* src = from_global ? gsrc : sm;
+  double* dst = to_global ? gdst : sm;
+  // B fragments of [[Re m, Im m], [-Im m, Re m]] (interleaved), kept in registers for the whole phase
+  double bf[KS][NT];
+  {
+    const cplx* m = d.m[P];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int b = 2 * ks + kpair, c = 4 * nt + (r >> 1), pp = r & 1;
+        const cplx v = m[b + N * c];
+        bf[ks][nt] = (part == pp) ? v.x : (part ? -v.y : v.y);
+      }
+  }
+  constexpr int ntiles = (F == 3 ? N * N : N) / 8;
+  double a[KS], an[KS];
+  auto tile_off = [&](int ti, long long so1, long long so2) { const int rho = 8 * ti + r; return (rho % N) * so1 + (rho / N) * so2; };
+  int ti = warp;
+  if (ti < ntiles) {
+    const long long soff = tile_off(ti, src_o1, src_o2);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) a[ks] = src[2 * (soff + (2 * ks + kpair) * src_m) + part];
+  }
+  for (; ti < ntiles; ti += nwarps) {
+    const int tn = ti + nwarps;
+    if (tn < ntiles) {
+      const long long soff = tile_off(tn, src_o1, src_o2);
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) an[ks] = src[2 * (soff + (2 * ks + kpair) * src_m) + part];
+    }
+    double acc[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = 0.0; acc[nt][1] = 0.0; }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) dmma884(acc[nt][0], acc[nt][1], a[ks], bf[ks][nt]);
+    const long long doff = tile_off(ti, dst_o1, dst_o2);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      double2 v; v.x = acc[nt][0]; v.y = acc[nt][1];
+      *reinterpret_cast<double2*>(dst + 2 * (doff + (q + 4 * nt) * dst_m)) = v;
+    }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) a[ks] = an[ks];
+  }
+}
+
+// grid: (2*N, items); block 256 (8 warps); dynamic shared memory: S1*N^(F-1) complex (max SLAB3)
+template <int N, int F>
+__device__ __forceinline__ void absorb_slab_body(const SlabDesc& d, double* sm) {
   const int s = blockIdx.x & 1, w = blockIdx.x >> 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int r = lane >> 2, q = lane & 3, kpair = q >> 1, part = q & 1;
-  const int F = d.F;
   long long NF = N; for (int i = 1; i < F; ++i) NF *= N;
   const double* gsrc = reinterpret_cast<const double*>(d.t + s + (long long)w * d.gw);
   double* gdst = reinterpret_cast<double*>(d.x + ((long long)w * 2 + s) * NF);
-  double* sm = reinterpret_cast<double*>(slab);
-  const long long sst[3] = {1, Cfg::S1, (long long)Cfg::S1 * N};   // shared strides
-  const long long xst[3] = {1, N, (long long)N * N};               // intermediate strides
-  const int nrows = (int)(NF / N);                                 // rows of every absorption
-
-  for (int p = 0; p < F; ++p) {
-    // B fragments of [[Re m, Im m], [-Im m, Re m]] (interleaved), kept in registers for the whole phase
-    double bf[KS][NT];
-    {
-      const cplx* m = d.m[p];
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          int b = 2 * ks + kpair, c = 4 * nt + (r >> 1), pp = r & 1;
-          cplx v = m[b + N * c];
-          bf[ks][nt] = (part == pp) ? v.x : (part ? -v.y : v.y);
-        }
-    }
-    const bool from_global = p == 0, to_global = p == F - 1;
-    const int o1 = p == 0 ? 1 : 0, o2 = p == 2 ? 1 : 2;             // the other slab legs, fastest first
-    const long long src_m = from_global ? d.g[p] : sst[p];
-    const long long src_o1 = from_global ? d.g[o1] : sst[o1];
-    const long long src_o2 = (F == 3) ? (from_global ? d.g[o2] : sst[o2]) : 0;
-    const long long dst_m = to_global ? xst[p] : sst[p];
-    const long long dst_o1 = to_global ? xst[o1] : sst[o1];
-    const long long dst_o2 = (F == 3) ? (to_global ? xst[o2] : sst[o2]) : 0;
-    const double* src = from_global ? gsrc : sm;
-    double* dst = to_global ? gdst : sm;
-    for (int ti = warp; ti < nrows / 8; ti += nwarps) {
-      const int rho = 8 * ti + r;
-      const int i1 = rho % N, i2 = rho / N;
-      const long long soff = i1 * src_o1 + i2 * src_o2;
-      const long long doff = i1 * dst_o1 + i2 * dst_o2;
-      double a[KS];
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) a[ks] = src[2 * (soff + (2 * ks + kpair) * src_m) + part];
-      double acc[NT][2];
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = 0.0; acc[nt][1] = 0.0; }
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) dmma884(acc[nt][0], acc[nt][1], a[ks], bf[ks][nt]);
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        double2 v; v.x = acc[nt][0]; v.y = acc[nt][1];
-        *reinterpret_cast<double2*>(dst + 2 * (doff + (q + 4 * nt) * dst_m)) = v;
-      }
-    }
+  absorb_phase<N, F, 0>(d, gsrc, gdst, sm, lane, warp, nwarps);
+  __syncthreads();
+  absorb_phase<N, F, 1>(d, gsrc, gdst, sm, lane, warp, nwarps);
+  if (F == 3) {
     __syncthreads();
+    absorb_phase<N, F, (F == 3 ? 2 : 1)>(d, gsrc, gdst, sm, lane, warp, nwarps);
   }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256, 2) k_absorb_slab(const SlabDesc* __restrict__ descs) {
+  const SlabDesc d = descs[blockIdx.y];
+  extern __shared__ cplx slab[];
+  double* sm = reinterpret_cast<double*>(slab);
+  if (d.F == 3) absorb_slab_body<N, 3>(d, sm); else absorb_slab_body<N, 2>(d, sm);
 }
 
 struct CloseDmmaDesc {
@@ -135,24 +158,33 @@ __global__ void __launch_bounds__(256, 2) k_close_dmma(const CloseDmmaDesc* __re
   for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int j = 0; j < MT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-  for (long long kap = k_begin + warp; kap < k_end; kap += 8) {
-    const int j = (int)(kap % (N / 2));
-    const long long rest = kap / (N / 2);
-    const int i2 = (int)(rest % N), i3 = (int)(rest / N);
-    const int i1 = 2 * j + di;
-    const long long sigma = i1 + (long long)N * i2 + (long long)N * N * i3;
-    const long long toff = s + i1 * d.g[0] + i2 * d.g[1] + (d.F == 3 ? i3 * d.g[2] : 0);
-    double a[MT], b[MT];
+  // two k-steps (16 operand loads) in flight per warp: the kernel is bound by the latency of its operand loads
+  for (long long kap = k_begin + warp; kap < k_end; kap += 16) {
+    double a[2][MT], b[2][MT];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      const int w = 4 * mt + wl;
-      a[mt] = X[2 * (((long long)w * 2 + s) * NF + sigma) + part];
-      b[mt] = T[2 * (toff + (long long)w * d.gw) + part];
+    for (int u = 0; u < 2; ++u) {
+      const long long kk = kap + 8 * u;
+      const bool ok = kk < k_end;
+      const long long kq = ok ? kk : kap;
+      const int j = (int)(kq % (N / 2));
+      const long long rest = kq / (N / 2);
+      const int i2 = (int)(rest % N), i3 = (int)(rest / N);
+      const int i1 = 2 * j + di;
+      const long long sigma = i1 + (long long)N * i2 + (long long)N * N * i3;
+      const long long toff = s + i1 * d.g[0] + i2 * d.g[1] + (d.F == 3 ? i3 * d.g[2] : 0);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int w = 4 * mt + wl;
+        a[u][mt] = ok ? X[2 * (((long long)w * 2 + s) * NF + sigma) + part] : 0.0;
+        b[u][mt] = ok ? T[2 * (toff + (long long)w * d.gw) + part] : 0.0;
+      }
     }
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int nt = 0; nt < MT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < MT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[u][mt], b[u][nt]);
   }
   // fixed-order reduction over the 8 warps
   constexpr int PD = 2 * N;                        // P is PD x PD real

@@ -246,9 +246,9 @@ __global__ void __launch_bounds__(256) k_close_reduce(const CloseReduceDesc* __r
       v = cmake(0.5 * (v.x + w.x), 0.5 * (v.y - w.y));
     }
     v = cmul(v, inv);
+    cplx p = d.diff ? d.prev[idx] : cmake(0, 0);      // read before the store: dst may alias prev (in-place message update)
     d.dst[idx] = v;
     if (d.diff) {
-      cplx p = d.prev[idx];
       dre += v.x * p.x + v.y * p.y;      // conj(v) * p
       dim += v.x * p.y - v.y * p.x;
       na += cabs2(v); nb += cabs2(p);

@@ -370,14 +370,14 @@ static void apply_1site_impl(tnqs_ctx* c, int n, const int32_t* vs, const double
   double* d_part = c->talloc<double>((size_t)n * NB);
   double* d_n2 = c->talloc<double>(n);
   std::vector<Gate1Desc> g1(n); std::vector<Norm2Desc> nd(n); std::vector<ScaleDesc> sd(n);
-  std::vector<cplx*> outs(n);
   for (int i = 0; i < n; ++i) {
     int v = vs[i];
-    outs[i] = (cplx*)c->dalloc(c->site_n[v] * sizeof(cplx));
-    g1[i].in = c->site[v]; g1[i].out = outs[i]; g1[i].gate = d_g + goff[i]; g1[i].d = c->d[v];
+    // in place: every thread owns one fibre T[:, rest] (reads its d values, writes them back), so no allocation and the
+    // site pointers (and any cached BP plan) stay valid
+    g1[i].in = c->site[v]; g1[i].out = c->site[v]; g1[i].gate = d_g + goff[i]; g1[i].d = c->d[v];
     g1[i].rest = c->site_n[v] / c->d[v]; g1[i].norm2_partial = d_part + (size_t)i * NB;
     nd[i].x = nullptr; nd[i].n = 0; nd[i].out = d_n2 + i; nd[i].partial = d_part + (size_t)i * NB; nd[i].npartial = NB;
-    sd[i].x = outs[i]; sd[i].n = c->site_n[v]; sd[i].scalar = d_n2 + i; sd[i].mode = 0;
+    sd[i].x = c->site[v]; sd[i].n = c->site_n[v]; sd[i].scalar = d_n2 + i; sd[i].mode = 0;
   }
   Gate1Desc* dg1 = c->upload(g1);
   LAUNCH(c, TNQS_KC_MISC, k_gate1, dim3(NB, n), 256, 0, dg1);
@@ -386,8 +386,6 @@ static void apply_1site_impl(tnqs_ctx* c, int n, const int32_t* vs, const double
     LAUNCH(c, TNQS_KC_MISC, k_norm2, n, 64, 0, dnd);
     LAUNCH(c, TNQS_KC_MISC, k_scale, dim3(NB, n), 256, 0, dsd);
   }
-  for (int i = 0; i < n; ++i) { c->dfree(c->site[vs[i]]); c->site[vs[i]] = outs[i]; }
-  ++c->state_version;
 }
 
 extern "C" int32_t tnqs_apply_1site(tnqs_ctx* c, int32_t n, const int32_t* v, const double* gates, int32_t normalize) {
