@@ -8,6 +8,7 @@
 #include <vector>
 #include <algorithm>
 #include <stdexcept>
+#include <chrono>
 
 #include "../../include/tnqs_cuda.h"
 #include "common.cuh"
@@ -71,7 +72,14 @@ struct tnqs_ctx {
   void* dalloc(size_t bytes) {
     void* p = nullptr;
     if (bytes == 0) bytes = 16;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("TNQS_DEBUG_ALLOC"); dbg = (e && e[0] == '1') ? 1 : 0; }
+    auto t0 = std::chrono::steady_clock::now();
     CU(cudaMallocAsync(&p, bytes, stream));
+    if (dbg) {
+      double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (ms > 0.5) fprintf(stderr, "[tnqs alloc] %.2f ms for %.1f MB\n", ms, bytes / 1048576.0);
+    }
     return p;
   }
   void dfree(void* p) { if (p) cudaFreeAsync(p, stream); }
@@ -171,6 +179,11 @@ struct Plan {
   Gate1Desc* d_gate1 = nullptr; ModeApplyDesc* d_apply = nullptr; ModeCloseDesc* d_close = nullptr;
   CloseReduceDesc* d_reduce = nullptr; int* d_commit = nullptr;
   SlabDesc* d_slab = nullptr; CloseDmmaDesc* d_dclose = nullptr;
+  // storage: a rebuilt plan of the same shape reuses the buffers of its predecessor, so device addresses (and a CUDA graph
+  // captured over them) stay valid when only the site pointers inside the descriptors changed
+  cplx* scratch = nullptr; size_t scratch_elems = 0; cplx* partial = nullptr; size_t partial_elems = 0;
+  size_t cnt[7] = {0, 0, 0, 0, 0, 0, 0};          // descriptor counts: gate1, apply, close, reduce, commit, slab, dclose
+  int nlaunch = 0;                   // kernel launches per run
   double flops = 0;                  // executed flops per run of the plan (8 per complex MAC)
 };
 
@@ -195,7 +208,13 @@ static int fast_path_N(const tnqs_ctx* c, const Chain& ch) {
 }
 
 // Build a plan for `levels` (vector of vector of chains).  All device buffers are temporaries of the current call.
-static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& levels, size_t scratch_budget_bytes) {
+template <typename T> static T* upload_into(tnqs_ctx* c, T* reuse, const std::vector<T>& v) {
+  if (!reuse) return c->upload(v);
+  if (!v.empty()) CU(cudaMemcpyAsync(reuse, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  return reuse;
+}
+
+static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& levels, size_t scratch_budget_bytes, const Plan* reuse = nullptr) {
   Plan plan;
   std::vector<Gate1Desc> g1; std::vector<ModeApplyDesc> ma; std::vector<ModeCloseDesc> mc;
   std::vector<CloseReduceDesc> rd; std::vector<int> commit;
@@ -237,8 +256,12 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
       max_partial = std::max(max_partial, part);
     }
   }
-  cplx* scratch = c->talloc<cplx>(max_scratch / sizeof(cplx) + 16);
-  cplx* partial = c->talloc<cplx>(max_partial + 16);
+  const size_t need_scratch = max_scratch / sizeof(cplx) + 16, need_partial = max_partial + 16;
+  const bool reuse_mem = reuse && reuse->scratch && reuse->scratch_elems >= need_scratch && reuse->partial_elems >= need_partial;
+  cplx* scratch = reuse_mem ? reuse->scratch : c->talloc<cplx>(need_scratch);
+  cplx* partial = reuse_mem ? reuse->partial : c->talloc<cplx>(need_partial);
+  plan.scratch = scratch; plan.scratch_elems = reuse_mem ? reuse->scratch_elems : need_scratch;
+  plan.partial = partial; plan.partial_elems = reuse_mem ? reuse->partial_elems : need_partial;
   // pass 2: descriptors
   for (size_t L = 0; L < levels.size(); ++L) {
     const auto& chains = levels[L];
@@ -383,10 +406,39 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
     lp.commit_count = (int)(commit.size() - lp.commit_off);
     plan.levels.push_back(lp);
   }
-  plan.d_gate1 = c->upload(g1); plan.d_apply = c->upload(ma); plan.d_close = c->upload(mc);
-  plan.d_reduce = c->upload(rd); plan.d_commit = c->upload(commit);
-  plan.d_slab = c->upload(sd); plan.d_dclose = c->upload(dc);
+  const size_t cnt[7] = {g1.size(), ma.size(), mc.size(), rd.size(), commit.size(), sd.size(), dc.size()};
+  bool same = reuse_mem;
+  for (int i = 0; i < 7 && same; ++i) same = cnt[i] == reuse->cnt[i];
+  for (int i = 0; i < 7; ++i) plan.cnt[i] = cnt[i];
+  plan.d_gate1 = upload_into(c, same ? reuse->d_gate1 : nullptr, g1); plan.d_apply = upload_into(c, same ? reuse->d_apply : nullptr, ma);
+  plan.d_close = upload_into(c, same ? reuse->d_close : nullptr, mc); plan.d_reduce = upload_into(c, same ? reuse->d_reduce : nullptr, rd);
+  plan.d_commit = upload_into(c, same ? reuse->d_commit : nullptr, commit);
+  plan.d_slab = upload_into(c, same ? reuse->d_slab : nullptr, sd); plan.d_dclose = upload_into(c, same ? reuse->d_dclose : nullptr, dc);
+  for (const LevelPlan& lp : plan.levels) {
+    for (const SubLevel& sl : lp.subs) plan.nlaunch += (sl.slab.count ? 2 : 0) + (sl.gate1.count ? 1 : 0) + (int)sl.steps.size() + (sl.close.count ? 1 : 0) + 1;
+    plan.nlaunch += lp.commit_count ? 1 : 0;
+  }
   return plan;
+}
+
+static bool same_rec(const LaunchRec& a, const LaunchRec& b) {
+  return a.off == b.off && a.count == b.count && a.grid.x == b.grid.x && a.grid.y == b.grid.y && a.grid.z == b.grid.z && a.smem == b.smem && a.dmma == b.dmma;
+}
+// True when two plans issue the same launches over the same device buffers (a captured CUDA graph of one replays the other).
+static bool same_launches(const Plan& a, const Plan& b) {
+  if (a.levels.size() != b.levels.size() || a.d_slab != b.d_slab || a.d_apply != b.d_apply || a.d_close != b.d_close ||
+      a.d_reduce != b.d_reduce || a.d_dclose != b.d_dclose || a.d_gate1 != b.d_gate1 || a.d_commit != b.d_commit) return false;
+  for (size_t L = 0; L < a.levels.size(); ++L) {
+    const LevelPlan &x = a.levels[L], &y = b.levels[L];
+    if (x.subs.size() != y.subs.size() || x.commit_off != y.commit_off || x.commit_count != y.commit_count) return false;
+    for (size_t i = 0; i < x.subs.size(); ++i) {
+      const SubLevel &p = x.subs[i], &q = y.subs[i];
+      if (p.fastN != q.fastN || p.steps.size() != q.steps.size() || !same_rec(p.slab, q.slab) || !same_rec(p.dclose, q.dclose) ||
+          !same_rec(p.gate1, q.gate1) || !same_rec(p.close, q.close) || !same_rec(p.reduce, q.reduce)) return false;
+      for (size_t j = 0; j < p.steps.size(); ++j) if (!same_rec(p.steps[j], q.steps[j])) return false;
+    }
+  }
+  return true;
 }
 
 // Upload and launch one batched mode_apply (tensor-core kernel when eligible).

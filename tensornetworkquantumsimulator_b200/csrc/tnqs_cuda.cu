@@ -236,12 +236,19 @@ extern "C" int32_t tnqs_reset_messages(tnqs_ctx* c) { API_BEGIN(c) reset_message
 struct BpPlanCache {
   Plan plan; std::vector<int> seq; int mode = -1, normalize = -1, hermitize = -1, want_diff = -1; long long version = -1;
   double* d_diff = nullptr; std::vector<void*> owned;
+  cudaGraphExec_t graph = nullptr;     // one sweep (all levels + the diff sum), captured once per launch structure
 };
 static void bp_cache_drop(tnqs_ctx* c) {
   BpPlanCache* pc = (BpPlanCache*)c->bp_cache;
   if (!pc) return;
+  if (pc->graph) cudaGraphExecDestroy(pc->graph);
   for (void* p : pc->owned) c->dfree(p);
   delete pc; c->bp_cache = nullptr;
+}
+static bool graphs_disabled() {
+  static int d = -1;
+  if (d < 0) { const char* e = getenv("TNQS_NO_GRAPH"); d = (e && e[0] == '1') ? 1 : 0; }
+  return d == 1;
 }
 
 static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, const tnqs_bp_opts& o, int* iters_out,
@@ -288,13 +295,16 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
     REQUIRE((int)uniq.size() == nseq, TNQS_ERR_INVALID_ARG, "JACOBI mode needs each directed edge at most once");
   }
   BpPlanCache* pc = (BpPlanCache*)c->bp_cache;
-  if (!(pc && pc->version == c->state_version && pc->mode == o.mode && pc->normalize == o.normalize && pc->hermitize == o.hermitize &&
-        pc->want_diff == (int)want_diff && pc->seq == seq)) {
-    bp_cache_drop(c);
-    pc = new BpPlanCache();
+  const bool same_request = pc && pc->mode == o.mode && pc->normalize == o.normalize && pc->hermitize == o.hermitize &&
+                            pc->want_diff == (int)want_diff && pc->seq == seq;
+  if (!(same_request && pc->version == c->state_version)) {
+    // (re)build; when only site pointers / values changed the new plan lands in the old one's buffers and keeps its graph
+    BpPlanCache* old = same_request ? pc : nullptr;
+    if (pc && !old) { bp_cache_drop(c); pc = nullptr; }
+    BpPlanCache* nc = old ? old : new BpPlanCache();
     std::vector<void*> saved; saved.swap(c->temp);            // allocations made while building belong to the cache
     try {
-      pc->d_diff = c->talloc<double>(nseq + 1);
+      if (!nc->d_diff) nc->d_diff = c->talloc<double>(nseq + 1);
       std::vector<std::vector<Chain>> levels(nlevels);
       for (int i = 0; i < nseq; ++i) {
         int k = seq[i], v = c->dsrc(k), w = c->ddst(k);
@@ -305,26 +315,48 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
           Absorb ab; ab.leg = (int)j; ab.mat = c->msg(c->dedge(u, ee)); ab.ldm = c->chi[ee]; ab.flags = 0;
           ch.absorb.push_back(ab);
         }
-        ch.dst = c->msg_st(k); ch.prev = c->msg(k); ch.diff = want_diff ? pc->d_diff + i : nullptr;
+        ch.dst = c->msg_st(k); ch.prev = c->msg(k); ch.diff = want_diff ? nc->d_diff + i : nullptr;
         ch.bp_mode = 1; ch.normalize = o.normalize; ch.hermitize = o.hermitize; ch.commit_k = k;
         levels[level[i]].push_back(ch);
       }
-      pc->plan = build_plan(c, levels, scratch_budget(c));
-    } catch (...) { for (void* p : c->temp) c->dfree(p); c->temp.swap(saved); delete pc; throw; }
-    pc->owned.swap(c->temp); c->temp.swap(saved);
-    pc->seq = seq; pc->mode = o.mode; pc->normalize = o.normalize; pc->hermitize = o.hermitize; pc->want_diff = want_diff;
-    pc->version = c->state_version;
-    c->bp_cache = pc;
+      Plan np = build_plan(c, levels, scratch_budget(c), old ? &old->plan : nullptr);
+      if (nc->graph && !same_launches(np, nc->plan)) { cudaGraphExecDestroy(nc->graph); nc->graph = nullptr; }
+      nc->plan = np;
+    } catch (...) { for (void* p : c->temp) c->dfree(p); c->temp.swap(saved); if (!old) delete nc; else { c->bp_cache = nullptr; } throw; }
+    for (void* p : c->temp) nc->owned.push_back(p);
+    c->temp.clear(); c->temp.swap(saved);
+    nc->seq = seq; nc->mode = o.mode; nc->normalize = o.normalize; nc->hermitize = o.hermitize; nc->want_diff = want_diff;
+    nc->version = c->state_version;
+    c->bp_cache = nc; pc = nc;
   }
   const Plan& plan = pc->plan;
   double* d_diff = pc->d_diff;
   double* d_sum = d_diff + nseq;
   int it = 0; double mean = NAN;
+  const bool use_graph = !c->profiling && !graphs_disabled() && plan.nlaunch >= 8;
   for (it = 1; it <= o.maxiter; ++it) {
-    run_plan(c, plan);
+    if (use_graph) {
+      if (!pc->graph) {                                     // capture one sweep: every level + the diff sum
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        try {
+          run_plan(c, plan);
+          if (want_diff) LAUNCH(c, TNQS_KC_BP_FINALIZE, k_sum, 1, 1024, 0, d_diff, nseq, d_sum);
+        } catch (...) { cudaStreamEndCapture(c->stream, &g); if (g) cudaGraphDestroy(g); throw; }
+        CU(cudaStreamEndCapture(c->stream, &g));
+        cudaError_t ge = cudaGraphInstantiate(&pc->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ge != cudaSuccess) throw TnqsError(TNQS_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ge));
+        c->launches -= plan.nlaunch + (want_diff ? 1 : 0);  // the capture pass launched nothing
+      }
+      CU(cudaGraphLaunch(pc->graph, c->stream));
+      c->launches += plan.nlaunch + (want_diff ? 1 : 0);
+    } else {
+      run_plan(c, plan);
+      if (want_diff) LAUNCH(c, TNQS_KC_BP_FINALIZE, k_sum, 1, 1024, 0, d_diff, nseq, d_sum);
+    }
     ++c->bp_sweeps; c->bp_msg_updates += nseq;
     if (want_diff) {
-      LAUNCH(c, TNQS_KC_BP_FINALIZE, k_sum, 1, 1024, 0, d_diff, nseq, d_sum);
       double s = 0;
       CU(cudaMemcpyAsync(&s, d_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       c->sync();
