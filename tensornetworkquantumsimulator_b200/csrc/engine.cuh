@@ -83,8 +83,28 @@ struct tnqs_ctx {
     return p;
   }
   void dfree(void* p) { if (p) cudaFreeAsync(p, stream); }
-  template <typename T> T* talloc(size_t count) { T* p = (T*)dalloc(count * sizeof(T)); temp.push_back(p); return p; }
-  void release_temps() { for (void* p : temp) dfree(p); temp.clear(); }
+  // Per-call temporaries come from a bump arena (chunks are kept for the life of the handle): a batch of ~1000 gates
+  // makes ~15000 small allocations, far too many for one cudaMallocAsync each.  `arena_bypass` = allocations that
+  // outlive the call (the cached BP plan) go to the pool directly and are tracked in `temp`.
+  struct ArenaChunk { char* base; size_t size; };
+  std::vector<ArenaChunk> arena; size_t arena_chunk = 0, arena_off = 0; bool arena_bypass = false;
+  void* arena_alloc(size_t bytes) {
+    bytes = (bytes + 255) / 256 * 256;
+    while (arena_chunk < arena.size()) {
+      if (arena_off + bytes <= arena[arena_chunk].size) { void* p = arena[arena_chunk].base + arena_off; arena_off += bytes; return p; }
+      ++arena_chunk; arena_off = 0;
+    }
+    size_t sz = std::max(bytes, (size_t)256 << 20);
+    ArenaChunk ch; ch.base = (char*)dalloc(sz); ch.size = sz;
+    arena.push_back(ch); arena_chunk = arena.size() - 1; arena_off = bytes;
+    return ch.base;
+  }
+  template <typename T> T* talloc(size_t count) {
+    if (arena_bypass) { T* p = (T*)dalloc(count * sizeof(T)); temp.push_back(p); return p; }
+    return (T*)arena_alloc(std::max<size_t>(count, 1) * sizeof(T));
+  }
+  void release_temps() { for (void* p : temp) dfree(p); temp.clear(); arena_chunk = 0; arena_off = 0; }
+  void arena_destroy() { for (auto& ch : arena) dfree(ch.base); arena.clear(); }
   template <typename T> T* upload(const std::vector<T>& v) {
     T* p = talloc<T>(std::max<size_t>(v.size(), 1));
     if (!v.empty()) CU(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
@@ -307,6 +327,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
             stride *= N;
           }
           for (; ai < 3; ++ai) { a.g[ai] = 0; b.g[ai] = 0; a.m[ai] = nullptr; }
+          a.gs = 1; a.nslabs = 2 * N; a.flags = 0;
           sd.push_back(a); dc.push_back(b);
           maxsplit_f = std::max(maxsplit_f, cm.nsplit);
           plan.flops += 8.0 * (double)c->site_n[v] * N * (F + 1);

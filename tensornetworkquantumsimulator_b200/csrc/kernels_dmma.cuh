@@ -27,6 +27,9 @@ struct SlabDesc {
   int F;                  // number of absorbed legs (2 or 3)
   long long g[3];         // canonical strides (complex elements) of the absorbed legs
   long long gw;           // canonical stride of the outgoing leg
+  long long gs;           // stride of the slab-pair index s (1 for site tensors: the site index; Po for matricised layouts)
+  int nslabs;             // slabs of this item (2N for a BP message; number of columns for a matricised tensor)
+  int flags;              // bit0: conj(m), bit1: m^T (as k_mode_apply)
 };
 
 template <int N> struct SlabCfg {
@@ -59,12 +62,14 @@ __device__ __forceinline__ void absorb_phase(const SlabDesc& d, const double* __
   double bf[KS][NT];
   {
     const cplx* m = d.m[P];
+    const bool conj_m = d.flags & 1, trans_m = d.flags & 2;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int b = 2 * ks + kpair, c = 4 * nt + (r >> 1), pp = r & 1;
-        const cplx v = m[b + N * c];
+        cplx v = trans_m ? m[c + N * b] : m[b + N * c];
+        if (conj_m) v.y = -v.y;
         bf[ks][nt] = (part == pp) ? v.x : (part ? -v.y : v.y);
       }
   }
@@ -108,7 +113,7 @@ __device__ __forceinline__ void absorb_slab_body(const SlabDesc& d, double* sm) 
   const int s = blockIdx.x & 1, w = blockIdx.x >> 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   long long NF = N; for (int i = 1; i < F; ++i) NF *= N;
-  const double* gsrc = reinterpret_cast<const double*>(d.t + s + (long long)w * d.gw);
+  const double* gsrc = reinterpret_cast<const double*>(d.t + (long long)s * d.gs + (long long)w * d.gw);
   double* gdst = reinterpret_cast<double*>(d.x + ((long long)w * 2 + s) * NF);
   absorb_phase<N, F, 0>(d, gsrc, gdst, sm, lane, warp, nwarps);
   __syncthreads();
@@ -122,6 +127,7 @@ __device__ __forceinline__ void absorb_slab_body(const SlabDesc& d, double* sm) 
 template <int N>
 __global__ void __launch_bounds__(256, 2) k_absorb_slab(const SlabDesc* __restrict__ descs) {
   const SlabDesc d = descs[blockIdx.y];
+  if ((int)blockIdx.x >= d.nslabs) return;
   extern __shared__ cplx slab[];
   double* sm = reinterpret_cast<double*>(slab);
   if (d.F == 3) absorb_slab_body<N, 3>(d, sm); else absorb_slab_body<N, 2>(d, sm);

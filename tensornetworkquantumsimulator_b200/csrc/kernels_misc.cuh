@@ -15,20 +15,24 @@ struct PermDesc {
   const double* norm2;             // matrix -> canonical only: multiply by 1/sqrt(*norm2) if non-null
 };
 
-// grid: (blocks, items); thread per matrix element (coalesced on the matrix side).
+// grid: (ceil(max Po / 256), items); a thread owns one outer multi-index rho: it decomposes rho once, then walks the bond
+// index, moving the d contiguous site-index values of the canonical side (a full 32-byte sector at d = 2) to / from d
+// matrix columns (coalesced across the warp on both sides when the first outer leg is the first canonical leg).
 __global__ void __launch_bounds__(256) k_permute(const PermDesc* __restrict__ descs) {
   const PermDesc p = descs[blockIdx.y];
-  const long long total = p.Po * p.d * p.chib;
+  const long long rho = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (rho >= p.Po) return;
   double scale = 1.0;
   if (!p.to_matrix && p.norm2) { double n2 = *p.norm2; scale = n2 > 0.0 ? 1.0 / sqrt(n2) : 1.0; }
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    long long rho = idx % p.Po, col = idx / p.Po;
-    int s = (int)(col % p.d), b = (int)(col / p.d);
-    long long off = s + (long long)b * p.bstride, r = rho;
-    for (int i = 0; i < p.nouter; ++i) { long long q = r / p.odim[i]; off += (r - q * p.odim[i]) * p.ostride[i]; r = q; }
-    if (p.to_matrix) p.dst[idx] = p.src[off];
-    else p.dst[off] = cscale(p.src[idx], scale);
+  long long off = 0, r = rho;
+  for (int i = 0; i < p.nouter; ++i) { long long q = r / p.odim[i]; off += (r - q * p.odim[i]) * p.ostride[i]; r = q; }
+  const int d = p.d;
+  if (p.to_matrix) {
+    for (int b = 0; b < p.chib; ++b)
+      for (int s = 0; s < d; ++s) p.dst[rho + p.Po * (s + (long long)d * b)] = p.src[off + (long long)b * p.bstride + s];
+  } else {
+    for (int b = 0; b < p.chib; ++b)
+      for (int s = 0; s < d; ++s) p.dst[off + (long long)b * p.bstride + s] = cscale(p.src[rho + p.Po * (s + (long long)d * b)], scale);
   }
 }
 

@@ -139,6 +139,7 @@ extern "C" int32_t tnqs_destroy(tnqs_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->collect_profile();
   bp_cache_drop(c);
+  c->arena_destroy();
   for (cplx* p : c->site) if (p) cudaFreeAsync(p, c->stream);
   if (c->msg_cur) cudaFreeAsync(c->msg_cur, c->stream);
   if (c->msg_stage) cudaFreeAsync(c->msg_stage, c->stream);
@@ -303,6 +304,7 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
     if (pc && !old) { bp_cache_drop(c); pc = nullptr; }
     BpPlanCache* nc = old ? old : new BpPlanCache();
     std::vector<void*> saved; saved.swap(c->temp);            // allocations made while building belong to the cache
+    c->arena_bypass = true;
     try {
       if (!nc->d_diff) nc->d_diff = c->talloc<double>(nseq + 1);
       std::vector<std::vector<Chain>> levels(nlevels);
@@ -322,7 +324,8 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
       Plan np = build_plan(c, levels, scratch_budget(c), old ? &old->plan : nullptr);
       if (nc->graph && !same_launches(np, nc->plan)) { cudaGraphExecDestroy(nc->graph); nc->graph = nullptr; }
       nc->plan = np;
-    } catch (...) { for (void* p : c->temp) c->dfree(p); c->temp.swap(saved); if (!old) delete nc; else { c->bp_cache = nullptr; } throw; }
+    } catch (...) { c->arena_bypass = false; for (void* p : c->temp) c->dfree(p); c->temp.swap(saved); if (!old) delete nc; else { c->bp_cache = nullptr; } throw; }
+    c->arena_bypass = false;
     for (void* p : c->temp) nc->owned.push_back(p);
     c->temp.clear(); c->temp.swap(saved);
     nc->seq = seq; nc->mode = o.mode; nc->normalize = o.normalize; nc->hermitize = o.hermitize; nc->want_diff = want_diff;
@@ -502,27 +505,53 @@ struct GateBatch {
 };
 
 void GateBatch::absorb_outer(bool inverse) {   // forward: on A (psi~); inverse: on the Q factor
-    size_t maxouter = 0;
-    for (int jj : LJ) { SiteJob& J = jobs[jj]; maxouter = std::max(maxouter, J.outer.size()); }
-    for (size_t s = 0; s < maxouter; ++s) {
-      std::vector<ModeApplyDesc> ma; long long maxtiles = 1;
-      for (int j : LJ) {
-        SiteJob& J = jobs[j];
-        if (s >= J.outer.size()) continue;
-        long long Lp = 1;
-        for (size_t i = 0; i < s; ++i) Lp *= c->chi[c->inc[J.v][J.outer[i]]];
-        int x = c->chi[c->inc[J.v][J.outer[s]]];
-        long long R = J.Po / (Lp * x) * ncols[j];
-        cplx* buf = inverse ? J.Q : J.A;
-        ModeApplyDesc d; d.in = buf; d.out = buf; d.m = inverse ? J.invroot[s] : J.root[s];
-        d.L = (int)Lp; d.n = x; d.np = x; d.R = (int)R; d.in_sb = Lp; d.in_sr = Lp * x; d.out_sb = Lp; d.out_sr = Lp * x;
-        d.ldm = x; d.flags = inverse ? 3 : 0;      // Q * dag(M^-1/2): element (c, b) = conj(Minv[b, c])
-        ma.push_back(d);
-        maxtiles = std::max(maxtiles, (Lp * R + MA_BM - 1) / MA_BM);
-      }
-      (void)maxtiles;
-      launch_mode_apply(c, TNQS_KC_MODE_APPLY, ma);
+  // Fast path: every outer leg of the same dimension N in {8, 16}, 2 or 3 of them: each column of the matricised tensor
+  // is a contiguous N^F slab, so the fused slab kernel absorbs all the legs in one pass, in place (k_absorb_slab).
+  std::vector<int> generic;
+  std::vector<SlabDesc> slab[2];                 // [0]: N = 8, [1]: N = 16
+  int maxcols[2] = {0, 0};
+  for (int j : LJ) {
+    SiteJob& J = jobs[j];
+    const int F = (int)J.outer.size();
+    int N = F ? c->chi[c->inc[J.v][J.outer[0]]] : 0;
+    bool ok = !dmma_disabled() && (F == 2 || F == 3) && (N == 8 || N == 16) && ncols[j] >= 1;
+    for (int l : J.outer) ok = ok && c->chi[c->inc[J.v][l]] == N;
+    if (!ok) { if (F) generic.push_back(j); continue; }
+    cplx* buf = inverse ? J.Q : J.A;
+    SlabDesc d; d.t = buf; d.x = buf; d.F = F;
+    long long st = 1;
+    for (int i = 0; i < 3; ++i) { d.g[i] = i < F ? st : 0; d.m[i] = i < F ? (inverse ? J.invroot[i] : J.root[i]) : nullptr; st *= N; }
+    d.gs = J.Po; d.gw = 2 * J.Po; d.nslabs = ncols[j]; d.flags = inverse ? 3 : 0;
+    slab[N == 16].push_back(d); maxcols[N == 16] = std::max(maxcols[N == 16], ncols[j]);
+  }
+  for (int w = 0; w < 2; ++w) {
+    if (slab[w].empty()) continue;
+    const int N = w ? 16 : 8;
+    SlabDesc* dsd = c->upload(slab[w]);
+    dim3 grid((unsigned)((maxcols[w] + 1) / 2 * 2), (unsigned)slab[w].size(), 1);
+    size_t smem = (size_t)(N + 2) * N * N * sizeof(cplx);
+    if (w) LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<16>, grid, 256, smem, dsd);
+    else LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<8>, grid, 256, smem, dsd);
+  }
+  size_t maxouter = 0;
+  for (int jj : generic) { SiteJob& J = jobs[jj]; maxouter = std::max(maxouter, J.outer.size()); }
+  for (size_t s = 0; s < maxouter; ++s) {
+    std::vector<ModeApplyDesc> ma;
+    for (int j : generic) {
+      SiteJob& J = jobs[j];
+      if (s >= J.outer.size()) continue;
+      long long Lp = 1;
+      for (size_t i = 0; i < s; ++i) Lp *= c->chi[c->inc[J.v][J.outer[i]]];
+      int x = c->chi[c->inc[J.v][J.outer[s]]];
+      long long R = J.Po / (Lp * x) * ncols[j];
+      cplx* buf = inverse ? J.Q : J.A;
+      ModeApplyDesc d; d.in = buf; d.out = buf; d.m = inverse ? J.invroot[s] : J.root[s];
+      d.L = (int)Lp; d.n = x; d.np = x; d.R = (int)R; d.in_sb = Lp; d.in_sr = Lp * x; d.out_sb = Lp; d.out_sr = Lp * x;
+      d.ldm = x; d.flags = inverse ? 3 : 0;      // Q * dag(M^-1/2): element (c, b) = conj(Minv[b, c])
+      ma.push_back(d);
     }
+    launch_mode_apply(c, TNQS_KC_MODE_APPLY, ma);
+  }
 }
 
 void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const double* gates, const tnqs_apply_opts& o_, const int32_t* remote) {
@@ -594,7 +623,8 @@ void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const d
   {
     std::vector<PermDesc> lp; for (int j : LJ) lp.push_back(pd[j]);
     PermDesc* dpd = c->upload(lp);
-    unsigned gx = (unsigned)std::min<long long>((maxtot + 255) / 256, 2048);
+    long long maxPo = 1; for (int j : LJ) maxPo = std::max(maxPo, jobs[j].Po);
+    unsigned gx = (unsigned)((maxPo + 255) / 256); (void)maxtot;
     if (!lp.empty()) LAUNCH(c, TNQS_KC_PERMUTE, k_permute, dim3(gx, (unsigned)lp.size()), 256, 0, dpd);
   }
   for (int j : LJ) dbg_norm(c, "matricised", j, jobs[j].A, (size_t)c->site_n[jobs[j].v]);
@@ -849,7 +879,8 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
     }
     std::vector<PermDesc> lp; for (int j : LJ) lp.push_back(pd[j]);
     PermDesc* dpd = c->upload(lp);
-    unsigned gx = (unsigned)std::min<long long>((maxtot2 + 255) / 256, 2048);
+    long long maxPo = 1; for (int j : LJ) maxPo = std::max(maxPo, jobs[j].Po);
+    unsigned gx = (unsigned)((maxPo + 255) / 256); (void)maxtot2;
     if (!lp.empty()) LAUNCH(c, TNQS_KC_PERMUTE, k_permute, dim3(gx, (unsigned)lp.size()), 256, 0, dpd);
   }
   // ---- 9. commit: bond dimensions, site pointers, messages <- diag(S) (apply_gates.jl:105-119) ----

@@ -172,7 +172,7 @@ def test_one_site_gates(E):
 
 def gate_case(E, g, psi_o, edges, gate_arrs, kw, sweeps=6, flip=None):
     bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=sweeps)
-    be = E.update(to_engine(psi_o, chi_cap=16), maxiter=sweeps)
+    be = E.update(to_engine(psi_o, chi_cap=max(16, psi_o.maxvirtualdim())), maxiter=sweeps)
     details = []
     for i, e in enumerate(edges):
         a, c = int(g.esrc[e]), int(g.edst[e])
@@ -210,6 +210,23 @@ def test_two_site_gate_batch(E, kw):
             u, _ = np.linalg.qr(h)
             arrs.append(u.reshape(2, 2, 2, 2))
         gate_case(E, g, psi_o, grp, arrs, kw, flip=[i % 2 for i in range(len(grp))])
+
+
+@pytest.mark.parametrize("chi", [8, 16])
+def test_two_site_gate_uniform_chi_tensor_core_paths(E, chi):
+    # uniform chi in {8, 16}: fused slab absorption on the matricised tensors, CholeskyQR2, tensor-core leg kernels
+    g = G.named_grid((3, 4)) if chi == 16 else G.named_grid((4, 4))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=chi, seed=61)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    grp = G.grid_edge_color(g)[1]
+    rs = np.random.default_rng(3)
+    arrs = []
+    for e in grp:
+        h = rs.normal(size=(4, 4)) + 1j * rs.normal(size=(4, 4))
+        u, _ = np.linalg.qr(h)
+        arrs.append(u.reshape(2, 2, 2, 2))
+    gate_case(E, g, psi_o, grp, arrs, dict(maxdim=chi, cutoff=1e-10, normalize_tensors=True), sweeps=3)
 
 
 def test_two_site_gate_ragged_and_degree3(E):
