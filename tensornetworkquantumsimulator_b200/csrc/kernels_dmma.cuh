@@ -152,8 +152,9 @@ __global__ void __launch_bounds__(256, 2) k_close_dmma(const CloseDmmaDesc* __re
   extern __shared__ double red[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 2, q = lane & 3;
-  const int s = q & 1, di = q >> 1, wl = r >> 1, part = r & 1;
+  const int wl = r >> 1, part = r & 1;
   long long NF = N; for (int i = 1; i < d.F; ++i) NF *= N;
+  // k-step = 4 consecutive slab indices (i1 = 4*j4 + q) at fixed s: an X fragment load touches 4 x 64 contiguous bytes
   const long long ksteps = NF / 2;
   const long long per = (ksteps + d.nsplit - 1) / d.nsplit;
   const long long k_begin = (long long)blockIdx.x * per, k_end = min(ksteps, k_begin + per);
@@ -172,10 +173,12 @@ __global__ void __launch_bounds__(256, 2) k_close_dmma(const CloseDmmaDesc* __re
       const long long kk = kap + 8 * u;
       const bool ok = kk < k_end;
       const long long kq = ok ? kk : kap;
-      const int j = (int)(kq % (N / 2));
-      const long long rest = kq / (N / 2);
+      const int s = (int)(kq & 1);
+      const long long jj = kq >> 1;
+      const int j4 = (int)(jj % (N / 4));
+      const long long rest = jj / (N / 4);
       const int i2 = (int)(rest % N), i3 = (int)(rest / N);
-      const int i1 = 2 * j + di;
+      const int i1 = 4 * j4 + q;
       const long long sigma = i1 + (long long)N * i2 + (long long)N * N * i3;
       const long long toff = s + i1 * d.g[0] + i2 * d.g[1] + (d.F == 3 ? i3 * d.g[2] : 0);
 #pragma unroll

@@ -22,7 +22,9 @@ __device__ __forceinline__ void rr_pair(int N, int s, int i, int& p, int& q) {
 // One-sided Jacobi on the columns of W (m x n, leading dim ldw); the same rotations are accumulated into the
 // rows of V (nv x n, leading dim ldv) unless V is null.  On exit the columns of W are mutually orthogonal.
 // Every thread of the CTA must call.  Returns the number of sweeps used, or -1 if not converged.
-__device__ int jacobi_columns(cplx* W, int ldw, int m, cplx* V, int ldv, int nv, int n) {
+// RPL = rows per lane held in registers between the inner products and the rotation (m, nv <= 32 * RPL).
+template <int RPL>
+__device__ int jacobi_columns_t(cplx* W, int ldw, int m, cplx* V, int ldv, int nv, int n) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int N = n + (n & 1);
   if (n < 2) return 0;
@@ -46,34 +48,53 @@ __device__ int jacobi_columns(cplx* W, int ldw, int m, cplx* V, int ldv, int nv,
         if (q >= n) continue;
         cplx* wp = W + (size_t)p * ldw;
         cplx* wq = W + (size_t)q * ldw;
+        cplx a[RPL], b[RPL];
         double al = 0, be = 0, gr = 0, gi = 0;
-        for (int r = lane; r < m; r += 32) {
-          cplx a = wp[r], b = wq[r];
-          al += cabs2(a); be += cabs2(b);
-          gr += a.x * b.x + a.y * b.y;         // conj(a) * b
-          gi += a.x * b.y - a.y * b.x;
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) {
+          const int r = lane + 32 * t;
+          a[t] = r < m ? wp[r] : cmake(0, 0); b[t] = r < m ? wq[r] : cmake(0, 0);
+          al += cabs2(a[t]); be += cabs2(b[t]);
+          gr += a[t].x * b[t].x + a[t].y * b[t].y;         // conj(a) * b
+          gi += a[t].x * b[t].y - a[t].y * b[t].x;
         }
         al = warp_sum(al); be = warp_sum(be); gr = warp_sum(gr); gi = warp_sum(gi);
         double g2 = gr * gr + gi * gi;
         if (!(g2 > tol2 * al * be) || g2 == 0.0 || al <= tiny2 || be <= tiny2) continue;
         if (g2 > conv2 * al * be) rotated = 1;
-        double ag = sqrt(g2);
-        cplx ph = cmake(gr / ag, -gi / ag);           // e^{-i phi}: makes <a_p, ph*a_q> real positive
-        double zeta = (be - al) / (2.0 * ag);
-        double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
-        for (int r = lane; r < m; r += 32) {
-          cplx a = wp[r], b = cmul(ph, wq[r]);
-          wp[r] = cmake(c * a.x - sn * b.x, c * a.y - sn * b.y);
-          wq[r] = cmake(sn * a.x + c * b.x, sn * a.y + c * b.y);
+        // rotation parameters on one lane, then broadcast: FP64 sqrt / divide are long multi-instruction sequences and
+        // 32 redundant copies per pair would saturate the SM's FP64 pipe
+        double c = 0, sn = 0, phx = 0, phy = 0;
+        if (lane == 0) {
+          double ag = sqrt(g2);
+          phx = gr / ag; phy = -gi / ag;                 // e^{-i phi}: makes <a_p, ph*a_q> real positive
+          double zeta = (be - al) / (2.0 * ag);
+          double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          c = 1.0 / sqrt(1.0 + t * t); sn = c * t;
+        }
+        c = __shfl_sync(0xffffffffu, c, 0); sn = __shfl_sync(0xffffffffu, sn, 0);
+        phx = __shfl_sync(0xffffffffu, phx, 0); phy = __shfl_sync(0xffffffffu, phy, 0);
+        const cplx ph = cmake(phx, phy);
+#pragma unroll
+        for (int u = 0; u < RPL; ++u) {
+          const int r = lane + 32 * u;
+          if (r < m) {
+            cplx x = a[u], y = cmul(ph, b[u]);
+            wp[r] = cmake(c * x.x - sn * y.x, c * x.y - sn * y.y);
+            wq[r] = cmake(sn * x.x + c * y.x, sn * x.y + c * y.y);
+          }
         }
         if (V) {
           cplx* vp = V + (size_t)p * ldv;
           cplx* vq = V + (size_t)q * ldv;
-          for (int r = lane; r < nv; r += 32) {
-            cplx a = vp[r], b = cmul(ph, vq[r]);
-            vp[r] = cmake(c * a.x - sn * b.x, c * a.y - sn * b.y);
-            vq[r] = cmake(sn * a.x + c * b.x, sn * a.y + c * b.y);
+#pragma unroll
+          for (int u = 0; u < RPL; ++u) {
+            const int r = lane + 32 * u;
+            if (r < nv) {
+              cplx x = vp[r], y = cmul(ph, vq[r]);
+              vp[r] = cmake(c * x.x - sn * y.x, c * x.y - sn * y.y);
+              vq[r] = cmake(sn * x.x + c * y.x, sn * x.y + c * y.y);
+            }
           }
         }
       }
@@ -82,6 +103,13 @@ __device__ int jacobi_columns(cplx* W, int ldw, int m, cplx* V, int ldv, int nv,
     if (!__syncthreads_or(rotated)) return sweep + 1;
   }
   return -1;
+}
+
+__device__ int jacobi_columns(cplx* W, int ldw, int m, cplx* V, int ldv, int nv, int n) {
+  const int mx = m > nv ? m : nv;
+  if (mx <= 32) return jacobi_columns_t<1>(W, ldw, m, V, ldv, nv, n);
+  if (mx <= 64) return jacobi_columns_t<2>(W, ldw, m, V, ldv, nv, n);
+  return jacobi_columns_t<4>(W, ldw, m, V, ldv, nv, n);          // m, nv <= 128 (d * chi <= 64 in the gate path)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -316,6 +344,9 @@ __global__ void __launch_bounds__(1024) k_svd_trunc(const SvdDesc* __restrict__ 
   __syncthreads();
   int sweeps = jacobi_columns(W, mm, mm, V, nn, nn, nn);
   if (sweeps < 0 && threadIdx.x == 0) atomicOr(status, ST_NO_CONV);
+#ifdef TNQS_TRACE_SVD
+  if (threadIdx.x == 0 && blockIdx.x < 4) printf("[svd] block %d m=%d n=%d sweeps=%d\n", blockIdx.x, m, n, sweeps);
+#endif
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int j = warp; j < nn; j += nwarps) {
     double s = 0;
