@@ -169,17 +169,27 @@ class Stepper:
         self.msg_updates += info["iters"] * len(self.seq)
 
     def step(self):
+        """One Trotter layer as the exact run/refresh schedule of apply_gates (engine.circuit_schedule mirrors the rule of
+        tnqs_apply_circuit; tests/test_gpu_parity.py checks bitwise equality with apply_gates)."""
         E, g = self.E, self.g
-        vs = list(range(g.nv))
-        _, ms = self._timed(lambda: (E.apply_1site_batch(self.bpc, vs, [self.rx] * g.nv), E.apply_1site_batch(self.bpc, vs, [self.rz] * g.nv)))
-        self.other_ms += ms
-        self.gates1 += 2 * g.nv
-        for grp in self.groups:
-            self.bp()                                            # refresh: the class touches affected vertices
-            _, ms = self._timed(lambda: E.apply_2site_batch(self.bpc, grp, [self.rzz] * len(grp), apply_kwargs=self.kw))
-            self.gate_ms += ms
-            self.gates2 += len(grp)
-        self.bp()                                                # final refresh (apply_gates.jl:87-89)
+        if not hasattr(self, "sched"):
+            self.layer = [(self.rx, [v]) for v in range(g.nv)] + [(self.rz, [v]) for v in range(g.nv)]
+            for grp in self.groups:
+                self.layer += [(self.rzz, [int(g.esrc[e]), int(g.edst[e])]) for e in grp]
+            self.sched = E.circuit_schedule(g, self.layer)
+        for item in self.sched:
+            if item[0] == "refresh":
+                self.bp()
+            elif item[0] == "gates1":
+                ids = item[1]
+                _, ms = self._timed(lambda: E.apply_1site_batch(self.bpc, [self.layer[i][1][0] for i in ids], [self.layer[i][0] for i in ids]))
+                self.other_ms += ms; self.gates1 += len(ids)
+            else:
+                ids = item[1]
+                es = [g.edge_of[(self.layer[i][1][0], self.layer[i][1][1])] for i in ids]
+                fl = [0 if int(g.esrc[e]) == self.layer[i][1][0] else 1 for e, i in zip(es, ids)]
+                _, ms = self._timed(lambda: E.apply_2site_batch(self.bpc, es, [self.layer[i][0] for i in ids], flip=fl, apply_kwargs=self.kw))
+                self.gate_ms += ms; self.gates2 += len(ids)
         (z,), ms = self._timed(lambda: (E.expect(self.bpc, ("Z", [self.obs_v])),))
         self.other_ms += ms
         return z
@@ -310,7 +320,9 @@ def run_engine(args):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(st.stream)
-    zs = [st.step() for _ in range(args.steps)]
+    zs, step_wall = [], []
+    for _ in range(args.steps):
+        t0 = time.perf_counter(); zs.append(st.step()); step_wall.append(1e3 * (time.perf_counter() - t0))
     ev1.record(st.stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -367,7 +379,7 @@ def run_engine(args):
                      "traffic": {"dram_bytes_per_launch": 214.3e6, "algorithmic_bytes_per_launch": 260.0e6, "launch": "62 messages x 32 slabs (ncu --set full, profiles/r01_dmma_ncu_full_raw.csv)"},
                      "peak_source": pk["source"], "launches_profiled": int(ln[0]), "avg_launch_ms": ms[0] / max(1, ln[0]),
                      "close_kernel_tflops": close_tf},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks, "step_wall_ms": [round(x, 1) for x in step_wall],
         "expect_z_center": [float(np.real(z)) for z in zs], "setup_s": setup_s,
     }
     del zsum
@@ -487,8 +499,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--nx", type=int, default=32)
     ap.add_argument("--ny", type=int, default=32)

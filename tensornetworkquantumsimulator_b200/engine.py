@@ -283,6 +283,39 @@ def apply_gates(circuit: Sequence[tuple], psi, apply_kwargs: Optional[dict] = No
 apply_circuit = apply_gates      # src/Apply/apply_gates.jl:133
 
 
+def circuit_schedule(g: Graph, circuit: Sequence[tuple], update_cache: bool = True) -> List[tuple]:
+    """The batches and BP refreshes `apply_gates` / tnqs_apply_circuit execute for an ordered gate list, by the reference's
+    rule (src/Apply/apply_gates.jl:56-89): a refresh before a 2-site gate that touches a vertex touched since the last
+    refresh (1-site gates mark vertices too), consecutive independent gates of equal arity form one batch, final refresh.
+    Returns [("refresh",) | ("gates1", [gate indices]) | ("gates2", [gate indices])].  Runs are defined by the rule, not by
+    colour: gates of a new colour class that precede its first overlapping gate are applied before the refresh."""
+    verts = []
+    for gate in circuit:
+        v = gate[1] if isinstance(gate[1], list) else [gate[1]]
+        verts.append([_vid(g, x) for x in v])
+    out: List[tuple] = []
+    affected, inbatch, batch, arity_b = set(), set(), [], 0
+
+    def flush():
+        nonlocal batch, inbatch
+        if batch:
+            out.append(("gates1" if arity_b == 1 else "gates2", batch))
+        batch, inbatch = [], set()
+
+    for i, vs in enumerate(verts):
+        arity = len(vs)
+        if update_cache and arity == 2 and any(v in affected for v in vs):
+            flush(); out.append(("refresh",)); affected = set()
+        if batch and (arity != arity_b or any(v in inbatch for v in vs)):
+            flush()
+        arity_b = arity
+        batch.append(i); inbatch |= set(vs); affected |= set(vs)
+    flush()
+    if update_cache:
+        out.append(("refresh",))
+    return out
+
+
 def apply_2site_batch(bpc: BeliefPropagationCache, edges: Sequence[int], gates: Sequence[np.ndarray], flip: Optional[Sequence[int]] = None,
                       apply_kwargs: Optional[dict] = None):
     """In place: one vertex-disjoint batch of two-site gates (apply_gate!, src/Apply/apply_gates.jl:95-122).

@@ -481,3 +481,41 @@ def test_partitioned_gates_match_single_handle(E):
         for lv, gv in enumerate(lgs[r].l2g_v):
             if lgs[r].owned[lv]:
                 assert rel(tl[lv], tr[int(gv)]) < 1e-12, f"site {gv} on rank {r}"
+
+
+def test_bench_phase_sequence_equals_apply_gates(E):
+    # bench.py times one Trotter layer as the explicit run / refresh schedule of engine.circuit_schedule; executing that
+    # schedule call by call must be bit-identical to apply_gates (tnqs_apply_circuit with the affected-vertices rule)
+    g = G.named_grid((4, 4))
+    groups = G.grid_edge_color(g)
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=4, seed=9)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    seq = G.forest_cover_edge_sequence(g)
+    kw = dict(maxdim=4, cutoff=1e-10, normalize_tensors=True)
+    bp_kw = dict(maxiter=25, tolerance=1e-8)
+    rx, rz, rzz = gates.gate_array(("Rx", [0], 0.5)), gates.gate_array(("Rz", [0], 0.4)), gates.gate_array(("Rzz", [0, 1], 0.25))
+    a = E.update(to_engine(psi_o, chi_cap=4), edge_sequence=seq, **bp_kw)
+    b = a.copy()
+    layer = [(rx, [v]) for v in range(g.nv)] + [(rz, [v]) for v in range(g.nv)]
+    for grp in groups:
+        layer += [(rzz, [int(g.esrc[e]), int(g.edst[e])]) for e in grp]
+    info = {}
+    a, errs = E.apply_gates(layer, a, apply_kwargs=kw, bp_update_kwargs=bp_kw, inplace=True, info=info)
+    sched = E.circuit_schedule(g, layer)
+    for item in sched:
+        if item[0] == "refresh":
+            E.update(b, edge_sequence=seq, inplace=True, **bp_kw)
+        elif item[0] == "gates1":
+            E.apply_1site_batch(b, [layer[i][1][0] for i in item[1]], [layer[i][0] for i in item[1]])
+        else:
+            es = [g.edge_of[(layer[i][1][0], layer[i][1][1])] for i in item[1]]
+            E.apply_2site_batch(b, es, [layer[i][0] for i in item[1]], flip=[0 if int(g.esrc[e]) == layer[i][1][0] else 1 for e, i in zip(es, item[1])], apply_kwargs=kw)
+    assert info["refreshes"] == 5 == sum(1 for it in sched if it[0] == "refresh")
+    # runs are defined by the rule, not by colour: the first gates of the third class precede its refresh
+    assert [len(it[1]) for it in sched if it[0] == "gates2"] != [len(grp) for grp in groups]
+    assert list(a.psi.bond_dims()) == list(b.psi.bond_dims())
+    for v in range(g.nv):
+        assert np.array_equal(a.psi[v], b.psi[v])
+    for k in range(2 * g.ne):
+        assert np.array_equal(E.message(a, k), E.message(b, k))
