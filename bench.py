@@ -376,7 +376,7 @@ def run_engine(args):
         "phase_ms_per_step": {"bp": bp_ms / args.steps, "two_site_gates": gate_ms / args.steps, "one_site_and_expect": other_ms / args.steps},
         "roofline": {"bound": "tensor", "kernel": "k_absorb_slab<16> (fused BP leg absorption, DMMA)", "achieved": apply_tf, "peak": pk["fp64_tflops_sustained"],
                      "unit": "TFLOP/s", "frac": (apply_tf / pk["fp64_tflops_sustained"]) if apply_tf else None,
-                     "traffic": {"dram_bytes_per_launch": 214.3e6, "algorithmic_bytes_per_launch": 260.0e6, "launch": "62 messages x 32 slabs (ncu --set full, profiles/r01_dmma_ncu_full_raw.csv)"},
+                     "traffic": {"dram_bytes_per_launch": 206.0e6, "algorithmic_bytes_per_launch": 260.0e6, "launch": "62 messages x 32 slabs (ncu --set full, profiles/r01_final_dmma_ncu_full_raw.csv)"},
                      "peak_source": pk["source"], "launches_profiled": int(ln[0]), "avg_launch_ms": ms[0] / max(1, ln[0]),
                      "close_kernel_tflops": close_tf},
         "gpu_launches": int(launches), "clocks": clocks, "step_wall_ms": [round(x, 1) for x in step_wall],
