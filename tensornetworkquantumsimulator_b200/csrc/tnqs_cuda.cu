@@ -68,6 +68,7 @@ static void reset_messages(tnqs_ctx* c) {
 }
 
 static size_t scratch_budget(tnqs_ctx* c) {
+  if (const char* e = getenv("TNQS_SCRATCH_MB")) { long mb = atol(e); if (mb > 0) return (size_t)mb << 20; }   // tests: force chunking
   size_t fr = 0, tot = 0;
   cudaMemGetInfo(&fr, &tot);
   size_t b = fr / 4;
@@ -913,9 +914,32 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
 static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_t* flips, const double* gates,
                              const tnqs_apply_opts& o, int32_t* ranks_out, double* err_out, double* svals_out) {
   if (n == 0) return;
-  GateBatch gb; gb.c = c;
-  gb.stage1(n, es, flips, gates, o, nullptr);
-  gb.stage2(nullptr, ranks_out, err_out, svals_out);
+  // The gates of a batch are independent (vertex-disjoint; none reads a message another one writes), so a batch whose
+  // temporaries (about four copies of the touched site tensors) would not fit is processed in chunks.
+  std::set<int> seen;
+  for (int i = 0; i < n; ++i) {
+    REQUIRE(es[i] >= 0 && es[i] < c->ne, TNQS_ERR_INVALID_ARG, "tnqs_apply_2site: edge out of range");
+    REQUIRE(seen.insert(c->esrc[es[i]]).second && seen.insert(c->edst[es[i]]).second, TNQS_ERR_OVERLAPPING_BATCH,
+            "tnqs_apply_2site: gates of a batch share a vertex");
+  }
+  const size_t budget = scratch_budget(c);
+  const cplx* g = (const cplx*)gates;
+  int i0 = 0; size_t goff = 0;
+  while (i0 < n) {
+    size_t bytes = 0, gcount = 0; int i1 = i0;
+    while (i1 < n) {
+      int e = es[i1], d = c->d[c->esrc[e]];
+      size_t need = (size_t)5 * (c->site_n[c->esrc[e]] + c->site_n[c->edst[e]]) * sizeof(cplx);
+      if (i1 > i0 && bytes + need > budget) break;
+      bytes += need; gcount += (size_t)d * d * d * d; ++i1;
+    }
+    GateBatch gb; gb.c = c;
+    gb.stage1(i1 - i0, es + i0, flips ? flips + i0 : nullptr, (const double*)(g + goff), o, nullptr);
+    gb.stage2(nullptr, ranks_out ? ranks_out + i0 : nullptr, err_out ? err_out + i0 : nullptr,
+              svals_out ? svals_out + (size_t)i0 * c->chi_cap : nullptr);
+    if (i1 < n) c->release_temps();
+    goff += gcount; i0 = i1;
+  }
 }
 
 extern "C" int32_t tnqs_apply_2site(tnqs_ctx* c, int32_t n, const int32_t* e, const int32_t* flip, const double* gates,

@@ -519,3 +519,34 @@ def test_bench_phase_sequence_equals_apply_gates(E):
         assert np.array_equal(a.psi[v], b.psi[v])
     for k in range(2 * g.ne):
         assert np.array_equal(E.message(a, k), E.message(b, k))
+
+
+def test_chunked_levels_and_gate_batches(E, monkeypatch):
+    # a 1 MB scratch budget forces BP levels into sub-levels (staged messages + commit pass) and gate batches into chunks
+    monkeypatch.setenv("TNQS_SCRATCH_MB", "1")
+    g = G.named_grid((4, 4))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=8, seed=71)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    seq = G.forest_cover_edge_sequence(g)
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=2, edge_sequence=seq)
+    be = E.update(to_engine(psi_o, chi_cap=8), maxiter=2, edge_sequence=seq)
+    check_messages(E, be, bo)
+    bj = O.BeliefPropagationCache(psi_o)
+    bj.messages = {k: O.updated_message(bj, k) for k in range(2 * g.ne)}
+    ej = E.update(to_engine(psi_o, chi_cap=8), maxiter=1, edge_sequence=np.arange(2 * g.ne), mode="jacobi")
+    check_messages(E, ej, bj)
+    grp = G.grid_edge_color(g)[2]
+    arr = gates.gate_array(("Rxx", [0, 1], 0.6))
+    dets = []
+    for e in grp:
+        det = {}
+        O.apply_gate(bo, arr, [int(g.esrc[e]), int(g.edst[e])], maxdim=8, cutoff=1e-12, detail=det)
+        dets.append(det)
+    ranks, errs, sv = E.apply_2site_batch(be, grp, [arr] * len(grp), apply_kwargs=dict(maxdim=8, cutoff=1e-12))
+    for i, det in enumerate(dets):
+        assert ranks[i] == det["rank"]
+        assert rel(sv[i, :ranks[i]], det["svals"]) < MSG_TOL
+    te = be.psi.tensors()
+    for e in grp:
+        assert rel(two_site(g, te, e), two_site(g, bo.network.tensors, e)) < 1e-9
