@@ -62,19 +62,14 @@ __device__ int jacobi_columns_t(cplx* W, int ldw, int m, cplx* V, int ldv, int n
         double g2 = gr * gr + gi * gi;
         if (!(g2 > tol2 * al * be) || g2 == 0.0 || al <= tiny2 || be <= tiny2) continue;
         if (g2 > conv2 * al * be) rotated = 1;
-        // rotation parameters on one lane, then broadcast: FP64 sqrt / divide are long multi-instruction sequences and
-        // 32 redundant copies per pair would saturate the SM's FP64 pipe
-        double c = 0, sn = 0, phx = 0, phy = 0;
-        if (lane == 0) {
-          double ag = sqrt(g2);
-          phx = gr / ag; phy = -gi / ag;                 // e^{-i phi}: makes <a_p, ph*a_q> real positive
-          double zeta = (be - al) / (2.0 * ag);
-          double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          c = 1.0 / sqrt(1.0 + t * t); sn = c * t;
-        }
-        c = __shfl_sync(0xffffffffu, c, 0); sn = __shfl_sync(0xffffffffu, sn, 0);
-        phx = __shfl_sync(0xffffffffu, phx, 0); phy = __shfl_sync(0xffffffffu, phy, 0);
-        const cplx ph = cmake(phx, phy);
+        // rotation parameters with reciprocal-square-root / reciprocal intrinsics: the chain of FP64 sqrt and divide
+        // subroutines (about 1000 dependent cycles) was the critical path of a Jacobi step
+        const double rg = rsqrt(g2);                              // 1 / |gamma|
+        const cplx ph = cmake(gr * rg, -gi * rg);                 // e^{-i phi}: makes <a_p, ph*a_q> real positive
+        const double zeta = 0.5 * (be - al) * rg;
+        const double z2 = fma(zeta, zeta, 1.0);
+        const double t = copysign(__drcp_rn(fabs(zeta) + z2 * rsqrt(z2)), zeta);
+        const double c = rsqrt(fma(t, t, 1.0)), sn = c * t;
 #pragma unroll
         for (int u = 0; u < RPL; ++u) {
           const int r = lane + 32 * u;
@@ -319,19 +314,21 @@ struct SvdDesc {
   int maxdim; double cutoff; int has_cutoff; int normalize; int cap; int mindim;
 };
 
-// dynamic shared memory: [W | V] if work == null, then sigma[nn] doubles, perm[nn] ints
-__global__ void __launch_bounds__(1024) k_svd_trunc(const SvdDesc* __restrict__ descs, int* status, size_t smem_wv_bytes) {
+// dynamic shared memory: W (mm x nn) if work == null, then sigma[nn] doubles, perm[nn] ints.
+// Only W = theta' * V_jacobi is iterated (half the shared-memory traffic and footprint, two CTAs per SM); the right
+// factor of the KEPT singular triplets is recovered afterwards from theta'^H W_j = sigma_j^2 v_j, whose relative error
+// eps * sigma_max / sigma_j stays below 1e-11 for anything a relative cutoff of 1e-10 on sigma^2 can keep.
+__global__ void __launch_bounds__(512, 2) k_svd_trunc(const SvdDesc* __restrict__ descs, int* status, size_t smem_wv_bytes) {
   const SvdDesc d = descs[blockIdx.x];
   extern __shared__ cplx ssm[];
   const int m = d.m, n = d.n;
   const bool swapped = m < n;
   const int mm = swapped ? n : m, nn = swapped ? m : n;
   cplx* W = d.work ? d.work : ssm;
-  cplx* V = W + (size_t)mm * nn;
   double* sigma = (double*)((char*)ssm + smem_wv_bytes);
   int* perm = (int*)(sigma + nn);
   __shared__ int sh_rank;
-  __shared__ double sh_norm;
+  __shared__ double sh_norm, sh_fro2;
   for (int idx = threadIdx.x; idx < mm * nn; idx += blockDim.x) {
     int r = idx % mm, c = idx / mm;
     cplx v;
@@ -339,10 +336,8 @@ __global__ void __launch_bounds__(1024) k_svd_trunc(const SvdDesc* __restrict__ 
     else v = cconj(d.theta[c + (size_t)r * m]);        // W = theta'^H
     W[idx] = v;
   }
-  for (int idx = threadIdx.x; idx < nn * nn; idx += blockDim.x)
-    V[idx] = cmake((idx % nn) == (idx / nn) ? 1.0 : 0.0, 0.0);
   __syncthreads();
-  int sweeps = jacobi_columns(W, mm, mm, V, nn, nn, nn);
+  int sweeps = jacobi_columns(W, mm, mm, nullptr, 0, 0, nn);
   if (sweeps < 0 && threadIdx.x == 0) atomicOr(status, ST_NO_CONV);
 #ifdef TNQS_TRACE_SVD
   if (threadIdx.x == 0 && blockIdx.x < 4) printf("[svd] block %d m=%d n=%d sweeps=%d\n", blockIdx.x, m, n, sweeps);
@@ -365,12 +360,12 @@ __global__ void __launch_bounds__(1024) k_svd_trunc(const SvdDesc* __restrict__ 
   if (threadIdx.x == 0) {
     // NDTensors truncate!: P = S^2 descending, sequential tail sums
     int k = nn;
-    double t = 0.0, err = 0.0;
+    double t = 0.0, err = 0.0, fro2 = 0.0;
+    for (int i = 0; i < nn; ++i) { double s = sigma[perm[i]]; fro2 += s * s; }
     if (k > 1) {
       int maxdim = d.maxdim > 0 ? min(d.maxdim, k) : k;
       while (k > maxdim) { double s = sigma[perm[k - 1]]; t += s * s; --k; }
-      double scale = 0.0;
-      for (int i = 0; i < nn; ++i) { double s = sigma[perm[i]]; scale += s * s; }
+      double scale = fro2;
       if (scale == 0.0) scale = 1.0;
       if (d.has_cutoff) {
         while (k > d.mindim) {
@@ -385,13 +380,14 @@ __global__ void __launch_bounds__(1024) k_svd_trunc(const SvdDesc* __restrict__ 
     double nrm = 0.0;
     for (int i = 0; i < k; ++i) { double s = sigma[perm[i]]; nrm += s * s; }
     nrm = sqrt(nrm);
-    sh_rank = k; sh_norm = (d.normalize && nrm > 0.0) ? 1.0 / nrm : 1.0;
+    sh_rank = k; sh_norm = (d.normalize && nrm > 0.0) ? 1.0 / nrm : 1.0; sh_fro2 = fro2;
     if (d.rank) *d.rank = k;
     if (d.truncerr) *d.truncerr = err;
   }
   __syncthreads();
   const int rank = sh_rank;
   const double sn = sh_norm;
+  const double tiny = sqrt((double)mm) * TNQS_EPS * sqrt(sh_fro2);      // columns below this are rounding noise
   for (int u = threadIdx.x; u < d.cap; u += blockDim.x)
     if (d.svals) d.svals[u] = u < rank ? sigma[perm[u]] * sn : 0.0;
   for (int idx = threadIdx.x; idx < rank * rank; idx += blockDim.x) {
@@ -400,21 +396,29 @@ __global__ void __launch_bounds__(1024) k_svd_trunc(const SvdDesc* __restrict__ 
     if (d.msg_a) d.msg_a[idx] = v;
     if (d.msg_b) d.msg_b[idx] = v;
   }
-  // factors: not swapped: U sqrt(S) = W_j / sqrt(sigma_j), sqrt(S) conj(V);  swapped: roles exchanged
+  // factors.  Left-hand factor of the iterated matrix: W_j / sqrt(sigma_j); the other one from theta' and W_j.
+  //   not swapped (W = theta' V):  r1 = U sqrt(S) = W_j / sqrt(s);  r2[i,u] = sqrt(s) conj(V[i,j]) = (sum_k theta'[k,i] conj(W[k,j])) / s^1.5
+  //   swapped (W = theta'^H U):    r2[i,u] = conj(W[i,j]) / sqrt(s); r1[i,u] = sqrt(s) U[i,j]   = (sum_k theta'[i,k] W[k,j]) / s^1.5
   for (int idx = threadIdx.x; idx < m * rank; idx += blockDim.x) {
     int i = idx % m, u = idx / m, j = perm[u];
     double s = sigma[j];
-    cplx v;
+    cplx v = cmake(0, 0);
     if (!swapped) { double f = s > 0.0 ? 1.0 / sqrt(s) : 0.0; v = cscale(W[i + (size_t)j * mm], f); }
-    else { v = cscale(V[i + (size_t)j * nn], sqrt(s)); }
+    else if (s > tiny) {
+      for (int k = 0; k < n; ++k) cfma(v, d.theta[i + (size_t)k * m], W[k + (size_t)j * mm]);
+      v = cscale(v, 1.0 / (s * sqrt(s)));
+    }
     d.r1out[idx] = v;
   }
   for (int idx = threadIdx.x; idx < n * rank; idx += blockDim.x) {
     int i = idx % n, u = idx / n, j = perm[u];
     double s = sigma[j];
-    cplx v;
-    if (!swapped) { v = cscale(cconj(V[i + (size_t)j * nn]), sqrt(s)); }
-    else { double f = s > 0.0 ? 1.0 / sqrt(s) : 0.0; v = cscale(cconj(W[i + (size_t)j * mm]), f); }
+    cplx v = cmake(0, 0);
+    if (swapped) { double f = s > 0.0 ? 1.0 / sqrt(s) : 0.0; v = cscale(cconj(W[i + (size_t)j * mm]), f); }
+    else if (s > tiny) {
+      for (int k = 0; k < m; ++k) cfma_cb(v, d.theta[k + (size_t)i * m], W[k + (size_t)j * mm]);
+      v = cscale(v, 1.0 / (s * sqrt(s)));
+    }
     d.r2out[idx] = v;
   }
 }

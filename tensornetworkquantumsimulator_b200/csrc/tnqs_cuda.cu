@@ -812,8 +812,8 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
       s.maxdim = o.maxdim; s.has_cutoff = !std::isnan(o.cutoff); s.cutoff = s.has_cutoff ? o.cutoff : 0.0;
       s.normalize = o.normalize_tensors; s.cap = cap; s.mindim = 1;
       int mm = std::max(m, nn), mn = std::min(m, nn);
-      size_t wv = ((size_t)mm * mn + (size_t)mn * mn) * sizeof(cplx);
-      if (wv + mn * 12 + 64 <= 190 * 1024) { s.work = nullptr; svd_smem_wv = std::max(svd_smem_wv, wv); }
+      size_t wv = (size_t)mm * mn * sizeof(cplx);                      // only W = theta' V is iterated (kernels_small.cuh)
+      if (wv + mn * 12 + 64 <= 100 * 1024) { s.work = nullptr; svd_smem_wv = std::max(svd_smem_wv, wv); }
       else { s.work = c->talloc<cplx>(wv / sizeof(cplx)); any_global = true; }
       svd_maxn = std::max(svd_maxn, mn);
     }
@@ -825,7 +825,7 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
     LAUNCH(c, TNQS_KC_SVD, k_theta, n, 256, 0, dtd);
     // ---- 6. Jacobi SVD + truncation (simple_update.jl:46-61) ----
     SvdDesc* dsv = c->upload(sv);
-    int threads = 32 * std::max(1, std::min(32, (svd_maxn + 1) / 2));
+    int threads = 32 * std::max(1, std::min(16, (svd_maxn + 1) / 2));
     size_t smem = svd_smem_wv + (size_t)svd_maxn * 12 + 64;
     LAUNCH(c, TNQS_KC_SVD, k_svd_trunc, n, threads, smem, dsv, c->d_status, svd_smem_wv);
   }
@@ -1224,7 +1224,7 @@ extern "C" int32_t tnqs_symmetric_gauge(tnqs_ctx* c, double regularization) {
       s.theta = m.c; s.m = x; s.n = x; s.work = nullptr; s.r1out = c->talloc<cplx>((size_t)x * x); s.r2out = c->talloc<cplx>((size_t)x * x);
       s.svals = d_sv + (size_t)e * c->chi_cap; s.rank = d_rank + e; s.truncerr = d_err + e; s.msg_a = nullptr; s.msg_b = nullptr;
       s.maxdim = 0; s.cutoff = 0; s.has_cutoff = 0; s.normalize = 0; s.cap = c->chi_cap; s.mindim = 1;
-      wvmax = std::max(wvmax, (size_t)2 * x * x * sizeof(cplx));
+      wvmax = std::max(wvmax, (size_t)x * x * sizeof(cplx));
       for (int side = 0; side < 2; ++side) {
         SmallMatmulDesc& t = mm2[2 * e + side];
         Nmat[2 * e + side] = c->talloc<cplx>((size_t)x * x);
@@ -1238,7 +1238,7 @@ extern "C" int32_t tnqs_symmetric_gauge(tnqs_ctx* c, double regularization) {
     SmallMatmulDesc* dmm = c->upload(mm);
     LAUNCH(c, TNQS_KC_MISC, k_small_matmul, ne, 256, 0, dmm);
     SvdDesc* dsv = c->upload(sv);
-    LAUNCH(c, TNQS_KC_SVD, k_svd_trunc, ne, threads, wvmax + (size_t)maxchi * 12 + 64, dsv, c->d_status, wvmax);
+    LAUNCH(c, TNQS_KC_SVD, k_svd_trunc, ne, std::min(threads, 512), wvmax + (size_t)maxchi * 12 + 64, dsv, c->d_status, wvmax);
     SmallMatmulDesc* dmm2 = c->upload(mm2);
     LAUNCH(c, TNQS_KC_MISC, k_small_matmul, 2 * ne, 256, 0, dmm2);
     int st = c->read_status();
