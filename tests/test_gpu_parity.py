@@ -550,3 +550,44 @@ def test_chunked_levels_and_gate_batches(E, monkeypatch):
     te = be.psi.tensors()
     for e in grp:
         assert rel(two_site(g, te, e), two_site(g, bo.network.tensors, e)) < 1e-9
+
+
+def test_config_c3_eagle_kicked_ising_small(E):
+    # BASELINE config C3 scaled down: 127-qubit Eagle heavy-hex, kicked Ising (Rx(0.4) on all, Rzz(pi/2) in 3 colour classes),
+    # 2 steps, maxdim=4, cutoff=1e-12, <Z> on all sites  (examples/heavyhexIsing_dynamics.jl:15-29)
+    g = G.eagle_heavy_hex()
+    groups = G.edge_color(g)
+    assert len(groups) == 3
+    layer = [("Rx", [g.names[v]], 0.4) for v in range(g.nv)]
+    for grp in groups:
+        layer += [("Rzz", [g.names[int(g.esrc[e])], g.names[int(g.edst[e])]], math.pi / 2) for e in grp]
+    kw = dict(maxdim=4, cutoff=1e-12, normalize_tensors=True)
+    psi_o, errs_o = O.apply_gates(layer * 2, O.tensornetworkstate(lambda v: "↑", g), apply_kwargs=kw)
+    psi_e, errs_e = E.apply_gates(layer * 2, E.tensornetworkstate(lambda v: "↑", g, chi_cap=4), apply_kwargs=kw)
+    assert list(psi_e.bond_dims()) == list(psi_o.bond_dims())
+    assert np.allclose(errs_e, errs_o, atol=1e-12)
+    obs = [("Z", [g.names[v]]) for v in range(g.nv)]
+    want = np.array(O.expect_tns(psi_o, obs))
+    got = np.array(E.expect(psi_e, obs))
+    assert np.max(np.abs(got - want)) < EXP_TOL
+
+
+def test_config_c4_cubic_small(E):
+    # BASELINE config C4 scaled down: 3x3x3 open cubic lattice (coordination up to 6), [Rz, Rxx in 6 colour classes, Rz],
+    # maxdim=3, BP run to tolerance 1e-12  (examples/3dIsing_dynamics.jl:22-28)
+    g = G.named_grid((3, 3, 3))
+    groups = G.grid_edge_color(g)
+    assert len(groups) == 6
+    layer = [("Rz", [g.names[v]], 0.3) for v in range(g.nv)]
+    for grp in groups:
+        layer += [("Rxx", [g.names[int(g.esrc[e])], g.names[int(g.edst[e])]], 0.4) for e in grp]
+    layer += [("Rz", [g.names[v]], 0.3) for v in range(g.nv)]
+    kw = dict(maxdim=3, cutoff=1e-10, normalize_tensors=True)
+    bp_kw = dict(maxiter=60, tolerance=1e-12)
+    psi_o, _ = O.apply_gates(layer * 2, O.tensornetworkstate(lambda v: "↑", g), apply_kwargs=kw, bp_update_kwargs=bp_kw)
+    psi_e, _ = E.apply_gates(layer * 2, E.tensornetworkstate(lambda v: "↑", g, chi_cap=3), apply_kwargs=kw, bp_update_kwargs=bp_kw)
+    assert list(psi_e.bond_dims()) == list(psi_o.bond_dims())
+    c = (2, 2, 2)
+    want = O.expect_tns(psi_o, ("Z", [c]), cache_update_kwargs=bp_kw)
+    got = E.expect(psi_e, ("Z", [c]), cache_update_kwargs=bp_kw)
+    assert abs(got - want) < EXP_TOL
