@@ -175,15 +175,17 @@ static bool dmma_disabled() {
 }
 
 // Kernel choice and grid of one batched mode_apply launch: the tensor-core kernel when every item has n, np <= 32.
-struct ApplyLaunch { bool dmma; dim3 grid; };
+struct ApplyLaunch { bool dmma; dim3 grid; size_t smem; };
 static ApplyLaunch plan_apply_launch(const ModeApplyDesc* d, size_t count) {
-  bool ok = !dmma_disabled(); long long maxrows = 1; int maxnp = 1;
+  bool ok = !dmma_disabled(); long long maxrows = 1, maxtiles = 1; int maxnp = 1; size_t smem = 0;
   for (size_t i = 0; i < count; ++i) {
-    ok = ok && d[i].n <= 32 && d[i].np <= 32;
-    maxrows = std::max(maxrows, (long long)d[i].L * d[i].R); maxnp = std::max(maxnp, d[i].np);
+    ok = ok && d[i].n <= 64 && d[i].np <= 64;
+    const long long rows = (long long)d[i].L * d[i].R;
+    maxrows = std::max(maxrows, rows); maxnp = std::max(maxnp, d[i].np);
+    if (ok) { const int rpc = leg_rows_per_cta(d[i].np); maxtiles = std::max(maxtiles, (rows + rpc - 1) / rpc); smem = std::max(smem, leg_smem_bytes(d[i].n, d[i].np)); }
   }
-  if (ok) return {true, dim3((unsigned)((maxrows + 127) / 128), (unsigned)count, 1)};
-  return {false, dim3((unsigned)((maxrows + MA_BM - 1) / MA_BM), (unsigned)count, (unsigned)((maxnp + MA_BN - 1) / MA_BN))};
+  if (ok) return {true, dim3((unsigned)maxtiles, (unsigned)count, 1), smem};
+  return {false, dim3((unsigned)((maxrows + MA_BM - 1) / MA_BM), (unsigned)count, (unsigned)((maxnp + MA_BN - 1) / MA_BN)), 0};
 }
 struct SubLevel {
   LaunchRec slab{0, 0, dim3(), 0}, dclose{0, 0, dim3(), 0};   // DMMA fast path (kernels_dmma.cuh)
@@ -381,7 +383,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         lr.count = (int)(ma.size() - lr.off);
         if (lr.count) {
           ApplyLaunch al = plan_apply_launch(ma.data() + lr.off, lr.count);
-          lr.grid = al.grid; lr.dmma = al.dmma;
+          lr.grid = al.grid; lr.dmma = al.dmma; lr.smem = al.smem;
           sl.steps.push_back(lr);
         }
         (void)maxtiles; (void)maxcol;
@@ -419,7 +421,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
       }
       sl.close.count = (int)(mc.size() - sl.close.off); sl.close.grid = dim3(maxsplit, std::max(1, sl.close.count), 1);
       sl.close.dmma = !dmma_disabled();
-      for (size_t i = sl.close.off; i < mc.size(); ++i) sl.close.dmma = sl.close.dmma && mc[i].n <= 32 && mc[i].np <= 32;
+      for (size_t i = sl.close.off; i < mc.size(); ++i) sl.close.dmma = sl.close.dmma && mc[i].n <= 64 && mc[i].np <= 64;
       sl.reduce.count = (int)sub.size(); sl.reduce.grid = dim3(sl.reduce.count, 1, 1); sl.reduce.smem = maxnn * sizeof(cplx);
       lp.subs.push_back(sl);
     }
@@ -467,7 +469,7 @@ static void launch_mode_apply(tnqs_ctx* c, int kc, const std::vector<ModeApplyDe
   if (ma.empty()) return;
   ModeApplyDesc* dma = c->upload(ma);
   ApplyLaunch al = plan_apply_launch(ma.data(), ma.size());
-  if (al.dmma) LAUNCH(c, kc, k_leg_dmma, al.grid, 256, 0, dma);
+  if (al.dmma) LAUNCH(c, kc, k_leg_dmma, al.grid, 256, al.smem, dma);
   else LAUNCH(c, kc, k_mode_apply, al.grid, 256, 0, dma);
 }
 
@@ -485,7 +487,7 @@ static void run_plan(tnqs_ctx* c, const Plan& p) {
       }
       if (sl.gate1.count) LAUNCH(c, TNQS_KC_MISC, k_gate1, sl.gate1.grid, 256, 0, p.d_gate1 + sl.gate1.off);
       for (const LaunchRec& lr : sl.steps) {
-        if (lr.dmma) LAUNCH(c, TNQS_KC_MODE_APPLY, k_leg_dmma, lr.grid, 256, 0, p.d_apply + lr.off);
+        if (lr.dmma) LAUNCH(c, TNQS_KC_MODE_APPLY, k_leg_dmma, lr.grid, 256, lr.smem, p.d_apply + lr.off);
         else LAUNCH(c, TNQS_KC_MODE_APPLY, k_mode_apply, lr.grid, 256, 0, p.d_apply + lr.off);
       }
       if (sl.close.count) {

@@ -223,32 +223,36 @@ __global__ void __launch_bounds__(256, 2) k_close_dmma(const CloseDmmaDesc* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_leg_dmma: tensor-core version of k_mode_apply for n, np <= 32:  out[l, c, r] = sum_b in[l, b, r] * M[b, c].
+// k_leg_dmma: tensor-core version of k_mode_apply for n, np <= 64:  out[l, c, r] = sum_b in[l, b, r] * M[b, c].
 // The real 2n x 2np matrix [[Re M, Im M], [-Im M, Re M]] (interleaved) sits in shared memory; A fragments are 8-byte
-// loads straight from global memory (each input element is read by exactly one thread), C fragments are 16-byte
-// stores.  A warp owns 32 rows x 16 complex columns (4 x 4 DMMA tiles); a CTA of 8 warps covers 128 rows x 32
-// columns or 256 rows x 16 columns.  A CTA-wide barrier separates the last load from the first store, so in == out
-// is allowed.  Same descriptor and flags as k_mode_apply.
-// grid: (row tiles, items); block 256; static shared memory 64 x 72 doubles.
+// loads straight from global memory (each input element is read by exactly one thread per column group), C fragments
+// are 16-byte stores.  A warp owns 32 rows x 16 complex columns (4 x 4 DMMA tiles); the 8 warps of a CTA are split into
+// G = ceil(np / 16) column groups x 8/G row groups.  A CTA-wide barrier separates the last load from the first store, so
+// in == out is allowed.  Same descriptor and flags as k_mode_apply.
+// grid: (row tiles of `leg_rows_per_cta(np)`, items); block 256; dynamic shared memory leg_smem_bytes(max n, max np).
 // ---------------------------------------------------------------------------------------------------------------
-#define LD_LDB 72            // leading dimension (doubles) of the shared B matrix: == 8 mod 32 -> conflict-free fragments
+__host__ __device__ inline int leg_groups(int np) { int g = (np + 15) / 16; return g == 3 ? 4 : g; }    // 1, 2 or 4
+__host__ __device__ inline int leg_rows_per_cta(int np) { return 32 * (8 / leg_groups(np)); }
+__host__ __device__ inline int leg_ldb(int np) { return 32 * leg_groups(np) + 8; }                       // == 8 mod 32: conflict-free
+inline size_t leg_smem_bytes(int n, int np) { return (size_t)(4 * ((n + 1) / 2)) * leg_ldb(np) * sizeof(double); }
 
 __global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __restrict__ descs) {
   const ModeApplyDesc d = descs[blockIdx.y];
-  const int halves = d.np > 16 ? 2 : 1;
-  const int rows_per_cta = halves == 2 ? 128 : 256;
+  const int G = leg_groups(d.np), LDB = leg_ldb(d.np);
+  const int rows_per_cta = leg_rows_per_cta(d.np);
   const long long rows = (long long)d.L * d.R;
   const long long row0 = (long long)blockIdx.x * rows_per_cta;
   if (row0 >= rows) return;
-  __shared__ double Bs[64 * LD_LDB];
+  extern __shared__ double Bs[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = lane >> 2, q = lane & 3, kpair = q >> 1, part = q & 1;
   const int n = d.n, np = d.np;
-  const int K2 = 2 * ((n + 1) / 2 * 2);          // real K rounded up to whole k-steps (multiples of 4)
+  const int K2 = 4 * ((n + 1) / 2);              // real K rounded up to whole k-steps (multiples of 4)
+  const int N2 = 32 * G;                         // real columns held in shared memory
   const bool conj_m = d.flags & 1, trans_m = d.flags & 2;
   // B[(b, p), (c, p')]: p == p' -> Re m[b,c]; (im, re) -> -Im; (re, im) -> +Im; zero padding outside n x np
-  for (int idx = tid; idx < 64 * 64; idx += 256) {
-    int kk = idx >> 6, nn = idx & 63;
+  for (int idx = tid; idx < K2 * N2; idx += 256) {
+    int kk = idx / N2, nn = idx - kk * N2;
     int b = kk >> 1, p = kk & 1, c = nn >> 1, pp = nn & 1;
     double v = 0.0;
     if (b < n && c < np) {
@@ -256,11 +260,11 @@ __global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __rest
       if (conj_m) m.y = -m.y;
       v = (p == pp) ? m.x : (p ? -m.y : m.y);
     }
-    Bs[kk * LD_LDB + nn] = v;
+    Bs[kk * LDB + nn] = v;
   }
   __syncthreads();
-  const int half = halves == 2 ? (warp & 1) : 0;
-  const int rg = halves == 2 ? (warp >> 1) : warp;            // row group of 32 rows
+  const int grp = warp % G;
+  const int rg = warp / G;                                     // row group of 32 rows
   const long long wrow0 = row0 + (long long)rg * 32;
   const double* in = reinterpret_cast<const double*>(d.in);
   double* out = reinterpret_cast<double*>(d.out);
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __rest
   for (int t = 0; t < 4; ++t)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc[t][j][0] = 0.0; acc[t][j][1] = 0.0; }
-  const int ncol0 = 32 * half;                                  // first real column of this warp's half
+  const int ncol0 = 32 * grp;                                   // first real column of this warp's group
   for (int ks0 = 0; ks0 < K2 / 4; ks0 += 4) {
     double a[4][4];
 #pragma unroll
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __rest
       if (4 * (ks0 + u) >= K2) break;
       double bf[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = Bs[(4 * (ks0 + u) + q) * LD_LDB + ncol0 + 8 * j + r];
+      for (int j = 0; j < 4; ++j) bf[j] = Bs[(4 * (ks0 + u) + q) * LDB + ncol0 + 8 * j + r];
 #pragma unroll
       for (int t = 0; t < 4; ++t)
 #pragma unroll
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __rest
     if (!valid[t]) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c = 16 * half + 4 * j + q;
+      const int c = 16 * grp + 4 * j + q;
       if (c < np) {
         double2 v; v.x = acc[t][j][0]; v.y = acc[t][j][1];
         *reinterpret_cast<double2*>(out + 2 * (doff[t] + (long long)c * d.out_sb)) = v;
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_close_leg_dmma: tensor-core version of k_mode_close for n, np <= 32:  G[b, b'] = sum_rows A[row, b] conj(B[row, b']).
+// k_close_leg_dmma: tensor-core version of k_mode_close for n, np <= 64:  G[b, b'] = sum_rows A[row, b] conj(B[row, b']).
 // Real GEMM P[(b,p),(b',p')] = sum_rows A_p[row, b] B_p'[row, b'] (M = 2n, N = 2np, K = rows); both operand fragments
 // are 8-byte loads from global memory (4 consecutive rows x 4 columns per warp load).  A warp owns a 32 x 32 real
 // quadrant of P; 8 warps = quadrants x K-slices; fixed-order reduction over the K-slices in shared memory; partials
@@ -330,61 +334,73 @@ __global__ void __launch_bounds__(256, 2) k_close_leg_dmma(const ModeCloseDesc* 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = lane >> 2, q = lane & 3, wl = r >> 1, part = r & 1;
   const int n = d.n, np = d.np;
-  const int qm = n > 16 ? 2 : 1, qn = np > 16 ? 2 : 1, nquad = qm * qn, nslice = 8 / nquad;
-  const int quad = warp % nquad, slice = warp / nquad;
-  const int mq = quad % qm, nq = quad / qm;
+  // P is split into 32 x 32 real quadrants (16 x 16 complex); up to 8 of them are accumulated per pass over the rows
+  // (n, np <= 32: one pass, the spare warps take K-slices; n or np up to 64: 2 passes of 8 quadrants)
+  const int qm = (n + 15) / 16, qn = (np + 15) / 16, nquad = qm * qn;
+  const int qpp = nquad < 8 ? nquad : 8;                  // quadrants per pass
+  const int npass = (nquad + qpp - 1) / qpp;
+  const int nslice = 8 / qpp;
   const long long rows = (long long)d.L * d.R;
   const long long r_begin = (long long)blockIdx.x * d.rows_per_split;
   const long long r_end = min(rows, r_begin + d.rows_per_split);
   const double* A = reinterpret_cast<const double*>(d.a);
   const double* B = reinterpret_cast<const double*>(d.b);
-  double acc[4][4][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-  for (long long k0 = r_begin + 4 * slice; k0 < r_end; k0 += 4 * nslice) {
-    const long long row = k0 + q;
-    const bool ok = row < r_end;
-    long long rr = ok ? row / d.L : 0, l = ok ? row - rr * d.L : 0;
-    const long long aoff = l + rr * d.a_sr, boff = l + rr * d.b_sr;
-    double a[4], b[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int ba = 16 * mq + 4 * t + wl, bb = 16 * nq + 4 * t + wl;
-      a[t] = (ok && ba < n) ? A[2 * (aoff + (long long)ba * d.a_sb) + part] : 0.0;
-      b[t] = (ok && bb < np) ? B[2 * (boff + (long long)bb * d.b_sb) + part] : 0.0;
-    }
+  cplx* out = d.partial + (size_t)blockIdx.x * n * np;
+  for (int pass = 0; pass < npass; ++pass) {
+    const int quad = pass * qpp + warp % qpp, slice = warp / qpp;
+    const bool live = quad < nquad && warp < qpp * nslice;
+    const int mq = quad % qm, nq = quad / qm;
+    double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-  }
-  // this warp's 32 x 32 real quadrant -> shared memory, then a fixed-order sum over the K-slices
-  double* mine = red + (size_t)warp * 1024;
+      for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    if (live) {
+      for (long long k0 = r_begin + 4 * slice; k0 < r_end; k0 += 4 * nslice) {
+        const long long row = k0 + q;
+        const bool ok = row < r_end;
+        long long rr = ok ? row / d.L : 0, l = ok ? row - rr * d.L : 0;
+        const long long aoff = l + rr * d.a_sr, boff = l + rr * d.b_sr;
+        double a[4], b[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+        for (int t = 0; t < 4; ++t) {
+          const int ba = 16 * mq + 4 * t + wl, bb = 16 * nq + 4 * t + wl;
+          a[t] = (ok && ba < n) ? A[2 * (aoff + (long long)ba * d.a_sb) + part] : 0.0;
+          b[t] = (ok && bb < np) ? B[2 * (boff + (long long)bb * d.b_sb) + part] : 0.0;
+        }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int row = 8 * i + r, col = 8 * j + 2 * q;
-      mine[row + 32 * col] = acc[i][j][0];
-      mine[row + 32 * (col + 1)] = acc[i][j][1];
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
     }
-  __syncthreads();
-  cplx* out = d.partial + (size_t)blockIdx.x * n * np;
-  for (int idx = tid; idx < n * np; idx += blockDim.x) {
-    const int b = idx % n, bp = idx / n;
-    const int qd = (b >> 4) + qm * (bp >> 4);
-    const int lb = b & 15, lbp = bp & 15;
-    double rr = 0, ii = 0, ir = 0, ri = 0;
-    for (int sl = 0; sl < nslice; ++sl) {
-      const double* P = red + (size_t)(qd + nquad * sl) * 1024;
-      rr += P[(2 * lb) + 32 * (2 * lbp)];
-      ii += P[(2 * lb + 1) + 32 * (2 * lbp + 1)];
-      ir += P[(2 * lb + 1) + 32 * (2 * lbp)];
-      ri += P[(2 * lb) + 32 * (2 * lbp + 1)];
+    // this warp's 32 x 32 real quadrant -> shared memory, then a fixed-order sum over the K-slices
+    double* mine = red + (size_t)warp * 1024;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int row = 8 * i + r, col = 8 * j + 2 * q;
+        mine[row + 32 * col] = acc[i][j][0];
+        mine[row + 32 * (col + 1)] = acc[i][j][1];
+      }
+    __syncthreads();
+    for (int idx = tid; idx < n * np; idx += blockDim.x) {
+      const int b = idx % n, bp = idx / n;
+      const int qd = (b >> 4) + qm * (bp >> 4);
+      if (qd / qpp != pass) continue;
+      const int lb = b & 15, lbp = bp & 15;
+      double rr = 0, ii = 0, ir = 0, ri = 0;
+      for (int sl = 0; sl < nslice; ++sl) {
+        const double* P = red + (size_t)(qd % qpp + qpp * sl) * 1024;
+        rr += P[(2 * lb) + 32 * (2 * lbp)];
+        ii += P[(2 * lb + 1) + 32 * (2 * lbp + 1)];
+        ir += P[(2 * lb + 1) + 32 * (2 * lbp)];
+        ri += P[(2 * lb) + 32 * (2 * lbp + 1)];
+      }
+      out[idx] = cmake(rr + ii, ir - ri);
     }
-    out[idx] = cmake(rr + ii, ir - ri);
+    __syncthreads();
   }
 }
 

@@ -48,6 +48,7 @@ static void set_smem_attrs() {
   cudaFuncSetAttribute(k_close_dmma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_close_dmma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_close_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   done = true;
 }
@@ -704,7 +705,7 @@ void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const d
     if (no_chol < 0) { const char* e = getenv("TNQS_NO_CHOLQR"); no_chol = (e && e[0] == '1') ? 1 : 0; }
     for (int j : LJ) {
       SiteJob& J = jobs[j];
-      if (!no_chol && !dmma_disabled() && J.nc <= 32 && J.Po >= 4 * (long long)J.nc) chol_list.push_back(j); else house_list.push_back(j);
+      if (!no_chol && !dmma_disabled() && J.nc <= 64 && J.Po >= 4 * (long long)J.nc) chol_list.push_back(j); else house_list.push_back(j);
     }
     if (!chol_list.empty()) {
       const int nj = (int)chol_list.size();

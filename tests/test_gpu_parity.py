@@ -229,6 +229,23 @@ def test_two_site_gate_uniform_chi_tensor_core_paths(E, chi):
     gate_case(E, g, psi_o, grp, arrs, dict(maxdim=chi, cutoff=1e-10, normalize_tensors=True), sweeps=3)
 
 
+@pytest.mark.parametrize("shape,chi", [((3, 3), 20), ((3, 2), 32), ((4, 3), 24)])
+def test_two_site_gate_large_bond(E, shape, chi):
+    # d*chi in 33..64: tensor-core leg / Gram kernels with 3-4 column groups, CholeskyQR2 at nc = 64, 128 x 128 SVD (global W)
+    g = G.named_grid(shape)
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=chi, seed=83)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    grp = G.grid_edge_color(g)[0]
+    rs = np.random.default_rng(4)
+    arrs = []
+    for e in grp:
+        h = rs.normal(size=(4, 4)) + 1j * rs.normal(size=(4, 4))
+        u, _ = np.linalg.qr(h)
+        arrs.append(u.reshape(2, 2, 2, 2))
+    gate_case(E, g, psi_o, grp, arrs, dict(maxdim=chi, cutoff=1e-10, normalize_tensors=True), sweeps=2)
+
+
 def test_two_site_gate_ragged_and_degree3(E):
     g = G.named_hexagonal_lattice_graph(2, 2)
     dims = np.random.default_rng(9).integers(1, 5, size=g.ne)
