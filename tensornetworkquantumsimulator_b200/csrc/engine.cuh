@@ -200,7 +200,7 @@ struct Plan {
   std::vector<LevelPlan> levels;
   Gate1Desc* d_gate1 = nullptr; ModeApplyDesc* d_apply = nullptr; ModeCloseDesc* d_close = nullptr;
   CloseReduceDesc* d_reduce = nullptr; int* d_commit = nullptr;
-  SlabDesc* d_slab = nullptr; CloseDmmaDesc* d_dclose = nullptr;
+  SlabDesc* d_slab = nullptr; CloseDmmaDesc* d_dclose = nullptr; int* d_ticket = nullptr;
   // storage: a rebuilt plan of the same shape reuses the buffers of its predecessor, so device addresses (and a CUDA graph
   // captured over them) stay valid when only the site pointers inside the descriptors changed
   cplx* scratch = nullptr; size_t scratch_elems = 0; cplx* partial = nullptr; size_t partial_elems = 0;
@@ -241,6 +241,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
   std::vector<Gate1Desc> g1; std::vector<ModeApplyDesc> ma; std::vector<ModeCloseDesc> mc;
   std::vector<CloseReduceDesc> rd; std::vector<int> commit;
   std::vector<SlabDesc> sd; std::vector<CloseDmmaDesc> dc;
+  std::vector<CloseReduceDesc> frd;            // epilogues of the fast-path chains, in the order of `dc`
   // pass 1: scratch requirement per chain, sub-level split, global scratch sizing
   struct ChainMem { size_t buf_elems; int nbuf; int nsplit; size_t partial_elems; };
   size_t max_scratch = 0, max_partial = 0;
@@ -321,6 +322,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
           const int v = ch.v, F = (int)ch.absorb.size();
           SlabDesc a; a.t = c->site[v]; a.x = buf0[j]; a.F = F;
           CloseDmmaDesc b; b.x = buf0[j]; b.t = c->site[v]; b.partial = partial + fast_poff[j]; b.F = F; b.nsplit = cm.nsplit;
+          b.epilogue = nullptr; b.ticket = nullptr;
           long long stride = 2;
           int ai = 0;
           for (int l = 0; l < (int)c->inc[v].size(); ++l) {
@@ -415,20 +417,23 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         // an un-chunked level has finished all its reads when its epilogue runs: write the message in place, no commit pass
         if (ch.commit_k >= 0 && subsets[L].size() == 1) r.dst = c->msg(ch.commit_k);
         r.mode = ch.bp_mode; r.normalize = ch.normalize; r.hermitize = ch.hermitize;
-        rd.push_back(r);
+        if (fast[j]) frd.push_back(r); else rd.push_back(r);
         maxnn = std::max(maxnn, (size_t)n * n);
         REQUIRE(n <= 64, TNQS_ERR_UNSUPPORTED, "closing extent > 64 is not supported");
       }
       sl.close.count = (int)(mc.size() - sl.close.off); sl.close.grid = dim3(maxsplit, std::max(1, sl.close.count), 1);
       sl.close.dmma = !dmma_disabled();
       for (size_t i = sl.close.off; i < mc.size(); ++i) sl.close.dmma = sl.close.dmma && mc[i].n <= 64 && mc[i].np <= 64;
-      sl.reduce.count = (int)sub.size(); sl.reduce.grid = dim3(sl.reduce.count, 1, 1); sl.reduce.smem = maxnn * sizeof(cplx);
+      sl.reduce.count = (int)(rd.size() - sl.reduce.off); sl.reduce.grid = dim3(std::max(1, sl.reduce.count), 1, 1); sl.reduce.smem = maxnn * sizeof(cplx);
       lp.subs.push_back(sl);
     }
     if (subsets[L].size() > 1) for (const Chain& ch : chains) if (ch.commit_k >= 0) commit.push_back(ch.commit_k);
     lp.commit_count = (int)(commit.size() - lp.commit_off);
     plan.levels.push_back(lp);
   }
+  // fast-path epilogues live behind the generic reduce descriptors in one array; tickets: one int per fast chain
+  const size_t nrd_generic = rd.size();
+  rd.insert(rd.end(), frd.begin(), frd.end());
   const size_t cnt[7] = {g1.size(), ma.size(), mc.size(), rd.size(), commit.size(), sd.size(), dc.size()};
   bool same = reuse_mem;
   for (int i = 0; i < 7 && same; ++i) same = cnt[i] == reuse->cnt[i];
@@ -436,9 +441,12 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
   plan.d_gate1 = upload_into(c, same ? reuse->d_gate1 : nullptr, g1); plan.d_apply = upload_into(c, same ? reuse->d_apply : nullptr, ma);
   plan.d_close = upload_into(c, same ? reuse->d_close : nullptr, mc); plan.d_reduce = upload_into(c, same ? reuse->d_reduce : nullptr, rd);
   plan.d_commit = upload_into(c, same ? reuse->d_commit : nullptr, commit);
+  plan.d_ticket = (same && reuse->d_ticket) ? reuse->d_ticket : c->talloc<int>(dc.size() + 1);
+  if (!(same && reuse->d_ticket)) CU(cudaMemsetAsync(plan.d_ticket, 0, (dc.size() + 1) * sizeof(int), c->stream));
+  for (size_t i = 0; i < dc.size(); ++i) { dc[i].epilogue = plan.d_reduce + nrd_generic + i; dc[i].ticket = plan.d_ticket + i; }
   plan.d_slab = upload_into(c, same ? reuse->d_slab : nullptr, sd); plan.d_dclose = upload_into(c, same ? reuse->d_dclose : nullptr, dc);
   for (const LevelPlan& lp : plan.levels) {
-    for (const SubLevel& sl : lp.subs) plan.nlaunch += (sl.slab.count ? 2 : 0) + (sl.gate1.count ? 1 : 0) + (int)sl.steps.size() + (sl.close.count ? 1 : 0) + 1;
+    for (const SubLevel& sl : lp.subs) plan.nlaunch += (sl.slab.count ? 2 : 0) + (sl.gate1.count ? 1 : 0) + (int)sl.steps.size() + (sl.close.count ? 1 : 0) + (sl.reduce.count ? 1 : 0);
     plan.nlaunch += lp.commit_count ? 1 : 0;
   }
   return plan;
@@ -494,7 +502,7 @@ static void run_plan(tnqs_ctx* c, const Plan& p) {
         if (sl.close.dmma) LAUNCH(c, TNQS_KC_MODE_CLOSE, k_close_leg_dmma, sl.close.grid, 256, 8 * 1024 * sizeof(double), p.d_close + sl.close.off);
         else LAUNCH(c, TNQS_KC_MODE_CLOSE, k_mode_close, sl.close.grid, 256, 0, p.d_close + sl.close.off);
       }
-      LAUNCH(c, TNQS_KC_BP_FINALIZE, k_close_reduce, sl.reduce.grid, 256, sl.reduce.smem, p.d_reduce + sl.reduce.off);
+      if (sl.reduce.count) LAUNCH(c, TNQS_KC_BP_FINALIZE, k_close_reduce, sl.reduce.grid, 256, sl.reduce.smem, p.d_reduce + sl.reduce.off);
     }
     if (lp.commit_count)
       LAUNCH(c, TNQS_KC_BP_FINALIZE, k_msg_commit, lp.commit_count, 128, 0, c->msg_cur, c->msg_stage, c->slot,

@@ -141,6 +141,10 @@ struct CloseDmmaDesc {
   long long g[3];         // canonical strides of the absorbed legs
   long long gw;           // canonical stride of the outgoing leg
   int nsplit;
+  // fused epilogue: the CTA that finishes the last split of a message (ticket counter) sums the partials in their fixed
+  // order and runs the message epilogue, so the level needs no separate reduce launch
+  const CloseReduceDesc* epilogue;   // may be null
+  int* ticket;                       // zero-initialised, reset by the last CTA
 };
 
 // grid: (max nsplit, items); block 256 (8 warps); dynamic shared memory: 8 * (2N)^2 doubles
@@ -219,6 +223,18 @@ __global__ void __launch_bounds__(256, 2) k_close_dmma(const CloseDmmaDesc* __re
       ri += P[(2 * w) + PD * (2 * wp + 1)];
     }
     out[idx] = cmake(rr + ii, ir - ri);              // X conj(T): re = rr + ii, im = ir - ri
+  }
+  if (d.epilogue) {
+    __shared__ int last;
+    __threadfence();                                   // partials visible before the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(d.ticket, 1) == d.nsplit - 1);
+    __syncthreads();
+    if (last) {
+      __threadfence();
+      if (threadIdx.x == 0) *d.ticket = 0;
+      close_reduce_body(*d.epilogue, reinterpret_cast<cplx*>(red), red + 2 * N * N);
+    }
   }
 }
 

@@ -202,11 +202,9 @@ struct CloseReduceDesc {
   int normalize, hermitize;
 };
 
-// one CTA (256 threads) per item; fixed summation order everywhere (deterministic).
-__global__ void __launch_bounds__(256) k_close_reduce(const CloseReduceDesc* __restrict__ descs) {
-  const CloseReduceDesc d = descs[blockIdx.x];
-  __shared__ double red[8];
-  extern __shared__ cplx gsm[];                 // n*np complex
+// Sum of the split partials + epilogue of one item, executed by a whole CTA (any block size); fixed summation order
+// everywhere (deterministic).  gsm: n*np complex of shared memory; red: >= 32 doubles of shared memory.
+__device__ __forceinline__ void close_reduce_body(const CloseReduceDesc& d, cplx* gsm, double* red) {
   const int nn = d.n * d.np;
   for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
     cplx s = cmake(0, 0);
@@ -263,4 +261,12 @@ __global__ void __launch_bounds__(256) k_close_reduce(const CloseReduceDesc* __r
       *d.diff = 1.0 - (fr * fr + fi * fi);
     }
   }
+}
+
+// one CTA (256 threads) per item
+__global__ void __launch_bounds__(256) k_close_reduce(const CloseReduceDesc* __restrict__ descs) {
+  const CloseReduceDesc d = descs[blockIdx.x];
+  __shared__ double red[32];
+  extern __shared__ cplx gsm[];                 // n*np complex
+  close_reduce_body(d, gsm, red);
 }
