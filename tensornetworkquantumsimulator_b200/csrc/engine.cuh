@@ -341,7 +341,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         if (sl.slab.count) {
           int N = sl.fastN;
           sl.slab.grid = dim3(2 * N, sl.slab.count, 1);
-          sl.slab.smem = (size_t)(N + 2) * N * N * sizeof(cplx);
+          sl.slab.smem = (size_t)((N + 4) * N + 4) * N * sizeof(cplx);
           sl.dclose.grid = dim3(maxsplit_f, sl.dclose.count, 1);
           sl.dclose.smem = (size_t)8 * (2 * N) * (2 * N) * sizeof(double);
         }

@@ -35,8 +35,9 @@ struct SlabDesc {
 template <int N> struct SlabCfg {
   static constexpr int KS = N / 2;        // k-steps of 4 real = 2 complex
   static constexpr int NT = N / 4;        // n-tiles of 8 real = 4 complex
-  static constexpr int S1 = N + 2;        // padded shared stride of the 2nd slab leg (== 2 mod 8: conflict-free fragments)
-  static constexpr int SLAB3 = S1 * N * N;
+  static constexpr int S1 = N + 4;        // padded shared stride of the 2nd slab leg (== 4 mod 8: conflict-free 8-byte fragment loads per half-warp)
+  static constexpr int S2 = S1 * N + 4;   // stride of the 3rd slab leg, also == 4 mod 8
+  static constexpr int SLAB3 = S2 * N;
 };
 
 // One absorption phase P of F: compile-time strides, next tile's A fragments prefetched while the current tile multiplies.
@@ -47,7 +48,7 @@ __device__ __forceinline__ void absorb_phase(const SlabDesc& d, const double* __
   constexpr int KS = Cfg::KS, NT = Cfg::NT;
   constexpr bool from_global = P == 0, to_global = P == F - 1;
   constexpr int O1 = P == 0 ? 1 : 0, O2 = P == 2 ? 1 : 2;              // the other slab legs, fastest first
-  constexpr long long SST[3] = {1, Cfg::S1, (long long)Cfg::S1 * N};    // shared strides
+  constexpr long long SST[3] = {1, Cfg::S1, Cfg::S2};                   // shared strides
   constexpr long long XST[3] = {1, N, (long long)N * N};                // intermediate strides
   const int r = lane >> 2, q = lane & 3, kpair = q >> 1, part = q & 1;
   const long long src_m = from_global ? d.g[P] : SST[P];

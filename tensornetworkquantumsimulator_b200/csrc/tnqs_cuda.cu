@@ -531,7 +531,7 @@ void GateBatch::absorb_outer(bool inverse) {   // forward: on A (psi~); inverse:
     const int N = w ? 16 : 8;
     SlabDesc* dsd = c->upload(slab[w]);
     dim3 grid((unsigned)((maxcols[w] + 1) / 2 * 2), (unsigned)slab[w].size(), 1);
-    size_t smem = (size_t)(N + 2) * N * N * sizeof(cplx);
+    size_t smem = (size_t)((N + 4) * N + 4) * N * sizeof(cplx);
     if (w) LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<16>, grid, 256, smem, dsd);
     else LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<8>, grid, 256, smem, dsd);
   }
