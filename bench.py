@@ -1,17 +1,18 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the tnqs-cuda engine (contract: see the task statement / DESIGN.md "measurement").
+"""bench.py — headline benchmark of the tnqs-cuda engine (contract: task statement; definitions: DESIGN.md section 5).
 
-Workload at N=1 (BASELINE.json configs[1], "C2"): 32x32 open grid, random TensorNetworkState chi=16 ComplexF64
-(counter-based generator, seed 1, BP-rescaled), one Trotter layer per step = Rx, Rz on every vertex + Rzz in 4
-deterministic colour classes with maxdim=16, cutoff=1e-10, the reference's lazy BP refreshes (default
-bp_update_kwargs: <=25 sweeps, tolerance 1e-8, forest-cover edge order, REFERENCE_ORDER schedule) and <Z> on (16,16).
-At N>1 ranks hold independent vertex strips of a (32*N)x32 lattice?  No: see `--gpus` below (weak scaling, row strips
-with halo exchange of boundary messages in JACOBI mode).
+N = 1 (BASELINE.json configs[1], "C2"): 32x32 open grid, random TensorNetworkState chi=16 ComplexF64 (counter-based generator,
+seed 1, BP-rescaled).  One step = one Trotter layer: Rx, Rz on every vertex + Rzz in 4 deterministic colour classes with maxdim=16,
+cutoff=1e-10, executed as the exact run / refresh schedule of the reference's apply_gates (lazy BP refreshes with the default
+bp_update_kwargs: <=25 sweeps, tolerance 1e-8, forest-cover edge order, REFERENCE_ORDER level schedule) and <Z> at the centre.
+N > 1: weak scaling, one 32x32 row strip per GPU of a 32x(32 N) lattice; BP in JACOBI mode with one NCCL halo exchange and one
+all-reduce per sweep, gates across a cut through tnqs_apply_2site_begin/_end with one R-factor exchange per colour class.
 
-One JSON line on stdout (rank 0).  value = BP edge-message updates / s (device-resident state, BP phases timed with
-CUDA events on the engine's stream); `gates` carries the two-site gate applications / s of the same steps; `e2e` is
-the same step through the host API with the state in pinned HOST memory (H2D of every site tensor, the layer, D2H of
-the state and the result inside the timed region).
+One JSON line on stdout (rank 0).  value = BP edge-message updates / s over the BP phases (device-resident state, CUDA events on
+the engine's stream); `gates` = two-site gate applications / s over the gate phases of the same steps; `e2e` = the same step
+through the host API with the state in pinned HOST memory (every site tensor H2D, the layer, every site tensor D2H inside the
+timed region); `roofline` = algorithmic flops of the dominant kernel / its CUDA-event time against the measured cuBLAS ZGEMM peak;
+`cpu_baseline` / `--impl reference` = the CPU oracle (NumPy + OpenBLAS, all host threads) on a bounded sample of the same tensors.
 """
 from __future__ import annotations
 

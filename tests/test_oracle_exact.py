@@ -191,3 +191,23 @@ def test_message_normalisation_and_diff():
     out = O.update(bpc, maxiter=100, tolerance=1e-14, info=info)
     assert info["iters"] < 100 and info["mean_diff"] <= 1e-14
     assert O.message_diff(m, 3.0 * m) == pytest.approx(0.0, abs=1e-15)
+
+
+def test_circuit_schedule_follows_the_reference_rule():
+    # runs are defined by the affected-vertices rule, not by colour (apply_gates.jl:56-89): the host-side
+    # schedule (engine.circuit_schedule, mirrored by tnqs_apply_circuit) must agree with the oracle's gate-by-gate loop
+    from tensornetworkquantumsimulator_b200.engine import circuit_schedule
+    for shape in [(3, 3), (4, 4), (5, 3)]:
+        g = G.named_grid(shape)
+        layer = ising_layer(g, groups=G.grid_edge_color(g))
+        sched = circuit_schedule(g, layer * 2)
+        info = {}
+        psi0 = O.tensornetworkstate(lambda v: "↑", g)
+        O.apply_gates(layer * 2, O.BeliefPropagationCache(psi0), apply_kwargs=dict(maxdim=2, cutoff=1e-10), info=info)
+        assert sum(1 for it in sched if it[0] == "refresh") == info["refreshes"]
+        ids = [i for it in sched if it[0] != "refresh" for i in it[1]]
+        assert ids == list(range(len(layer) * 2))                       # program order is preserved
+        for it in sched:
+            if it[0] == "gates2":                                        # a batch is vertex-disjoint
+                vs = [g.v(x) for i in it[1] for x in (layer * 2)[i][1]]
+                assert len(vs) == len(set(vs))
