@@ -509,7 +509,10 @@ def run_reference(args):
     if rank != 0:
         return None
     cores = os.cpu_count()
-    n_msgs, n_gates = args.cpu_msgs, args.cpu_gates
+    # bounded sample per step so that the whole --steps/--warmup run stays within a few minutes (~15 s of CPU work per 3000 messages)
+    budget = max(1, args.warmup + args.steps)
+    n_msgs = int(max(200, min(args.cpu_msgs, args.cpu_msgs * 8 // budget)))
+    n_gates = int(max(10, min(args.cpu_gates, args.cpu_gates * 8 // budget)))
     vals, gvals = [], []
     for s in range(args.warmup + args.steps):
         mps, gps, t_msg, t_gate = cpu_sample(args.nx, args.ny, args.chi, n_msgs, n_gates)
