@@ -60,6 +60,7 @@ static void alloc_site(tnqs_ctx* c, int v) {
 }
 
 static void upload_chi(tnqs_ctx* c) {
+  if (c->ne == 0) return;
   CU(cudaMemcpyAsync(c->d_chi, c->chi.data(), sizeof(int) * std::max(c->ne, 1), cudaMemcpyHostToDevice, c->stream));
 }
 

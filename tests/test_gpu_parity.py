@@ -608,3 +608,64 @@ def test_config_c4_cubic_small(E):
     want = O.expect_tns(psi_o, ("Z", [c]), cache_update_kwargs=bp_kw)
     got = E.expect(psi_e, ("Z", [c]), cache_update_kwargs=bp_kw)
     assert abs(got - want) < EXP_TOL
+
+
+@pytest.mark.parametrize("d", [3, 4])
+def test_site_dimension_3_and_4(E, d):
+    # spin-1 (d=3) and Pauli-basis (d=4) sites (tensornetworkstate_constructors.jl:19-35): generic kernels, d^2 x d^2 gates
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=29, d=d)
+    seq = G.forest_cover_edge_sequence(g)
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=4, edge_sequence=seq)
+    be = E.update(to_engine(psi_o, chi_cap=9), maxiter=4, edge_sequence=seq)
+    check_messages(E, be, bo)
+    rho = E.rdm_1site(be, list(range(g.nv)))
+    for v in range(g.nv):
+        want = O.rdm_1site(bo, v)
+        got = rho[v][:d, :d] / np.trace(rho[v][:d, :d])
+        assert np.max(np.abs(got - want)) < EXP_TOL
+    rs = np.random.default_rng(6)
+    grp = G.grid_edge_color(g)[0]
+    arrs = []
+    for e in grp:
+        h = rs.normal(size=(d * d, d * d)) + 1j * rs.normal(size=(d * d, d * d))
+        u, _ = np.linalg.qr(h)
+        arrs.append(u.reshape(d, d, d, d))
+    dets = []
+    for e, a in zip(grp, arrs):
+        det = {}
+        O.apply_gate(bo, a, [int(g.esrc[e]), int(g.edst[e])], maxdim=6, cutoff=1e-12, detail=det)
+        dets.append(det)
+    ranks, errs, sv = E.apply_2site_batch(be, grp, arrs, apply_kwargs=dict(maxdim=6, cutoff=1e-12))
+    for i, det in enumerate(dets):
+        assert ranks[i] == det["rank"]
+        assert rel(sv[i, :ranks[i]], det["svals"]) < MSG_TOL
+    te = be.psi.tensors()
+    for e in grp:
+        assert rel(two_site(g, te, e), two_site(g, bo.network.tensors, e)) < 1e-9
+
+
+def test_empty_and_degenerate_inputs(E):
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=1)
+    be = to_engine(psi_o)
+    before = be.psi.tensors()
+    out, errs = E.apply_gates([], be, apply_kwargs=dict(maxdim=2), update_cache=False)        # empty circuit: a copy
+    assert len(errs) == 0
+    for a, b in zip(before, out.psi.tensors()):
+        assert np.array_equal(a, b)
+    assert E.expect(be, []) == []                                                              # no observables
+    assert E.expect(be, ("Z", [(2, 2)], 0)) == 0                                               # zero coefficient (expect.jl:63)
+    # a single isolated vertex: no edges, no messages, expectation from the site alone
+    g1 = G.Graph([(1,)], [], [])
+    psi1 = E.TensorNetworkState.from_arrays(g1, [np.array([0.6, 0.8j])])
+    b1 = E.update(E.BeliefPropagationCache(psi1), edge_sequence=[])
+    assert E.expect(b1, ("Z", [(1,)])) == pytest.approx(0.36 - 0.64, abs=1e-14)
+    # tree: default maxiter is 1 and BP is exact (beliefpropagationcache.jl:31)
+    gt = G.path_graph(5)
+    psit = O.random_tensornetworkstate(gt, bond_dimension=3, seed=3)
+    info = {}
+    bt = E.update(to_engine(psit), info=info)
+    assert info["iters"] == 1
+    sv_ = O.to_statevector(psit)
+    assert abs(E.expect(bt, ("Z", [(3,)])) - O.statevector_expect(sv_, 5, {2: gates.Z})) < 1e-12
