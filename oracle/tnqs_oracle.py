@@ -592,6 +592,34 @@ def truncate_tns(psi: TensorNetworkState, **kwargs) -> TensorNetworkState:
     return truncate_bp(bpc, **kwargs).network
 
 
+def sample(psi: TensorNetworkState, nsamples: int, bp_update_kwargs: Optional[dict] = None, gauge_state: bool = True, rng=None):
+    """src/sampling.jl:3-46 (BP branch).  The projection keeps the site index and zeroes the other components, which gives
+    the same BP contractions as the reference's removal of the index (norm_factors, tensornetworkstate.jl:48-49)."""
+    rng = rng if rng is not None else np.random.default_rng()
+    kw = dict(bp_update_kwargs or {})
+    g = psi.g
+    bpc = update(BeliefPropagationCache(psi), **kw)
+    if gauge_state:
+        bpc = symmetric_gauge(rescale(bpc))
+    out = []
+    for _ in range(nsamples):
+        proj = bpc.copy()
+        bits = {}
+        for v in range(g.nv):
+            rho = rdm_1site(proj, v)
+            p = np.real(np.diag(rho))
+            p = np.clip(p / p.sum(), 0.0, None)
+            config = int(min(np.searchsorted(np.cumsum(p), rng.random() * p.sum(), side="right"), len(p) - 1))
+            bits[g.names[v]] = config
+            op = np.zeros((len(p), len(p)), dtype=np.complex128)
+            op[config, config] = 1.0
+            apply_gate(proj, op, [v], normalize_tensors=False)
+            if v != g.nv - 1:
+                proj = update(proj, **kw)
+        out.append(bits)
+    return out, psi
+
+
 # ---------------------------------------------------------------------------------------------
 # exact helpers for tiny systems (independent ground truth, not part of the restatement)
 # ---------------------------------------------------------------------------------------------

@@ -544,3 +544,47 @@ def entanglement(x, edge, alg: str = "bp") -> float:
         if abs(d) >= np.finfo(np.float64).eps:
             ee -= d * d * math.log(d * d)
     return abs(ee)
+
+
+def normalize(psi: TensorNetworkState, alg: str = "bp", cache_update_kwargs: Optional[dict] = None) -> TensorNetworkState:
+    """BP normalisation (src/normalize.jl:1-6): update, then rescale so every vertex and edge scalar is 1."""
+    if alg != "bp":
+        raise ValueError("Only alg='bp' is on the CUDA path")
+    kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(psi)
+    bpc = update(BeliefPropagationCache(psi.copy()), inplace=True, **kw)
+    return rescale(bpc, inplace=True).psi
+
+
+def sample(psi: TensorNetworkState, nsamples: int, alg: str = "bp", bp_update_kwargs: Optional[dict] = None,
+           gauge_state: bool = True, rng=None):
+    """Site-by-site BP sampling (src/sampling.jl:3-46): per vertex the BP reduced density matrix,
+    a draw from its diagonal, projection of the site onto the outcome, and a BP update of the projected cache.
+    Every tensor operation is an existing C-ABI call; only the draw (inverse CDF on `rng.random()`) happens on the host.
+    Returns ([{vertex name: outcome}], psi) like the reference."""
+    if alg != "bp":
+        raise ValueError("Only alg='bp' is on the CUDA path")
+    rng = rng if rng is not None else np.random.default_rng()
+    kw = dict(bp_update_kwargs or {})
+    g = psi.g
+    bpc = update(BeliefPropagationCache(psi.copy()), inplace=True, **kw)
+    if gauge_state:                                        # symmetrize_and_normalize (src/symmetric_gauge.jl:70-74)
+        rescale(bpc, inplace=True)
+        symmetric_gauge(bpc, inplace=True)
+    out = []
+    for _ in range(nsamples):
+        proj = bpc.copy()
+        bits = {}
+        for v in range(g.nv):
+            rho = rdm_1site(proj, [v])[0]
+            p = np.real(np.diag(rho))
+            p = np.clip(p / p.sum(), 0.0, None)
+            config = int(min(np.searchsorted(np.cumsum(p), rng.random() * p.sum(), side="right"), len(p) - 1))
+            bits[g.names[v]] = config
+            d = len(p)
+            proj_op = np.zeros((d, d), dtype=np.complex128)
+            proj_op[config, config] = 1.0
+            apply_1site_batch(proj, [v], [proj_op], normalize_tensors=False)
+            if v != g.nv - 1:
+                update(proj, inplace=True, **kw)
+        out.append(bits)
+    return out, psi

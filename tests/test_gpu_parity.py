@@ -669,3 +669,15 @@ def test_empty_and_degenerate_inputs(E):
     assert info["iters"] == 1
     sv_ = O.to_statevector(psit)
     assert abs(E.expect(bt, ("Z", [(3,)])) - O.statevector_expect(sv_, 5, {2: gates.Z})) < 1e-12
+
+
+def test_bp_sampling_matches_oracle_draw_for_draw(E):
+    # SURVEY.md 8f item 2 (src/sampling.jl:3-46): same uniform draws -> same bit strings; product state -> its own configuration
+    g = G.named_comb_tree((3, 2))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=13)
+    want, _ = O.sample(psi_o, 4, rng=np.random.default_rng(7))
+    got, _ = E.sample(E.TensorNetworkState.from_arrays(g, psi_o.tensors), 4, rng=np.random.default_rng(7))
+    assert got == want
+    g2 = G.named_grid((3, 3))
+    bits, _ = E.sample(E.tensornetworkstate(lambda v: "↓", g2), 2, bp_update_kwargs=dict(maxiter=3), rng=np.random.default_rng(0))
+    assert all(b == 1 for s in bits for b in s.values())

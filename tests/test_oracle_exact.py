@@ -211,3 +211,14 @@ def test_circuit_schedule_follows_the_reference_rule():
             if it[0] == "gates2":                                        # a batch is vertex-disjoint
                 vs = [g.v(x) for i in it[1] for x in (layer * 2)[i][1]]
                 assert len(vs) == len(set(vs))
+
+
+def test_bp_sampling_known_answers():
+    # /root/reference/test/test_sampling.jl:15-21: a product state samples to its own configuration; GHZ samples are all-equal
+    g = G.named_grid((3, 2))
+    bits, _ = O.sample(O.tensornetworkstate(lambda v: "↑", g), 3, rng=np.random.default_rng(0))
+    assert all(b == 0 for s in bits for b in s.values())
+    gt = G.named_comb_tree((3, 2))
+    outs, _ = O.sample(ghz(gt), 8, rng=np.random.default_rng(1))
+    assert all(len(set(s.values())) == 1 for s in outs)
+    assert {next(iter(s.values())) for s in outs} == {0, 1}
