@@ -164,6 +164,7 @@ struct Chain {
   cplx* dst = nullptr;               // n x n result (BP: staged message)
   const cplx* prev = nullptr; double* diff = nullptr; int bp_mode = 0, normalize = 0, hermitize = 0;
   int commit_k = -1;                 // BP: directed edge to commit at the end of the level
+  int split_cap = 16;                // upper bound of the split-K factor of the closing (a property of the request, never of the batch)
 };
 
 struct LaunchRec { size_t off; int count; dim3 grid; size_t smem; bool dmma = false; };
@@ -264,14 +265,14 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
     }
     if (!cur.empty()) subsets[L].push_back(cur);
     for (auto& sub : subsets[L]) {
-      // split-K factor depends on the tensor only (never on the batch), so a message is computed bit-identically whatever
+      // split-K factor depends on the tensor and the request only (never on the batch), so a message is computed bit-identically whatever
       // else shares its launch: partitioned (multi-GPU) JACOBI sweeps reproduce the single-GPU result exactly.
       size_t part = 0;
       for (int i : sub) {
         const Chain& ch = chains[i];
         int n = ch.close_leg < 0 ? c->d[ch.v] : c->chi[c->inc[ch.v][ch.close_leg]];
         long long rows = c->site_n[ch.v] / n;
-        int ns = (int)std::min<long long>(16, std::max<long long>(1, rows / 512));
+        int ns = (int)std::min<long long>(ch.split_cap, std::max<long long>(1, rows / 512));
         mem[L][i].nsplit = std::max(1, ns);
         mem[L][i].partial_elems = (size_t)mem[L][i].nsplit * n * n;
         part += mem[L][i].partial_elems;

@@ -322,6 +322,7 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
         }
         ch.dst = c->msg_st(k); ch.prev = c->msg(k); ch.diff = want_diff ? nc->d_diff + i : nullptr;
         ch.bp_mode = 1; ch.normalize = o.normalize; ch.hermitize = o.hermitize; ch.commit_k = k;
+        ch.split_cap = o.mode == TNQS_BP_JACOBI ? 4 : 16;      // whole-sweep launches want long CTAs, level launches want many
         levels[level[i]].push_back(ch);
       }
       Plan np = build_plan(c, levels, scratch_budget(c), old ? &old->plan : nullptr);
