@@ -6,6 +6,7 @@
 
 static thread_local std::string g_create_error;
 static void bp_cache_drop(tnqs_ctx* c);
+static void drop_pending_gate(tnqs_ctx* c);
 
 #define API_BEGIN(ctx) if (!(ctx)) return TNQS_ERR_INVALID_ARG; try { CU(cudaSetDevice((ctx)->device));
 #define API_END(ctx) } catch (const TnqsError& e) { (ctx)->err = e.msg; (ctx)->release_temps(); return e.code; } \
@@ -36,9 +37,7 @@ const char* tnqs_last_error(const tnqs_ctx* ctx) { return ctx ? ctx->err.c_str()
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------------
-static void set_smem_attrs() {
-  static bool done = false;
-  if (done) return;
+static void set_smem_attrs() {   // per device: called at every handle creation (cheap)
   cudaFuncSetAttribute(k_eigh_sqrt, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_house_qr, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_svd_trunc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -50,7 +49,6 @@ static void set_smem_attrs() {
   cudaFuncSetAttribute(k_close_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  done = true;
 }
 
 static void alloc_site(tnqs_ctx* c, int v) {
@@ -141,6 +139,7 @@ extern "C" int32_t tnqs_destroy(tnqs_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->collect_profile();
+  drop_pending_gate(c);
   bp_cache_drop(c);
   c->arena_destroy();
   for (cplx* p : c->site) if (p) cudaFreeAsync(p, c->stream);
@@ -952,6 +951,10 @@ extern "C" int32_t tnqs_apply_2site(tnqs_ctx* c, int32_t n, const int32_t* e, co
   apply_2site_impl(c, n, e, flip, gates, *opts, ranks, truncerr, svals);
   c->release_temps();
   API_END(c)
+}
+
+static void drop_pending_gate(tnqs_ctx* c) {
+  if (c->pending_gate) { delete (GateBatch*)c->pending_gate; c->pending_gate = nullptr; }
 }
 
 extern "C" int32_t tnqs_apply_2site_begin(tnqs_ctx* c, int32_t n, const int32_t* e, const int32_t* flip, const double* gates,
