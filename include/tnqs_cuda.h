@@ -152,6 +152,10 @@ int32_t tnqs_rdm_1site(tnqs_ctx* ctx, int32_t n, const int32_t* v, double* rho /
 /* Two-site nearest-neighbour observables on edges e[i]: out[i] = <O1 (x) O2> numerator and denominator
  * (out[4i..4i+1] = numer re,im; out[4i+2..4i+3] = denom re,im); ops[i] = O1[s',s] then O2[s',s] (2*d*d cplx). */
 int32_t tnqs_expect_2site_nn(tnqs_ctx* ctx, int32_t n, const int32_t* e, const double* ops, double* out);
+/* Two-site observables on vertices joined by a path of the network (the Steiner tree of the support, src/expect.jl:66):
+ * path i = path_v[path_off[i] .. path_off[i+1]) (consecutive vertices share an edge), O1 acts on its first vertex, O2 on
+ * its last; ops and out as in tnqs_expect_2site_nn. */
+int32_t tnqs_expect_path(tnqs_ctx* ctx, int32_t n, const int32_t* path_off, const int32_t* path_v, const double* ops, double* out);
 /* vertex_scalar (src/MessagePassing/abstractbeliefpropagationcache.jl:21-27) for all vertices, [nv] cplx;
  * edge_scalar (src/MessagePassing/beliefpropagationcache.jl:38-40) for all edges, [ne] cplx. */
 int32_t tnqs_vertex_scalars(tnqs_ctx* ctx, double* out);

@@ -1149,6 +1149,78 @@ extern "C" int32_t tnqs_expect_2site_nn(tnqs_ctx* c, int32_t n, const int32_t* e
   API_END(c)
 }
 
+// Observables with one operator at each end of a path v_0 .. v_L of the network (the Steiner tree of two vertices,
+// src/expect.jl:66): vertex i absorbs the messages from every neighbour off the path and the environment handed over by
+// v_{i-1}, and closes on the bond towards v_{i+1} (the last vertex closes on the site index).  One level per path position.
+extern "C" int32_t tnqs_expect_path(tnqs_ctx* c, int32_t n, const int32_t* path_off, const int32_t* path_v, const double* ops,
+                                    double* out) {
+  API_BEGIN(c)
+  REQUIRE(n >= 0 && (n == 0 || (path_off && path_v && ops && out)), TNQS_ERR_INVALID_ARG, "tnqs_expect_path: null argument");
+  if (n > 0) {
+    size_t maxlen = 0;
+    for (int i = 0; i < n; ++i) {
+      int len = path_off[i + 1] - path_off[i];
+      REQUIRE(len >= 2, TNQS_ERR_INVALID_ARG, "a path needs at least two vertices");
+      maxlen = std::max(maxlen, (size_t)len);
+    }
+    std::vector<std::vector<Chain>> levels(maxlen);
+    size_t opoff = 0; std::vector<cplx> hops; std::vector<size_t> o1(n), o2(n);
+    for (int i = 0; i < n; ++i) {
+      const int* pv = path_v + path_off[i]; int len = path_off[i + 1] - path_off[i];
+      for (int j = 0; j < len; ++j) REQUIRE(pv[j] >= 0 && pv[j] < c->nv, TNQS_ERR_INVALID_ARG, "path vertex out of range");
+      int da = c->d[pv[0]], db = c->d[pv[len - 1]];
+      const cplx* src = (const cplx*)ops + opoff;
+      o1[i] = hops.size(); hops.insert(hops.end(), src, src + da * da);
+      o2[i] = hops.size(); hops.insert(hops.end(), src + da * da, src + da * da + db * db);
+      opoff += da * da + db * db;
+    }
+    cplx* d_ops = c->upload(hops);
+    const int dd = c->dmax * c->dmax;
+    cplx* res = c->talloc<cplx>((size_t)2 * n * dd);
+    auto edge_between = [&](int a, int b) { for (int e : c->inc[a]) if (c->other(e, a) == b) return e; return -1; };
+    for (int i = 0; i < n; ++i) {
+      const int* pv = path_v + path_off[i]; int len = path_off[i + 1] - path_off[i];
+      for (int w = 0; w < 2; ++w) {                         // w = 0: numerator (with operators), 1: denominator
+        cplx* env_prev = nullptr;
+        for (int j = 0; j < len; ++j) {
+          int v = pv[j], prev = j > 0 ? pv[j - 1] : -1, next = j + 1 < len ? pv[j + 1] : -1;
+          Chain ch; ch.v = v;
+          for (size_t l = 0; l < c->inc[v].size(); ++l) {
+            int e = c->inc[v][l], u = c->other(e, v);
+            if (u == next) continue;
+            Absorb ab; ab.leg = (int)l; ab.ldm = c->chi[e]; ab.flags = 0;
+            if (u == prev) ab.mat = env_prev; else ab.mat = c->msg(c->dedge(u, e));
+            ch.absorb.push_back(ab);
+          }
+          if (w == 0 && j == 0) ch.op = d_ops + o1[i];
+          if (w == 0 && j == len - 1) ch.op = d_ops + o2[i];
+          if (next >= 0) {
+            int e = edge_between(v, next);
+            REQUIRE(e >= 0, TNQS_ERR_INVALID_ARG, "consecutive path vertices do not share an edge");
+            ch.close_leg = c->leg(v, e); ch.dst = c->talloc<cplx>((size_t)c->slot);
+            env_prev = ch.dst;
+          } else { ch.close_leg = -1; ch.dst = res + (size_t)(2 * i + w) * dd; }
+          levels[j].push_back(ch);
+        }
+      }
+    }
+    Plan p = build_plan(c, levels, scratch_budget(c));
+    run_plan(c, p);
+    std::vector<cplx> h((size_t)2 * n * dd);
+    CU(cudaMemcpyAsync(h.data(), res, h.size() * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    for (int i = 0; i < n; ++i)
+      for (int w = 0; w < 2; ++w) {
+        int d = c->d[path_v[path_off[i + 1] - 1]];
+        double re = 0, im = 0;
+        for (int s = 0; s < d; ++s) { cplx x = h[(size_t)(2 * i + w) * dd + s + s * d]; re += x.x; im += x.y; }
+        out[4 * i + 2 * w] = re; out[4 * i + 2 * w + 1] = im;
+      }
+  }
+  c->release_temps();
+  API_END(c)
+}
+
 static void vertex_scalars_impl(tnqs_ctx* c, cplx* d_vs /* [nv] device */) {
   std::vector<int> vs(c->nv);
   for (int v = 0; v < c->nv; ++v) vs[v] = v;

@@ -400,8 +400,8 @@ def _collect_observable(g: Graph, obs: tuple):
 
 
 def expect(x, obs, alg: str = "bp", cache_update_kwargs: Optional[dict] = None):
-    """<O> by belief propagation (src/expect.jl:53-83,115-136): one-site observables and two-site observables on
-    neighbouring vertices; a TensorNetworkState input builds and updates a fresh cache first."""
+    """<O> by belief propagation (src/expect.jl:53-83,115-136): one-site observables and two-site observables (contracted
+    along the path joining the two vertices); a TensorNetworkState input builds and updates a fresh cache first."""
     if alg != "bp":
         raise ValueError("Only alg='bp' is on the CUDA path (Expected BeliefPropagationCache or TensorNetworkState for 'bp' algorithm)")
     if isinstance(x, TensorNetworkState):
@@ -415,7 +415,7 @@ def expect(x, obs, alg: str = "bp", cache_update_kwargs: Optional[dict] = None):
     one = [(i, p) for i, p in enumerate(parsed) if len(p[1]) == 1 and p[2] != 0]
     two = [(i, p) for i, p in enumerate(parsed) if len(p[1]) == 2 and p[2] != 0]
     if any(len(p[1]) > 2 for p in parsed):
-        raise NotImplementedError("the CUDA path measures one-site and nearest-neighbour two-site observables")
+        raise NotImplementedError("the CUDA path measures one-site and two-site observables")
     if one:
         rho = rdm_1site(x, [p[1][0] for _, p in one])
         for (i, (names, vs, coeff)), r in zip(one, rho):
@@ -424,23 +424,41 @@ def expect(x, obs, alg: str = "bp", cache_update_kwargs: Optional[dict] = None):
             r = r[:d, :d]
             out[i] = coeff * np.sum(o.T * r) / np.trace(r)        # sum_{s,s'} O[s',s] rho[s,s']
     if two:
-        es, ops = [], []
+        # the Steiner tree of two vertices is a shortest path between them (src/expect.jl:66); BFS, lowest ids first
+        offs, pv, ops = [0], [], []
         for _, (names, vs, coeff) in two:
-            if (vs[0], vs[1]) not in g.edge_of:
-                raise NotImplementedError("two-site observables must sit on an edge of the network")
-            e = g.edge_of[(vs[0], vs[1])]
-            o1, o2 = _gates.PAULI[names[0]], _gates.PAULI[names[1]]
-            if int(g.esrc[e]) != vs[0]:
-                o1, o2 = o2, o1
-            es.append(e)
-            ops += [o1.ravel(order="F"), o2.ravel(order="F")]
-        es_a = i32(es)
+            path = _shortest_path(g, vs[0], vs[1])
+            pv += path
+            offs.append(len(pv))
+            ops += [_gates.PAULI[names[0]].ravel(order="F"), _gates.PAULI[names[1]].ravel(order="F")]
+        offs_a, pv_a = i32(offs), i32(pv)
         ops_a = np.concatenate(ops).astype(np.complex128).view(np.float64)
-        res = np.zeros(4 * len(es), dtype=np.float64)
-        check(x.psi._h.ptr, _lib.load().tnqs_expect_2site_nn(x.psi._h.ptr, len(es), ptr_i32(es_a), ptr_f64(ops_a), ptr_f64(res)))
+        res = np.zeros(4 * len(two), dtype=np.float64)
+        check(x.psi._h.ptr, _lib.load().tnqs_expect_path(x.psi._h.ptr, len(two), ptr_i32(offs_a), ptr_i32(pv_a), ptr_f64(ops_a), ptr_f64(res)))
         for j, (i, (names, vs, coeff)) in enumerate(two):
             out[i] = coeff * complex(res[4 * j], res[4 * j + 1]) / complex(res[4 * j + 2], res[4 * j + 3])
     return out[0] if single else out
+
+
+def _shortest_path(g: Graph, a: int, b: int) -> List[int]:
+    if a == b:
+        raise ValueError("Repeated vertex in collection")
+    prev = {a: -1}
+    queue = [a]
+    while queue:
+        u = queue.pop(0)
+        if u == b:
+            break
+        for w in g.neighbors(u):
+            if w not in prev:
+                prev[w] = u
+                queue.append(w)
+    if b not in prev:
+        raise ValueError("vertices are not connected")
+    path = [b]
+    while path[-1] != a:
+        path.append(prev[path[-1]])
+    return path[::-1]
 
 
 def vertex_scalars(bpc: BeliefPropagationCache) -> np.ndarray:

@@ -681,3 +681,22 @@ def test_bp_sampling_matches_oracle_draw_for_draw(E):
     g2 = G.named_grid((3, 3))
     bits, _ = E.sample(E.tensornetworkstate(lambda v: "↓", g2), 2, bp_update_kwargs=dict(maxiter=3), rng=np.random.default_rng(0))
     assert all(b == 1 for s in bits for b in s.values())
+
+
+def test_two_site_expectation_along_paths(E):
+    # src/expect.jl:58-83 with the Steiner tree (= shortest path) of two non-adjacent vertices
+    g = G.named_grid((4, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=37)
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=12)
+    be = E.update(to_engine(psi_o), maxiter=12)
+    obs = [("ZZ", [(1, 1), (3, 2)]), ("XY", [(4, 3), (1, 1)], 2.0), ("YZ", [(2, 2), (2, 3)]), ("ZX", [(1, 3), (4, 1)])]
+    got, want = E.expect(be, obs), [O.expect(bo, o) for o in obs]
+    assert np.max(np.abs(np.array(got) - np.array(want))) < EXP_TOL
+    # exact on a tree
+    gt = G.named_comb_tree((3, 3))
+    psit = O.random_tensornetworkstate(gt, bond_dimension=2, seed=5)
+    bt = E.update(to_engine(psit))
+    sv = O.to_statevector(psit)
+    a, b = gt.v((1, 3)), gt.v((3, 3))
+    ex = O.statevector_expect(sv, gt.nv, {a: gates.X, b: gates.Z})
+    assert abs(E.expect(bt, ("XZ", [(1, 3), (3, 3)])) - ex) < 1e-12
