@@ -700,3 +700,47 @@ def test_two_site_expectation_along_paths(E):
     a, b = gt.v((1, 3)), gt.v((3, 3))
     ex = O.statevector_expect(sv, gt.nv, {a: gates.X, b: gates.Z})
     assert abs(E.expect(bt, ("XZ", [(1, 3), (3, 3)])) - ex) < 1e-12
+
+
+def test_full_size_c2_properties(E):
+    # BASELINE config C2 at full size (32x32, chi=16, 1.77 GiB): size-independent properties instead of an oracle run
+    import bench
+    g, groups, rx, rz, rzz, seq = bench.workload(32, 32)
+    psi = E.random_tensornetworkstate(g, bond_dimension=16, seed=1)
+    bpc = E.BeliefPropagationCache(psi)
+    info = {}
+    E.update(bpc, edge_sequence=seq, inplace=True, maxiter=40, tolerance=1e-10, info=info)
+    assert info["iters"] < 40 and info["mean_diff"] <= 1e-10
+    # idempotence: one more sweep on converged messages changes nothing beyond the tolerance
+    m0 = E.message(bpc, 1234)
+    E.update(bpc, edge_sequence=seq, inplace=True, maxiter=1, tolerance=0.0, info=info)
+    assert info["mean_diff"] < 1e-9 and rel(E.message(bpc, 1234), m0) < 1e-4
+    # messages are Hermitian, positive and normalised to unit entry sum
+    w = np.linalg.eigvalsh(m0)
+    assert np.allclose(m0, m0.conj().T, atol=1e-12) and w.min() > -1e-12 and abs(m0.sum() - 1) < 1e-12
+    # rescale: every vertex and edge scalar becomes 1, the BP partition function 1
+    E.rescale(bpc, inplace=True)
+    assert np.allclose(E.vertex_scalars(bpc), 1.0, atol=1e-9) and np.allclose(E.edge_scalars(bpc), 1.0, atol=1e-9)
+    # the sequential order and the JACOBI schedule reach the same fixed point
+    z_ref = E.expect(bpc, ("Z", [(16, 16)]))
+    bj = bpc.copy()
+    E.update(bj, edge_sequence=np.arange(2 * g.ne), inplace=True, maxiter=60, tolerance=1e-12, mode="jacobi")
+    assert abs(E.expect(bj, ("Z", [(16, 16)])) - z_ref) < 1e-6
+    # one colour class of Rzz with maxdim = chi: ranks <= chi, 0 <= truncation error < 1, unit-norm singular values that
+    # become the bond messages; a second identical run is bit-identical (no atomics, fixed reduction orders)
+    kw = dict(maxdim=16, cutoff=1e-10, normalize_tensors=True)
+    b2 = bpc.copy()
+    r1, e1, s1 = E.apply_2site_batch(bpc, groups[0], [rzz] * len(groups[0]), apply_kwargs=kw)
+    r2, e2, s2 = E.apply_2site_batch(b2, groups[0], [rzz] * len(groups[0]), apply_kwargs=kw)
+    assert np.array_equal(r1, r2) and np.array_equal(e1, e2) and np.array_equal(s1, s2)
+    assert r1.max() <= 16 and r1.min() >= 1 and e1.min() >= 0 and e1.max() < 1
+    assert np.allclose(np.sum(s1 ** 2, axis=1), 1.0, atol=1e-12)
+    e = groups[0][17]
+    assert np.allclose(np.diag(E.message(bpc, 2 * e)).real, s1[17, :r1[17]], atol=1e-14)
+    for v in (int(g.esrc[e]), int(g.edst[e])):
+        assert abs(np.linalg.norm(bpc.psi[v]) - 1.0) < 1e-12
+    # unitary one-site gates preserve <Z>-independent quantities: the BP norm stays 1 after Rx on every site + refresh
+    E.apply_1site_batch(bpc, list(range(g.nv)), [rx] * g.nv)
+    E.update(bpc, edge_sequence=seq, inplace=True, maxiter=25, tolerance=1e-8)
+    zs = E.expect(bpc, [("Z", [g.names[v]]) for v in (0, 500, 1023)])
+    assert all(abs(z.imag) < 1e-10 and abs(z.real) <= 1 + 1e-10 for z in zs)
