@@ -236,10 +236,21 @@ extern "C" int32_t tnqs_reset_messages(tnqs_ctx* c) { API_BEGIN(c) reset_message
 // The last BP plan (level schedule, descriptors, scratch) is kept on the handle and reused by later updates with the same
 // edge sequence and options as long as no site tensor or bond dimension changed: a refresh of 25 sweeps, or the
 // sweep-by-sweep calls of a partitioned run, build it once.
+// Loop state of a refresh that runs as ONE graph launch: the sweep body sits in a conditional WHILE node, so the
+// "stop when the mean diff <= tolerance or after maxiter sweeps" test (abstractbeliefpropagationcache.jl:201-218) runs on
+// the device and no host round trip separates two sweeps.
+struct BpLoopState { double tol; double mean; int maxiter; int iter; int has_tol; int pad; };
+__global__ void k_bp_loop_check(cudaGraphConditionalHandle h, BpLoopState* st, const double* d_sum, int nseq) {
+  const int it = ++st->iter;
+  bool more = it < st->maxiter;
+  if (st->has_tol) { const double mean = *d_sum / nseq; st->mean = mean; if (mean <= st->tol) more = false; }
+  cudaGraphSetConditional(h, more ? 1u : 0u);
+}
 struct BpPlanCache {
   Plan plan; std::vector<int> seq; int mode = -1, normalize = -1, hermitize = -1, want_diff = -1; long long version = -1;
   double* d_diff = nullptr; std::vector<void*> owned;
-  cudaGraphExec_t graph = nullptr;     // one sweep (all levels + the diff sum), captured once per launch structure
+  BpLoopState* d_loop = nullptr;
+  cudaGraphExec_t graph = nullptr;     // the whole refresh: WHILE(sweep: all levels + diff sum + loop test), built once per launch structure
 };
 static void bp_cache_drop(tnqs_ctx* c) {
   BpPlanCache* pc = (BpPlanCache*)c->bp_cache;
@@ -309,6 +320,7 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
     c->arena_bypass = true;
     try {
       if (!nc->d_diff) nc->d_diff = c->talloc<double>(nseq + 1);
+      if (!nc->d_loop) nc->d_loop = (BpLoopState*)c->talloc<double>(sizeof(BpLoopState) / sizeof(double));
       std::vector<std::vector<Chain>> levels(nlevels);
       for (int i = 0; i < nseq; ++i) {
         int k = seq[i], v = c->dsrc(k), w = c->ddst(k);
@@ -340,34 +352,54 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
   double* d_sum = d_diff + nseq;
   int it = 0; double mean = NAN;
   const bool use_graph = !c->profiling && !graphs_disabled() && plan.nlaunch >= 8;
-  for (it = 1; it <= o.maxiter; ++it) {
-    if (use_graph) {
-      if (!pc->graph) {                                     // capture one sweep: every level + the diff sum
-        cudaGraph_t g = nullptr;
-        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  const int per_sweep = plan.nlaunch + (want_diff ? 1 : 0);
+  if (use_graph) {
+    if (!pc->graph) {
+      cudaGraph_t g = nullptr;
+      CU(cudaGraphCreate(&g, 0));
+      try {
+        cudaGraphConditionalHandle h;
+        CU(cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault));     // every launch enters the body once
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = h; np.conditional.type = cudaGraphCondTypeWhile; np.conditional.size = 1;
+        cudaGraphNode_t node;
+        CU(cudaGraphAddNode(&node, g, nullptr, 0, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        CU(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        cudaGraph_t cap = nullptr;
         try {
           run_plan(c, plan);
           if (want_diff) LAUNCH(c, TNQS_KC_BP_FINALIZE, k_sum, 1, 1024, 0, d_diff, nseq, d_sum);
-        } catch (...) { cudaStreamEndCapture(c->stream, &g); if (g) cudaGraphDestroy(g); throw; }
-        CU(cudaStreamEndCapture(c->stream, &g));
+          LAUNCH(c, TNQS_KC_BP_FINALIZE, k_bp_loop_check, 1, 1, 0, h, pc->d_loop, d_sum, nseq);
+        } catch (...) { cudaStreamEndCapture(c->stream, &cap); throw; }
+        CU(cudaStreamEndCapture(c->stream, &cap));
         cudaError_t ge = cudaGraphInstantiate(&pc->graph, g, 0);
-        cudaGraphDestroy(g);
         if (ge != cudaSuccess) throw TnqsError(TNQS_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ge));
-        c->launches -= plan.nlaunch + (want_diff ? 1 : 0);  // the capture pass launched nothing
-      }
-      CU(cudaGraphLaunch(pc->graph, c->stream));
-      c->launches += plan.nlaunch + (want_diff ? 1 : 0);
-    } else {
+      } catch (...) { cudaGraphDestroy(g); throw; }
+      cudaGraphDestroy(g);
+      c->launches -= per_sweep + 1;                           // the capture pass launched nothing
+    }
+    BpLoopState hs; hs.tol = o.tolerance; hs.mean = NAN; hs.maxiter = o.maxiter; hs.iter = 0; hs.has_tol = want_diff; hs.pad = 0;
+    CU(cudaMemcpyAsync(pc->d_loop, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaGraphLaunch(pc->graph, c->stream));
+    CU(cudaMemcpyAsync(&hs, pc->d_loop, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    it = hs.iter; mean = want_diff ? hs.mean : NAN;
+    c->launches += (long long)it * (per_sweep + 1);
+    c->bp_sweeps += it; c->bp_msg_updates += (long long)it * nseq;
+  } else {
+    for (it = 1; it <= o.maxiter; ++it) {
       run_plan(c, plan);
       if (want_diff) LAUNCH(c, TNQS_KC_BP_FINALIZE, k_sum, 1, 1024, 0, d_diff, nseq, d_sum);
-    }
-    ++c->bp_sweeps; c->bp_msg_updates += nseq;
-    if (want_diff) {
-      double s = 0;
-      CU(cudaMemcpyAsync(&s, d_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      c->sync();
-      mean = s / nseq;
-      if (mean <= o.tolerance) break;
+      ++c->bp_sweeps; c->bp_msg_updates += nseq;
+      if (want_diff) {
+        double s = 0;
+        CU(cudaMemcpyAsync(&s, d_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        c->sync();
+        mean = s / nseq;
+        if (mean <= o.tolerance) break;
+      }
     }
   }
   if (it > o.maxiter) it = o.maxiter;
@@ -869,7 +901,9 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
     for (int j : LJ) {
       SiteJob& J = jobs[j]; int r = ranks[j / 2];
       long long tot = J.Po * J.d * r;
-      newsite[j] = (cplx*)c->dalloc((size_t)tot * sizeof(cplx));
+      // same size as before (saturated bonds): the old tensor is dead by now, write over it and keep its address, so
+      // cached BP plans (which hold site pointers) stay valid
+      newsite[j] = tot == c->site_n[J.v] ? c->site[J.v] : (cplx*)c->dalloc((size_t)tot * sizeof(cplx));
       PermDesc& p = pd[j];
       p.src = Tm[j]; p.dst = newsite[j]; p.chib = r; p.to_matrix = 0; p.norm2 = o.normalize_tensors ? d_n2 + j : nullptr;
       long long stride = J.d;
@@ -887,20 +921,24 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
     if (!lp.empty()) LAUNCH(c, TNQS_KC_PERMUTE, k_permute, dim3(gx, (unsigned)lp.size()), 256, 0, dpd);
   }
   // ---- 9. commit: bond dimensions, site pointers, messages <- diag(S) (apply_gates.jl:105-119) ----
-  for (int i = 0; i < n; ++i) c->chi[es[i]] = ranks[i];
-  ++c->state_version;
-  upload_chi(c);
+  bool layout_changed = false;
+  for (int i = 0; i < n; ++i) { if (c->chi[es[i]] != ranks[i]) layout_changed = true; c->chi[es[i]] = ranks[i]; }
+  if (layout_changed) upload_chi(c);
   for (int j : LJ) {
-    c->dfree(c->site[jobs[j].v]); c->site[jobs[j].v] = newsite[j];
-    c->site_n[jobs[j].v] = jobs[j].Po * jobs[j].d * ranks[j / 2];
+    const int v = jobs[j].v;
+    if (newsite[j] != c->site[v]) { c->dfree(c->site[v]); c->site[v] = newsite[j]; layout_changed = true; }
+    c->site_n[v] = jobs[j].Po * jobs[j].d * ranks[j / 2];
   }
   for (int j = 0; j < NJ; ++j) {                      // ghost placeholders follow the new bond dimension
     if (!jobs[j].remote) continue;
     int v = jobs[j].v;
+    if (c->site_n[v] == c->site_elems(v)) continue;
     c->dfree(c->site[v]); c->site_n[v] = c->site_elems(v);
     c->site[v] = (cplx*)c->dalloc((size_t)c->site_n[v] * sizeof(cplx));
     CU(cudaMemsetAsync(c->site[v], 0, (size_t)c->site_n[v] * sizeof(cplx), c->stream));
+    layout_changed = true;
   }
+  if (layout_changed) ++c->state_version;
   {
     std::vector<int> ks(es.begin(), es.end());
     int* dks = c->upload(ks);
