@@ -190,6 +190,7 @@ static ApplyLaunch plan_apply_launch(const ModeApplyDesc* d, size_t count) {
 }
 struct SubLevel {
   LaunchRec slab{0, 0, dim3(), 0}, dclose{0, 0, dim3(), 0};   // DMMA fast path (kernels_dmma.cuh)
+  LaunchRec fused{0, 0, dim3(), 0};                            // the same chains as one persistent launch (k_bp_level): queue items
   int fastN = 0;
   LaunchRec gate1{0, 0, dim3(), 0};
   std::vector<LaunchRec> steps;
@@ -202,10 +203,11 @@ struct Plan {
   Gate1Desc* d_gate1 = nullptr; ModeApplyDesc* d_apply = nullptr; ModeCloseDesc* d_close = nullptr;
   CloseReduceDesc* d_reduce = nullptr; int* d_commit = nullptr;
   SlabDesc* d_slab = nullptr; CloseDmmaDesc* d_dclose = nullptr; int* d_ticket = nullptr;
+  int2* d_items = nullptr; int* d_qctr = nullptr; int* d_slab_done = nullptr;       // k_bp_level queue, its counters, per-chain slab counters
   // storage: a rebuilt plan of the same shape reuses the buffers of its predecessor, so device addresses (and a CUDA graph
   // captured over them) stay valid when only the site pointers inside the descriptors changed
   cplx* scratch = nullptr; size_t scratch_elems = 0; cplx* partial = nullptr; size_t partial_elems = 0;
-  size_t cnt[7] = {0, 0, 0, 0, 0, 0, 0};          // descriptor counts: gate1, apply, close, reduce, commit, slab, dclose
+  size_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // descriptor counts: gate1, apply, close, reduce, commit, slab, dclose, queue items
   int nlaunch = 0;                   // kernel launches per run
   double flops = 0;                  // executed flops per run of the plan (8 per complex MAC)
 };
@@ -237,8 +239,27 @@ template <typename T> static T* upload_into(tnqs_ctx* c, T* reuse, const std::ve
   return reuse;
 }
 
-static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& levels, size_t scratch_budget_bytes, const Plan* reuse = nullptr) {
+// The persistent one-launch-per-level kernel (k_bp_level) is opt-in (TNQS_FUSE=1): measured on C2 it does not beat the
+// two-launch level (its closing items wait on slabs too often); TNQS_FUSE_LAG sets the queue lag in messages.
+static bool fuse_disabled() {
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("TNQS_FUSE"); disabled = (e && e[0] == '1') ? 0 : 1; }
+  return disabled == 1;
+}
+static int fuse_lag() {
+  static int lag = 0;
+  if (!lag) { const char* e = getenv("TNQS_FUSE_LAG"); lag = e ? std::max(1, atoi(e)) : 12; }
+  return lag;
+}
+
+// strict_levels: no chain of a level reads a message that another chain of the same level writes (the caller built the
+// levels that way), so epilogues may write their message in place even while other chains of the level are in flight.
+static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& levels, size_t scratch_budget_bytes, const Plan* reuse = nullptr,
+                       bool strict_levels = false) {
   Plan plan;
+  std::vector<int2> items;
+  int sm_count = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
   std::vector<Gate1Desc> g1; std::vector<ModeApplyDesc> ma; std::vector<ModeCloseDesc> mc;
   std::vector<CloseReduceDesc> rd; std::vector<int> commit;
   std::vector<SlabDesc> sd; std::vector<CloseDmmaDesc> dc;
@@ -291,6 +312,11 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
     const auto& chains = levels[L];
     LevelPlan lp;
     lp.commit_off = commit.size();
+    // one persistent launch per level for the fast-path chains; without the strict-level guarantee its epilogues stage
+    // their messages and the level ends with a commit pass
+    const bool fuse = !fuse_disabled() && subsets[L].size() == 1;
+    bool level_staged = subsets[L].size() > 1;
+    if (fuse && !strict_levels) for (const Chain& ch : chains) if (fast_path_N(c, ch) && ch.commit_k >= 0) level_staged = true;
     for (auto& sub : subsets[L]) {
       SubLevel sl;
       size_t soff = 0, poff = 0;
@@ -342,9 +368,23 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         if (sl.slab.count) {
           int N = sl.fastN;
           sl.slab.grid = dim3(2 * N, sl.slab.count, 1);
-          sl.slab.smem = (size_t)((N + 4) * N + 4) * N * sizeof(cplx);
+          sl.slab.smem = N == 16 ? SlabCfg<16>::SMEM : SlabCfg<8>::SMEM;
           sl.dclose.grid = dim3(maxsplit_f, sl.dclose.count, 1);
-          sl.dclose.smem = (size_t)8 * (2 * N) * (2 * N) * sizeof(double);
+          sl.dclose.smem = (size_t)8 * 2 * N * N * sizeof(double);
+          if (fuse) {
+            // queue: absorb items of chain m, then the closing items of chain m - D (their slabs were drawn >= D chains ago)
+            const int nf = sl.slab.count, D = std::min(nf, fuse_lag());
+            sl.fused.off = items.size();
+            auto push_close = [&](int m) { for (int j = 0; j < dc[sl.dclose.off + m].nsplit; ++j) items.push_back(make_int2(~(int)(sl.dclose.off + m), j)); };
+            for (int m = 0; m < nf; ++m) {
+              for (int x = 0; x < sd[sl.slab.off + m].nslabs; ++x) items.push_back(make_int2((int)(sl.slab.off + m), x));
+              if (m >= D) push_close(m - D);
+            }
+            for (int m = std::max(0, nf - D); m < nf; ++m) push_close(m);
+            sl.fused.count = (int)(items.size() - sl.fused.off);
+            sl.fused.grid = dim3((unsigned)std::min(sl.fused.count, 2 * sm_count), 1, 1);
+            sl.fused.smem = std::max(sl.slab.smem, sl.dclose.smem);
+          }
         }
       }
       // one-site operators
@@ -416,7 +456,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         CloseReduceDesc r;
         r.partial = part; r.nsplit = cm.nsplit; r.n = n; r.np = n; r.dst = ch.dst; r.prev = ch.prev; r.diff = ch.diff;
         // an un-chunked level has finished all its reads when its epilogue runs: write the message in place, no commit pass
-        if (ch.commit_k >= 0 && subsets[L].size() == 1) r.dst = c->msg(ch.commit_k);
+        if (ch.commit_k >= 0 && !level_staged) r.dst = c->msg(ch.commit_k);
         r.mode = ch.bp_mode; r.normalize = ch.normalize; r.hermitize = ch.hermitize;
         if (fast[j]) frd.push_back(r); else rd.push_back(r);
         maxnn = std::max(maxnn, (size_t)n * n);
@@ -428,17 +468,17 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
       sl.reduce.count = (int)(rd.size() - sl.reduce.off); sl.reduce.grid = dim3(std::max(1, sl.reduce.count), 1, 1); sl.reduce.smem = maxnn * sizeof(cplx);
       lp.subs.push_back(sl);
     }
-    if (subsets[L].size() > 1) for (const Chain& ch : chains) if (ch.commit_k >= 0) commit.push_back(ch.commit_k);
+    if (level_staged) for (const Chain& ch : chains) if (ch.commit_k >= 0) commit.push_back(ch.commit_k);
     lp.commit_count = (int)(commit.size() - lp.commit_off);
     plan.levels.push_back(lp);
   }
   // fast-path epilogues live behind the generic reduce descriptors in one array; tickets: one int per fast chain
   const size_t nrd_generic = rd.size();
   rd.insert(rd.end(), frd.begin(), frd.end());
-  const size_t cnt[7] = {g1.size(), ma.size(), mc.size(), rd.size(), commit.size(), sd.size(), dc.size()};
+  const size_t cnt[8] = {g1.size(), ma.size(), mc.size(), rd.size(), commit.size(), sd.size(), dc.size(), items.size()};
   bool same = reuse_mem;
-  for (int i = 0; i < 7 && same; ++i) same = cnt[i] == reuse->cnt[i];
-  for (int i = 0; i < 7; ++i) plan.cnt[i] = cnt[i];
+  for (int i = 0; i < 8 && same; ++i) same = cnt[i] == reuse->cnt[i];
+  for (int i = 0; i < 8; ++i) plan.cnt[i] = cnt[i];
   plan.d_gate1 = upload_into(c, same ? reuse->d_gate1 : nullptr, g1); plan.d_apply = upload_into(c, same ? reuse->d_apply : nullptr, ma);
   plan.d_close = upload_into(c, same ? reuse->d_close : nullptr, mc); plan.d_reduce = upload_into(c, same ? reuse->d_reduce : nullptr, rd);
   plan.d_commit = upload_into(c, same ? reuse->d_commit : nullptr, commit);
@@ -446,8 +486,16 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
   if (!(same && reuse->d_ticket)) CU(cudaMemsetAsync(plan.d_ticket, 0, (dc.size() + 1) * sizeof(int), c->stream));
   for (size_t i = 0; i < dc.size(); ++i) { dc[i].epilogue = plan.d_reduce + nrd_generic + i; dc[i].ticket = plan.d_ticket + i; }
   plan.d_slab = upload_into(c, same ? reuse->d_slab : nullptr, sd); plan.d_dclose = upload_into(c, same ? reuse->d_dclose : nullptr, dc);
+  plan.d_items = upload_into(c, same ? reuse->d_items : nullptr, items);
+  const bool keep_ctr = same && reuse->d_qctr && reuse->d_slab_done;
+  plan.d_qctr = keep_ctr ? reuse->d_qctr : c->talloc<int>(4);
+  plan.d_slab_done = keep_ctr ? reuse->d_slab_done : c->talloc<int>(sd.size() + 1);
+  if (!keep_ctr) {
+    CU(cudaMemsetAsync(plan.d_qctr, 0, 4 * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(plan.d_slab_done, 0, (sd.size() + 1) * sizeof(int), c->stream));
+  }
   for (const LevelPlan& lp : plan.levels) {
-    for (const SubLevel& sl : lp.subs) plan.nlaunch += (sl.slab.count ? 2 : 0) + (sl.gate1.count ? 1 : 0) + (int)sl.steps.size() + (sl.close.count ? 1 : 0) + (sl.reduce.count ? 1 : 0);
+    for (const SubLevel& sl : lp.subs) plan.nlaunch += (sl.slab.count ? (sl.fused.count ? 1 : 2) : 0) + (sl.gate1.count ? 1 : 0) + (int)sl.steps.size() + (sl.close.count ? 1 : 0) + (sl.reduce.count ? 1 : 0);
     plan.nlaunch += lp.commit_count ? 1 : 0;
   }
   return plan;
@@ -458,14 +506,14 @@ static bool same_rec(const LaunchRec& a, const LaunchRec& b) {
 }
 // True when two plans issue the same launches over the same device buffers (a captured CUDA graph of one replays the other).
 static bool same_launches(const Plan& a, const Plan& b) {
-  if (a.levels.size() != b.levels.size() || a.d_slab != b.d_slab || a.d_apply != b.d_apply || a.d_close != b.d_close ||
+  if (a.levels.size() != b.levels.size() || a.d_slab != b.d_slab || a.d_items != b.d_items || a.d_qctr != b.d_qctr || a.d_slab_done != b.d_slab_done || a.d_apply != b.d_apply || a.d_close != b.d_close ||
       a.d_reduce != b.d_reduce || a.d_dclose != b.d_dclose || a.d_gate1 != b.d_gate1 || a.d_commit != b.d_commit) return false;
   for (size_t L = 0; L < a.levels.size(); ++L) {
     const LevelPlan &x = a.levels[L], &y = b.levels[L];
     if (x.subs.size() != y.subs.size() || x.commit_off != y.commit_off || x.commit_count != y.commit_count) return false;
     for (size_t i = 0; i < x.subs.size(); ++i) {
       const SubLevel &p = x.subs[i], &q = y.subs[i];
-      if (p.fastN != q.fastN || p.steps.size() != q.steps.size() || !same_rec(p.slab, q.slab) || !same_rec(p.dclose, q.dclose) ||
+      if (p.fastN != q.fastN || p.steps.size() != q.steps.size() || !same_rec(p.slab, q.slab) || !same_rec(p.dclose, q.dclose) || !same_rec(p.fused, q.fused) ||
           !same_rec(p.gate1, q.gate1) || !same_rec(p.close, q.close) || !same_rec(p.reduce, q.reduce)) return false;
       for (size_t j = 0; j < p.steps.size(); ++j) if (!same_rec(p.steps[j], q.steps[j])) return false;
     }
@@ -485,7 +533,12 @@ static void launch_mode_apply(tnqs_ctx* c, int kc, const std::vector<ModeApplyDe
 static void run_plan(tnqs_ctx* c, const Plan& p) {
   for (const LevelPlan& lp : p.levels) {
     for (const SubLevel& sl : lp.subs) {
-      if (sl.slab.count) {
+      if (sl.fused.count) {
+        LevelQueue Q; Q.items = p.d_items + sl.fused.off; Q.n = sl.fused.count; Q.counter = p.d_qctr;
+        Q.slabs = p.d_slab; Q.closes = p.d_dclose; Q.slab_done = p.d_slab_done;
+        if (sl.fastN == 16) LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_level<16>, sl.fused.grid, 256, sl.fused.smem, Q);
+        else LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_level<8>, sl.fused.grid, 256, sl.fused.smem, Q);
+      } else if (sl.slab.count) {
         if (sl.fastN == 16) {
           LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<16>, sl.slab.grid, 256, sl.slab.smem, p.d_slab + sl.slab.off);
           LAUNCH(c, TNQS_KC_MODE_CLOSE, k_close_dmma<16>, sl.dclose.grid, 256, sl.dclose.smem, p.d_dclose + sl.dclose.off);

@@ -32,106 +32,133 @@ struct SlabDesc {
   int flags;              // bit0: conj(m), bit1: m^T (as k_mode_apply)
 };
 
+// Shared-memory slab: N^F complex, unpadded, XOR-swizzled in its fastest index: element (i0, i1, i2) sits at
+// (i0 ^ f(i1) ^ f(i2)) + N*i1 + N^2*i2 with f(x) = ((x & 1) << 2) | (x & 2).  Every 16-byte access pattern of the kernel
+// (a quarter-warp = 2 consecutive rows x 4 consecutive indices of the contracted / produced leg) then hits 8 distinct
+// 16-byte bank groups, for loads and stores of every phase.
+__device__ __forceinline__ int slab_f(int x) { return ((x & 1) << 2) | (x & 2); }
 template <int N> struct SlabCfg {
-  static constexpr int KS = N / 2;        // k-steps of 4 real = 2 complex
+  static constexpr int KK = N / 4;        // 16-byte A loads per row: element b = 4*kk + q feeds k-steps 2kk (re) and 2kk+1 (im)
   static constexpr int NT = N / 4;        // n-tiles of 8 real = 4 complex
-  static constexpr int S1 = N + 4;        // padded shared stride of the 2nd slab leg (== 4 mod 8: conflict-free 8-byte fragment loads per half-warp)
-  static constexpr int S2 = S1 * N + 4;   // stride of the 3rd slab leg, also == 4 mod 8
-  static constexpr int SLAB3 = S2 * N;
+  static constexpr int SLAB3 = N * N * N;
+  static constexpr int MSM = 3 * N * N;   // staged messages
+  static constexpr size_t SMEM = (size_t)(SLAB3 + MSM) * sizeof(cplx);
 };
 
-// One absorption phase P of F: compile-time strides, next tile's A fragments prefetched while the current tile multiplies.
+// One absorption phase P of F.  K ordering: lane (r, q) loads the whole complex element b = 4kk + q of its row (one
+// 16-byte load) and feeds its real part to k-step 2kk and its imaginary part to k-step 2kk+1; the B fragments are built
+// for the same ordering, so a row costs N/4 vector loads instead of N/2 scalar ones and global sectors are used whole.
 template <int N, int F, int P>
-__device__ __forceinline__ void absorb_phase(const SlabDesc& d, const double* __restrict__ gsrc, double* __restrict__ gdst,
-                                             double* __restrict__ sm, int lane, int warp, int nwarps) {
+__device__ __forceinline__ void absorb_phase(const SlabDesc& d, const cplx* __restrict__ gsrc, cplx* __restrict__ gdst,
+                                             cplx* __restrict__ sm, const cplx* __restrict__ msm, int lane, int warp, int nwarps) {
   using Cfg = SlabCfg<N>;
-  constexpr int KS = Cfg::KS, NT = Cfg::NT;
+  constexpr int KK = Cfg::KK, NT = Cfg::NT;
   constexpr bool from_global = P == 0, to_global = P == F - 1;
   constexpr int O1 = P == 0 ? 1 : 0, O2 = P == 2 ? 1 : 2;              // the other slab legs, fastest first
-  constexpr long long SST[3] = {1, Cfg::S1, Cfg::S2};                   // shared strides
   constexpr long long XST[3] = {1, N, (long long)N * N};                // intermediate strides
-  const int r = lane >> 2, q = lane & 3, kpair = q >> 1, part = q & 1;
-  const long long src_m = from_global ? d.g[P] : SST[P];
-  const long long src_o1 = from_global ? d.g[O1] : SST[O1];
-  const long long src_o2 = (F == 3) ? (from_global ? d.g[O2] : SST[O2]) : 0;
-  constexpr long long dst_m = to_global ? XST[P] : SST[P];
-  constexpr long long dst_o1 = to_global ? XST[O1] : SST[O1];
-  constexpr long long dst_o2 = (F == 3) ? (to_global ? XST[O2] : SST[O2]) : 0;
-  const double* src = from_global ? gsrc : sm;
-  double* dst = to_global ? gdst : sm;
-  // B fragments of [[Re m, Im m], [-Im m, Re m]] (interleaved), kept in registers for the whole phase
-  double bf[KS][NT];
+  const int r = lane >> 2, q = lane & 3;
+  // B fragments of [[Re m, Im m], [-Im m, Re m]], kept in registers for the whole phase
+  double bf[2 * KK][NT];
   {
-    const cplx* m = d.m[P];
+    const cplx* m = msm + P * N * N;
     const bool conj_m = d.flags & 1, trans_m = d.flags & 2;
+    const int pp = r & 1;
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
+    for (int kk = 0; kk < KK; ++kk)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        const int b = 2 * ks + kpair, c = 4 * nt + (r >> 1), pp = r & 1;
+        const int b = 4 * kk + q, c = 4 * nt + (r >> 1);
         cplx v = trans_m ? m[c + N * b] : m[b + N * c];
         if (conj_m) v.y = -v.y;
-        bf[ks][nt] = (part == pp) ? v.x : (part ? -v.y : v.y);
+        bf[2 * kk][nt] = pp ? v.y : v.x;            // row (b, re): Re m to the real column, +Im m to the imaginary one
+        bf[2 * kk + 1][nt] = pp ? v.x : -v.y;       // row (b, im): -Im m to the real column, Re m to the imaginary one
       }
   }
   constexpr int ntiles = (F == 3 ? N * N : N) / 8;
-  double a[KS], an[KS];
-  auto tile_off = [&](int ti, long long so1, long long so2) { const int rho = 8 * ti + r; return (rho % N) * so1 + (rho / N) * so2; };
+  const int fq = slab_f(q);
+  cplx a[KK];
+  // source offset (complex elements) of element b = q of row rho; element 4kk + q is `kstride * kk` further
+  auto src_off = [&](int rho) -> long long {
+    const int o1 = rho % N, o2 = rho / N;
+    if (from_global) return (long long)o1 * d.g[O1] + (F == 3 ? (long long)o2 * d.g[O2] : 0) + (long long)q * d.g[P];
+    if (P == 1) return (o1 ^ fq ^ slab_f(o2)) + N * q + N * N * o2;            // (i0 = o1, i1 = b, i2 = o2)
+    return (o1 ^ slab_f(o2) ^ fq) + N * o2 + N * N * q;                        // P == 2: (i0 = o1, i1 = o2, i2 = b)
+  };
+  const long long kstride = from_global ? 4 * d.g[P] : (P == 1 ? 4 * N : 4 * N * N);
+  const cplx* src = from_global ? gsrc : sm;
   int ti = warp;
   if (ti < ntiles) {
-    const long long soff = tile_off(ti, src_o1, src_o2);
+    const long long so = src_off(8 * ti + r);
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) a[ks] = src[2 * (soff + (2 * ks + kpair) * src_m) + part];
+    for (int kk = 0; kk < KK; ++kk) a[kk] = src[so + kk * kstride];
   }
   for (; ti < ntiles; ti += nwarps) {
+    // the next tile's element replaces a[kk] as soon as its two k-steps are issued: one tile of prefetch distance for
+    // every load without a second register set
     const int tn = ti + nwarps;
-    if (tn < ntiles) {
-      const long long soff = tile_off(tn, src_o1, src_o2);
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) an[ks] = src[2 * (soff + (2 * ks + kpair) * src_m) + part];
-    }
+    const bool more = tn < ntiles;
+    const long long son = more ? src_off(8 * tn + r) : 0;
     double acc[NT][2];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = 0.0; acc[nt][1] = 0.0; }
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
+    for (int kk = 0; kk < KK; ++kk) {
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) dmma884(acc[nt][0], acc[nt][1], a[ks], bf[ks][nt]);
-    const long long doff = tile_off(ti, dst_o1, dst_o2);
+      for (int nt = 0; nt < NT; ++nt) dmma884(acc[nt][0], acc[nt][1], a[kk].x, bf[2 * kk][nt]);
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      double2 v; v.x = acc[nt][0]; v.y = acc[nt][1];
-      *reinterpret_cast<double2*>(dst + 2 * (doff + (q + 4 * nt) * dst_m)) = v;
+      for (int nt = 0; nt < NT; ++nt) dmma884(acc[nt][0], acc[nt][1], a[kk].y, bf[2 * kk + 1][nt]);
+      if (more) a[kk] = src[son + kk * kstride];
     }
+    const int rho = 8 * ti + r, o1 = rho % N, o2 = rho / N;
+    if (to_global) {
+      cplx* dst = gdst + (long long)o1 * XST[O1] + (F == 3 ? (long long)o2 * XST[O2] : 0) + (long long)q * XST[P];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) a[ks] = an[ks];
+      for (int nt = 0; nt < NT; ++nt) dst[(long long)4 * nt * XST[P]] = cmake(acc[nt][0], acc[nt][1]);
+    } else if (P == 0) {                         // (i0 = c, i1 = o1, i2 = o2)
+      const int z = slab_f(o1) ^ slab_f(o2);
+      cplx* dst = sm + N * o1 + N * N * o2;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) dst[(4 * nt + q) ^ z] = cmake(acc[nt][0], acc[nt][1]);
+    } else {                                     // P == 1 of 3, in place: (i0 = o1, i1 = c, i2 = o2)
+      cplx* dst = sm + ((o1 ^ fq ^ slab_f(o2)) + N * q + N * N * o2);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) dst[4 * N * nt] = cmake(acc[nt][0], acc[nt][1]);
+    }
   }
 }
 
-// grid: (2*N, items); block 256 (8 warps); dynamic shared memory: S1*N^(F-1) complex (max SLAB3)
+// One slab `sub` = (w, s) of item d by a whole CTA; shared memory: N^3 complex slab + 3 N^2 complex staged messages.
 template <int N, int F>
-__device__ __forceinline__ void absorb_slab_body(const SlabDesc& d, double* sm) {
-  const int s = blockIdx.x & 1, w = blockIdx.x >> 1;
+__device__ __forceinline__ void absorb_slab_body(const SlabDesc& d, int sub, cplx* sm, const cplx* msm) {
+  const int s = sub & 1, w = sub >> 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   long long NF = N; for (int i = 1; i < F; ++i) NF *= N;
-  const double* gsrc = reinterpret_cast<const double*>(d.t + (long long)s * d.gs + (long long)w * d.gw);
-  double* gdst = reinterpret_cast<double*>(d.x + ((long long)w * 2 + s) * NF);
-  absorb_phase<N, F, 0>(d, gsrc, gdst, sm, lane, warp, nwarps);
+  const cplx* gsrc = d.t + (long long)s * d.gs + (long long)w * d.gw;
+  cplx* gdst = d.x + ((long long)w * 2 + s) * NF;
+  absorb_phase<N, F, 0>(d, gsrc, gdst, sm, msm, lane, warp, nwarps);
   __syncthreads();
-  absorb_phase<N, F, 1>(d, gsrc, gdst, sm, lane, warp, nwarps);
+  absorb_phase<N, F, 1>(d, gsrc, gdst, sm, msm, lane, warp, nwarps);
   if (F == 3) {
     __syncthreads();
-    absorb_phase<N, F, (F == 3 ? 2 : 1)>(d, gsrc, gdst, sm, lane, warp, nwarps);
+    absorb_phase<N, F, (F == 3 ? 2 : 1)>(d, gsrc, gdst, sm, msm, lane, warp, nwarps);
   }
 }
 
+template <int N>
+__device__ __forceinline__ void absorb_slab_item(const SlabDesc& d, int sub, cplx* sm, cplx* msm) {
+  // the item's messages, staged once: every phase builds its B fragments from shared memory
+  for (int idx = threadIdx.x; idx < d.F * N * N; idx += blockDim.x) msm[idx] = __ldg(d.m[idx / (N * N)] + idx % (N * N));
+  __syncthreads();
+  if (d.F == 3) absorb_slab_body<N, 3>(d, sub, sm, msm); else absorb_slab_body<N, 2>(d, sub, sm, msm);
+}
+
+// grid: (slabs, items); block 256 (8 warps); dynamic shared memory SlabCfg<N>::SMEM
 template <int N>
 __global__ void __launch_bounds__(256, 2) k_absorb_slab(const SlabDesc* __restrict__ descs) {
   const SlabDesc d = descs[blockIdx.y];
   if ((int)blockIdx.x >= d.nslabs) return;
   extern __shared__ cplx slab[];
-  double* sm = reinterpret_cast<double*>(slab);
-  if (d.F == 3) absorb_slab_body<N, 3>(d, sm); else absorb_slab_body<N, 2>(d, sm);
+  absorb_slab_item<N>(d, blockIdx.x, slab, slab + SlabCfg<N>::SLAB3);
 }
 
 struct CloseDmmaDesc {
@@ -148,94 +175,177 @@ struct CloseDmmaDesc {
   int* ticket;                       // zero-initialised, reset by the last CTA
 };
 
-// grid: (max nsplit, items); block 256 (8 warps); dynamic shared memory: 8 * (2N)^2 doubles
+// Split `sub` of the closing of item d by a whole CTA (256 threads); shared memory: 8 * 2 N^2 doubles.  Returns true in
+// the CTA that took the last ticket of the item (it has run the epilogue).
+// M[w, w'] = sum_K X[K, w] conj(T[K, w']) as the real GEMM  (w) x (K, part)  times  (K, part) x (w', part')  with
+// B[(K,re),(w',re)] = Re T, B[(K,im),(w',re)] = Im T, B[(K,re),(w',im)] = -Im T, B[(K,im),(w',im)] = Re T.  Lane (r, q) loads
+// whole complex elements (16 bytes) and feeds the real part to one k-step, the imaginary part to the next.  A K-group is
+// 4 complex K = (i1 pair) x (s pair): its 64 bytes are contiguous in T and two full sectors in X, so every sector that is
+// fetched is used whole.  Three groups are in flight per warp (register sets reloaded in place).
 template <int N>
-__global__ void __launch_bounds__(256, 2) k_close_dmma(const CloseDmmaDesc* __restrict__ descs) {
-  constexpr int MT = N / 4;               // tiles of 8 real rows = 4 w x (re, im)
-  const CloseDmmaDesc d = descs[blockIdx.y];
-  if ((int)blockIdx.x >= d.nsplit) return;
-  extern __shared__ double red[];
+__device__ __forceinline__ bool close_dmma_item(const CloseDmmaDesc& d, int sub, double* red) {
+  constexpr int MT = N / 8;               // m-tiles of 8 complex rows w
+  constexpr int NT = N / 4;               // n-tiles of 8 real columns = 4 w' x (re, im)
+  constexpr int NSET = 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 2, q = lane & 3;
-  const int wl = r >> 1, part = r & 1;
+  const int s = q & 1, ih = q >> 1, pp = r & 1;
   long long NF = N; for (int i = 1; i < d.F; ++i) NF *= N;
-  // k-step = 4 consecutive slab indices (i1 = 4*j4 + q) at fixed s: an X fragment load touches 4 x 64 contiguous bytes
-  const long long ksteps = NF / 2;
-  const long long per = (ksteps + d.nsplit - 1) / d.nsplit;
-  const long long k_begin = (long long)blockIdx.x * per, k_end = min(ksteps, k_begin + per);
-  const double* X = reinterpret_cast<const double*>(d.x);
-  const double* T = reinterpret_cast<const double*>(d.t);
-  double acc[MT][MT][2];
+  const long long groups = NF / 2;        // (i1 pair, i2, i3)
+  const long long per = (groups + d.nsplit - 1) / d.nsplit;
+  const long long g_begin = (long long)sub * per, g_end = min(groups, g_begin + per);
+  // lane-constant parts of the addresses
+  const cplx* xl = d.x + (long long)s * NF + ih;                 // + (8 mt + r) * 2 NF + sigma0
+  const cplx* tl = d.t + s + (long long)ih * d.g[0] + (long long)(r >> 1) * d.gw;     // + 4 nt * gw + toff0
+  const long long g2 = d.F == 3 ? d.g[2] : 0;
+  cplx a[NSET][MT], b[NSET][NT];
+  auto load = [&](int set, long long g) {
+    if (g < g_end) {
+      const int j = (int)(g % (N / 2));
+      const long long rest = g / (N / 2);
+      const int i2 = (int)(rest % N), i3 = (int)(rest / N);
+      const long long sigma0 = 2 * j + (long long)N * i2 + (long long)N * N * i3;
+      const long long toff0 = 2 * j * d.g[0] + i2 * d.g[1] + i3 * g2;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) a[set][mt] = __ldcg(xl + (long long)(8 * mt + r) * 2 * NF + sigma0);   // X: written by other CTAs, read through L2
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) b[set][nt] = tl[toff0 + (long long)4 * nt * d.gw];
+    } else {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) a[set][mt] = cmake(0, 0);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) b[set][nt] = cmake(0, 0);
+    }
+  };
+  double acc[MT][NT][2];
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < MT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-  // two k-steps (16 operand loads) in flight per warp: the kernel is bound by the latency of its operand loads
-  for (long long kap = k_begin + warp; kap < k_end; kap += 16) {
-    double a[2][MT], b[2][MT];
+    for (int j = 0; j < NT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  long long g = g_begin + warp;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const long long kk = kap + 8 * u;
-      const bool ok = kk < k_end;
-      const long long kq = ok ? kk : kap;
-      const int s = (int)(kq & 1);
-      const long long jj = kq >> 1;
-      const int j4 = (int)(jj % (N / 4));
-      const long long rest = jj / (N / 4);
-      const int i2 = (int)(rest % N), i3 = (int)(rest / N);
-      const int i1 = 4 * j4 + q;
-      const long long sigma = i1 + (long long)N * i2 + (long long)N * N * i3;
-      const long long toff = s + i1 * d.g[0] + i2 * d.g[1] + (d.F == 3 ? i3 * d.g[2] : 0);
+  for (int u = 0; u < NSET; ++u) load(u, g + 8 * u);
+  for (; g < g_end; g += 8 * NSET) {
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        const int w = 4 * mt + wl;
-        a[u][mt] = ok ? X[2 * (((long long)w * 2 + s) * NF + sigma) + part] : 0.0;
-        b[u][mt] = ok ? T[2 * (toff + (long long)w * d.gw) + part] : 0.0;
+    for (int u = 0; u < NSET; ++u) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {            // in place: (Re T, Im T) -> (B of k-step re, B of k-step im) for this lane's column parity
+        const cplx t = b[u][nt];
+        b[u][nt] = pp ? cmake(-t.y, t.x) : t;
       }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < MT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[u][mt], b[u][nt]);
+        for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[u][mt].x, b[u][nt].x);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[u][mt].y, b[u][nt].y);
+      load(u, g + 8 * (u + NSET));
+    }
   }
-  // fixed-order reduction over the 8 warps
-  constexpr int PD = 2 * N;                        // P is PD x PD real
-  double* mine = red + (size_t)warp * PD * PD;
+  // fixed-order reduction over the 8 warps: each warp's N x 2N real block, then column pairs -> complex
+  constexpr int LD = N;
+  double* mine = red + (size_t)warp * 2 * N * N;
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < MT; ++nt) {
-      int row = 8 * mt + r, col = 8 * nt + 2 * q;
-      mine[row + PD * col] = acc[mt][nt][0];
-      mine[row + PD * (col + 1)] = acc[mt][nt][1];
+    for (int nt = 0; nt < NT; ++nt) {
+      const int row = 8 * mt + r, col = 8 * nt + 2 * q;
+      mine[row + LD * col] = acc[mt][nt][0];
+      mine[row + LD * (col + 1)] = acc[mt][nt][1];
     }
   __syncthreads();
-  cplx* out = d.partial + (size_t)blockIdx.x * N * N;
+  cplx* out = d.partial + (size_t)sub * N * N;
   for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
     const int w = idx % N, wp = idx / N;
-    double rr = 0, ii = 0, ir = 0, ri = 0;
+    double re = 0, im = 0;
     for (int wv = 0; wv < 8; ++wv) {
-      const double* P = red + (size_t)wv * PD * PD;
-      rr += P[(2 * w) + PD * (2 * wp)];
-      ii += P[(2 * w + 1) + PD * (2 * wp + 1)];
-      ir += P[(2 * w + 1) + PD * (2 * wp)];
-      ri += P[(2 * w) + PD * (2 * wp + 1)];
+      const double* P = red + (size_t)wv * 2 * N * N;
+      re += P[w + LD * (2 * wp)];
+      im += P[w + LD * (2 * wp + 1)];
     }
-    out[idx] = cmake(rr + ii, ir - ri);              // X conj(T): re = rr + ii, im = ir - ri
+    __stcg(out + idx, cmake(re, im));
   }
-  if (d.epilogue) {
-    __shared__ int last;
-    __threadfence();                                   // partials visible before the ticket
+  if (!d.epilogue) return false;
+  __shared__ int last;
+  __threadfence();                                   // partials visible before the ticket
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(d.ticket, 1) == d.nsplit - 1);
+  __syncthreads();
+  const bool is_last = last;
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x == 0) *d.ticket = 0;
+    close_reduce_body(*d.epilogue, reinterpret_cast<cplx*>(red), red + 2 * N * N);
+  }
+  return is_last;
+}
+
+// grid: (max nsplit, items); block 256 (8 warps); dynamic shared memory: 8 * 2 N^2 doubles (>= N^2 complex + 32 doubles)
+template <int N>
+__global__ void __launch_bounds__(256, 2) k_close_dmma(const CloseDmmaDesc* __restrict__ descs) {
+  const CloseDmmaDesc d = descs[blockIdx.y];
+  if ((int)blockIdx.x >= d.nsplit) return;
+  extern __shared__ double red[];
+  close_dmma_item<N>(d, blockIdx.x, red);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_bp_level: one dependency level of a BP sweep as ONE persistent launch.  CTAs draw work items from an in-order queue:
+// absorb items (one slab of one message) and closing items (one split of one message; the last one runs the message
+// epilogue).  A closing item waits until every slab of its message is done; the queue lists the closing items of message
+// m - D right after the absorb items of message m, so they are normally ready when drawn, and the memory-bound closing
+// of one message overlaps the tensor-bound absorption of the next ones.  Every wait is on items that were drawn
+// earlier, i.e. that are running on resident CTAs and never wait themselves: the queue cannot deadlock.
+// ---------------------------------------------------------------------------------------------------------------
+struct LevelQueue {
+  const int2* items;      // x >= 0: absorb slab y of fast chain x; x < 0: closing split y of fast chain ~x
+  int n;
+  int* counter;           // [0] next item, [1] CTAs that left the loop (the last one resets both), [2] error flag
+  const SlabDesc* slabs;
+  const CloseDmmaDesc* closes;
+  int* slab_done;         // per fast chain; reset by the CTA that runs the chain's epilogue
+};
+
+template <int N>
+__global__ void __launch_bounds__(256, 2) k_bp_level(const LevelQueue Q) {
+  extern __shared__ cplx dyn[];
+  cplx* msm = dyn + SlabCfg<N>::SLAB3;
+  __shared__ int s_item;
+  __shared__ int2 s_entry;
+  for (;;) {
+    if (threadIdx.x == 0) { const int i = atomicAdd(Q.counter, 1); s_item = i; s_entry = Q.items[min(i, Q.n - 1)]; }
     __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(d.ticket, 1) == d.nsplit - 1);
-    __syncthreads();
-    if (last) {
-      __threadfence();
-      if (threadIdx.x == 0) *d.ticket = 0;
-      close_reduce_body(*d.epilogue, reinterpret_cast<cplx*>(red), red + 2 * N * N);
+    const int it = s_item;
+    if (it >= Q.n) break;
+    const int2 e = s_entry;
+    if (e.x >= 0) {
+      const SlabDesc d = Q.slabs[e.x];
+      absorb_slab_item<N>(d, e.y, dyn, msm);
+      __syncthreads();                               // the CTA's part of X ...
+      if (threadIdx.x == 0) { __threadfence(); atomicAdd(Q.slab_done + e.x, 1); }     // ... is visible before the slab counter moves
+    } else {
+      const int ci = ~e.x;
+      const CloseDmmaDesc d = Q.closes[ci];
+      if (threadIdx.x == 0) {
+        const int need = Q.slabs[ci].nslabs;
+        long long spins = 0;
+        while (*(volatile int*)(Q.slab_done + ci) < need) {
+          __nanosleep(100);
+          if (++spins > (1ll << 24)) { atomicExch(Q.counter + 2, 1); break; }     // never hang the device
+        }
+        if (spins) atomicAdd(Q.counter + 3, (int)min(spins, 1000000ll));             // statistics: polls spent waiting
+        __threadfence();
+      }
+      __syncthreads();
+      if (close_dmma_item<N>(d, e.y, reinterpret_cast<double*>(dyn)) && threadIdx.x == 0) Q.slab_done[ci] = 0;
     }
+    __syncthreads();                                 // shared memory, s_item and s_entry are reused by the next item
+  }
+  if (threadIdx.x == 0) {
+    const int gone = atomicAdd(Q.counter + 1, 1);
+    if (gone == (int)gridDim.x - 1) { Q.counter[0] = 0; Q.counter[1] = 0; __threadfence(); }
   }
 }
 

@@ -46,6 +46,8 @@ static void set_smem_attrs() {   // per device: called at every handle creation 
   cudaFuncSetAttribute(k_absorb_slab<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_close_dmma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_close_dmma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_bp_level<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_bp_level<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_close_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -259,6 +261,11 @@ static void bp_cache_drop(tnqs_ctx* c) {
   for (void* p : pc->owned) c->dfree(p);
   delete pc; c->bp_cache = nullptr;
 }
+static int bp_level_split_cap() {
+  static int cap = 0;
+  if (!cap) { const char* e = getenv("TNQS_BP_SPLIT"); cap = e ? std::max(1, atoi(e)) : 16; }
+  return cap;
+}
 static bool graphs_disabled() {
   static int d = -1;
   if (d < 0) { const char* e = getenv("TNQS_NO_GRAPH"); d = (e && e[0] == '1') ? 1 : 0; }
@@ -280,7 +287,7 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
   if (mean_out) *mean_out = NAN;
   if (nseq == 0) return;
   const bool want_diff = o.tolerance >= 0;
-  // dependency levels of the sequential (Gauss-Seidel) order; reads of a level happen before its commit
+  // dependency levels of the sequential (Gauss-Seidel) order; no message is read and written in the same level
   std::vector<int> level(nseq, 0);
   int nlevels = 1;
   if (o.mode == TNQS_BP_REFERENCE_ORDER) {
@@ -293,7 +300,9 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
         int r = c->dedge(u, e);
         if (lastwrite[r] >= 0) lvl = std::max(lvl, lastwrite[r] + 1);     // RAW
       }
-      lvl = std::max(lvl, lastread[k]);                                     // WAR (same level is safe)
+      lvl = std::max(lvl, lastread[k] + 1);                                 // WAR: strictly later, so a fused level (absorb and
+                                                                            // epilogue items of different messages in flight
+                                                                            // together) may update its messages in place
       lvl = std::max(lvl, lastwrite[k] + 1);                                // WAW
       level[i] = lvl; lastwrite[k] = lvl;
       for (int e : c->inc[v]) {
@@ -333,10 +342,10 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
         }
         ch.dst = c->msg_st(k); ch.prev = c->msg(k); ch.diff = want_diff ? nc->d_diff + i : nullptr;
         ch.bp_mode = 1; ch.normalize = o.normalize; ch.hermitize = o.hermitize; ch.commit_k = k;
-        ch.split_cap = o.mode == TNQS_BP_JACOBI ? 4 : 16;      // whole-sweep launches want long CTAs, level launches want many
+        ch.split_cap = o.mode == TNQS_BP_JACOBI ? 4 : bp_level_split_cap();      // whole-sweep launches want long CTAs, level launches more
         levels[level[i]].push_back(ch);
       }
-      Plan np = build_plan(c, levels, scratch_budget(c), old ? &old->plan : nullptr);
+      Plan np = build_plan(c, levels, scratch_budget(c), old ? &old->plan : nullptr, /*strict_levels=*/o.mode == TNQS_BP_REFERENCE_ORDER);
       if (nc->graph && !same_launches(np, nc->plan)) { cudaGraphExecDestroy(nc->graph); nc->graph = nullptr; }
       nc->plan = np;
     } catch (...) { c->arena_bypass = false; for (void* p : c->temp) c->dfree(p); c->temp.swap(saved); if (!old) delete nc; else { c->bp_cache = nullptr; } throw; }
@@ -401,6 +410,13 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
         if (mean <= o.tolerance) break;
       }
     }
+  }
+  if (plan.d_qctr) {
+    int q[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(q, plan.d_qctr, sizeof(q), cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    if (q[3]) { static const char* dbg = getenv("TNQS_DEBUG_QUEUE"); if (dbg) fprintf(stderr, "[tnqs] k_bp_level waits: %d polls in %d sweeps\n", q[3], it); CU(cudaMemsetAsync(plan.d_qctr + 3, 0, sizeof(int), c->stream)); }
+    REQUIRE(q[2] == 0, TNQS_ERR_CUDA, "internal: a BP level queue wait timed out");
   }
   if (it > o.maxiter) it = o.maxiter;
   if (iters_out) *iters_out = it;
@@ -564,7 +580,7 @@ void GateBatch::absorb_outer(bool inverse) {   // forward: on A (psi~); inverse:
     const int N = w ? 16 : 8;
     SlabDesc* dsd = c->upload(slab[w]);
     dim3 grid((unsigned)((maxcols[w] + 1) / 2 * 2), (unsigned)slab[w].size(), 1);
-    size_t smem = (size_t)((N + 4) * N + 4) * N * sizeof(cplx);
+    size_t smem = N == 16 ? SlabCfg<16>::SMEM : SlabCfg<8>::SMEM;
     if (w) LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<16>, grid, 256, smem, dsd);
     else LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<8>, grid, 256, smem, dsd);
   }
