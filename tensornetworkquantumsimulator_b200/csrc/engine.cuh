@@ -167,7 +167,7 @@ struct Chain {
   int split_cap = 16;                // upper bound of the split-K factor of the closing (a property of the request, never of the batch)
 };
 
-struct LaunchRec { size_t off; int count; dim3 grid; size_t smem; bool dmma = false; };
+struct LaunchRec { size_t off; int count; dim3 grid; size_t smem; bool dmma = false; int tpc = 1; };
 
 static bool dmma_disabled() {
   static int disabled = -1;
@@ -176,7 +176,7 @@ static bool dmma_disabled() {
 }
 
 // Kernel choice and grid of one batched mode_apply launch: the tensor-core kernel when every item has n, np <= 32.
-struct ApplyLaunch { bool dmma; dim3 grid; size_t smem; };
+struct ApplyLaunch { bool dmma; dim3 grid; size_t smem; int tpc; };      // tpc: row tiles per CTA of k_leg_dmma
 static ApplyLaunch plan_apply_launch(const ModeApplyDesc* d, size_t count) {
   bool ok = !dmma_disabled(); long long maxrows = 1, maxtiles = 1; int maxnp = 1; size_t smem = 0;
   for (size_t i = 0; i < count; ++i) {
@@ -185,13 +185,18 @@ static ApplyLaunch plan_apply_launch(const ModeApplyDesc* d, size_t count) {
     maxrows = std::max(maxrows, rows); maxnp = std::max(maxnp, d[i].np);
     if (ok) { const int rpc = leg_rows_per_cta(d[i].np); maxtiles = std::max(maxtiles, (rows + rpc - 1) / rpc); smem = std::max(smem, leg_smem_bytes(d[i].n, d[i].np)); }
   }
-  if (ok) return {true, dim3((unsigned)maxtiles, (unsigned)count, 1), smem};
-  return {false, dim3((unsigned)((maxrows + MA_BM - 1) / MA_BM), (unsigned)count, (unsigned)((maxnp + MA_BN - 1) / MA_BN)), 0};
+  if (ok) {
+    // several row tiles per CTA once the launch is many waves deep (2 CTAs x 148 SMs per wave): the matrix fill is amortised
+    long long tpc = std::max<long long>(1, std::min<long long>(8, maxtiles * (long long)count / (8 * 296)));
+    tpc = std::min(tpc, maxtiles);
+    return {true, dim3((unsigned)((maxtiles + tpc - 1) / tpc), (unsigned)count, 1), smem, (int)tpc};
+  }
+  return {false, dim3((unsigned)((maxrows + MA_BM - 1) / MA_BM), (unsigned)count, (unsigned)((maxnp + MA_BN - 1) / MA_BN)), 0, 1};
 }
 struct SubLevel {
   LaunchRec slab{0, 0, dim3(), 0}, dclose{0, 0, dim3(), 0};   // DMMA fast path (kernels_dmma.cuh)
   LaunchRec fused{0, 0, dim3(), 0};                            // the same chains as one persistent launch (k_bp_level): queue items
-  int fastN = 0;
+  int fastN = 0, close_cap = 16;                               // close_cap: split cap of the fast chains (selects the closing CTA size)
   LaunchRec gate1{0, 0, dim3(), 0};
   std::vector<LaunchRec> steps;
   LaunchRec close{0, 0, dim3(), 0}, reduce{0, 0, dim3(), 0};
@@ -345,7 +350,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
           fast_poff[j] = pscan; pscan += cm.partial_elems;
           if (!N) continue;
           REQUIRE(sl.fastN == 0 || sl.fastN == N, TNQS_ERR_UNSUPPORTED, "mixed fast-path bond dimensions in one level");
-          sl.fastN = N; fast[j] = 1;
+          sl.fastN = N; fast[j] = 1; sl.close_cap = ch.split_cap;
           const int v = ch.v, F = (int)ch.absorb.size();
           SlabDesc a; a.t = c->site[v]; a.x = buf0[j]; a.F = F;
           CloseDmmaDesc b; b.x = buf0[j]; b.t = c->site[v]; b.partial = partial + fast_poff[j]; b.F = F; b.nsplit = cm.nsplit;
@@ -426,7 +431,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         lr.count = (int)(ma.size() - lr.off);
         if (lr.count) {
           ApplyLaunch al = plan_apply_launch(ma.data() + lr.off, lr.count);
-          lr.grid = al.grid; lr.dmma = al.dmma; lr.smem = al.smem;
+          lr.grid = al.grid; lr.dmma = al.dmma; lr.smem = al.smem; lr.tpc = al.tpc;
           sl.steps.push_back(lr);
         }
         (void)maxtiles; (void)maxcol;
@@ -502,7 +507,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
 }
 
 static bool same_rec(const LaunchRec& a, const LaunchRec& b) {
-  return a.off == b.off && a.count == b.count && a.grid.x == b.grid.x && a.grid.y == b.grid.y && a.grid.z == b.grid.z && a.smem == b.smem && a.dmma == b.dmma;
+  return a.off == b.off && a.count == b.count && a.grid.x == b.grid.x && a.grid.y == b.grid.y && a.grid.z == b.grid.z && a.smem == b.smem && a.dmma == b.dmma && a.tpc == b.tpc;
 }
 // True when two plans issue the same launches over the same device buffers (a captured CUDA graph of one replays the other).
 static bool same_launches(const Plan& a, const Plan& b) {
@@ -513,7 +518,7 @@ static bool same_launches(const Plan& a, const Plan& b) {
     if (x.subs.size() != y.subs.size() || x.commit_off != y.commit_off || x.commit_count != y.commit_count) return false;
     for (size_t i = 0; i < x.subs.size(); ++i) {
       const SubLevel &p = x.subs[i], &q = y.subs[i];
-      if (p.fastN != q.fastN || p.steps.size() != q.steps.size() || !same_rec(p.slab, q.slab) || !same_rec(p.dclose, q.dclose) || !same_rec(p.fused, q.fused) ||
+      if (p.fastN != q.fastN || p.close_cap != q.close_cap || p.steps.size() != q.steps.size() || !same_rec(p.slab, q.slab) || !same_rec(p.dclose, q.dclose) || !same_rec(p.fused, q.fused) ||
           !same_rec(p.gate1, q.gate1) || !same_rec(p.close, q.close) || !same_rec(p.reduce, q.reduce)) return false;
       for (size_t j = 0; j < p.steps.size(); ++j) if (!same_rec(p.steps[j], q.steps[j])) return false;
     }
@@ -526,10 +531,19 @@ static void launch_mode_apply(tnqs_ctx* c, int kc, const std::vector<ModeApplyDe
   if (ma.empty()) return;
   ModeApplyDesc* dma = c->upload(ma);
   ApplyLaunch al = plan_apply_launch(ma.data(), ma.size());
-  if (al.dmma) LAUNCH(c, kc, k_leg_dmma, al.grid, 256, al.smem, dma);
+  if (al.dmma) LAUNCH(c, kc, k_leg_dmma, al.grid, 256, al.smem, dma, al.tpc);
   else LAUNCH(c, kc, k_mode_apply, al.grid, 256, 0, dma);
 }
 
+// CTA size of the closing launch.  Level launches (requests with a split cap above 4: REFERENCE_ORDER) use 4-warp CTAs, so
+// that 4 fit an SM and a 32-message level is one wave; whole-sweep launches (JACOBI) use 8 warps.  Like the split factor
+// it is a property of the request, never of the batch: a partitioned sweep sums in the same order as the full one.
+static int close_threads(int split_cap) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("TNQS_CLOSE_THREADS"); forced = e ? atoi(e) : 0; }
+  if (forced) return forced;
+  (void)split_cap; return 256;      // measured on C2: 4-warp CTAs (one wave per level) are not faster than 8-warp ones
+}
 static void run_plan(tnqs_ctx* c, const Plan& p) {
   for (const LevelPlan& lp : p.levels) {
     for (const SubLevel& sl : lp.subs) {
@@ -541,15 +555,15 @@ static void run_plan(tnqs_ctx* c, const Plan& p) {
       } else if (sl.slab.count) {
         if (sl.fastN == 16) {
           LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<16>, sl.slab.grid, 256, sl.slab.smem, p.d_slab + sl.slab.off);
-          LAUNCH(c, TNQS_KC_MODE_CLOSE, k_close_dmma<16>, sl.dclose.grid, 256, sl.dclose.smem, p.d_dclose + sl.dclose.off);
+          LAUNCH(c, TNQS_KC_MODE_CLOSE, k_close_dmma<16>, sl.dclose.grid, close_threads(sl.close_cap), sl.dclose.smem, p.d_dclose + sl.dclose.off);
         } else {
           LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<8>, sl.slab.grid, 256, sl.slab.smem, p.d_slab + sl.slab.off);
-          LAUNCH(c, TNQS_KC_MODE_CLOSE, k_close_dmma<8>, sl.dclose.grid, 256, sl.dclose.smem, p.d_dclose + sl.dclose.off);
+          LAUNCH(c, TNQS_KC_MODE_CLOSE, k_close_dmma<8>, sl.dclose.grid, close_threads(sl.close_cap), sl.dclose.smem, p.d_dclose + sl.dclose.off);
         }
       }
       if (sl.gate1.count) LAUNCH(c, TNQS_KC_MISC, k_gate1, sl.gate1.grid, 256, 0, p.d_gate1 + sl.gate1.off);
       for (const LaunchRec& lr : sl.steps) {
-        if (lr.dmma) LAUNCH(c, TNQS_KC_MODE_APPLY, k_leg_dmma, lr.grid, 256, lr.smem, p.d_apply + lr.off);
+        if (lr.dmma) LAUNCH(c, TNQS_KC_MODE_APPLY, k_leg_dmma, lr.grid, 256, lr.smem, p.d_apply + lr.off, lr.tpc);
         else LAUNCH(c, TNQS_KC_MODE_APPLY, k_mode_apply, lr.grid, 256, 0, p.d_apply + lr.off);
       }
       if (sl.close.count) {

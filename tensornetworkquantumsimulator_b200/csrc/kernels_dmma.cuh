@@ -175,7 +175,7 @@ struct CloseDmmaDesc {
   int* ticket;                       // zero-initialised, reset by the last CTA
 };
 
-// Split `sub` of the closing of item d by a whole CTA (256 threads); shared memory: 8 * 2 N^2 doubles.  Returns true in
+// Split `sub` of the closing of item d by a whole CTA (any number of warps nw <= 8); shared memory: nw * 2 N^2 doubles (>= N^2 complex + 32 doubles).  Returns true in
 // the CTA that took the last ticket of the item (it has run the epilogue).
 // M[w, w'] = sum_K X[K, w] conj(T[K, w']) as the real GEMM  (w) x (K, part)  times  (K, part) x (w', part')  with
 // B[(K,re),(w',re)] = Re T, B[(K,im),(w',re)] = Im T, B[(K,re),(w',im)] = -Im T, B[(K,im),(w',im)] = Re T.  Lane (r, q) loads
@@ -187,7 +187,7 @@ __device__ __forceinline__ bool close_dmma_item(const CloseDmmaDesc& d, int sub,
   constexpr int MT = N / 8;               // m-tiles of 8 complex rows w
   constexpr int NT = N / 4;               // n-tiles of 8 real columns = 4 w' x (re, im)
   constexpr int NSET = 3;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int r = lane >> 2, q = lane & 3;
   const int s = q & 1, ih = q >> 1, pp = r & 1;
   long long NF = N; for (int i = 1; i < d.F; ++i) NF *= N;
@@ -224,8 +224,8 @@ __device__ __forceinline__ bool close_dmma_item(const CloseDmmaDesc& d, int sub,
     for (int j = 0; j < NT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
   long long g = g_begin + warp;
 #pragma unroll
-  for (int u = 0; u < NSET; ++u) load(u, g + 8 * u);
-  for (; g < g_end; g += 8 * NSET) {
+  for (int u = 0; u < NSET; ++u) load(u, g + nw * u);
+  for (; g < g_end; g += nw * NSET) {
 #pragma unroll
     for (int u = 0; u < NSET; ++u) {
 #pragma unroll
@@ -241,10 +241,10 @@ __device__ __forceinline__ bool close_dmma_item(const CloseDmmaDesc& d, int sub,
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[u][mt].y, b[u][nt].y);
-      load(u, g + 8 * (u + NSET));
+      load(u, g + nw * (u + NSET));
     }
   }
-  // fixed-order reduction over the 8 warps: each warp's N x 2N real block, then column pairs -> complex
+  // fixed-order reduction over the warps: each warp's N x 2N real block, then column pairs -> complex
   constexpr int LD = N;
   double* mine = red + (size_t)warp * 2 * N * N;
 #pragma unroll
@@ -260,7 +260,7 @@ __device__ __forceinline__ bool close_dmma_item(const CloseDmmaDesc& d, int sub,
   for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
     const int w = idx % N, wp = idx / N;
     double re = 0, im = 0;
-    for (int wv = 0; wv < 8; ++wv) {
+    for (int wv = 0; wv < nw; ++wv) {
       const double* P = red + (size_t)wv * 2 * N * N;
       re += P[w + LD * (2 * wp)];
       im += P[w + LD * (2 * wp + 1)];
@@ -283,6 +283,7 @@ __device__ __forceinline__ bool close_dmma_item(const CloseDmmaDesc& d, int sub,
 }
 
 // grid: (max nsplit, items); block 256 (8 warps); dynamic shared memory: 8 * 2 N^2 doubles (>= N^2 complex + 32 doubles)
+// Level launches use 128-thread CTAs (4 resident per SM: a 32-message level fits one wave), whole-sweep launches 256.
 template <int N>
 __global__ void __launch_bounds__(256, 2) k_close_dmma(const CloseDmmaDesc* __restrict__ descs) {
   const CloseDmmaDesc d = descs[blockIdx.y];
@@ -360,21 +361,27 @@ __global__ void __launch_bounds__(256, 2) k_bp_level(const LevelQueue Q) {
 // ---------------------------------------------------------------------------------------------------------------
 __host__ __device__ inline int leg_groups(int np) { int g = (np + 15) / 16; return g == 3 ? 4 : g; }    // 1, 2 or 4
 __host__ __device__ inline int leg_rows_per_cta(int np) { return 32 * (8 / leg_groups(np)); }
-__host__ __device__ inline int leg_ldb(int np) { return 32 * leg_groups(np) + 8; }                       // == 8 mod 32: conflict-free
-inline size_t leg_smem_bytes(int n, int np) { return (size_t)(4 * ((n + 1) / 2)) * leg_ldb(np) * sizeof(double); }
+__host__ __device__ inline int leg_ldb(int np) { return 32 * leg_groups(np) + 2; }                       // == 2 mod 8: conflict-free fragment loads
+__host__ __device__ inline int leg_kk(int n) { return ((n + 3) / 4 + 1) / 2 * 2; }                       // groups of 4 complex K, rounded up to even
+inline size_t leg_smem_bytes(int n, int np) { return (size_t)(8 * leg_kk(n)) * leg_ldb(np) * sizeof(double); }
 
-__global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __restrict__ descs) {
+// K order: lane (r, q) loads the whole complex element b = 4kk + q of its row (16 bytes) and feeds the real part to one
+// k-step and the imaginary part to the next (B rows (b, re) and (b, im)); the next group's loads are in flight while the
+// current one multiplies.
+// A CTA fills the expanded matrix once and then walks `tpc` consecutive row tiles with it (the fill costs about as much as
+// one tile at n = 32).
+__global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __restrict__ descs, int tpc) {
   const ModeApplyDesc d = descs[blockIdx.y];
   const int G = leg_groups(d.np), LDB = leg_ldb(d.np);
   const int rows_per_cta = leg_rows_per_cta(d.np);
   const long long rows = (long long)d.L * d.R;
-  const long long row0 = (long long)blockIdx.x * rows_per_cta;
-  if (row0 >= rows) return;
+  if ((long long)blockIdx.x * tpc * rows_per_cta >= rows) return;
   extern __shared__ double Bs[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r = lane >> 2, q = lane & 3, kpair = q >> 1, part = q & 1;
+  const int r = lane >> 2, q = lane & 3;
   const int n = d.n, np = d.np;
-  const int K2 = 4 * ((n + 1) / 2);              // real K rounded up to whole k-steps (multiples of 4)
+  const int KK = leg_kk(n);                      // K groups (4 complex each), even
+  const int K2 = 8 * KK;                         // real K rows held in shared memory
   const int N2 = 32 * G;                         // real columns held in shared memory
   const bool conj_m = d.flags & 1, trans_m = d.flags & 2;
   // B[(b, p), (c, p')]: p == p' -> Re m[b,c]; (im, re) -> -Im; (re, im) -> +Im; zero padding outside n x np
@@ -392,58 +399,68 @@ __global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __rest
   __syncthreads();
   const int grp = warp % G;
   const int rg = warp / G;                                     // row group of 32 rows
+  const double* bs = Bs + 32 * grp + r + 2 * q * LDB;          // + (8 kk + part) * LDB + 8 j
+  for (int tile = 0; tile < tpc; ++tile) {
+  const long long row0 = ((long long)blockIdx.x * tpc + tile) * rows_per_cta;
+  if (row0 >= rows) break;
   const long long wrow0 = row0 + (long long)rg * 32;
-  const double* in = reinterpret_cast<const double*>(d.in);
-  double* out = reinterpret_cast<double*>(d.out);
-  long long soff[4], doff[4];
+  int soff[4];                                                 // tensors have fewer than 2^31 elements
   bool valid[4];
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     long long row = wrow0 + 8 * t + r;
     valid[t] = row < rows;
     long long rr = valid[t] ? row / d.L : 0, l = valid[t] ? row - rr * d.L : 0;
-    soff[t] = l + rr * d.in_sr; doff[t] = l + rr * d.out_sr;
+    soff[t] = (int)(l + rr * d.in_sr);
   }
   double acc[4][4][2];
 #pragma unroll
   for (int t = 0; t < 4; ++t)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc[t][j][0] = 0.0; acc[t][j][1] = 0.0; }
-  const int ncol0 = 32 * grp;                                   // first real column of this warp's group
-  for (int ks0 = 0; ks0 < K2 / 4; ks0 += 4) {
-    double a[4][4];
+  cplx a[2][4];
+  auto load = [&](int set, int kk) {
+    const int b = 4 * kk + q;
+    const bool bok = b < n;
+    const cplx* in_b = d.in + (long long)b * d.in_sb;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int b = 2 * (ks0 + u) + kpair;
+    for (int t = 0; t < 4; ++t) a[set][t] = (valid[t] && bok) ? in_b[soff[t]] : cmake(0, 0);
+  };
+  auto mult = [&](int set, int kk) {
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
-        a[u][t] = (valid[t] && b < n) ? in[2 * (soff[t] + (long long)b * d.in_sb) + part] : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (4 * (ks0 + u) >= K2) break;
+    for (int part = 0; part < 2; ++part) {
       double bf[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = Bs[(4 * (ks0 + u) + q) * LDB + ncol0 + 8 * j + r];
+      for (int j = 0; j < 4; ++j) bf[j] = bs[(8 * kk + part) * LDB + 8 * j];
 #pragma unroll
       for (int t = 0; t < 4; ++t)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[t][j][0], acc[t][j][1], a[u][t], bf[j]);
+        for (int j = 0; j < 4; ++j) dmma884(acc[t][j][0], acc[t][j][1], part ? a[set][t].y : a[set][t].x, bf[j]);
     }
+  };
+  load(0, 0);
+  for (int kk = 0; kk < KK; kk += 2) {
+    load(1, kk + 1);
+    mult(0, kk);
+    if (kk + 2 < KK) load(0, kk + 2);
+    mult(1, kk + 1);
   }
   __syncthreads();                                              // every load of the CTA tile precedes every store
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     if (!valid[t]) continue;
+    // output fields are re-read from the descriptor here instead of living in registers through the multiply loop
+    const ModeApplyDesc* dp = descs + blockIdx.y;
+    const long long out_sr = dp->out_sr, out_sb = dp->out_sb;
+    const long long row = wrow0 + 8 * t + r, rr = row / d.L, l = row - rr * d.L;
+    cplx* o = dp->out + l + rr * out_sr;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = 16 * grp + 4 * j + q;
-      if (c < np) {
-        double2 v; v.x = acc[t][j][0]; v.y = acc[t][j][1];
-        *reinterpret_cast<double2*>(out + 2 * (doff[t] + (long long)c * d.out_sb)) = v;
-      }
+      if (c < np) o[(long long)c * out_sb] = cmake(acc[t][j][0], acc[t][j][1]);
     }
   }
+  }   // tiles
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -526,6 +543,106 @@ __global__ void __launch_bounds__(256, 2) k_close_leg_dmma(const ModeCloseDesc* 
         ri += P[(2 * lb) + 32 * (2 * lbp + 1)];
       }
       out[idx] = cmake(rr + ii, ir - ri);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_gram_dmma: Gram matrix of a tall column-major matrix, G[b, b'] = sum_rows A[row, b] conj(A[row, b']) (n <= 64), the
+// CholeskyQR2 step.  Same formulation as the BP closing (complex rows, 16-byte operand loads, K order permuted so that a
+// K-group = 4 consecutive rows = 64 contiguous bytes of a column, three groups in flight per warp).  A warp owns a
+// 16 x 16 complex quadrant of G; the 8 warps are quadrants x K-slices, several passes when n > 32.  Fixed-order
+// reductions; partials in the layout k_close_reduce consumes.  Descriptor: ModeCloseDesc with a == b, R == 1
+// (rows = L contiguous, a_sb = column stride).  grid: (max nsplit, items); block 256; dynamic shared memory 8 * 512 doubles.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) k_gram_dmma(const ModeCloseDesc* __restrict__ descs) {
+  const ModeCloseDesc d = descs[blockIdx.y];
+  if ((int)blockIdx.x >= d.nsplit) return;
+  extern __shared__ double red[];
+  constexpr int NSET = 3;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = lane >> 2, q = lane & 3, pp = r & 1;
+  const int n = d.n;
+  const int qm = (n + 15) / 16, nquad = qm * qm;
+  const int qpp = nquad < 8 ? (nquad == 1 ? 1 : (nquad <= 4 ? 4 : 8)) : 8;      // quadrants per pass: 1, 4 or 8
+  const int npass = (nquad + qpp - 1) / qpp;
+  const int nslice = 8 / qpp;
+  const long long r_begin = (long long)blockIdx.x * d.rows_per_split;
+  const long long r_end = min((long long)d.L, r_begin + d.rows_per_split);
+  const long long g_begin = r_begin / 4, g_end = (r_end + 3) / 4;               // rows_per_split is a multiple of 4
+  cplx* out = d.partial + (size_t)blockIdx.x * n * n;
+  for (int pass = 0; pass < npass; ++pass) {
+    const int quad = pass * qpp + warp % qpp, slice = warp / qpp;
+    const bool live = quad < nquad;
+    const int mq = quad % qm, nq = quad / qm;
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    if (live) {
+      // columns beyond n read column 0 and are masked by a zero weight afterwards (their rows of G are never stored)
+      const int sb = (int)d.a_sb;                                  // the matrix has fewer than 2^31 elements
+      const int acol0 = min(16 * mq + r, n - 1) * sb + q, acol1 = min(16 * mq + 8 + r, n - 1) * sb + q;
+      const int bcol0 = min(16 * nq + (r >> 1), n - 1) * sb + q;
+      const int bstep = 4 * sb;
+      const bool b1 = 16 * nq + 4 + (r >> 1) < n, b2 = 16 * nq + 8 + (r >> 1) < n, b3 = 16 * nq + 12 + (r >> 1) < n;
+      cplx a[NSET][2], b[NSET][4];
+      auto load = [&](int set, long long g) {
+        const long long row = 4 * g;
+        if (g < g_end && row + q < r_end) {
+          const cplx* p = d.a + row;
+          a[set][0] = p[acol0]; a[set][1] = p[acol1];
+          b[set][0] = p[bcol0]; b[set][1] = p[b1 ? bcol0 + bstep : bcol0]; b[set][2] = p[b2 ? bcol0 + 2 * bstep : bcol0]; b[set][3] = p[b3 ? bcol0 + 3 * bstep : bcol0];
+        } else {
+          a[set][0] = a[set][1] = cmake(0, 0);
+          b[set][0] = b[set][1] = b[set][2] = b[set][3] = cmake(0, 0);
+        }
+      };
+      long long g = g_begin + slice;
+#pragma unroll
+      for (int u = 0; u < NSET; ++u) load(u, g + (long long)nslice * u);
+      for (; g < g_end; g += (long long)nslice * NSET) {
+#pragma unroll
+        for (int u = 0; u < NSET; ++u) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) { const cplx t = b[u][nt]; b[u][nt] = pp ? cmake(-t.y, t.x) : t; }
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[u][mt].x, b[u][nt].x);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[u][mt].y, b[u][nt].y);
+          load(u, g + (long long)nslice * (u + NSET));
+        }
+      }
+    }
+    // this warp's 16 x 32 real block -> shared memory, then a fixed-order sum over the K-slices
+    double* mine = red + (size_t)warp * 512;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int row = 8 * mt + r, col = 8 * nt + 2 * q;
+        mine[row + 16 * col] = acc[mt][nt][0];
+        mine[row + 16 * (col + 1)] = acc[mt][nt][1];
+      }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+      const int bb = idx % n, bp = idx / n;
+      const int qd = (bb >> 4) + qm * (bp >> 4);
+      if (qd / qpp != pass) continue;
+      const int lb = bb & 15, lbp = bp & 15;
+      double re = 0, im = 0;
+      for (int sl = 0; sl < nslice; ++sl) {
+        const double* P = red + (size_t)(qd % qpp + qpp * sl) * 512;
+        re += P[lb + 16 * (2 * lbp)];
+        im += P[lb + 16 * (2 * lbp + 1)];
+      }
+      out[idx] = cmake(re, im);
     }
     __syncthreads();
   }

@@ -22,10 +22,18 @@ __device__ __forceinline__ void rr_pair(int N, int s, int i, int& p, int& q) {
 // One-sided Jacobi on the columns of W (m x n, leading dim ldw); the same rotations are accumulated into the
 // rows of V (nv x n, leading dim ldv) unless V is null.  On exit the columns of W are mutually orthogonal.
 // Every thread of the CTA must call.  Returns the number of sweeps used, or -1 if not converged.
-// RPL = rows per lane held in registers between the inner products and the rotation (m, nv <= 32 * RPL).
-template <int RPL>
+// A column pair belongs to a HALF-warp (16 lanes x RPH rows per lane, m, nv <= 16 * RPH): one warp instruction serves two
+// pairs, so the butterfly reductions (4 rounds instead of 5) and the rotation parameters cost half as many shuffle and
+// FP64 issue slots per pair, and a CTA of 16 warps covers the 32 pairs of a 64-column step in one pass.
+__device__ __forceinline__ double half_sum(double v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int RPH>
 __device__ int jacobi_columns_t(cplx* W, int ldw, int m, cplx* V, int ldv, int nv, int n) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int hw = lane >> 4, sl = lane & 15;
   const int N = n + (n & 1);
   if (n < 2) return 0;
   // rotate whenever |<a_p,a_q>| > sqrt(m) eps |a_p||a_q| (LAPACK zgesvj's threshold), but call the iteration
@@ -42,25 +50,29 @@ __device__ int jacobi_columns_t(cplx* W, int ldw, int m, cplx* V, int ldv, int n
   for (int sweep = 0; sweep < TNQS_JACOBI_MAX_SWEEPS; ++sweep) {
     int rotated = 0;
     for (int s = 0; s < N - 1; ++s) {
-      for (int i = warp; i < N / 2; i += nwarps) {
-        int p, q;
-        rr_pair(N, s, i, p, q);
-        if (q >= n) continue;
+      for (int i0 = 2 * warp; i0 < N / 2; i0 += 2 * nwarps) {
+        const int i = i0 + hw;
+        int p = 0, q = 0;
+        bool act = i < N / 2;
+        if (act) { rr_pair(N, s, i, p, q); act = q < n; }
         cplx* wp = W + (size_t)p * ldw;
         cplx* wq = W + (size_t)q * ldw;
-        cplx a[RPL], b[RPL];
+        constexpr bool KEEP = RPH <= 4;                      // columns stay in registers between the inner products and the rotation
+        cplx a[KEEP ? RPH : 1], b[KEEP ? RPH : 1];
         double al = 0, be = 0, gr = 0, gi = 0;
 #pragma unroll
-        for (int t = 0; t < RPL; ++t) {
-          const int r = lane + 32 * t;
-          a[t] = r < m ? wp[r] : cmake(0, 0); b[t] = r < m ? wq[r] : cmake(0, 0);
-          al += cabs2(a[t]); be += cabs2(b[t]);
-          gr += a[t].x * b[t].x + a[t].y * b[t].y;         // conj(a) * b
-          gi += a[t].x * b[t].y - a[t].y * b[t].x;
+        for (int t = 0; t < RPH; ++t) {
+          const int r = sl + 16 * t;
+          const bool ok = act && r < m;
+          const cplx x = ok ? wp[r] : cmake(0, 0), y = ok ? wq[r] : cmake(0, 0);
+          if (KEEP) { a[t] = x; b[t] = y; }
+          al += cabs2(x); be += cabs2(y);
+          gr += x.x * y.x + x.y * y.y;         // conj(a) * b
+          gi += x.x * y.y - x.y * y.x;
         }
-        al = warp_sum(al); be = warp_sum(be); gr = warp_sum(gr); gi = warp_sum(gi);
-        double g2 = gr * gr + gi * gi;
-        if (!(g2 > tol2 * al * be) || g2 == 0.0 || al <= tiny2 || be <= tiny2) continue;
+        al = half_sum(al); be = half_sum(be); gr = half_sum(gr); gi = half_sum(gi);
+        const double g2 = gr * gr + gi * gi;
+        if (!act || !(g2 > tol2 * al * be) || g2 == 0.0 || al <= tiny2 || be <= tiny2) continue;    // uniform per half-warp; no shuffles below
         if (g2 > conv2 * al * be) rotated = 1;
         // rotation parameters with reciprocal-square-root / reciprocal intrinsics: the chain of FP64 sqrt and divide
         // subroutines (about 1000 dependent cycles) was the critical path of a Jacobi step
@@ -71,10 +83,10 @@ __device__ int jacobi_columns_t(cplx* W, int ldw, int m, cplx* V, int ldv, int n
         const double t = copysign(__drcp_rn(fabs(zeta) + z2 * rsqrt(z2)), zeta);
         const double c = rsqrt(fma(t, t, 1.0)), sn = c * t;
 #pragma unroll
-        for (int u = 0; u < RPL; ++u) {
-          const int r = lane + 32 * u;
+        for (int u = 0; u < RPH; ++u) {
+          const int r = sl + 16 * u;
           if (r < m) {
-            cplx x = a[u], y = cmul(ph, b[u]);
+            cplx x = KEEP ? a[u] : wp[r], y = cmul(ph, KEEP ? b[u] : wq[r]);
             wp[r] = cmake(c * x.x - sn * y.x, c * x.y - sn * y.y);
             wq[r] = cmake(sn * x.x + c * y.x, sn * x.y + c * y.y);
           }
@@ -83,8 +95,8 @@ __device__ int jacobi_columns_t(cplx* W, int ldw, int m, cplx* V, int ldv, int n
           cplx* vp = V + (size_t)p * ldv;
           cplx* vq = V + (size_t)q * ldv;
 #pragma unroll
-          for (int u = 0; u < RPL; ++u) {
-            const int r = lane + 32 * u;
+          for (int u = 0; u < RPH; ++u) {
+            const int r = sl + 16 * u;
             if (r < nv) {
               cplx x = vp[r], y = cmul(ph, vq[r]);
               vp[r] = cmake(c * x.x - sn * y.x, c * x.y - sn * y.y);
@@ -102,9 +114,10 @@ __device__ int jacobi_columns_t(cplx* W, int ldw, int m, cplx* V, int ldv, int n
 
 __device__ int jacobi_columns(cplx* W, int ldw, int m, cplx* V, int ldv, int nv, int n) {
   const int mx = m > nv ? m : nv;
-  if (mx <= 32) return jacobi_columns_t<1>(W, ldw, m, V, ldv, nv, n);
-  if (mx <= 64) return jacobi_columns_t<2>(W, ldw, m, V, ldv, nv, n);
-  return jacobi_columns_t<4>(W, ldw, m, V, ldv, nv, n);          // m, nv <= 128 (d * chi <= 64 in the gate path)
+  if (mx <= 16) return jacobi_columns_t<1>(W, ldw, m, V, ldv, nv, n);
+  if (mx <= 32) return jacobi_columns_t<2>(W, ldw, m, V, ldv, nv, n);
+  if (mx <= 64) return jacobi_columns_t<4>(W, ldw, m, V, ldv, nv, n);
+  return jacobi_columns_t<8>(W, ldw, m, V, ldv, nv, n);          // m, nv <= 128 (d * chi <= 64 in the gate path)
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -263,7 +263,7 @@ static void bp_cache_drop(tnqs_ctx* c) {
 }
 static int bp_level_split_cap() {
   static int cap = 0;
-  if (!cap) { const char* e = getenv("TNQS_BP_SPLIT"); cap = e ? std::max(1, atoi(e)) : 16; }
+  if (!cap) { const char* e = getenv("TNQS_BP_SPLIT"); cap = e ? std::max(1, atoi(e)) : 8; }
   return cap;
 }
 static bool graphs_disabled() {
@@ -541,6 +541,8 @@ struct GateBatch {
   struct SiteJob {
     int v, e, jb, d, chib; long long Po; int nc, q; std::vector<int> outer;   // outer: bond leg indices ascending
     cplx* A; cplx* Q; cplx* Rbuf; std::vector<cplx*> root, invroot;             // Q: where the thin Q factor lives
+    cplx* colfix = nullptr;     // CholeskyQR2: Q holds Q1 = A R1^-1 and the true factor is Q1 * colfix (colfix = R2^-1, nc x nc); the column
+                                // operation is folded into T' = Q R' (it commutes with the outer-leg absorptions on the rows)
     bool remote;
   };
   tnqs_ctx* c; int n = 0, NJ = 0, cap = 1; tnqs_apply_opts o;
@@ -551,6 +553,16 @@ struct GateBatch {
   std::vector<int> cut;                 // gate indices that have a remote vertex, in batch order
   cplx* xsend = nullptr; long long xslot = 0;
   void absorb_outer(bool inverse);
+  std::vector<char> from_site;          // forward absorption reads the canonical site tensor directly (no matricise pass)
+  bool slab_ok(int j) const {           // fused slab kernel: 2 or 3 outer legs, all of the same dimension N in {8, 16}
+    const SiteJob& J = jobs[j];
+    const int F = (int)J.outer.size();
+    if (dmma_disabled() || (F != 2 && F != 3)) return false;
+    const int N = c->chi[c->inc[J.v][J.outer[0]]];
+    if (N != 8 && N != 16) return false;
+    for (int l : J.outer) if (c->chi[c->inc[J.v][l]] != N) return false;
+    return true;
+  }
   void stage1(int n_, const int32_t* es_, const int32_t* flips, const double* gates, const tnqs_apply_opts& o_, const int32_t* remote);
   void stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, double* svals_out);
 };
@@ -565,14 +577,18 @@ void GateBatch::absorb_outer(bool inverse) {   // forward: on A (psi~); inverse:
     SiteJob& J = jobs[j];
     const int F = (int)J.outer.size();
     int N = F ? c->chi[c->inc[J.v][J.outer[0]]] : 0;
-    bool ok = !dmma_disabled() && (F == 2 || F == 3) && (N == 8 || N == 16) && ncols[j] >= 1;
-    for (int l : J.outer) ok = ok && c->chi[c->inc[J.v][l]] == N;
+    const bool ok = slab_ok(j) && ncols[j] >= 1;
     if (!ok) { if (F) generic.push_back(j); continue; }
     cplx* buf = inverse ? J.Q : J.A;
     SlabDesc d; d.t = buf; d.x = buf; d.F = F;
     long long st = 1;
     for (int i = 0; i < 3; ++i) { d.g[i] = i < F ? st : 0; d.m[i] = i < F ? (inverse ? J.invroot[i] : J.root[i]) : nullptr; st *= N; }
     d.gs = J.Po; d.gw = 2 * J.Po; d.nslabs = ncols[j]; d.flags = inverse ? 3 : 0;
+    if (!inverse && from_site[j]) {     // column (s, b) of the matrix = slab T[s, :, :, :, b] of the canonical tensor: matricise on the fly
+      d.t = c->site[J.v];
+      for (int i = 0; i < F; ++i) d.g[i] = pd[j].ostride[i];
+      d.gs = 1; d.gw = pd[j].bstride;
+    }
     slab[N == 16].push_back(d); maxcols[N == 16] = std::max(maxcols[N == 16], ncols[j]);
   }
   for (int w = 0; w < 2; ++w) {
@@ -671,14 +687,17 @@ void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const d
     p.Po = J.Po; p.to_matrix = 1; p.norm2 = nullptr;
     maxtot = std::max(maxtot, (long long)c->site_n[J.v]);
   }
+  from_site.assign(NJ, 0);
   {
-    std::vector<PermDesc> lp; for (int j : LJ) lp.push_back(pd[j]);
+    // sites whose outer legs go through the fused slab kernel are matricised by that kernel (it reads the canonical layout)
+    std::vector<PermDesc> lp;
+    for (int j : LJ) { if (jobs[j].d == 2 && slab_ok(j)) from_site[j] = 1; else lp.push_back(pd[j]); }
     PermDesc* dpd = c->upload(lp);
     long long maxPo = 1; for (int j : LJ) maxPo = std::max(maxPo, jobs[j].Po);
     unsigned gx = (unsigned)((maxPo + 255) / 256); (void)maxtot;
     if (!lp.empty()) LAUNCH(c, TNQS_KC_PERMUTE, k_permute, dim3(gx, (unsigned)lp.size()), 256, 0, dpd);
   }
-  for (int j : LJ) dbg_norm(c, "matricised", j, jobs[j].A, (size_t)c->site_n[jobs[j].v]);
+  for (int j : LJ) if (!from_site[j]) dbg_norm(c, "matricised", j, jobs[j].A, (size_t)c->site_n[jobs[j].v]);
   // ---- 3. absorb sqrt(M_k) on the outer legs, in place in the matrix layout (simple_update.jl:35-36) ----
   ncols.assign(NJ, 0);
   for (int j = 0; j < NJ; ++j) ncols[j] = jobs[j].nc;
@@ -787,17 +806,20 @@ void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const d
           maxnn = std::max(maxnn, (size_t)J.nc * J.nc); maxn = std::max(maxn, J.nc);
         }
         ModeCloseDesc* dmc = c->upload(mc);
-        LAUNCH(c, TNQS_KC_QR, k_close_leg_dmma, dim3(nsplit, nj), 256, 8 * 1024 * sizeof(double), dmc);
+        LAUNCH(c, TNQS_KC_QR, k_gram_dmma, dim3(nsplit, nj), 256, 8 * 512 * sizeof(double), dmc);
         CloseReduceDesc* drd = c->upload(rd);
         LAUNCH(c, TNQS_KC_QR, k_close_reduce, nj, 256, maxnn * sizeof(cplx), drd);
         CholDesc* dcd = c->upload(cd);
         LAUNCH(c, TNQS_KC_QR, k_chol_inv, nj, 64, 2 * (size_t)maxn * maxn * sizeof(cplx), dcd);
-        launch_mode_apply(c, TNQS_KC_QR, ma);
+        if (pass == 0) launch_mode_apply(c, TNQS_KC_QR, ma);        // Q1 = A R1^-1; the second factor R2^-1 stays pending (colfix)
       }
       std::vector<int> flags(nj);
       CU(cudaMemcpyAsync(flags.data(), d_flag, nj * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       c->sync();
-      for (int i = 0; i < nj; ++i) { if (flags[i]) house_list.push_back(chol_list[i]); else jobs[chol_list[i]].Q = Qb[i]; }
+      for (int i = 0; i < nj; ++i) {
+        if (flags[i]) house_list.push_back(chol_list[i]);
+        else { jobs[chol_list[i]].Q = Qb[i]; jobs[chol_list[i]].colfix = Rinv[i]; }
+      }
     }
     householder_qr(house_list);
   }
@@ -892,12 +914,24 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
   // ---- 8. T' = Q R' (simple_update.jl:57), normalise, back to the canonical layout ----
   std::vector<cplx*> Tm(NJ), newsite(NJ);
   {
+    // pending column factors of CholeskyQR2: R'' = R2^-1 R' (one small product per site instead of a pass over Q)
+    std::vector<cplx*> rfin(NJ, nullptr);
+    std::vector<SmallMatmulDesc> sm;
+    for (int j : LJ) {
+      SiteJob& J = jobs[j]; int r = ranks[j / 2];
+      rfin[j] = (j & 1) ? r2n[j / 2] : r1n[j / 2];
+      if (!J.colfix) continue;
+      SmallMatmulDesc x; x.a = J.colfix; x.b = rfin[j]; x.m = J.nc; x.k = J.q; x.n = J.d * r; x.lda = J.nc; x.ldb = J.q; x.ldc = J.nc; x.transA = 0;
+      x.c = c->talloc<cplx>((size_t)J.nc * J.d * r);
+      rfin[j] = x.c; sm.push_back(x);
+    }
+    if (!sm.empty()) { SmallMatmulDesc* dsm = c->upload(sm); LAUNCH(c, TNQS_KC_MISC, k_small_matmul, (unsigned)sm.size(), 256, 0, dsm); }
     std::vector<ModeApplyDesc> ma; long long maxtiles = 1; int maxcol = 1;
     for (int j : LJ) {
       SiteJob& J = jobs[j]; int r = ranks[j / 2];
       Tm[j] = c->talloc<cplx>((size_t)J.Po * J.d * r);
       ma.emplace_back(); ModeApplyDesc& d = ma.back();
-      d.in = J.Q; d.out = Tm[j]; d.m = (j & 1) ? r2n[j / 2] : r1n[j / 2];
+      d.in = J.Q; d.out = Tm[j]; d.m = rfin[j];
       d.L = (int)J.Po; d.n = J.q; d.np = J.d * r; d.R = 1; d.in_sb = J.Po; d.in_sr = 0; d.out_sb = J.Po; d.out_sr = 0;
       d.ldm = J.q; d.flags = 0;
       maxtiles = std::max(maxtiles, (J.Po + MA_BM - 1) / MA_BM); maxcol = std::max(maxcol, (d.np + MA_BN - 1) / MA_BN);
