@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes as C
+import gc
 import json
 import os
 import subprocess
@@ -223,22 +224,32 @@ def run_distributed(args, torch, dist, rank, world, local):
     batches = [P.class_gates_local(gg, lg, owner, rank, grp) for grp in groups]
     stats = {"bp_s": 0.0, "gate_s": 0.0, "other_s": 0.0, "msg": 0, "gates2": 0, "sweeps": 0, "halo": 0}
 
+    estream = torch.cuda.ExternalStream(lib.load().tnqs_stream(psi._h.ptr))
+
+    def dev_timed(fn):
+        """Device time of fn: CUDA events on the engine's stream and on torch's current stream (NCCL), after a full
+        synchronisation; the later end event counts."""
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(estream)
+        r = fn()
+        e1.record(estream); e2.record(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        return r, 1e-3 * max(e0.elapsed_time(e1), e0.elapsed_time(e2))
+
     def bp():
-        torch.cuda.synchronize(); t0 = time.perf_counter()
         info = {}
-        P.update_distributed(lg, comp, dist, slot, torch, dev, maxiter=25, tolerance=1e-8, info=info)
-        torch.cuda.synchronize(); stats["bp_s"] += time.perf_counter() - t0
+        _, dt = dev_timed(lambda: P.update_distributed(lg, comp, dist, slot, torch, dev, maxiter=25, tolerance=1e-8, info=info))
+        stats["bp_s"] += dt
         stats["msg"] += info["iters"] * info["messages_per_sweep"]; stats["sweeps"] += info["iters"]; stats["halo"] += info["halo_bytes"]
 
     def step():
-        t0 = time.perf_counter()
-        E.apply_1site_batch(bpc, owned_v, [rx] * len(owned_v)); E.apply_1site_batch(bpc, owned_v, [rz] * len(owned_v))
-        stats["other_s"] += time.perf_counter() - t0
+        _, dt = dev_timed(lambda: (E.apply_1site_batch(bpc, owned_v, [rx] * len(owned_v)), E.apply_1site_batch(bpc, owned_v, [rz] * len(owned_v))))
+        stats["other_s"] += dt
         for grp, batch in zip(groups, batches):
             bp()
-            torch.cuda.synchronize(); t0 = time.perf_counter()
-            ranks, errs = P.apply_class_distributed(E, bpc, gg, lg, owner, rank, grp, rzz, kw, dist, torch, dev, batch=batch)
-            torch.cuda.synchronize(); stats["gate_s"] += time.perf_counter() - t0
+            _, dt = dev_timed(lambda: P.apply_class_distributed(E, bpc, gg, lg, owner, rank, grp, rzz, kw, dist, torch, dev, batch=batch))
+            stats["gate_s"] += dt
             es, rm, _ = batch
             stats["gates2"] += int(np.sum(rm == 0)) + 0.5 * int(np.sum(rm != 0))          # a cut gate counts half on each side
         bp()
@@ -249,6 +260,7 @@ def run_distributed(args, torch, dist, rank, world, local):
     for k in stats:
         stats[k] = 0
     launches0 = psi.kernel_launches()
+    gc.collect(); gc.freeze(); gc.disable()                       # no collector pauses inside the timed region (as timeit does)
     dist.barrier(); torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -260,6 +272,7 @@ def run_distributed(args, torch, dist, rank, world, local):
     ev1.record(); torch.cuda.synchronize()
     dist.barrier()
     total_ms = ev0.elapsed_time(ev1)
+    gc.enable()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([total_ms, stats["bp_s"], stats["gate_s"], stats["other_s"], float(stats["msg"]), float(stats["gates2"]), float(stats["sweeps"]),
                       float(stats["halo"]), float(psi.kernel_launches() - launches0)], dtype=torch.float64, device=dev)
@@ -288,18 +301,17 @@ def run_distributed(args, torch, dist, rank, world, local):
     sizes = [int(L.tnqs_site_size(h, v)) for v in owned_v]
     host = [torch.empty(2 * n, dtype=torch.float64).pin_memory() for n in sizes]
     ptrs = [C.cast(t_.data_ptr(), C.POINTER(C.c_double)) for t_ in host]
-    for v, p_, n in zip(owned_v, ptrs, sizes):
-        L.tnqs_get_site(h, v, p_, n)
+    vs_arr = lib.i32(owned_v); ns_arr = np.asarray(sizes, dtype=np.int64)
+    parr = (C.POINTER(C.c_double) * len(ptrs))(*ptrs)
+    lib.check(h, L.tnqs_get_sites(h, len(ptrs), lib.ptr_i32(vs_arr), parr, lib.ptr_i64(ns_arr)))
     e2e_t, e2e_msg = 0.0, 0
     nrep = max(1, min(args.steps, 2))
     for rep in range(nrep + 1):                                   # first pass is a warm-up
         dist.barrier(); torch.cuda.synchronize()
         m0 = stats["msg"]; t0 = time.perf_counter()
-        for v, p_, n in zip(owned_v, ptrs, sizes):
-            lib.check(h, L.tnqs_set_site(h, v, p_, n))
+        lib.check(h, L.tnqs_set_sites(h, len(ptrs), lib.ptr_i32(vs_arr), parr, lib.ptr_i64(ns_arr)))
         step()
-        for v, p_, n in zip(owned_v, ptrs, sizes):
-            lib.check(h, L.tnqs_get_site(h, v, p_, n))
+        lib.check(h, L.tnqs_get_sites(h, len(ptrs), lib.ptr_i32(vs_arr), parr, lib.ptr_i64(ns_arr)))
         torch.cuda.synchronize(); dist.barrier()
         if rep > 0:
             e2e_t += time.perf_counter() - t0; e2e_msg += stats["msg"] - m0
@@ -308,7 +320,7 @@ def run_distributed(args, torch, dist, rank, world, local):
     tsm = te.clone(); dist.all_reduce(tsm, op=dist.ReduceOp.SUM)
     out["e2e"] = {"value": tsm[1].item() / tmx[0].item(), "unit": "messages/s", "h2d_bytes_per_step": int(tsm[2].item()),
                   "d2h_bytes_per_step": int(tsm[2].item()), "ms_per_step": 1e3 * tmx[0].item() / nrep,
-                  "note": "every owned site tensor H2D from pinned host memory, the distributed layer, every owned site tensor D2H; host wall clock, max over ranks"}
+                  "note": "every owned site tensor H2D from pinned host memory (tnqs_set_sites), the distributed layer, every owned site tensor D2H (tnqs_get_sites); host wall clock around the public calls, max over ranks"}
     return out
 
 
@@ -337,6 +349,7 @@ def run_engine(args):
         st.step()
     st.reset()
     launches0 = psi.kernel_launches()
+    gc.collect(); gc.freeze(); gc.disable()                       # no collector pauses inside the timed region (as timeit does)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -353,6 +366,7 @@ def run_engine(args):
     if world > 1:
         dist.barrier()
     total_ms = ev0.elapsed_time(ev1)
+    gc.enable()
     clocks = sampler.stop() if rank == 0 else None
     launches = psi.kernel_launches() - launches0
     stats = torch.tensor([total_ms, st.bp_ms, st.gate_ms, st.other_ms, float(st.msg_updates), float(st.gates2), float(st.bp_sweeps)], dtype=torch.float64, device="cuda")
@@ -378,8 +392,13 @@ def run_engine(args):
     sweep_flops = float(fm[np.asarray(seq)].sum())
     zsum = sum(g.degree(g.dsrc(int(k))) for k in seq)
     apply_flops = sweep_flops - 8.0 * 2 * sum(chi ** g.degree(g.dsrc(int(k))) * chi for k in seq)   # sweeps minus the closings
-    apply_tf = 2 * apply_flops / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else None
-    close_tf = 2 * (sweep_flops - apply_flops) / (ms[1] * 1e-3) / 1e12 if ms[1] > 0 else None
+    one_launch_per_sweep = ln[0] == 2 and ln[1] == 0            # k_bp_sweep: absorptions + closings + epilogues of a whole sweep in one launch
+    if one_launch_per_sweep:
+        apply_tf = 2 * sweep_flops / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else None
+        close_tf = None
+    else:
+        apply_tf = 2 * apply_flops / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else None
+        close_tf = 2 * (sweep_flops - apply_flops) / (ms[1] * 1e-3) / 1e12 if ms[1] > 0 else None
     jac_seq = np.arange(2 * g.ne, dtype=np.int32)
     E.update(bpc, edge_sequence=jac_seq, inplace=True, maxiter=2, mode="jacobi")
     j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -405,7 +424,8 @@ def run_engine(args):
                "jacobi_mode_messages_per_s": jacobi_value, "jacobi_mode_frac_of_fp64_peak": jacobi_value * sweep_flops / len(seq) / 1e12 / pk["fp64_tflops_sustained"],
                "frac_of_fp64_peak": bp_tf / pk["fp64_tflops_sustained"]},
         "phase_ms_per_step": {"bp": bp_ms / args.steps, "two_site_gates": gate_ms / args.steps, "one_site_and_expect": other_ms / args.steps},
-        "roofline": {"bound": "tensor", "kernel": "k_absorb_slab<16> (fused BP leg absorption, DMMA)", "achieved": apply_tf, "peak": pk["fp64_tflops_sustained"],
+        "roofline": {"bound": "tensor", "kernel": "k_bp_sweep<16> (one persistent launch per BP sweep: DMMA leg absorptions, closings and message epilogues of all 3968 updates)" if one_launch_per_sweep
+                     else "k_absorb_slab<16> (fused BP leg absorption, DMMA)", "achieved": apply_tf, "peak": pk["fp64_tflops_sustained"],
                      "unit": "TFLOP/s", "frac": (apply_tf / pk["fp64_tflops_sustained"]) if apply_tf else None,
                      "traffic": {"dram_bytes_per_launch": 206.0e6, "algorithmic_bytes_per_launch": 260.0e6, "launch": "62 messages x 32 slabs (ncu --set full, profiles/r01_final_dmma_ncu_full_raw.csv)"},
                      "peak_source": pk["source"], "launches_profiled": int(ln[0]), "avg_launch_ms": ms[0] / max(1, ln[0]),
@@ -431,8 +451,9 @@ def run_e2e(ctx, steps):
     sizes = [int(L.tnqs_site_size(h, v)) for v in range(g.nv)]
     host = [torch.empty(2 * n, dtype=torch.float64).pin_memory() for n in sizes]
     ptrs = [C.cast(t.data_ptr(), C.POINTER(C.c_double)) for t in host]
-    for v in range(g.nv):
-        L.tnqs_get_site(h, v, ptrs[v], sizes[v])
+    vs_arr = lib.i32(np.arange(g.nv)); ns_arr = np.asarray(sizes, dtype=np.int64)
+    parr = (C.POINTER(C.c_double) * g.nv)(*ptrs)
+    lib.check(h, L.tnqs_get_sites(h, g.nv, lib.ptr_i32(vs_arr), parr, lib.ptr_i64(ns_arr)))
     layer = [(rx, [v]) for v in range(g.nv)] + [(rz, [v]) for v in range(g.nv)]
     for grp in groups:
         layer += [(rzz, [int(g.esrc[e]), int(g.edst[e])]) for e in grp]
@@ -441,24 +462,32 @@ def run_e2e(ctx, steps):
     d2h = sum(16 * n for n in sizes) + 8 * len(layer) + 16 * 4
     t_tot = 0.0
     upd = 0
+    parts = np.zeros(4)
+    gc.collect(); gc.freeze(); gc.disable()
     for s in range(steps + 1):                       # first pass is a warm-up
         torch.cuda.synchronize()
         u0 = L.tnqs_bp_message_updates_total(h)
         t0 = time.perf_counter()
-        for v in range(g.nv):
-            lib.check(h, L.tnqs_set_site(h, v, ptrs[v], sizes[v]))
+        lib.check(h, L.tnqs_set_sites(h, g.nv, lib.ptr_i32(vs_arr), parr, lib.ptr_i64(ns_arr)))
+        t1 = time.perf_counter()
         info = {}
         _, errs = E.apply_gates(layer, bpc, apply_kwargs=kw, inplace=True, info=info)
+        t2 = time.perf_counter()
         z = E.expect(bpc, ("Z", [st.obs_v]))
-        for v in range(g.nv):
-            lib.check(h, L.tnqs_get_site(h, v, ptrs[v], sizes[v]))
+        t3 = time.perf_counter()
+        lib.check(h, L.tnqs_get_sites(h, g.nv, lib.ptr_i32(vs_arr), parr, lib.ptr_i64(ns_arr)))
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        t4 = time.perf_counter()
+        dt = t4 - t0
         if s > 0:
             t_tot += dt
             upd += L.tnqs_bp_message_updates_total(h) - u0
+            parts += [t1 - t0, t2 - t1, t3 - t2, t4 - t3]
+    gc.enable()
     return {"value": upd / t_tot, "message_updates_per_step": upd / steps, "unit": "messages/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": 1e3 * t_tot / steps, "note": "host wall clock around set_site x V + apply_gates + expect + get_site x V"}
+            "ms_per_step": 1e3 * t_tot / steps,
+            "parts_ms": {"h2d_set_sites": 1e3 * parts[0] / steps, "apply_gates": 1e3 * parts[1] / steps, "expect": 1e3 * parts[2] / steps, "d2h_get_sites": 1e3 * parts[3] / steps},
+            "note": "host wall clock around tnqs_set_sites (all V sites from pinned host memory) + apply_gates + expect + tnqs_get_sites (all V sites back)"}
 
 
 def cpu_sample(nx, ny, chi, n_msgs, n_gates, seed=1):

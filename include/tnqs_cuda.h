@@ -94,6 +94,11 @@ int64_t tnqs_site_size(const tnqs_ctx* ctx, int32_t v);      /* number of Comple
  * `n` = element count of the host buffer, must equal tnqs_site_size. */
 int32_t tnqs_set_site(tnqs_ctx* ctx, int32_t v, const double* data, int64_t n);
 int32_t tnqs_get_site(const tnqs_ctx* ctx, int32_t v, double* data, int64_t n);
+/* The same for a list of sites in one call (a whole state): data[i] / n[i] belong to vertex v[i].  Every copy is queued on
+ * the handle's stream and the call synchronises once, so pinned host buffers move at PCIe speed instead of paying one
+ * round trip per site (what a Julia caller does for `ψ[v] = T` over all v, tensornetworkstate.jl:124-144). */
+int32_t tnqs_set_sites(tnqs_ctx* ctx, int32_t count, const int32_t* v, const double* const* data, const int64_t* n);
+int32_t tnqs_get_sites(const tnqs_ctx* ctx, int32_t count, const int32_t* v, double* const* data, const int64_t* n);
 /* Fill every site with N(0,1)+iN(0,1) from the counter-based generator (stream = vertex id, element =
  * column-major offset); random_tensornetworkstate, src/TensorNetworks/tensornetworkstate.jl:82-92. */
 int32_t tnqs_fill_random(tnqs_ctx* ctx, uint64_t seed);

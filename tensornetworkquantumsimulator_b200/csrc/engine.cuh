@@ -105,8 +105,24 @@ struct tnqs_ctx {
   }
   void release_temps() { for (void* p : temp) dfree(p); temp.clear(); arena_chunk = 0; arena_off = 0; }
   void arena_destroy() { for (auto& ch : arena) dfree(ch.base); arena.clear(); }
+  // TNQS_DEBUG_STALL=<ms>: report host-side API calls (uploads, launches) that block longer than the threshold
+  static double stall_ms() {
+    static double t = -2;
+    if (t < -1) { const char* e = getenv("TNQS_DEBUG_STALL"); t = e ? atof(e) : -1; }
+    return t;
+  }
+  struct StallProbe {
+    const char* what; std::chrono::steady_clock::time_point t0; bool on;
+    explicit StallProbe(const char* w) : what(w), on(stall_ms() >= 0) { if (on) t0 = std::chrono::steady_clock::now(); }
+    ~StallProbe() {
+      if (!on) return;
+      double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (ms > stall_ms()) fprintf(stderr, "[tnqs stall] %s blocked the host for %.2f ms\n", what, ms);
+    }
+  };
   template <typename T> T* upload(const std::vector<T>& v) {
     T* p = talloc<T>(std::max<size_t>(v.size(), 1));
+    StallProbe sp("upload");
     if (!v.empty()) CU(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
     return p;
   }
@@ -146,7 +162,7 @@ struct tnqs_ctx {
   }
 };
 
-#define LAUNCH(ctx, kc, kernel, grid, block, smem, ...) do { (ctx)->pre_launch(kc); \
+#define LAUNCH(ctx, kc, kernel, grid, block, smem, ...) do { tnqs_ctx::StallProbe _sp("launch " #kernel); (ctx)->pre_launch(kc); \
   kernel<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__); (ctx)->post_launch(); } while (0)
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -208,7 +224,11 @@ struct Plan {
   Gate1Desc* d_gate1 = nullptr; ModeApplyDesc* d_apply = nullptr; ModeCloseDesc* d_close = nullptr;
   CloseReduceDesc* d_reduce = nullptr; int* d_commit = nullptr;
   SlabDesc* d_slab = nullptr; CloseDmmaDesc* d_dclose = nullptr; int* d_ticket = nullptr;
-  int2* d_items = nullptr; int* d_qctr = nullptr; int* d_slab_done = nullptr;       // k_bp_level queue, its counters, per-chain slab counters
+  int2* d_items = nullptr; int* d_qctr = nullptr; int* d_slab_done = nullptr;       // k_bp_level / k_bp_sweep queue, its counters, per-chain slab counters
+  // whole-sweep persistent launch (k_bp_sweep): every chain of every level in one data-flow queue
+  bool sweep = false; int sweepN = 0, sweep_items = 0; dim3 sweep_grid; size_t sweep_smem = 0;
+  SweepChain* d_chains = nullptr; int* d_chain_done = nullptr; size_t nchains = 0;
+  int sweep_commit = 0;              // staged (JACOBI) sweeps end with a commit pass over this many messages
   // storage: a rebuilt plan of the same shape reuses the buffers of its predecessor, so device addresses (and a CUDA graph
   // captured over them) stay valid when only the site pointers inside the descriptors changed
   cplx* scratch = nullptr; size_t scratch_elems = 0; cplx* partial = nullptr; size_t partial_elems = 0;
@@ -322,6 +342,13 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
     const bool fuse = !fuse_disabled() && subsets[L].size() == 1;
     bool level_staged = subsets[L].size() > 1;
     if (fuse && !strict_levels) for (const Chain& ch : chains) if (fast_path_N(c, ch) && ch.commit_k >= 0) level_staged = true;
+    if (!strict_levels) {
+      // the epilogues of the fast-path chains run before the generic chains of the level read their messages: without the
+      // strict-level guarantee (JACOBI) a level that mixes both kinds must stage
+      bool has_fast = false, has_generic = false;
+      for (const Chain& ch : chains) if (ch.commit_k >= 0) { if (fast_path_N(c, ch)) has_fast = true; else has_generic = true; }
+      if (has_fast && has_generic) level_staged = true;
+    }
     for (auto& sub : subsets[L]) {
       SubLevel sl;
       size_t soff = 0, poff = 0;
@@ -506,11 +533,194 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
   return plan;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Whole-sweep plan (k_bp_sweep).  Eligible: every chain is a BP message update on the DMMA fast path (uniform bond
+// dimension N in {8, 16}, degree 3 or 4) or a degree-2 vertex with the same N.  TNQS_SWEEP=0 falls back to level launches.
+// ---------------------------------------------------------------------------------------------------------------
+static bool sweep_disabled() { const char* e = getenv("TNQS_SWEEP"); return e && e[0] == '0'; }
+static int sweep_lag() { const char* e = getenv("TNQS_SWEEP_LAG"); return e ? std::max(1, atoi(e)) : 12; }
+static int sweep_ring() { const char* e = getenv("TNQS_SWEEP_RING"); return e ? std::max(2, atoi(e)) : 48; }
+
+static int small_chain_N(const tnqs_ctx* c, const Chain& ch) {
+  if (dmma_disabled() || ch.op || ch.close_leg < 0) return 0;
+  const int v = ch.v;
+  if (c->d[v] != 2 || c->inc[v].size() != 2 || ch.absorb.size() != 1) return 0;
+  const int N = c->chi[c->inc[v][0]];
+  if ((N != 8 && N != 16) || c->chi[c->inc[v][1]] != N) return 0;
+  const Absorb& ab = ch.absorb[0];
+  if (ab.leg != 1 - ch.close_leg || ab.flags != 0 || ab.ldm != N) return 0;
+  return N;
+}
+
+// Returns false (plan untouched) when the request is not eligible.  in_place: REFERENCE_ORDER (messages are updated in
+// place, readers and writers ordered by per-chain flags); otherwise every message goes to the staged slab and the sweep ends
+// with a commit pass (JACOBI).
+static bool build_sweep_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& levels, bool in_place, const Plan* reuse, Plan& out) {
+  if (sweep_disabled() || dmma_disabled()) return false;
+  // JACOBI sweeps are not faster through the queue than as two whole-sweep launches (measured on C2: 11.4 vs 9.9 ms), so the
+  // staged variant is opt-in (TNQS_SWEEP_JACOBI=1)
+  if (!in_place) { const char* e = getenv("TNQS_SWEEP_JACOBI"); if (!(e && e[0] == '1')) return false; }
+  // queue order: level-major; inside a level, chains whose producers sit early in the previous levels come first, so the
+  // distance (in chains) between a producer and its consumers stays about one level and closings are rarely pulled forward
+  std::vector<const Chain*> chains;
+  {
+    std::vector<int> writer_pos(2 * c->ne, -1);
+    for (const auto& lv : levels) {
+      std::vector<std::pair<int, const Chain*>> keyed;
+      for (const Chain& ch : lv) {
+        int key = -1;
+        if (in_place) for (const Absorb& ab : ch.absorb) {
+          const long long kin = (ab.mat - c->msg_cur) / c->slot;
+          if (kin >= 0 && kin < 2 * c->ne) key = std::max(key, writer_pos[kin]);
+        }
+        keyed.push_back({key, &ch});
+      }
+      std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<int, const Chain*>& a, const std::pair<int, const Chain*>& b) { return a.first < b.first; });
+      for (auto& kc : keyed) { if (kc.second->commit_k >= 0 && kc.second->commit_k < 2 * c->ne) writer_pos[kc.second->commit_k] = (int)chains.size(); chains.push_back(kc.second); }
+    }
+  }
+  const int nch = (int)chains.size();
+  if (nch < 2) return false;
+  int N = 0; size_t max_elems = 0; int max_split = 1;
+  std::vector<char> small(nch, 0);
+  for (int i = 0; i < nch; ++i) {
+    const Chain& ch = *chains[i];
+    if (ch.bp_mode != 1 || ch.commit_k < 0) return false;
+    int n = fast_path_N(c, ch);
+    if (!n) { n = small_chain_N(c, ch); small[i] = 1; }
+    if (!n || (N && n != N)) return false;
+    N = n;
+    max_elems = std::max(max_elems, (size_t)c->site_n[ch.v]);
+  }
+  const int R = std::max(2, std::min(nch, sweep_ring())), D = sweep_lag();
+  // dependencies between chains, in queue (= level-major sequence) order
+  std::vector<SweepChain> sc(nch);
+  {
+    std::vector<int> last_writer(2 * c->ne, -1);
+    std::vector<std::vector<int>> readers(2 * c->ne);
+    auto add = [](int* list, int x) -> bool {
+      for (int i = 0; i < 4; ++i) { if (list[i] == x) return true; if (list[i] < 0) { list[i] = x; return true; } }
+      return false;
+    };
+    for (int i = 0; i < nch; ++i) {
+      const Chain& ch = *chains[i];
+      for (int j = 0; j < 4; ++j) { sc[i].dep[j] = -1; sc[i].war[j] = -1; }
+      if (i - R >= 0 && !add(sc[i].dep, i - R)) return false;             // previous user of the ring slot (X and partials)
+      if (in_place) {
+        for (const Absorb& ab : ch.absorb) {
+          const int kin = (int)((ab.mat - c->msg_cur) / c->slot);
+          if (kin < 0 || kin >= 2 * c->ne || c->msg(kin) != ab.mat) return false;
+          if (last_writer[kin] >= 0 && !add(sc[i].dep, last_writer[kin])) return false;
+        }
+        const int k = ch.commit_k;
+        for (int r : readers[k]) if (!add(sc[i].war, r)) return false;
+        if (last_writer[k] >= 0 && !add(sc[i].war, last_writer[k])) return false;
+        readers[k].clear(); last_writer[k] = i;
+        for (const Absorb& ab : ch.absorb) readers[(int)((ab.mat - c->msg_cur) / c->slot)].push_back(i);
+      }
+    }
+  }
+  if (const char* e = getenv("TNQS_SWEEP_NOWAIT")) if (e[0] == '1')            // timing experiment only: results are wrong
+    for (int i = 0; i < nch; ++i) for (int j = 0; j < 4; ++j) { sc[i].dep[j] = -1; sc[i].war[j] = -1; }
+  Plan plan; plan.sweep = true; plan.sweepN = N; plan.nchains = (size_t)nch;
+  std::vector<SlabDesc> sd(nch); std::vector<CloseDmmaDesc> dc(nch); std::vector<CloseReduceDesc> rd(nch);
+  std::vector<int> commit;
+  std::vector<int> nsplit(nch, 1);
+  for (int i = 0; i < nch; ++i) {
+    const Chain& ch = *chains[i];
+    if (!small[i]) {
+      const long long rows = c->site_n[ch.v] / N;
+      nsplit[i] = (int)std::max<long long>(1, std::min<long long>(ch.split_cap, rows / 512));
+    }
+    max_split = std::max(max_split, nsplit[i]);
+  }
+  const size_t xslot = align_up(max_elems * sizeof(cplx), 256) / sizeof(cplx), pslot = (size_t)max_split * N * N;
+  const size_t need_scratch = xslot * R + 16, need_partial = pslot * R + 16;
+  const bool reuse_mem = reuse && reuse->scratch && reuse->scratch_elems >= need_scratch && reuse->partial_elems >= need_partial;
+  plan.scratch = reuse_mem ? reuse->scratch : c->talloc<cplx>(need_scratch);
+  plan.partial = reuse_mem ? reuse->partial : c->talloc<cplx>(need_partial);
+  plan.scratch_elems = reuse_mem ? reuse->scratch_elems : need_scratch;
+  plan.partial_elems = reuse_mem ? reuse->partial_elems : need_partial;
+  for (int i = 0; i < nch; ++i) {
+    const Chain& ch = *chains[i];
+    const int v = ch.v, F = (int)ch.absorb.size();
+    SlabDesc& a = sd[i]; CloseDmmaDesc& b = dc[i]; CloseReduceDesc& r = rd[i];
+    a.t = c->site[v]; a.x = plan.scratch + (size_t)(i % R) * xslot; a.F = F;
+    b.x = a.x; b.t = a.t; b.partial = plan.partial + (size_t)(i % R) * pslot; b.F = F; b.nsplit = nsplit[i];
+    b.epilogue = nullptr; b.ticket = nullptr;
+    long long stride = 2; int ai = 0;
+    for (int l = 0; l < (int)c->inc[v].size(); ++l) {
+      if (l == ch.close_leg) { a.gw = stride; b.gw = stride; }
+      else { a.g[ai] = stride; b.g[ai] = stride; a.m[ai] = ch.absorb[ai].mat; ++ai; }
+      stride *= N;
+    }
+    for (; ai < 3; ++ai) { a.g[ai] = 0; b.g[ai] = 0; a.m[ai] = nullptr; }
+    a.gs = 1; a.nslabs = small[i] ? 0 : 2 * N; a.flags = 0;
+    r.partial = b.partial; r.nsplit = nsplit[i]; r.n = N; r.np = N;
+    r.dst = in_place ? c->msg(ch.commit_k) : ch.dst; r.prev = ch.prev; r.diff = ch.diff;
+    r.mode = ch.bp_mode; r.normalize = ch.normalize; r.hermitize = ch.hermitize;
+    if (!in_place) commit.push_back(ch.commit_k);
+    plan.flops += 8.0 * (double)c->site_n[v] * N * (F + 1);
+  }
+  // queue: absorb items of chain i, closing items of chain i - D; a chain's closing is pulled forward when a later chain
+  // depends on it, so no item ever waits on a later item
+  std::vector<int2> items;
+  {
+    std::vector<int> pending; size_t head = 0;
+    std::vector<char> closed(nch, 0);
+    auto emit_close = [&](int m) { for (int j = 0; j < nsplit[m]; ++j) items.push_back(make_int2(~m, j)); closed[m] = 1; };
+    for (int i = 0; i < nch; ++i) {
+      int upto = -1;
+      for (int j = 0; j < 4; ++j) { const int p = sc[i].dep[j]; if (p >= 0 && !closed[p]) upto = std::max(upto, p); }
+      while (upto >= 0 && head < pending.size() && pending[head] <= upto) emit_close(pending[head++]);
+      if (small[i]) { items.push_back(make_int2(i, -1)); closed[i] = 1; }
+      else {
+        for (int y = 0; y < 2 * N; ++y) items.push_back(make_int2(i, y));
+        pending.push_back(i);
+        while (pending.size() - head > (size_t)D) emit_close(pending[head++]);
+      }
+    }
+    while (head < pending.size()) emit_close(pending[head++]);
+  }
+  plan.sweep_items = (int)items.size();
+  plan.sweep_grid = dim3((unsigned)std::min<long long>((long long)items.size(), 2LL * c->num_sms), 1, 1);
+  plan.sweep_smem = N == 16 ? SlabCfg<16>::SMEM : SlabCfg<8>::SMEM;
+  plan.sweep_commit = (int)commit.size();
+  const size_t cnt[8] = {0, 0, 0, rd.size(), commit.size(), sd.size(), dc.size(), items.size()};
+  bool same = reuse_mem && reuse->sweep && reuse->nchains == (size_t)nch && reuse->d_chains && reuse->d_chain_done;
+  for (int i = 0; i < 8 && same; ++i) same = cnt[i] == reuse->cnt[i];
+  for (int i = 0; i < 8; ++i) plan.cnt[i] = cnt[i];
+  plan.d_reduce = upload_into(c, same ? reuse->d_reduce : nullptr, rd);
+  plan.d_commit = upload_into(c, same ? reuse->d_commit : nullptr, commit);
+  plan.d_ticket = same ? reuse->d_ticket : c->talloc<int>(nch + 1);
+  if (!same) CU(cudaMemsetAsync(plan.d_ticket, 0, (nch + 1) * sizeof(int), c->stream));
+  for (int i = 0; i < nch; ++i) { dc[i].epilogue = plan.d_reduce + i; dc[i].ticket = plan.d_ticket + i; }
+  plan.d_slab = upload_into(c, same ? reuse->d_slab : nullptr, sd);
+  plan.d_dclose = upload_into(c, same ? reuse->d_dclose : nullptr, dc);
+  plan.d_items = upload_into(c, same ? reuse->d_items : nullptr, items);
+  plan.d_chains = upload_into(c, same ? reuse->d_chains : nullptr, sc);
+  plan.d_qctr = same ? reuse->d_qctr : c->talloc<int>(8);
+  plan.d_slab_done = same ? reuse->d_slab_done : c->talloc<int>(nch + 1);
+  plan.d_chain_done = same ? reuse->d_chain_done : c->talloc<int>(nch + 1);
+  if (!same) {
+    CU(cudaMemsetAsync(plan.d_qctr, 0, 8 * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(plan.d_slab_done, 0, (nch + 1) * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(plan.d_chain_done, 0, (nch + 1) * sizeof(int), c->stream));
+  }
+  plan.nlaunch = 1 + (plan.sweep_commit ? 1 : 0);
+  out = plan;
+  return true;
+}
+
 static bool same_rec(const LaunchRec& a, const LaunchRec& b) {
   return a.off == b.off && a.count == b.count && a.grid.x == b.grid.x && a.grid.y == b.grid.y && a.grid.z == b.grid.z && a.smem == b.smem && a.dmma == b.dmma && a.tpc == b.tpc;
 }
 // True when two plans issue the same launches over the same device buffers (a captured CUDA graph of one replays the other).
 static bool same_launches(const Plan& a, const Plan& b) {
+  if (a.sweep != b.sweep) return false;
+  if (a.sweep) return a.sweepN == b.sweepN && a.sweep_items == b.sweep_items && a.sweep_grid.x == b.sweep_grid.x && a.sweep_smem == b.sweep_smem &&
+                      a.sweep_commit == b.sweep_commit && a.d_items == b.d_items && a.d_qctr == b.d_qctr && a.d_slab == b.d_slab && a.d_dclose == b.d_dclose &&
+                      a.d_chains == b.d_chains && a.d_slab_done == b.d_slab_done && a.d_chain_done == b.d_chain_done && a.d_commit == b.d_commit;
   if (a.levels.size() != b.levels.size() || a.d_slab != b.d_slab || a.d_items != b.d_items || a.d_qctr != b.d_qctr || a.d_slab_done != b.d_slab_done || a.d_apply != b.d_apply || a.d_close != b.d_close ||
       a.d_reduce != b.d_reduce || a.d_dclose != b.d_dclose || a.d_gate1 != b.d_gate1 || a.d_commit != b.d_commit) return false;
   for (size_t L = 0; L < a.levels.size(); ++L) {
@@ -545,6 +755,14 @@ static int close_threads(int split_cap) {
   (void)split_cap; return 256;      // measured on C2: 4-warp CTAs (one wave per level) are not faster than 8-warp ones
 }
 static void run_plan(tnqs_ctx* c, const Plan& p) {
+  if (p.sweep) {
+    SweepQueue Q; Q.items = p.d_items; Q.n = p.sweep_items; Q.counter = p.d_qctr; Q.slabs = p.d_slab; Q.closes = p.d_dclose;
+    Q.chains = p.d_chains; Q.slab_done = p.d_slab_done; Q.chain_done = p.d_chain_done;
+    if (p.sweepN == 16) LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_sweep<16>, p.sweep_grid, 256, p.sweep_smem, Q);
+    else LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_sweep<8>, p.sweep_grid, 256, p.sweep_smem, Q);
+    if (p.sweep_commit) LAUNCH(c, TNQS_KC_BP_FINALIZE, k_msg_commit, p.sweep_commit, 128, 0, c->msg_cur, c->msg_stage, c->slot, p.d_commit, c->d_chi);
+    return;
+  }
   for (const LevelPlan& lp : p.levels) {
     for (const SubLevel& sl : lp.subs) {
       if (sl.fused.count) {

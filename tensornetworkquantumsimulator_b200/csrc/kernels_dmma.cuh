@@ -144,10 +144,14 @@ __device__ __forceinline__ void absorb_slab_body(const SlabDesc& d, int sub, cpl
   }
 }
 
-template <int N>
+// COHERENT: the messages may have been written by another CTA of the same launch (k_bp_sweep) - read them through L2.
+template <int N, bool COHERENT = false>
 __device__ __forceinline__ void absorb_slab_item(const SlabDesc& d, int sub, cplx* sm, cplx* msm) {
   // the item's messages, staged once: every phase builds its B fragments from shared memory
-  for (int idx = threadIdx.x; idx < d.F * N * N; idx += blockDim.x) msm[idx] = __ldg(d.m[idx / (N * N)] + idx % (N * N));
+  for (int idx = threadIdx.x; idx < d.F * N * N; idx += blockDim.x) {
+    const cplx* src = d.m[idx / (N * N)] + idx % (N * N);
+    msm[idx] = COHERENT ? __ldcg(src) : __ldg(src);
+  }
   __syncthreads();
   if (d.F == 3) absorb_slab_body<N, 3>(d, sub, sm, msm); else absorb_slab_body<N, 2>(d, sub, sm, msm);
 }
@@ -182,8 +186,11 @@ struct CloseDmmaDesc {
 // whole complex elements (16 bytes) and feeds the real part to one k-step, the imaginary part to the next.  A K-group is
 // 4 complex K = (i1 pair) x (s pair): its 64 bytes are contiguous in T and two full sectors in X, so every sector that is
 // fetched is used whole.  Three groups are in flight per warp (register sets reloaded in place).
-template <int N>
-__device__ __forceinline__ bool close_dmma_item(const CloseDmmaDesc& d, int sub, double* red) {
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+// `pre_epilogue` runs in the CTA that took the last ticket, after the partials are complete and before the epilogue
+// writes the message (k_bp_sweep waits there for the readers of the old value).
+template <int N, typename Hook = NoHook>
+__device__ __forceinline__ bool close_dmma_item(const CloseDmmaDesc& d, int sub, double* red, Hook pre_epilogue = Hook()) {
   constexpr int MT = N / 8;               // m-tiles of 8 complex rows w
   constexpr int NT = N / 4;               // n-tiles of 8 real columns = 4 w' x (re, im)
   constexpr int NSET = 3;
@@ -277,6 +284,7 @@ __device__ __forceinline__ bool close_dmma_item(const CloseDmmaDesc& d, int sub,
   if (is_last) {
     __threadfence();
     if (threadIdx.x == 0) *d.ticket = 0;
+    pre_epilogue();
     close_reduce_body(*d.epilogue, reinterpret_cast<cplx*>(red), red + 2 * N * N);
   }
   return is_last;
@@ -347,6 +355,149 @@ __global__ void __launch_bounds__(256, 2) k_bp_level(const LevelQueue Q) {
   if (threadIdx.x == 0) {
     const int gone = atomicAdd(Q.counter + 1, 1);
     if (gone == (int)gridDim.x - 1) { Q.counter[0] = 0; Q.counter[1] = 0; __threadfence(); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_bp_sweep: a whole BP sweep (every dependency level of the sequential Gauss-Seidel order, or a JACOBI sweep) as ONE
+// persistent launch with data-flow synchronisation instead of level barriers.  CTAs draw items from an in-order queue:
+//   absorb item  (chain m, slab y)  - waits until the chains in `dep` are done in this sweep (the producers of the
+//                                     messages it reads, and the previous user of its ring slot of the intermediate X);
+//   closing item (chain m, split j) - waits until the 2N slabs of chain m are done; the CTA that takes the last ticket
+//                                     waits for the chains in `war` (earlier readers of the old value of the message),
+//                                     runs the message epilogue in place and publishes chain_done[m];
+//   small item   (chain m)          - a degree-2 vertex (one absorbed leg): the whole update by one CTA.
+// The host emits the closing items of chain m `lag` chains after its absorb items (so they are normally ready when
+// drawn and the memory-bound closing of one message overlaps the tensor-bound absorption of later ones), but never after
+// an absorb item that depends on them: every wait is on items that were drawn EARLIER, i.e. that are finished or running
+// on resident CTAs - the queue cannot deadlock.  chain_done holds epoch + 1 (the epoch counter lives in counter[4] and
+// is advanced by the last CTA to leave), so nothing has to be reset between the sweeps of a refresh.  Arithmetic per
+// message (absorption order, split factor, reduction order) is exactly that of k_absorb_slab + k_close_dmma.
+// ---------------------------------------------------------------------------------------------------------------
+struct SweepChain { int dep[4]; int war[4]; };
+struct SweepQueue {
+  const int2* items;      // x >= 0: absorb slab y of chain x (y < 0: small chain x);  x < 0: closing split y of chain ~x
+  int n;
+  int* counter;           // [0] next item, [1] CTAs that left, [2] error flag, [4] epoch; polls spent waiting: [3] producers / ring, [5] slabs, [6] readers
+  const SlabDesc* slabs;
+  const CloseDmmaDesc* closes;
+  const SweepChain* chains;
+  int* slab_done;         // per chain; reset by the CTA that runs the chain's epilogue
+  int* chain_done;        // per chain: epoch + 1 once its message is written
+};
+
+// The whole CTA waits until chain_done[list[i]] == done_val for the (up to 4) chains of `list` (-1 = none).
+__device__ __forceinline__ void sweep_wait_chains(const SweepQueue& Q, const int* __restrict__ list, int done_val, int stat = 3) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const int dep = lane < 4 ? list[lane] : -1;
+    bool ok = dep < 0 || *(volatile int*)(Q.chain_done + dep) == done_val;
+    int spins = 0;
+    while (!__all_sync(0xffffffffu, ok)) {
+      __nanosleep(40);
+      if (!ok) ok = *(volatile int*)(Q.chain_done + dep) == done_val;
+      ++spins;
+      bool giveup = false;
+      if ((spins & 255) == 0 && lane == 0) {                                   // never hang the device
+        if (*(volatile int*)(Q.counter + 2)) giveup = true;
+        else if (spins > (1 << 22)) { atomicExch(Q.counter + 2, 1); giveup = true; }
+      }
+      if (__any_sync(0xffffffffu, giveup)) break;
+    }
+    if (lane == 0 && spins) atomicAdd(Q.counter + stat, spins);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// One update of a degree-2 vertex (F == 1) by a whole CTA: X[s,i',w] = sum_i T[s,i,w] m[i,i'];
+// M[w,w'] = sum_{s,i'} X[s,i',w] conj(T[s,i',w']) -> partial (nsplit == 1).  Shared memory: 5 N^2 complex.
+template <int N>
+__device__ __forceinline__ void small_chain_body(const SlabDesc& a, const CloseDmmaDesc& b, cplx* sm) {
+  cplx* Ts = sm;                    // [s][i][w]
+  cplx* Xs = sm + 2 * N * N;        // [s][i'][w]
+  cplx* Ms = sm + 4 * N * N;        // m[i][i']
+  for (int idx = threadIdx.x; idx < 2 * N * N; idx += blockDim.x) {
+    const int s = idx & 1, i = (idx >> 1) % N, w = (idx >> 1) / N;
+    Ts[(s * N + i) * N + w] = a.t[s + (long long)i * a.g[0] + (long long)w * a.gw];
+  }
+  for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) Ms[idx] = __ldcg(a.m[0] + idx);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * N * N; idx += blockDim.x) {
+    const int w = idx % N, ip = (idx / N) % N, s = idx / (N * N);
+    cplx acc = cmake(0, 0);
+    for (int i = 0; i < N; ++i) cfma(acc, Ts[(s * N + i) * N + w], Ms[i + N * ip]);
+    Xs[(s * N + ip) * N + w] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
+    const int w = idx % N, wp = idx / N;
+    cplx acc = cmake(0, 0);
+    for (int k = 0; k < 2 * N; ++k) cfma(acc, Xs[k * N + w], cconj(Ts[k * N + wp]));
+    __stcg(b.partial + idx, acc);
+  }
+  __syncthreads();
+}
+
+template <int N>
+__global__ void __launch_bounds__(256, 2) k_bp_sweep(const SweepQueue Q) {
+  extern __shared__ cplx dyn[];
+  cplx* msm = dyn + SlabCfg<N>::SLAB3;
+  __shared__ int s_item, s_epoch;
+  __shared__ int2 s_entry;
+  if (threadIdx.x == 0) s_epoch = *(volatile int*)(Q.counter + 4);
+  __syncthreads();
+  const int done_val = s_epoch + 1;
+  for (;;) {
+    if (threadIdx.x == 0) { const int i = atomicAdd(Q.counter, 1); s_item = i; s_entry = Q.items[min(i, Q.n - 1)]; }
+    __syncthreads();
+    const int it = s_item;
+    if (it >= Q.n) break;
+    const int2 e = s_entry;
+    if (e.x >= 0 && e.y >= 0) {
+      sweep_wait_chains(Q, Q.chains[e.x].dep, done_val);
+      const SlabDesc d = Q.slabs[e.x];
+      absorb_slab_item<N, true>(d, e.y, dyn, msm);
+      __syncthreads();                               // the CTA's part of X ...
+      if (threadIdx.x == 0) { __threadfence(); atomicAdd(Q.slab_done + e.x, 1); }     // ... is visible before the slab counter moves
+    } else if (e.x >= 0) {
+      sweep_wait_chains(Q, Q.chains[e.x].dep, done_val);
+      const SlabDesc a = Q.slabs[e.x];
+      const CloseDmmaDesc d = Q.closes[e.x];
+      small_chain_body<N>(a, d, dyn);
+      sweep_wait_chains(Q, Q.chains[e.x].war, done_val, 6);
+      close_reduce_body(*d.epilogue, dyn, reinterpret_cast<double*>(dyn + N * N));
+      __syncthreads();
+      if (threadIdx.x == 0) { __threadfence(); *(volatile int*)(Q.chain_done + e.x) = done_val; }
+    } else {
+      const int ci = ~e.x;
+      const CloseDmmaDesc d = Q.closes[ci];
+      if (threadIdx.x == 0) {
+        const int need = Q.slabs[ci].nslabs;
+        int spins = 0;
+        while (*(volatile int*)(Q.slab_done + ci) < need) {
+          __nanosleep(40);
+          ++spins;
+          if ((spins & 255) == 0) {
+            if (*(volatile int*)(Q.counter + 2)) break;
+            if (spins > (1 << 22)) { atomicExch(Q.counter + 2, 1); break; }
+          }
+        }
+        if (spins) atomicAdd(Q.counter + 5, spins);
+        __threadfence();
+      }
+      __syncthreads();
+      auto hook = [&]() { sweep_wait_chains(Q, Q.chains[ci].war, done_val, 6); };
+      if (close_dmma_item<N>(d, e.y, reinterpret_cast<double*>(dyn), hook)) {
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); Q.slab_done[ci] = 0; *(volatile int*)(Q.chain_done + ci) = done_val; }
+      }
+    }
+    __syncthreads();                                 // shared memory, s_item and s_entry are reused by the next item
+  }
+  if (threadIdx.x == 0) {
+    const int gone = atomicAdd(Q.counter + 1, 1);
+    if (gone == (int)gridDim.x - 1) { Q.counter[0] = 0; Q.counter[1] = 0; Q.counter[4] = done_val; __threadfence(); }
   }
 }
 

@@ -208,7 +208,7 @@ __device__ __forceinline__ void close_reduce_body(const CloseReduceDesc& d, cplx
   const int nn = d.n * d.np;
   for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
     cplx s = cmake(0, 0);
-    for (int p = 0; p < d.nsplit; ++p) s = cadd(s, d.partial[(size_t)p * nn + idx]);
+    for (int p = 0; p < d.nsplit; ++p) s = cadd(s, __ldcg(d.partial + (size_t)p * nn + idx));      // partials and the previous message come from other CTAs: read through L2
     gsm[idx] = s;
   }
   __syncthreads();
@@ -244,7 +244,7 @@ __device__ __forceinline__ void close_reduce_body(const CloseReduceDesc& d, cplx
       v = cmake(0.5 * (v.x + w.x), 0.5 * (v.y - w.y));
     }
     v = cmul(v, inv);
-    cplx p = d.diff ? d.prev[idx] : cmake(0, 0);      // read before the store: dst may alias prev (in-place message update)
+    cplx p = d.diff ? __ldcg(d.prev + idx) : cmake(0, 0);      // read before the store: dst may alias prev (in-place message update)
     d.dst[idx] = v;
     if (d.diff) {
       dre += v.x * p.x + v.y * p.y;      // conj(v) * p

@@ -48,6 +48,8 @@ static void set_smem_attrs() {   // per device: called at every handle creation 
   cudaFuncSetAttribute(k_close_dmma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_bp_level<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_bp_level<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_bp_sweep<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_bp_sweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_close_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -201,6 +203,29 @@ extern "C" int32_t tnqs_get_site(const tnqs_ctx* cc, int32_t v, double* data, in
   c->sync();
   API_END(c)
 }
+extern "C" int32_t tnqs_set_sites(tnqs_ctx* c, int32_t count, const int32_t* v, const double* const* data, const int64_t* n) {
+  API_BEGIN(c)
+  REQUIRE(count >= 0 && (count == 0 || (v && data && n)), TNQS_ERR_INVALID_ARG, "tnqs_set_sites: null argument");
+  for (int i = 0; i < count; ++i) {
+    REQUIRE(v[i] >= 0 && v[i] < c->nv && data[i], TNQS_ERR_INVALID_ARG, "tnqs_set_sites: bad vertex or null data");
+    REQUIRE(n[i] == c->site_n[v[i]], TNQS_ERR_SHAPE, "tnqs_set_sites: element count does not match the site tensor");
+  }
+  for (int i = 0; i < count; ++i) CU(cudaMemcpyAsync(c->site[v[i]], data[i], n[i] * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  c->sync();
+  API_END(c)
+}
+extern "C" int32_t tnqs_get_sites(const tnqs_ctx* cc, int32_t count, const int32_t* v, double* const* data, const int64_t* n) {
+  tnqs_ctx* c = const_cast<tnqs_ctx*>(cc);
+  API_BEGIN(c)
+  REQUIRE(count >= 0 && (count == 0 || (v && data && n)), TNQS_ERR_INVALID_ARG, "tnqs_get_sites: null argument");
+  for (int i = 0; i < count; ++i) {
+    REQUIRE(v[i] >= 0 && v[i] < c->nv && data[i], TNQS_ERR_INVALID_ARG, "tnqs_get_sites: bad vertex or null data");
+    REQUIRE(n[i] == c->site_n[v[i]], TNQS_ERR_SHAPE, "tnqs_get_sites: element count does not match the site tensor");
+  }
+  for (int i = 0; i < count; ++i) CU(cudaMemcpyAsync(data[i], c->site[v[i]], n[i] * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  API_END(c)
+}
 extern "C" int32_t tnqs_fill_random(tnqs_ctx* c, uint64_t seed) {
   API_BEGIN(c)
   for (int v = 0; v < c->nv; ++v) {
@@ -345,7 +370,9 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
         ch.split_cap = o.mode == TNQS_BP_JACOBI ? 4 : bp_level_split_cap();      // whole-sweep launches want long CTAs, level launches more
         levels[level[i]].push_back(ch);
       }
-      Plan np = build_plan(c, levels, scratch_budget(c), old ? &old->plan : nullptr, /*strict_levels=*/o.mode == TNQS_BP_REFERENCE_ORDER);
+      Plan np;
+      if (!build_sweep_plan(c, levels, /*in_place=*/o.mode == TNQS_BP_REFERENCE_ORDER, old ? &old->plan : nullptr, np))
+        np = build_plan(c, levels, scratch_budget(c), (old && !old->plan.sweep) ? &old->plan : nullptr, /*strict_levels=*/o.mode == TNQS_BP_REFERENCE_ORDER);
       if (nc->graph && !same_launches(np, nc->plan)) { cudaGraphExecDestroy(nc->graph); nc->graph = nullptr; }
       nc->plan = np;
     } catch (...) { c->arena_bypass = false; for (void* p : c->temp) c->dfree(p); c->temp.swap(saved); if (!old) delete nc; else { c->bp_cache = nullptr; } throw; }
@@ -360,7 +387,7 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
   double* d_diff = pc->d_diff;
   double* d_sum = d_diff + nseq;
   int it = 0; double mean = NAN;
-  const bool use_graph = !c->profiling && !graphs_disabled() && plan.nlaunch >= 8;
+  const bool use_graph = !c->profiling && !graphs_disabled() && (plan.nlaunch >= 8 || plan.sweep);
   const int per_sweep = plan.nlaunch + (want_diff ? 1 : 0);
   if (use_graph) {
     if (!pc->graph) {
@@ -412,11 +439,16 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
     }
   }
   if (plan.d_qctr) {
-    int q[4] = {0, 0, 0, 0};
-    CU(cudaMemcpyAsync(q, plan.d_qctr, sizeof(q), cudaMemcpyDeviceToHost, c->stream));
+    int q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CU(cudaMemcpyAsync(q, plan.d_qctr, (plan.sweep ? 8 : 4) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     c->sync();
-    if (q[3]) { static const char* dbg = getenv("TNQS_DEBUG_QUEUE"); if (dbg) fprintf(stderr, "[tnqs] k_bp_level waits: %d polls in %d sweeps\n", q[3], it); CU(cudaMemsetAsync(plan.d_qctr + 3, 0, sizeof(int), c->stream)); }
-    REQUIRE(q[2] == 0, TNQS_ERR_CUDA, "internal: a BP level queue wait timed out");
+    if (q[3] || q[5] || q[6]) {
+      static const char* dbg = getenv("TNQS_DEBUG_QUEUE");
+      if (dbg) fprintf(stderr, "[tnqs] %s wait polls in %d sweeps: producers/ring %d, slabs %d, readers %d\n", plan.sweep ? "k_bp_sweep" : "k_bp_level", it, q[3], q[5], q[6]);
+      CU(cudaMemsetAsync(plan.d_qctr + 3, 0, sizeof(int), c->stream));
+      if (plan.sweep) CU(cudaMemsetAsync(plan.d_qctr + 5, 0, 2 * sizeof(int), c->stream));
+    }
+    if (q[2]) { bp_cache_drop(c); throw TnqsError(TNQS_ERR_CUDA, "internal: a BP queue wait timed out"); }
   }
   if (it > o.maxiter) it = o.maxiter;
   if (iters_out) *iters_out = it;

@@ -73,9 +73,16 @@ class TensorNetworkState:
         cap = int(chi_cap if chi_cap is not None else max(1, chi.max()))
         h = _create(g, [t.shape[0] for t in tensors], chi[:g.ne], cap, device)
         psi = TensorNetworkState(g, h, cap, device)
-        for v, t in enumerate(tensors):
-            psi.set_site(v, t)
+        psi.set_sites(range(g.nv), tensors)
         return psi
+
+    def set_sites(self, vs, tensors) -> None:
+        """Several site tensors in one call (tnqs_set_sites: copies queued back to back, one synchronisation)."""
+        vs = i32(list(vs))
+        flats = [np.asfortranarray(t, dtype=np.complex128).ravel(order="F").view(np.float64) for t in tensors]
+        ptrs = (C.POINTER(C.c_double) * len(flats))(*[ptr_f64(f) for f in flats])
+        ns = np.asarray([f.size // 2 for f in flats], dtype=np.int64)
+        check(self._h.ptr, _lib.load().tnqs_set_sites(self._h.ptr, len(flats), ptr_i32(vs), ptrs, _lib.ptr_i64(ns)))
 
     def set_site(self, v: int, t: np.ndarray) -> None:
         a = np.asfortranarray(t, dtype=np.complex128)
@@ -94,7 +101,20 @@ class TensorNetworkState:
         return buf.view(np.complex128).reshape(shape, order="F")
 
     def tensors(self) -> List[np.ndarray]:
-        return [self[v] for v in range(self.g.nv)]
+        """Every site tensor (tnqs_get_sites: one call, one synchronisation)."""
+        lib = _lib.load()
+        nv = self.g.nv
+        ns = np.asarray([lib.tnqs_site_size(self._h.ptr, v) for v in range(nv)], dtype=np.int64)
+        bufs = [np.empty(2 * int(n), dtype=np.float64) for n in ns]
+        ptrs = (C.POINTER(C.c_double) * nv)(*[ptr_f64(b) for b in bufs])
+        vs = i32(np.arange(nv))
+        check(self._h.ptr, lib.tnqs_get_sites(self._h.ptr, nv, ptr_i32(vs), ptrs, _lib.ptr_i64(ns)))
+        chi = self.bond_dims()
+        out = []
+        for v in range(nv):
+            dims = tuple(int(chi[e]) for e in self.g.incident[v])
+            out.append(bufs[v].view(np.complex128).reshape((int(ns[v]) // int(np.prod(dims, dtype=np.int64)),) + dims, order="F"))
+        return out
 
     def bond_dims(self) -> np.ndarray:
         chi = np.ones(max(self.g.ne, 1), dtype=np.int32)

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libtnqs_cuda.so")
 SYMBOLS = [
     "tnqs_version", "tnqs_status_string", "tnqs_last_error", "tnqs_create", "tnqs_destroy", "tnqs_clone",
     "tnqs_sync", "tnqs_num_vertices", "tnqs_num_edges", "tnqs_get_bond_dims", "tnqs_site_size", "tnqs_set_site",
-    "tnqs_get_site", "tnqs_fill_random", "tnqs_set_message", "tnqs_get_message", "tnqs_reset_messages",
+    "tnqs_get_site", "tnqs_set_sites", "tnqs_get_sites", "tnqs_fill_random", "tnqs_set_message", "tnqs_get_message", "tnqs_reset_messages",
     "tnqs_bp_update", "tnqs_apply_1site", "tnqs_apply_2site", "tnqs_apply_2site_begin", "tnqs_apply_2site_end", "tnqs_apply_circuit", "tnqs_rdm_1site",
     "tnqs_expect_2site_nn", "tnqs_expect_path", "tnqs_vertex_scalars", "tnqs_edge_scalars", "tnqs_rescale", "tnqs_symmetric_gauge",
     "tnqs_truncate", "tnqs_message_slab", "tnqs_halo_pack", "tnqs_halo_unpack", "tnqs_set_partition",
@@ -70,6 +70,7 @@ def load() -> C.CDLL:
     lib.tnqs_get_bond_dims.argtypes = [p, i32p]
     lib.tnqs_site_size.argtypes = [p, i32]; lib.tnqs_site_size.restype = i64
     lib.tnqs_set_site.argtypes = [p, i32, f64p, i64]; lib.tnqs_get_site.argtypes = [p, i32, f64p, i64]
+    lib.tnqs_set_sites.argtypes = [p, i32, i32p, C.POINTER(f64p), i64p]; lib.tnqs_get_sites.argtypes = [p, i32, i32p, C.POINTER(f64p), i64p]
     lib.tnqs_fill_random.argtypes = [p, C.c_uint64]
     lib.tnqs_set_message.argtypes = [p, i32, f64p, i64]; lib.tnqs_get_message.argtypes = [p, i32, f64p, i64]
     lib.tnqs_reset_messages.argtypes = [p]

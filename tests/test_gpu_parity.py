@@ -744,3 +744,68 @@ def test_full_size_c2_properties(E):
     E.update(bpc, edge_sequence=seq, inplace=True, maxiter=25, tolerance=1e-8)
     zs = E.expect(bpc, [("Z", [g.names[v]]) for v in (0, 500, 1023)])
     assert all(abs(z.imag) < 1e-10 and abs(z.real) <= 1 + 1e-10 for z in zs)
+
+
+def _oracle_jacobi(psi_o, sweeps):
+    bo = O.BeliefPropagationCache(psi_o)
+    for _ in range(sweeps):                 # Jacobi: every message from the previous sweep's values
+        bo.messages = {k: O.updated_message(bo, k) for k in range(2 * bo.g.ne)}
+    return bo
+
+
+@pytest.mark.parametrize("shape,chi", [((6, 6), 8), ((5, 4), 16)])
+def test_bp_whole_sweep_kernel_matches_level_launches_and_oracle(E, monkeypatch, shape, chi):
+    # REFERENCE_ORDER sweeps as ONE persistent data-flow launch (k_bp_sweep, the default on uniform chi in {8, 16} grids)
+    # against the level-by-level launches (TNQS_SWEEP=0) and the oracle; the ring of 4 intermediates forces slot reuse
+    g = G.named_grid(shape)
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=chi, seed=5)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    seq = G.forest_cover_edge_sequence(g)
+    io = {}
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=3, tolerance=0.0, edge_sequence=seq, info=io)
+    res = {}
+    for name, env in (("level", {"TNQS_SWEEP": "0"}), ("sweep", {"TNQS_SWEEP": "1"}), ("sweep_ring4", {"TNQS_SWEEP": "1", "TNQS_SWEEP_RING": "4", "TNQS_SWEEP_LAG": "2"})):
+        for k, val in env.items():
+            monkeypatch.setenv(k, val)
+        ie = {}
+        be = E.update(to_engine(psi_o, chi_cap=chi), maxiter=3, tolerance=0.0, edge_sequence=seq, info=ie)
+        launches = be.psi.kernel_launches()
+        for k in env:
+            monkeypatch.delenv(k)
+        check_messages(E, be, bo)
+        assert ie["iters"] == io["iters"] == 3 and abs(ie["mean_diff"] - io["mean_diff"]) < 1e-10 * max(1.0, abs(io["mean_diff"]))
+        res[name] = ([E.message(be, k) for k in range(2 * g.ne)], launches)
+    assert res["sweep"][1] < res["level"][1]          # one launch per sweep instead of two per level
+    for k in range(2 * g.ne):                          # the fast-path arithmetic is the same; degree-2 vertices differ in rounding only
+        assert rel(res["sweep"][0][k], res["level"][0][k]) < 1e-13
+        assert np.array_equal(res["sweep"][0][k], res["sweep_ring4"][0][k])     # queue shape never changes a result
+
+
+@pytest.mark.parametrize("env", [{}, {"TNQS_SWEEP_JACOBI": "1"}, {"TNQS_SWEEP_JACOBI": "1", "TNQS_SWEEP_RING": "3", "TNQS_SWEEP_LAG": "1"}])
+def test_bp_jacobi_two_sweeps_uniform_chi(E, monkeypatch, env):
+    # JACOBI on a lattice that mixes tensor-core chains (degree 3, 4) and generic ones (corners): every message of sweep 2
+    # must be computed from the values of sweep 1 (a level that mixes both kinds stages its messages)
+    for k, val in env.items():
+        monkeypatch.setenv(k, val)
+    g = G.named_grid((4, 4))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=8, seed=9)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    for sweeps in (1, 2):
+        bo = _oracle_jacobi(psi_o, sweeps)
+        be = E.update(to_engine(psi_o, chi_cap=8), maxiter=sweeps, edge_sequence=np.arange(2 * g.ne), mode="jacobi")
+        check_messages(E, be, bo)
+
+
+def test_set_get_sites_batched_round_trip(E):
+    g = G.named_grid((3, 3))
+    psi_o = ragged_state(g, [1 + (e % 3) for e in range(g.ne)], seed=3)
+    psi = to_engine(psi_o).psi
+    ts = psi.tensors()                                       # tnqs_get_sites
+    for v in range(g.nv):
+        assert np.array_equal(ts[v], psi_o.tensors[v]) and np.array_equal(psi[v], ts[v])
+    psi.set_sites([4, 0], [2 * ts[4], 3 * ts[0]])            # tnqs_set_sites
+    assert np.array_equal(psi[4], 2 * ts[4]) and np.array_equal(psi[0], 3 * ts[0]) and np.array_equal(psi[1], ts[1])
+    with pytest.raises(Exception):
+        psi.set_sites([1], [ts[4]])                          # wrong element count
