@@ -120,13 +120,35 @@ struct tnqs_ctx {
       if (ms > stall_ms()) fprintf(stderr, "[tnqs stall] %s blocked the host for %.2f ms\n", what, ms);
     }
   };
+  // Descriptor uploads go through a pinned staging buffer owned by the handle: a copy from pageable memory makes the
+  // driver stage (or page-lock) the source on every call, which is slow and erratic on a host that holds gigabytes of
+  // pinned memory (measured: +35..70 ms per layer).  The buffer is a bump allocator that rewinds at every stream
+  // synchronisation; a request that does not fit falls back to the pageable copy.
+  char* hstage = nullptr; size_t hstage_size = 0, hstage_off = 0;
+  void h2d(void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return;
+    StallProbe sp("upload");
+    if (!hstage && hstage_size == 0) {
+      const char* e = getenv("TNQS_NO_HSTAGE");
+      hstage_size = (e && e[0] == '1') ? 1 : (size_t)32 << 20;
+      if (cudaHostAlloc((void**)&hstage, hstage_size, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); hstage = nullptr; }
+    }
+    const size_t need = (bytes + 255) / 256 * 256;
+    if (hstage && hstage_off + need <= hstage_size) {
+      char* s = hstage + hstage_off; hstage_off += need;
+      memcpy(s, src, bytes);
+      CU(cudaMemcpyAsync(dst, s, bytes, cudaMemcpyHostToDevice, stream));
+    } else {
+      CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    }
+  }
+  void hstage_destroy() { if (hstage) cudaFreeHost(hstage); hstage = nullptr; hstage_size = 0; hstage_off = 0; }
   template <typename T> T* upload(const std::vector<T>& v) {
     T* p = talloc<T>(std::max<size_t>(v.size(), 1));
-    StallProbe sp("upload");
-    if (!v.empty()) CU(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+    h2d(p, v.data(), v.size() * sizeof(T));
     return p;
   }
-  void sync() { CU(cudaStreamSynchronize(stream)); }
+  void sync() { CU(cudaStreamSynchronize(stream)); hstage_off = 0; }
 
   // ---- launch accounting ----
   void pre_launch(int kc) {
@@ -157,7 +179,7 @@ struct tnqs_ctx {
     int st = 0;
     CU(cudaMemcpyAsync(&st, d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
     sync();
-    if (st) { int z = 0; CU(cudaMemcpyAsync(d_status, &z, sizeof(int), cudaMemcpyHostToDevice, stream)); }
+    if (st) { int z = 0; h2d(d_status, &z, sizeof(int)); }
     return st;
   }
 };
@@ -260,7 +282,7 @@ static int fast_path_N(const tnqs_ctx* c, const Chain& ch) {
 // Build a plan for `levels` (vector of vector of chains).  All device buffers are temporaries of the current call.
 template <typename T> static T* upload_into(tnqs_ctx* c, T* reuse, const std::vector<T>& v) {
   if (!reuse) return c->upload(v);
-  if (!v.empty()) CU(cudaMemcpyAsync(reuse, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  c->h2d(reuse, v.data(), v.size() * sizeof(T));
   return reuse;
 }
 
@@ -538,7 +560,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
 // dimension N in {8, 16}, degree 3 or 4) or a degree-2 vertex with the same N.  TNQS_SWEEP=0 falls back to level launches.
 // ---------------------------------------------------------------------------------------------------------------
 static bool sweep_disabled() { const char* e = getenv("TNQS_SWEEP"); return e && e[0] == '0'; }
-static int sweep_lag() { const char* e = getenv("TNQS_SWEEP_LAG"); return e ? std::max(1, atoi(e)) : 12; }
+static int sweep_lag() { const char* e = getenv("TNQS_SWEEP_LAG"); return e ? std::max(1, atoi(e)) : 8; }
 static int sweep_ring() { const char* e = getenv("TNQS_SWEEP_RING"); return e ? std::max(2, atoi(e)) : 48; }
 
 static int small_chain_N(const tnqs_ctx* c, const Chain& ch) {
@@ -758,6 +780,7 @@ static void run_plan(tnqs_ctx* c, const Plan& p) {
   if (p.sweep) {
     SweepQueue Q; Q.items = p.d_items; Q.n = p.sweep_items; Q.counter = p.d_qctr; Q.slabs = p.d_slab; Q.closes = p.d_dclose;
     Q.chains = p.d_chains; Q.slab_done = p.d_slab_done; Q.chain_done = p.d_chain_done;
+    Q.nchains = (int)p.nchains; Q.ahead = std::max(1, (int)((long long)p.sweep_grid.x * p.nchains / std::max(1, p.sweep_items)));
     if (p.sweepN == 16) LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_sweep<16>, p.sweep_grid, 256, p.sweep_smem, Q);
     else LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_sweep<8>, p.sweep_grid, 256, p.sweep_smem, Q);
     if (p.sweep_commit) LAUNCH(c, TNQS_KC_BP_FINALIZE, k_msg_commit, p.sweep_commit, 128, 0, c->msg_cur, c->msg_stage, c->slot, p.d_commit, c->d_chi);

@@ -384,6 +384,7 @@ struct SweepQueue {
   const SweepChain* chains;
   int* slab_done;         // per chain; reset by the CTA that runs the chain's epilogue
   int* chain_done;        // per chain: epoch + 1 once its message is written
+  int nchains, ahead;     // ahead: chains between an item and the one the same CTA is likely to draw next (L1 prefetch distance)
 };
 
 // The whole CTA waits until chain_done[list[i]] == done_val for the (up to 4) chains of `list` (-1 = none).
@@ -439,27 +440,45 @@ __device__ __forceinline__ void small_chain_body(const SlabDesc& a, const CloseD
   __syncthreads();
 }
 
+// fire-and-forget load: brings the line into L1 without ever waiting for it
+__device__ __forceinline__ void touch_l1(const void* p) {
+  unsigned tmp;
+  asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(tmp) : "l"(p));
+}
+
 template <int N>
 __global__ void __launch_bounds__(256, 2) k_bp_sweep(const SweepQueue Q) {
   extern __shared__ cplx dyn[];
   cplx* msm = dyn + SlabCfg<N>::SLAB3;
   __shared__ int s_item, s_epoch;
-  __shared__ int2 s_entry;
-  if (threadIdx.x == 0) s_epoch = *(volatile int*)(Q.counter + 4);
+  const int tid = threadIdx.x;
+  if (tid == 0) { s_epoch = *(volatile int*)(Q.counter + 4); s_item = atomicAdd(Q.counter, 1); }
   __syncthreads();
   const int done_val = s_epoch + 1;
   for (;;) {
-    if (threadIdx.x == 0) { const int i = atomicAdd(Q.counter, 1); s_item = i; s_entry = Q.items[min(i, Q.n - 1)]; }
-    __syncthreads();
     const int it = s_item;
     if (it >= Q.n) break;
-    const int2 e = s_entry;
+    const int2 e = Q.items[it];
+    const int ci = e.x >= 0 ? e.x : ~e.x;
+    // what this CTA will most likely need for its next item (gridDim.x items further down the queue), into L1 while this
+    // item computes: queue entries, dependency lists and descriptors are constant during a sweep
+    if (tid < 8) {
+      const int itn = min(it + (int)gridDim.x, Q.n - 1);
+      const int cn = min(ci + Q.ahead, Q.nchains - 1);
+      if (tid == 0) touch_l1(Q.items + itn);
+      else if (tid == 1) touch_l1(Q.chains + cn);
+      else if (tid < 5) touch_l1(reinterpret_cast<const char*>(Q.slabs + cn) + 64 * (tid - 2));
+      else touch_l1(reinterpret_cast<const char*>(Q.closes + cn) + 64 * (tid - 5));
+    }
+    __syncthreads();                                 // everybody has read s_item
     if (e.x >= 0 && e.y >= 0) {
       sweep_wait_chains(Q, Q.chains[e.x].dep, done_val);
       const SlabDesc d = Q.slabs[e.x];
       absorb_slab_item<N, true>(d, e.y, dyn, msm);
+      int nx = 0;
+      if (tid == 0) nx = atomicAdd(Q.counter, 1);                                       // next index: in flight across the barrier
       __syncthreads();                               // the CTA's part of X ...
-      if (threadIdx.x == 0) { __threadfence(); atomicAdd(Q.slab_done + e.x, 1); }     // ... is visible before the slab counter moves
+      if (tid == 0) { __threadfence(); atomicAdd(Q.slab_done + e.x, 1); s_item = nx; } // ... is visible before the slab counter moves
     } else if (e.x >= 0) {
       sweep_wait_chains(Q, Q.chains[e.x].dep, done_val);
       const SlabDesc a = Q.slabs[e.x];
@@ -468,34 +487,37 @@ __global__ void __launch_bounds__(256, 2) k_bp_sweep(const SweepQueue Q) {
       sweep_wait_chains(Q, Q.chains[e.x].war, done_val, 6);
       close_reduce_body(*d.epilogue, dyn, reinterpret_cast<double*>(dyn + N * N));
       __syncthreads();
-      if (threadIdx.x == 0) { __threadfence(); *(volatile int*)(Q.chain_done + e.x) = done_val; }
+      if (tid == 0) { __threadfence(); *(volatile int*)(Q.chain_done + e.x) = done_val; s_item = atomicAdd(Q.counter, 1); }
     } else {
-      const int ci = ~e.x;
       const CloseDmmaDesc d = Q.closes[ci];
-      if (threadIdx.x == 0) {
+      if (tid == 0) {
         const int need = Q.slabs[ci].nslabs;
-        int spins = 0;
-        while (*(volatile int*)(Q.slab_done + ci) < need) {
-          __nanosleep(40);
-          ++spins;
-          if ((spins & 255) == 0) {
-            if (*(volatile int*)(Q.counter + 2)) break;
-            if (spins > (1 << 22)) { atomicExch(Q.counter + 2, 1); break; }
+        if (*(volatile int*)(Q.slab_done + ci) < need) {
+          int spins = 0;
+          while (*(volatile int*)(Q.slab_done + ci) < need) {
+            __nanosleep(32);
+            ++spins;
+            if ((spins & 255) == 0) {
+              if (*(volatile int*)(Q.counter + 2)) break;
+              if (spins > (1 << 22)) { atomicExch(Q.counter + 2, 1); break; }
+            }
           }
+          atomicAdd(Q.counter + 5, spins);
         }
-        if (spins) atomicAdd(Q.counter + 5, spins);
         __threadfence();
       }
       __syncthreads();
       auto hook = [&]() { sweep_wait_chains(Q, Q.chains[ci].war, done_val, 6); };
-      if (close_dmma_item<N>(d, e.y, reinterpret_cast<double*>(dyn), hook)) {
-        __syncthreads();
-        if (threadIdx.x == 0) { __threadfence(); Q.slab_done[ci] = 0; *(volatile int*)(Q.chain_done + ci) = done_val; }
+      const bool last = close_dmma_item<N>(d, e.y, reinterpret_cast<double*>(dyn), hook);
+      if (last) __syncthreads();
+      if (tid == 0) {
+        if (last) { __threadfence(); Q.slab_done[ci] = 0; *(volatile int*)(Q.chain_done + ci) = done_val; }
+        s_item = atomicAdd(Q.counter, 1);
       }
     }
-    __syncthreads();                                 // shared memory, s_item and s_entry are reused by the next item
+    __syncthreads();                                 // shared memory and s_item are reused by the next item
   }
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     const int gone = atomicAdd(Q.counter + 1, 1);
     if (gone == (int)gridDim.x - 1) { Q.counter[0] = 0; Q.counter[1] = 0; Q.counter[4] = done_val; __threadfence(); }
   }

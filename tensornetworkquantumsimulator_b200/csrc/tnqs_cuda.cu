@@ -63,7 +63,7 @@ static void alloc_site(tnqs_ctx* c, int v) {
 
 static void upload_chi(tnqs_ctx* c) {
   if (c->ne == 0) return;
-  CU(cudaMemcpyAsync(c->d_chi, c->chi.data(), sizeof(int) * std::max(c->ne, 1), cudaMemcpyHostToDevice, c->stream));
+  c->h2d(c->d_chi, c->chi.data(), sizeof(int) * std::max(c->ne, 1));
 }
 
 static void reset_messages(tnqs_ctx* c) {
@@ -146,6 +146,7 @@ extern "C" int32_t tnqs_destroy(tnqs_ctx* c) {
   drop_pending_gate(c);
   bp_cache_drop(c);
   c->arena_destroy();
+  c->hstage_destroy();
   for (cplx* p : c->site) if (p) cudaFreeAsync(p, c->stream);
   if (c->msg_cur) cudaFreeAsync(c->msg_cur, c->stream);
   if (c->msg_stage) cudaFreeAsync(c->msg_stage, c->stream);
@@ -417,7 +418,7 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
       c->launches -= per_sweep + 1;                           // the capture pass launched nothing
     }
     BpLoopState hs; hs.tol = o.tolerance; hs.mean = NAN; hs.maxiter = o.maxiter; hs.iter = 0; hs.has_tol = want_diff; hs.pad = 0;
-    CU(cudaMemcpyAsync(pc->d_loop, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream));
+    c->h2d(pc->d_loop, &hs, sizeof(hs));
     CU(cudaGraphLaunch(pc->graph, c->stream));
     CU(cudaMemcpyAsync(&hs, pc->d_loop, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
     c->sync();
@@ -921,7 +922,7 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
       else { s.work = c->talloc<cplx>(wv / sizeof(cplx)); any_global = true; }
       svd_maxn = std::max(svd_maxn, mn);
     }
-    CU(cudaMemcpyAsync(d_gates, hg.data(), hg.size() * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+    c->h2d(d_gates, hg.data(), hg.size() * sizeof(cplx));
   }
   (void)any_global;
   {
@@ -1355,7 +1356,7 @@ static void vertex_scalars_impl(tnqs_ctx* c, cplx* d_vs /* [nv] device */) {
     for (int s = 0; s < d; ++s) { re += h[(size_t)v * dd + s + s * d].x; im += h[(size_t)v * dd + s + s * d].y; }
     t[v] = cmake(re, im);
   }
-  CU(cudaMemcpyAsync(d_vs, t.data(), c->nv * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  c->h2d(d_vs, t.data(), c->nv * sizeof(cplx));
 }
 
 extern "C" int32_t tnqs_vertex_scalars(tnqs_ctx* c, double* out) {

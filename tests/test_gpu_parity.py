@@ -765,7 +765,7 @@ def test_bp_whole_sweep_kernel_matches_level_launches_and_oracle(E, monkeypatch,
     io = {}
     bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=3, tolerance=0.0, edge_sequence=seq, info=io)
     res = {}
-    for name, env in (("level", {"TNQS_SWEEP": "0"}), ("sweep", {"TNQS_SWEEP": "1"}), ("sweep_ring4", {"TNQS_SWEEP": "1", "TNQS_SWEEP_RING": "4", "TNQS_SWEEP_LAG": "2"})):
+    for name, env in (("level", {"TNQS_SWEEP": "0"}), ("sweep", {"TNQS_SWEEP": "1"}), ("sweep_ring4", {"TNQS_SWEEP": "1", "TNQS_SWEEP_RING": "4"})):
         for k, val in env.items():
             monkeypatch.setenv(k, val)
         ie = {}
@@ -782,7 +782,7 @@ def test_bp_whole_sweep_kernel_matches_level_launches_and_oracle(E, monkeypatch,
         assert np.array_equal(res["sweep"][0][k], res["sweep_ring4"][0][k])     # queue shape never changes a result
 
 
-@pytest.mark.parametrize("env", [{}, {"TNQS_SWEEP_JACOBI": "1"}, {"TNQS_SWEEP_JACOBI": "1", "TNQS_SWEEP_RING": "3", "TNQS_SWEEP_LAG": "1"}])
+@pytest.mark.parametrize("env", [{}, {"TNQS_SWEEP_JACOBI": "1"}, {"TNQS_SWEEP_JACOBI": "1", "TNQS_SWEEP_RING": "3"}])
 def test_bp_jacobi_two_sweeps_uniform_chi(E, monkeypatch, env):
     # JACOBI on a lattice that mixes tensor-core chains (degree 3, 4) and generic ones (corners): every message of sweep 2
     # must be computed from the values of sweep 1 (a level that mixes both kinds stages its messages)

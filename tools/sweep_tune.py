@@ -23,8 +23,8 @@ def run(mode, env):
         L.tnqs_sync(h); ts.append(1e3 * (time.perf_counter() - t0) / 4)
     for k in env: os.environ.pop(k)
     return min(ts)
-combos = [{"TNQS_SWEEP": "0"}, {}, {"TNQS_SWEEP_NOWAIT": "1"}, {"TNQS_SWEEP_LAG": "4"}, {"TNQS_SWEEP_LAG": "24"}, {"TNQS_SWEEP_LAG": "40", "TNQS_SWEEP_RING": "96"},
-          {"TNQS_SWEEP_RING": "24"}, {"TNQS_SWEEP_RING": "128"}]
+combos = [{"TNQS_SWEEP": "0"}, {}, {"TNQS_SWEEP_NOWAIT": "1"}, {"TNQS_SWEEP_LAG": "2"}, {"TNQS_SWEEP_LAG": "4"}, {"TNQS_SWEEP_LAG": "6"}, {"TNQS_SWEEP_LAG": "8"}, {"TNQS_SWEEP_LAG": "6", "TNQS_SWEEP_RING": "32"}, {"TNQS_SWEEP_LAG": "6", "TNQS_SWEEP_RING": "96"}]
+os.environ["TNQS_SWEEP_JACOBI"] = "1"
 for mode in ("reference", "jacobi"):
     for env in combos:
         sys.stderr.write(f"--- {mode} {env}\n"); sys.stderr.flush()
