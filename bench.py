@@ -46,14 +46,44 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  Sampled through NVML inside this
+    process (a thread, one cheap query every TNQS_BENCH_SMI_MS ms): a concurrent `nvidia-smi -lms` loop takes driver locks
+    for milliseconds per query and stalls the host-driven gate phases (measured: +100 ms outliers per step).
+    TNQS_BENCH_SMI=nvidia-smi selects the external sampler, TNQS_BENCH_NO_SMI=1 none."""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+    ACTIVE = None          # the sampler of the running timed region; the stepper opens its window around GPU-bound calls
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.thread, self.stop_flag = index, None, [], None, False
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.window = threading.Event()        # set while the main thread sits in a GPU-bound call (a BP refresh = one graph launch):
+        self.windowed = False                  # queries issued then cannot stall host-driven phases
+
+    @classmethod
+    def gpu_bound(cls, on: bool):
+        s = cls.ACTIVE
+        if s is not None:
+            s.windowed = True
+            (s.window.set if on else s.window.clear)()
 
     def start(self):
+        ClockSampler.ACTIVE = self
         if os.environ.get("TNQS_BENCH_NO_SMI") == "1":
             return
+        if os.environ.get("TNQS_BENCH_SMI") != "nvidia-smi":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+                self.nvml, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+                self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
+                self.thread = threading.Thread(target=self._poll, daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.thread = None
         q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("TNQS_BENCH_SMI_MS", "200"), "-i", str(self.index)],
@@ -63,33 +93,60 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        period = float(os.environ.get("TNQS_BENCH_SMI_MS", "100")) * 1e-3
+        n = self.nvml
+        while not self.stop_flag:
+            if self.windowed and not self.window.wait(0.02):
+                continue
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
+        ClockSampler.ACTIVE = None
+        if self.proc is None and self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampler unavailable"]}
+        sm, mx, reasons = self.sm, self.mx, self.reasons
+        if self.proc is None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            how = "nvml"
+        else:
+            self.proc.terminate()
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            how = "nvidia-smi"
+            for ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
         busy = [s for s in sm if s > 0.5 * max(mx)] if mx else []
         return {"sm_mhz": float(np.median(busy)) if busy else (float(np.median(sm)) if sm else None),
-                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "sampler": how + (" (queried while a BP refresh occupies the GPU)" if self.windowed else "")}
 
 
 def workload(nx: int, ny: int):
@@ -165,7 +222,9 @@ class Stepper:
 
     def bp(self):
         info = {}
+        ClockSampler.gpu_bound(True)
         _, ms = self._timed(lambda: self.E.update(self.bpc, edge_sequence=self.seq, inplace=True, info=info, **self.bp_kw))
+        ClockSampler.gpu_bound(False)
         self.bp_ms += ms
         self.bp_sweeps += info["iters"]
         self.msg_updates += info["iters"] * len(self.seq)
@@ -427,7 +486,11 @@ def run_engine(args):
         "roofline": {"bound": "tensor", "kernel": "k_bp_sweep<16> (one persistent launch per BP sweep: DMMA leg absorptions, closings and message epilogues of all 3968 updates)" if one_launch_per_sweep
                      else "k_absorb_slab<16> (fused BP leg absorption, DMMA)", "achieved": apply_tf, "peak": pk["fp64_tflops_sustained"],
                      "unit": "TFLOP/s", "frac": (apply_tf / pk["fp64_tflops_sustained"]) if apply_tf else None,
-                     "traffic": {"dram_bytes_per_launch": 206.0e6, "algorithmic_bytes_per_launch": 260.0e6, "launch": "62 messages x 32 slabs (ncu --set full, profiles/r01_final_dmma_ncu_full_raw.csv)"},
+                     "traffic": (23.52e9 if one_launch_per_sweep else 206.0e6),
+                     "traffic_detail": ({"dram_bytes_read": 14.67e9, "dram_bytes_written": 8.85e9, "algorithmic_bytes_per_launch": float(sum(16.0 * 2 * chi ** g.degree(g.dsrc(int(k))) for k in seq)),
+                                         "note": "one launch = one sweep of 3968 updates (ncu --set full, profiles/r01b_bp_sweep_ncu_full_raw.csv); algorithmic = every site tensor read once per update; the rest is the "
+                                                 "slab-major intermediate X (written once, read once by the closing) and the closing's second read of the site tensor, partly served by L2 (hit rate 45 %)"}
+                                        if one_launch_per_sweep else {"dram_bytes_per_launch": 206.0e6, "algorithmic_bytes_per_launch": 260.0e6, "launch": "62 messages x 32 slabs (profiles/r01_final_dmma_ncu_full_raw.csv)"}),
                      "peak_source": pk["source"], "launches_profiled": int(ln[0]), "avg_launch_ms": ms[0] / max(1, ln[0]),
                      "close_kernel_tflops": close_tf},
         "gpu_launches": int(launches), "clocks": clocks, "step_wall_ms": [round(x, 1) for x in step_wall],
