@@ -275,9 +275,12 @@ def run_distributed(args, torch, dist, rank, world, local):
     lib.check(psi._h.ptr, lib.load().tnqs_set_partition(psi._h.ptr, lib.ptr_i32(ow), rank))
     comp = P.EngineCompute(bpc, dev)
     slot = chi * chi
+    # boundary messages: written by the BP kernels straight into the neighbour's buffer (peer memory over NVLink, CUDA IPC);
+    # TNQS_BENCH_HALO=nccl selects the pack / send / recv / unpack exchange instead
+    p2p = None if os.environ.get("TNQS_BENCH_HALO") == "nccl" else P.halo_setup_p2p(lg, comp, dist, rank, world)
     kw = dict(maxdim=chi, cutoff=1e-10, normalize_tensors=True)
     owned_v = [v for v in range(lg.g.nv) if lg.owned[v]]
-    P.update_distributed(lg, comp, dist, slot, torch, dev, maxiter=10)
+    P.update_distributed(lg, comp, dist, slot, torch, dev, maxiter=10, p2p_bytes=p2p)
     E.rescale(bpc, inplace=True)
     P.halo_exchange(lg, comp, dist, slot, torch, dev)
     batches = [P.class_gates_local(gg, lg, owner, rank, grp) for grp in groups]
@@ -298,7 +301,7 @@ def run_distributed(args, torch, dist, rank, world, local):
 
     def bp():
         info = {}
-        _, dt = dev_timed(lambda: P.update_distributed(lg, comp, dist, slot, torch, dev, maxiter=25, tolerance=1e-8, info=info))
+        _, dt = dev_timed(lambda: P.update_distributed(lg, comp, dist, slot, torch, dev, maxiter=25, tolerance=1e-8, info=info, p2p_bytes=p2p))
         stats["bp_s"] += dt
         stats["msg"] += info["iters"] * info["messages_per_sweep"]; stats["sweeps"] += info["iters"]; stats["halo"] += info["halo_bytes"]
 
@@ -347,7 +350,8 @@ def run_distributed(args, torch, dist, rank, world, local):
         "dtype": "c128 (f64 arithmetic)", "data": "synthetic",
         "config": {"workload": f"C2 strips: {nx}x{ny * world} open grid cut into {world} row strips of {nx}x{ny} (one per GPU), random TNS chi={chi} "
                                "ComplexF64; step = one Trotter layer (Rx,Rz + 4 Rzz classes, maxdim=chi, cutoff=1e-10), lazy BP refreshes "
-                               "(<=25 sweeps, tol 1e-8) + <Z>", "chi": chi, "bp_mode": "JACOBI + NCCL halo exchange and all-reduce per sweep",
+                               "(<=25 sweeps, tol 1e-8) + <Z>", "chi": chi, "bp_mode": ("JACOBI; boundary messages stored by the message epilogue straight into the neighbour GPU's buffer (P2P over NVLink, CUDA IPC), one all-reduce (= barrier) + commit per sweep"
+                                                    if p2p is not None else "JACOBI + NCCL halo exchange (pack / send / recv / unpack) and all-reduce per sweep"),
                    "gates": "cut-crossing gates via R-factor exchange (tnqs_apply_2site_begin/_end)", "per_rank_lattice": f"{nx}x{ny}",
                    "l2": f"inputs larger than L2: state {psi_bytes(G.named_grid((nx, ny)), chi) / 2**30:.2f} GiB per GPU vs 126 MB"},
         "gates": {"metric": "two_site_gate_applications_per_sec", "value": gates2 / gate_s, "unit": "gates/s"},

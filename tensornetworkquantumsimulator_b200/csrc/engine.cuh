@@ -43,6 +43,15 @@ struct tnqs_ctx {
   int* d_chi = nullptr;                            // device copy of chi[ne]
   int* d_status = nullptr;
   std::vector<int> owner; int rank = 0; bool partitioned = false;
+  // peer-memory halo (tnqs_halo_*): this handle's receive buffer (2 parity halves of halo_nrecv slots, cudaMalloc'ed so it
+  // can be exported over CUDA IPC), the opened buffers of the peers, and where each owned -> ghost message goes
+  cplx* halo_in = nullptr; int halo_nrecv = 0; std::vector<int> halo_recv_k;
+  struct HaloPeer { cplx* base = nullptr; int nrecv = 0; bool ipc = false; };
+  std::vector<HaloPeer> halo_peers;
+  struct HaloRoute { int peer = -1; int slot = 0; };
+  std::vector<HaloRoute> halo_route;               // per directed edge (peer < 0: not a boundary message)
+  int* d_halo_parity = nullptr; int halo_sweeps = 0; int halo_last_parity = 0;
+  bool halo_active() const { return partitioned && !halo_route.empty() && d_halo_parity; }
   std::string err;
   long long launches = 0;
   long long bp_sweeps = 0, bp_msg_updates = 0;
@@ -200,6 +209,7 @@ struct Chain {
   int close_leg = -1;                // bond leg to close on; -1 = close on the site index (RDM)
   // output
   cplx* dst = nullptr;               // n x n result (BP: staged message)
+  cplx* dst2 = nullptr; long long dst2_pstride = 0; const int* parity = nullptr;     // peer-memory halo copy (CloseReduceDesc)
   const cplx* prev = nullptr; double* diff = nullptr; int bp_mode = 0, normalize = 0, hermitize = 0;
   int commit_k = -1;                 // BP: directed edge to commit at the end of the level
   int split_cap = 16;                // upper bound of the split-K factor of the closing (a property of the request, never of the batch)
@@ -512,6 +522,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         // an un-chunked level has finished all its reads when its epilogue runs: write the message in place, no commit pass
         if (ch.commit_k >= 0 && !level_staged) r.dst = c->msg(ch.commit_k);
         r.mode = ch.bp_mode; r.normalize = ch.normalize; r.hermitize = ch.hermitize;
+        r.dst2 = ch.dst2; r.dst2_pstride = ch.dst2_pstride; r.parity = ch.parity;
         if (fast[j]) frd.push_back(r); else rd.push_back(r);
         maxnn = std::max(maxnn, (size_t)n * n);
         REQUIRE(n <= 64, TNQS_ERR_UNSUPPORTED, "closing extent > 64 is not supported");
@@ -681,6 +692,7 @@ static bool build_sweep_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>&
     r.partial = b.partial; r.nsplit = nsplit[i]; r.n = N; r.np = N;
     r.dst = in_place ? c->msg(ch.commit_k) : ch.dst; r.prev = ch.prev; r.diff = ch.diff;
     r.mode = ch.bp_mode; r.normalize = ch.normalize; r.hermitize = ch.hermitize;
+    r.dst2 = ch.dst2; r.dst2_pstride = ch.dst2_pstride; r.parity = ch.parity;
     if (!in_place) commit.push_back(ch.commit_k);
     plan.flops += 8.0 * (double)c->site_n[v] * N * (F + 1);
   }

@@ -200,6 +200,11 @@ struct CloseReduceDesc {
   double* diff;              // BP: where 1 - fidelity goes (may be null)
   int mode;                  // 0 = store, 1 = BP message epilogue
   int normalize, hermitize;
+  // peer-memory halo (vertex-partitioned BP): a boundary message is also written straight into the halo buffer of the
+  // GPU that owns its destination vertex (a P2P store over NVLink); the buffer is double-buffered by sweep parity
+  cplx* dst2 = nullptr;            // slot in the peer's halo buffer for parity 0, or null
+  long long dst2_pstride = 0;      // elements between the two parity halves of the peer's buffer
+  const int* parity = nullptr;     // device word holding the parity of the running sweep
 };
 
 // Sum of the split partials + epilogue of one item, executed by a whole CTA (any block size); fixed summation order
@@ -236,6 +241,7 @@ __device__ __forceinline__ void close_reduce_body(const CloseReduceDesc& d, cplx
     inv = cmake(sre / den, -sim / den);
   }
   double dre = 0, dim = 0, na = 0, nb = 0;
+  cplx* const dst2 = d.dst2 ? d.dst2 + (size_t)(*d.parity) * d.dst2_pstride : nullptr;
   for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
     cplx v = gsm[idx];
     if (d.hermitize) {
@@ -246,6 +252,7 @@ __device__ __forceinline__ void close_reduce_body(const CloseReduceDesc& d, cplx
     v = cmul(v, inv);
     cplx p = d.diff ? __ldcg(d.prev + idx) : cmake(0, 0);      // read before the store: dst may alias prev (in-place message update)
     d.dst[idx] = v;
+    if (dst2) dst2[idx] = v;
     if (d.diff) {
       dre += v.x * p.x + v.y * p.y;      // conj(v) * p
       dim += v.x * p.y - v.y * p.x;

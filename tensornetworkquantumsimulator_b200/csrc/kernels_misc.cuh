@@ -111,6 +111,12 @@ __global__ void k_msg_commit(cplx* cur, const cplx* stage, long long slot, const
   const cplx* s = stage + (size_t)k * slot; cplx* c = cur + (size_t)k * slot;
   for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) c[idx] = s[idx];
 }
+// commit the messages the peers wrote into this handle's halo buffer: cur[list[j]] <- halo[j]
+__global__ void k_halo_commit(cplx* cur, const cplx* halo, long long slot, const int* list, const int* chi) {
+  const int k = list[blockIdx.x], n = chi[k >> 1];
+  const cplx* s = halo + (size_t)blockIdx.x * slot; cplx* c = cur + (size_t)k * slot;
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) c[idx] = s[idx];
+}
 __global__ void k_halo_pack(const cplx* slab, long long slot, const int* list, cplx* buf, int pack) {
   int k = list[blockIdx.x];
   cplx* s = const_cast<cplx*>(slab) + (size_t)k * slot; cplx* b = buf + (size_t)blockIdx.x * slot;

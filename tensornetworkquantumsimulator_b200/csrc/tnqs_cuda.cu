@@ -147,6 +147,9 @@ extern "C" int32_t tnqs_destroy(tnqs_ctx* c) {
   bp_cache_drop(c);
   c->arena_destroy();
   c->hstage_destroy();
+  for (auto& p : c->halo_peers) if (p.base && p.ipc) cudaIpcCloseMemHandle(p.base);
+  if (c->halo_in) cudaFree(c->halo_in);
+  if (c->d_halo_parity) cudaFreeAsync(c->d_halo_parity, c->stream);
   for (cplx* p : c->site) if (p) cudaFreeAsync(p, c->stream);
   if (c->msg_cur) cudaFreeAsync(c->msg_cur, c->stream);
   if (c->msg_stage) cudaFreeAsync(c->msg_stage, c->stream);
@@ -368,6 +371,11 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
         }
         ch.dst = c->msg_st(k); ch.prev = c->msg(k); ch.diff = want_diff ? nc->d_diff + i : nullptr;
         ch.bp_mode = 1; ch.normalize = o.normalize; ch.hermitize = o.hermitize; ch.commit_k = k;
+        if (c->halo_active() && c->halo_route[k].peer >= 0) {
+          const tnqs_ctx::HaloRoute& rt = c->halo_route[k];
+          const tnqs_ctx::HaloPeer& pr = c->halo_peers[rt.peer];
+          ch.dst2 = pr.base + (size_t)rt.slot * c->slot; ch.dst2_pstride = (long long)pr.nrecv * c->slot; ch.parity = c->d_halo_parity;
+        }
         ch.split_cap = o.mode == TNQS_BP_JACOBI ? 4 : bp_level_split_cap();      // whole-sweep launches want long CTAs, level launches more
         levels[level[i]].push_back(ch);
       }
@@ -385,6 +393,13 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
     c->bp_cache = nc; pc = nc;
   }
   const Plan& plan = pc->plan;
+  if (c->halo_active()) {
+    // one parity per call: the partitioned driver runs one sweep per call and commits the received half after its barrier
+    REQUIRE(o.maxiter == 1 && o.mode == TNQS_BP_JACOBI, TNQS_ERR_INVALID_ARG, "peer-memory halo: run one JACOBI sweep per call (then barrier + tnqs_halo_commit)");
+    const int par = c->halo_sweeps & 1;
+    c->h2d(c->d_halo_parity, &par, sizeof(int));
+    c->halo_last_parity = par; ++c->halo_sweeps;
+  }
   double* d_diff = pc->d_diff;
   double* d_sum = d_diff + nseq;
   int it = 0; double mean = NAN;
@@ -1531,6 +1546,71 @@ static int32_t halo(tnqs_ctx* c, int32_t n, const int32_t* k, void* buf, int pac
 }
 extern "C" int32_t tnqs_halo_pack(tnqs_ctx* c, int32_t n, const int32_t* k, void* dev_buf) { return halo(c, n, k, dev_buf, 1); }
 extern "C" int32_t tnqs_halo_unpack(tnqs_ctx* c, int32_t n, const int32_t* k, const void* dev_buf) { return halo(c, n, k, const_cast<void*>(dev_buf), 0); }
+
+// ---- peer-memory halo -------------------------------------------------------------------------------------------
+extern "C" int32_t tnqs_halo_alloc(tnqs_ctx* c, int32_t nrecv, const int32_t* recv_k, void* ipc_handle, void** dev_ptr) {
+  API_BEGIN(c)
+  REQUIRE(nrecv >= 0 && (nrecv == 0 || recv_k), TNQS_ERR_INVALID_ARG, "tnqs_halo_alloc: null argument");
+  for (int i = 0; i < nrecv; ++i) REQUIRE(recv_k[i] >= 0 && recv_k[i] < 2 * c->ne, TNQS_ERR_INVALID_ARG, "tnqs_halo_alloc: directed edge out of range");
+  c->sync();
+  if (c->halo_in) { cudaFree(c->halo_in); c->halo_in = nullptr; }
+  c->halo_nrecv = nrecv; c->halo_recv_k.assign(recv_k, recv_k + nrecv);
+  const size_t bytes = std::max<size_t>(1, (size_t)2 * nrecv * c->slot) * sizeof(cplx);
+  CU(cudaMalloc((void**)&c->halo_in, bytes));                         // not from the stream-ordered pool: IPC needs a plain allocation
+  CU(cudaMemsetAsync(c->halo_in, 0, bytes, c->stream));
+  if (!c->d_halo_parity) { c->d_halo_parity = (int*)c->dalloc(sizeof(int)); CU(cudaMemsetAsync(c->d_halo_parity, 0, sizeof(int), c->stream)); }
+  c->halo_sweeps = 0; c->halo_last_parity = 0;
+  if (ipc_handle) { cudaIpcMemHandle_t h; CU(cudaIpcGetMemHandle(&h, c->halo_in)); memcpy(ipc_handle, &h, sizeof(h)); }
+  if (dev_ptr) *dev_ptr = c->halo_in;
+  c->sync();
+  API_END(c)
+}
+extern "C" int32_t tnqs_halo_peer(tnqs_ctx* c, int32_t peer, const void* ipc_handle, void* raw_dev_ptr, int32_t peer_nrecv) {
+  API_BEGIN(c)
+  REQUIRE(peer >= 0 && peer < 4096 && peer_nrecv >= 0 && ((ipc_handle != nullptr) != (raw_dev_ptr != nullptr)), TNQS_ERR_INVALID_ARG,
+          "tnqs_halo_peer: give either an IPC handle (another process) or a device pointer (same process)");
+  if ((int)c->halo_peers.size() <= peer) c->halo_peers.resize(peer + 1);
+  tnqs_ctx::HaloPeer& p = c->halo_peers[peer];
+  if (p.base && p.ipc) cudaIpcCloseMemHandle(p.base);
+  p = tnqs_ctx::HaloPeer();
+  if (ipc_handle) {
+    cudaIpcMemHandle_t h; memcpy(&h, ipc_handle, sizeof(h));
+    void* q = nullptr;
+    CU(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+    p.base = (cplx*)q; p.ipc = true;
+  } else {
+    p.base = (cplx*)raw_dev_ptr; p.ipc = false;
+  }
+  p.nrecv = peer_nrecv;
+  ++c->state_version;                                                 // cached BP plans hold the old destinations
+  API_END(c)
+}
+extern "C" int32_t tnqs_halo_route(tnqs_ctx* c, int32_t n, const int32_t* k, const int32_t* peer, const int32_t* peer_slot) {
+  API_BEGIN(c)
+  REQUIRE(n >= 0 && (n == 0 || (k && peer && peer_slot)), TNQS_ERR_INVALID_ARG, "tnqs_halo_route: null argument");
+  c->halo_route.assign(2 * c->ne, tnqs_ctx::HaloRoute());
+  for (int i = 0; i < n; ++i) {
+    REQUIRE(k[i] >= 0 && k[i] < 2 * c->ne, TNQS_ERR_INVALID_ARG, "tnqs_halo_route: directed edge out of range");
+    REQUIRE(peer[i] >= 0 && peer[i] < (int)c->halo_peers.size() && c->halo_peers[peer[i]].base, TNQS_ERR_INVALID_ARG, "tnqs_halo_route: peer buffer not opened (tnqs_halo_peer)");
+    REQUIRE(peer_slot[i] >= 0 && peer_slot[i] < c->halo_peers[peer[i]].nrecv, TNQS_ERR_INVALID_ARG, "tnqs_halo_route: slot outside the peer's buffer");
+    c->halo_route[k[i]].peer = peer[i]; c->halo_route[k[i]].slot = peer_slot[i];
+  }
+  if (n == 0) c->halo_route.clear();
+  ++c->state_version;
+  API_END(c)
+}
+extern "C" int32_t tnqs_halo_commit(tnqs_ctx* c) {
+  API_BEGIN(c)
+  REQUIRE(c->halo_in || c->halo_nrecv == 0, TNQS_ERR_INVALID_ARG, "tnqs_halo_commit: no halo buffer (tnqs_halo_alloc)");
+  if (c->halo_nrecv > 0) {
+    int* dk = c->upload(c->halo_recv_k);
+    const cplx* src = c->halo_in + (size_t)c->halo_last_parity * c->halo_nrecv * c->slot;
+    LAUNCH(c, TNQS_KC_BP_FINALIZE, k_halo_commit, c->halo_nrecv, 128, 0, c->msg_cur, src, c->slot, dk, c->d_chi);
+  }
+  c->sync();
+  c->release_temps();
+  API_END(c)
+}
 extern "C" int32_t tnqs_set_partition(tnqs_ctx* c, const int32_t* owner, int32_t rank) {
   if (!c) return TNQS_ERR_INVALID_ARG;
   if (!owner) { c->partitioned = false; c->owner.clear(); return TNQS_OK; }

@@ -5,8 +5,12 @@ set of vertices (contiguous row strips for grids) and builds a *local* graph = o
 neighbours across a cut) + every edge with an owned endpoint, keeping the global relative order of vertices and edges so
 the canonical leg order of owned site tensors is unchanged.  Ghost sites carry no data; only messages cross a cut:
 
-  * BP runs in JACOBI mode: all owned-source messages from the previous sweep's values (one C-ABI call), then ONE halo
-    exchange of the boundary message slots (grouped send/recv) and ONE all-reduce of the diff sum per sweep.
+  * BP runs in JACOBI mode: all owned-source messages from the previous sweep's values (one C-ABI call).  With the
+    peer-memory halo (`halo_setup_p2p`, the default on GPUs) the message epilogue of that call stores every boundary
+    message straight into the receive buffer of the neighbouring GPU (P2P store over NVLink, buffers opened through CUDA
+    IPC), so a sweep ends with ONE all-reduce of the diff sum - which is also the barrier after which each rank commits
+    what it received (`tnqs_halo_commit`).  Without it (gloo tests, `p2p=False`): one grouped send/recv of the boundary
+    slots per sweep (`halo_exchange`).
     The reference's sequential order is a diagonal wavefront that would idle most strips, so distributed
     results are compared with the single-GPU engine in JACOBI mode (same kernels, batch-independent reduction splits).
   * Two-site gates whose vertices are both owned run locally.  A gate across a cut is listed by BOTH ranks: each absorbs
@@ -116,6 +120,33 @@ class EngineCompute(LocalCompute):
         self.torch.cuda.current_stream().synchronize()
         lib.check(self.bpc.psi._h.ptr, lib.load().tnqs_halo_unpack(self.bpc.psi._h.ptr, len(k), lib.ptr_i32(k), buf.data_ptr()))
 
+    # ---- peer-memory halo (tnqs_halo_*) ----
+    def halo_alloc(self, recv_k):
+        """Receive buffer for the ghost -> owned messages `recv_k`; returns (64-byte CUDA IPC handle, device pointer)."""
+        import ctypes as C
+        from . import lib
+        k = lib.i32(recv_k)
+        handle = (C.c_char * 64)()
+        ptr = C.c_void_p()
+        lib.check(self.bpc.psi._h.ptr, lib.load().tnqs_halo_alloc(self.bpc.psi._h.ptr, len(k), lib.ptr_i32(k), C.cast(handle, C.c_void_p), C.byref(ptr)))
+        return bytes(handle), int(ptr.value or 0)
+
+    def halo_peer(self, peer, nrecv, handle=None, ptr=None):
+        import ctypes as C
+        from . import lib
+        hb = C.create_string_buffer(handle, 64) if handle is not None else None
+        lib.check(self.bpc.psi._h.ptr, lib.load().tnqs_halo_peer(self.bpc.psi._h.ptr, int(peer), C.cast(hb, C.c_void_p) if hb is not None else None,
+                                                                  C.c_void_p(ptr) if ptr is not None else None, int(nrecv)))
+
+    def halo_route(self, ks, peers, slots):
+        from . import lib
+        k, p, s = lib.i32(ks), lib.i32(peers), lib.i32(slots)
+        lib.check(self.bpc.psi._h.ptr, lib.load().tnqs_halo_route(self.bpc.psi._h.ptr, len(k), lib.ptr_i32(k), lib.ptr_i32(p), lib.ptr_i32(s)))
+
+    def halo_commit(self):
+        from . import lib
+        lib.check(self.bpc.psi._h.ptr, lib.load().tnqs_halo_commit(self.bpc.psi._h.ptr))
+
 
 def halo_exchange(lgraph: LocalGraph, comp: LocalCompute, dist, slot: int, torch, device) -> int:
     """Send every owned->ghost message to the ghost's owner, receive every ghost->owned message.  Returns bytes sent."""
@@ -136,12 +167,68 @@ def halo_exchange(lgraph: LocalGraph, comp: LocalCompute, dist, slot: int, torch
     return sent
 
 
+def halo_layout(lgraph: LocalGraph):
+    """Order of this rank's receive buffer: neighbours ascending, inside a neighbour ascending global directed edge id (the
+    order of lgraph.recv[r]).  Returns (local directed edges per slot, {neighbour: first slot})."""
+    recv_k, first = [], {}
+    for r in sorted(lgraph.recv):
+        first[r] = len(recv_k)
+        recv_k += [int(k) for k in lgraph.recv[r]]
+    return np.array(recv_k, dtype=np.int32), first
+
+
+def halo_routes(lgraph: LocalGraph, rank: int, first_of_peer: Dict[int, Dict[int, int]]):
+    """Where each owned -> ghost message goes: (local directed edges, peer ranks, slots in the peer's receive buffer).
+    first_of_peer[p][rank] = first slot of this rank's block in p's buffer; both sides order a block by global directed id."""
+    ks, peers, slots = [], [], []
+    for p in sorted(lgraph.send):
+        base = first_of_peer[p][rank]
+        for j, k in enumerate(lgraph.send[p]):
+            ks.append(int(k)); peers.append(int(p)); slots.append(base + j)
+    return ks, peers, slots
+
+
+def halo_setup_p2p(lgraph: LocalGraph, comp, dist, rank: int, world: int) -> int:
+    """Open the peer-memory halo between the processes of one node: every rank allocates its receive buffer, the CUDA IPC
+    handles and buffer layouts are all-gathered, and each rank routes its boundary messages into its neighbours'
+    buffers.  Returns the bytes this rank writes to peers per sweep."""
+    recv_k, first = halo_layout(lgraph)
+    handle, _ = comp.halo_alloc(recv_k)
+    mine = {"handle": handle, "nrecv": int(len(recv_k)), "first": {int(r): int(o) for r, o in first.items()}}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    for p in sorted(lgraph.send):
+        comp.halo_peer(p, everyone[p]["nrecv"], handle=everyone[p]["handle"])
+    ks, peers, slots = halo_routes(lgraph, rank, {p: everyone[p]["first"] for p in lgraph.send})
+    comp.halo_route(ks, peers, slots)
+    dist.barrier()
+    return 16 * comp.slot * len(ks)
+
+
 def update_distributed(lgraph: LocalGraph, comp: LocalCompute, dist, slot: int, torch, device, maxiter: int, tolerance=None,
-                       info: dict | None = None) -> None:
-    """JACOBI BP over the partitioned network: per sweep one local C-ABI call, one halo exchange, one all-reduce."""
+                       info: dict | None = None, p2p_bytes: int | None = None) -> None:
+    """JACOBI BP over the partitioned network.  p2p_bytes = None: per sweep one local C-ABI call, one halo exchange
+    (send/recv), one all-reduce.  p2p_bytes = result of halo_setup_p2p: the sweep's kernels write the boundary messages
+    into the neighbours' buffers themselves; per sweep one C-ABI call, one all-reduce (the barrier), one commit."""
     g = lgraph.g
     seq = np.array([k for k in range(2 * g.ne) if lgraph.owned[g.dsrc(k)]], dtype=np.int32)
     iters, mean, halo_bytes = 0, float("nan"), 0
+    if p2p_bytes is not None:
+        for it in range(1, maxiter + 1):
+            iters = it
+            s = comp.sweep(seq, tolerance is not None)
+            t = torch.tensor([s, float(len(seq))], dtype=torch.float64, device=device)
+            dist.all_reduce(t)                                  # convergence sum; also: every rank's stores have landed
+            t = t.cpu()
+            comp.halo_commit()
+            halo_bytes += p2p_bytes
+            if tolerance is not None:
+                mean = float(t[0] / t[1])
+                if mean <= tolerance:
+                    break
+        if info is not None:
+            info.update(iters=iters, mean_diff=mean, halo_bytes=halo_bytes, messages_per_sweep=len(seq))
+        return
     for it in range(1, maxiter + 1):
         iters = it
         s = comp.sweep(seq, tolerance is not None)

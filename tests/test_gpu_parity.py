@@ -809,3 +809,40 @@ def test_set_get_sites_batched_round_trip(E):
     assert np.array_equal(psi[4], 2 * ts[4]) and np.array_equal(psi[0], 3 * ts[0]) and np.array_equal(psi[1], ts[1])
     with pytest.raises(Exception):
         psi.set_sites([1], [ts[4]])                          # wrong element count
+
+
+@pytest.mark.parametrize("shape,chi", [((4, 6), 3), ((4, 6), 8)])
+def test_partitioned_bp_peer_memory_halo_matches_single_handle(E, shape, chi):
+    # two "ranks" inside one process: each handle's BP kernels store their boundary messages straight into the other
+    # handle's receive buffer (tnqs_halo_alloc / _peer / _route), the parity halves alternate, tnqs_halo_commit installs them
+    import torch
+    from tensornetworkquantumsimulator_b200 import parallel as P
+    g = G.named_grid(shape)
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=chi, seed=17)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    owner, lgs, caches = _two_rank_setup(E, g, psi_o, chi)
+    ref = E.update(to_engine(psi_o, chi_cap=chi), maxiter=3, edge_sequence=np.arange(2 * g.ne), mode="jacobi")
+    comps = [P.EngineCompute(c, torch.device("cuda", 0)) for c in caches]
+    layouts = [P.halo_layout(lg) for lg in lgs]
+    ptrs = [comps[r].halo_alloc(layouts[r][0])[1] for r in range(2)]
+    for r in range(2):
+        comps[r].halo_peer(1 - r, len(layouts[1 - r][0]), ptr=ptrs[1 - r])
+        comps[r].halo_route(*P.halo_routes(lgs[r], r, {1 - r: layouts[1 - r][1]}))
+    for sweep in range(3):
+        sums = []
+        for r in range(2):
+            lg = lgs[r]
+            seq = np.array([k for k in range(2 * lg.g.ne) if lg.owned[lg.g.dsrc(k)]], dtype=np.int32)
+            sums.append(comps[r].sweep(seq, True))
+        for r in range(2):                                   # after the barrier of a real run
+            comps[r].halo_commit()
+    for r in range(2):
+        lg = lgs[r]
+        for lk in range(2 * lg.g.ne):
+            if not lg.owned[lg.g.dsrc(lk)] and not lg.owned[lg.g.ddst(lk)]:
+                continue
+            kg = 2 * int(lg.l2g_e[lk // 2]) + (lk & 1)
+            assert np.array_equal(E.message(caches[r], lk), E.message(ref, kg)), "peer-memory halo must reproduce the single-handle JACOBI result bitwise"
+    with pytest.raises(Exception):                           # a handle with an open halo runs one JACOBI sweep per call
+        E.update(caches[0], maxiter=2, edge_sequence=np.array([0], dtype=np.int32), mode="jacobi", inplace=True)
