@@ -301,7 +301,9 @@ def run_distributed(args, torch, dist, rank, world, local):
 
     def bp():
         info = {}
+        ClockSampler.gpu_bound(True)
         _, dt = dev_timed(lambda: P.update_distributed(lg, comp, dist, slot, torch, dev, maxiter=25, tolerance=1e-8, info=info, p2p_bytes=p2p))
+        ClockSampler.gpu_bound(False)
         stats["bp_s"] += dt
         stats["msg"] += info["iters"] * info["messages_per_sweep"]; stats["sweeps"] += info["iters"]; stats["halo"] += info["halo_bytes"]
 
