@@ -186,19 +186,23 @@ int32_t tnqs_message_slab(tnqs_ctx* ctx, void** dev_ptr, int64_t* n_complex, int
 /* Gather / scatter the listed directed-edge slots to / from a contiguous device buffer (halo pack / unpack). */
 int32_t tnqs_halo_pack(tnqs_ctx* ctx, int32_t n, const int32_t* k, void* dev_buf);
 int32_t tnqs_halo_unpack(tnqs_ctx* ctx, int32_t n, const int32_t* k, const void* dev_buf);
-/* Peer-memory halo: the boundary exchange fused into the BP kernels.  Every handle owns a receive buffer of 2 x nrecv
- * message slots (two sweep parities); slot j belongs to the ghost -> owned message recv_k[j].  A rank opens the buffers
- * of its neighbours (CUDA IPC handle for another process of the node, plain device pointer inside one process) and
- * routes each owned -> ghost message k to (peer, slot).  From then on the message epilogue of a JACOBI sweep
- * (tnqs_bp_update with maxiter = 1) stores such a message both locally and, with a P2P store over NVLink, in the
- * peer's buffer - no pack / send / recv / unpack step.  After the sweep the ranks meet at one barrier (the all-reduce
- * of the convergence sum) and each calls tnqs_halo_commit, which copies the half written in that sweep into its
- * message slab; the next sweep writes the other half, so no second barrier is needed.
- * ipc_handle: 64 bytes (cudaIpcMemHandle_t), may be NULL; dev_ptr: the buffer's device address, may be NULL. */
-int32_t tnqs_halo_alloc(tnqs_ctx* ctx, int32_t nrecv, const int32_t* recv_k, void* ipc_handle, void** dev_ptr);
+/* Peer-memory halo: the boundary exchange and the convergence all-reduce of vertex-partitioned BP, fused into the kernels.
+ * Every handle owns one block (cudaMalloc, exportable over CUDA IPC) = a signal area + a receive buffer of 2 x nrecv message
+ * slots (two sweep parities); slot j belongs to the ghost -> owned message recv_k[j].  A rank opens the blocks of ALL other
+ * ranks (CUDA IPC handle for another process of the node, plain device pointer inside one process) and routes each
+ * owned -> ghost message k to (peer, slot).  From then on tnqs_bp_update (JACOBI) needs no host-side exchange:
+ *   - the message epilogue stores a boundary message both locally and, with a P2P store over NVLink, in the peer's buffer;
+ *   - every sweep ends with a device-side barrier: each rank stores {epoch, diff sum, message count} into every rank's signal
+ *     area and waits for the others' (k_halo_barrier), sums in rank order (the same bits everywhere) and commits the half
+ *     of its receive buffer written in that sweep; the next sweep writes the other half;
+ *   - the "stop when the global mean diff <= tolerance or after maxiter sweeps" test runs on the device (WHILE graph node), so a
+ *     whole refresh is ONE graph launch per rank.  All ranks must call tnqs_bp_update together with the same options; iters and
+ *     mean_diff are global.  A rank that never arrives makes the others fail with TNQS_ERR_NCCL after a time-out (no hang).
+ * ipc_handle: 64 bytes (cudaIpcMemHandle_t), may be NULL; dev_ptr: the block's device address, may be NULL. */
+int32_t tnqs_halo_alloc(tnqs_ctx* ctx, int32_t world, int32_t nrecv, const int32_t* recv_k, void* ipc_handle, void** dev_ptr);
 int32_t tnqs_halo_peer(tnqs_ctx* ctx, int32_t peer, const void* ipc_handle, void* raw_dev_ptr, int32_t peer_nrecv);
 int32_t tnqs_halo_route(tnqs_ctx* ctx, int32_t n, const int32_t* k, const int32_t* peer, const int32_t* peer_slot);
-int32_t tnqs_halo_commit(tnqs_ctx* ctx);
+int32_t tnqs_halo_close(tnqs_ctx* ctx);
 /* Restrict BP updates / diffs to messages whose source vertex has owner[v] == rank (NULL => own everything). */
 int32_t tnqs_set_partition(tnqs_ctx* ctx, const int32_t* owner, int32_t rank);
 

@@ -43,15 +43,18 @@ struct tnqs_ctx {
   int* d_chi = nullptr;                            // device copy of chi[ne]
   int* d_status = nullptr;
   std::vector<int> owner; int rank = 0; bool partitioned = false;
-  // peer-memory halo (tnqs_halo_*): this handle's receive buffer (2 parity halves of halo_nrecv slots, cudaMalloc'ed so it
-  // can be exported over CUDA IPC), the opened buffers of the peers, and where each owned -> ghost message goes
-  cplx* halo_in = nullptr; int halo_nrecv = 0; std::vector<int> halo_recv_k;
-  struct HaloPeer { cplx* base = nullptr; int nrecv = 0; bool ipc = false; };
+  // peer-memory halo (tnqs_halo_*): one cudaMalloc'ed block per handle (exportable over CUDA IPC) = [signal area of the
+  // device-side barrier | receive buffer: 2 parity halves of halo_nrecv message slots]; the opened blocks of the other ranks;
+  // where each owned -> ghost message goes
+  char* halo_block = nullptr; cplx* halo_in = nullptr; int halo_nrecv = 0; std::vector<int> halo_recv_k; int* d_halo_recv_k = nullptr;
+  struct HaloPeer { char* block = nullptr; cplx* base = nullptr; int nrecv = 0; bool ipc = false; };
   std::vector<HaloPeer> halo_peers;
   struct HaloRoute { int peer = -1; int slot = 0; };
   std::vector<HaloRoute> halo_route;               // per directed edge (peer < 0: not a boundary message)
-  int* d_halo_parity = nullptr; int halo_sweeps = 0; int halo_last_parity = 0;
-  bool halo_active() const { return partitioned && !halo_route.empty() && d_halo_parity; }
+  int* d_halo_parity = nullptr;                    // device words: [0] half the next sweep writes to, [1] sweeps completed (epoch)
+  double* d_halo_out = nullptr;                    // device: [0] global diff sum, [1] global message count of the last sweep
+  int halo_world = 0;
+  bool halo_active() const { return partitioned && halo_world > 1 && halo_block && d_halo_parity; }
   std::string err;
   long long launches = 0;
   long long bp_sweeps = 0, bp_msg_updates = 0;
@@ -151,7 +154,22 @@ struct tnqs_ctx {
       CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
     }
   }
-  void hstage_destroy() { if (hstage) cudaFreeHost(hstage); hstage = nullptr; hstage_size = 0; hstage_off = 0; }
+  void hstage_destroy() { if (hstage) cudaFreeHost(hstage); hstage = nullptr; hstage_size = 0; hstage_off = 0; if (hret) cudaFreeHost(hret); hret = nullptr; }
+  // Small device -> host reads (loop state, status word, counters) land in a pinned page and the call then waits on the
+  // stream: a copy into pageable memory blocks inside the driver, which serialises every other thread of the process - fatal
+  // when those threads drive other handles whose kernels this handle's kernels wait for (device-side halo barrier).
+  char* hret = nullptr;
+  void d2h_small(void* dst, const void* dev_src, size_t bytes) {
+    if (!hret && cudaHostAlloc((void**)&hret, 4096, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); hret = nullptr; }
+    if (hret && bytes <= 4096) {
+      CU(cudaMemcpyAsync(hret, dev_src, bytes, cudaMemcpyDeviceToHost, stream));
+      sync();
+      memcpy(dst, hret, bytes);
+    } else {
+      CU(cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToHost, stream));
+      sync();
+    }
+  }
   template <typename T> T* upload(const std::vector<T>& v) {
     T* p = talloc<T>(std::max<size_t>(v.size(), 1));
     h2d(p, v.data(), v.size() * sizeof(T));
@@ -186,8 +204,7 @@ struct tnqs_ctx {
   }
   int read_status() {
     int st = 0;
-    CU(cudaMemcpyAsync(&st, d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    sync();
+    d2h_small(&st, d_status, sizeof(int));
     if (st) { int z = 0; h2d(d_status, &z, sizeof(int)); }
     return st;
   }

@@ -111,11 +111,64 @@ __global__ void k_msg_commit(cplx* cur, const cplx* stage, long long slot, const
   const cplx* s = stage + (size_t)k * slot; cplx* c = cur + (size_t)k * slot;
   for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) c[idx] = s[idx];
 }
-// commit the messages the peers wrote into this handle's halo buffer: cur[list[j]] <- halo[j]
-__global__ void k_halo_commit(cplx* cur, const cplx* halo, long long slot, const int* list, const int* chi) {
+// commit the messages the peers wrote into this handle's halo buffer: cur[list[j]] <- halo[half][j], half = the parity the
+// sweep that just ended wrote to (= *next_parity ^ 1: the barrier has already advanced the word)
+__global__ void k_halo_commit(cplx* cur, const cplx* halo, long long slot, int nrecv, const int* list, const int* chi, const int* next_parity) {
   const int k = list[blockIdx.x], n = chi[k >> 1];
-  const cplx* s = halo + (size_t)blockIdx.x * slot; cplx* c = cur + (size_t)k * slot;
+  const int half = (*next_parity) ^ 1;
+  const cplx* s = halo + ((size_t)half * nrecv + blockIdx.x) * slot; cplx* c = cur + (size_t)k * slot;
   for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) c[idx] = s[idx];
+}
+
+// Device-side barrier + all-reduce of one BP sweep of a vertex-partitioned run (one CTA, thread t talks to rank t).
+// Every rank owns a signal area of world x 2 slots of 4 doubles {epoch, diff sum, message count, -}; rank r writes its
+// slot [r][epoch & 1] in EVERY rank's area with P2P stores over NVLink (payload, system fence, epoch), then waits until
+// all slots of its own area carry the epoch: at that point every peer has finished the sweep, so the boundary messages
+// its kernels stored in this rank's halo buffer (earlier in its stream) have landed.  The global sum is taken in rank
+// order - the same bits on every rank, so all ranks take the same "stop / continue" decision in their WHILE graph.
+// Slots alternate with the epoch parity because a peer may already be one sweep ahead.  The spin has a time-out.
+constexpr int HALO_MAX_WORLD = 64;
+constexpr int HALO_SIG_DOUBLES = HALO_MAX_WORLD * 2 * 4;
+struct HaloBarrierArgs {
+  double* sig[HALO_MAX_WORLD];     // signal area of every rank (own area at [rank])
+  int world, rank;
+  int* epoch;                      // device word: sweeps completed by this handle since the halo was opened
+  int* next_parity;                // device word: half of the halo buffers the NEXT sweep writes to
+  const double* local_sum;         // may be null (no convergence test): contributes 0
+  double local_cnt;
+  double* out_sum; double* out_cnt;
+  int* status; int timeout_bit;
+};
+__global__ void __launch_bounds__(HALO_MAX_WORLD) k_halo_barrier(const HaloBarrierArgs a) {
+  const int t = threadIdx.x;
+  const int e = *a.epoch + 1, p = e & 1;
+  __shared__ int s_bad;
+  if (t == 0) s_bad = 0;
+  __syncthreads();
+  if (t < a.world) {
+    double* dst = a.sig[t] + (size_t)(a.rank * 2 + p) * 4;
+    dst[1] = a.local_sum ? *a.local_sum : 0.0;
+    dst[2] = a.local_cnt;
+    __threadfence_system();
+    *(volatile double*)dst = (double)e;
+    __threadfence_system();
+    const volatile double* mine = a.sig[a.rank] + (size_t)(t * 2 + p) * 4;
+    long long spins = 0;
+    while (*mine != (double)e) {
+      __nanosleep(200);
+      if (++spins > (1ll << 23)) { s_bad = 1; break; }              // a few seconds: a peer never arrived
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (t == 0) {
+    double s = 0, c = 0;
+    const double* mine = a.sig[a.rank];
+    for (int r = 0; r < a.world; ++r) { s += __ldcg(mine + (size_t)(r * 2 + p) * 4 + 1); c += __ldcg(mine + (size_t)(r * 2 + p) * 4 + 2); }
+    *a.out_sum = s; *a.out_cnt = c;
+    *a.epoch = e; *a.next_parity = (e + 1) & 1;
+    if (s_bad) atomicOr(a.status, a.timeout_bit);
+  }
 }
 __global__ void k_halo_pack(const cplx* slab, long long slot, const int* list, cplx* buf, int pack) {
   int k = list[blockIdx.x];

@@ -10,7 +10,7 @@
 #define TNQS_EPS 2.220446049250313e-16
 #define TNQS_JACOBI_MAX_SWEEPS 60
 
-enum { ST_NEG_EIG = 1, ST_NO_CONV = 2, ST_RANK_CAP = 4 };
+enum { ST_NEG_EIG = 1, ST_NO_CONV = 2, ST_RANK_CAP = 4, ST_HALO_TIMEOUT = 8 };
 
 // Round-robin (circle method) pairing: N even players, round s in [0, N-1), pair i in [0, N/2).
 __device__ __forceinline__ void rr_pair(int N, int s, int i, int& p, int& q) {

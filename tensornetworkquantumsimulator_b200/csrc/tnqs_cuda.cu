@@ -6,6 +6,7 @@
 
 static thread_local std::string g_create_error;
 static void bp_cache_drop(tnqs_ctx* c);
+static void halo_release(tnqs_ctx* c);
 static void drop_pending_gate(tnqs_ctx* c);
 
 #define API_BEGIN(ctx) if (!(ctx)) return TNQS_ERR_INVALID_ARG; try { CU(cudaSetDevice((ctx)->device));
@@ -147,9 +148,10 @@ extern "C" int32_t tnqs_destroy(tnqs_ctx* c) {
   bp_cache_drop(c);
   c->arena_destroy();
   c->hstage_destroy();
-  for (auto& p : c->halo_peers) if (p.base && p.ipc) cudaIpcCloseMemHandle(p.base);
-  if (c->halo_in) cudaFree(c->halo_in);
+  halo_release(c);
   if (c->d_halo_parity) cudaFreeAsync(c->d_halo_parity, c->stream);
+  if (c->d_halo_out) cudaFreeAsync(c->d_halo_out, c->stream);
+  if (c->d_halo_recv_k) cudaFreeAsync(c->d_halo_recv_k, c->stream);
   for (cplx* p : c->site) if (p) cudaFreeAsync(p, c->stream);
   if (c->msg_cur) cudaFreeAsync(c->msg_cur, c->stream);
   if (c->msg_stage) cudaFreeAsync(c->msg_stage, c->stream);
@@ -271,10 +273,12 @@ extern "C" int32_t tnqs_reset_messages(tnqs_ctx* c) { API_BEGIN(c) reset_message
 // "stop when the mean diff <= tolerance or after maxiter sweeps" test (abstractbeliefpropagationcache.jl:201-218) runs on
 // the device and no host round trip separates two sweeps.
 struct BpLoopState { double tol; double mean; int maxiter; int iter; int has_tol; int pad; };
-__global__ void k_bp_loop_check(cudaGraphConditionalHandle h, BpLoopState* st, const double* d_sum, int nseq) {
+// d_cnt: device denominator (the global message count of a partitioned run) or null (nseq)
+__global__ void k_bp_loop_check(cudaGraphConditionalHandle h, BpLoopState* st, const double* d_sum, int nseq, const double* d_cnt, const int* status) {
   const int it = ++st->iter;
   bool more = it < st->maxiter;
-  if (st->has_tol) { const double mean = *d_sum / nseq; st->mean = mean; if (mean <= st->tol) more = false; }
+  if (st->has_tol) { const double mean = *d_sum / (d_cnt ? *d_cnt : (double)nseq); st->mean = mean; if (mean <= st->tol) more = false; }
+  if (status && (*status & ST_HALO_TIMEOUT)) more = false;
   cudaGraphSetConditional(h, more ? 1u : 0u);
 }
 struct BpPlanCache {
@@ -371,7 +375,7 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
         }
         ch.dst = c->msg_st(k); ch.prev = c->msg(k); ch.diff = want_diff ? nc->d_diff + i : nullptr;
         ch.bp_mode = 1; ch.normalize = o.normalize; ch.hermitize = o.hermitize; ch.commit_k = k;
-        if (c->halo_active() && c->halo_route[k].peer >= 0) {
+        if (c->halo_active() && !c->halo_route.empty() && c->halo_route[k].peer >= 0) {
           const tnqs_ctx::HaloRoute& rt = c->halo_route[k];
           const tnqs_ctx::HaloPeer& pr = c->halo_peers[rt.peer];
           ch.dst2 = pr.base + (size_t)rt.slot * c->slot; ch.dst2_pstride = (long long)pr.nrecv * c->slot; ch.parity = c->d_halo_parity;
@@ -393,17 +397,33 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
     c->bp_cache = nc; pc = nc;
   }
   const Plan& plan = pc->plan;
-  if (c->halo_active()) {
-    // one parity per call: the partitioned driver runs one sweep per call and commits the received half after its barrier
-    REQUIRE(o.maxiter == 1 && o.mode == TNQS_BP_JACOBI, TNQS_ERR_INVALID_ARG, "peer-memory halo: run one JACOBI sweep per call (then barrier + tnqs_halo_commit)");
-    const int par = c->halo_sweeps & 1;
-    c->h2d(c->d_halo_parity, &par, sizeof(int));
-    c->halo_last_parity = par; ++c->halo_sweeps;
+  // vertex-partitioned run with an open peer-memory halo: every sweep ends with the device-side barrier / all-reduce and the
+  // commit of what the peers stored, inside the same graph - a whole refresh is one launch per rank, no host round trip
+  const bool halo = c->halo_active();
+  REQUIRE(!halo || o.mode == TNQS_BP_JACOBI, TNQS_ERR_INVALID_ARG, "peer-memory halo: partitioned BP runs in JACOBI mode");
+  HaloBarrierArgs hb;
+  if (halo) {
+    memset(&hb, 0, sizeof(hb));
+    hb.world = c->halo_world; hb.rank = c->rank;
+    for (int r = 0; r < c->halo_world; ++r) {
+      hb.sig[r] = r == c->rank ? (double*)c->halo_block : (double*)c->halo_peers[r].block;
+      REQUIRE(hb.sig[r], TNQS_ERR_INVALID_ARG, "peer-memory halo: the block of every other rank must be opened (tnqs_halo_peer)");
+    }
+    hb.epoch = c->d_halo_parity + 1; hb.next_parity = c->d_halo_parity;
+    hb.local_sum = want_diff ? pc->d_diff + nseq : nullptr; hb.local_cnt = (double)nseq;
+    hb.out_sum = c->d_halo_out; hb.out_cnt = c->d_halo_out + 1;
+    hb.status = c->d_status; hb.timeout_bit = ST_HALO_TIMEOUT;
   }
+  auto end_of_sweep = [&]() {                                  // after the sweep's kernels and k_sum
+    if (!halo) return;
+    LAUNCH(c, TNQS_KC_BP_FINALIZE, k_halo_barrier, 1, HALO_MAX_WORLD, 0, hb);
+    if (c->halo_nrecv > 0)
+      LAUNCH(c, TNQS_KC_BP_FINALIZE, k_halo_commit, c->halo_nrecv, 128, 0, c->msg_cur, c->halo_in, c->slot, c->halo_nrecv, c->d_halo_recv_k, c->d_chi, c->d_halo_parity);
+  };
   double* d_diff = pc->d_diff;
   double* d_sum = d_diff + nseq;
   int it = 0; double mean = NAN;
-  const bool use_graph = !c->profiling && !graphs_disabled() && (plan.nlaunch >= 8 || plan.sweep);
+  const bool use_graph = !c->profiling && !graphs_disabled() && (plan.nlaunch >= 8 || plan.sweep || halo);
   const int per_sweep = plan.nlaunch + (want_diff ? 1 : 0);
   if (use_graph) {
     if (!pc->graph) {
@@ -423,41 +443,41 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
         try {
           run_plan(c, plan);
           if (want_diff) LAUNCH(c, TNQS_KC_BP_FINALIZE, k_sum, 1, 1024, 0, d_diff, nseq, d_sum);
-          LAUNCH(c, TNQS_KC_BP_FINALIZE, k_bp_loop_check, 1, 1, 0, h, pc->d_loop, d_sum, nseq);
+          end_of_sweep();
+          LAUNCH(c, TNQS_KC_BP_FINALIZE, k_bp_loop_check, 1, 1, 0, h, pc->d_loop, halo ? (const double*)c->d_halo_out : (const double*)d_sum, nseq,
+                 halo ? (const double*)(c->d_halo_out + 1) : (const double*)nullptr, (const int*)c->d_status);
         } catch (...) { cudaStreamEndCapture(c->stream, &cap); throw; }
         CU(cudaStreamEndCapture(c->stream, &cap));
         cudaError_t ge = cudaGraphInstantiate(&pc->graph, g, 0);
         if (ge != cudaSuccess) throw TnqsError(TNQS_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ge));
       } catch (...) { cudaGraphDestroy(g); throw; }
       cudaGraphDestroy(g);
-      c->launches -= per_sweep + 1;                           // the capture pass launched nothing
+      c->launches -= per_sweep + 1 + (halo ? 1 + (c->halo_nrecv > 0 ? 1 : 0) : 0);       // the capture pass launched nothing
     }
     BpLoopState hs; hs.tol = o.tolerance; hs.mean = NAN; hs.maxiter = o.maxiter; hs.iter = 0; hs.has_tol = want_diff; hs.pad = 0;
     c->h2d(pc->d_loop, &hs, sizeof(hs));
     CU(cudaGraphLaunch(pc->graph, c->stream));
-    CU(cudaMemcpyAsync(&hs, pc->d_loop, sizeof(hs), cudaMemcpyDeviceToHost, c->stream));
-    c->sync();
+    c->d2h_small(&hs, pc->d_loop, sizeof(hs));
     it = hs.iter; mean = want_diff ? hs.mean : NAN;
-    c->launches += (long long)it * (per_sweep + 1);
+    c->launches += (long long)it * (per_sweep + 1 + (halo ? 1 + (c->halo_nrecv > 0 ? 1 : 0) : 0));
     c->bp_sweeps += it; c->bp_msg_updates += (long long)it * nseq;
   } else {
     for (it = 1; it <= o.maxiter; ++it) {
       run_plan(c, plan);
       if (want_diff) LAUNCH(c, TNQS_KC_BP_FINALIZE, k_sum, 1, 1024, 0, d_diff, nseq, d_sum);
+      end_of_sweep();
       ++c->bp_sweeps; c->bp_msg_updates += nseq;
       if (want_diff) {
-        double s = 0;
-        CU(cudaMemcpyAsync(&s, d_sum, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        c->sync();
-        mean = s / nseq;
+        double s[2] = {0, (double)nseq};
+        c->d2h_small(s, halo ? c->d_halo_out : d_sum, (halo ? 2 : 1) * sizeof(double));
+        mean = s[0] / s[1];
         if (mean <= o.tolerance) break;
       }
     }
   }
   if (plan.d_qctr) {
     int q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    CU(cudaMemcpyAsync(q, plan.d_qctr, (plan.sweep ? 8 : 4) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    c->sync();
+    c->d2h_small(q, plan.d_qctr, (plan.sweep ? 8 : 4) * sizeof(int));
     if (q[3] || q[5] || q[6]) {
       static const char* dbg = getenv("TNQS_DEBUG_QUEUE");
       if (dbg) fprintf(stderr, "[tnqs] %s wait polls in %d sweeps: producers/ring %d, slabs %d, readers %d\n", plan.sweep ? "k_bp_sweep" : "k_bp_level", it, q[3], q[5], q[6]);
@@ -466,6 +486,7 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
     }
     if (q[2]) { bp_cache_drop(c); throw TnqsError(TNQS_ERR_CUDA, "internal: a BP queue wait timed out"); }
   }
+  if (halo) { const int st = c->read_status(); if (st & ST_HALO_TIMEOUT) { bp_cache_drop(c); throw TnqsError(TNQS_ERR_NCCL, "peer-memory halo: a rank did not reach the sweep barrier (time-out)"); } }
   if (it > o.maxiter) it = o.maxiter;
   if (iters_out) *iters_out = it;
   if (mean_out) *mean_out = mean;
@@ -1548,67 +1569,80 @@ extern "C" int32_t tnqs_halo_pack(tnqs_ctx* c, int32_t n, const int32_t* k, void
 extern "C" int32_t tnqs_halo_unpack(tnqs_ctx* c, int32_t n, const int32_t* k, const void* dev_buf) { return halo(c, n, k, const_cast<void*>(dev_buf), 0); }
 
 // ---- peer-memory halo -------------------------------------------------------------------------------------------
-extern "C" int32_t tnqs_halo_alloc(tnqs_ctx* c, int32_t nrecv, const int32_t* recv_k, void* ipc_handle, void** dev_ptr) {
+static void halo_release(tnqs_ctx* c) {
+  for (auto& p : c->halo_peers) if (p.block && p.ipc) cudaIpcCloseMemHandle(p.block);
+  c->halo_peers.clear(); c->halo_route.clear();
+  if (c->halo_block) cudaFree(c->halo_block);
+  c->halo_block = nullptr; c->halo_in = nullptr; c->halo_nrecv = 0; c->halo_world = 0;
+}
+extern "C" int32_t tnqs_halo_alloc(tnqs_ctx* c, int32_t world, int32_t nrecv, const int32_t* recv_k, void* ipc_handle, void** dev_ptr) {
   API_BEGIN(c)
-  REQUIRE(nrecv >= 0 && (nrecv == 0 || recv_k), TNQS_ERR_INVALID_ARG, "tnqs_halo_alloc: null argument");
+  REQUIRE(c->partitioned, TNQS_ERR_INVALID_ARG, "tnqs_halo_alloc: set the partition first (tnqs_set_partition)");
+  REQUIRE(world >= 1 && world <= HALO_MAX_WORLD && c->rank < world && nrecv >= 0 && (nrecv == 0 || recv_k), TNQS_ERR_INVALID_ARG, "tnqs_halo_alloc: bad argument");
   for (int i = 0; i < nrecv; ++i) REQUIRE(recv_k[i] >= 0 && recv_k[i] < 2 * c->ne, TNQS_ERR_INVALID_ARG, "tnqs_halo_alloc: directed edge out of range");
   c->sync();
-  if (c->halo_in) { cudaFree(c->halo_in); c->halo_in = nullptr; }
-  c->halo_nrecv = nrecv; c->halo_recv_k.assign(recv_k, recv_k + nrecv);
-  const size_t bytes = std::max<size_t>(1, (size_t)2 * nrecv * c->slot) * sizeof(cplx);
-  CU(cudaMalloc((void**)&c->halo_in, bytes));                         // not from the stream-ordered pool: IPC needs a plain allocation
-  CU(cudaMemsetAsync(c->halo_in, 0, bytes, c->stream));
-  if (!c->d_halo_parity) { c->d_halo_parity = (int*)c->dalloc(sizeof(int)); CU(cudaMemsetAsync(c->d_halo_parity, 0, sizeof(int), c->stream)); }
-  c->halo_sweeps = 0; c->halo_last_parity = 0;
-  if (ipc_handle) { cudaIpcMemHandle_t h; CU(cudaIpcGetMemHandle(&h, c->halo_in)); memcpy(ipc_handle, &h, sizeof(h)); }
-  if (dev_ptr) *dev_ptr = c->halo_in;
+  bp_cache_drop(c);
+  halo_release(c);
+  c->halo_world = world; c->halo_nrecv = nrecv; c->halo_recv_k.assign(recv_k, recv_k + nrecv);
+  const size_t sig_bytes = HALO_SIG_DOUBLES * sizeof(double);
+  const size_t bytes = sig_bytes + std::max<size_t>(1, (size_t)2 * nrecv * c->slot) * sizeof(cplx);
+  CU(cudaMalloc((void**)&c->halo_block, bytes));                      // not from the stream-ordered pool: IPC needs a plain allocation
+  CU(cudaMemsetAsync(c->halo_block, 0, bytes, c->stream));
+  c->halo_in = (cplx*)(c->halo_block + sig_bytes);
+  if (!c->d_halo_parity) { c->d_halo_parity = (int*)c->dalloc(2 * sizeof(int)); c->d_halo_out = (double*)c->dalloc(2 * sizeof(double)); }
+  const int init[2] = {1, 0};                                         // the first sweep is epoch 1: it writes half 1
+  c->h2d(c->d_halo_parity, init, sizeof(init));
+  CU(cudaMemsetAsync(c->d_halo_out, 0, 2 * sizeof(double), c->stream));
+  if (c->d_halo_recv_k) { c->dfree(c->d_halo_recv_k); c->d_halo_recv_k = nullptr; }
+  c->d_halo_recv_k = (int*)c->dalloc(std::max(1, nrecv) * sizeof(int));
+  c->h2d(c->d_halo_recv_k, c->halo_recv_k.data(), nrecv * sizeof(int));
+  c->halo_peers.assign(world, tnqs_ctx::HaloPeer());
+  if (ipc_handle) { cudaIpcMemHandle_t h; CU(cudaIpcGetMemHandle(&h, c->halo_block)); memcpy(ipc_handle, &h, sizeof(h)); }
+  if (dev_ptr) *dev_ptr = c->halo_block;
   c->sync();
   API_END(c)
 }
 extern "C" int32_t tnqs_halo_peer(tnqs_ctx* c, int32_t peer, const void* ipc_handle, void* raw_dev_ptr, int32_t peer_nrecv) {
   API_BEGIN(c)
-  REQUIRE(peer >= 0 && peer < 4096 && peer_nrecv >= 0 && ((ipc_handle != nullptr) != (raw_dev_ptr != nullptr)), TNQS_ERR_INVALID_ARG,
-          "tnqs_halo_peer: give either an IPC handle (another process) or a device pointer (same process)");
-  if ((int)c->halo_peers.size() <= peer) c->halo_peers.resize(peer + 1);
+  REQUIRE(c->halo_block && peer >= 0 && peer < c->halo_world && peer != c->rank && peer_nrecv >= 0 && ((ipc_handle != nullptr) != (raw_dev_ptr != nullptr)),
+          TNQS_ERR_INVALID_ARG, "tnqs_halo_peer: after tnqs_halo_alloc; give either an IPC handle (another process) or a device pointer (same process)");
+  bp_cache_drop(c);
   tnqs_ctx::HaloPeer& p = c->halo_peers[peer];
-  if (p.base && p.ipc) cudaIpcCloseMemHandle(p.base);
+  if (p.block && p.ipc) cudaIpcCloseMemHandle(p.block);
   p = tnqs_ctx::HaloPeer();
   if (ipc_handle) {
     cudaIpcMemHandle_t h; memcpy(&h, ipc_handle, sizeof(h));
     void* q = nullptr;
     CU(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
-    p.base = (cplx*)q; p.ipc = true;
+    p.block = (char*)q; p.ipc = true;
   } else {
-    p.base = (cplx*)raw_dev_ptr; p.ipc = false;
+    p.block = (char*)raw_dev_ptr; p.ipc = false;
   }
+  p.base = (cplx*)(p.block + HALO_SIG_DOUBLES * sizeof(double));
   p.nrecv = peer_nrecv;
-  ++c->state_version;                                                 // cached BP plans hold the old destinations
+  ++c->state_version;
   API_END(c)
 }
 extern "C" int32_t tnqs_halo_route(tnqs_ctx* c, int32_t n, const int32_t* k, const int32_t* peer, const int32_t* peer_slot) {
   API_BEGIN(c)
-  REQUIRE(n >= 0 && (n == 0 || (k && peer && peer_slot)), TNQS_ERR_INVALID_ARG, "tnqs_halo_route: null argument");
+  REQUIRE(c->halo_block && n >= 0 && (n == 0 || (k && peer && peer_slot)), TNQS_ERR_INVALID_ARG, "tnqs_halo_route: after tnqs_halo_alloc; null argument");
+  bp_cache_drop(c);
   c->halo_route.assign(2 * c->ne, tnqs_ctx::HaloRoute());
   for (int i = 0; i < n; ++i) {
     REQUIRE(k[i] >= 0 && k[i] < 2 * c->ne, TNQS_ERR_INVALID_ARG, "tnqs_halo_route: directed edge out of range");
-    REQUIRE(peer[i] >= 0 && peer[i] < (int)c->halo_peers.size() && c->halo_peers[peer[i]].base, TNQS_ERR_INVALID_ARG, "tnqs_halo_route: peer buffer not opened (tnqs_halo_peer)");
+    REQUIRE(peer[i] >= 0 && peer[i] < (int)c->halo_peers.size() && c->halo_peers[peer[i]].block, TNQS_ERR_INVALID_ARG, "tnqs_halo_route: peer block not opened (tnqs_halo_peer)");
     REQUIRE(peer_slot[i] >= 0 && peer_slot[i] < c->halo_peers[peer[i]].nrecv, TNQS_ERR_INVALID_ARG, "tnqs_halo_route: slot outside the peer's buffer");
     c->halo_route[k[i]].peer = peer[i]; c->halo_route[k[i]].slot = peer_slot[i];
   }
-  if (n == 0) c->halo_route.clear();
   ++c->state_version;
   API_END(c)
 }
-extern "C" int32_t tnqs_halo_commit(tnqs_ctx* c) {
+extern "C" int32_t tnqs_halo_close(tnqs_ctx* c) {
   API_BEGIN(c)
-  REQUIRE(c->halo_in || c->halo_nrecv == 0, TNQS_ERR_INVALID_ARG, "tnqs_halo_commit: no halo buffer (tnqs_halo_alloc)");
-  if (c->halo_nrecv > 0) {
-    int* dk = c->upload(c->halo_recv_k);
-    const cplx* src = c->halo_in + (size_t)c->halo_last_parity * c->halo_nrecv * c->slot;
-    LAUNCH(c, TNQS_KC_BP_FINALIZE, k_halo_commit, c->halo_nrecv, 128, 0, c->msg_cur, src, c->slot, dk, c->d_chi);
-  }
   c->sync();
-  c->release_temps();
+  bp_cache_drop(c);
+  halo_release(c);
+  ++c->state_version;
   API_END(c)
 }
 extern "C" int32_t tnqs_set_partition(tnqs_ctx* c, const int32_t* owner, int32_t rank) {

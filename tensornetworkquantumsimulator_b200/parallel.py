@@ -5,12 +5,13 @@ set of vertices (contiguous row strips for grids) and builds a *local* graph = o
 neighbours across a cut) + every edge with an owned endpoint, keeping the global relative order of vertices and edges so
 the canonical leg order of owned site tensors is unchanged.  Ghost sites carry no data; only messages cross a cut:
 
-  * BP runs in JACOBI mode: all owned-source messages from the previous sweep's values (one C-ABI call).  With the
-    peer-memory halo (`halo_setup_p2p`, the default on GPUs) the message epilogue of that call stores every boundary
-    message straight into the receive buffer of the neighbouring GPU (P2P store over NVLink, buffers opened through CUDA
-    IPC), so a sweep ends with ONE all-reduce of the diff sum - which is also the barrier after which each rank commits
-    what it received (`tnqs_halo_commit`).  Without it (gloo tests, `p2p=False`): one grouped send/recv of the boundary
-    slots per sweep (`halo_exchange`).
+  * BP runs in JACOBI mode: all owned-source messages from the previous sweep's values.  With the peer-memory halo
+    (`halo_setup_p2p`, the default on GPUs) a whole refresh is ONE C-ABI call = one CUDA-graph launch per rank: the message
+    epilogues store every boundary message straight into the receive buffer of the neighbouring GPU (P2P store over NVLink,
+    blocks opened through CUDA IPC), every sweep ends with a device-side barrier that also all-reduces the diff sum
+    (`k_halo_barrier`: each rank stores its sum into every rank's signal area and waits for the others'), the received half
+    is committed and the convergence test runs on the device.  Without it (gloo tests, `p2p_bytes=None`): per sweep one
+    C-ABI call, one grouped send/recv of the boundary slots (`halo_exchange`) and one all-reduce.
     The reference's sequential order is a diagonal wavefront that would idle most strips, so distributed
     results are compared with the single-GPU engine in JACOBI mode (same kernels, batch-independent reduction splits).
   * Two-site gates whose vertices are both owned run locally.  A gate across a cut is listed by BOTH ranks: each absorbs
@@ -121,14 +122,14 @@ class EngineCompute(LocalCompute):
         lib.check(self.bpc.psi._h.ptr, lib.load().tnqs_halo_unpack(self.bpc.psi._h.ptr, len(k), lib.ptr_i32(k), buf.data_ptr()))
 
     # ---- peer-memory halo (tnqs_halo_*) ----
-    def halo_alloc(self, recv_k):
-        """Receive buffer for the ghost -> owned messages `recv_k`; returns (64-byte CUDA IPC handle, device pointer)."""
+    def halo_alloc(self, world, recv_k):
+        """This rank's halo block for the ghost -> owned messages `recv_k`; returns (64-byte CUDA IPC handle, device pointer)."""
         import ctypes as C
         from . import lib
         k = lib.i32(recv_k)
         handle = (C.c_char * 64)()
         ptr = C.c_void_p()
-        lib.check(self.bpc.psi._h.ptr, lib.load().tnqs_halo_alloc(self.bpc.psi._h.ptr, len(k), lib.ptr_i32(k), C.cast(handle, C.c_void_p), C.byref(ptr)))
+        lib.check(self.bpc.psi._h.ptr, lib.load().tnqs_halo_alloc(self.bpc.psi._h.ptr, int(world), len(k), lib.ptr_i32(k), C.cast(handle, C.c_void_p), C.byref(ptr)))
         return bytes(handle), int(ptr.value or 0)
 
     def halo_peer(self, peer, nrecv, handle=None, ptr=None):
@@ -143,9 +144,11 @@ class EngineCompute(LocalCompute):
         k, p, s = lib.i32(ks), lib.i32(peers), lib.i32(slots)
         lib.check(self.bpc.psi._h.ptr, lib.load().tnqs_halo_route(self.bpc.psi._h.ptr, len(k), lib.ptr_i32(k), lib.ptr_i32(p), lib.ptr_i32(s)))
 
-    def halo_commit(self):
-        from . import lib
-        lib.check(self.bpc.psi._h.ptr, lib.load().tnqs_halo_commit(self.bpc.psi._h.ptr))
+    def refresh(self, seq, maxiter, tolerance):
+        """A whole partitioned BP refresh in one call (needs the peer-memory halo): returns (sweeps, global mean diff)."""
+        info = {}
+        self.E.update(self.bpc, maxiter=maxiter, tolerance=tolerance, edge_sequence=seq, mode="jacobi", inplace=True, info=info)
+        return info["iters"], info["mean_diff"]
 
 
 def halo_exchange(lgraph: LocalGraph, comp: LocalCompute, dist, slot: int, torch, device) -> int:
@@ -189,16 +192,17 @@ def halo_routes(lgraph: LocalGraph, rank: int, first_of_peer: Dict[int, Dict[int
 
 
 def halo_setup_p2p(lgraph: LocalGraph, comp, dist, rank: int, world: int) -> int:
-    """Open the peer-memory halo between the processes of one node: every rank allocates its receive buffer, the CUDA IPC
-    handles and buffer layouts are all-gathered, and each rank routes its boundary messages into its neighbours'
-    buffers.  Returns the bytes this rank writes to peers per sweep."""
+    """Open the peer-memory halo between the processes of one node: every rank allocates its block, the CUDA IPC handles and
+    buffer layouts are all-gathered, every rank opens every other rank's block (the barrier signals go all-to-all) and routes
+    its boundary messages into its neighbours' receive buffers.  Returns the bytes this rank stores in peers per sweep."""
     recv_k, first = halo_layout(lgraph)
-    handle, _ = comp.halo_alloc(recv_k)
+    handle, _ = comp.halo_alloc(world, recv_k)
     mine = {"handle": handle, "nrecv": int(len(recv_k)), "first": {int(r): int(o) for r, o in first.items()}}
     everyone = [None] * world
     dist.all_gather_object(everyone, mine)
-    for p in sorted(lgraph.send):
-        comp.halo_peer(p, everyone[p]["nrecv"], handle=everyone[p]["handle"])
+    for p in range(world):
+        if p != rank:
+            comp.halo_peer(p, everyone[p]["nrecv"], handle=everyone[p]["handle"])
     ks, peers, slots = halo_routes(lgraph, rank, {p: everyone[p]["first"] for p in lgraph.send})
     comp.halo_route(ks, peers, slots)
     dist.barrier()
@@ -208,26 +212,15 @@ def halo_setup_p2p(lgraph: LocalGraph, comp, dist, rank: int, world: int) -> int
 def update_distributed(lgraph: LocalGraph, comp: LocalCompute, dist, slot: int, torch, device, maxiter: int, tolerance=None,
                        info: dict | None = None, p2p_bytes: int | None = None) -> None:
     """JACOBI BP over the partitioned network.  p2p_bytes = None: per sweep one local C-ABI call, one halo exchange
-    (send/recv), one all-reduce.  p2p_bytes = result of halo_setup_p2p: the sweep's kernels write the boundary messages
-    into the neighbours' buffers themselves; per sweep one C-ABI call, one all-reduce (the barrier), one commit."""
+    (send/recv), one all-reduce.  p2p_bytes = result of halo_setup_p2p: the whole refresh is one C-ABI call (one graph launch
+    per rank; boundary stores, barrier, all-reduce and convergence test on the device)."""
     g = lgraph.g
     seq = np.array([k for k in range(2 * g.ne) if lgraph.owned[g.dsrc(k)]], dtype=np.int32)
     iters, mean, halo_bytes = 0, float("nan"), 0
     if p2p_bytes is not None:
-        for it in range(1, maxiter + 1):
-            iters = it
-            s = comp.sweep(seq, tolerance is not None)
-            t = torch.tensor([s, float(len(seq))], dtype=torch.float64, device=device)
-            dist.all_reduce(t)                                  # convergence sum; also: every rank's stores have landed
-            t = t.cpu()
-            comp.halo_commit()
-            halo_bytes += p2p_bytes
-            if tolerance is not None:
-                mean = float(t[0] / t[1])
-                if mean <= tolerance:
-                    break
+        iters, mean = comp.refresh(seq, maxiter, tolerance)
         if info is not None:
-            info.update(iters=iters, mean_diff=mean, halo_bytes=halo_bytes, messages_per_sweep=len(seq))
+            info.update(iters=iters, mean_diff=mean, halo_bytes=iters * p2p_bytes, messages_per_sweep=len(seq))
         return
     for it in range(1, maxiter + 1):
         iters = it

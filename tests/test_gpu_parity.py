@@ -811,38 +811,71 @@ def test_set_get_sites_batched_round_trip(E):
         psi.set_sites([1], [ts[4]])                          # wrong element count
 
 
-@pytest.mark.parametrize("shape,chi", [((4, 6), 3), ((4, 6), 8)])
-def test_partitioned_bp_peer_memory_halo_matches_single_handle(E, shape, chi):
-    # two "ranks" inside one process: each handle's BP kernels store their boundary messages straight into the other
-    # handle's receive buffer (tnqs_halo_alloc / _peer / _route), the parity halves alternate, tnqs_halo_commit installs them
+@pytest.mark.parametrize("shape,chi,world", [((4, 6), 3, 2), ((4, 6), 8, 2), ((3, 8), 4, 4)])
+def test_partitioned_bp_peer_memory_halo_matches_single_handle(E, shape, chi, world):
+    # `world` "ranks" inside one process (one host thread per handle, all on cuda:0): each handle's BP kernels store their
+    # boundary messages straight into the neighbours' receive buffers, every sweep ends with the device-side barrier /
+    # all-reduce, and a whole refresh (fixed sweeps, then run to tolerance) is one call per rank - no host-side exchange
+    import threading
     import torch
-    from tensornetworkquantumsimulator_b200 import parallel as P
+    from tensornetworkquantumsimulator_b200 import parallel as P, lib
     g = G.named_grid(shape)
     psi_o = O.random_tensornetworkstate(g, bond_dimension=chi, seed=17)
     for v in range(g.nv):
         psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
-    owner, lgs, caches = _two_rank_setup(E, g, psi_o, chi)
-    ref = E.update(to_engine(psi_o, chi_cap=chi), maxiter=3, edge_sequence=np.arange(2 * g.ne), mode="jacobi")
+    owner = P.strip_owner(g, world, axis=1)
+    lgs = [P.build_local_graph(g, owner, r) for r in range(world)]
+    caches = []
+    for r, lg in enumerate(lgs):
+        ts = []
+        for lv, gv in enumerate(lg.l2g_v):
+            if lg.owned[lv]:
+                ts.append(psi_o.tensors[int(gv)])
+            else:
+                ts.append(np.zeros([2] + [psi_o.bond_dim(int(lg.l2g_e[e])) for e in lg.g.incident[lv]], dtype=np.complex128))
+        psi = E.TensorNetworkState.from_arrays(lg.g, ts, chi_cap=chi)
+        ow = lib.i32(lg.owner_local)
+        lib.check(psi._h.ptr, lib.load().tnqs_set_partition(psi._h.ptr, lib.ptr_i32(ow), r))
+        caches.append(E.BeliefPropagationCache(psi))
     comps = [P.EngineCompute(c, torch.device("cuda", 0)) for c in caches]
     layouts = [P.halo_layout(lg) for lg in lgs]
-    ptrs = [comps[r].halo_alloc(layouts[r][0])[1] for r in range(2)]
-    for r in range(2):
-        comps[r].halo_peer(1 - r, len(layouts[1 - r][0]), ptr=ptrs[1 - r])
-        comps[r].halo_route(*P.halo_routes(lgs[r], r, {1 - r: layouts[1 - r][1]}))
-    for sweep in range(3):
-        sums = []
-        for r in range(2):
-            lg = lgs[r]
-            seq = np.array([k for k in range(2 * lg.g.ne) if lg.owned[lg.g.dsrc(k)]], dtype=np.int32)
-            sums.append(comps[r].sweep(seq, True))
-        for r in range(2):                                   # after the barrier of a real run
-            comps[r].halo_commit()
-    for r in range(2):
-        lg = lgs[r]
-        for lk in range(2 * lg.g.ne):
-            if not lg.owned[lg.g.dsrc(lk)] and not lg.owned[lg.g.ddst(lk)]:
-                continue
-            kg = 2 * int(lg.l2g_e[lk // 2]) + (lk & 1)
-            assert np.array_equal(E.message(caches[r], lk), E.message(ref, kg)), "peer-memory halo must reproduce the single-handle JACOBI result bitwise"
-    with pytest.raises(Exception):                           # a handle with an open halo runs one JACOBI sweep per call
-        E.update(caches[0], maxiter=2, edge_sequence=np.array([0], dtype=np.int32), mode="jacobi", inplace=True)
+    ptrs = [comps[r].halo_alloc(world, layouts[r][0])[1] for r in range(world)]
+    for r in range(world):
+        for p in range(world):
+            if p != r:
+                comps[r].halo_peer(p, len(layouts[p][0]), ptr=ptrs[p])
+        comps[r].halo_route(*P.halo_routes(lgs[r], r, {p: layouts[p][1] for p in lgs[r].send}))
+    seqs = [np.array([k for k in range(2 * lg.g.ne) if lg.owned[lg.g.dsrc(k)]], dtype=np.int32) for lg in lgs]
+
+    def run(maxiter, tolerance):
+        out, errs = [None] * world, []
+        def work(r):
+            try:
+                out[r] = comps[r].refresh(seqs[r], maxiter, tolerance)
+            except Exception as ex:                              # pragma: no cover
+                errs.append(ex)
+        th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        [t.start() for t in th]; [t.join() for t in th]
+        assert not errs, errs
+        return out
+
+    def compare(ref, bitwise):
+        for r, lg in enumerate(lgs):
+            for lk in range(2 * lg.g.ne):
+                if not lg.owned[lg.g.dsrc(lk)] and not lg.owned[lg.g.ddst(lk)]:
+                    continue
+                kg = 2 * int(lg.l2g_e[lk // 2]) + (lk & 1)
+                if bitwise:
+                    assert np.array_equal(E.message(caches[r], lk), E.message(ref, kg)), "peer-memory halo must reproduce the single-handle JACOBI result bitwise"
+                else:
+                    assert rel(E.message(caches[r], lk), E.message(ref, kg)) < 1e-12
+
+    run(3, None)
+    compare(E.update(to_engine(psi_o, chi_cap=chi), maxiter=3, edge_sequence=np.arange(2 * g.ne), mode="jacobi"), True)
+    # convergence test on the device with the global mean: same sweep count on every rank and as the single handle
+    res = run(200, 1e-10)
+    info = {}
+    ref = E.update(to_engine(psi_o, chi_cap=chi), maxiter=203, tolerance=1e-10, edge_sequence=np.arange(2 * g.ne), mode="jacobi", info=info)
+    assert len({it for it, _ in res}) == 1 and res[0][0] + 3 == info["iters"]
+    assert all(abs(m - info["mean_diff"]) <= 1e-12 * max(1.0, abs(info["mean_diff"])) for _, m in res)
+    compare(ref, False)

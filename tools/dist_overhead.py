@@ -42,18 +42,14 @@ if rank == 0: print("gate class before IPC (ms):", [round(1e3 * x, 1) for x in g
 # ---- peer-memory halo ----
 t0 = time.perf_counter(); p2p = P.halo_setup_p2p(lg, comp, dist, rank, world); torch.cuda.synchronize()
 if rank == 0: print("halo_setup_p2p %.1f ms, bytes to peers per sweep %d" % (1e3 * (time.perf_counter() - t0), p2p), flush=True)
-t = {"sweep": 0.0, "allreduce": 0.0, "commit": 0.0}
-for it in range(12):
+ts = []
+for it in range(4):
     sync(); t0 = time.perf_counter()
-    s = comp.sweep(seq, True)
-    torch.cuda.synchronize(); t1 = time.perf_counter()
-    x = torch.tensor([s, float(len(seq))], dtype=torch.float64, device=dev); dist.all_reduce(x); x = x.cpu()
-    t2 = time.perf_counter()
-    comp.halo_commit()
-    torch.cuda.synchronize(); t3 = time.perf_counter()
-    if it >= 2:
-        t["sweep"] += t1 - t0; t["allreduce"] += t2 - t1; t["commit"] += t3 - t2
-report("peer-memory halo, ms per sweep:", t)
+    comp.refresh(seq, 10, None)                      # one call = one graph launch: 10 sweeps incl. boundary stores, barrier, commit
+    torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) / 10)
+if rank == 0: print("peer-memory halo, device-driven refresh, ms per sweep:", [round(1e3 * x, 3) for x in ts], flush=True)
+it_, mean_ = comp.refresh(seq, 25, 1e-8)
+if rank == 0: print("refresh to 1e-8:", it_, "sweeps, global mean diff", mean_, flush=True)
 g2 = [gate_class() for _ in range(4)]
 if rank == 0: print("gate class after IPC (ms):", [round(1e3 * x, 1) for x in g2], flush=True)
 dist.destroy_process_group()
