@@ -5,8 +5,10 @@ N = 1 (BASELINE.json configs[1], "C2"): 32x32 open grid, random TensorNetworkSta
 seed 1, BP-rescaled).  One step = one Trotter layer: Rx, Rz on every vertex + Rzz in 4 deterministic colour classes with maxdim=16,
 cutoff=1e-10, executed as the exact run / refresh schedule of the reference's apply_gates (lazy BP refreshes with the default
 bp_update_kwargs: <=25 sweeps, tolerance 1e-8, forest-cover edge order, REFERENCE_ORDER level schedule) and <Z> at the centre.
-N > 1: weak scaling, one 32x32 row strip per GPU of a 32x(32 N) lattice; BP in JACOBI mode with one NCCL halo exchange and one
-all-reduce per sweep, gates across a cut through tnqs_apply_2site_begin/_end with one R-factor exchange per colour class.
+N > 1: weak scaling, one 32x32 row strip per GPU of a 32x(32 N) lattice; BP in JACOBI mode, a refresh = one graph launch per rank
+(boundary messages stored into the neighbour GPU's buffer by the message epilogue, device-side barrier + all-reduce over NVLink
+peer memory; TNQS_BENCH_HALO=nccl: pack / send / recv / unpack per sweep instead), gates across a cut through
+tnqs_apply_2site_begin/_end with one R-factor exchange per colour class.
 
 One JSON line on stdout (rank 0).  value = BP edge-message updates / s over the BP phases (device-resident state, CUDA events on
 the engine's stream); `gates` = two-site gate applications / s over the gate phases of the same steps; `e2e` = the same step
@@ -352,7 +354,7 @@ def run_distributed(args, torch, dist, rank, world, local):
         "dtype": "c128 (f64 arithmetic)", "data": "synthetic",
         "config": {"workload": f"C2 strips: {nx}x{ny * world} open grid cut into {world} row strips of {nx}x{ny} (one per GPU), random TNS chi={chi} "
                                "ComplexF64; step = one Trotter layer (Rx,Rz + 4 Rzz classes, maxdim=chi, cutoff=1e-10), lazy BP refreshes "
-                               "(<=25 sweeps, tol 1e-8) + <Z>", "chi": chi, "bp_mode": ("JACOBI; boundary messages stored by the message epilogue straight into the neighbour GPU's buffer (P2P over NVLink, CUDA IPC), one all-reduce (= barrier) + commit per sweep"
+                               "(<=25 sweeps, tol 1e-8) + <Z>", "chi": chi, "bp_mode": ("JACOBI; a refresh is one graph launch per rank: boundary messages stored by the message epilogue straight into the neighbour GPU's buffer (P2P over NVLink, CUDA IPC), device-side barrier + all-reduce + convergence test per sweep"
                                                     if p2p is not None else "JACOBI + NCCL halo exchange (pack / send / recv / unpack) and all-reduce per sweep"),
                    "gates": "cut-crossing gates via R-factor exchange (tnqs_apply_2site_begin/_end)", "per_rank_lattice": f"{nx}x{ny}",
                    "l2": f"inputs larger than L2: state {psi_bytes(G.named_grid((nx, ny)), chi) / 2**30:.2f} GiB per GPU vs 126 MB"},
