@@ -148,6 +148,15 @@ int32_t tnqs_apply_circuit(tnqs_ctx* ctx, int32_t ngates, const int32_t* gate_v,
                            const double* gate_data, const tnqs_apply_opts* aopts,
                            const int32_t* edge_seq, int32_t nseq, const tnqs_bp_opts* bopts,
                            int32_t update_cache, double* truncerr, int32_t* refreshes);
+/* The same, and every listed site tensor is copied to the host as soon as the last gate is done, on a second stream that runs
+ * beside the closing BP refresh (what a caller does next anyway: `ψ[v]` for all v after apply_gates).  fetch_n[i]: capacity
+ * of fetch_data[i] in ComplexF64 on entry, element count written on return (bond dimensions may have changed:
+ * tnqs_get_bond_dims).  Pinned host buffers make the copies asynchronous; pageable ones work but serialise. */
+int32_t tnqs_apply_circuit_fetch(tnqs_ctx* ctx, int32_t ngates, const int32_t* gate_v, const int64_t* gate_off,
+                                 const double* gate_data, const tnqs_apply_opts* aopts,
+                                 const int32_t* edge_seq, int32_t nseq, const tnqs_bp_opts* bopts,
+                                 int32_t update_cache, double* truncerr, int32_t* refreshes,
+                                 int32_t fetch_count, const int32_t* fetch_v, double* const* fetch_data, int64_t* fetch_n);
 
 /* ---- BP measurements ------------------------------------------------------------------------------------------
  * replaces: expect(::Algorithm"bp", cache, obs) for one-site observables (src/expect.jl:58-83): returns the

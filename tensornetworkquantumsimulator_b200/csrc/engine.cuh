@@ -33,6 +33,7 @@ struct tnqs_ctx {
   int num_sms = 148;
   size_t smem_optin = 227 * 1024;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;              // device -> host copies that overlap the closing BP refresh (tnqs_apply_circuit_fetch)
   int nv = 0, ne = 0, chi_cap = 1, dmax = 2;
   std::vector<int> esrc, edst, d, chi;
   std::vector<std::vector<int>> inc;               // v -> incident edge ids ascending

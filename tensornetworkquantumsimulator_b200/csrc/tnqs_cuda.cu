@@ -149,6 +149,7 @@ extern "C" int32_t tnqs_destroy(tnqs_ctx* c) {
   c->arena_destroy();
   c->hstage_destroy();
   halo_release(c);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); c->copy_stream = nullptr; }
   if (c->d_halo_parity) cudaFreeAsync(c->d_halo_parity, c->stream);
   if (c->d_halo_out) cudaFreeAsync(c->d_halo_out, c->stream);
   if (c->d_halo_recv_k) cudaFreeAsync(c->d_halo_recv_k, c->stream);
@@ -1142,11 +1143,10 @@ extern "C" int32_t tnqs_apply_2site_end(tnqs_ctx* c, const void* recv_buf, int32
   API_END(c)
 }
 
-extern "C" int32_t tnqs_apply_circuit(tnqs_ctx* c, int32_t ngates, const int32_t* gate_v, const int64_t* gate_off,
-                                      const double* gate_data, const tnqs_apply_opts* aopts, const int32_t* edge_seq,
-                                      int32_t nseq, const tnqs_bp_opts* bopts, int32_t update_cache, double* truncerr,
-                                      int32_t* refreshes) {
-  API_BEGIN(c)
+static void apply_circuit_impl(tnqs_ctx* c, int32_t ngates, const int32_t* gate_v, const int64_t* gate_off,
+                               const double* gate_data, const tnqs_apply_opts* aopts, const int32_t* edge_seq,
+                               int32_t nseq, const tnqs_bp_opts* bopts, int32_t update_cache, double* truncerr,
+                               int32_t* refreshes, int32_t fetch_count, const int32_t* fetch_v, double* const* fetch_data, int64_t* fetch_n) {
   REQUIRE(ngates >= 0 && aopts && bopts && (ngates == 0 || (gate_v && gate_off && gate_data)), TNQS_ERR_INVALID_ARG,
           "tnqs_apply_circuit: null argument");
   const cplx* gd = (const cplx*)gate_data;
@@ -1196,9 +1196,46 @@ extern "C" int32_t tnqs_apply_circuit(tnqs_ctx* c, int32_t ngates, const int32_t
     if (v2 >= 0) { inbatch[v2] = 1; affected[v2] = 1; }
   }
   flush();
-  if (update_cache) refresh();
+  // Fetch: the site tensors are final once the last batch is done; their device -> host copies run on a second stream while
+  // the closing BP refresh (which only reads the sites) runs on the main one.
+  if (fetch_count > 0) {
+    if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, ev, 0));
+    cudaEventDestroy(ev);
+    for (int i = 0; i < fetch_count; ++i) {
+      const int v = fetch_v[i];
+      REQUIRE(v >= 0 && v < c->nv && fetch_data[i], TNQS_ERR_INVALID_ARG, "tnqs_apply_circuit_fetch: bad vertex or null buffer");
+      REQUIRE(fetch_n[i] >= c->site_n[v], TNQS_ERR_SHAPE, "tnqs_apply_circuit_fetch: host buffer smaller than the site tensor");
+      fetch_n[i] = c->site_n[v];
+      CU(cudaMemcpyAsync(fetch_data[i], c->site[v], (size_t)c->site_n[v] * sizeof(cplx), cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+  }
+  try {
+    if (update_cache) refresh();
+    c->sync();
+  } catch (...) { if (fetch_count > 0) cudaStreamSynchronize(c->copy_stream); throw; }     // no copy may outlive the call
   if (refreshes) *refreshes = nrefresh;
-  c->sync();
+  if (fetch_count > 0) CU(cudaStreamSynchronize(c->copy_stream));
+}
+
+extern "C" int32_t tnqs_apply_circuit(tnqs_ctx* c, int32_t ngates, const int32_t* gate_v, const int64_t* gate_off,
+                                      const double* gate_data, const tnqs_apply_opts* aopts, const int32_t* edge_seq,
+                                      int32_t nseq, const tnqs_bp_opts* bopts, int32_t update_cache, double* truncerr,
+                                      int32_t* refreshes) {
+  API_BEGIN(c)
+  apply_circuit_impl(c, ngates, gate_v, gate_off, gate_data, aopts, edge_seq, nseq, bopts, update_cache, truncerr, refreshes, 0, nullptr, nullptr, nullptr);
+  API_END(c)
+}
+extern "C" int32_t tnqs_apply_circuit_fetch(tnqs_ctx* c, int32_t ngates, const int32_t* gate_v, const int64_t* gate_off,
+                                            const double* gate_data, const tnqs_apply_opts* aopts, const int32_t* edge_seq,
+                                            int32_t nseq, const tnqs_bp_opts* bopts, int32_t update_cache, double* truncerr,
+                                            int32_t* refreshes, int32_t fetch_count, const int32_t* fetch_v, double* const* fetch_data, int64_t* fetch_n) {
+  API_BEGIN(c)
+  REQUIRE(fetch_count >= 0 && (fetch_count == 0 || (fetch_v && fetch_data && fetch_n)), TNQS_ERR_INVALID_ARG, "tnqs_apply_circuit_fetch: null argument");
+  apply_circuit_impl(c, ngates, gate_v, gate_off, gate_data, aopts, edge_seq, nseq, bopts, update_cache, truncerr, refreshes, fetch_count, fetch_v, fetch_data, fetch_n);
   API_END(c)
 }
 

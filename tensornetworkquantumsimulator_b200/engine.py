@@ -272,14 +272,16 @@ def _pack_circuit(g: Graph, circuit: Sequence[tuple]):
 
 
 def apply_gates(circuit: Sequence[tuple], psi, apply_kwargs: Optional[dict] = None, bp_update_kwargs: Optional[dict] = None,
-                update_cache: bool = True, verbose: bool = False, inplace: bool = False, info: Optional[dict] = None):
+                update_cache: bool = True, verbose: bool = False, inplace: bool = False, info: Optional[dict] = None, fetch=None):
     """Apply an ordered list of one/two-site gates by simple update with lazy BP refreshes
     (src/Apply/apply_gates.jl:13-23 for a TensorNetworkState, :42-92 for a cache).  Returns
-    (state or cache, truncation errors)."""
+    (state or cache, truncation errors).  fetch = (vertex ids int32, ctypes array of double*, capacities int64): the listed site
+    tensors are copied into those host buffers while the closing BP refresh runs (tnqs_apply_circuit_fetch); the int64 array
+    holds the element counts afterwards."""
     if isinstance(psi, TensorNetworkState):
         kw = bp_update_kwargs if bp_update_kwargs is not None else default_bp_update_kwargs(psi)
         bpc = update(BeliefPropagationCache(psi if inplace else psi.copy()), inplace=True, **kw)
-        bpc, errs = apply_gates(circuit, bpc, apply_kwargs, kw, update_cache, verbose, True, info)
+        bpc, errs = apply_gates(circuit, bpc, apply_kwargs, kw, update_cache, verbose, True, info, fetch)
         return bpc.psi, errs
     out = psi if inplace else psi.copy()
     g = out.g
@@ -292,9 +294,15 @@ def apply_gates(circuit: Sequence[tuple], psi, apply_kwargs: Optional[dict] = No
     gv, off, data = _pack_circuit(g, circuit)
     errs = np.zeros(max(len(circuit), 1), dtype=np.float64)
     refreshes = C.c_int32(0)
-    check(out.psi._h.ptr, _lib.load().tnqs_apply_circuit(
-        out.psi._h.ptr, len(circuit), ptr_i32(gv), ptr_i64(off), ptr_f64(data), C.byref(aopts), ptr_i32(seq), len(seq),
-        C.byref(bopts), int(update_cache), ptr_f64(errs), C.byref(refreshes)))
+    if fetch is None:
+        check(out.psi._h.ptr, _lib.load().tnqs_apply_circuit(
+            out.psi._h.ptr, len(circuit), ptr_i32(gv), ptr_i64(off), ptr_f64(data), C.byref(aopts), ptr_i32(seq), len(seq),
+            C.byref(bopts), int(update_cache), ptr_f64(errs), C.byref(refreshes)))
+    else:
+        fv, fptrs, fns = fetch
+        check(out.psi._h.ptr, _lib.load().tnqs_apply_circuit_fetch(
+            out.psi._h.ptr, len(circuit), ptr_i32(gv), ptr_i64(off), ptr_f64(data), C.byref(aopts), ptr_i32(seq), len(seq),
+            C.byref(bopts), int(update_cache), ptr_f64(errs), C.byref(refreshes), len(fv), ptr_i32(fv), fptrs, ptr_i64(fns)))
     if info is not None:
         info["refreshes"] = refreshes.value
     return out, errs[:len(circuit)]

@@ -20,7 +20,7 @@ SYMBOLS = [
     "tnqs_version", "tnqs_status_string", "tnqs_last_error", "tnqs_create", "tnqs_destroy", "tnqs_clone",
     "tnqs_sync", "tnqs_num_vertices", "tnqs_num_edges", "tnqs_get_bond_dims", "tnqs_site_size", "tnqs_set_site",
     "tnqs_get_site", "tnqs_set_sites", "tnqs_get_sites", "tnqs_fill_random", "tnqs_set_message", "tnqs_get_message", "tnqs_reset_messages",
-    "tnqs_bp_update", "tnqs_apply_1site", "tnqs_apply_2site", "tnqs_apply_2site_begin", "tnqs_apply_2site_end", "tnqs_apply_circuit", "tnqs_rdm_1site",
+    "tnqs_bp_update", "tnqs_apply_1site", "tnqs_apply_2site", "tnqs_apply_2site_begin", "tnqs_apply_2site_end", "tnqs_apply_circuit", "tnqs_apply_circuit_fetch", "tnqs_rdm_1site",
     "tnqs_expect_2site_nn", "tnqs_expect_path", "tnqs_vertex_scalars", "tnqs_edge_scalars", "tnqs_rescale", "tnqs_symmetric_gauge",
     "tnqs_truncate", "tnqs_message_slab", "tnqs_halo_pack", "tnqs_halo_unpack", "tnqs_set_partition", "tnqs_halo_alloc", "tnqs_halo_peer", "tnqs_halo_route", "tnqs_halo_close",
     "tnqs_kernel_launches", "tnqs_bp_sweeps_total", "tnqs_bp_message_updates_total", "tnqs_profile_enable", "tnqs_profile_read", "tnqs_stream",
@@ -80,6 +80,7 @@ def load() -> C.CDLL:
     lib.tnqs_apply_2site_begin.argtypes = [p, i32, i32p, i32p, f64p, C.POINTER(ApplyOpts), i32p, C.POINTER(vp), i64p, i64p]
     lib.tnqs_apply_2site_end.argtypes = [p, vp, i32p, f64p, f64p]
     lib.tnqs_apply_circuit.argtypes = [p, i32, i32p, i64p, f64p, C.POINTER(ApplyOpts), i32p, i32, C.POINTER(BpOpts), i32, f64p, i32p]
+    lib.tnqs_apply_circuit_fetch.argtypes = [p, i32, i32p, i64p, f64p, C.POINTER(ApplyOpts), i32p, i32, C.POINTER(BpOpts), i32, f64p, i32p, i32, i32p, C.POINTER(f64p), i64p]
     lib.tnqs_rdm_1site.argtypes = [p, i32, i32p, f64p]
     lib.tnqs_expect_2site_nn.argtypes = [p, i32, i32p, f64p, f64p]
     lib.tnqs_expect_path.argtypes = [p, i32, i32p, i32p, f64p, f64p]

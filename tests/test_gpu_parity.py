@@ -879,3 +879,27 @@ def test_partitioned_bp_peer_memory_halo_matches_single_handle(E, shape, chi, wo
     assert len({it for it, _ in res}) == 1 and res[0][0] + 3 == info["iters"]
     assert all(abs(m - info["mean_diff"]) <= 1e-12 * max(1.0, abs(info["mean_diff"])) for _, m in res)
     compare(ref, False)
+
+
+def test_apply_gates_fetch_returns_final_sites(E):
+    # tnqs_apply_circuit_fetch: the site tensors copied out beside the closing refresh are the final ones, sizes reported
+    import ctypes as C
+    from tensornetworkquantumsimulator_b200 import lib
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=4)
+    circuit = [("Rx", [v], 0.3) for v in g.names] + [("Rzz", [g.names[int(g.esrc[e])], g.names[int(g.edst[e])]], 0.4) for e in range(g.ne)]
+    kw = dict(maxdim=4, cutoff=1e-12, normalize_tensors=True)
+    a = to_engine(psi_o, chi_cap=4)
+    b = to_engine(psi_o, chi_cap=4)
+    E.apply_gates(circuit, a, apply_kwargs=kw, inplace=True)
+    cap = 2 * 4 ** 4
+    bufs = [np.zeros(2 * cap, dtype=np.float64) for _ in range(g.nv)]
+    ptrs = (C.POINTER(C.c_double) * g.nv)(*[lib.ptr_f64(x) for x in bufs])
+    ns = np.full(g.nv, cap, dtype=np.int64)
+    E.apply_gates(circuit, b, apply_kwargs=kw, inplace=True, fetch=(lib.i32(np.arange(g.nv)), ptrs, ns))
+    ta = a.psi.tensors()
+    for v in range(g.nv):
+        assert ns[v] == ta[v].size
+        assert np.array_equal(bufs[v][:2 * ns[v]].view(np.complex128), ta[v].ravel(order="F"))
+    for k in range(2 * g.ne):
+        assert np.array_equal(E.message(a, k), E.message(b, k))
