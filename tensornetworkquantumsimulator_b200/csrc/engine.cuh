@@ -161,8 +161,9 @@ struct tnqs_ctx {
   // when those threads drive other handles whose kernels this handle's kernels wait for (device-side halo barrier).
   char* hret = nullptr;
   void d2h_small(void* dst, const void* dev_src, size_t bytes) {
-    if (!hret && cudaHostAlloc((void**)&hret, 4096, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); hret = nullptr; }
-    if (hret && bytes <= 4096) {
+    constexpr size_t HRET = 256 << 10;
+    if (!hret && cudaHostAlloc((void**)&hret, HRET, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); hret = nullptr; }
+    if (hret && bytes <= HRET) {
       CU(cudaMemcpyAsync(hret, dev_src, bytes, cudaMemcpyDeviceToHost, stream));
       sync();
       memcpy(dst, hret, bytes);

@@ -884,8 +884,7 @@ void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const d
         if (pass == 0) launch_mode_apply(c, TNQS_KC_QR, ma);        // Q1 = A R1^-1; the second factor R2^-1 stays pending (colfix)
       }
       std::vector<int> flags(nj);
-      CU(cudaMemcpyAsync(flags.data(), d_flag, nj * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-      c->sync();
+      c->d2h_small(flags.data(), d_flag, nj * sizeof(int));
       for (int i = 0; i < nj; ++i) {
         if (flags[i]) house_list.push_back(chol_list[i]);
         else { jobs[chol_list[i]].Q = Qb[i]; jobs[chol_list[i]].colfix = Rinv[i]; }
@@ -973,7 +972,7 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
   }
   for (int i = 0; i < n; ++i) dbg_norm(c, "theta", i, td[i].theta, (size_t)sv[i].m * sv[i].n);
   std::vector<int> ranks(n);
-  CU(cudaMemcpyAsync(ranks.data(), d_rank, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  c->d2h_small(ranks.data(), d_rank, n * sizeof(int));
   int st = c->read_status();
   if (st & ST_NEG_EIG) throw TnqsError(TNQS_ERR_NEGATIVE_EIGENVALUE, "message eigenvalue < -10 eps in simple update");
   if (st & ST_NO_CONV) throw TnqsError(TNQS_ERR_SVD_NO_CONVERGENCE, "Jacobi eigen/SVD iteration did not converge");
@@ -1066,8 +1065,8 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
   }
 
   if (ranks_out) for (int i = 0; i < n; ++i) ranks_out[i] = ranks[i];
-  if (err_out) CU(cudaMemcpyAsync(err_out, d_err, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  if (svals_out) CU(cudaMemcpyAsync(svals_out, d_sv, (size_t)n * cap * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (err_out) c->d2h_small(err_out, d_err, n * sizeof(double));
+  if (svals_out) c->d2h_small(svals_out, d_sv, (size_t)n * cap * sizeof(double));
   c->sync();
 }
 
