@@ -465,7 +465,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
             }
             for (int m = std::max(0, nf - D); m < nf; ++m) push_close(m);
             sl.fused.count = (int)(items.size() - sl.fused.off);
-            sl.fused.grid = dim3((unsigned)std::min(sl.fused.count, 2 * sm_count), 1, 1);
+            sl.fused.grid = dim3((unsigned)std::min(sl.fused.count, QUEUE_CTAS * sm_count), 1, 1);
             sl.fused.smem = std::max(sl.slab.smem, sl.dclose.smem);
           }
         }
@@ -736,7 +736,7 @@ static bool build_sweep_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>&
     while (head < pending.size()) emit_close(pending[head++]);
   }
   plan.sweep_items = (int)items.size();
-  plan.sweep_grid = dim3((unsigned)std::min<long long>((long long)items.size(), 2LL * c->num_sms), 1, 1);
+  plan.sweep_grid = dim3((unsigned)std::min<long long>((long long)items.size(), (long long)QUEUE_CTAS * c->num_sms), 1, 1);
   plan.sweep_smem = N == 16 ? SlabCfg<16>::SMEM : SlabCfg<8>::SMEM;
   plan.sweep_commit = (int)commit.size();
   const size_t cnt[8] = {0, 0, 0, rd.size(), commit.size(), sd.size(), dc.size(), items.size()};
@@ -812,8 +812,8 @@ static void run_plan(tnqs_ctx* c, const Plan& p) {
     SweepQueue Q; Q.items = p.d_items; Q.n = p.sweep_items; Q.counter = p.d_qctr; Q.slabs = p.d_slab; Q.closes = p.d_dclose;
     Q.chains = p.d_chains; Q.slab_done = p.d_slab_done; Q.chain_done = p.d_chain_done;
     Q.nchains = (int)p.nchains; Q.ahead = std::max(1, (int)((long long)p.sweep_grid.x * p.nchains / std::max(1, p.sweep_items)));
-    if (p.sweepN == 16) LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_sweep<16>, p.sweep_grid, 256, p.sweep_smem, Q);
-    else LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_sweep<8>, p.sweep_grid, 256, p.sweep_smem, Q);
+    if (p.sweepN == 16) LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_sweep<16>, p.sweep_grid, QUEUE_THREADS, p.sweep_smem, Q);
+    else LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_sweep<8>, p.sweep_grid, QUEUE_THREADS, p.sweep_smem, Q);
     if (p.sweep_commit) LAUNCH(c, TNQS_KC_BP_FINALIZE, k_msg_commit, p.sweep_commit, 128, 0, c->msg_cur, c->msg_stage, c->slot, p.d_commit, c->d_chi);
     return;
   }
@@ -822,14 +822,14 @@ static void run_plan(tnqs_ctx* c, const Plan& p) {
       if (sl.fused.count) {
         LevelQueue Q; Q.items = p.d_items + sl.fused.off; Q.n = sl.fused.count; Q.counter = p.d_qctr;
         Q.slabs = p.d_slab; Q.closes = p.d_dclose; Q.slab_done = p.d_slab_done;
-        if (sl.fastN == 16) LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_level<16>, sl.fused.grid, 256, sl.fused.smem, Q);
-        else LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_level<8>, sl.fused.grid, 256, sl.fused.smem, Q);
+        if (sl.fastN == 16) LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_level<16>, sl.fused.grid, QUEUE_THREADS, sl.fused.smem, Q);
+        else LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_level<8>, sl.fused.grid, QUEUE_THREADS, sl.fused.smem, Q);
       } else if (sl.slab.count) {
         if (sl.fastN == 16) {
-          LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<16>, sl.slab.grid, 256, sl.slab.smem, p.d_slab + sl.slab.off);
+          LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<16>, sl.slab.grid, SLAB_THREADS, sl.slab.smem, p.d_slab + sl.slab.off);
           LAUNCH(c, TNQS_KC_MODE_CLOSE, k_close_dmma<16>, sl.dclose.grid, close_threads(sl.close_cap), sl.dclose.smem, p.d_dclose + sl.dclose.off);
         } else {
-          LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<8>, sl.slab.grid, 256, sl.slab.smem, p.d_slab + sl.slab.off);
+          LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<8>, sl.slab.grid, SLAB_THREADS, sl.slab.smem, p.d_slab + sl.slab.off);
           LAUNCH(c, TNQS_KC_MODE_CLOSE, k_close_dmma<8>, sl.dclose.grid, close_threads(sl.close_cap), sl.dclose.smem, p.d_dclose + sl.dclose.off);
         }
       }

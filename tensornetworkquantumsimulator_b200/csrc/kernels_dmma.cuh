@@ -41,9 +41,19 @@ template <int N> struct SlabCfg {
   static constexpr int KK = N / 4;        // 16-byte A loads per row: element b = 4*kk + q feeds k-steps 2kk (re) and 2kk+1 (im)
   static constexpr int NT = N / 4;        // n-tiles of 8 real = 4 complex
   static constexpr int SLAB3 = N * N * N;
-  static constexpr int MSM = 3 * N * N;   // staged messages
+  static constexpr int MSM = 2 * N * N;   // two staged messages (the third one replaces the first while the second phase runs)
   static constexpr size_t SMEM = (size_t)(SLAB3 + MSM) * sizeof(cplx);
 };
+// CTA shape of the throughput-bound slab kernel (k_absorb_slab: JACOBI sweeps, level launches, the gate path): 4 warps,
+// 3 CTAs per SM (72 KB of shared memory each at N = 16).  A CTA is idle on the DMMA pipe while it stages messages, waits for
+// its first loads, sits at a phase barrier or drains its stores; three short CTAs in different phases keep the pipe busier
+// than two long ones (absorption of a JACOBI sweep 6.9 -> 6.4 ms, gate-path absorptions 5.2 -> 4.5 ms per class).
+// The persistent reference-order kernels (k_bp_sweep, k_bp_level) keep 8 warps x 2 CTAs: there the latency of one item
+// is on the critical path of the 124 dependency levels (measured: 13.8 ms per sweep with 4-warp CTAs against 12.1).
+constexpr int SLAB_THREADS = 128;
+constexpr int SLAB_CTAS = 3;
+constexpr int QUEUE_THREADS = 256;
+constexpr int QUEUE_CTAS = 2;
 
 // One absorption phase P of F.  K ordering: lane (r, q) loads the whole complex element b = 4kk + q of its row (one
 // 16-byte load) and feeds its real part to k-step 2kk and its imaginary part to k-step 2kk+1; the B fragments are built
@@ -60,7 +70,7 @@ __device__ __forceinline__ void absorb_phase(const SlabDesc& d, const cplx* __re
   // B fragments of [[Re m, Im m], [-Im m, Re m]], kept in registers for the whole phase
   double bf[2 * KK][NT];
   {
-    const cplx* m = msm + P * N * N;
+    const cplx* m = msm;
     const bool conj_m = d.flags & 1, trans_m = d.flags & 2;
     const int pp = r & 1;
 #pragma unroll
@@ -127,9 +137,10 @@ __device__ __forceinline__ void absorb_phase(const SlabDesc& d, const cplx* __re
   }
 }
 
-// One slab `sub` = (w, s) of item d by a whole CTA; shared memory: N^3 complex slab + 3 N^2 complex staged messages.
-template <int N, int F>
-__device__ __forceinline__ void absorb_slab_body(const SlabDesc& d, int sub, cplx* sm, const cplx* msm) {
+// One slab `sub` = (w, s) of item d by a whole CTA; shared memory: N^3 complex slab + 2 N^2 complex staged messages
+// (msm[0]: legs 0 and 2, msm[1]: leg 1; the third message travels through registers while the second phase runs).
+template <int N, int F, bool COHERENT>
+__device__ __forceinline__ void absorb_slab_body(const SlabDesc& d, int sub, cplx* sm, cplx* msm) {
   const int s = sub & 1, w = sub >> 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   long long NF = N; for (int i = 1; i < F; ++i) NF *= N;
@@ -137,8 +148,22 @@ __device__ __forceinline__ void absorb_slab_body(const SlabDesc& d, int sub, cpl
   cplx* gdst = d.x + ((long long)w * 2 + s) * NF;
   absorb_phase<N, F, 0>(d, gsrc, gdst, sm, msm, lane, warp, nwarps);
   __syncthreads();
-  absorb_phase<N, F, 1>(d, gsrc, gdst, sm, msm, lane, warp, nwarps);
+  constexpr int PER = (N * N + SLAB_THREADS - 1) / SLAB_THREADS;      // enough for the smaller of the two CTA shapes
+  cplx pre[PER];
   if (F == 3) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = threadIdx.x + i * blockDim.x;
+      if (idx < N * N) pre[i] = COHERENT ? __ldcg(d.m[2] + idx) : __ldg(d.m[2] + idx);
+    }
+  }
+  absorb_phase<N, F, 1>(d, gsrc, gdst, sm, msm + N * N, lane, warp, nwarps);
+  if (F == 3) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = threadIdx.x + i * blockDim.x;
+      if (idx < N * N) msm[idx] = pre[i];            // msm[0] is free: every warp built its phase-0 fragments before the barrier above
+    }
     __syncthreads();
     absorb_phase<N, F, (F == 3 ? 2 : 1)>(d, gsrc, gdst, sm, msm, lane, warp, nwarps);
   }
@@ -147,18 +172,18 @@ __device__ __forceinline__ void absorb_slab_body(const SlabDesc& d, int sub, cpl
 // COHERENT: the messages may have been written by another CTA of the same launch (k_bp_sweep) - read them through L2.
 template <int N, bool COHERENT = false>
 __device__ __forceinline__ void absorb_slab_item(const SlabDesc& d, int sub, cplx* sm, cplx* msm) {
-  // the item's messages, staged once: every phase builds its B fragments from shared memory
-  for (int idx = threadIdx.x; idx < d.F * N * N; idx += blockDim.x) {
+  // the messages of the first two legs, staged once: a phase builds its B fragments from shared memory
+  for (int idx = threadIdx.x; idx < 2 * N * N; idx += blockDim.x) {
     const cplx* src = d.m[idx / (N * N)] + idx % (N * N);
     msm[idx] = COHERENT ? __ldcg(src) : __ldg(src);
   }
   __syncthreads();
-  if (d.F == 3) absorb_slab_body<N, 3>(d, sub, sm, msm); else absorb_slab_body<N, 2>(d, sub, sm, msm);
+  if (d.F == 3) absorb_slab_body<N, 3, COHERENT>(d, sub, sm, msm); else absorb_slab_body<N, 2, COHERENT>(d, sub, sm, msm);
 }
 
-// grid: (slabs, items); block 256 (8 warps); dynamic shared memory SlabCfg<N>::SMEM
+// grid: (slabs, items); block SLAB_THREADS; dynamic shared memory SlabCfg<N>::SMEM
 template <int N>
-__global__ void __launch_bounds__(256, 2) k_absorb_slab(const SlabDesc* __restrict__ descs) {
+__global__ void __launch_bounds__(SLAB_THREADS, SLAB_CTAS) k_absorb_slab(const SlabDesc* __restrict__ descs) {
   const SlabDesc d = descs[blockIdx.y];
   if ((int)blockIdx.x >= d.nslabs) return;
   extern __shared__ cplx slab[];
@@ -318,7 +343,7 @@ struct LevelQueue {
 };
 
 template <int N>
-__global__ void __launch_bounds__(256, 2) k_bp_level(const LevelQueue Q) {
+__global__ void __launch_bounds__(QUEUE_THREADS, QUEUE_CTAS) k_bp_level(const LevelQueue Q) {
   extern __shared__ cplx dyn[];
   cplx* msm = dyn + SlabCfg<N>::SLAB3;
   __shared__ int s_item;
@@ -447,7 +472,7 @@ __device__ __forceinline__ void touch_l1(const void* p) {
 }
 
 template <int N>
-__global__ void __launch_bounds__(256, 2) k_bp_sweep(const SweepQueue Q) {
+__global__ void __launch_bounds__(QUEUE_THREADS, QUEUE_CTAS) k_bp_sweep(const SweepQueue Q) {
   extern __shared__ cplx dyn[];
   cplx* msm = dyn + SlabCfg<N>::SLAB3;
   __shared__ int s_item, s_epoch;

@@ -53,6 +53,8 @@ static void set_smem_attrs() {   // per device: called at every handle creation 
   cudaFuncSetAttribute(k_bp_sweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_close_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  // three 72 KB CTAs per SM need the largest shared-memory carve-out
+  cudaFuncSetAttribute(k_absorb_slab<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 }
 
@@ -667,8 +669,8 @@ void GateBatch::absorb_outer(bool inverse) {   // forward: on A (psi~); inverse:
     SlabDesc* dsd = c->upload(slab[w]);
     dim3 grid((unsigned)((maxcols[w] + 1) / 2 * 2), (unsigned)slab[w].size(), 1);
     size_t smem = N == 16 ? SlabCfg<16>::SMEM : SlabCfg<8>::SMEM;
-    if (w) LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<16>, grid, 256, smem, dsd);
-    else LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<8>, grid, 256, smem, dsd);
+    if (w) LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<16>, grid, SLAB_THREADS, smem, dsd);
+    else LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<8>, grid, SLAB_THREADS, smem, dsd);
   }
   size_t maxouter = 0;
   for (int jj : generic) { SiteJob& J = jobs[jj]; maxouter = std::max(maxouter, J.outer.size()); }
