@@ -137,14 +137,19 @@ struct tnqs_ctx {
   // driver stage (or page-lock) the source on every call, which is slow and erratic on a host that holds gigabytes of
   // pinned memory (measured: +35..70 ms per layer).  The buffer is a bump allocator that rewinds at every stream
   // synchronisation; a request that does not fit falls back to the pageable copy.
-  char* hstage = nullptr; size_t hstage_size = 0, hstage_off = 0;
+  char* hstage = nullptr; size_t hstage_size = 0, hstage_off = 0, hstage_want = 0; bool hstage_disabled = false;
+  void hstage_resize(size_t bytes) {
+    if (hstage) { cudaFreeHost(hstage); hstage = nullptr; }
+    hstage_size = 0; hstage_off = 0;
+    if (cudaHostAlloc((void**)&hstage, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); hstage = nullptr; hstage_disabled = true; return; }
+    hstage_size = bytes;
+  }
   void h2d(void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return;
     StallProbe sp("upload");
-    if (!hstage && hstage_size == 0) {
+    if (!hstage && !hstage_disabled) {
       const char* e = getenv("TNQS_NO_HSTAGE");
-      hstage_size = (e && e[0] == '1') ? 1 : (size_t)32 << 20;
-      if (cudaHostAlloc((void**)&hstage, hstage_size, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); hstage = nullptr; }
+      if (e && e[0] == '1') hstage_disabled = true; else hstage_resize((size_t)1 << 20);        // grows with the largest call (up to 64 MB)
     }
     const size_t need = (bytes + 255) / 256 * 256;
     if (hstage && hstage_off + need <= hstage_size) {
@@ -152,6 +157,7 @@ struct tnqs_ctx {
       memcpy(s, src, bytes);
       CU(cudaMemcpyAsync(dst, s, bytes, cudaMemcpyHostToDevice, stream));
     } else {
+      hstage_want = std::min<size_t>((size_t)64 << 20, std::max(hstage_want, 2 * (hstage_off + need)));   // pageable this time, a bigger buffer after the next sync
       CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
     }
   }
@@ -177,7 +183,7 @@ struct tnqs_ctx {
     h2d(p, v.data(), v.size() * sizeof(T));
     return p;
   }
-  void sync() { CU(cudaStreamSynchronize(stream)); hstage_off = 0; }
+  void sync() { CU(cudaStreamSynchronize(stream)); hstage_off = 0; if (hstage_want > hstage_size && !hstage_disabled) hstage_resize(hstage_want); }
 
   // ---- launch accounting ----
   void pre_launch(int kc) {
