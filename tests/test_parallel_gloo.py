@@ -84,3 +84,33 @@ def test_partition_halo_lists_are_consistent():
             mine = [2 * int(lg.l2g_e[k // 2]) + (k & 1) for k in ks]
             theirs = [2 * int(lgs[nb].l2g_e[k // 2]) + (k & 1) for k in lgs[nb].recv[r]]
             assert mine == theirs and len(mine) > 0
+
+
+@pytest.mark.parametrize("shape,world", [((4, 6), 2), ((3, 8), 4), ((5, 16), 8)])
+def test_peer_memory_halo_layout_and_routes_are_consistent(shape, world):
+    # host logic of the peer-memory halo (parallel.halo_layout / halo_routes): every owned -> ghost message of a rank is
+    # routed to the slot of its neighbour's receive buffer that the neighbour reads back as the same global directed edge,
+    # every slot is written exactly once, and nothing is routed to a rank that is not a neighbour
+    sys.path.insert(0, ROOT)
+    from tensornetworkquantumsimulator_b200 import graphs as G, parallel as P
+    g = G.named_grid(shape)
+    owner = P.strip_owner(g, world, axis=1)
+    lgs = [P.build_local_graph(g, owner, r) for r in range(world)]
+    layouts = [P.halo_layout(lg) for lg in lgs]
+
+    def global_dedge(lg, lk):
+        return 2 * int(lg.l2g_e[lk // 2]) + (lk & 1)
+
+    written = [np.zeros(len(layouts[r][0]), dtype=int) for r in range(world)]
+    for r, lg in enumerate(lgs):
+        ks, peers, slots = P.halo_routes(lg, r, {p: layouts[p][1] for p in lg.send})
+        assert len(ks) == sum(len(v) for v in lg.send.values())
+        for k, p, s in zip(ks, peers, slots):
+            assert p != r and p in lgs[r].send and r in lgs[p].recv
+            assert lg.owned[lg.g.dsrc(k)] and not lg.owned[lg.g.ddst(k)]
+            peer_k = int(layouts[p][0][s])                       # what the peer commits from that slot
+            assert global_dedge(lg, k) == global_dedge(lgs[p], peer_k)
+            assert lgs[p].owned[lgs[p].g.ddst(peer_k)] and not lgs[p].owned[lgs[p].g.dsrc(peer_k)]
+            written[p][s] += 1
+    for r in range(world):
+        assert np.all(written[r] == 1), "every receive slot is written by exactly one peer message"
