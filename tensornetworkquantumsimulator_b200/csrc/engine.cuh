@@ -678,8 +678,6 @@ static bool build_sweep_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>&
       }
     }
   }
-  if (const char* e = getenv("TNQS_SWEEP_NOWAIT")) if (e[0] == '1')            // timing experiment only: results are wrong
-    for (int i = 0; i < nch; ++i) for (int j = 0; j < 4; ++j) { sc[i].dep[j] = -1; sc[i].war[j] = -1; }
   Plan plan; plan.sweep = true; plan.sweepN = N; plan.nchains = (size_t)nch;
   std::vector<SlabDesc> sd(nch); std::vector<CloseDmmaDesc> dc(nch); std::vector<CloseReduceDesc> rd(nch);
   std::vector<int> commit;

@@ -1,4 +1,4 @@
-"""Timing of k_bp_sweep under queue settings (TNQS_SWEEP_LAG / _RING / _NOWAIT): python tools/sweep_tune.py [nx] [chi]."""
+"""Timing of k_bp_sweep under queue settings (TNQS_SWEEP_LAG / _RING): python tools/sweep_tune.py [nx] [chi]."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -23,7 +23,7 @@ def run(mode, env):
         L.tnqs_sync(h); ts.append(1e3 * (time.perf_counter() - t0) / 4)
     for k in env: os.environ.pop(k)
     return min(ts)
-combos = [{"TNQS_SWEEP": "0"}, {}, {"TNQS_SWEEP_NOWAIT": "1"}, {"TNQS_SWEEP_LAG": "2"}, {"TNQS_SWEEP_LAG": "4"}, {"TNQS_SWEEP_LAG": "6"}, {"TNQS_SWEEP_LAG": "8"}, {"TNQS_SWEEP_LAG": "6", "TNQS_SWEEP_RING": "32"}, {"TNQS_SWEEP_LAG": "6", "TNQS_SWEEP_RING": "96"}]
+combos = [{"TNQS_SWEEP": "0"}, {}, {"TNQS_SWEEP_LAG": "2"}, {"TNQS_SWEEP_LAG": "4"}, {"TNQS_SWEEP_LAG": "6"}, {"TNQS_SWEEP_LAG": "8"}, {"TNQS_SWEEP_LAG": "6", "TNQS_SWEEP_RING": "32"}, {"TNQS_SWEEP_LAG": "6", "TNQS_SWEEP_RING": "96"}]
 os.environ["TNQS_SWEEP_JACOBI"] = "1"
 for mode in ("reference", "jacobi"):
     for env in combos:
