@@ -187,6 +187,13 @@ int32_t tnqs_truncate(tnqs_ctx* ctx, int32_t ngroups, const int32_t* group_off, 
                       const tnqs_apply_opts* aopts, const int32_t* edge_seq, int32_t nseq,
                       const tnqs_bp_opts* bopts);
 
+/* replaces: BilinearForm(ket, bra) + BeliefPropagationCache over it (src/Forms/bilinearform.jl:28-54, src/inner.jl:82-86).
+ * With a bra attached, every BP contraction of `ctx` (tnqs_bp_update, tnqs_vertex_scalars, ...) closes the ket tensors of `ctx`
+ * against the conjugated site tensors of `bra` (same device, graph, site and bond dimensions; it must stay alive and unchanged
+ * while attached; NULL detaches).  Messages are chi x chi but no longer Hermitian; inner(psi, phi; alg = "bp") is the product of
+ * the vertex scalars over the product of the edge scalars after an update.  Gates and gauges are meaningless on such a handle. */
+int32_t tnqs_set_bra(tnqs_ctx* ctx, tnqs_ctx* bra);
+
 /* ---- multi-GPU halo (vertex partition; one handle per rank holds the whole graph's topology but only its own
  * vertices' tensors are meaningful) -------------------------------------------------------------------------
  * Device pointer + element count of the contiguous message slab; slot k starts at k*chi_cap^2 complex elements.

@@ -64,9 +64,14 @@ class TensorNetworkState:
 class BeliefPropagationCache:
     network: TensorNetworkState
     messages: Dict[int, np.ndarray] = field(default_factory=dict)
+    bra: Optional[TensorNetworkState] = None        # BilinearForm(ket = network, bra): src/Forms/bilinearform.jl:28-54
 
     def copy(self) -> "BeliefPropagationCache":
-        return BeliefPropagationCache(self.network.copy(), {k: m.copy() for k, m in self.messages.items()})
+        return BeliefPropagationCache(self.network.copy(), {k: m.copy() for k, m in self.messages.items()}, self.bra)
+
+    def bra_tensor(self, v: int) -> np.ndarray:
+        """The tensor whose conjugate closes a contraction at v: the state itself, or the bra of a bilinear form."""
+        return (self.bra if self.bra is not None else self.network).tensors[v]
 
     @property
     def g(self) -> Graph:
@@ -137,7 +142,7 @@ def updated_message(bpc: BeliefPropagationCache, k: int, normalize: bool = True,
         a = _absorb(a, axis, m)
     ax_w = 1 + g.leg(v, k // 2)
     others = [i for i in range(t.ndim) if i != ax_w]
-    out = np.tensordot(a, t.conj(), axes=(others, others))          # [b_w, b_w']
+    out = np.tensordot(a, bpc.bra_tensor(v).conj(), axes=(others, others))          # [b_w, b_w']
     if enforce_hermiticity:                                          # beliefpropagationcache.jl:123-127
         out = (out + out.conj().T) / 2
     if normalize:
@@ -201,7 +206,7 @@ def vertex_scalar(bpc: BeliefPropagationCache, v: int) -> complex:
     a = t
     for axis, m in incoming(bpc, v):
         a = _absorb(a, axis, m)
-    return complex(np.vdot(t, a))            # sum conj(t) * a
+    return complex(np.vdot(bpc.bra_tensor(v), a))            # sum conj(t) * a
 
 
 def edge_scalar(bpc: BeliefPropagationCache, e: int) -> complex:
@@ -220,6 +225,17 @@ def freenergy(bpc: BeliefPropagationCache) -> complex:
 
 def partitionfunction(bpc: BeliefPropagationCache) -> complex:
     return complex(np.exp(freenergy(bpc)))
+
+
+def inner(psi: TensorNetworkState, phi: TensorNetworkState, maxiter: Optional[int] = None, tolerance: Optional[float] = None,
+          edge_sequence: Optional[Sequence[int]] = None) -> complex:
+    """inner(psi, phi; alg = "bp") (src/inner.jl:82-86): BP on BilinearForm(psi, phi) - the bra layer is dag(phi), the operator
+    layer the identity (src/Forms/bilinearform.jl:28-37) - then the partition function.  <phi|psi> exactly on trees."""
+    kw = default_bp_update_kwargs(psi)
+    bpc = BeliefPropagationCache(psi.copy(), {}, phi)
+    bpc = update(bpc, maxiter=maxiter if maxiter is not None else kw["maxiter"],
+                 tolerance=tolerance if tolerance is not None else kw["tolerance"], edge_sequence=edge_sequence)
+    return partitionfunction(bpc)
 
 
 def _csign(x: complex) -> complex:

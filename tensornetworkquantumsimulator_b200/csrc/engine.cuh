@@ -68,6 +68,11 @@ struct tnqs_ctx {
   void* bp_cache = nullptr;                        // BpPlanCache: last BP plan, reused while sites / bonds are unchanged
   long long state_version = 0;                     // bumped whenever a site pointer or a bond dimension changes                    // GateBatch between tnqs_apply_2site_begin and _end
 
+  // Bilinear form <phi|psi> (src/Forms/bilinearform.jl:28-54): when `bra` is attached, every BP contraction of this handle closes
+  // its ket tensors against the conjugated site tensors of that handle instead of its own (messages are then not Hermitian).
+  tnqs_ctx* bra = nullptr;
+  const cplx* bra_site(int v) const { return bra ? bra->site[v] : site[v]; }
+
   // ---- graph helpers ----
   int other(int e, int v) const { return esrc[e] == v ? edst[e] : esrc[e]; }
   int dsrc(int k) const { return (k & 1) ? edst[k >> 1] : esrc[k >> 1]; }
@@ -437,7 +442,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
           sl.fastN = N; fast[j] = 1; sl.close_cap = ch.split_cap;
           const int v = ch.v, F = (int)ch.absorb.size();
           SlabDesc a; a.t = c->site[v]; a.x = buf0[j]; a.F = F;
-          CloseDmmaDesc b; b.x = buf0[j]; b.t = c->site[v]; b.partial = partial + fast_poff[j]; b.F = F; b.nsplit = cm.nsplit;
+          CloseDmmaDesc b; b.x = buf0[j]; b.t = c->bra_site(v); b.partial = partial + fast_poff[j]; b.F = F; b.nsplit = cm.nsplit;
           b.epilogue = nullptr; b.ticket = nullptr;
           long long stride = 2;
           int ai = 0;
@@ -534,7 +539,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         cplx* part = partial + fast_poff[j];
         if (!fast[j]) {
           ModeCloseDesc d;
-          d.a = curp[j]; d.b = c->site[v]; d.partial = part;
+          d.a = curp[j]; d.b = c->bra_site(v); d.partial = part;
           d.L = (int)Lp; d.R = (int)R; d.n = n; d.np = n;
           d.a_sb = Lp; d.a_sr = Lp * n; d.b_sb = Lp; d.b_sr = Lp * n;
           d.nsplit = cm.nsplit; d.rows_per_split = (Lp * R + cm.nsplit - 1) / cm.nsplit;
@@ -702,7 +707,7 @@ static bool build_sweep_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>&
     const int v = ch.v, F = (int)ch.absorb.size();
     SlabDesc& a = sd[i]; CloseDmmaDesc& b = dc[i]; CloseReduceDesc& r = rd[i];
     a.t = c->site[v]; a.x = plan.scratch + (size_t)(i % R) * xslot; a.F = F;
-    b.x = a.x; b.t = a.t; b.partial = plan.partial + (size_t)(i % R) * pslot; b.F = F; b.nsplit = nsplit[i];
+    b.x = a.x; b.t = c->bra_site(v); b.partial = plan.partial + (size_t)(i % R) * pslot; b.F = F; b.nsplit = nsplit[i];
     b.epilogue = nullptr; b.ticket = nullptr;
     long long stride = 2; int ai = 0;
     for (int l = 0; l < (int)c->inc[v].size(); ++l) {

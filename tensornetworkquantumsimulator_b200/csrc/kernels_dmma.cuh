@@ -437,15 +437,19 @@ __device__ __forceinline__ void sweep_wait_chains(const SweepQueue& Q, const int
 }
 
 // One update of a degree-2 vertex (F == 1) by a whole CTA: X[s,i',w] = sum_i T[s,i,w] m[i,i'];
-// M[w,w'] = sum_{s,i'} X[s,i',w] conj(T[s,i',w']) -> partial (nsplit == 1).  Shared memory: 5 N^2 complex.
+// M[w,w'] = sum_{s,i'} X[s,i',w] conj(B[s,i',w']) -> partial (nsplit == 1), B = b.t (the site tensor itself, or the bra of a
+// bilinear form).  Shared memory: 7 N^2 complex.
 template <int N>
 __device__ __forceinline__ void small_chain_body(const SlabDesc& a, const CloseDmmaDesc& b, cplx* sm) {
   cplx* Ts = sm;                    // [s][i][w]
   cplx* Xs = sm + 2 * N * N;        // [s][i'][w]
   cplx* Ms = sm + 4 * N * N;        // m[i][i']
+  cplx* Bs = sm + 5 * N * N;        // [s][i'][w'] of the closing tensor
   for (int idx = threadIdx.x; idx < 2 * N * N; idx += blockDim.x) {
     const int s = idx & 1, i = (idx >> 1) % N, w = (idx >> 1) / N;
-    Ts[(s * N + i) * N + w] = a.t[s + (long long)i * a.g[0] + (long long)w * a.gw];
+    const long long off = s + (long long)i * a.g[0] + (long long)w * a.gw;
+    Ts[(s * N + i) * N + w] = a.t[off];
+    Bs[(s * N + i) * N + w] = b.t[off];
   }
   for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) Ms[idx] = __ldcg(a.m[0] + idx);
   __syncthreads();
@@ -459,7 +463,7 @@ __device__ __forceinline__ void small_chain_body(const SlabDesc& a, const CloseD
   for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
     const int w = idx % N, wp = idx / N;
     cplx acc = cmake(0, 0);
-    for (int k = 0; k < 2 * N; ++k) cfma(acc, Xs[k * N + w], cconj(Ts[k * N + wp]));
+    for (int k = 0; k < 2 * N; ++k) cfma(acc, Xs[k * N + w], cconj(Bs[k * N + wp]));
     __stcg(b.partial + idx, acc);
   }
   __syncthreads();

@@ -1683,6 +1683,20 @@ extern "C" int32_t tnqs_halo_close(tnqs_ctx* c) {
   ++c->state_version;
   API_END(c)
 }
+extern "C" int32_t tnqs_set_bra(tnqs_ctx* c, tnqs_ctx* bra) {
+  API_BEGIN(c)
+  if (bra) {
+    REQUIRE(bra != c && bra->device == c->device && bra->nv == c->nv && bra->ne == c->ne && bra->esrc == c->esrc && bra->edst == c->edst,
+            TNQS_ERR_INVALID_ARG, "tnqs_set_bra: the bra must be another handle on the same device with the same graph");
+    REQUIRE(bra->d == c->d && bra->chi == c->chi, TNQS_ERR_SHAPE, "tnqs_set_bra: site and bond dimensions of ket and bra must agree");
+    CU(cudaStreamSynchronize(bra->stream));
+  }
+  c->sync();
+  bp_cache_drop(c);
+  c->bra = bra;
+  ++c->state_version;
+  API_END(c)
+}
 extern "C" int32_t tnqs_set_partition(tnqs_ctx* c, const int32_t* owner, int32_t rank) {
   if (!c) return TNQS_ERR_INVALID_ARG;
   if (!owner) { c->partitioned = false; c->owner.clear(); return TNQS_OK; }

@@ -175,7 +175,11 @@ class BeliefPropagationCache:
         return self.psi.g
 
     def copy(self) -> "BeliefPropagationCache":
-        return BeliefPropagationCache(self.psi.copy(), _keep_messages=True)
+        out = BeliefPropagationCache(self.psi.copy(), _keep_messages=True)
+        bra = getattr(self, "_bra", None)
+        if bra is not None:
+            _attach_bra(out, bra)
+        return out
 
 
 def network(x) -> TensorNetworkState:
@@ -507,6 +511,28 @@ def partitionfunction(bpc: BeliefPropagationCache) -> complex:
     if np.any(den == 0):
         return 0.0
     return complex(np.exp(np.sum(np.log(num)) - np.sum(np.log(den))))
+
+
+def _attach_bra(bpc: "BeliefPropagationCache", bra: Optional[TensorNetworkState]) -> None:
+    check(bpc.psi._h.ptr, _lib.load().tnqs_set_bra(bpc.psi._h.ptr, bra._h.ptr if bra is not None else None))
+    bpc._bra = bra                                   # keeps the bra's handle alive while it is attached
+
+
+def bilinear_cache(psi: TensorNetworkState, phi: TensorNetworkState) -> "BeliefPropagationCache":
+    """BeliefPropagationCache(BilinearForm(psi, phi)) (src/Forms/bilinearform.jl:28-37): BP messages of <phi|psi>; phi must share
+    psi's graph, site and bond dimensions and stay unchanged while the cache lives."""
+    bpc = BeliefPropagationCache(psi.copy())
+    _attach_bra(bpc, phi)
+    return bpc
+
+
+def inner(psi: TensorNetworkState, phi: TensorNetworkState, alg: str = "bp", cache_update_kwargs: Optional[dict] = None) -> complex:
+    """inner(psi, phi; alg = "bp") = <phi|psi> by BP on the bilinear form (src/inner.jl:82-86): exact on trees."""
+    if alg != "bp":
+        raise ValueError("Only alg='bp' is on the CUDA path")
+    kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(psi)
+    bpc = update(bilinear_cache(psi, phi), inplace=True, **kw)
+    return partitionfunction(bpc)
 
 
 def norm_sqr(x, alg: str = "bp", cache_update_kwargs: Optional[dict] = None) -> complex:

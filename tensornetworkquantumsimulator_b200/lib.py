@@ -22,7 +22,7 @@ SYMBOLS = [
     "tnqs_get_site", "tnqs_set_sites", "tnqs_get_sites", "tnqs_fill_random", "tnqs_set_message", "tnqs_get_message", "tnqs_reset_messages",
     "tnqs_bp_update", "tnqs_apply_1site", "tnqs_apply_2site", "tnqs_apply_2site_begin", "tnqs_apply_2site_end", "tnqs_apply_circuit", "tnqs_apply_circuit_fetch", "tnqs_rdm_1site",
     "tnqs_expect_2site_nn", "tnqs_expect_path", "tnqs_vertex_scalars", "tnqs_edge_scalars", "tnqs_rescale", "tnqs_symmetric_gauge",
-    "tnqs_truncate", "tnqs_message_slab", "tnqs_halo_pack", "tnqs_halo_unpack", "tnqs_set_partition", "tnqs_halo_alloc", "tnqs_halo_peer", "tnqs_halo_route", "tnqs_halo_close",
+    "tnqs_truncate", "tnqs_message_slab", "tnqs_halo_pack", "tnqs_halo_unpack", "tnqs_set_partition", "tnqs_set_bra", "tnqs_halo_alloc", "tnqs_halo_peer", "tnqs_halo_route", "tnqs_halo_close",
     "tnqs_kernel_launches", "tnqs_bp_sweeps_total", "tnqs_bp_message_updates_total", "tnqs_profile_enable", "tnqs_profile_read", "tnqs_stream",
 ]
 
@@ -91,6 +91,7 @@ def load() -> C.CDLL:
     lib.tnqs_message_slab.argtypes = [p, C.POINTER(vp), i64p, i64p]
     lib.tnqs_halo_pack.argtypes = [p, i32, i32p, vp]; lib.tnqs_halo_unpack.argtypes = [p, i32, i32p, vp]
     lib.tnqs_set_partition.argtypes = [p, i32p, i32]
+    lib.tnqs_set_bra.argtypes = [p, p]
     lib.tnqs_halo_alloc.argtypes = [p, i32, i32, i32p, vp, C.POINTER(vp)]
     lib.tnqs_halo_peer.argtypes = [p, i32, vp, vp, i32]
     lib.tnqs_halo_route.argtypes = [p, i32, i32p, i32p, i32p]

@@ -903,3 +903,35 @@ def test_apply_gates_fetch_returns_final_sites(E):
         assert np.array_equal(bufs[v][:2 * ns[v]].view(np.complex128), ta[v].ravel(order="F"))
     for k in range(2 * g.ne):
         assert np.array_equal(E.message(a, k), E.message(b, k))
+
+
+@pytest.mark.parametrize("name,chi", [("comb3x3", 3), ("grid4x4", 4), ("grid4x4", 8)])
+def test_bilinear_form_bp_inner(E, name, chi):
+    # BilinearForm BP (tnqs_set_bra): messages of <phi|psi> after fixed sweeps against the oracle (1e-10), the partition function
+    # = inner(psi, phi; alg = "bp") (src/inner.jl:82-86), exact on the tree; chi = 8 runs the tensor-core sweep kernel with a bra
+    g = GRAPHS[name]()
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=chi, seed=31)
+    phi_o = O.random_tensornetworkstate(g, bond_dimension=chi, seed=32)
+    for s in (psi_o, phi_o):
+        for v in range(g.nv):
+            s.tensors[v] /= np.linalg.norm(s.tensors[v])
+    seq = G.forest_cover_edge_sequence(g)
+    psi_e = E.TensorNetworkState.from_arrays(g, psi_o.tensors, chi_cap=chi)
+    phi_e = E.TensorNetworkState.from_arrays(g, phi_o.tensors, chi_cap=chi)
+    bo = O.update(O.BeliefPropagationCache(psi_o.copy(), {}, phi_o), maxiter=3, edge_sequence=seq)
+    be = E.update(E.bilinear_cache(psi_e, phi_e), maxiter=3, edge_sequence=seq, inplace=True)
+    check_messages(E, be, bo)
+    zo, ze = O.partitionfunction(bo), E.partitionfunction(be)
+    assert abs(ze - zo) < 1e-9 * abs(zo)
+    bc = be.copy()                                       # a copy stays a bilinear form
+    E.update(bc, maxiter=1, edge_sequence=seq, inplace=True)
+    bo1 = O.update(bo, maxiter=1, edge_sequence=seq)
+    check_messages(E, bc, bo1)
+    if name == "comb3x3":
+        exact = np.vdot(O.to_statevector(phi_o), O.to_statevector(psi_o))
+        assert abs(E.inner(psi_e, phi_e) - exact) < 1e-10 * abs(exact)
+    # detaching the bra gives the norm network back
+    from tensornetworkquantumsimulator_b200 import engine as _E
+    _E._attach_bra(be, None)
+    bn = E.update(E.BeliefPropagationCache(be.psi), maxiter=3, edge_sequence=seq, inplace=True)      # (the constructor resets the messages)
+    check_messages(E, bn, O.update(O.BeliefPropagationCache(psi_o), maxiter=3, edge_sequence=seq))

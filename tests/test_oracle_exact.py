@@ -222,3 +222,16 @@ def test_bp_sampling_known_answers():
     outs, _ = O.sample(ghz(gt), 8, rng=np.random.default_rng(1))
     assert all(len(set(s.values())) == 1 for s in outs)
     assert {next(iter(s.values())) for s in outs} == {0, 1}
+
+
+def test_bilinear_form_bp_is_exact_on_trees_and_reduces_to_the_norm():
+    # inner(psi, phi; alg = "bp") (src/inner.jl:82-86 over src/Forms/bilinearform.jl:28-54): <phi|psi> exactly on a tree;
+    # BilinearForm(psi, psi) is the norm network
+    g = G.named_comb_tree((3, 3))
+    psi = O.random_tensornetworkstate(g, bond_dimension=3, seed=1)
+    phi = O.random_tensornetworkstate(g, bond_dimension=3, seed=2)
+    exact = np.vdot(O.to_statevector(phi), O.to_statevector(psi))
+    assert abs(O.inner(psi, phi) - exact) < 1e-12 * abs(exact)
+    assert abs(O.inner(phi, psi) - np.conj(exact)) < 1e-12 * abs(exact)
+    n2 = O.partitionfunction(O.update(O.BeliefPropagationCache(psi)))
+    assert abs(O.inner(psi, psi) - n2) < 1e-13 * abs(n2)
