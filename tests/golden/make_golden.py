@@ -47,6 +47,29 @@ def circuit_case():
     np.savez(os.path.join(HERE, "circuit_c1_4x4.npz"), bond_dims=psi.bond_dims(), expect_z=z, expect_zz=zz, errs=errs)
 
 
+def bp_tensor_core_case():
+    # uniform chi = 8 grid: the shape the FP64 tensor-core kernels (k_bp_sweep / k_absorb_slab / k_close_dmma) carry, plus
+    # the BP inner product of two states on it (bilinear form)
+    g = G.named_grid((4, 4))
+    psi = O.random_tensornetworkstate(g, bond_dimension=8, seed=51)
+    phi = O.random_tensornetworkstate(g, bond_dimension=8, seed=52)
+    for s in (psi, phi):
+        for v in range(g.nv):
+            s.tensors[v] /= np.linalg.norm(s.tensors[v])
+    seq = G.forest_cover_edge_sequence(g)
+    info = {}
+    bpc = O.update(O.BeliefPropagationCache(psi), maxiter=4, tolerance=0.0, edge_sequence=seq, info=info)
+    msgs = np.stack([O.message(bpc, k) for k in range(2 * g.ne)])
+    z = np.array([O.expect(bpc, ("Z", [g.names[v]])) for v in range(g.nv)])
+    bj = O.BeliefPropagationCache(psi)
+    for _ in range(2):
+        bj.messages = {k: O.updated_message(bj, k) for k in range(2 * g.ne)}
+    bb = O.update(O.BeliefPropagationCache(psi.copy(), {}, phi), maxiter=4, edge_sequence=seq)
+    np.savez(os.path.join(HERE, "bp_grid4x4_chi8.npz"), seed_psi=51, seed_phi=52, chi=8, seq=seq, messages=msgs, expect_z=z, mean_diff=info["mean_diff"],
+             jacobi_messages=np.stack([O.message(bj, k) for k in range(2 * g.ne)]),
+             bilinear_messages=np.stack([O.message(bb, k) for k in range(2 * g.ne)]), bilinear_z=O.partitionfunction(bb))
+
+
 if __name__ == "__main__":
-    bp_case(); gate_case(); circuit_case()
+    bp_case(); gate_case(); circuit_case(); bp_tensor_core_case()
     print(sorted(os.listdir(HERE)))
