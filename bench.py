@@ -98,9 +98,9 @@ class ClockSampler:
     def _poll(self):
         period = float(os.environ.get("TNQS_BENCH_SMI_MS", "100")) * 1e-3
         n = self.nvml
-        while not self.stop_flag:
-            if self.windowed and not self.window.wait(0.02):
-                continue
+        last = 0.0
+
+        def sample():
             try:
                 self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
                 try:
@@ -112,7 +112,21 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(period)
+
+        while not self.stop_flag:
+            if self.windowed:
+                # one query at the OPENING of a GPU-bound window (a BP refresh lasts >= 10 ms), never late in it: the query must be
+                # over before the host-driven phase that follows starts launching
+                if not self.window.wait(0.02):
+                    continue
+                if time.monotonic() - last >= period:
+                    sample()
+                    last = time.monotonic()
+                while self.window.is_set() and not self.stop_flag:
+                    time.sleep(0.001)
+            else:
+                sample()
+                time.sleep(period)
 
     def _read(self):
         for line in self.proc.stdout:
