@@ -44,3 +44,23 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_bench_work_counts_match_the_survey():
+    # the algorithmic work per unit behind `roofline.achieved`: 8 z d chi^(z+1) flops per message,
+    # 0.426 GFLOP per interior two-site gate at chi = 16
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import numpy as np
+    import bench
+    from tensornetworkquantumsimulator_b200 import graphs as G
+    g = G.named_grid((32, 32))
+    fm = bench.flops_per_message(g, 16)
+    assert len(fm) == 3968 and fm.max() == 8 * 4 * 2 * 16 ** 5 == 67108864
+    assert abs(fm.mean() / 1e6 - 61.17) < 0.01                      # lattice average quoted in DESIGN.md
+    interior = [e for e in range(g.ne) if g.degree(int(g.esrc[e])) == 4 and g.degree(int(g.edst[e])) == 4]
+    assert abs(bench.gate_flops(g, interior[0], 16) / 1e9 - 0.426) < 0.002
+    groups = G.grid_edge_color(g)
+    avg = np.mean([bench.gate_flops(g, e, 16) for grp in groups for e in grp])
+    assert abs(avg / 1e9 - 0.3907) < 0.001
+    assert bench.psi_bytes(g, 16) == sum(16 * 2 * 16 ** g.degree(v) for v in range(g.nv))
