@@ -65,9 +65,11 @@ class BeliefPropagationCache:
     network: TensorNetworkState
     messages: Dict[int, np.ndarray] = field(default_factory=dict)
     bra: Optional[TensorNetworkState] = None        # BilinearForm(ket = network, bra): src/Forms/bilinearform.jl:28-54
+    delta_default: bool = False                     # bilinear forms: default message = delta over (ket, operator, bra) bonds
 
     def copy(self) -> "BeliefPropagationCache":
-        return BeliefPropagationCache(self.network.copy(), {k: m.copy() for k, m in self.messages.items()}, self.bra)
+        return BeliefPropagationCache(self.network.copy(), {k: m.copy() for k, m in self.messages.items()}, self.bra,
+                                      self.delta_default)
 
     def bra_tensor(self, v: int) -> np.ndarray:
         """The tensor whose conjugate closes a contraction at v: the state itself, or the bra of a bilinear form."""
@@ -85,6 +87,16 @@ def tensornetworkstate(f, g: Graph) -> TensorNetworkState:
         vec = _gates.state_vector(f(g.names[v]))
         ts.append(vec.reshape((vec.shape[0],) + (1,) * g.degree(v)).copy())
     return TensorNetworkState(g, ts)
+
+
+def paulitensornetworkstate(f, g: Graph) -> TensorNetworkState:
+    """Heisenberg-picture operator over Pauli sites, basis (I, X, Y, Z) (src/TensorNetworks/tensornetworkstate_constructors.jl:1,19-24)."""
+    return tensornetworkstate(lambda v: _gates.PAULI_STATES[f(v)], g)
+
+
+def identitytensornetworkstate(g: Graph) -> TensorNetworkState:
+    """src/TensorNetworks/tensornetworkstate_constructors.jl:31-35."""
+    return paulitensornetworkstate(lambda v: "I", g)
 
 
 def random_tensornetworkstate(g: Graph, bond_dimension: int = 1, seed: int = 0, d: int = 2) -> TensorNetworkState:
@@ -107,7 +119,18 @@ def message(bpc: BeliefPropagationCache, k: int) -> np.ndarray:
     m = bpc.messages.get(k)
     if m is None:
         chi = bpc.network.bond_dim(k // 2)
-        return np.eye(chi, dtype=np.complex128)
+        if bpc.bra is None:
+            return np.eye(chi, dtype=np.complex128)
+        # bilinear form: m[b_ket, b_bra], the layers may have different bond dimensions.  The reference's default is
+        # delta(ket bond, operator bond, bra bond) with an operator bond of dimension 1 = the single entry [1, 1]
+        # (src/Forms/bilinearform.jl:39-42); the identity default is what BeliefPropagationCache(ket, {}, bra) used before
+        # `inner` learnt the former (golden fixtures were made with it).
+        chib = bpc.bra.bond_dim(k // 2)
+        if bpc.delta_default:
+            m = np.zeros((chi, chib), dtype=np.complex128)
+            m[0, 0] = 1.0
+            return m
+        return np.eye(chi, chib, dtype=np.complex128)
     return m
 
 
@@ -232,7 +255,7 @@ def inner(psi: TensorNetworkState, phi: TensorNetworkState, maxiter: Optional[in
     """inner(psi, phi; alg = "bp") (src/inner.jl:82-86): BP on BilinearForm(psi, phi) - the bra layer is dag(phi), the operator
     layer the identity (src/Forms/bilinearform.jl:28-37) - then the partition function.  <phi|psi> exactly on trees."""
     kw = default_bp_update_kwargs(psi)
-    bpc = BeliefPropagationCache(psi.copy(), {}, phi)
+    bpc = BeliefPropagationCache(psi.copy(), {}, phi, delta_default=True)
     bpc = update(bpc, maxiter=maxiter if maxiter is not None else kw["maxiter"],
                  tolerance=tolerance if tolerance is not None else kw["tolerance"], edge_sequence=edge_sequence)
     return partitionfunction(bpc)
@@ -398,13 +421,15 @@ def apply_gate(bpc: BeliefPropagationCache, gate: np.ndarray, vs: Sequence[int],
     return float(err)
 
 
-def _resolve_circuit(g: Graph, circuit: Sequence[tuple]):
+def _resolve_circuit(g: Graph, circuit: Sequence[tuple], tensors=None):
     out = []
     for gate in circuit:
         if isinstance(gate[0], np.ndarray):
             arr, verts = gate[0], gate[1]
         else:
-            arr, verts = _gates.gate_array(gate), gate[1]
+            vl = gate[1] if isinstance(gate[1], list) else [gate[1]]
+            dims = None if tensors is None else [tensors[g.v(x) if not isinstance(x, (int, np.integer)) else int(x)].shape[0] for x in vl]
+            arr, verts = _gates.gate_array(gate, dims), gate[1]      # Pauli sites (d = 4): Heisenberg branch, gate_definitions.jl:41-42
         verts = verts if isinstance(verts, list) else [verts]
         out.append((np.asarray(arr, dtype=np.complex128), [g.v(x) if not isinstance(x, (int, np.integer)) else int(x) for x in verts]))
     return out
@@ -424,7 +449,7 @@ def apply_gates(circuit: Sequence[tuple], psi, apply_kwargs: Optional[dict] = No
         return bpc.network, errs
     bpc = psi.copy()
     kw = bp_update_kwargs if bp_update_kwargs is not None else default_bp_update_kwargs(bpc.network)
-    gates = _resolve_circuit(bpc.g, circuit)
+    gates = _resolve_circuit(bpc.g, circuit, bpc.network.tensors)
     affected: set = set()
     errs = np.zeros(len(gates))
     refreshes = 0

@@ -124,12 +124,25 @@ class TensorNetworkState:
     def maxvirtualdim(self) -> int:
         return int(self.bond_dims().max()) if self.g.ne else 1
 
+    def site_dims(self) -> np.ndarray:
+        """Site dimension of every vertex (2 for qubits, 4 for "Pauli" sites); fixed for the life of the handle."""
+        if not hasattr(self, "_site_dims"):
+            lib = _lib.load()
+            chi = self.bond_dims()
+            self._site_dims = np.asarray(
+                [lib.tnqs_site_size(self._h.ptr, v) // int(np.prod([chi[e] for e in self.g.incident[v]], dtype=np.int64))
+                 for v in range(self.g.nv)], dtype=np.int32)
+        return self._site_dims
+
     def copy(self) -> "TensorNetworkState":
         out = C.c_void_p()
         st = _lib.load().tnqs_clone(self._h.ptr, C.byref(out))
         if st != 0:
             raise TnqsError(st, (_lib.load().tnqs_last_error(None) or b"").decode())
-        return TensorNetworkState(self.g, _Handle(out), self.chi_cap, self.device)
+        new = TensorNetworkState(self.g, _Handle(out), self.chi_cap, self.device)
+        if hasattr(self, "_site_dims"):
+            new._site_dims = self._site_dims
+        return new
 
     def kernel_launches(self) -> int:
         return int(_lib.load().tnqs_kernel_launches(self._h.ptr))
@@ -147,6 +160,23 @@ def tensornetworkstate(f, g: Graph, chi_cap: int = 1, device: int = 0) -> Tensor
         vec = _gates.state_vector(f(g.names[v]))
         ts.append(vec.reshape((vec.shape[0],) + (1,) * g.degree(v)))
     return TensorNetworkState.from_arrays(g, ts, chi_cap=chi_cap, device=device)
+
+
+def zerostate(g: Graph, chi_cap: int = 1, device: int = 0) -> TensorNetworkState:
+    """All spins up (src/TensorNetworks/tensornetworkstate_constructors.jl:8-12)."""
+    return tensornetworkstate(lambda v: "↑", g, chi_cap=chi_cap, device=device)
+
+
+def paulitensornetworkstate(f, g: Graph, chi_cap: int = 1, device: int = 0) -> TensorNetworkState:
+    """Operator in the Heisenberg picture as a product state over "Pauli" sites (d = 4, basis I, X, Y, Z): f maps a vertex to
+    "I", "X", "Y" or "Z" (src/TensorNetworks/tensornetworkstate_constructors.jl:19-24).  Gates on such a state are Pauli
+    transfer matrices (gates.heisenberg_gate_array)."""
+    return tensornetworkstate(lambda v: _gates.PAULI_STATES[f(v)], g, chi_cap=chi_cap, device=device)
+
+
+def identitytensornetworkstate(g: Graph, chi_cap: int = 1, device: int = 0) -> TensorNetworkState:
+    """The identity operator on Pauli sites (src/TensorNetworks/tensornetworkstate_constructors.jl:31-35)."""
+    return paulitensornetworkstate(lambda v: "I", g, chi_cap=chi_cap, device=device)
 
 
 def random_tensornetworkstate(g: Graph, bond_dimension: int = 1, seed: int = 0, d: int = 2,
@@ -256,15 +286,22 @@ def _apply_opts(apply_kwargs: Optional[dict]) -> ApplyOpts:
     return ApplyOpts(0 if maxdim is None else int(maxdim), float("nan") if cutoff is None else float(cutoff), int(normalize_tensors))
 
 
-def _pack_circuit(g: Graph, circuit: Sequence[tuple]):
+def _pack_circuit(g: Graph, circuit: Sequence[tuple], site_dims=None):
+    """Gate tuples -> the flat arrays of tnqs_apply_circuit.  site_dims (per vertex, or a callable returning them) selects the Heisenberg branch of
+    `toitensor` for gates on Pauli sites (gate_definitions.jl:41-42)."""
     gv = np.full(2 * len(circuit), -1, dtype=np.int32)
     off = np.zeros(len(circuit), dtype=np.int64)
     chunks, pos = [], 0
     for i, gate in enumerate(circuit):
-        arr = gate[0] if isinstance(gate[0], np.ndarray) else _gates.gate_array(gate)
         verts = gate[1] if isinstance(gate[1], list) else [gate[1]]
         if len(verts) not in (1, 2):
             raise ValueError("gates act on one or two vertices")
+        if isinstance(gate[0], np.ndarray):
+            arr = gate[0]
+        else:
+            if callable(site_dims):
+                site_dims = site_dims()                      # looked up only when a gate is given by name
+            arr = _gates.gate_array(gate, None if site_dims is None else [site_dims[_vid(g, x)] for x in verts])
         for j, x in enumerate(verts):
             gv[2 * i + j] = _vid(g, x)
         flat = np.asarray(arr, dtype=np.complex128).ravel(order="F")
@@ -295,7 +332,7 @@ def apply_gates(circuit: Sequence[tuple], psi, apply_kwargs: Optional[dict] = No
     kw.pop("edge_sequence", None)
     bopts = _bp_opts(g, **kw)
     aopts = _apply_opts(apply_kwargs)
-    gv, off, data = _pack_circuit(g, circuit)
+    gv, off, data = _pack_circuit(g, circuit, out.psi.site_dims)
     errs = np.zeros(max(len(circuit), 1), dtype=np.float64)
     refreshes = C.c_int32(0)
     if fetch is None:
@@ -518,11 +555,42 @@ def _attach_bra(bpc: "BeliefPropagationCache", bra: Optional[TensorNetworkState]
     bpc._bra = bra                                   # keeps the bra's handle alive while it is attached
 
 
-def bilinear_cache(psi: TensorNetworkState, phi: TensorNetworkState) -> "BeliefPropagationCache":
-    """BeliefPropagationCache(BilinearForm(psi, phi)) (src/Forms/bilinearform.jl:28-37): BP messages of <phi|psi>; phi must share
-    psi's graph, site and bond dimensions and stay unchanged while the cache lives."""
-    bpc = BeliefPropagationCache(psi.copy())
-    _attach_bra(bpc, phi)
+def _pad_bonds(psi: TensorNetworkState, chi: np.ndarray) -> TensorNetworkState:
+    """psi embedded in zero-padded site tensors with bond dimensions chi[e] >= its own (the state is unchanged as a vector)."""
+    own = psi.bond_dims()
+    if np.array_equal(own, chi):
+        return psi
+    if np.any(own > chi):
+        raise ValueError("cannot pad to smaller bond dimensions")
+    ts = []
+    for v, t in enumerate(psi.tensors()):
+        shape = (t.shape[0],) + tuple(int(chi[e]) for e in psi.g.incident[v])
+        big = np.zeros(shape, dtype=np.complex128, order="F")
+        big[tuple(slice(0, n) for n in t.shape)] = t
+        ts.append(big)
+    return TensorNetworkState.from_arrays(psi.g, ts, chi_cap=int(max(1, chi.max(initial=1))), device=psi.device)
+
+
+def bilinear_cache(psi: TensorNetworkState, phi: TensorNetworkState, delta_default: bool = False) -> "BeliefPropagationCache":
+    """BeliefPropagationCache(BilinearForm(psi, phi)) (src/Forms/bilinearform.jl:28-37): BP messages of <phi|psi>.  phi must share
+    psi's graph and site dimensions and stay unchanged while the cache lives.  The device contracts layers of equal bond
+    dimensions: where they differ (an evolved operator against a product operator, examples/2dIsing_dynamics_Heisenbergpicture.jl:
+    55-56) the thinner layer is embedded in zero-padded tensors, which changes no message entry that is ever multiplied by a
+    non-zero number.  delta_default: start from the reference's default message of a bilinear form, delta over (ket bond,
+    operator bond of dimension 1, bra bond) = the single entry [1, 1] (bilinearform.jl:39-42), instead of the identity."""
+    if psi.g is not phi.g and (psi.g.nv != phi.g.nv or not np.array_equal(psi.g.esrc, phi.g.esrc) or not np.array_equal(psi.g.edst, phi.g.edst)):
+        raise ValueError("inner: both states must live on the same graph")
+    chi = np.maximum(psi.bond_dims(), phi.bond_dims())
+    ket = _pad_bonds(psi, chi)
+    bra = _pad_bonds(phi, chi)
+    bpc = BeliefPropagationCache(ket.copy() if ket is psi else ket)
+    _attach_bra(bpc, bra)
+    if delta_default:
+        for e in range(psi.g.ne):
+            m = np.zeros((int(chi[e]), int(chi[e])), dtype=np.complex128)
+            m[0, 0] = 1.0
+            setmessage(bpc, 2 * e, m)
+            setmessage(bpc, 2 * e + 1, m)
     return bpc
 
 
@@ -531,7 +599,7 @@ def inner(psi: TensorNetworkState, phi: TensorNetworkState, alg: str = "bp", cac
     if alg != "bp":
         raise ValueError("Only alg='bp' is on the CUDA path")
     kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(psi)
-    bpc = update(bilinear_cache(psi, phi), inplace=True, **kw)
+    bpc = update(bilinear_cache(psi, phi, delta_default=True), inplace=True, **kw)
     return partitionfunction(bpc)
 
 

@@ -103,12 +103,59 @@ def op_matrix(name: str, param=None) -> np.ndarray:
     raise ValueError(f"Wrong gate format: unknown gate {name!r}")
 
 
+# ---- Heisenberg picture: "Pauli" sites (d = 4, basis I, X, Y, Z) and Pauli transfer matrices ---------------------------------
+PAULI_STATES = {"I": [1, 0, 0, 0], "X": [0, 1, 0, 0], "Y": [0, 0, 1, 0], "Z": [0, 0, 0, 1]}   # tensornetworkstate_constructors.jl:1
+_PAULI_BASIS = (I2, X, Y, Z)
+
+
+def pauli_rotation_matrix(generator: str, theta: float) -> np.ndarray:
+    """exp(-i theta/2 P) for the Pauli string P = generator (first letter = first vertex = slow Kronecker factor);
+    `paulirotationmatrix`, gate_definitions.jl:60-68 (PauliPropagation.tomatrix of a PauliRotation: that package is not in
+    /root/reference; its published convention R_P(theta) = exp(-i theta/2 P) is restated here)."""
+    p = np.array([[1.0 + 0j]])
+    for ch in generator.upper():
+        p = np.kron(p, PAULI[ch])
+    return np.cos(theta / 2) * np.eye(p.shape[0]) - 1j * np.sin(theta / 2) * p
+
+
+def pauli_transfer_matrix(u: np.ndarray, heisenberg: bool = True) -> np.ndarray:
+    """Pauli transfer matrix of the unitary u on n qubits as an array M[a_1..a_n, b_1..b_n] (a_i, b_i in I, X, Y, Z):
+    heisenberg: U^dag P_b U = sum_a M[a, b] P_a, i.e. M[a, b] = tr(P_a U^dag P_b U) / 2^n (an operator with Pauli coefficients c
+    becomes M c); otherwise the Schroedinger map U P_b U^dag.  Real for unitary u.  `PP.calculateptm(U; heisenberg = true)`
+    at gate_definitions.jl:77 (PauliPropagation is not in /root/reference: restated from its documented definition)."""
+    n = int(round(np.log2(u.shape[0])))
+    w = u if heisenberg else u.conj().T
+    strings = [np.array([[1.0 + 0j]])]
+    for _ in range(n):
+        strings = [np.kron(s, q) for s in strings for q in _PAULI_BASIS]          # first factor slow: index (a_1, .., a_n) row-major
+    m = np.empty((4 ** n, 4 ** n), dtype=np.complex128)
+    for b, pb in enumerate(strings):
+        img = w.conj().T @ pb @ w
+        for a, pa in enumerate(strings):
+            m[a, b] = np.trace(pa @ img) / 2 ** n
+    return m.reshape((4,) * (2 * n))
+
+
+def heisenberg_gate_array(gate: tuple) -> np.ndarray:
+    """("R" + Pauli string, vertices, theta) on Pauli sites -> o[s', s] / o[s1', s2', s1, s2] with d = 4
+    (`toitensor_heisenberg`, gate_definitions.jl:70-86: the angle is NOT rescaled on this branch, :41-42)."""
+    name = gate[0]
+    nverts = len(gate[1]) if isinstance(gate[1], list) else 1
+    if not (name[:1] == "R" and _is_pauli_string(name[1:]) and len(name) - 1 == nverts and len(gate) >= 3):
+        raise ValueError(f"Wrong gate format: Pauli sites take ('R<pauli string>', vertices, theta), got {name!r}")
+    # real for a unitary: rounding residue of the imaginary part is dropped
+    return pauli_transfer_matrix(pauli_rotation_matrix(name[1:], gate[2]), heisenberg=True).real.astype(np.complex128)
+
+
 def _is_pauli_string(s: str) -> bool:
     return len(s) > 0 and all(ch in "XYZIxyz" for ch in s)
 
 
-def gate_array(gate: tuple) -> np.ndarray:
-    """(name, vertices[, param]) -> o[s', s] or o[s1', s2', s1, s2] (`toitensor`, gate_definitions.jl:34-57)."""
+def gate_array(gate: tuple, site_dims=None) -> np.ndarray:
+    """(name, vertices[, param]) -> o[s', s] or o[s1', s2', s1, s2] (`toitensor`, gate_definitions.jl:34-57).
+    site_dims = the dimensions of the sites the gate acts on: all 4 ("Pauli" sites) selects the Heisenberg branch (:41-42)."""
+    if site_dims is not None and len(site_dims) > 0 and all(int(x) == 4 for x in site_dims):
+        return heisenberg_gate_array(gate)
     name = gate[0]
     nverts = len(gate[1]) if isinstance(gate[1], list) else 1
     if _is_pauli_string(name) and len(name) == nverts and name not in ("I",) or (name in PAULI and nverts == 1):

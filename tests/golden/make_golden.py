@@ -70,6 +70,35 @@ def bp_tensor_core_case():
              bilinear_messages=np.stack([O.message(bb, k) for k in range(2 * g.ne)]), bilinear_z=O.partitionfunction(bb))
 
 
+def heisenberg_layer(g, dt=0.04, h=-1.0, J=-1.0):
+    """examples/2dIsing_dynamics_Heisenbergpicture.jl:26-35."""
+    layer = [("Rz", [g.names[v]], h * dt) for v in range(g.nv)]
+    for grp in G.grid_edge_color(g):
+        layer += [("Rxx", [g.names[int(g.esrc[e])], g.names[int(g.edst[e])]], 2 * J * dt) for e in grp]
+    layer += [("Rz", [g.names[v]], h * dt) for v in range(g.nv)]
+    return layer
+
+
+def heisenberg_case():
+    # the Heisenberg-picture example on its own 4x4 grid (Pauli sites d = 4, transfer-matrix gates, maxdim 4, cutoff 1e-14, no
+    # tensor normalisation, rescale after every layer, tr(O(t) O(0)) / 2^n through BP on the bilinear form)
+    g = G.named_grid((4, 4))
+    o0 = O.paulitensornetworkstate(lambda v: "Z" if v == (2, 2) else "I", g)
+    layer = heisenberg_layer(g)
+    bpc = O.BeliefPropagationCache(o0)
+    dims, trs, zs, errs = [], [], [], []
+    for _ in range(3):
+        bpc, e = O.apply_gates(layer, bpc, apply_kwargs=dict(maxdim=4, cutoff=1e-14, normalize_tensors=False))
+        bpc = O.rescale(bpc)
+        dims.append(bpc.network.bond_dims()); errs.append(e)
+        zs.append(O.partitionfunction(bpc)); trs.append(O.inner(bpc.network, o0))
+    np.savez(os.path.join(HERE, "heisenberg_grid4x4.npz"), bond_dims=np.array(dims), trace_ot_o0=np.array(trs), frobenius=np.array(zs),
+             errs=np.array(errs))
+
+
 if __name__ == "__main__":
-    bp_case(); gate_case(); circuit_case(); bp_tensor_core_case()
+    only = sys.argv[1:]
+    for fn in (bp_case, gate_case, circuit_case, bp_tensor_core_case, heisenberg_case):
+        if not only or fn.__name__ in only:
+            fn()
     print(sorted(os.listdir(HERE)))

@@ -1,0 +1,59 @@
+"""GPU leg of the Heisenberg-picture path (tests/test_heisenberg.py holds the CPU leg): the example's 4x4 grid on Pauli sites
+through the C-ABI against the committed oracle numbers (tests/golden/heisenberg_grid4x4.npz) and the oracle itself.
+
+STATUS: written after this round's GPU minutes were spent - the host code (gates.heisenberg_gate_array, engine.paulitensornetworkstate,
+engine._pad_bonds / bilinear_cache(delta_default=True)) composes entry points that are each covered by tests/test_gpu_parity.py
+(d = 4 sites and gates: test_site_dimension_3_and_4; tnqs_set_bra: test_bilinear_form_bp_inner; growth from a product state:
+test_engine_circuit_matches_golden), but this composition has not run on a B200 yet.  The tests are therefore non-strict xfail: a
+pass shows up as XPASS in the round-end log, a failure does not mask the verified suite.  The file sorts last for the same reason."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import tnqs_oracle as O
+from tensornetworkquantumsimulator_b200 import graphs as G
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(reason="composition first written after the round's GPU budget was spent; not yet run on a B200", strict=False)]
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _layer(g):
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg.heisenberg_layer(g)
+
+
+def test_heisenberg_example_matches_golden():
+    from tensornetworkquantumsimulator_b200 import engine as E
+    d = np.load(os.path.join(GOLD, "heisenberg_grid4x4.npz"))
+    g = G.named_grid((4, 4))
+    f = lambda v: "Z" if v == (2, 2) else "I"
+    o0 = E.paulitensornetworkstate(f, g, chi_cap=4)
+    assert list(o0.site_dims()) == [4] * g.nv
+    bpc = E.BeliefPropagationCache(o0.copy())
+    kw = dict(maxdim=4, cutoff=1e-14, normalize_tensors=False)
+    for l in range(3):
+        bpc, errs = E.apply_gates(_layer(g), bpc, apply_kwargs=kw)
+        bpc = E.rescale(bpc)
+        assert list(bpc.psi.bond_dims()) == list(d["bond_dims"][l])                     # truncation ranks exact
+        assert np.allclose(errs, d["errs"][l], rtol=1e-6, atol=1e-12)
+        assert abs(E.partitionfunction(bpc) - d["frobenius"][l]) < 1e-8                 # Frobenius norm of O(t) reset to 1
+        assert abs(E.inner(bpc.psi, o0) - d["trace_ot_o0"][l]) < 1e-8                   # tr(O(t) O(0)) / 2^n, ragged chi vs chi = 1
+
+
+def test_inner_between_different_bond_dimensions_on_a_tree():
+    from tensornetworkquantumsimulator_b200 import engine as E
+    g = G.named_comb_tree((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=4, seed=71, d=4)
+    phi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=72, d=4)
+    exact = np.vdot(O.to_statevector(phi_o), O.to_statevector(psi_o))
+    assert abs(O.inner(psi_o, phi_o) - exact) < 1e-12 * abs(exact)
+    psi_e = E.TensorNetworkState.from_arrays(g, psi_o.tensors)
+    phi_e = E.TensorNetworkState.from_arrays(g, phi_o.tensors)
+    assert abs(E.inner(psi_e, phi_e) - exact) < 1e-10 * abs(exact)
+    assert abs(E.inner(phi_e, psi_e) - np.conj(exact)) < 1e-10 * abs(exact)
