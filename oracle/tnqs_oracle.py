@@ -31,7 +31,7 @@ import numpy as np
 
 from tensornetworkquantumsimulator_b200 import gates as _gates
 from tensornetworkquantumsimulator_b200 import rng as _rng
-from tensornetworkquantumsimulator_b200.graphs import Graph, forest_cover_edge_sequence, edge_color
+from tensornetworkquantumsimulator_b200.graphs import Graph, forest_cover_edge_sequence, edge_color, steiner_tree
 
 EPS = float(np.finfo(np.float64).eps)
 DEFAULT_BP_MAXITER = 25          # src/MessagePassing/beliefpropagationcache.jl:108
@@ -512,8 +512,43 @@ def _region_contract(bpc: BeliefPropagationCache, region: List[int], ops: Dict[i
     raise AssertionError
 
 
-def expect(bpc: BeliefPropagationCache, obs: tuple) -> complex:
-    """obs = (op string or list of op names, vertex names/ids[, coeff]); src/expect.jl:58-83,160-176."""
+def _tree_region_contract(bpc: BeliefPropagationCache, vertices: Sequence[int], edges: Sequence[int], ops: Dict[int, np.ndarray]) -> complex:
+    """Contract [T, conj(T) (+ op)] over the vertices of a tree region with every message that enters the region from outside
+    (src/expect.jl:66-81 with steiner_vs = the tree's vertices).  Recursive: the environment a subtree passes to its parent is a
+    matrix on their shared bond.  The region must not contain an edge of the graph outside the tree."""
+    g = bpc.g
+    vs, es = set(int(v) for v in vertices), set(int(e) for e in edges)
+    for e in range(g.ne):
+        if e not in es and int(g.esrc[e]) in vs and int(g.edst[e]) in vs:
+            raise NotImplementedError("region with a loop")
+    tree_nb = {v: [] for v in vs}
+    for e in es:
+        a, b = int(g.esrc[e]), int(g.edst[e])
+        tree_nb[a].append(b); tree_nb[b].append(a)
+
+    def absorbed(v: int, parent: Optional[int]) -> np.ndarray:
+        t = bpc.network.tensors[v]
+        ket = np.tensordot(ops[v], t, axes=([1], [0])) if v in ops else t
+        for axis, m in incoming(bpc, v, ignore=tuple(tree_nb[v])):           # messages from outside the region
+            ket = _absorb(ket, axis, m)
+        for c in tree_nb[v]:
+            if c != parent:
+                ket = _absorb(ket, 1 + g.leg(v, g.edge_of[(c, v)]), env(c, v))
+        return ket
+
+    def env(v: int, parent: int) -> np.ndarray:
+        ket = absorbed(v, parent)
+        ax = 1 + g.leg(v, g.edge_of[(v, parent)])
+        others = [j for j in range(ket.ndim) if j != ax]
+        return np.tensordot(ket, bpc.bra_tensor(v).conj(), axes=(others, others))      # [b, b']
+
+    root = min(vs)
+    return complex(np.vdot(bpc.bra_tensor(root), absorbed(root, None)))
+
+
+def expect(bpc: BeliefPropagationCache, obs: tuple, tree=None) -> complex:
+    """obs = (op string or list of op names, vertex names/ids[, coeff]); src/expect.jl:58-83,160-176.  tree = (vertices, edge ids)
+    of the Steiner tree to contract over for three or more vertices (default graphs.steiner_tree)."""
     g = bpc.g
     op, verts = obs[0], obs[1]
     coeff = obs[2] if len(obs) > 2 else 1
@@ -529,7 +564,9 @@ def expect(bpc: BeliefPropagationCache, obs: tuple) -> complex:
     elif len(vs) == 2:
         region = _tree_path(g, vs[0], vs[1])
     else:
-        raise NotImplementedError("oracle expect handles one- and two-site observables")
+        tv, te = tree if tree is not None else steiner_tree(g, vs)
+        ops = {v: _gates.PAULI[n] for v, n in zip(vs, names)}
+        return coeff * _tree_region_contract(bpc, tv, te, ops) / _tree_region_contract(bpc, tv, te, {})
     ops = {v: _gates.PAULI[n] for v, n in zip(vs, names)}
     denom = _region_contract(bpc, region, {})
     numer = _region_contract(bpc, region, ops)

@@ -21,7 +21,7 @@ import numpy as np
 
 from . import gates as _gates
 from . import lib as _lib
-from .graphs import Graph, edge_color as _edge_color, forest_cover_edge_sequence
+from .graphs import Graph, edge_color as _edge_color, forest_cover_edge_sequence, steiner_tree as _steiner_tree, tree_schedule as _tree_schedule
 from .lib import ApplyOpts, BpOpts, TnqsError, check, i32, ptr_f64, ptr_i32, ptr_i64
 
 DEFAULT_BP_MAXITER = 25      # src/MessagePassing/beliefpropagationcache.jl:108
@@ -468,9 +468,34 @@ def _collect_observable(g: Graph, obs: tuple):
     return names, [_vid(g, x) for x in verts], coeff
 
 
-def expect(x, obs, alg: str = "bp", cache_update_kwargs: Optional[dict] = None):
-    """<O> by belief propagation (src/expect.jl:53-83,115-136): one-site observables and two-site observables (contracted
-    along the path joining the two vertices); a TensorNetworkState input builds and updates a fresh cache first."""
+def _expect_tree(bpc: BeliefPropagationCache, vs: Sequence[int], ops: Sequence[np.ndarray], tree=None) -> complex:
+    """<O_1 .. O_n> on three or more vertices: numerator / denominator of the contraction over their Steiner tree with the
+    converged messages entering the region (src/expect.jl:66-81).  A tree region is contracted by passing un-normalised messages
+    from its leaves to a root, so this is a composition of existing entry points on two clones of the handle:
+    numerator = clone with the operators applied (tnqs_apply_1site, no normalisation) and the original state attached as the bra
+    (tnqs_set_bra), one un-normalised tnqs_bp_update over the tree's child -> parent edges, then the root's vertex scalar;
+    denominator = the same without operators."""
+    g = bpc.g
+    tv, te = tree if tree is not None else _steiner_tree(g, vs)
+    root = min(int(v) for v in tv)
+    seq = _tree_schedule(g, tv, te, root)
+    vals = []
+    for with_ops in (True, False):
+        work = bpc.copy()                                       # state + converged messages
+        if with_ops:
+            apply_1site_batch(work, list(vs), list(ops), normalize_tensors=False)
+            _attach_bra(work, bpc.psi)
+        update(work, maxiter=1, tolerance=None, edge_sequence=seq, normalize=False, inplace=True)
+        vals.append(complex(vertex_scalars(work)[root]))
+        if with_ops:
+            _attach_bra(work, None)
+    return vals[0] / vals[1]
+
+
+def expect(x, obs, alg: str = "bp", cache_update_kwargs: Optional[dict] = None, tree=None):
+    """<O> by belief propagation (src/expect.jl:53-83,115-136): one-site observables, two-site observables (contracted
+    along the path joining the two vertices) and observables on three or more vertices (contracted over their Steiner tree;
+    tree = (vertices, edge ids) overrides graphs.steiner_tree); a TensorNetworkState input builds and updates a fresh cache first."""
     if alg != "bp":
         raise ValueError("Only alg='bp' is on the CUDA path (Expected BeliefPropagationCache or TensorNetworkState for 'bp' algorithm)")
     if isinstance(x, TensorNetworkState):
@@ -483,8 +508,9 @@ def expect(x, obs, alg: str = "bp", cache_update_kwargs: Optional[dict] = None):
     out: List[complex] = [0j] * len(parsed)
     one = [(i, p) for i, p in enumerate(parsed) if len(p[1]) == 1 and p[2] != 0]
     two = [(i, p) for i, p in enumerate(parsed) if len(p[1]) == 2 and p[2] != 0]
-    if any(len(p[1]) > 2 for p in parsed):
-        raise NotImplementedError("the CUDA path measures one-site and two-site observables")
+    for i, (names, vs, coeff) in enumerate(parsed):
+        if len(vs) > 2 and coeff != 0:
+            out[i] = coeff * _expect_tree(x, vs, [_gates.PAULI[n] for n in names], tree)
     if one:
         rho = rdm_1site(x, [p[1][0] for _, p in one])
         for (i, (names, vs, coeff)), r in zip(one, rho):

@@ -289,6 +289,66 @@ def forest_cover_edge_sequence(g: Graph) -> np.ndarray:
 # ---------------------------------------------------------------------------------------------
 # edge colouring
 # ---------------------------------------------------------------------------------------------
+def steiner_tree(g: Graph, terminals: Sequence[int]) -> Tuple[List[int], List[int]]:
+    """A tree of g that spans `terminals`: (vertices, undirected edge ids).  Greedy shortest-path growth (start from the first
+    terminal, repeatedly join the terminal nearest to the tree by a BFS shortest path, lowest ids first) - exact for two
+    terminals and on trees.  The reference calls `steiner_tree(network, obs_vs)` of Graphs.jl (src/expect.jl:66, src/rdm.jl:55),
+    which is not in /root/reference; on a loopy graph equally short trees give different BP regions, so the tree is an input of
+    the measurement functions (`tree=`) and this is only the default."""
+    terms = [int(t) for t in terminals]
+    if len(set(terms)) != len(terms):
+        raise ValueError("Repeated vertex in collection")
+    in_tree = {terms[0]}
+    edges: List[int] = []
+    todo = [t for t in terms[1:]]
+    while todo:
+        prev = {v: -1 for v in sorted(in_tree)}              # multi-source BFS from the tree
+        queue = sorted(in_tree)
+        hit = None
+        while queue and hit is None:
+            u = queue.pop(0)
+            for w in g.neighbors(u):
+                if w not in prev:
+                    prev[w] = u
+                    queue.append(w)
+                    if w in todo:
+                        hit = w
+                        break
+        if hit is None:
+            raise ValueError("vertices are not connected")
+        w = hit
+        while prev[w] != -1:
+            edges.append(int(g.edge_of[(prev[w], w)]))
+            in_tree.add(w)
+            w = prev[w]
+        todo = [t for t in todo if t not in in_tree]
+    return sorted(in_tree), sorted(edges)
+
+
+def tree_schedule(g: Graph, vertices: Sequence[int], edges: Sequence[int], root: int) -> List[int]:
+    """Directed edge ids child -> parent of the tree (vertices, edges), children before parents (post-order towards `root`);
+    raises if the vertex set has an edge of g that is not in the tree (the induced region would have a loop)."""
+    vs, es = set(int(v) for v in vertices), set(int(e) for e in edges)
+    for e in range(g.ne):
+        if e not in es and int(g.esrc[e]) in vs and int(g.edst[e]) in vs:
+            raise NotImplementedError("the region of this observable has a loop (an edge between two tree vertices that is not in the tree)")
+    adj: Dict[int, List[int]] = {v: [] for v in vs}
+    for e in es:
+        a, b = int(g.esrc[e]), int(g.edst[e])
+        adj[a].append(b); adj[b].append(a)
+    order, parent, stack = [], {root: -1}, [root]
+    while stack:
+        u = stack.pop()
+        order.append(u)
+        for w in sorted(adj[u]):
+            if w not in parent:
+                parent[w] = u
+                stack.append(w)
+    if len(order) != len(vs) or len(es) != len(vs) - 1:
+        raise ValueError("not a tree")
+    return [g.dedge(u, parent[u]) for u in reversed(order) if parent[u] != -1]
+
+
 def grid_edge_color(g: Graph) -> List[List[int]]:
     """Deterministic closed-form colouring of an open hypercubic grid: per axis, edges starting at an odd
     coordinate, then at an even one (2*ndim colours).  Stands in for the solver-dependent

@@ -130,3 +130,59 @@ def test_engine_packs_heisenberg_gates_for_pauli_sites():
     assert np.array_equal(data.view(np.complex128)[16:], m.ravel(order="F"))
     gv2, off2, data2 = E._pack_circuit(g, circ, lambda: np.full(g.nv, 2, dtype=np.int32))
     assert list(off2) == [0, 4] and data2.size == 2 * (4 + 16)
+
+
+# ---- observables on three or more vertices: contraction over the Steiner tree of the support -----------------
+def _composed_tree_expect(bpc, vs, ops, tv, te):
+    """The engine's composition (engine._expect_tree) replayed with oracle primitives: operators applied to a copy of the ket, the
+    original state as the bra, one un-normalised sweep over the tree's child -> parent edges, the root's vertex scalar."""
+    g = bpc.g
+    root = min(tv)
+    seq = G.tree_schedule(g, tv, te, root)
+    vals = []
+    for with_ops in (True, False):
+        ket = bpc.network.copy()
+        if with_ops:
+            for v, o in zip(vs, ops):
+                ket.tensors[v] = np.tensordot(o, ket.tensors[v], axes=([1], [0]))
+        work = O.BeliefPropagationCache(ket, {k: m.copy() for k, m in bpc.messages.items()}, bpc.network if with_ops else None)
+        work = O.update(work, maxiter=1, tolerance=None, edge_sequence=seq, normalize=False)
+        vals.append(O.vertex_scalar(work, root))
+    return vals[0] / vals[1]
+
+
+def test_multi_site_observables_over_the_steiner_tree():
+    from util import ising_layer
+    # (1) on a tree BP is exact: three- and four-site observables against the statevector
+    g = G.named_comb_tree((3, 3))
+    circ = ising_layer(g, dt=0.2) * 2
+    psi, _ = O.apply_gates(circ, O.tensornetworkstate(lambda v: "↑", g), apply_kwargs=dict(maxdim=16, cutoff=None, normalize_tensors=True))
+    sv = O.statevector_circuit(g, lambda v: "↑", circ)
+    bpc = O.update(O.BeliefPropagationCache(psi), maxiter=1)
+    for names, vs in (("ZXZ", [0, 4, 8]), ("XYZX", [2, 3, 6, 7]), ("ZZZ", [0, 1, 2])):
+        want = O.statevector_expect(sv, g.nv, {v: gates.PAULI[n] for v, n in zip(vs, names)})
+        got = O.expect(bpc, (names, vs))
+        assert abs(got - want) < 1e-12, (names, got, want)
+        tv, te = G.steiner_tree(g, vs)
+        assert set(vs) <= set(tv) and len(te) == len(tv) - 1
+        assert abs(_composed_tree_expect(bpc, vs, [gates.PAULI[n] for n in names], tv, te) - want) < 1e-12
+    # (2) loopy grid: the message-passing composition equals the recursive region contraction, the two-vertex case equals the
+    # path contraction, and a region with a chord is refused
+    g = G.named_grid((4, 4))
+    psi = O.random_tensornetworkstate(g, bond_dimension=3, seed=9)
+    bpc = O.update(O.BeliefPropagationCache(psi), maxiter=30, tolerance=1e-12)
+    vs = [g.v((1, 1)), g.v((1, 3)), g.v((3, 2))]
+    tv, te = G.steiner_tree(g, vs)
+    a = O.expect(bpc, ("ZXZ", vs), tree=(tv, te))
+    b = _composed_tree_expect(bpc, vs, [gates.Z, gates.X, gates.Z], tv, te)
+    assert abs(a - b) < 1e-12 and abs(a.imag) < 1e-10
+    pv = O._tree_path(g, vs[0], vs[2])
+    pe = [g.edge_of[(pv[i], pv[i + 1])] for i in range(len(pv) - 1)]
+    two = O._tree_region_contract(bpc, pv, pe, {vs[0]: gates.Z, vs[2]: gates.X}) / O._tree_region_contract(bpc, pv, pe, {})
+    assert abs(two - O.expect(bpc, ("ZX", [vs[0], vs[2]]))) < 1e-12
+    plaquette = [g.v((1, 1)), g.v((1, 2)), g.v((2, 2)), g.v((2, 1))]
+    edges3 = [g.edge_of[(plaquette[i], plaquette[i + 1])] for i in range(3)]
+    with pytest.raises(NotImplementedError):
+        G.tree_schedule(g, plaquette, edges3, plaquette[0])
+    with pytest.raises(NotImplementedError):
+        O.expect(bpc, ("ZZZZ", plaquette), tree=(plaquette, edges3))

@@ -57,3 +57,29 @@ def test_inner_between_different_bond_dimensions_on_a_tree():
     phi_e = E.TensorNetworkState.from_arrays(g, phi_o.tensors)
     assert abs(E.inner(psi_e, phi_e) - exact) < 1e-10 * abs(exact)
     assert abs(E.inner(phi_e, psi_e) - np.conj(exact)) < 1e-10 * abs(exact)
+
+
+def test_multi_site_observables_over_the_steiner_tree():
+    # <O_1 O_2 O_3> contracted over the Steiner tree of the support (src/expect.jl:66-81); the engine passes
+    # un-normalised messages from the leaves of the tree to its root (engine._expect_tree), the oracle contracts the region recursively
+    from tensornetworkquantumsimulator_b200 import engine as E
+    from tensornetworkquantumsimulator_b200 import gates
+    from util import to_engine
+    for g, chi in ((G.named_comb_tree((3, 3)), 3), (G.named_grid((4, 4)), 3), (G.named_grid((4, 4)), 8)):
+        psi_o = O.random_tensornetworkstate(g, bond_dimension=chi, seed=9)
+        for v in range(g.nv):
+            psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+        kw = dict(maxiter=30, tolerance=1e-12)
+        bo = O.update(O.BeliefPropagationCache(psi_o), **kw)
+        be = E.update(to_engine(psi_o), **kw)
+        cases = [("ZXZ", [0, 4, 8]), ("XYZX", [2, 3, 6, 7])] if g.is_tree() else \
+                [("ZXZ", [g.v((1, 1)), g.v((1, 3)), g.v((3, 2))]), ("ZZZ", [g.v((2, 1)), g.v((2, 2)), g.v((2, 3))])]
+        for names, vs in cases:
+            tree = G.steiner_tree(g, vs)
+            want = O.expect(bo, (names, vs), tree=tree)
+            got = E.expect(be, (names, vs), tree=tree)
+            assert abs(got - want) < 1e-8, (names, got, want)
+        if g.is_tree():
+            sv = O.to_statevector(psi_o)
+            want = O.statevector_expect(sv, g.nv, {0: gates.Z, 4: gates.X, 8: gates.Z})
+            assert abs(E.expect(be, ("ZXZ", [0, 4, 8])) - want) < 1e-8
