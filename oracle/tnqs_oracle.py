@@ -582,6 +582,33 @@ def expect_tns(psi: TensorNetworkState, obs, cache_update_kwargs: Optional[dict]
     return expect(bpc, obs)
 
 
+def reduced_density_matrix(bpc: BeliefPropagationCache, vs: Sequence[int], tree=None) -> np.ndarray:
+    """Normalised BP reduced density matrix of the vertices vs (src/rdm.jl:49-70) as rho[(s_1..s_n), (s_1'..s_n')], first vertex
+    slow: the region (shortest path / Steiner tree) is contracted once per matrix element with |s><s'| inserted on the sites
+    (the reference leaves those site legs open in a single contraction)."""
+    g = bpc.g
+    n = len(vs)
+    if n == 1:
+        return rdm_1site(bpc, vs[0])
+    if n == 2:
+        tv = _tree_path(g, vs[0], vs[1])
+        te = [g.edge_of[(tv[i], tv[i + 1])] for i in range(len(tv) - 1)]
+    else:
+        tv, te = tree if tree is not None else steiner_tree(g, vs)
+    dims = [bpc.network.tensors[v].shape[0] for v in vs]
+    big = int(np.prod(dims))
+    rho = np.zeros((big, big), dtype=np.complex128)
+    for i, si in enumerate(np.ndindex(*dims)):
+        for j, sj in enumerate(np.ndindex(*dims)):
+            ops = {}
+            for v, d, a, b in zip(vs, dims, si, sj):
+                o = np.zeros((d, d), dtype=np.complex128)
+                o[b, a] = 1.0                               # |s'><s|: tr(rho |s'><s|) = rho[s, s']
+                ops[v] = o
+            rho[i, j] = _tree_region_contract(bpc, tv, te, ops)
+    return rho / np.trace(rho)
+
+
 def rdm_1site(bpc: BeliefPropagationCache, v: int) -> np.ndarray:
     """BP one-site reduced density matrix rho[s, s'] (src/rdm.jl:49-70 restricted to one vertex), trace 1."""
     t = bpc.network.tensors[v]

@@ -535,6 +535,38 @@ def expect(x, obs, alg: str = "bp", cache_update_kwargs: Optional[dict] = None, 
     return out[0] if single else out
 
 
+def reduced_density_matrix(x, vertices, alg: str = "bp", normalize: bool = True, cache_update_kwargs: Optional[dict] = None, tree=None) -> np.ndarray:
+    """BP reduced density matrix of one or more qubits (src/rdm.jl:49-70) as a 2^n x 2^n matrix rho[(s_1..s_n), (s_1'..s_n')],
+    first vertex slow.  One vertex: tnqs_rdm_1site.  Several: rho = 2^-n sum_a <P_a> P_a over the 4^n Pauli strings, every <P_a>
+    measured on the same region as the reference's single contraction (shortest path / Steiner tree), so only the normalised
+    matrix is available."""
+    if alg != "bp":
+        raise ValueError("Only alg='bp' is on the CUDA path")
+    if isinstance(x, TensorNetworkState):
+        kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(x)
+        x = update(BeliefPropagationCache(x.copy()), inplace=True, **kw)
+    vs = [_vid(x.g, v) for v in (vertices if isinstance(vertices, list) else [vertices])]
+    if len(vs) == 1:
+        r = rdm_1site(x, vs)[0]
+        d = int(x.psi.site_dims()[vs[0]])
+        r = r[:d, :d]
+        return r / np.trace(r) if normalize else r
+    if not normalize:
+        raise NotImplementedError("multi-site reduced density matrices are assembled from expectation values: normalised only")
+    if any(int(x.psi.site_dims()[v]) != 2 for v in vs):
+        raise NotImplementedError("multi-site reduced density matrices need qubit sites")
+    n = len(vs)
+    strings = ["".join(p) for p in __import__("itertools").product("IXYZ", repeat=n)]
+    vals = expect(x, [(s, list(vs)) for s in strings[1:]], tree=tree)
+    rho = np.eye(2 ** n, dtype=np.complex128)
+    for s, val in zip(strings[1:], vals):
+        p = np.array([[1.0 + 0j]])
+        for ch in s:
+            p = np.kron(p, _gates.PAULI[ch])
+        rho += val * p
+    return rho / 2 ** n
+
+
 def _shortest_path(g: Graph, a: int, b: int) -> List[int]:
     if a == b:
         raise ValueError("Repeated vertex in collection")

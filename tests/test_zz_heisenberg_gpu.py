@@ -83,3 +83,22 @@ def test_multi_site_observables_over_the_steiner_tree():
             sv = O.to_statevector(psi_o)
             want = O.statevector_expect(sv, g.nv, {0: gates.Z, 4: gates.X, 8: gates.Z})
             assert abs(E.expect(be, ("ZXZ", [0, 4, 8])) - want) < 1e-8
+
+
+def test_two_and_three_site_reduced_density_matrices():
+    # src/rdm.jl:49-70 for several vertices: engine.reduced_density_matrix assembles rho from the 4^n Pauli-string expectation values
+    # (tnqs_expect_path for two vertices, the tree composition for three) - against the oracle's direct region contraction
+    from tensornetworkquantumsimulator_b200 import engine as E
+    from util import to_engine
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=18)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    kw = dict(maxiter=40, tolerance=1e-13)
+    bo = O.update(O.BeliefPropagationCache(psi_o), **kw)
+    be = E.update(to_engine(psi_o), **kw)
+    for vs in ([4], [0, 8], [0, 2, 7]):
+        tree = G.steiner_tree(g, vs) if len(vs) > 2 else None
+        want = O.reduced_density_matrix(bo, vs, tree=tree)
+        got = E.reduced_density_matrix(be, vs, tree=tree)
+        assert np.max(np.abs(got - want)) < 1e-8
