@@ -21,7 +21,8 @@ module TNQSCuda
 
 using ITensors, NamedGraphs, Dictionaries, LinearAlgebra
 using NamedGraphs: NamedEdge, NamedGraph
-using Graphs: vertices, edges, src, dst, a_star
+using NamedGraphs.GraphsExtensions: post_order_dfs_edges
+using Graphs: vertices, edges, src, dst, a_star, has_edge
 import TensorNetworkQuantumSimulator as TN
 import TensorNetworkQuantumSimulator: update, apply_gates, expect, rescale, rescale!, symmetric_gauge, symmetric_gauge!,
     network, message, messages, partitionfunction, entanglement, inner, maxvirtualdim, graph
@@ -377,8 +378,41 @@ function expect(c::CudaBeliefPropagationCache, obs::Tuple)
         check(c.ctx, tnqs_expect_path(c.ctx, 1, Int32[0, length(path)], path, opbuf, out))
         return coeff * out[1] / out[2]
     end
-    error("observables on more than two vertices are not on the CUDA path yet")
+    return coeff * _expect_tree(c, verts, ops)
 end
+
+# three or more vertices: the region is the Steiner tree of the support (src/expect.jl:66); a tree region is contracted by passing
+# un-normalised messages from its leaves to a root, i.e. with existing entry points on two clones of the handle (engine.py
+# `_expect_tree` is the executable twin): numerator = clone with the operators applied and the original state attached as the bra,
+# one un-normalised sweep over the child -> parent edges, the root's vertex scalar; denominator = the same without operators.
+function _expect_tree(c::CudaBeliefPropagationCache, verts::Vector, ops::Vector{String})
+    t = NamedGraphs.steiner_tree(c.g, verts)
+    tvs = collect(vertices(t)); root = first(tvs)
+    for e in edges(c.g)                                           # a chord would make the region loopy
+        (src(e) in tvs && dst(e) in tvs && !(has_edge(t, src(e), dst(e)))) && error("the region of this observable has a loop")
+    end
+    # post_order_dfs_edges lists child -> parent edges, children first (the first half of forest_cover_edge_sequence,
+    # src/MessagePassing/beliefpropagationcache.jl:80-81)
+    seq = Int32[directed_id(c, e) for e in post_order_dfs_edges(t, root)]
+    vals = ComplexF64[]
+    for with_ops in (true, false)
+        w = copy(c)
+        if with_ops
+            vids = Int32[vertex_id(c, v) for v in verts]
+            gates = reduce(vcat, [vec(_opmatrix(c, o, v)) for (o, v) in zip(ops, verts)])
+            check(w.ctx, tnqs_apply_1site(w.ctx, length(vids), vids, gates, 0))
+            check(w.ctx, tnqs_set_bra(w.ctx, c.ctx)); w.bra = c
+        end
+        opts = BpOpts(1, -1.0, 0, 0, BP_REFERENCE_ORDER)
+        iters = Ref{Int32}(0); diff = Ref{Float64}(NaN)
+        check(w.ctx, tnqs_bp_update(w.ctx, seq, length(seq), opts, iters, diff))
+        num = zeros(ComplexF64, length(c.vs)); check(w.ctx, tnqs_vertex_scalars(w.ctx, num))
+        push!(vals, num[vertex_id(c, root) + 1])
+        with_ops && check(w.ctx, tnqs_set_bra(w.ctx, C_NULL))
+    end
+    return vals[1] / vals[2]
+end
+
 expect(c::CudaBeliefPropagationCache, obs::Vector{<:Tuple}) = [expect(c, o) for o in obs]
 
 # ---- scalars, rescale, gauge, truncate, entanglement
