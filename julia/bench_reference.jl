@@ -39,9 +39,14 @@ function main()
         bpc, errs = apply_gates(layer, bpc; apply_kwargs)
         expect(bpc, ("Z", [(nx ÷ 2, ny ÷ 2)]))
     end
-    println("""{"impl": "reference", "metric": "bp_edge_message_updates_per_s", "value": $(nmsg / t_bp), "unit": "messages/s", """ *
-            """"ms_per_step": $(1000 * t_layer / steps), "cpu_baseline": {"kind": "reference", "cores": $(Threads.nthreads()), """ *
-            """"blas_threads": $(BLAS.get_num_threads()), "sample": "one reference-order sweep of $(nmsg) messages; $(steps) full layer(s)"}, """ *
-            """"config": {"workload": "C2 $(nx)x$(ny) grid chi=$(χ) ComplexF64"}}""")
+    q(x) = "\"" * string(x) * "\""                                             # JSON string
+    fields = [q("impl") * ": " * q("reference"), q("metric") * ": " * q("bp_edge_message_updates_per_sec"),
+              q("value") * ": " * string(nmsg / t_bp), q("unit") * ": " * q("messages/s"),
+              q("ms_per_step") * ": " * string(1000 * t_layer / steps),
+              q("cpu_baseline") * ": {" * q("kind") * ": " * q("reference") * ", " * q("cores") * ": " * string(Threads.nthreads()) * ", " *
+                  q("blas_threads") * ": " * string(BLAS.get_num_threads()) * ", " *
+                  q("sample") * ": " * q("one reference-order sweep of $(nmsg) messages; $(steps) full layer(s)") * "}",
+              q("config") * ": {" * q("workload") * ": " * q("C2 $(nx)x$(ny) grid chi=$(χ) ComplexF64") * "}"]
+    println("{" * join(fields, ", ") * "}")
 end
 main()
