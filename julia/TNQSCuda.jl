@@ -187,12 +187,12 @@ tensor in the ABI's canonical layout with one `tnqs_set_sites` call; messages st
 (src/TensorNetworks/tensornetworkstate.jl:64-67).  `chi_cap` = the largest bond dimension gates may grow the state to.
 """
 function CudaBeliefPropagationCache(ψ::TensorNetworkState; chi_cap::Integer = maxvirtualdim(ψ), device::Integer = 0,
-                                    bond_dims::Union{Nothing, Vector{<:Integer}} = nothing)
+                                    pad_to::Union{Nothing, Vector{<:Integer}} = nothing)
     g = graph(ψ); vs = collect(vertices(g)); es = collect(edges(g))
     binds = Index[only(virtualinds(ψ, e)) for e in es]
     bufs = _canonical_arrays(ψ, vs, es, binds)
-    if bond_dims !== nothing                      # embed in zero-padded tensors with the given bond dimensions (see `inner`)
-        binds = Index[dim(binds[k]) == bond_dims[k] ? binds[k] : Index(Int(bond_dims[k]); tags = tags(binds[k])) for k in 1:length(es)]
+    if pad_to !== nothing                         # embed in zero-padded tensors with the given bond dimensions (see `inner`)
+        binds = Index[dim(binds[k]) == pad_to[k] ? binds[k] : Index(Int(pad_to[k]); tags = tags(binds[k])) for k in 1:length(es)]
         bufs = [_zero_pad(bufs[i], (size(bufs[i], 1), (dim(binds[k]) for k in _incident(es, v))...)) for (i, v) in enumerate(vs)]
     end
     vid = Dict(v => Int32(i - 1) for (i, v) in enumerate(vs))
@@ -360,8 +360,8 @@ end
 _opmatrix(c, name::String, v) = ComplexF64.(ITensors.array(ITensors.op(name, only(c.sinds[v])), only(c.sinds[v])', only(c.sinds[v])))  # O[s', s]
 
 function expect(c::CudaBeliefPropagationCache, obs::Tuple)
-    ops, verts, coeff = TN.collectobservable(obs)                              # src/expect.jl:160-176
-    ops = [string(o) for o in ops]
+    ops, verts, coeff = TN.collectobservable(obs, c.g)                         # src/expect.jl:158-175
+    iszero(coeff) && return 0                                                  # :63
     if length(verts) == 1
         v = only(verts); d = dim(only(c.sinds[v]))
         ρ = reduced_density_matrix_1site(c, [v])[1:d, 1:d, 1]
@@ -471,8 +471,8 @@ end
 function inner(ψ::TensorNetworkState, ϕ::TensorNetworkState, ::Val{:cuda}; device::Integer = 0, kwargs...)
     es = collect(edges(graph(ψ)))
     χ = [max(dim(only(virtualinds(ψ, e))), dim(only(virtualinds(ϕ, e)))) for e in es]
-    ket = CudaBeliefPropagationCache(ψ; bond_dims = χ, device)
-    bra = CudaBeliefPropagationCache(ϕ; bond_dims = χ, device)
+    ket = CudaBeliefPropagationCache(ψ; pad_to = χ, device)
+    bra = CudaBeliefPropagationCache(ϕ; pad_to = χ, device)
     return inner(ket, bra; kwargs...)
 end
 
