@@ -14,6 +14,7 @@ All arithmetic runs in the CUDA library; nothing here falls back to the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import math
 from typing import List, Optional, Sequence
 
@@ -556,7 +557,7 @@ def reduced_density_matrix(x, vertices, alg: str = "bp", normalize: bool = True,
     if any(int(x.psi.site_dims()[v]) != 2 for v in vs):
         raise NotImplementedError("multi-site reduced density matrices need qubit sites")
     n = len(vs)
-    strings = ["".join(p) for p in __import__("itertools").product("IXYZ", repeat=n)]
+    strings = ["".join(p) for p in itertools.product("IXYZ", repeat=n)]
     vals = expect(x, [(s, list(vs)) for s in strings[1:]], tree=tree)
     rho = np.eye(2 ** n, dtype=np.complex128)
     for s, val in zip(strings[1:], vals):
