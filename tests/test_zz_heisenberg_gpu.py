@@ -102,3 +102,17 @@ def test_two_and_three_site_reduced_density_matrices():
         want = O.reduced_density_matrix(bo, vs, tree=tree)
         got = E.reduced_density_matrix(be, vs, tree=tree)
         assert np.max(np.abs(got - want)) < 1e-8
+
+
+def test_plain_c_program_through_the_abi(tmp_path):
+    # examples/c_abi_demo.c: the library driven from C99 alone (|+>^4 on a 2x2 grid, one Rzz(0.8) layer through tnqs_apply_circuit,
+    # <X_0>, <Z_0> from tnqs_rdm_1site); on this single loop BP gives cos(0.8)^2 for <X_0> (oracle: 0.485400238849)
+    import re
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_abi import _build_c_demo
+    r = _build_c_demo(tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bond dimensions: 2 2 2 2" in r.stdout
+    z, x = (float(v) for v in re.search(r"<Z_0> = (\S+)\s+<X_0> = (\S+)", r.stdout).groups())
+    assert abs(z) < 1e-8 and abs(x - np.cos(0.8) ** 2) < 1e-8
