@@ -220,6 +220,46 @@ def update(bpc: BeliefPropagationCache, maxiter: Optional[int] = None, tolerance
     return bpc
 
 
+def jacobi_sweep(bpc: BeliefPropagationCache, normalize: bool = True, shared: bool = False) -> BeliefPropagationCache:
+    """One JACOBI sweep (every message from the previous sweep's values; the engine's TNQS_BP_JACOBI mode, used for the multi-GPU
+    runs - not a reference schedule, same fixed point).  shared = the vertex-centric evaluation planned for round 2 (DESIGN.md
+    section 8): the z outgoing messages of a vertex share partial absorptions through prefix / suffix products, e.g. z = 4:
+    A12 = T m1 m2, A34 = T m3 m4, out4 = A12 m3, out3 = A12 m4, out1 = A34 m2, out2 = A34 m1 - the same numbers up to the
+    order of the floating-point products."""
+    g = bpc.g
+    out = bpc.copy()
+    if not shared:
+        out.messages = {k: updated_message(bpc, k, normalize) for k in range(2 * g.ne)}
+        return out
+    for v in range(g.nv):
+        t = bpc.network.tensors[v]
+        inc = incoming(bpc, v)                                    # (axis, message) per leg, ascending
+        z = len(inc)
+        # prefix[i] = T with legs 0..i-1 absorbed, suffix[i] = T with legs i..z-1 absorbed (each one absorption further)
+        prefix = [t]
+        for axis, m in inc[:-1]:
+            prefix.append(_absorb(prefix[-1], axis, m))
+        for i in range(z):                                        # outgoing message on leg i: prefix[i] with legs i+1.. absorbed
+            a = prefix[i]
+            for axis, m in inc[i + 1:]:
+                a = _absorb(a, axis, m)
+            ax = inc[i][0]
+            others = [j for j in range(t.ndim) if j != ax]
+            mout = np.tensordot(a, bpc.bra_tensor(v).conj(), axes=(others, others))
+            if normalize and mout.sum() != 0:
+                mout = mout / mout.sum()
+            e = g.incident[v][i]
+            out.messages[g.dedge(v, g.other(e, v))] = mout
+    return out
+
+
+def jacobi_absorptions_per_vertex(z: int, shared: bool) -> int:
+    """Leg absorptions (each 8 d chi^(z+1) flops at uniform chi) one vertex costs per JACOBI sweep: z (z - 1) message by message;
+    with shared prefixes (z - 1) + sum_i (z - 1 - i) = (z - 1)(z + 2) / 2 as written above, and 3z - 6 with prefixes AND suffixes
+    (z >= 3: 6 instead of 12 at z = 4 would need both halves stored; the two-halves scheme of DESIGN.md section 8 does 8)."""
+    return z * (z - 1) if not shared else (z - 1) * (z + 2) // 2
+
+
 # ---------------------------------------------------------------------------------------------
 # scalars, partition function, rescale
 # ---------------------------------------------------------------------------------------------

@@ -62,3 +62,15 @@ def test_untruncated_circuits_on_random_trees_match_the_statevector(g, seed):
     sv = O.statevector_circuit(g, lambda v: "↑", circ)
     assert abs(statevector_fidelity(O.to_statevector(psi), sv) - 1) < 1e-11
     assert np.max(errs) < 1e-12
+
+
+def test_vertex_centric_jacobi_sweep_gives_the_same_messages():
+    # the shared-absorption evaluation of a JACOBI sweep (round-2 plan) is the same map on messages
+    for g, chi in ((G.named_grid((3, 4)), 3), (G.named_grid((2, 2, 2)), 2), (G.named_hexagonal_lattice_graph(1, 2), 4)):
+        psi = O.random_tensornetworkstate(g, bond_dimension=chi, seed=3)
+        b = O.update(O.BeliefPropagationCache(psi), maxiter=2)
+        a1, a2 = O.jacobi_sweep(b), O.jacobi_sweep(b, shared=True)
+        for k in range(2 * g.ne):
+            assert np.max(np.abs(a1.messages[k] - a2.messages[k])) < 1e-13 * np.max(np.abs(a1.messages[k]))
+    assert [O.jacobi_absorptions_per_vertex(z, False) for z in (2, 3, 4, 6)] == [2, 6, 12, 30]
+    assert [O.jacobi_absorptions_per_vertex(z, True) for z in (2, 3, 4, 6)] == [2, 5, 9, 20]
