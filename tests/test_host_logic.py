@@ -1,0 +1,109 @@
+"""The HOST logic of engine.py executed without a GPU: tests/fake_lib.py answers the C-ABI calls with the oracle, so what is tested
+here is the Python side only - argument packing, column-major flattening, shapes, and the ORDER OF CALLS of the composed operations
+(inner between different bond dimensions, observables over a Steiner tree, multi-site density matrices, the Heisenberg-picture
+circuit).  The device side of the same calls is tests/test_gpu_parity.py / tests/test_zz_heisenberg_gpu.py."""
+import gc
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import tnqs_oracle as O
+from tensornetworkquantumsimulator_b200 import graphs as G, gates, lib
+from fake_lib import FakeLib
+from util import to_engine
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture
+def E(monkeypatch):
+    fake = FakeLib()
+    monkeypatch.setattr(lib, "_lib", fake)
+    from tensornetworkquantumsimulator_b200 import engine
+    engine._fake = fake
+    yield engine
+    gc.collect()
+    fake.close()
+
+
+def test_basic_round_trips(E):
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=4)
+    be = to_engine(psi_o)
+    for a, b in zip(be.psi.tensors(), psi_o.tensors):
+        assert np.array_equal(a, b)
+    assert list(be.psi.site_dims()) == [2] * g.nv and be.psi.maxvirtualdim() == 3
+    seq = G.forest_cover_edge_sequence(g)
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=3, edge_sequence=seq)
+    be = E.update(be, maxiter=3, edge_sequence=seq)
+    for k in range(2 * g.ne):
+        assert np.array_equal(E.message(be, k), O.message(bo, k))
+    assert abs(E.expect(be, ("Z", [(2, 2)])) - O.expect(bo, ("Z", [(2, 2)]))) < 1e-14
+    assert abs(E.expect(be, ("ZX", [(1, 1), (3, 2)])) - O.expect(bo, ("ZX", [(1, 1), (3, 2)]))) < 1e-14
+    assert abs(E.partitionfunction(be) - O.partitionfunction(bo)) < 1e-12 * abs(O.partitionfunction(bo))
+
+
+def test_heisenberg_example_through_the_host_api(E):
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    d = np.load(os.path.join(GOLD, "heisenberg_grid4x4.npz"))
+    g = G.named_grid((4, 4))
+    o0 = E.paulitensornetworkstate(lambda v: "Z" if v == (2, 2) else "I", g, chi_cap=4)
+    assert list(o0.site_dims()) == [4] * g.nv
+    bpc = E.BeliefPropagationCache(o0.copy())
+    for l in range(2):
+        bpc, errs = E.apply_gates(mg.heisenberg_layer(g), bpc, apply_kwargs=dict(maxdim=4, cutoff=1e-14, normalize_tensors=False))
+        bpc = E.rescale(bpc)
+        assert list(bpc.psi.bond_dims()) == list(d["bond_dims"][l])
+        assert abs(E.partitionfunction(bpc) - d["frobenius"][l]) < 1e-12
+        n0 = len(E._fake.calls)
+        assert abs(E.inner(bpc.psi, o0) - d["trace_ot_o0"][l]) < 1e-12           # ragged chi against chi = 1: zero-padded bra
+        calls = E._fake.calls[n0:]
+        assert calls.count("tnqs_set_bra") == 1 and calls.count("tnqs_set_message") == 2 * g.ne and calls[-1] == "tnqs_bp_update"
+
+
+def test_inner_pads_the_thinner_layer(E):
+    g = G.named_comb_tree((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=4, seed=71, d=4)
+    phi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=72, d=4)
+    exact = np.vdot(O.to_statevector(phi_o), O.to_statevector(psi_o))
+    psi_e = E.TensorNetworkState.from_arrays(g, psi_o.tensors)
+    phi_e = E.TensorNetworkState.from_arrays(g, phi_o.tensors)
+    assert abs(E.inner(psi_e, phi_e) - exact) < 1e-12 * abs(exact)
+    assert abs(E.inner(phi_e, psi_e) - np.conj(exact)) < 1e-12 * abs(exact)
+    assert list(phi_e.bond_dims()) == [2] * g.ne                                   # the inputs are left alone
+    with pytest.raises(ValueError):
+        E.inner(psi_e, E.TensorNetworkState.from_arrays(G.named_grid((3, 3)), O.random_tensornetworkstate(G.named_grid((3, 3)), 2, 1).tensors))
+
+
+def test_multi_site_observables_and_density_matrices(E):
+    for g in (G.named_comb_tree((3, 3)), G.named_grid((4, 4))):
+        psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=9)
+        kw = dict(maxiter=30, tolerance=1e-12)
+        bo = O.update(O.BeliefPropagationCache(psi_o), **kw)
+        be = E.update(to_engine(psi_o), **kw)
+        cases = [("ZXZ", [0, 4, 8]), ("XYZX", [2, 3, 6, 7])] if g.is_tree() else \
+                [("ZXZ", [g.v((1, 1)), g.v((1, 3)), g.v((3, 2))]), ("ZZZ", [g.v((2, 1)), g.v((2, 2)), g.v((2, 3))])]
+        for names, vs in cases:
+            tree = G.steiner_tree(g, vs)
+            n0 = len(E._fake.calls)
+            got = E.expect(be, (names, vs), tree=tree)
+            assert abs(got - O.expect(bo, (names, vs), tree=tree)) < 1e-12
+            calls = E._fake.calls[n0:]
+            # numerator clone: operators, then the bra, then one partial sweep; denominator clone: the sweep alone
+            assert calls[:4] == ["tnqs_clone", "tnqs_apply_1site", "tnqs_set_bra", "tnqs_bp_update"] and calls.count("tnqs_clone") == 2
+        assert abs(E.expect(be, ("ZXZ", cases[0][1], 0)) - 0) == 0
+        before = [m.copy() for m in E.messages(be)]
+        for vs in ([cases[0][1][0]], cases[0][1][:2], cases[0][1]):
+            tree = G.steiner_tree(g, vs) if len(vs) > 2 else None
+            assert np.max(np.abs(E.reduced_density_matrix(be, vs, tree=tree) - O.reduced_density_matrix(bo, vs, tree=tree))) < 1e-12
+        for a, b in zip(before, E.messages(be)):                                   # measuring leaves the cache untouched
+            assert np.array_equal(a, b)
+    with pytest.raises(NotImplementedError):
+        g = G.named_grid((3, 3))
+        be = E.update(to_engine(O.random_tensornetworkstate(g, bond_dimension=2, seed=1)), maxiter=2)
+        plaquette = [g.v((1, 1)), g.v((1, 2)), g.v((2, 2)), g.v((2, 1))]
+        E.expect(be, ("ZZZZ", plaquette), tree=(plaquette, [g.edge_of[(plaquette[i], plaquette[i + 1])] for i in range(3)]))
