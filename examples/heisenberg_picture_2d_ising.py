@@ -29,6 +29,8 @@ def main():
         print(f"Layer {l}: Frobenius norm {E.partitionfunction(bpc).real:.12f}, max bond dimension {E.maxvirtualdim(bpc)}, "
               f"max gate error {errors.max():.2e}")
         psi = E.network(bpc)
+        # Trace(O(t)) is exactly zero for a traceless O(0): BP then divides numerically vanishing scalars, so the printed number is
+        # rounding noise (the reference prints the same kind of noise)
         print(f"  Trace(O(t) O(0)) = {E.inner(psi, psi0):.10f}   Trace(O(t)) = {E.inner(psi, ident):.3e}")
 
 
