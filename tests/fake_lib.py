@@ -227,6 +227,54 @@ class FakeLib:
         refreshes._obj.value = int(info["refreshes"])
         return 0
 
+    def tnqs_apply_2site(self, h, n, e, flip, gates, opts, ranks, truncerr, svals):
+        self.calls.append("tnqs_apply_2site")
+        st, a = self._s(h), opts._obj
+        es, fl = _arr(e, n, np.int32), _arr(flip, n, np.int32)
+        touched = [int(st.g.esrc[x]) for x in es] + [int(st.g.edst[x]) for x in es]
+        if len(set(touched)) != len(touched):
+            return -3                                              # TNQS_ERR_OVERLAPPING_BATCH
+        pos = 0
+        for i in range(n):
+            v1, v2 = int(st.g.esrc[es[i]]), int(st.g.edst[es[i]])
+            if fl[i]:
+                v1, v2 = v2, v1
+            d1, d2 = st.bpc.network.tensors[v1].shape[0], st.bpc.network.tensors[v2].shape[0]
+            sz = (d1 * d2) ** 2
+            flat = np.ctypeslib.as_array(gates, shape=(2 * (pos + sz),)).view(np.complex128)[pos:pos + sz]
+            pos += sz
+            det = {}
+            err = O.apply_gate(st.bpc, flat.reshape((d1, d2, d1, d2), order="F").copy(), [v1, v2],
+                               maxdim=None if a.maxdim <= 0 else int(a.maxdim), cutoff=None if np.isnan(a.cutoff) else float(a.cutoff),
+                               normalize_tensors=bool(a.normalize_tensors), detail=det)
+            if ranks:
+                _arr(ranks, n, np.int32)[i] = det["rank"]
+            if truncerr:
+                _arr(truncerr, n, np.float64)[i] = err
+            if svals:
+                _arr(svals, n * st.chi_cap, np.float64)[i * st.chi_cap:i * st.chi_cap + det["rank"]] = det["svals"]
+        return 0
+
+    def tnqs_truncate(self, h, ngroups, group_off, group_edges, aopts, seq, nseq, bopts):
+        self.calls.append("tnqs_truncate")
+        st, a, b = self._s(h), aopts._obj, bopts._obj
+        off = _arr(group_off, ngroups + 1, np.int32)
+        ge = _arr(group_edges, int(off[ngroups]), np.int32)
+        groups = [[int(x) for x in ge[off[i]:off[i + 1]]] for i in range(ngroups)]
+        kw = dict(maxiter=int(b.maxiter), tolerance=None if b.tolerance < 0 else float(b.tolerance),
+                  edge_sequence=_arr(seq, nseq, np.int32).tolist())
+        new = O.truncate_bp(self._bpc(st), maxdim=int(a.maxdim), cutoff=None if np.isnan(a.cutoff) else float(a.cutoff),
+                            normalize_tensors=bool(a.normalize_tensors), edge_groups=groups, bp_update_kwargs=kw)
+        st.bpc.network.tensors, st.bpc.messages = new.network.tensors, new.messages
+        return 0
+
+    def tnqs_symmetric_gauge(self, h, regularization):
+        self.calls.append("tnqs_symmetric_gauge")
+        st = self._s(h)
+        new = O.symmetric_gauge(self._bpc(st), float(regularization))
+        st.bpc.network.tensors, st.bpc.messages = new.network.tensors, new.messages
+        return 0
+
     # ---- measurements ----
     def tnqs_rdm_1site(self, h, n, v, rho):
         st = self._s(h)

@@ -107,3 +107,52 @@ def test_multi_site_observables_and_density_matrices(E):
         be = E.update(to_engine(O.random_tensornetworkstate(g, bond_dimension=2, seed=1)), maxiter=2)
         plaquette = [g.v((1, 1)), g.v((1, 2)), g.v((2, 2)), g.v((2, 1))]
         E.expect(be, ("ZZZZ", plaquette), tree=(plaquette, [g.edge_of[(plaquette[i], plaquette[i + 1])] for i in range(3)]))
+
+
+def test_gate_batches_truncate_gauge_sampling_through_the_host_api(E):
+    from util import ising_layer, two_site
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=21)
+    kw = dict(maxiter=20, tolerance=1e-10)
+    bo = O.update(O.BeliefPropagationCache(psi_o), **kw)
+    be = E.update(to_engine(psi_o, chi_cap=6), **kw)
+    # one vertex-disjoint batch, second half of it flipped
+    grp = G.grid_edge_color(g)[0]
+    arr = gates.gate_array(("CRx", [0, 1], 0.7))
+    flip = [i % 2 for i in range(len(grp))]
+    dets = []
+    for e, f in zip(grp, flip):
+        a, c = int(g.esrc[e]), int(g.edst[e])
+        det = {}
+        O.apply_gate(bo, arr, [c, a] if f else [a, c], maxdim=4, cutoff=1e-12, detail=det)
+        dets.append(det)
+    ranks, errs, sv = E.apply_2site_batch(be, grp, [arr] * len(grp), flip=flip, apply_kwargs=dict(maxdim=4, cutoff=1e-12))
+    assert list(ranks) == [d["rank"] for d in dets]
+    for i, d in enumerate(dets):
+        assert np.allclose(sv[i, :ranks[i]], d["svals"], rtol=0, atol=1e-14) and np.all(sv[i, ranks[i]:] == 0)
+    for e in grp:
+        assert np.array_equal(two_site(g, be.psi.tensors(), e), two_site(g, bo.network.tensors, e))
+    with pytest.raises(lib.TnqsError) as ei:                       # two edges sharing a vertex in one batch
+        E.apply_2site_batch(be, [0, [e for e in g.incident[int(g.esrc[0])] if e != 0][0]], [arr, arr])
+    assert ei.value.status == -3
+    # the circuit entry point and the run / refresh schedule agree on the number of refreshes
+    layer = ising_layer(g, groups=G.grid_edge_color(g))
+    info_e, info_o = {}, {}
+    ce, errs_e = E.apply_gates(layer, be, apply_kwargs=dict(maxdim=4, cutoff=1e-10), info=info_e)
+    co, errs_o = O.apply_gates(layer, bo, apply_kwargs=dict(maxdim=4, cutoff=1e-10), info=info_o)
+    assert info_e["refreshes"] == info_o["refreshes"] == sum(1 for s in E.circuit_schedule(g, layer) if s[0] == "refresh")
+    assert np.array_equal(errs_e, errs_o) and list(ce.psi.bond_dims()) == list(co.network.bond_dims())
+    # truncate / symmetric gauge / entanglement / normalize
+    te = E.truncate(ce, maxdim=2)
+    to = O.truncate_bp(co, maxdim=2)
+    assert te.psi.maxvirtualdim() == 2 and abs(E.expect(te, ("Z", [(2, 2)])) - O.expect(to, ("Z", [(2, 2)]))) < 1e-13
+    ge, go = E.symmetric_gauge(ce), O.symmetric_gauge(co)
+    for e in range(g.ne):
+        assert abs(E.entanglement(ge, e) - O.entanglement(go, e)) < 1e-12
+    ne = E.normalize(ce.psi)
+    assert abs(E.norm_sqr(ne) - 1) < 1e-10
+    # sampling: the same draws as the oracle with the same generator
+    small = O.random_tensornetworkstate(G.named_comb_tree((2, 3)), bond_dimension=2, seed=5)
+    se, _ = E.sample(E.TensorNetworkState.from_arrays(small.g, small.tensors), 4, rng=np.random.default_rng(7))
+    so, _ = O.sample(small, 4, rng=np.random.default_rng(7))
+    assert se == so
