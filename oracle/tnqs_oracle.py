@@ -766,6 +766,60 @@ def sample(psi: TensorNetworkState, nsamples: int, bp_update_kwargs: Optional[di
 
 
 # ---------------------------------------------------------------------------------------------
+# single-layer networks: contract(tn; alg = "bp") (src/contract.jl:7-9)
+# ---------------------------------------------------------------------------------------------
+def contract_bp(g: Graph, tensors: Sequence[np.ndarray], maxiter: Optional[int] = None, tolerance: Optional[float] = DEFAULT_TOL_F64,
+                edge_sequence: Optional[Sequence[int]] = None, info: Optional[dict] = None) -> complex:
+    """BP contraction of a plain TensorNetwork (no site indices; tensors[v] = A_v[b_e1 .. b_ez]): messages are vectors on the
+    bonds, default = all ones (`delta` of a single index, src/TensorNetworks/tensornetwork.jl:62-64), factors = the tensors
+    themselves (:66-68); update / normalisation / diff / partition function as for states
+    (src/MessagePassing/abstractbeliefpropagationcache.jl:144-218,252-267).  Written directly with vector messages, independent of
+    the bilinear-form embedding the engine uses for the same quantity."""
+    if maxiter is None:
+        maxiter = 1 if g.is_tree() else DEFAULT_BP_MAXITER
+    seq = [int(k) for k in (edge_sequence if edge_sequence is not None else forest_cover_edge_sequence(g))]
+    msg = {k: np.ones(tensors[g.dsrc(k)].shape[g.leg(g.dsrc(k), k // 2)], dtype=np.complex128) for k in range(2 * g.ne)}
+
+    def absorbed(v: int, skip: Optional[int]) -> np.ndarray:
+        a = tensors[v]
+        for i in reversed(range(a.ndim)):                        # contract from the last leg so that the axes keep their numbers
+            e = g.incident[v][i]
+            u = g.other(e, v)
+            if u == skip:
+                continue
+            a = np.tensordot(a, msg[g.dedge(u, v)], axes=([i], [0]))
+        return a
+
+    iters, mean = 0, float("nan")
+    for it in range(1, maxiter + 1):
+        iters, diff = it, 0.0
+        for k in seq:
+            new = absorbed(g.dsrc(k), g.ddst(k))
+            s = new.sum()
+            if s != 0:
+                new = new / s
+            if tolerance is not None:
+                diff += message_diff(new, msg[k])
+            msg[k] = new
+        if tolerance is not None:
+            mean = diff / len(seq)
+            if mean <= tolerance:
+                break
+    if info is not None:
+        info["iters"], info["mean_diff"], info["messages"] = iters, mean, msg
+    num = np.array([complex(absorbed(v, None)) for v in range(g.nv)])
+    den = np.array([np.sum(msg[2 * e] * msg[2 * e + 1]) for e in range(g.ne)])
+    if np.any(den == 0):
+        return 0.0
+    return complex(np.exp(np.sum(np.log(num.astype(np.complex128))) - np.sum(np.log(den.astype(np.complex128)))))
+
+
+def contract_exact(g: Graph, tensors: Sequence[np.ndarray]) -> complex:
+    """Full contraction of a small single-layer network (independent ground truth)."""
+    return complex(to_statevector(TensorNetworkState(g, [t[None, ...] for t in tensors]))[0])
+
+
+# ---------------------------------------------------------------------------------------------
 # exact helpers for tiny systems (independent ground truth, not part of the restatement)
 # ---------------------------------------------------------------------------------------------
 def to_statevector(psi: TensorNetworkState) -> np.ndarray:

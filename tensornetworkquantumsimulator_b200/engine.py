@@ -662,6 +662,30 @@ def inner(psi: TensorNetworkState, phi: TensorNetworkState, alg: str = "bp", cac
     return partitionfunction(bpc)
 
 
+def contract(tensors: Sequence[np.ndarray], g: Graph, alg: str = "bp", bp_update_kwargs: Optional[dict] = None, device: int = 0,
+             info: Optional[dict] = None) -> complex:
+    """contract(tn; alg = "bp") for a plain TensorNetwork without site indices (src/contract.jl:7-9): tensors[v] = A_v[b_e1 .. b_ez].
+    The device sees it as the bilinear form of a ket with site dimension 1 against the all-ones product bra (bond dimension 1,
+    zero-padded): its messages m[b, b'] carry the reference's vector message in column b' = 0 and zeros elsewhere, the
+    normalisation, the diff and the partition function are then the reference's, and the start is its all-ones default
+    (src/TensorNetworks/tensornetwork.jl:62-64)."""
+    if alg != "bp":
+        raise ValueError("Only alg='bp' is on the CUDA path")
+    ket = TensorNetworkState.from_arrays(g, [np.asarray(t, dtype=np.complex128)[None, ...] for t in tensors], device=device)
+    ones = TensorNetworkState.from_arrays(g, [np.ones((1,) * (1 + g.degree(v)), dtype=np.complex128) for v in range(g.nv)], device=device)
+    chi = ket.bond_dims()
+    bpc = BeliefPropagationCache(ket)
+    _attach_bra(bpc, _pad_bonds(ones, chi))
+    for e in range(g.ne):
+        m = np.zeros((int(chi[e]), int(chi[e])), dtype=np.complex128)
+        m[:, 0] = 1.0
+        setmessage(bpc, 2 * e, m)
+        setmessage(bpc, 2 * e + 1, m)
+    kw = bp_update_kwargs if bp_update_kwargs is not None else default_bp_update_kwargs(ket)
+    update(bpc, inplace=True, info=info, **kw)
+    return partitionfunction(bpc)
+
+
 def norm_sqr(x, alg: str = "bp", cache_update_kwargs: Optional[dict] = None) -> complex:
     """BP norm (src/norm_sqr.jl:56-76): partition function of the updated cache."""
     if isinstance(x, TensorNetworkState):

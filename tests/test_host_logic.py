@@ -156,3 +156,25 @@ def test_gate_batches_truncate_gauge_sampling_through_the_host_api(E):
     se, _ = E.sample(E.TensorNetworkState.from_arrays(small.g, small.tensors), 4, rng=np.random.default_rng(7))
     so, _ = O.sample(small, 4, rng=np.random.default_rng(7))
     assert se == so
+
+
+def test_single_layer_network_contraction(E):
+    # contract(tn; alg = "bp") (src/contract.jl:7-9, test/test_beliefpropagation.jl:12-28): exact on a tree; on a loopy graph the
+    # engine's bilinear embedding follows the oracle's vector-message BP sweep by sweep
+    rs = np.random.default_rng(12)
+    g = G.named_comb_tree((3, 3))
+    ts = [rs.normal(size=(2,) * g.degree(v)) + 1j * rs.normal(size=(2,) * g.degree(v)) for v in range(g.nv)]
+    exact = O.contract_exact(g, ts)
+    assert abs(O.contract_bp(g, ts) - exact) < 1e-12 * abs(exact)
+    assert abs(E.contract(ts, g) - exact) < 1e-12 * abs(exact)
+    g = G.named_grid((3, 3))
+    ts = [rs.uniform(0.5, 1.5, size=(3,) * g.degree(v)) + 0.1j * rs.normal(size=(3,) * g.degree(v)) for v in range(g.nv)]
+    for sweeps in (1, 2, 5):
+        kw = dict(maxiter=sweeps, tolerance=1e-14)
+        io, ie = {}, {}
+        zo = O.contract_bp(g, ts, info=io, **kw)
+        ze = E.contract(ts, g, bp_update_kwargs=kw, info=ie)
+        assert abs(ze - zo) < 1e-12 * abs(zo) and ie["iters"] == io["iters"] and abs(ie["mean_diff"] - io["mean_diff"]) < 1e-13
+    zo = O.contract_bp(g, ts)
+    assert abs(E.contract(ts, g) - zo) < 1e-10 * abs(zo)
+    assert abs(zo - O.contract_exact(g, ts)) < 0.05 * abs(zo)               # BP is approximate on loops, close for a near-positive network

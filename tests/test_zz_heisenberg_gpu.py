@@ -116,3 +116,22 @@ def test_plain_c_program_through_the_abi(tmp_path):
     assert "bond dimensions: 2 2 2 2" in r.stdout
     z, x = (float(v) for v in re.search(r"<Z_0> = (\S+)\s+<X_0> = (\S+)", r.stdout).groups())
     assert abs(z) < 1e-8 and abs(x - np.cos(0.8) ** 2) < 1e-8
+
+
+def test_single_layer_network_contraction():
+    # contract(tn; alg = "bp") (src/contract.jl:7-9): site dimension 1 ket against the zero-padded all-ones bra on the device,
+    # against the oracle's direct vector-message BP
+    from tensornetworkquantumsimulator_b200 import engine as E
+    rs = np.random.default_rng(12)
+    g = G.named_comb_tree((3, 3))
+    ts = [rs.normal(size=(2,) * g.degree(v)) + 1j * rs.normal(size=(2,) * g.degree(v)) for v in range(g.nv)]
+    exact = O.contract_exact(g, ts)
+    assert abs(E.contract(ts, g) - exact) < 1e-10 * abs(exact)
+    g = G.named_grid((3, 3))
+    ts = [rs.uniform(0.5, 1.5, size=(3,) * g.degree(v)) + 0.1j * rs.normal(size=(3,) * g.degree(v)) for v in range(g.nv)]
+    for sweeps in (1, 5):
+        kw = dict(maxiter=sweeps, tolerance=1e-14)
+        io, ie = {}, {}
+        zo = O.contract_bp(g, ts, info=io, **kw)
+        ze = E.contract(ts, g, bp_update_kwargs=kw, info=ie)
+        assert abs(ze - zo) < 1e-9 * abs(zo) and ie["iters"] == io["iters"]
