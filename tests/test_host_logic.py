@@ -1,7 +1,7 @@
 """The HOST logic of engine.py executed without a GPU: tests/fake_lib.py answers the C-ABI calls with the oracle, so what is tested
 here is the Python side only - argument packing, column-major flattening, shapes, and the ORDER OF CALLS of the composed operations
 (inner between different bond dimensions, observables over a Steiner tree, multi-site density matrices, the Heisenberg-picture
-circuit).  The device side of the same calls is tests/test_gpu_parity.py / tests/test_zz_heisenberg_gpu.py."""
+circuit).  The device side of the same calls is tests/test_gpu_parity.py / tests/test_zz_pending_gpu.py."""
 import gc
 import importlib.util
 import os

@@ -1,11 +1,8 @@
-"""GPU leg of the Heisenberg-picture path (tests/test_heisenberg.py holds the CPU leg): the example's 4x4 grid on Pauli sites
-through the C-ABI against the committed oracle numbers (tests/golden/heisenberg_grid4x4.npz) and the oracle itself.
-
-STATUS: written after this round's GPU minutes were spent - the host code (gates.heisenberg_gate_array, engine.paulitensornetworkstate,
-engine._pad_bonds / bilinear_cache(delta_default=True)) composes entry points that are each covered by tests/test_gpu_parity.py
-(d = 4 sites and gates: test_site_dimension_3_and_4; tnqs_set_bra: test_bilinear_form_bp_inner; growth from a product state:
-test_engine_circuit_matches_golden), but this composition has not run on a B200 yet.  The tests are therefore non-strict xfail: a
-pass shows up as XPASS in the round-end log, a failure does not mask the verified suite.  The file sorts last for the same reason."""
+"""Bodies of the GPU tests of the end-of-round-1 compositions (tests/test_heisenberg.py, tests/test_rdm.py and
+tests/test_host_logic.py hold the CPU legs).  NOT collected by `pytest tests/` (the file name does not match test_*.py):
+tests/test_zz_pending_gpu.py runs every function below in a child process, so that neither a crash nor a hang of code that has not
+run on a B200 yet can take the verified suite down with it.  Run them directly with
+    python -m pytest tests/zz_bodies_gpu.py -m gpu -q"""
 import importlib.util
 import os
 
@@ -15,8 +12,7 @@ import pytest
 from oracle import tnqs_oracle as O
 from tensornetworkquantumsimulator_b200 import graphs as G
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="composition first written after the round's GPU budget was spent; not yet run on a B200", strict=False)]
+pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
