@@ -286,7 +286,7 @@ def run_distributed(args, torch, dist, rank, world, local):
     dt, hx, hz, J = 0.25, 1.0, 0.8, 0.5
     rx = gates.gate_array(("Rx", [0], 2 * hx * dt)); rz = gates.gate_array(("Rz", [0], 2 * hz * dt)); rzz = gates.gate_array(("Rzz", [0, 1], 2 * J * dt))
     psi = E.random_tensornetworkstate(lg.g, bond_dimension=chi, seed=1 + rank, device=local)
-    bpc = E.BeliefPropagationCache(psi)
+    bpc = E.BeliefPropagationCache(psi, _share=True)
     ow = lib.i32(lg.owner_local)
     lib.check(psi._h.ptr, lib.load().tnqs_set_partition(psi._h.ptr, lib.ptr_i32(ow), rank))
     comp = P.EngineCompute(bpc, dev)
@@ -429,7 +429,7 @@ def run_engine(args):
     g, groups, rx, rz, rzz, seq = workload(nx, ny)
     t0 = time.time()
     psi = E.random_tensornetworkstate(g, bond_dimension=chi, seed=1 + rank, device=local)
-    bpc = E.BeliefPropagationCache(psi)
+    bpc = E.BeliefPropagationCache(psi, _share=True)
     E.update(bpc, edge_sequence=seq, inplace=True, maxiter=10)
     E.rescale(bpc, inplace=True)
     setup_s = time.time() - t0

@@ -15,7 +15,7 @@ def main():
     maxdim, cutoff = 4, 1.0e-14
     psi0 = E.paulitensornetworkstate(lambda v: "Z" if v == vz else "I", g, chi_cap=maxdim)
     apply_kwargs = dict(maxdim=maxdim, cutoff=cutoff, normalize_tensors=False)
-    bpc = E.BeliefPropagationCache(psi0.copy())
+    bpc = E.BeliefPropagationCache(psi0.copy(), _share=True)
     h, J, dt, steps = -1.0, -1.0, 0.04, 10
     layer = [("Rz", [v], h * dt) for v in g.names]
     for grp in G.edge_color(g, 4):

@@ -461,6 +461,16 @@ def apply_gate(bpc: BeliefPropagationCache, gate: np.ndarray, vs: Sequence[int],
     return float(err)
 
 
+def _vid(g: Graph, x) -> int:
+    """Vertex NAME -> dense id; the reference resolves by name only (e.g. the integer labels of build_graph_from_gates,
+    graph_ops.jl:53-67).  On a graph whose names are integers an integer is a name; elsewhere it may also be a dense id."""
+    if isinstance(x, (int, np.integer)) and not isinstance(x, bool):
+        if any(isinstance(n, (int, np.integer)) for n in g.names):
+            return g.index[int(x)]
+        return int(x)
+    return g.v(x)
+
+
 def _resolve_circuit(g: Graph, circuit: Sequence[tuple], tensors=None):
     out = []
     for gate in circuit:
@@ -468,10 +478,10 @@ def _resolve_circuit(g: Graph, circuit: Sequence[tuple], tensors=None):
             arr, verts = gate[0], gate[1]
         else:
             vl = gate[1] if isinstance(gate[1], list) else [gate[1]]
-            dims = None if tensors is None else [tensors[g.v(x) if not isinstance(x, (int, np.integer)) else int(x)].shape[0] for x in vl]
+            dims = None if tensors is None else [tensors[_vid(g, x)].shape[0] for x in vl]
             arr, verts = _gates.gate_array(gate, dims), gate[1]      # Pauli sites (d = 4): Heisenberg branch, gate_definitions.jl:41-42
         verts = verts if isinstance(verts, list) else [verts]
-        out.append((np.asarray(arr, dtype=np.complex128), [g.v(x) if not isinstance(x, (int, np.integer)) else int(x) for x in verts]))
+        out.append((np.asarray(arr, dtype=np.complex128), [_vid(g, x) for x in verts]))
     return out
 
 
@@ -593,7 +603,7 @@ def expect(bpc: BeliefPropagationCache, obs: tuple, tree=None) -> complex:
     op, verts = obs[0], obs[1]
     coeff = obs[2] if len(obs) > 2 else 1
     verts = verts if isinstance(verts, list) else [verts]
-    vs = [g.v(x) if not isinstance(x, (int, np.integer)) else int(x) for x in verts]
+    vs = [_vid(g, x) for x in verts]
     names = list(op) if isinstance(op, str) else list(op)
     if len(names) != len(vs):
         raise ValueError("Invalid observable: need as many operators as vertices passed.")

@@ -71,6 +71,7 @@ struct tnqs_ctx {
   // Bilinear form <phi|psi> (src/Forms/bilinearform.jl:28-54): when `bra` is attached, every BP contraction of this handle closes
   // its ket tensors against the conjugated site tensors of that handle instead of its own (messages are then not Hermitian).
   tnqs_ctx* bra = nullptr;
+  std::vector<tnqs_ctx*> bra_users;                // handles whose `bra` points here: detached when this handle is destroyed
   const cplx* bra_site(int v) const { return bra ? bra->site[v] : site[v]; }
 
   // ---- graph helpers ----
@@ -360,15 +361,24 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
     const auto& chains = levels[L];
     mem[L].resize(chains.size());
     std::vector<int> cur; size_t cur_bytes = 0;
-    for (size_t i = 0; i < chains.size(); ++i) {
+    // a sub-level launches one slab / closing kernel pair, i.e. one fast-path bond dimension: chains are taken grouped by it
+    // (generic chains first; they ride along with any group), and a change of N opens a new sub-level.  Inhomogeneous states
+    // (a region still at 8 next to one at 16 under a cutoff-driven truncation) therefore cost one more launch pair, not an error.
+    std::vector<int> order(chains.size()), fN(chains.size());
+    for (size_t i = 0; i < chains.size(); ++i) { order[i] = (int)i; fN[i] = fast_path_N(c, chains[i]); }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return fN[a] < fN[b]; });
+    int curN = 0;
+    for (int i : order) {
       const Chain& ch = chains[i];
       int nsteps = (ch.op ? 1 : 0) + (int)ch.absorb.size();
       ChainMem cm; cm.buf_elems = (size_t)c->site_n[ch.v]; cm.nbuf = std::min(nsteps, 2); cm.nsplit = 1; cm.partial_elems = 0;
-      if (fast_path_N(c, ch)) cm.nbuf = 1;
+      if (fN[i]) cm.nbuf = 1;
       mem[L][i] = cm;
       size_t bytes = align_up(cm.buf_elems * sizeof(cplx), 256) * cm.nbuf;
-      if (!cur.empty() && cur_bytes + bytes > scratch_budget_bytes) { subsets[L].push_back(cur); cur.clear(); cur_bytes = 0; }
-      cur.push_back((int)i); cur_bytes += bytes;
+      const bool otherN = fN[i] && curN && fN[i] != curN;
+      if (!cur.empty() && (cur_bytes + bytes > scratch_budget_bytes || otherN)) { subsets[L].push_back(cur); cur.clear(); cur_bytes = 0; curN = 0; }
+      cur.push_back(i); cur_bytes += bytes;
+      if (fN[i]) curN = fN[i];
       max_scratch = std::max(max_scratch, cur_bytes);
     }
     if (!cur.empty()) subsets[L].push_back(cur);

@@ -117,8 +117,12 @@ __device__ int jacobi_columns(cplx* W, int ldw, int m, cplx* V, int ldv, int nv,
   if (mx <= 16) return jacobi_columns_t<1>(W, ldw, m, V, ldv, nv, n);
   if (mx <= 32) return jacobi_columns_t<2>(W, ldw, m, V, ldv, nv, n);
   if (mx <= 64) return jacobi_columns_t<4>(W, ldw, m, V, ldv, nv, n);
-  return jacobi_columns_t<8>(W, ldw, m, V, ldv, nv, n);          // m, nv <= 128 (d * chi <= 64 in the gate path)
+  if (mx <= 128) return jacobi_columns_t<8>(W, ldw, m, V, ldv, nv, n);
+  // theta' of the gate path is (q1 d) x (q2 d) with q <= d chi <= 64: up to 256 rows on d = 4 (Pauli) sites, 192 on d = 3;
+  // the host refuses anything longer (GateBatch::stage2), so no row is ever left out of the inner products
+  return jacobi_columns_t<16>(W, ldw, m, V, ldv, nv, n);
 }
+constexpr int TNQS_JACOBI_MAX_ROWS = 256;
 
 // ---------------------------------------------------------------------------------------------------------------
 struct EighDesc {

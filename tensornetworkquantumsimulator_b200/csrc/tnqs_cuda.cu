@@ -148,6 +148,10 @@ extern "C" int32_t tnqs_destroy(tnqs_ctx* c) {
   c->collect_profile();
   drop_pending_gate(c);
   bp_cache_drop(c);
+  // bilinear forms: no handle may keep a pointer to this one (its cached BP plan holds our site pointers), nor we to another
+  for (tnqs_ctx* u : c->bra_users) { cudaStreamSynchronize(u->stream); bp_cache_drop(u); u->bra = nullptr; ++u->state_version; }
+  c->bra_users.clear();
+  if (c->bra) { auto& us = c->bra->bra_users; us.erase(std::remove(us.begin(), us.end(), c), us.end()); c->bra = nullptr; }
   c->arena_destroy();
   c->hstage_destroy();
   halo_release(c);
@@ -285,7 +289,7 @@ __global__ void k_bp_loop_check(cudaGraphConditionalHandle h, BpLoopState* st, c
   cudaGraphSetConditional(h, more ? 1u : 0u);
 }
 struct BpPlanCache {
-  Plan plan; std::vector<int> seq; int mode = -1, normalize = -1, hermitize = -1, want_diff = -1; long long version = -1;
+  Plan plan; std::vector<int> seq; int mode = -1, normalize = -1, hermitize = -1, want_diff = -1; long long version = -1, bra_version = -1;
   double* d_diff = nullptr; std::vector<void*> owned;
   BpLoopState* d_loop = nullptr;
   cudaGraphExec_t graph = nullptr;     // the whole refresh: WHILE(sweep: all levels + diff sum + loop test), built once per launch structure
@@ -311,6 +315,10 @@ static bool graphs_disabled() {
 static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, const tnqs_bp_opts& o, int* iters_out,
                            double* mean_out) {
   REQUIRE(o.maxiter >= 1, TNQS_ERR_INVALID_ARG, "You need to specify a number of iterations for BP!");
+  // a gate applied to either layer since tnqs_set_bra may have changed its bond dimensions: the closings would read the
+  // bra's site tensors with the ket's extents
+  REQUIRE(!c->bra || (c->bra->chi == c->chi && c->bra->d == c->d), TNQS_ERR_SHAPE,
+          "bilinear form: bond dimensions of ket and bra differ (a layer changed after tnqs_set_bra)");
   std::vector<int> seq;
   for (int i = 0; i < nseq_in; ++i) {
     int k = seq_in[i];
@@ -356,7 +364,8 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
   BpPlanCache* pc = (BpPlanCache*)c->bp_cache;
   const bool same_request = pc && pc->mode == o.mode && pc->normalize == o.normalize && pc->hermitize == o.hermitize &&
                             pc->want_diff == (int)want_diff && pc->seq == seq;
-  if (!(same_request && pc->version == c->state_version)) {
+  const long long bra_version = c->bra ? c->bra->state_version : -1;      // the plan holds the bra's site pointers too
+  if (!(same_request && pc->version == c->state_version && pc->bra_version == bra_version)) {
     // (re)build; when only site pointers / values changed the new plan lands in the old one's buffers and keeps its graph
     BpPlanCache* old = same_request ? pc : nullptr;
     if (pc && !old) { bp_cache_drop(c); pc = nullptr; }
@@ -396,7 +405,7 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
     for (void* p : c->temp) nc->owned.push_back(p);
     c->temp.clear(); c->temp.swap(saved);
     nc->seq = seq; nc->mode = o.mode; nc->normalize = o.normalize; nc->hermitize = o.hermitize; nc->want_diff = want_diff;
-    nc->version = c->state_version;
+    nc->version = c->state_version; nc->bra_version = bra_version;
     c->bp_cache = nc; pc = nc;
   }
   const Plan& plan = pc->plan;
@@ -946,6 +955,7 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
       ThetaDesc& t = td[i];
       t.r1 = A.Rbuf; t.q1 = A.q; t.ld1 = A.q; t.r2 = B.Rbuf; t.q2 = B.q; t.ld2 = B.q; t.gate = d_gates + hoff; t.d = d; t.chi = A.chib;
       int m = A.q * d, nn = B.q * d;
+      REQUIRE(std::max(m, nn) <= TNQS_JACOBI_MAX_ROWS, TNQS_ERR_UNSUPPORTED, "two-site gate: theta has more than 256 rows (q * d) - not supported by the Jacobi SVD");
       t.theta = c->talloc<cplx>((size_t)m * nn);
       r1n[i] = c->talloc<cplx>((size_t)m * std::min(std::min(m, nn), cap));
       r2n[i] = c->talloc<cplx>((size_t)nn * std::min(std::min(m, nn), cap));
@@ -1693,7 +1703,9 @@ extern "C" int32_t tnqs_set_bra(tnqs_ctx* c, tnqs_ctx* bra) {
   }
   c->sync();
   bp_cache_drop(c);
+  if (c->bra) { auto& us = c->bra->bra_users; us.erase(std::remove(us.begin(), us.end(), c), us.end()); }
   c->bra = bra;
+  if (bra) bra->bra_users.push_back(c);
   ++c->state_version;
   API_END(c)
 }

@@ -91,8 +91,8 @@ class TensorNetworkState:
         check(self._h.ptr, _lib.load().tnqs_set_site(self._h.ptr, int(v), ptr_f64(flat), a.size))
 
     def __getitem__(self, v) -> np.ndarray:
-        """Site tensor as ndarray [s, b_e1..b_ez] (getindex)."""
-        v = self.g.v(v) if not isinstance(v, (int, np.integer)) else int(v)
+        """Site tensor as ndarray [s, b_e1..b_ez] (getindex); v is a vertex name (see _vid)."""
+        v = _vid(self.g, v)
         lib = _lib.load()
         n = lib.tnqs_site_size(self._h.ptr, v)
         buf = np.empty(2 * n, dtype=np.float64)
@@ -192,22 +192,24 @@ def random_tensornetworkstate(g: Graph, bond_dimension: int = 1, seed: int = 0, 
 
 
 class BeliefPropagationCache:
-    """Network + one message per directed edge (src/MessagePassing/beliefpropagationcache.jl:9-13).
-    Shares the device handle of the TensorNetworkState it wraps (the reference shares the tensors too);
-    every non-mutating function clones the handle first."""
+    """Network + one message per directed edge (src/MessagePassing/beliefpropagationcache.jl:9-13), messages at their default.
+    On the device the messages live in the same handle as the site tensors, so the public constructor wraps a CLONE of psi:
+    a second cache over the same state does not clobber the messages of the first, and in-place operations on the cache never
+    reach the caller's state (the reference's constructor does not alias either).  `_share=True` (internal; callers that
+    have just made their own copy, or that want the state to follow the cache) wraps psi's handle itself."""
 
-    def __init__(self, psi: TensorNetworkState, _keep_messages: bool = False):
-        self.psi = psi
+    def __init__(self, psi: TensorNetworkState, _keep_messages: bool = False, _share: bool = False):
+        self.psi = psi if _share else psi.copy()
         if not _keep_messages:
-            check(psi._h.ptr, _lib.load().tnqs_reset_messages(psi._h.ptr))
+            check(self.psi._h.ptr, _lib.load().tnqs_reset_messages(self.psi._h.ptr))
 
     @property
     def g(self) -> Graph:
         return self.psi.g
 
     def copy(self) -> "BeliefPropagationCache":
-        out = BeliefPropagationCache(self.psi.copy(), _keep_messages=True)
-        bra = getattr(self, "_bra", None)
+        out = BeliefPropagationCache(self.psi.copy(), _keep_messages=True, _share=True)
+        bra = getattr(self.psi, "_bra", None)
         if bra is not None:
             _attach_bra(out, bra)
         return out
@@ -217,8 +219,27 @@ def network(x) -> TensorNetworkState:
     return x.psi if isinstance(x, BeliefPropagationCache) else x
 
 
+def _int_named(g: Graph) -> bool:
+    flag = getattr(g, "_int_named", None)
+    if flag is None:
+        flag = any(isinstance(n, (int, np.integer)) and not isinstance(n, bool) for n in g.names)
+        g._int_named = flag
+    return flag
+
+
 def _vid(g: Graph, x) -> int:
-    return int(x) if isinstance(x, (int, np.integer)) else g.v(x)
+    """Vertex NAME -> dense 0-based id.  The reference resolves vertices by name only (graph_ops.jl:53-67 keeps whatever labels
+    the circuit uses, e.g. [("Rx", [3], ..), ("CPHASE", [3, 1], ..)]): on a graph with integer names an integer is therefore
+    always a name, never an id.  Graphs whose names are tuples / strings additionally accept a dense id (internal callers and
+    the benchmarks address vertices that way)."""
+    if isinstance(x, (int, np.integer)) and not isinstance(x, bool):
+        if _int_named(g):
+            try:
+                return g.index[int(x)]
+            except KeyError:
+                raise KeyError(f"vertex {int(x)} is not in the graph (integer-named graphs are addressed by name)") from None
+        return int(x)
+    return g.v(x)
 
 
 def message(bpc: BeliefPropagationCache, edge) -> np.ndarray:
@@ -322,7 +343,7 @@ def apply_gates(circuit: Sequence[tuple], psi, apply_kwargs: Optional[dict] = No
     holds the element counts afterwards."""
     if isinstance(psi, TensorNetworkState):
         kw = bp_update_kwargs if bp_update_kwargs is not None else default_bp_update_kwargs(psi)
-        bpc = update(BeliefPropagationCache(psi if inplace else psi.copy()), inplace=True, **kw)
+        bpc = update(BeliefPropagationCache(psi if inplace else psi.copy(), _share=True), inplace=True, **kw)
         bpc, errs = apply_gates(circuit, bpc, apply_kwargs, kw, update_cache, verbose, True, info, fetch)
         return bpc.psi, errs
     out = psi if inplace else psi.copy()
@@ -501,7 +522,7 @@ def expect(x, obs, alg: str = "bp", cache_update_kwargs: Optional[dict] = None, 
         raise ValueError("Only alg='bp' is on the CUDA path (Expected BeliefPropagationCache or TensorNetworkState for 'bp' algorithm)")
     if isinstance(x, TensorNetworkState):
         kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(x)
-        x = update(BeliefPropagationCache(x.copy()), inplace=True, **kw)
+        x = update(BeliefPropagationCache(x.copy(), _share=True), inplace=True, **kw)
     single = isinstance(obs, tuple)
     obs_list = [obs] if single else list(obs)
     g = x.g
@@ -545,7 +566,7 @@ def reduced_density_matrix(x, vertices, alg: str = "bp", normalize: bool = True,
         raise ValueError("Only alg='bp' is on the CUDA path")
     if isinstance(x, TensorNetworkState):
         kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(x)
-        x = update(BeliefPropagationCache(x.copy()), inplace=True, **kw)
+        x = update(BeliefPropagationCache(x.copy(), _share=True), inplace=True, **kw)
     vs = [_vid(x.g, v) for v in (vertices if isinstance(vertices, list) else [vertices])]
     if len(vs) == 1:
         r = rdm_1site(x, vs)[0]
@@ -558,7 +579,7 @@ def reduced_density_matrix(x, vertices, alg: str = "bp", normalize: bool = True,
         raise NotImplementedError("multi-site reduced density matrices need qubit sites")
     n = len(vs)
     strings = ["".join(p) for p in itertools.product("IXYZ", repeat=n)]
-    vals = expect(x, [(s, list(vs)) for s in strings[1:]], tree=tree)
+    vals = expect(x, [(s, [x.g.names[v] for v in vs]) for s in strings[1:]], tree=tree)
     rho = np.eye(2 ** n, dtype=np.complex128)
     for s, val in zip(strings[1:], vals):
         p = np.array([[1.0 + 0j]])
@@ -611,7 +632,9 @@ def partitionfunction(bpc: BeliefPropagationCache) -> complex:
 
 def _attach_bra(bpc: "BeliefPropagationCache", bra: Optional[TensorNetworkState]) -> None:
     check(bpc.psi._h.ptr, _lib.load().tnqs_set_bra(bpc.psi._h.ptr, bra._h.ptr if bra is not None else None))
-    bpc._bra = bra                                   # keeps the bra's handle alive while it is attached
+    # the reference lives on the state that owns the device handle (the raw bra pointer sits in that handle), not on the cache
+    # object: network(bilinear_cache(..)) stays valid after the cache is dropped.  The library also detaches on tnqs_destroy.
+    bpc.psi._bra = bra
 
 
 def _pad_bonds(psi: TensorNetworkState, chi: np.ndarray) -> TensorNetworkState:
@@ -642,7 +665,7 @@ def bilinear_cache(psi: TensorNetworkState, phi: TensorNetworkState, delta_defau
     chi = np.maximum(psi.bond_dims(), phi.bond_dims())
     ket = _pad_bonds(psi, chi)
     bra = _pad_bonds(phi, chi)
-    bpc = BeliefPropagationCache(ket.copy() if ket is psi else ket)
+    bpc = BeliefPropagationCache(ket.copy() if ket is psi else ket, _share=True)
     _attach_bra(bpc, bra)
     if delta_default:
         for e in range(psi.g.ne):
@@ -674,7 +697,7 @@ def contract(tensors: Sequence[np.ndarray], g: Graph, alg: str = "bp", bp_update
     ket = TensorNetworkState.from_arrays(g, [np.asarray(t, dtype=np.complex128)[None, ...] for t in tensors], device=device)
     ones = TensorNetworkState.from_arrays(g, [np.ones((1,) * (1 + g.degree(v)), dtype=np.complex128) for v in range(g.nv)], device=device)
     chi = ket.bond_dims()
-    bpc = BeliefPropagationCache(ket)
+    bpc = BeliefPropagationCache(ket, _share=True)
     _attach_bra(bpc, _pad_bonds(ones, chi))
     for e in range(g.ne):
         m = np.zeros((int(chi[e]), int(chi[e])), dtype=np.complex128)
@@ -690,7 +713,7 @@ def norm_sqr(x, alg: str = "bp", cache_update_kwargs: Optional[dict] = None) -> 
     """BP norm (src/norm_sqr.jl:56-76): partition function of the updated cache."""
     if isinstance(x, TensorNetworkState):
         kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(x)
-        x = update(BeliefPropagationCache(x.copy()), inplace=True, **kw)
+        x = update(BeliefPropagationCache(x.copy(), _share=True), inplace=True, **kw)
     return partitionfunction(x)
 
 
@@ -706,7 +729,7 @@ def symmetric_gauge(x, regularization: float = 10 * np.finfo(np.float64).eps, ca
     """src/symmetric_gauge.jl:1-68.  A TensorNetworkState is updated with maxiter=40 first and a state is returned."""
     if isinstance(x, TensorNetworkState):
         kw = cache_update_kwargs if cache_update_kwargs is not None else dict(maxiter=40)
-        bpc = update(BeliefPropagationCache(x.copy()), inplace=True, **kw)
+        bpc = update(BeliefPropagationCache(x.copy(), _share=True), inplace=True, **kw)
         return symmetric_gauge(bpc, regularization, inplace=True).psi
     out = x if inplace else x.copy()
     check(out.psi._h.ptr, _lib.load().tnqs_symmetric_gauge(out.psi._h.ptr, float(regularization)))
@@ -716,7 +739,7 @@ def symmetric_gauge(x, regularization: float = 10 * np.finfo(np.float64).eps, ca
 def gauge_and_scale(psi: TensorNetworkState, cache_update_kwargs: Optional[dict] = None) -> TensorNetworkState:
     """symmetrize_and_bpnormalize (src/symmetric_gauge.jl:76-83)."""
     kw = cache_update_kwargs if cache_update_kwargs is not None else dict(maxiter=40)
-    bpc = update(BeliefPropagationCache(psi.copy()), inplace=True, **kw)
+    bpc = update(BeliefPropagationCache(psi.copy(), _share=True), inplace=True, **kw)
     rescale(bpc, inplace=True)
     return symmetric_gauge(bpc, inplace=True).psi
 
@@ -727,7 +750,7 @@ def truncate(x, maxdim: int, cutoff: Optional[float] = None, normalize_tensors: 
     if alg != "bp":
         raise ValueError("Only alg='bp' is on the CUDA path")
     if isinstance(x, TensorNetworkState):
-        bpc = update(BeliefPropagationCache(x.copy()), inplace=True)
+        bpc = update(BeliefPropagationCache(x.copy(), _share=True), inplace=True)
         return truncate(bpc, maxdim, cutoff, normalize_tensors, alg, edge_groups, bp_update_kwargs, True).psi
     out = x if inplace else x.copy()
     g = out.g
@@ -750,7 +773,7 @@ def entanglement(x, edge, alg: str = "bp") -> float:
     chi x chi messages are read back and the scalar is formed on the host, like the reference's own scalar
     post-processing."""
     if isinstance(x, TensorNetworkState):
-        x = update(BeliefPropagationCache(x.copy()), inplace=True)
+        x = update(BeliefPropagationCache(x.copy(), _share=True), inplace=True)
     g = x.g
     e = int(edge) if isinstance(edge, (int, np.integer)) else g.edge_of[(_vid(g, edge[0]), _vid(g, edge[1]))]
     roots = []
@@ -774,7 +797,7 @@ def normalize(psi: TensorNetworkState, alg: str = "bp", cache_update_kwargs: Opt
     if alg != "bp":
         raise ValueError("Only alg='bp' is on the CUDA path")
     kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(psi)
-    bpc = update(BeliefPropagationCache(psi.copy()), inplace=True, **kw)
+    bpc = update(BeliefPropagationCache(psi.copy(), _share=True), inplace=True, **kw)
     return rescale(bpc, inplace=True).psi
 
 
@@ -789,7 +812,7 @@ def sample(psi: TensorNetworkState, nsamples: int, alg: str = "bp", bp_update_kw
     rng = rng if rng is not None else np.random.default_rng()
     kw = dict(bp_update_kwargs or {})
     g = psi.g
-    bpc = update(BeliefPropagationCache(psi.copy()), inplace=True, **kw)
+    bpc = update(BeliefPropagationCache(psi.copy(), _share=True), inplace=True, **kw)
     if gauge_state:                                        # symmetrize_and_normalize (src/symmetric_gauge.jl:70-74)
         rescale(bpc, inplace=True)
         symmetric_gauge(bpc, inplace=True)

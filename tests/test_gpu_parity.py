@@ -425,7 +425,7 @@ def _two_rank_setup(E, g, psi_o, chi_cap):
                 dims = [psi_o.bond_dim(int(lg.l2g_e[e])) for e in lg.g.incident[lv]]
                 ts.append(np.zeros([2] + dims, dtype=np.complex128))
         psi = E.TensorNetworkState.from_arrays(lg.g, ts, chi_cap=chi_cap)
-        bpc = E.BeliefPropagationCache(psi)
+        bpc = E.BeliefPropagationCache(psi, _share=True)
         from tensornetworkquantumsimulator_b200 import lib
         ow = lib.i32(lg.owner_local)
         lib.check(psi._h.ptr, lib.load().tnqs_set_partition(psi._h.ptr, lib.ptr_i32(ow), r))
@@ -707,7 +707,7 @@ def test_full_size_c2_properties(E):
     import bench
     g, groups, rx, rz, rzz, seq = bench.workload(32, 32)
     psi = E.random_tensornetworkstate(g, bond_dimension=16, seed=1)
-    bpc = E.BeliefPropagationCache(psi)
+    bpc = E.BeliefPropagationCache(psi, _share=True)
     info = {}
     E.update(bpc, edge_sequence=seq, inplace=True, maxiter=40, tolerance=1e-10, info=info)
     assert info["iters"] < 40 and info["mean_diff"] <= 1e-10
@@ -836,7 +836,7 @@ def test_partitioned_bp_peer_memory_halo_matches_single_handle(E, shape, chi, wo
         psi = E.TensorNetworkState.from_arrays(lg.g, ts, chi_cap=chi)
         ow = lib.i32(lg.owner_local)
         lib.check(psi._h.ptr, lib.load().tnqs_set_partition(psi._h.ptr, lib.ptr_i32(ow), r))
-        caches.append(E.BeliefPropagationCache(psi))
+        caches.append(E.BeliefPropagationCache(psi, _share=True))
     comps = [P.EngineCompute(c, torch.device("cuda", 0)) for c in caches]
     layouts = [P.halo_layout(lg) for lg in lgs]
     ptrs = [comps[r].halo_alloc(world, layouts[r][0])[1] for r in range(world)]
@@ -935,3 +935,75 @@ def test_bilinear_form_bp_inner(E, name, chi):
     _E._attach_bra(be, None)
     bn = E.update(E.BeliefPropagationCache(be.psi), maxiter=3, edge_sequence=seq, inplace=True)      # (the constructor resets the messages)
     check_messages(E, bn, O.update(O.BeliefPropagationCache(psi_o), maxiter=3, edge_sequence=seq))
+
+
+@pytest.mark.parametrize("d,shape,chi,rows", [(4, (3, 2), 16, 256), (4, (3, 3), 9, 144), (3, (3, 3), 15, 135)])
+def test_two_site_gate_theta_longer_than_128_rows(E, d, shape, chi, rows):
+    # Pauli (d = 4) and spin-1 (d = 3) sites with d * chi close to 64: theta' = (q d) x (q d) with q = d chi, i.e. up to 256 rows -
+    # the Jacobi SVD must rotate every row (a row loop that stops at 128 returns garbage singular values with status 0)
+    g = G.named_grid(shape)
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=chi, seed=97, d=d)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    deg = [g.degree(v) for v in range(g.nv)]
+    e = max(range(g.ne), key=lambda e: deg[int(g.esrc[e])] + deg[int(g.edst[e])])       # the edge between the best-connected vertices
+    q = [min(chi ** (deg[v] - 1), d * chi) for v in (int(g.esrc[e]), int(g.edst[e]))]
+    assert max(q) * d == rows
+    rs = np.random.default_rng(11)
+    h = rs.normal(size=(d * d, d * d)) + 1j * rs.normal(size=(d * d, d * d))
+    u, _ = np.linalg.qr(h)
+    gate_case(E, g, psi_o, [e], [u.reshape(d, d, d, d)], dict(maxdim=chi, cutoff=1e-10, normalize_tensors=True), sweeps=3)
+
+
+@pytest.mark.parametrize("mode", ["jacobi", "reference"])
+def test_bp_regions_of_bond_dimension_8_and_16_in_one_sweep(E, mode):
+    # an inhomogeneous state (cutoff-driven truncation with maxdim = 16): vertices with all bonds 8 and vertices with all bonds 16
+    # in the same BP level -> one slab / closing launch pair per bond dimension, vertices in between on the generic kernels
+    g = G.named_grid((6, 3))
+    dims = np.array([16 if min(g.names[int(a)][0], g.names[int(b)][0]) >= 4 else 8 for a, b in zip(g.esrc, g.edst)])
+    psi_o = ragged_state(g, dims, seed=23)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    kinds = {tuple(sorted(set(int(dims[e]) for e in g.incident[v]))) for v in range(g.nv)}
+    assert {(8,), (16,), (8, 16)} <= kinds
+    if mode == "jacobi":
+        bo = O.BeliefPropagationCache(psi_o)
+        for _ in range(2):
+            bo.messages = {k: O.updated_message(bo, k) for k in range(2 * g.ne)}
+        be = E.update(to_engine(psi_o, chi_cap=16), maxiter=2, edge_sequence=np.arange(2 * g.ne), mode="jacobi")
+    else:
+        seq = G.forest_cover_edge_sequence(g)
+        bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=2, edge_sequence=seq)
+        be = E.update(to_engine(psi_o, chi_cap=16), maxiter=2, edge_sequence=seq)
+    check_messages(E, be, bo)
+
+
+def test_bilinear_form_outlives_its_cache_and_checks_shapes(E):
+    # the bra pointer lives in the ket's device handle: dropping the cache object (or the bra) must not leave it dangling, and a
+    # gate that changes the ket's bond dimensions while a bra is attached must be refused by the next BP update
+    import gc
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=41)
+    phi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=42)
+    seq = G.forest_cover_edge_sequence(g)
+    psi = E.TensorNetworkState.from_arrays(g, psi_o.tensors, chi_cap=4)
+    phi = E.TensorNetworkState.from_arrays(g, phi_o.tensors, chi_cap=4)
+    ket = E.network(E.bilinear_cache(psi, phi))           # the cache is garbage from here on
+    del phi
+    gc.collect()
+    bn = E.update(E.BeliefPropagationCache(ket, _share=True), maxiter=3, edge_sequence=seq, inplace=True)
+    bo = O.update(O.BeliefPropagationCache(psi_o.copy(), {}, phi_o), maxiter=3, edge_sequence=seq)
+    check_messages(E, bn, bo)
+    # grow one bond of the ket: 2 -> 4 under a generic two-site gate; BP must now fail loudly instead of reading the bra out of bounds
+    rs = np.random.default_rng(2)
+    u, _ = np.linalg.qr(rs.normal(size=(4, 4)) + 1j * rs.normal(size=(4, 4)))
+    ranks, _, _ = E.apply_2site_batch(bn, [0], [u.reshape(2, 2, 2, 2)], apply_kwargs=dict(maxdim=4, cutoff=None))
+    assert ranks[0] == 4
+    with pytest.raises(E.TnqsError) as ei:
+        E.update(bn, maxiter=1, edge_sequence=seq, inplace=True)
+    assert ei.value.status == -2                           # TNQS_ERR_SHAPE
+    # destroying the bra detaches it: the ket is a plain state again
+    ket._bra = None
+    gc.collect()
+    plain = E.update(E.BeliefPropagationCache(ket, _share=True), maxiter=1, edge_sequence=seq, inplace=True)
+    assert np.isfinite(E.partitionfunction(plain))

@@ -1,7 +1,7 @@
 """The HOST logic of engine.py executed without a GPU: tests/fake_lib.py answers the C-ABI calls with the oracle, so what is tested
 here is the Python side only - argument packing, column-major flattening, shapes, and the ORDER OF CALLS of the composed operations
 (inner between different bond dimensions, observables over a Steiner tree, multi-site density matrices, the Heisenberg-picture
-circuit).  The device side of the same calls is tests/test_gpu_parity.py / tests/test_zz_pending_gpu.py."""
+circuit).  The device side of the same calls is tests/test_gpu_parity.py / tests/test_gpu_compositions.py."""
 import gc
 import importlib.util
 import os
@@ -53,7 +53,7 @@ def test_heisenberg_example_through_the_host_api(E):
     g = G.named_grid((4, 4))
     o0 = E.paulitensornetworkstate(lambda v: "Z" if v == (2, 2) else "I", g, chi_cap=4)
     assert list(o0.site_dims()) == [4] * g.nv
-    bpc = E.BeliefPropagationCache(o0.copy())
+    bpc = E.BeliefPropagationCache(o0.copy(), _share=True)
     for l in range(2):
         bpc, errs = E.apply_gates(mg.heisenberg_layer(g), bpc, apply_kwargs=dict(maxdim=4, cutoff=1e-14, normalize_tensors=False))
         bpc = E.rescale(bpc)
@@ -178,3 +178,49 @@ def test_single_layer_network_contraction(E):
     zo = O.contract_bp(g, ts)
     assert abs(E.contract(ts, g) - zo) < 1e-10 * abs(zo)
     assert abs(zo - O.contract_exact(g, ts)) < 0.05 * abs(zo)               # BP is approximate on loops, close for a near-positive network
+
+
+def test_integer_vertex_names_resolve_by_name(E):
+    # circuits with integer vertex labels (graph_ops.jl:53-67 numbers nothing: [("Rx", [3], ..), ("CNOT", [3, 10]), ..]): an integer
+    # is a NAME there, never a dense id.  Truth = a hand-written 3-qubit statevector, independent of any name resolution.
+    circuit = [("Rx", [3], 0.7), ("Rx", [10], 0.3), ("Rx", [1], 1.1), ("CNOT", [3, 10]), ("CNOT", [10, 1]), ("Rx", [1], 0.4)]
+    g = G.build_graph_from_gates(circuit)
+    assert g.names == [3, 10, 1] and g.ne == 2                      # ids 0, 1, 2 by first appearance: name 1 is id 2, name 3 is id 0
+    psi = E.tensornetworkstate(lambda v: "↑", g, chi_cap=4)
+    out, errs = E.apply_gates(circuit, psi, apply_kwargs=dict(maxdim=4, cutoff=1e-14))
+    rx = lambda t: np.array([[np.cos(t / 2), -1j * np.sin(t / 2)], [-1j * np.sin(t / 2), np.cos(t / 2)]])
+    cnot = np.eye(4)[[0, 1, 3, 2]].astype(complex)
+    I2 = np.eye(2)
+    sv = np.zeros(8, complex); sv[0] = 1                            # qubit order (3, 10, 1), first slowest
+    sv = np.kron(np.kron(rx(0.7), rx(0.3)), rx(1.1)) @ sv
+    sv = np.kron(cnot, I2) @ sv
+    sv = np.kron(I2, cnot) @ sv
+    sv = np.kron(np.kron(I2, I2), rx(0.4)) @ sv
+    Z = np.diag([1.0, -1.0])
+    want = {3: np.vdot(sv, np.kron(np.kron(Z, I2), I2) @ sv).real, 10: np.vdot(sv, np.kron(np.kron(I2, Z), I2) @ sv).real,
+            1: np.vdot(sv, np.kron(np.kron(I2, I2), Z) @ sv).real}
+    for name, w in want.items():
+        assert abs(E.expect(out, ("Z", [name])) - w) < 1e-12        # a path is a tree: BP is exact
+    assert abs(E.expect(out, ("ZZ", [3, 1])) - np.vdot(sv, np.kron(np.kron(Z, I2), Z) @ sv).real) < 1e-12
+    assert out[10].shape[0] == 2 and out[10].ndim == 3              # getindex by name: the middle vertex has two bonds
+    with pytest.raises(KeyError):
+        E.expect(out, ("Z", [0]))                                   # 0 is not a vertex of this graph
+    assert E.circuit_schedule(g, circuit)[-1] == ("refresh",)
+    # the oracle resolves the same way
+    bo, _ = O.apply_gates(circuit, O.tensornetworkstate(lambda v: "↑", g), apply_kwargs=dict(maxdim=4, cutoff=1e-14))
+    assert abs(O.expect(O.update(O.BeliefPropagationCache(bo)), ("Z", [1])) - want[1]) < 1e-12
+
+
+def test_cache_constructor_does_not_alias_the_state(E):
+    # BeliefPropagationCache(psi) wraps a clone: a second cache over the same state keeps the first one's messages intact and
+    # in-place work on a cache never reaches psi (the reference's constructor does not alias either)
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=8)
+    psi = E.TensorNetworkState.from_arrays(g, psi_o.tensors, chi_cap=4)
+    b1 = E.update(E.BeliefPropagationCache(psi), maxiter=4, inplace=True)
+    m1 = [m.copy() for m in E.messages(b1)]
+    b2 = E.BeliefPropagationCache(psi)
+    for a, b in zip(E.messages(b1), m1):
+        assert np.array_equal(a, b)
+    E.apply_1site_batch(b2, [0], [gates.gate_array(("X", [0]))], normalize_tensors=False)
+    assert np.array_equal(psi[(1, 1)], psi_o.tensors[0]) and not np.array_equal(b2.psi[(1, 1)], psi_o.tensors[0])

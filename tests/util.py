@@ -17,7 +17,7 @@ def ragged_state(g, dims, seed, d=2):
 def to_engine(psi_o, chi_cap=None, with_messages=None):
     from tensornetworkquantumsimulator_b200 import engine as E
     psi = E.TensorNetworkState.from_arrays(psi_o.g, psi_o.tensors, chi_cap=chi_cap)
-    bpc = E.BeliefPropagationCache(psi)
+    bpc = E.BeliefPropagationCache(psi, _share=True)
     if with_messages is not None:
         for k, m in with_messages.items():
             E.setmessage(bpc, k, m)

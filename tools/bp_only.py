@@ -10,7 +10,7 @@ mode = sys.argv[3] if len(sys.argv) > 3 else "reference"
 sweeps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 g, groups, rx, rz, rzz, seq = bench.workload(nx, nx)
 psi = E.random_tensornetworkstate(g, bond_dimension=chi, seed=1)
-bpc = E.BeliefPropagationCache(psi)
+bpc = E.BeliefPropagationCache(psi, _share=True)
 E.update(bpc, edge_sequence=seq, inplace=True, maxiter=3); E.rescale(bpc, inplace=True)
 s = seq if mode == "reference" else np.arange(2 * g.ne)
 kw = dict(mode="jacobi") if mode != "reference" else {}

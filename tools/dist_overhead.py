@@ -10,7 +10,7 @@ chi = 16
 gg = G.named_grid((32, 32 * world)); owner = P.strip_owner(gg, world, axis=1); lg = P.build_local_graph(gg, owner, rank)
 groups = G.grid_edge_color(gg)
 psi = E.random_tensornetworkstate(lg.g, bond_dimension=chi, seed=1 + rank, device=local)
-bpc = E.BeliefPropagationCache(psi)
+bpc = E.BeliefPropagationCache(psi, _share=True)
 ow = lib.i32(lg.owner_local); lib.check(psi._h.ptr, lib.load().tnqs_set_partition(psi._h.ptr, lib.ptr_i32(ow), rank))
 dev = torch.device("cuda", local); comp = P.EngineCompute(bpc, dev); slot = chi * chi
 seq = np.array([k for k in range(2 * lg.g.ne) if lg.owned[lg.g.dsrc(k)]], dtype=np.int32)

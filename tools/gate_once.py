@@ -7,7 +7,7 @@ nx = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 chi = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 g, groups, rx, rz, rzz, seq = bench.workload(nx, nx)
 psi = E.random_tensornetworkstate(g, bond_dimension=chi, seed=1)
-bpc = E.BeliefPropagationCache(psi)
+bpc = E.BeliefPropagationCache(psi, _share=True)
 E.update(bpc, edge_sequence=seq, inplace=True, maxiter=3); E.rescale(bpc, inplace=True)
 kw = dict(maxdim=chi, cutoff=1e-10, normalize_tensors=True)
 for grp in groups[:2]:

@@ -5,7 +5,7 @@ import bench
 from tensornetworkquantumsimulator_b200 import engine as E, lib
 g, groups, rx, rz, rzz, seq = bench.workload(32, 32)
 psi = E.random_tensornetworkstate(g, bond_dimension=16, seed=1)
-bpc = E.BeliefPropagationCache(psi)
+bpc = E.BeliefPropagationCache(psi, _share=True)
 E.update(bpc, edge_sequence=seq, inplace=True, maxiter=3); E.rescale(bpc, inplace=True)
 L = lib.load(); h = psi._h.ptr
 def t(fn, n=3):

@@ -6,7 +6,7 @@ import torch, bench
 from tensornetworkquantumsimulator_b200 import engine as E
 g, groups, rx, rz, rzz, seq = bench.workload(32, 32)
 psi = E.random_tensornetworkstate(g, bond_dimension=16, seed=1)
-bpc = E.BeliefPropagationCache(psi)
+bpc = E.BeliefPropagationCache(psi, _share=True)
 E.update(bpc, edge_sequence=seq, inplace=True, maxiter=10); E.rescale(bpc, inplace=True)
 st = bench.Stepper(E, torch, bpc, g, groups, rx, rz, rzz, seq, 16, obs_v=g.v((16, 16)))
 st.step()

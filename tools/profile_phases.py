@@ -8,7 +8,7 @@ nx = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 chi = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 g, groups, rx, rz, rzz, seq = bench.workload(nx, nx)
 psi = E.random_tensornetworkstate(g, bond_dimension=chi, seed=1)
-bpc = E.BeliefPropagationCache(psi)
+bpc = E.BeliefPropagationCache(psi, _share=True)
 E.update(bpc, edge_sequence=seq, inplace=True, maxiter=5); E.rescale(bpc, inplace=True)
 L = lib.load(); h = psi._h.ptr
 def prof(name, fn, reps=1):

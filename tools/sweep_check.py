@@ -11,7 +11,7 @@ L = lib.load()
 def run(mode, sweep, iters=3):
     os.environ["TNQS_SWEEP"] = "1" if sweep else "0"
     psi = E.random_tensornetworkstate(g, bond_dimension=chi, seed=1)
-    bpc = E.BeliefPropagationCache(psi)
+    bpc = E.BeliefPropagationCache(psi, _share=True)
     h = psi._h.ptr
     s = seq if mode == "reference" else np.arange(2 * g.ne, dtype=np.int32)
     kw = {} if mode == "reference" else {"mode": "jacobi"}

@@ -9,7 +9,7 @@ def run(sweep, iters, env=None):
     os.environ["TNQS_SWEEP"] = "1" if sweep else "0"
     for k, v in (env or {}).items(): os.environ[k] = v
     psi = E.random_tensornetworkstate(g, bond_dimension=chi, seed=1)
-    bpc = E.BeliefPropagationCache(psi)
+    bpc = E.BeliefPropagationCache(psi, _share=True)
     E.update(bpc, edge_sequence=np.arange(2 * g.ne, dtype=np.int32), inplace=True, maxiter=iters, mode="jacobi")
     for k in (env or {}): os.environ.pop(k)
     return [E.message(bpc, k) for k in range(2 * g.ne)]
