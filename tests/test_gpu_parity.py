@@ -997,6 +997,7 @@ def test_bilinear_form_outlives_its_cache_and_checks_shapes(E):
     # grow one bond of the ket: 2 -> 4 under a generic two-site gate; BP must now fail loudly instead of reading the bra out of bounds
     rs = np.random.default_rng(2)
     u, _ = np.linalg.qr(rs.normal(size=(4, 4)) + 1j * rs.normal(size=(4, 4)))
+    bn = E.BeliefPropagationCache(ket, _share=True)        # identity messages again (those of a bilinear form are not positive)
     ranks, _, _ = E.apply_2site_batch(bn, [0], [u.reshape(2, 2, 2, 2)], apply_kwargs=dict(maxdim=4, cutoff=None))
     assert ranks[0] == 4
     with pytest.raises(E.TnqsError) as ei:
