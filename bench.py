@@ -370,12 +370,7 @@ def run_distributed(args, torch, dist, rank, world, local):
         "metric": "bp_edge_message_updates_per_sec", "value": msg / bp_s, "unit": "messages/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "c128 (f64 arithmetic)", "data": "synthetic",
-        "config": {"workload": f"C2 strips: {nx}x{ny * world} open grid cut into {world} row strips of {nx}x{ny} (one per GPU), random TNS chi={chi} "
-                               "ComplexF64; step = one Trotter layer (Rx,Rz + 4 Rzz classes, maxdim=chi, cutoff=1e-10), lazy BP refreshes "
-                               "(<=25 sweeps, tol 1e-8) + <Z>", "chi": chi, "bp_mode": ("JACOBI; a refresh is one graph launch per rank: boundary messages stored by the message epilogue straight into the neighbour GPU's buffer (P2P over NVLink, CUDA IPC), device-side barrier + all-reduce + convergence test per sweep"
-                                                    if p2p is not None else "JACOBI + NCCL halo exchange (pack / send / recv / unpack) and all-reduce per sweep"),
-                   "gates": "cut-crossing gates via R-factor exchange (tnqs_apply_2site_begin/_end)", "per_rank_lattice": f"{nx}x{ny}",
-                   "l2": f"inputs larger than L2: state {psi_bytes(G.named_grid((nx, ny)), chi) / 2**30:.2f} GiB per GPU vs 126 MB"},
+        "config": bench_config(nx, ny, chi, world, p2p is not None),
         "gates": {"metric": "two_site_gate_applications_per_sec", "value": gates2 / gate_s, "unit": "gates/s"},
         "bp": {"sweeps_per_step": mx[6].item() / args.steps, "approx_tflops": msg / bp_s * fm / 1e12, "halo_bytes_per_step": halo / args.steps},
         "phase_ms_per_step": {"bp": 1e3 * bp_s / args.steps, "two_site_gates": 1e3 * gate_s / args.steps, "one_site": 1e3 * other_s / args.steps},
@@ -501,11 +496,7 @@ def run_engine(args):
         "metric": "bp_edge_message_updates_per_sec", "value": bp_value, "unit": "messages/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64 arithmetic)", "data": "synthetic",
-        "config": {"workload": f"C2: {nx}x{ny} open grid, random TNS chi={chi} ComplexF64 seed 1 (BP-rescaled); step = one Trotter layer "
-                               "(Rx,Rz all sites + 4 Rzz colour classes, maxdim=chi, cutoff=1e-10) with the reference's lazy BP refreshes "
-                               "(<=25 sweeps, tol 1e-8, forest-cover order, REFERENCE_ORDER) + <Z> at the centre",
-                   "chi": chi, "messages_per_sweep": int(len(seq)), "bp_mode": "REFERENCE_ORDER", "per_rank_lattice": f"{nx}x{ny}",
-                   "l2": f"inputs larger than L2: state {psi_bytes(g, chi) / 2**30:.2f} GiB per GPU vs 126 MB"},
+        "config": bench_config(nx, ny, chi, 1),
         "gates": {"metric": "two_site_gate_applications_per_sec", "value": gate_value, "unit": "gates/s",
                   "gflop_per_gate_nominal": gflops / 1e9, "achieved_tflops": gate_value * gflops / 1e12,
                   "frac_of_fp64_peak": gate_value * gflops / 1e12 / pk["fp64_tflops_sustained"]},
@@ -623,6 +614,26 @@ def cpu_sample(nx, ny, chi, n_msgs, n_gates, seed=1):
     return len(ks) / t_msg, (len(es) / t_gate) if es else None, t_msg, t_gate
 
 
+def bench_config(nx, ny, chi, world, p2p=True):
+    """The `config` object of the JSON line - ONE definition for the engine arm and the `--impl reference` arm, so that the driver
+    compares like with like (its `same_config` check)."""
+    from tensornetworkquantumsimulator_b200 import graphs as G
+    if world > 1:
+        return {"workload": f"C2 strips: {nx}x{ny * world} open grid cut into {world} row strips of {nx}x{ny} (one per GPU), random TNS chi={chi} "
+                            "ComplexF64; step = one Trotter layer (Rx,Rz + 4 Rzz classes, maxdim=chi, cutoff=1e-10), lazy BP refreshes "
+                            "(<=25 sweeps, tol 1e-8) + <Z>", "chi": chi,
+                "bp_mode": ("JACOBI; a refresh is one graph launch per rank: boundary messages stored by the message epilogue straight into the neighbour GPU's buffer (P2P over NVLink, CUDA IPC), device-side barrier + all-reduce + convergence test per sweep"
+                            if p2p else "JACOBI + NCCL halo exchange (pack / send / recv / unpack) and all-reduce per sweep"),
+                "gates": "cut-crossing gates via R-factor exchange (tnqs_apply_2site_begin/_end)", "per_rank_lattice": f"{nx}x{ny}",
+                "l2": f"inputs larger than L2: state {psi_bytes(G.named_grid((nx, ny)), chi) / 2**30:.2f} GiB per GPU vs 126 MB"}
+    g = G.named_grid((nx, ny))
+    return {"workload": f"C2: {nx}x{ny} open grid, random TNS chi={chi} ComplexF64 seed 1 (BP-rescaled); step = one Trotter layer "
+                        "(Rx,Rz all sites + 4 Rzz colour classes, maxdim=chi, cutoff=1e-10) with the reference's lazy BP refreshes "
+                        "(<=25 sweeps, tol 1e-8, forest-cover order, REFERENCE_ORDER) + <Z> at the centre",
+            "chi": chi, "messages_per_sweep": 2 * g.ne, "bp_mode": "REFERENCE_ORDER", "per_rank_lattice": f"{nx}x{ny}",
+            "l2": f"inputs larger than L2: state {psi_bytes(g, chi) / 2**30:.2f} GiB per GPU vs 126 MB"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm as restated by the oracle (Julia cannot run here),
     all host threads, bounded sample of the same config per step."""
@@ -644,7 +655,7 @@ def run_reference(args):
     return {"impl": "reference", "metric": "bp_edge_message_updates_per_sec", "value": v, "unit": "messages/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_msgs / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "c128 (f64 arithmetic)", "data": "synthetic",
-            "config": {"workload": f"C2: {args.nx}x{args.ny} open grid, random TNS chi={args.chi} ComplexF64", "chi": args.chi},
+            "config": bench_config(args.nx, args.ny, args.chi, int(os.environ.get("WORLD_SIZE", "1")), os.environ.get("TNQS_BENCH_HALO") != "nccl"),
             "gates": {"metric": "two_site_gate_applications_per_sec", "value": float(np.mean(gvals)), "unit": "gates/s"},
             "cpu_baseline": {"value": v, "unit": "messages/s", "cores": cores, "kind": "port", "sample": sample,
                              "note": "restated CPU oracle (NumPy + OpenBLAS, all host threads) - not Julia"},

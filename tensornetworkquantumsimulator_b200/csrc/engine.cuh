@@ -291,6 +291,7 @@ struct Plan {
   // whole-sweep persistent launch (k_bp_sweep): every chain of every level in one data-flow queue
   bool sweep = false; int sweepN = 0, sweep_items = 0; dim3 sweep_grid; size_t sweep_smem = 0;
   SweepChain* d_chains = nullptr; int* d_chain_done = nullptr; size_t nchains = 0;
+  long long* d_prof = nullptr;       // TNQS_SWEEP_TRACE=1: 32 cycle counters of the sweep kernel (SweepTrace)
   int sweep_commit = 0;              // staged (JACOBI) sweeps end with a commit pass over this many messages
   // storage: a rebuilt plan of the same shape reuses the buffers of its predecessor, so device addresses (and a CUDA graph
   // captured over them) stay valid when only the site pointers inside the descriptors changed
@@ -300,6 +301,8 @@ struct Plan {
   double flops = 0;                  // executed flops per run of the plan (8 per complex MAC)
 };
 
+// smallest K extent (rows of the matricised tensor) of one split of a closing contraction
+static long long split_rows() { const char* e = getenv("TNQS_SPLIT_ROWS"); return e ? std::max(64, atoi(e)) : 512; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // DMMA fast path eligibility: BP-type chain (no operator, closes on a bond leg), site dimension 2, every leg of the
@@ -390,7 +393,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         const Chain& ch = chains[i];
         int n = ch.close_leg < 0 ? c->d[ch.v] : c->chi[c->inc[ch.v][ch.close_leg]];
         long long rows = c->site_n[ch.v] / n;
-        int ns = (int)std::min<long long>(ch.split_cap, std::max<long long>(1, rows / 512));
+        int ns = (int)std::min<long long>(ch.split_cap, std::max<long long>(1, rows / split_rows()));
         mem[L][i].nsplit = std::max(1, ns);
         mem[L][i].partial_elems = (size_t)mem[L][i].nsplit * n * n;
         part += mem[L][i].partial_elems;
@@ -701,7 +704,7 @@ static bool build_sweep_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>&
     const Chain& ch = *chains[i];
     if (!small[i]) {
       const long long rows = c->site_n[ch.v] / N;
-      nsplit[i] = (int)std::max<long long>(1, std::min<long long>(ch.split_cap, rows / 512));
+      nsplit[i] = (int)std::max<long long>(1, std::min<long long>(ch.split_cap, rows / split_rows()));
     }
     max_split = std::max(max_split, nsplit[i]);
   }
@@ -757,7 +760,15 @@ static bool build_sweep_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>&
   plan.sweep_items = (int)items.size();
   plan.sweep_grid = dim3((unsigned)std::min<long long>((long long)items.size(), (long long)QUEUE_CTAS * c->num_sms), 1, 1);
   plan.sweep_smem = N == 16 ? SlabCfg<16>::SMEM : SlabCfg<8>::SMEM;
+  if (const char* e = getenv("TNQS_SWEEP_PAD_SMEM")) plan.sweep_smem += (size_t)atoi(e);      // experiment: shrink the L1 share of the SM
   plan.sweep_commit = (int)commit.size();
+  if (getenv("TNQS_DEBUG_QUEUE")) {
+    int occ = 0;
+    if (N == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bp_sweep<16>, QUEUE_THREADS, plan.sweep_smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bp_sweep<8>, QUEUE_THREADS, plan.sweep_smem);
+    fprintf(stderr, "[tnqs] sweep plan: %d chains, %d items, grid %u, %zu B shared memory, %d CTAs per SM\n", nch, plan.sweep_items,
+            plan.sweep_grid.x, plan.sweep_smem, occ);
+  }
   const size_t cnt[8] = {0, 0, 0, rd.size(), commit.size(), sd.size(), dc.size(), items.size()};
   bool same = reuse_mem && reuse->sweep && reuse->nchains == (size_t)nch && reuse->d_chains && reuse->d_chain_done;
   for (int i = 0; i < 8 && same; ++i) same = cnt[i] == reuse->cnt[i];
@@ -778,6 +789,10 @@ static bool build_sweep_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>&
     CU(cudaMemsetAsync(plan.d_qctr, 0, 8 * sizeof(int), c->stream));
     CU(cudaMemsetAsync(plan.d_slab_done, 0, (nch + 1) * sizeof(int), c->stream));
     CU(cudaMemsetAsync(plan.d_chain_done, 0, (nch + 1) * sizeof(int), c->stream));
+  }
+  if (const char* e = getenv("TNQS_SWEEP_TRACE")) if (e[0] == '1') {
+    plan.d_prof = (same && reuse->d_prof) ? reuse->d_prof : c->talloc<long long>(32);
+    if (!(same && reuse->d_prof)) CU(cudaMemsetAsync(plan.d_prof, 0, 32 * sizeof(long long), c->stream));
   }
   plan.nlaunch = 1 + (plan.sweep_commit ? 1 : 0);
   out = plan;
@@ -830,8 +845,11 @@ static void run_plan(tnqs_ctx* c, const Plan& p) {
   if (p.sweep) {
     SweepQueue Q; Q.items = p.d_items; Q.n = p.sweep_items; Q.counter = p.d_qctr; Q.slabs = p.d_slab; Q.closes = p.d_dclose;
     Q.chains = p.d_chains; Q.slab_done = p.d_slab_done; Q.chain_done = p.d_chain_done;
+    Q.prof = p.d_prof;
+    { const char* e = getenv("TNQS_SWEEP_ABLATE"); Q.ablate = e ? atoi(e) : 0; }
     Q.nchains = (int)p.nchains; Q.ahead = std::max(1, (int)((long long)p.sweep_grid.x * p.nchains / std::max(1, p.sweep_items)));
-    if (p.sweepN == 16) LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_sweep<16>, p.sweep_grid, QUEUE_THREADS, p.sweep_smem, Q);
+    if (p.sweepN == 16 && (Q.ablate || Q.prof)) LAUNCH(c, TNQS_KC_MODE_APPLY, (k_bp_sweep<16, true>), p.sweep_grid, QUEUE_THREADS, p.sweep_smem, Q);
+    else if (p.sweepN == 16) LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_sweep<16>, p.sweep_grid, QUEUE_THREADS, p.sweep_smem, Q);
     else LAUNCH(c, TNQS_KC_MODE_APPLY, k_bp_sweep<8>, p.sweep_grid, QUEUE_THREADS, p.sweep_smem, Q);
     if (p.sweep_commit) LAUNCH(c, TNQS_KC_BP_FINALIZE, k_msg_commit, p.sweep_commit, 128, 0, c->msg_cur, c->msg_stage, c->slot, p.d_commit, c->d_chi);
     return;

@@ -52,7 +52,13 @@ template <int N> struct SlabCfg {
 // is on the critical path of the 124 dependency levels (measured: 13.8 ms per sweep with 4-warp CTAs against 12.1).
 constexpr int SLAB_THREADS = 128;
 constexpr int SLAB_CTAS = 3;
-constexpr int QUEUE_THREADS = 256;
+#ifndef TNQS_CLOSE_QUAD
+#define TNQS_CLOSE_QUAD 1
+#endif
+#ifndef TNQS_QUEUE_THREADS
+#define TNQS_QUEUE_THREADS 256
+#endif
+constexpr int QUEUE_THREADS = TNQS_QUEUE_THREADS;
 constexpr int QUEUE_CTAS = 2;
 
 // One absorption phase P of F.  K ordering: lane (r, q) loads the whole complex element b = 4kk + q of its row (one
@@ -221,23 +227,39 @@ __device__ __forceinline__ bool close_dmma_item(const CloseDmmaDesc& d, int sub,
   constexpr int NSET = 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int r = lane >> 2, q = lane & 3;
-  const int s = q & 1, ih = q >> 1, pp = r & 1;
+  const int pp = r & 1;
   long long NF = N; for (int i = 1; i < d.F; ++i) NF *= N;
-  const long long groups = NF / 2;        // (i1 pair, i2, i3)
+  const long long groups = NF / 2;        // (i1 pair, i2, i3) x (s pair), or with TNQS_CLOSE_QUAD (s, i1 quad, i2, i3)
   const long long per = (groups + d.nsplit - 1) / d.nsplit;
   const long long g_begin = (long long)sub * per, g_end = min(groups, g_begin + per);
   // lane-constant parts of the addresses
+#if TNQS_CLOSE_QUAD
+  // a K-group = 4 consecutive values of the first absorbed index at one s: the four q lanes of a row read 64 contiguous bytes of
+  // X (8 lines per load instruction instead of 16); the two s halves of a line of T are asked for by consecutive groups
+  const cplx* xl = d.x + q;                                                            // + s NF + (8 mt + r) * 2 NF + sigma0
+  const cplx* tl = d.t + (long long)q * d.g[0] + (long long)(r >> 1) * d.gw;           // + s + 4 nt * gw + toff0
+#else
+  const int s = q & 1, ih = q >> 1;
   const cplx* xl = d.x + (long long)s * NF + ih;                 // + (8 mt + r) * 2 NF + sigma0
   const cplx* tl = d.t + s + (long long)ih * d.g[0] + (long long)(r >> 1) * d.gw;     // + 4 nt * gw + toff0
+#endif
   const long long g2 = d.F == 3 ? d.g[2] : 0;
   cplx a[NSET][MT], b[NSET][NT];
   auto load = [&](int set, long long g) {
     if (g < g_end) {
+#if TNQS_CLOSE_QUAD
+      const int sg = (int)(g & 1), j = (int)((g >> 1) % (N / 4));
+      const long long rest = (g >> 1) / (N / 4);
+      const int i2 = (int)(rest % N), i3 = (int)(rest / N);
+      const long long sigma0 = (long long)sg * NF + 4 * j + (long long)N * i2 + (long long)N * N * i3;
+      const long long toff0 = sg + 4 * j * d.g[0] + i2 * d.g[1] + i3 * g2;
+#else
       const int j = (int)(g % (N / 2));
       const long long rest = g / (N / 2);
       const int i2 = (int)(rest % N), i3 = (int)(rest / N);
       const long long sigma0 = 2 * j + (long long)N * i2 + (long long)N * N * i3;
       const long long toff0 = 2 * j * d.g[0] + i2 * d.g[1] + i3 * g2;
+#endif
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) a[set][mt] = __ldcg(xl + (long long)(8 * mt + r) * 2 * NF + sigma0);   // X: written by other CTAs, read through L2
 #pragma unroll
@@ -410,7 +432,20 @@ struct SweepQueue {
   int* slab_done;         // per chain; reset by the CTA that runs the chain's epilogue
   int* chain_done;        // per chain: epoch + 1 once its message is written
   int nchains, ahead;     // ahead: chains between an item and the one the same CTA is likely to draw next (L1 prefetch distance)
+  int ablate;             // TNQS_SWEEP_ABLATE (timing experiments only, results are wrong): 1 no dependency waits, 2 no closing arithmetic,
+                          // 4 no absorption arithmetic, 8 static round-robin item assignment instead of the atomic draw, 16 no epilogue
+  long long* prof;        // TNQS_SWEEP_TRACE=1: cycle totals per section of the item types (thread 0 of every CTA), else null
 };
+
+// Trace sections (SweepQueue::prof): absorb item [0] count, [2] producer wait, [8] the three phases, [9] publish;
+// closing item [16] count, [17] slab wait, [18] accumulation + reduction + epilogue, [19] next-item bookkeeping
+template <bool ON> struct SweepTraceT {
+  long long* p; long long t;
+  __device__ __forceinline__ SweepTraceT(long long* prof) : p(ON && threadIdx.x == 0 ? prof : nullptr), t(0) { if (ON && p) t = clock64(); }
+  __device__ __forceinline__ void mark(int slot) { if (ON && p) { const long long n = clock64(); atomicAdd((unsigned long long*)(p + slot), (unsigned long long)(n - t)); t = n; } }
+  __device__ __forceinline__ void count(int slot) { if (ON && p) atomicAdd((unsigned long long*)(p + slot), 1ull); }
+};
+typedef SweepTraceT<true> SweepTrace;
 
 // The whole CTA waits until chain_done[list[i]] == done_val for the (up to 4) chains of `list` (-1 = none).
 __device__ __forceinline__ void sweep_wait_chains(const SweepQueue& Q, const int* __restrict__ list, int done_val, int stat = 3) {
@@ -475,13 +510,17 @@ __device__ __forceinline__ void touch_l1(const void* p) {
   asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(tmp) : "l"(p));
 }
 
-template <int N>
+// DBG: the instantiation with the trace counters and the ablation switches (TNQS_SWEEP_TRACE / TNQS_SWEEP_ABLATE); the production
+// kernel carries none of it (the extra live values cost registers in a kernel that is compiled at its register limit)
+template <int N, bool DBG = false>
 __global__ void __launch_bounds__(QUEUE_THREADS, QUEUE_CTAS) k_bp_sweep(const SweepQueue Q) {
   extern __shared__ cplx dyn[];
   cplx* msm = dyn + SlabCfg<N>::SLAB3;
+  const int ablate = DBG ? Q.ablate : 0;
+  typedef SweepTraceT<DBG> Trace;
   __shared__ int s_item, s_epoch;
   const int tid = threadIdx.x;
-  if (tid == 0) { s_epoch = *(volatile int*)(Q.counter + 4); s_item = atomicAdd(Q.counter, 1); }
+  if (tid == 0) { s_epoch = *(volatile int*)(Q.counter + 4); s_item = (ablate & 8) ? (int)blockIdx.x : atomicAdd(Q.counter, 1); }
   __syncthreads();
   const int done_val = s_epoch + 1;
   for (;;) {
@@ -501,13 +540,17 @@ __global__ void __launch_bounds__(QUEUE_THREADS, QUEUE_CTAS) k_bp_sweep(const Sw
     }
     __syncthreads();                                 // everybody has read s_item
     if (e.x >= 0 && e.y >= 0) {
-      sweep_wait_chains(Q, Q.chains[e.x].dep, done_val);
+      Trace tr(Q.prof); tr.count(0);
+      if (!(ablate & 1)) sweep_wait_chains(Q, Q.chains[e.x].dep, done_val);
+      tr.mark(2);
       const SlabDesc d = Q.slabs[e.x];
-      absorb_slab_item<N, true>(d, e.y, dyn, msm);
+      if (!(ablate & 4)) absorb_slab_item<N, true>(d, e.y, dyn, msm);
       int nx = 0;
-      if (tid == 0) nx = atomicAdd(Q.counter, 1);                                       // next index: in flight across the barrier
+      if (tid == 0) nx = (ablate & 8) ? it + (int)gridDim.x : atomicAdd(Q.counter, 1);  // next index: in flight across the barrier
       __syncthreads();                               // the CTA's part of X ...
+      tr.mark(8);
       if (tid == 0) { __threadfence(); atomicAdd(Q.slab_done + e.x, 1); s_item = nx; } // ... is visible before the slab counter moves
+      tr.mark(9);
     } else if (e.x >= 0) {
       sweep_wait_chains(Q, Q.chains[e.x].dep, done_val);
       const SlabDesc a = Q.slabs[e.x];
@@ -516,12 +559,15 @@ __global__ void __launch_bounds__(QUEUE_THREADS, QUEUE_CTAS) k_bp_sweep(const Sw
       sweep_wait_chains(Q, Q.chains[e.x].war, done_val, 6);
       close_reduce_body(*d.epilogue, dyn, reinterpret_cast<double*>(dyn + N * N));
       __syncthreads();
-      if (tid == 0) { __threadfence(); *(volatile int*)(Q.chain_done + e.x) = done_val; s_item = atomicAdd(Q.counter, 1); }
+      if (tid == 0) { __threadfence(); *(volatile int*)(Q.chain_done + e.x) = done_val; s_item = (ablate & 8) ? it + (int)gridDim.x : atomicAdd(Q.counter, 1); }
     } else {
-      const CloseDmmaDesc d = Q.closes[ci];
+      CloseDmmaDesc d = Q.closes[ci];
+      if (ablate & 2) d.F = 0;                     // no K range: the accumulation loop is empty
+      if (ablate & 16) d.epilogue = nullptr;
+      Trace tr(Q.prof); tr.count(16);
       if (tid == 0) {
         const int need = Q.slabs[ci].nslabs;
-        if (*(volatile int*)(Q.slab_done + ci) < need) {
+        if (!(ablate & 1) && *(volatile int*)(Q.slab_done + ci) < need) {
           int spins = 0;
           while (*(volatile int*)(Q.slab_done + ci) < need) {
             __nanosleep(32);
@@ -536,13 +582,16 @@ __global__ void __launch_bounds__(QUEUE_THREADS, QUEUE_CTAS) k_bp_sweep(const Sw
         __threadfence();
       }
       __syncthreads();
-      auto hook = [&]() { sweep_wait_chains(Q, Q.chains[ci].war, done_val, 6); };
+      tr.mark(17);
+      auto hook = [&]() { if (!(ablate & 1)) sweep_wait_chains(Q, Q.chains[ci].war, done_val, 6); };
       const bool last = close_dmma_item<N>(d, e.y, reinterpret_cast<double*>(dyn), hook);
       if (last) __syncthreads();
+      tr.mark(18);
       if (tid == 0) {
         if (last) { __threadfence(); Q.slab_done[ci] = 0; *(volatile int*)(Q.chain_done + ci) = done_val; }
-        s_item = atomicAdd(Q.counter, 1);
+        s_item = (ablate & 8) ? it + (int)gridDim.x : atomicAdd(Q.counter, 1);
       }
+      tr.mark(19);
     }
     __syncthreads();                                 // shared memory and s_item are reused by the next item
   }

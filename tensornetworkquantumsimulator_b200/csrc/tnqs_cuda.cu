@@ -49,7 +49,14 @@ static void set_smem_attrs() {   // per device: called at every handle creation 
   cudaFuncSetAttribute(k_close_dmma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_bp_level<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_bp_level<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_bp_sweep<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute((k_bp_sweep<16, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  cudaFuncSetAttribute(k_bp_sweep<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  // NOT the maximal carve-out here: the sweep kernel needs the L1 that two 72 KB CTAs leave (measured: 11.6 ms per sweep with the
+  // default split, 14.3 ms with the L1 carved down to the minimum).  TNQS_SWEEP_CARVEOUT=<percent> overrides (experiments).
+  if (const char* e = getenv("TNQS_SWEEP_CARVEOUT")) {
+    cudaFuncSetAttribute(k_bp_sweep<16>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+    cudaFuncSetAttribute((k_bp_sweep<16, true>), cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+  }
   cudaFuncSetAttribute(k_bp_sweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_close_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -301,11 +308,7 @@ static void bp_cache_drop(tnqs_ctx* c) {
   for (void* p : pc->owned) c->dfree(p);
   delete pc; c->bp_cache = nullptr;
 }
-static int bp_level_split_cap() {
-  static int cap = 0;
-  if (!cap) { const char* e = getenv("TNQS_BP_SPLIT"); cap = e ? std::max(1, atoi(e)) : 8; }
-  return cap;
-}
+static int bp_level_split_cap() { const char* e = getenv("TNQS_BP_SPLIT"); return e ? std::max(1, atoi(e)) : 8; }      // read at plan-build time only
 static bool graphs_disabled() {
   static int d = -1;
   if (d < 0) { const char* e = getenv("TNQS_NO_GRAPH"); d = (e && e[0] == '1') ? 1 : 0; }
@@ -486,6 +489,14 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
         if (mean <= o.tolerance) break;
       }
     }
+  }
+  if (plan.sweep && plan.d_prof) {
+    long long t[32];
+    c->d2h_small(t, plan.d_prof, sizeof(t));
+    CU(cudaMemsetAsync(plan.d_prof, 0, sizeof(t), c->stream));
+    const double na = (double)std::max(1ll, t[0]), nc = (double)std::max(1ll, t[16]);
+    fprintf(stderr, "[tnqs trace] %lld absorb items, cycles each: producer wait %.0f, body %.0f, publish %.0f | %lld closing items: slab wait %.0f, body %.0f, tail %.0f\n",
+            t[0], t[2] / na, t[8] / na, t[9] / na, t[16], t[17] / nc, t[18] / nc, t[19] / nc);
   }
   if (plan.d_qctr) {
     int q[8] = {0, 0, 0, 0, 0, 0, 0, 0};

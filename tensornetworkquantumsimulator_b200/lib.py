@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtnqs_cuda.so")
+LIB_PATH = os.environ.get("TNQS_LIB_PATH") or os.path.join(_HERE, "libtnqs_cuda.so")      # the override selects another BUILD of the same
+                                                                                              # library (kernel experiments, tools/ab.py)
 
 # every symbol include/tnqs_cuda.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
