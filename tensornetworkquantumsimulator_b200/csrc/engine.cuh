@@ -244,6 +244,7 @@ struct Chain {
   const cplx* prev = nullptr; double* diff = nullptr; int bp_mode = 0, normalize = 0, hermitize = 0;
   int commit_k = -1;                 // BP: directed edge to commit at the end of the level
   int split_cap = 16;                // upper bound of the split-K factor of the closing (a property of the request, never of the batch)
+  int split_rows = 0;                // smallest K extent of one split (0: the default, split_rows())
 };
 
 struct LaunchRec { size_t off; int count; dim3 grid; size_t smem; bool dmma = false; int tpc = 1; };
@@ -393,7 +394,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         const Chain& ch = chains[i];
         int n = ch.close_leg < 0 ? c->d[ch.v] : c->chi[c->inc[ch.v][ch.close_leg]];
         long long rows = c->site_n[ch.v] / n;
-        int ns = (int)std::min<long long>(ch.split_cap, std::max<long long>(1, rows / split_rows()));
+        int ns = (int)std::min<long long>(ch.split_cap, std::max<long long>(1, rows / (ch.split_rows ? ch.split_rows : split_rows())));
         mem[L][i].nsplit = std::max(1, ns);
         mem[L][i].partial_elems = (size_t)mem[L][i].nsplit * n * n;
         part += mem[L][i].partial_elems;
@@ -704,7 +705,7 @@ static bool build_sweep_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>&
     const Chain& ch = *chains[i];
     if (!small[i]) {
       const long long rows = c->site_n[ch.v] / N;
-      nsplit[i] = (int)std::max<long long>(1, std::min<long long>(ch.split_cap, rows / split_rows()));
+      nsplit[i] = (int)std::max<long long>(1, std::min<long long>(ch.split_cap, rows / (ch.split_rows ? ch.split_rows : split_rows())));
     }
     max_split = std::max(max_split, nsplit[i]);
   }
