@@ -167,7 +167,21 @@ struct tnqs_ctx {
       CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
     }
   }
-  void hstage_destroy() { if (hstage) cudaFreeHost(hstage); hstage = nullptr; hstage_size = 0; hstage_off = 0; if (hret) cudaFreeHost(hret); hret = nullptr; }
+  void hstage_destroy() { if (hstage) cudaFreeHost(hstage); hstage = nullptr; hstage_size = 0; hstage_off = 0; if (hret) cudaFreeHost(hret); hret = nullptr;
+                          if (hside) cudaFreeHost(hside); hside = nullptr; hside_size = 0; }
+  // Second pinned return page, grown on demand: results that come back on the copy stream (gate ranks) or in one batch at the end
+  // of a call (truncation errors, singular values).  Valid until the next request.
+  char* hside = nullptr; size_t hside_size = 0;
+  void* hret_side(size_t bytes) {
+    if (bytes > hside_size) {
+      if (hside) cudaFreeHost(hside);
+      hside = nullptr; hside_size = 0;
+      const size_t want = std::max<size_t>(bytes, (size_t)64 << 10);
+      if (cudaHostAlloc((void**)&hside, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); hside = nullptr; throw TnqsError(TNQS_ERR_OOM, "pinned host page for device results"); }
+      hside_size = want;
+    }
+    return hside;
+  }
   // Small device -> host reads (loop state, status word, counters) land in a pinned page and the call then waits on the
   // stream: a copy into pageable memory blocks inside the driver, which serialises every other thread of the process - fatal
   // when those threads drive other handles whose kernels this handle's kernels wait for (device-side halo barrier).

@@ -663,6 +663,12 @@ struct GateBatch {
     for (int l : J.outer) if (c->chi[c->inc[J.v][l]] != N) return false;
     return true;
   }
+  // CholeskyQR2 runs optimistically for every tall matrix; its per-matrix flags (a pivot below the tolerance) are read as late as
+  // possible - after the host has built the next stage's descriptors, while the device finishes the QR kernels - and the flagged
+  // matrices are then redone by Householder TSQR
+  std::vector<int> chol_list; std::vector<cplx*> chol_Qb, chol_Rinv; int* d_chol_flag = nullptr; bool chol_pending = false;
+  void householder_qr(const std::vector<int>& list);
+  void resolve_chol_flags();
   void stage1(int n_, const int32_t* es_, const int32_t* flips, const double* gates, const tnqs_apply_opts& o_, const int32_t* remote);
   void stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, double* svals_out);
 };
@@ -719,6 +725,78 @@ void GateBatch::absorb_outer(bool inverse) {   // forward: on A (psi~); inverse:
     }
     launch_mode_apply(c, TNQS_KC_MODE_APPLY, ma);
   }
+}
+
+void GateBatch::householder_qr(const std::vector<int>& list) {
+    if (list.empty()) return;
+    for (int j : list) jobs[j].Q = jobs[j].A;
+    std::vector<std::vector<QrLevel>> trees(NJ);
+    size_t maxlev = 0;
+    for (int j : list) {
+      SiteJob& J = jobs[j];
+      const long long hmax = 2 * J.nc;      // small blocks: many resident CTAs hide the latency of the column-by-column sweep
+      QrLevel lv; lv.base = J.A; lv.ld = J.Po; lv.rows = J.Po;
+      while (true) {
+        long long nb = lv.rows <= hmax ? 1 : (lv.rows + hmax - 1) / hmax;
+        lv.blk_begin.clear();
+        for (long long b = 0; b <= nb; ++b) lv.blk_begin.push_back(lv.rows * b / nb);
+        trees[j].push_back(lv);
+        if (nb == 1) break;
+        QrLevel nx; nx.rows = nb * J.nc; nx.ld = nx.rows; nx.base = c->talloc<cplx>((size_t)nx.rows * J.nc);
+        lv = nx;
+      }
+      maxlev = std::max(maxlev, trees[j].size());
+    }
+    // upward sweep: factor every block, R factors stack into the next level
+    for (size_t l = 0; l < maxlev; ++l) {
+      std::vector<QrDesc> qd; size_t smem = 0;
+      for (int j : list) {
+        if (l >= trees[j].size()) continue;
+        SiteJob& J = jobs[j]; QrLevel& lv = trees[j][l];
+        bool top = l + 1 == trees[j].size();
+        size_t nb = lv.blk_begin.size() - 1;
+        for (size_t b = 0; b < nb; ++b) {
+          QrDesc d; d.a = lv.base + lv.blk_begin[b]; d.lda = lv.ld; d.h = (int)(lv.blk_begin[b + 1] - lv.blk_begin[b]); d.nc = J.nc;
+          if (top) { d.rout = J.Rbuf; d.ldr = std::min(d.h, J.nc); }
+          else { d.rout = trees[j][l + 1].base + (long long)b * J.nc; d.ldr = (int)trees[j][l + 1].ld; }
+          qd.push_back(d);
+          smem = std::max(smem, ((size_t)d.h * d.nc + d.nc + 2) * sizeof(cplx));
+        }
+      }
+      REQUIRE(smem <= 200 * 1024, TNQS_ERR_UNSUPPORTED, "QR block does not fit shared memory");
+      QrDesc* dqd = c->upload(qd);
+      LAUNCH(c, TNQS_KC_QR, k_house_qr, (unsigned)qd.size(), 256, smem, dqd);
+    }
+    // downward sweep: Q_block <- Q_block * (its nc x nc slice of the parent's explicit Q)
+    for (int l = (int)maxlev - 2; l >= 0; --l) {
+      std::vector<ModeApplyDesc> ma; long long maxtiles = 1;
+      for (int j : list) {
+        if ((size_t)l + 1 >= trees[j].size()) continue;
+        SiteJob& J = jobs[j]; QrLevel& lv = trees[j][l]; QrLevel& up = trees[j][l + 1];
+        size_t nb = lv.blk_begin.size() - 1;
+        for (size_t b = 0; b < nb; ++b) {
+          ModeApplyDesc d; d.in = lv.base + lv.blk_begin[b]; d.out = const_cast<cplx*>(d.in);
+          d.m = up.base + (long long)b * J.nc; d.ldm = (int)up.ld; d.flags = 0;
+          d.L = (int)(lv.blk_begin[b + 1] - lv.blk_begin[b]); d.n = J.nc; d.np = J.nc; d.R = 1;
+          d.in_sb = lv.ld; d.in_sr = 0; d.out_sb = lv.ld; d.out_sr = 0;
+          ma.push_back(d);
+          maxtiles = std::max(maxtiles, ((long long)d.L + MA_BM - 1) / MA_BM);
+        }
+      }
+      (void)maxtiles;
+      launch_mode_apply(c, TNQS_KC_QR, ma);
+    }
+  }
+
+void GateBatch::resolve_chol_flags() {
+  if (!chol_pending) return;
+  chol_pending = false;
+  const int nj = (int)chol_list.size();
+  std::vector<int> flags(nj);
+  c->d2h_small(flags.data(), d_chol_flag, nj * sizeof(int));
+  std::vector<int> redo;
+  for (int i = 0; i < nj; ++i) if (flags[i]) { redo.push_back(chol_list[i]); jobs[chol_list[i]].colfix = nullptr; }
+  householder_qr(redo);                       // overwrites Q (= A, in place) and Rbuf of the flagged matrices
 }
 
 void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const double* gates, const tnqs_apply_opts& o_, const int32_t* remote) {
@@ -807,68 +885,8 @@ void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const d
   // Tall, well-conditioned matrices: CholeskyQR2 on the tensor cores (Gram -> Cholesky -> Q = A R^-1, twice; as
   // accurate as Householder while cond(A) < ~1e6, which the Cholesky pivots check on the device).  Everything else
   // (short, wide, rank-deficient or ill-conditioned - the norm while bonds are still growing): Householder TSQR.
-  auto householder_qr = [&](const std::vector<int>& list) {
-    if (list.empty()) return;
-    for (int j : list) jobs[j].Q = jobs[j].A;
-    std::vector<std::vector<QrLevel>> trees(NJ);
-    size_t maxlev = 0;
-    for (int j : list) {
-      SiteJob& J = jobs[j];
-      const long long hmax = 2 * J.nc;      // small blocks: many resident CTAs hide the latency of the column-by-column sweep
-      QrLevel lv; lv.base = J.A; lv.ld = J.Po; lv.rows = J.Po;
-      while (true) {
-        long long nb = lv.rows <= hmax ? 1 : (lv.rows + hmax - 1) / hmax;
-        lv.blk_begin.clear();
-        for (long long b = 0; b <= nb; ++b) lv.blk_begin.push_back(lv.rows * b / nb);
-        trees[j].push_back(lv);
-        if (nb == 1) break;
-        QrLevel nx; nx.rows = nb * J.nc; nx.ld = nx.rows; nx.base = c->talloc<cplx>((size_t)nx.rows * J.nc);
-        lv = nx;
-      }
-      maxlev = std::max(maxlev, trees[j].size());
-    }
-    // upward sweep: factor every block, R factors stack into the next level
-    for (size_t l = 0; l < maxlev; ++l) {
-      std::vector<QrDesc> qd; size_t smem = 0;
-      for (int j : list) {
-        if (l >= trees[j].size()) continue;
-        SiteJob& J = jobs[j]; QrLevel& lv = trees[j][l];
-        bool top = l + 1 == trees[j].size();
-        size_t nb = lv.blk_begin.size() - 1;
-        for (size_t b = 0; b < nb; ++b) {
-          QrDesc d; d.a = lv.base + lv.blk_begin[b]; d.lda = lv.ld; d.h = (int)(lv.blk_begin[b + 1] - lv.blk_begin[b]); d.nc = J.nc;
-          if (top) { d.rout = J.Rbuf; d.ldr = std::min(d.h, J.nc); }
-          else { d.rout = trees[j][l + 1].base + (long long)b * J.nc; d.ldr = (int)trees[j][l + 1].ld; }
-          qd.push_back(d);
-          smem = std::max(smem, ((size_t)d.h * d.nc + d.nc + 2) * sizeof(cplx));
-        }
-      }
-      REQUIRE(smem <= 200 * 1024, TNQS_ERR_UNSUPPORTED, "QR block does not fit shared memory");
-      QrDesc* dqd = c->upload(qd);
-      LAUNCH(c, TNQS_KC_QR, k_house_qr, (unsigned)qd.size(), 256, smem, dqd);
-    }
-    // downward sweep: Q_block <- Q_block * (its nc x nc slice of the parent's explicit Q)
-    for (int l = (int)maxlev - 2; l >= 0; --l) {
-      std::vector<ModeApplyDesc> ma; long long maxtiles = 1;
-      for (int j : list) {
-        if ((size_t)l + 1 >= trees[j].size()) continue;
-        SiteJob& J = jobs[j]; QrLevel& lv = trees[j][l]; QrLevel& up = trees[j][l + 1];
-        size_t nb = lv.blk_begin.size() - 1;
-        for (size_t b = 0; b < nb; ++b) {
-          ModeApplyDesc d; d.in = lv.base + lv.blk_begin[b]; d.out = const_cast<cplx*>(d.in);
-          d.m = up.base + (long long)b * J.nc; d.ldm = (int)up.ld; d.flags = 0;
-          d.L = (int)(lv.blk_begin[b + 1] - lv.blk_begin[b]); d.n = J.nc; d.np = J.nc; d.R = 1;
-          d.in_sb = lv.ld; d.in_sr = 0; d.out_sb = lv.ld; d.out_sr = 0;
-          ma.push_back(d);
-          maxtiles = std::max(maxtiles, ((long long)d.L + MA_BM - 1) / MA_BM);
-        }
-      }
-      (void)maxtiles;
-      launch_mode_apply(c, TNQS_KC_QR, ma);
-    }
-  };
   {
-    std::vector<int> chol_list, house_list;
+    std::vector<int> house_list;
     static int no_chol = -1;
     if (no_chol < 0) { const char* e = getenv("TNQS_NO_CHOLQR"); no_chol = (e && e[0] == '1') ? 1 : 0; }
     for (int j : LJ) {
@@ -913,14 +931,11 @@ void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const d
         LAUNCH(c, TNQS_KC_QR, k_chol_inv, nj, 64, 2 * (size_t)maxn * maxn * sizeof(cplx), dcd);
         if (pass == 0) launch_mode_apply(c, TNQS_KC_QR, ma);        // Q1 = A R1^-1; the second factor R2^-1 stays pending (colfix)
       }
-      std::vector<int> flags(nj);
-      c->d2h_small(flags.data(), d_flag, nj * sizeof(int));
-      for (int i = 0; i < nj; ++i) {
-        if (flags[i]) house_list.push_back(chol_list[i]);
-        else { jobs[chol_list[i]].Q = Qb[i]; jobs[chol_list[i]].colfix = Rinv[i]; }
-      }
+      for (int i = 0; i < nj; ++i) { jobs[chol_list[i]].Q = Qb[i]; jobs[chol_list[i]].colfix = Rinv[i]; }
+      d_chol_flag = d_flag; chol_pending = true;
     }
     householder_qr(house_list);
+    if (!cut.empty()) resolve_chol_flags();      // the R factors of cut-crossing gates leave the device at the end of this stage
   }
 
   for (int j : LJ) { dbg_norm(c, "Q", j, jobs[j].Q, (size_t)jobs[j].Po * jobs[j].q); dbg_norm(c, "R", j, jobs[j].Rbuf, (size_t)jobs[j].q * jobs[j].nc); }
@@ -992,6 +1007,7 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
     c->h2d(d_gates, hg.data(), hg.size() * sizeof(cplx));
   }
   (void)any_global;
+  resolve_chol_flags();        // the only host read between the stages; by now the device has (nearly) drained the QR kernels
   {
     ThetaDesc* dtd = c->upload(td);
     LAUNCH(c, TNQS_KC_SVD, k_theta, n, 256, 0, dtd);
@@ -1002,15 +1018,32 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
     LAUNCH(c, TNQS_KC_SVD, k_svd_trunc, n, threads, smem, dsv, c->d_status, svd_smem_wv);
   }
   for (int i = 0; i < n; ++i) dbg_norm(c, "theta", i, td[i].theta, (size_t)sv[i].m * sv[i].n);
+  // The kept ranks decide every shape from here on, so the host has to see them - but step 7 does not depend on them: the ranks
+  // and the status word travel to a pinned page on the copy stream as soon as the SVD is done, while the main stream already
+  // runs the inverse absorption; the host builds the remaining descriptors behind that kernel instead of an idle device.
   std::vector<int> ranks(n);
-  c->d2h_small(ranks.data(), d_rank, n * sizeof(int));
-  int st = c->read_status();
+  int st = 0;
+  {
+    if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    int* hr = (int*)c->hret_side((size_t)(n + 1) * sizeof(int));
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, ev, 0));
+    cudaEventDestroy(ev);
+    CU(cudaMemcpyAsync(hr, d_rank, n * sizeof(int), cudaMemcpyDeviceToHost, c->copy_stream));
+    CU(cudaMemcpyAsync(hr + n, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->copy_stream));
+    // ---- 7. Q <- Q * dag(M^-1/2) on the outer legs (simple_update.jl:55-56) ----
+    for (int j = 0; j < NJ; ++j) ncols[j] = jobs[j].q;
+    absorb_outer(true);
+    CU(cudaStreamSynchronize(c->copy_stream));
+    memcpy(ranks.data(), hr, n * sizeof(int));
+    st = hr[n];
+    if (st) { int z = 0; c->h2d(c->d_status, &z, sizeof(int)); }
+  }
   if (st & ST_NEG_EIG) throw TnqsError(TNQS_ERR_NEGATIVE_EIGENVALUE, "message eigenvalue < -10 eps in simple update");
   if (st & ST_NO_CONV) throw TnqsError(TNQS_ERR_SVD_NO_CONVERGENCE, "Jacobi eigen/SVD iteration did not converge");
   if (st & ST_RANK_CAP) throw TnqsError(TNQS_ERR_SHAPE, "kept rank exceeds chi_cap (raise chi_cap or set maxdim)");
-  // ---- 7. Q <- Q * dag(M^-1/2) on the outer legs (simple_update.jl:55-56) ----
-  for (int j = 0; j < NJ; ++j) ncols[j] = jobs[j].q;
-  absorb_outer(true);
   // ---- 8. T' = Q R' (simple_update.jl:57), normalise, back to the canonical layout ----
   std::vector<cplx*> Tm(NJ), newsite(NJ);
   {
@@ -1096,9 +1129,14 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
   }
 
   if (ranks_out) for (int i = 0; i < n; ++i) ranks_out[i] = ranks[i];
-  if (err_out) c->d2h_small(err_out, d_err, n * sizeof(double));
-  if (svals_out) c->d2h_small(svals_out, d_sv, (size_t)n * cap * sizeof(double));
+  // truncation errors and singular values: one pinned staging copy each, one synchronisation for everything
+  const size_t eb = err_out ? n * sizeof(double) : 0, sb = svals_out ? (size_t)n * cap * sizeof(double) : 0;
+  char* hb = (eb + sb) ? (char*)c->hret_side(eb + sb) : nullptr;
+  if (eb) CU(cudaMemcpyAsync(hb, d_err, eb, cudaMemcpyDeviceToHost, c->stream));
+  if (sb) CU(cudaMemcpyAsync(hb + eb, d_sv, sb, cudaMemcpyDeviceToHost, c->stream));
   c->sync();
+  if (eb) memcpy(err_out, hb, eb);
+  if (sb) memcpy(svals_out, hb + eb, sb);
 }
 
 static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_t* flips, const double* gates,
