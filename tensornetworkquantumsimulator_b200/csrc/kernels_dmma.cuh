@@ -52,6 +52,9 @@ template <int N> struct SlabCfg {
 // is on the critical path of the 124 dependency levels (measured: 13.8 ms per sweep with 4-warp CTAs against 12.1).
 constexpr int SLAB_THREADS = 128;
 constexpr int SLAB_CTAS = 3;
+#ifndef TNQS_CLOSE_NSET
+#define TNQS_CLOSE_NSET 3      // K-groups in flight per warp of the closing contraction
+#endif
 #ifndef TNQS_CLOSE_QUAD
 #define TNQS_CLOSE_QUAD 1
 #endif
@@ -224,7 +227,7 @@ template <int N, typename Hook = NoHook>
 __device__ __forceinline__ bool close_dmma_item(const CloseDmmaDesc& d, int sub, double* red, Hook pre_epilogue = Hook()) {
   constexpr int MT = N / 8;               // m-tiles of 8 complex rows w
   constexpr int NT = N / 4;               // n-tiles of 8 real columns = 4 w' x (re, im)
-  constexpr int NSET = 3;
+  constexpr int NSET = TNQS_CLOSE_NSET;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int r = lane >> 2, q = lane & 3;
   const int pp = r & 1;

@@ -407,6 +407,24 @@ def circuit_schedule(g: Graph, circuit: Sequence[tuple], update_cache: bool = Tr
     return out
 
 
+def _pack_gate_arrays(gates: Sequence[np.ndarray]) -> np.ndarray:
+    """Gate arrays o[s1', s2', s1, s2] (or o[s', s]) -> one flat float64 buffer, each gate column-major (the layout of the C-ABI).
+    Vectorised: a colour class is typically one gate repeated, or gates of one shape."""
+    n = len(gates)
+    if n == 0:
+        return np.zeros(2, dtype=np.float64)
+    first = gates[0]
+    if all(a is first for a in gates):
+        flat = np.asarray(first, dtype=np.complex128).ravel(order="F")
+        return np.tile(flat, n).view(np.float64)
+    shapes = {np.shape(a) for a in gates}
+    if len(shapes) == 1:
+        arr = np.asarray(gates, dtype=np.complex128)                       # [n, ...]
+        arr = arr.transpose((0,) + tuple(range(arr.ndim - 1, 0, -1)))      # reversed axes per gate = column-major order when flattened C-style
+        return np.ascontiguousarray(arr).reshape(-1).view(np.float64)
+    return np.concatenate([np.asarray(a, dtype=np.complex128).ravel(order="F") for a in gates]).view(np.float64)
+
+
 def apply_2site_batch(bpc: BeliefPropagationCache, edges: Sequence[int], gates: Sequence[np.ndarray], flip: Optional[Sequence[int]] = None,
                       apply_kwargs: Optional[dict] = None):
     """In place: one vertex-disjoint batch of two-site gates (apply_gate!, src/Apply/apply_gates.jl:95-122).
@@ -414,7 +432,7 @@ def apply_2site_batch(bpc: BeliefPropagationCache, edges: Sequence[int], gates: 
     n = len(edges)
     es = i32(edges)
     fl = i32(flip if flip is not None else [0] * n)
-    data = np.concatenate([np.asarray(a, dtype=np.complex128).ravel(order="F") for a in gates]).view(np.float64)
+    data = _pack_gate_arrays(gates)
     ranks = np.zeros(n, dtype=np.int32)
     errs = np.zeros(n, dtype=np.float64)
     sv = np.zeros((n, bpc.psi.chi_cap), dtype=np.float64)
@@ -431,7 +449,7 @@ def apply_2site_begin(bpc: BeliefPropagationCache, edges: Sequence[int], gates: 
     n = len(edges)
     es, fl = i32(edges), i32(flip if flip is not None else [0] * n)
     rm = i32(remote if remote is not None else [0] * n)
-    data = np.concatenate([np.asarray(a, dtype=np.complex128).ravel(order="F") for a in gates]).view(np.float64)
+    data = _pack_gate_arrays(gates)
     aopts = _apply_opts(apply_kwargs)
     send, ncut, slot = C.c_void_p(), C.c_int64(0), C.c_int64(0)
     check(bpc.psi._h.ptr, _lib.load().tnqs_apply_2site_begin(bpc.psi._h.ptr, n, ptr_i32(es), ptr_i32(fl), ptr_f64(data), C.byref(aopts),
@@ -451,7 +469,7 @@ def apply_2site_end(bpc: BeliefPropagationCache, n: int, recv_ptr):
 def apply_1site_batch(x, vertices: Sequence[int], gates: Sequence[np.ndarray], normalize_tensors: bool = True) -> None:
     psi = network(x)
     vs = i32(vertices)
-    data = np.concatenate([np.asarray(a, dtype=np.complex128).ravel(order="F") for a in gates]).view(np.float64)
+    data = _pack_gate_arrays(gates)
     check(psi._h.ptr, _lib.load().tnqs_apply_1site(psi._h.ptr, len(vs), ptr_i32(vs), ptr_f64(data), int(normalize_tensors)))
 
 
