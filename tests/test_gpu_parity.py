@@ -1008,3 +1008,45 @@ def test_bilinear_form_outlives_its_cache_and_checks_shapes(E):
     gc.collect()
     plain = E.update(E.BeliefPropagationCache(ket, _share=True), maxiter=1, edge_sequence=seq, inplace=True)
     assert np.isfinite(E.partitionfunction(plain))
+
+
+def test_config_c1_full_size(E):
+    # BASELINE config C1 as the README runs it (README.md:40-66): 5x5 grid, J = 1, hx = 2.5, hz = 0.2, dt = 0.01, 50 Trotter layers in
+    # ONE apply_gates call (one lazy-refresh schedule over all 5750 gates), maxdim = 10, cutoff = 1e-10, then <Z> at (2, 2) by BP
+    g = G.named_grid((5, 5))
+    layer = ising_layer(g, dt=0.01, hx=2.5, hz=0.2, J=1.0, groups=G.grid_edge_color(g))
+    circuit = layer * 50
+    kw = dict(maxdim=10, cutoff=1e-10, normalize_tensors=True)
+    io, ie = {}, {}
+    psi_o, errs_o = O.apply_gates(circuit, O.tensornetworkstate(lambda v: "↑", g), apply_kwargs=kw, info=io)
+    psi_e, errs_e = E.apply_gates(circuit, E.tensornetworkstate(lambda v: "↑", g, chi_cap=10), apply_kwargs=kw, info=ie)
+    assert ie["refreshes"] == io["refreshes"]
+    assert list(psi_e.bond_dims()) == list(psi_o.bond_dims())                      # truncation ranks exact
+    assert np.allclose(errs_e, errs_o, rtol=1e-6, atol=1e-13)
+    for obs in [("Z", [(2, 2)]), ("Z", [(1, 1)]), ("ZZ", [(2, 2), (2, 3)]), ("X", [(3, 3)])]:
+        assert abs(E.expect(psi_e, obs, alg="bp") - O.expect_tns(psi_o, obs)) < EXP_TOL
+
+
+def test_config_c3_full_size_eagle(E):
+    # BASELINE config C3 at full size (examples/heavyhexIsing_dynamics.jl:15-29): 127-qubit Eagle heavy-hex, kicked Ising, 20 steps of
+    # [Rx(0.4) on all, Rzz(pi/2) in 3 colour classes], maxdim = 32, cutoff = 1e-12, <Z> on all 127 sites after every 5th step.
+    # Bonds grow 1 -> 32 (ragged dimensions, Householder / CholeskyQR2 mix, theta' up to 128 x 128) and saturate around step 7.
+    g = G.eagle_heavy_hex()
+    groups = G.edge_color(g)
+    layer = [("Rx", [g.names[v]], 0.4) for v in range(g.nv)]
+    for grp in groups:
+        layer += [("Rzz", [g.names[int(g.esrc[e])], g.names[int(g.edst[e])]], math.pi / 2) for e in grp]
+    kw = dict(maxdim=32, cutoff=1e-12, normalize_tensors=True)
+    psi_o = O.tensornetworkstate(lambda v: "↑", g)
+    psi_e = E.tensornetworkstate(lambda v: "↑", g, chi_cap=32)
+    obs = [("Z", [g.names[v]]) for v in range(g.nv)]
+    for step in range(20):
+        psi_o, errs_o = O.apply_gates(layer, psi_o, apply_kwargs=kw)
+        psi_e, errs_e = E.apply_gates(layer, psi_e, apply_kwargs=kw)
+        assert list(psi_e.bond_dims()) == list(psi_o.bond_dims()), f"bond dimensions after step {step + 1}"
+        assert np.allclose(errs_e, errs_o, rtol=1e-6, atol=1e-12), f"truncation errors of step {step + 1}"
+        if (step + 1) % 5 == 0:
+            want = np.array(O.expect_tns(psi_o, obs))
+            got = np.array(E.expect(psi_e, obs))
+            assert np.max(np.abs(got - want)) < EXP_TOL, f"<Z> after step {step + 1}"
+    assert psi_e.maxvirtualdim() == 32
