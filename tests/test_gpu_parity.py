@@ -746,6 +746,84 @@ def test_full_size_c2_properties(E):
     assert all(abs(z.imag) < 1e-10 and abs(z.real) <= 1 + 1e-10 for z in zs)
 
 
+def test_full_size_c4_properties(E):
+    # BASELINE config C4 at full size (examples/3dIsing_dynamics.jl:8-28 scaled to 8x8x8, open boundaries: 512 sites of coordination
+    # up to 6, 1344 edges in 6 colour classes, chi = 8: 8 MiB per interior site, 3.2 GiB in all), BP run to tolerance 1e-12:
+    # size-independent properties instead of an oracle run (one CPU sweep of this state is 0.5 TFLOP)
+    g = G.named_grid((8, 8, 8))
+    groups = G.grid_edge_color(g)
+    assert g.nv == 512 and g.ne == 1344 and len(groups) == 6 and max(g.degree(v) for v in range(g.nv)) == 6
+    psi = E.random_tensornetworkstate(g, bond_dimension=8, seed=2)
+    bpc = E.BeliefPropagationCache(psi, _share=True)
+    seq = G.forest_cover_edge_sequence(g)
+    info = {}
+    E.update(bpc, edge_sequence=seq, inplace=True, maxiter=100, tolerance=1e-12, info=info)
+    assert info["iters"] < 100 and info["mean_diff"] <= 1e-12
+    k = 2 * g.edge_of[(g.v((4, 4, 4)), g.v((4, 4, 5)))]
+    m0 = E.message(bpc, k)
+    E.update(bpc, edge_sequence=seq, inplace=True, maxiter=1, tolerance=0.0, info=info)            # idempotence at the fixed point
+    assert info["mean_diff"] < 1e-11 and rel(E.message(bpc, k), m0) < 1e-5
+    w = np.linalg.eigvalsh(m0)
+    assert np.allclose(m0, m0.conj().T, atol=1e-12) and w.min() > -1e-12 and abs(m0.sum() - 1) < 1e-12
+    E.rescale(bpc, inplace=True)
+    assert np.allclose(E.vertex_scalars(bpc), 1.0, atol=1e-9) and np.allclose(E.edge_scalars(bpc), 1.0, atol=1e-9)
+    c = (4, 4, 4)
+    z_ref = E.expect(bpc, ("Z", [c]))
+    bj = bpc.copy()
+    E.update(bj, edge_sequence=np.arange(2 * g.ne), inplace=True, maxiter=200, tolerance=1e-14, mode="jacobi")
+    assert abs(E.expect(bj, ("Z", [c])) - z_ref) < 1e-6                                             # same fixed point in both orders
+    # linearity of the vertex scalar in |T_v|^2 (a scalar multiple of one site tensor)
+    vs0 = E.vertex_scalars(bpc)
+    v = g.v(c)
+    t = bpc.psi[v]
+    bpc.psi.set_site(v, 3.0 * t)
+    assert abs(E.vertex_scalars(bpc)[v] / vs0[v] - 9.0) < 1e-10
+    bpc.psi.set_site(v, t)
+    # one colour class of Rxx with maxdim = chi (QR of 32768 x 16 matrices, 32 x 32 theta'): reproducible bit for bit, unit-norm
+    # singular values that become the bond messages, unit-norm site tensors
+    rxx = gates.gate_array(("Rxx", [0, 1], 0.4))
+    kw = dict(maxdim=8, cutoff=1e-10, normalize_tensors=True)
+    b2 = bpc.copy()
+    r1, e1, s1 = E.apply_2site_batch(bpc, groups[0], [rxx] * len(groups[0]), apply_kwargs=kw)
+    r2, e2, s2 = E.apply_2site_batch(b2, groups[0], [rxx] * len(groups[0]), apply_kwargs=kw)
+    assert np.array_equal(r1, r2) and np.array_equal(e1, e2) and np.array_equal(s1, s2)
+    assert r1.max() <= 8 and r1.min() >= 1 and e1.min() >= 0 and e1.max() < 1
+    assert np.allclose(np.sum(s1 ** 2, axis=1), 1.0, atol=1e-12) and np.all(np.diff(s1, axis=1) <= 1e-15)
+    e = groups[0][5]
+    assert np.allclose(np.diag(E.message(bpc, 2 * e)).real, s1[5, :r1[5]], atol=1e-14)
+    for u in (int(g.esrc[e]), int(g.edst[e])):
+        assert abs(np.linalg.norm(bpc.psi[u]) - 1.0) < 1e-12
+
+
+def test_c5_strip_chi32_properties(E):
+    # BASELINE config C5 is a 128x128 grid at chi = 32 (497 GiB, >= 4 GPUs); one 16x16 strip of it (7.3 GiB) exercises the same
+    # kernels on one GPU: chi = 32 message updates (generic tensor-core leg / closing kernels, chunked levels), JACOBI sweeps as the
+    # partitioned runs use them, 128 x 128 theta' with the Jacobi iteration in global memory
+    g = G.named_grid((16, 16))
+    groups = G.grid_edge_color(g)
+    psi = E.random_tensornetworkstate(g, bond_dimension=32, seed=3)
+    bpc = E.BeliefPropagationCache(psi, _share=True)
+    info = {}
+    E.update(bpc, edge_sequence=np.arange(2 * g.ne), inplace=True, maxiter=60, tolerance=1e-10, mode="jacobi", info=info)
+    assert info["iters"] < 60 and info["mean_diff"] <= 1e-10
+    E.rescale(bpc, inplace=True)
+    assert np.allclose(E.vertex_scalars(bpc), 1.0, atol=1e-9) and np.allclose(E.edge_scalars(bpc), 1.0, atol=1e-9)
+    z_j = E.expect(bpc, ("Z", [(8, 8)]))
+    br = bpc.copy()
+    E.update(br, inplace=True, maxiter=25, tolerance=1e-12)                                          # sequential order from the Jacobi fixed point
+    assert abs(E.expect(br, ("Z", [(8, 8)])) - z_j) < 1e-6
+    rzz = gates.gate_array(("Rzz", [0, 1], 0.25))
+    kw = dict(maxdim=32, cutoff=1e-10, normalize_tensors=True)
+    grp = groups[1][:24]
+    r1, e1, s1 = E.apply_2site_batch(bpc, grp, [rzz] * len(grp), apply_kwargs=kw)
+    assert r1.max() <= 32 and r1.min() >= 1 and e1.min() >= 0 and e1.max() < 1
+    assert np.allclose(np.sum(s1 ** 2, axis=1), 1.0, atol=1e-12) and np.all(np.diff(s1, axis=1) <= 1e-15)
+    e = grp[3]
+    assert np.allclose(np.diag(E.message(bpc, 2 * e)).real, s1[3, :r1[3]], atol=1e-14)
+    for u in (int(g.esrc[e]), int(g.edst[e])):
+        assert abs(np.linalg.norm(bpc.psi[u]) - 1.0) < 1e-12
+
+
 def _oracle_jacobi(psi_o, sweeps):
     bo = O.BeliefPropagationCache(psi_o)
     for _ in range(sweeps):                 # Jacobi: every message from the previous sweep's values
