@@ -383,12 +383,14 @@ def run_distributed(args, torch, dist, rank, world, local):
         "gates": {"metric": "two_site_gate_applications_per_sec", "value": gates2 / gate_s, "unit": "gates/s"},
         "bp": {"sweeps_per_step": mx[6].item() / args.steps, "approx_tflops": msg / bp_s * fm / 1e12, "halo_bytes_per_step": halo / args.steps},
         "phase_ms_per_step": {"bp": 1e3 * bp_s / args.steps, "two_site_gates": 1e3 * gate_s / args.steps, "one_site": 1e3 * other_s / args.steps},
-        "roofline": {"bound": "tensor", "kernel": "k_absorb_slab<16> + k_close_dmma<16> (the two launches of a JACOBI sweep) incl. the device-side barrier; whole BP phases, per GPU",
+        "roofline": {"bound": "tensor", "kernel": (f"k_absorb_slab<{chi}> + k_close_dmma<{chi}> (the two launches of a JACOBI sweep)" if chi in (8, 16) else "k_leg_dmma x 3 + k_close_leg_dmma (generic tensor-core leg / closing kernels of a JACOBI sweep, chunked levels)") + " incl. the device-side barrier; whole BP phases, per GPU",
                      "achieved": msg / bp_s * fm / 1e12 / world, "peak": pk["fp64_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": msg / bp_s * fm / 1e12 / world / pk["fp64_tflops_sustained"], "traffic": None, "peak_source": pk["source"],
                      "note": "per-GPU rate over the BP phases (max over ranks, so the skew between ranks at the first sweep barrier is inside); single-kernel counters: profiles/README.md"},
         "gpu_launches": int(launches), "clocks": clocks, "expect_z": [float(np.real(z)) for z in zs],
     }
+    if args.no_e2e:
+        return out
     # ---- e2e: the same distributed step with this rank's site tensors in pinned HOST memory (H2D before, D2H after) ----
     L = lib.load(); h = psi._h.ptr
     sizes = [int(L.tnqs_site_size(h, v)) for v in owned_v]
@@ -628,7 +630,8 @@ def bench_config(nx, ny, chi, world, p2p=True):
     compares like with like (its `same_config` check)."""
     from tensornetworkquantumsimulator_b200 import graphs as G
     if world > 1:
-        return {"workload": f"C2 strips: {nx}x{ny * world} open grid cut into {world} row strips of {nx}x{ny} (one per GPU), random TNS chi={chi} "
+        name = "C5" if (nx, ny * world, chi) == (128, 128, 32) else "C2 strips"
+        return {"workload": f"{name}: {nx}x{ny * world} open grid cut into {world} row strips of {nx}x{ny} (one per GPU), random TNS chi={chi} "
                             "ComplexF64; step = one Trotter layer (Rx,Rz + 4 Rzz classes, maxdim=chi, cutoff=1e-10), lazy BP refreshes "
                             "(<=25 sweeps, tol 1e-8) + <Z>", "chi": chi,
                 "bp_mode": ("JACOBI; a refresh is one graph launch per rank: boundary messages stored by the message epilogue straight into the neighbour GPU's buffer (P2P over NVLink, CUDA IPC), device-side barrier + all-reduce + convergence test per sweep"
