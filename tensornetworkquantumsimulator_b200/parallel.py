@@ -260,9 +260,21 @@ def apply_class_distributed(E, bpc, gg: Graph, lgraph: LocalGraph, owner, rank, 
     """One colour class of identical two-site gates over the partitioned network (tnqs_apply_2site_begin / _end + one
     grouped exchange of R factors).  `batch` = a precomputed class_gates_local(...) result.  Returns (ranks, truncation
     errors) of this rank's batch."""
-    es, rm, cut_with = batch if batch is not None else class_gates_local(gg, lgraph, owner, rank, edges_global)
-    if len(es) == 0:
+    es_all, rm_all, cut_with = batch if batch is not None else class_gates_local(gg, lgraph, owner, rank, edges_global)
+    if len(es_all) == 0:
         return np.zeros(0, dtype=np.int32), np.zeros(0)
+    ranks_all, errs_all = np.zeros(len(es_all), dtype=np.int32), np.zeros(len(es_all))
+    # gates with both vertices on this rank need no exchange: they go through tnqs_apply_2site, which processes a batch in
+    # memory-bounded chunks (a whole class of chi = 32 gates holds ~5 copies of 2 x 32 MiB per gate); only the cut-crossing gates
+    # take the two-stage path, all of them in one exchange (their positions in `cut_with` count cut gates only)
+    inner = np.flatnonzero(rm_all == 0)
+    if len(inner):
+        r_in, e_in, _ = E.apply_2site_batch(bpc, es_all[inner], [gate] * len(inner), apply_kwargs=apply_kwargs)
+        ranks_all[inner], errs_all[inner] = r_in, e_in
+    cutpos = np.flatnonzero(rm_all != 0)
+    if len(cutpos) == 0:
+        return ranks_all, errs_all
+    es, rm = es_all[cutpos], rm_all[cutpos]
     send_ptr, ncut, slot = E.apply_2site_begin(bpc, es, [gate] * len(es), remote=rm, apply_kwargs=apply_kwargs)
     recv = None
     if ncut:
@@ -281,7 +293,8 @@ def apply_class_distributed(E, bpc, gg: Graph, lgraph: LocalGraph, owner, rank, 
             recv.view(ncut, slot)[idx] = rb
         torch.cuda.synchronize()
     ranks, errs, _ = E.apply_2site_end(bpc, len(es), recv.data_ptr() if recv is not None else None)
-    return ranks, errs
+    ranks_all[cutpos], errs_all[cutpos] = ranks, errs
+    return ranks_all, errs_all
 
 
 def _wrap_device(torch, ptr: int, n_complex: int, device):
