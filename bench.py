@@ -558,6 +558,7 @@ def run_e2e(ctx, steps):
     t_tot = 0.0
     upd = 0
     parts = np.zeros(4)
+    per_step = []
     gc.collect(); gc.freeze(); gc.disable()
     for s in range(steps + 1):                       # first pass is a warm-up
         torch.cuda.synchronize()
@@ -575,11 +576,12 @@ def run_e2e(ctx, steps):
         dt = t4 - t0
         if s > 0:
             t_tot += dt
+            per_step.append(round(1e3 * dt, 1))
             upd += L.tnqs_bp_message_updates_total(h) - u0
             parts += [t1 - t0, t2 - t1, t3 - t2, t4 - t3]
     gc.enable()
     return {"value": upd / t_tot, "message_updates_per_step": upd / steps, "unit": "messages/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": 1e3 * t_tot / steps,
+            "ms_per_step": 1e3 * t_tot / steps, "steps": steps, "step_ms": per_step,
             "parts_ms": {"h2d_set_sites": 1e3 * parts[0] / steps, "apply_gates_with_d2h_of_all_sites": 1e3 * parts[1] / steps, "expect": 1e3 * parts[2] / steps},
             "note": "host wall clock around tnqs_set_sites (all V sites from pinned host memory) + apply_gates(fetch=...) = tnqs_apply_circuit_fetch (the layer; every site tensor copied back to pinned host memory beside the closing BP refresh) + expect"}
 
@@ -696,7 +698,7 @@ def main():
     out, ctx = run_engine(args)
     rank = int(os.environ.get("RANK", "0"))
     if not args.no_e2e and ctx is not None:
-        out["e2e"] = run_e2e(ctx, max(1, min(args.steps, 2)))
+        out["e2e"] = run_e2e(ctx, max(1, min(args.steps, 6)))
     if rank == 0:
         if not args.no_cpu and int(os.environ.get("WORLD_SIZE", "1")) == 1:
             mps, gps, t_msg, t_gate = cpu_sample(args.nx, args.ny, args.chi, args.cpu_msgs, args.cpu_gates)
