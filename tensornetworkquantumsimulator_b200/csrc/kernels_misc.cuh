@@ -13,6 +13,7 @@ struct PermDesc {
   long long Po;                    // product of outer dims
   int to_matrix;                   // 1: canonical -> matrix; 0: matrix -> canonical
   const double* norm2;             // matrix -> canonical only: multiply by 1/sqrt(*norm2) if non-null
+  const int* commit;               // optimistic gate batches: the result is written only if *commit != 0 (null: always)
 };
 
 // grid: (ceil(max Po / 256), items); a thread owns one outer multi-index rho: it decomposes rho once, then walks the bond
@@ -22,6 +23,7 @@ __global__ void __launch_bounds__(256) k_permute(const PermDesc* __restrict__ de
   const PermDesc p = descs[blockIdx.y];
   const long long rho = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (rho >= p.Po) return;
+  if (p.commit && *p.commit == 0) return;
   double scale = 1.0;
   if (!p.to_matrix && p.norm2) { double n2 = *p.norm2; scale = n2 > 0.0 ? 1.0 / sqrt(n2) : 1.0; }
   long long off = 0, r = rho;

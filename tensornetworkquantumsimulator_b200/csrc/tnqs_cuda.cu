@@ -584,8 +584,9 @@ extern "C" int32_t tnqs_apply_1site(tnqs_ctx* c, int32_t n, const int32_t* v, co
 }
 
 // both directed messages of edge list[i] <- diag(svals[i*cap .. i*cap + rank[i]))
-__global__ void k_msg_diag(cplx* slab, long long slot, const int* list, const double* svals, const int* rank, int cap) {
+__global__ void k_msg_diag(cplx* slab, long long slot, const int* list, const double* svals, const int* rank, int cap, const int* commit = nullptr) {
   int i = blockIdx.x, e = list[i], r = rank[i];
+  if (commit && commit[i] == 0) return;
   cplx* a = slab + (size_t)(2 * e) * slot; cplx* b = a + slot;
   for (int idx = threadIdx.x; idx < r * r; idx += blockDim.x) {
     int x = idx % r, y = idx / r;
@@ -594,6 +595,16 @@ __global__ void k_msg_diag(cplx* slab, long long slot, const int* list, const do
   }
 }
 
+
+// Optimistic gate batches: gate i may commit (overwrite its two site tensors in place, reset its messages) iff its kept rank is the
+// one the host assumed, neither of its QR factorisations raised the CholeskyQR2 flag and no kernel of the batch reported an error.
+// flag_idx[2i], flag_idx[2i+1]: positions of the two sites in the flag array, or -1 (Householder path / remote half).
+__global__ void k_gate_ok(int n, const int* rank, const int* expect, const int* flags, const int* flag_idx, const int* status, int* ok) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int fa = flag_idx[2 * i], fb = flag_idx[2 * i + 1];
+  ok[i] = rank[i] == expect[i] && (fa < 0 || flags[fa] == 0) && (fb < 0 || flags[fb] == 0) && *status == 0;
+}
 
 // Debug aid (TNQS_DEBUG=1): Frobenius norm^2 and finiteness of a device buffer, printed to stderr.
 static void dbg_norm(tnqs_ctx* c, const char* name, int idx, const cplx* p, size_t n) {
@@ -667,6 +678,11 @@ struct GateBatch {
   // possible - after the host has built the next stage's descriptors, while the device finishes the QR kernels - and the flagged
   // matrices are then redone by Householder TSQR
   std::vector<int> chol_list; std::vector<cplx*> chol_Qb, chol_Rinv; int* d_chol_flag = nullptr; bool chol_pending = false;
+  // Optimistic mode (saturated bonds: every gate of the batch is expected to keep its bond dimension, the steady state of a
+  // truncated evolution): the host assumes rank = old chi and no CholeskyQR2 flag, enqueues the whole chain without reading
+  // anything back, and the device commits a gate only if the assumptions held (k_gate_ok).  One synchronisation per batch; the
+  // gates whose assumptions failed are left untouched and listed in `failed` for a second, conventional pass.
+  bool optimistic = false; int* d_ok = nullptr; std::vector<int> failed;
   void householder_qr(const std::vector<int>& list);
   void resolve_chol_flags();
   void stage1(int n_, const int32_t* es_, const int32_t* flips, const double* gates, const tnqs_apply_opts& o_, const int32_t* remote);
@@ -1007,7 +1023,7 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
     c->h2d(d_gates, hg.data(), hg.size() * sizeof(cplx));
   }
   (void)any_global;
-  resolve_chol_flags();        // the only host read between the stages; by now the device has (nearly) drained the QR kernels
+  if (!optimistic) resolve_chol_flags();        // the only host read between the stages; by now the device has (nearly) drained the QR kernels
   {
     ThetaDesc* dtd = c->upload(td);
     LAUNCH(c, TNQS_KC_SVD, k_theta, n, 256, 0, dtd);
@@ -1023,7 +1039,17 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
   // runs the inverse absorption; the host builds the remaining descriptors behind that kernel instead of an idle device.
   std::vector<int> ranks(n);
   int st = 0;
-  {
+  if (optimistic) {
+    std::vector<int> fidx(2 * n, -1);
+    for (size_t i = 0; i < chol_list.size(); ++i) fidx[chol_list[i]] = (int)i;      // job index 2 * gate + side
+    for (int i = 0; i < n; ++i) ranks[i] = c->chi[es[i]];
+    int* d_expect = c->upload(ranks); int* d_fidx = c->upload(fidx);
+    d_ok = c->talloc<int>(n);
+    int* no_flags = d_chol_flag ? d_chol_flag : c->d_status;                           // never read when every index is -1
+    LAUNCH(c, TNQS_KC_MISC, k_gate_ok, (n + 127) / 128, 128, 0, n, d_rank, d_expect, no_flags, d_fidx, c->d_status, d_ok);
+    for (int j = 0; j < NJ; ++j) ncols[j] = jobs[j].q;
+    absorb_outer(true);
+  } else {
     if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     int* hr = (int*)c->hret_side((size_t)(n + 1) * sizeof(int));
     cudaEvent_t ev;
@@ -1086,9 +1112,11 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
       long long tot = J.Po * J.d * r;
       // same size as before (saturated bonds): the old tensor is dead by now, write over it and keep its address, so
       // cached BP plans (which hold site pointers) stay valid
+      REQUIRE(!optimistic || tot == c->site_n[J.v], TNQS_ERR_INVALID_ARG, "internal: optimistic gate batch on an unsaturated bond");
       newsite[j] = tot == c->site_n[J.v] ? c->site[J.v] : (cplx*)c->dalloc((size_t)tot * sizeof(cplx));
       PermDesc& p = pd[j];
       p.src = Tm[j]; p.dst = newsite[j]; p.chib = r; p.to_matrix = 0; p.norm2 = o.normalize_tensors ? d_n2 + j : nullptr;
+      p.commit = optimistic ? d_ok + j / 2 : nullptr;
       long long stride = J.d;
       for (size_t l = 0, oi = 0; l < c->inc[J.v].size(); ++l) {
         int x = (int)l == J.jb ? r : c->chi[c->inc[J.v][l]];
@@ -1102,6 +1130,31 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
     long long maxPo = 1; for (int j : LJ) maxPo = std::max(maxPo, jobs[j].Po);
     unsigned gx = (unsigned)((maxPo + 255) / 256); (void)maxtot2;
     if (!lp.empty()) LAUNCH(c, TNQS_KC_PERMUTE, k_permute, dim3(gx, (unsigned)lp.size()), 256, 0, dpd);
+  }
+  if (optimistic) {
+    // nothing changes shape or address in this mode (rank = old chi, every tensor rewritten in place); the device decides per gate
+    std::vector<int> ks(es.begin(), es.end());
+    int* dks = c->upload(ks);
+    LAUNCH(c, TNQS_KC_MISC, k_msg_diag, n, 128, 0, c->msg_cur, c->slot, dks, d_sv, d_rank, cap, d_ok);
+    const size_t ob = n * sizeof(int), eb = err_out ? n * sizeof(double) : 0, sb = svals_out ? (size_t)n * cap * sizeof(double) : 0;
+    char* hb = (char*)c->hret_side(ob + sizeof(int) + eb + sb + 16);
+    CU(cudaMemcpyAsync(hb, d_ok, ob, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hb + ob, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    const size_t off = (ob + sizeof(int) + 15) / 16 * 16;
+    if (eb) CU(cudaMemcpyAsync(hb + off, d_err, eb, cudaMemcpyDeviceToHost, c->stream));
+    if (sb) CU(cudaMemcpyAsync(hb + off + eb, d_sv, sb, cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    st = *(int*)(hb + ob);
+    if (st) { int z = 0; c->h2d(c->d_status, &z, sizeof(int)); }
+    if (st & ST_NEG_EIG) throw TnqsError(TNQS_ERR_NEGATIVE_EIGENVALUE, "message eigenvalue < -10 eps in simple update");
+    if (st & ST_NO_CONV) throw TnqsError(TNQS_ERR_SVD_NO_CONVERGENCE, "Jacobi eigen/SVD iteration did not converge");
+    if (st & ST_RANK_CAP) throw TnqsError(TNQS_ERR_SHAPE, "kept rank exceeds chi_cap (raise chi_cap or set maxdim)");
+    const int* ok = (const int*)hb;
+    for (int i = 0; i < n; ++i) if (!ok[i]) failed.push_back(i);
+    if (ranks_out) for (int i = 0; i < n; ++i) ranks_out[i] = ranks[i];
+    if (eb) memcpy(err_out, hb + off, eb);
+    if (sb) memcpy(svals_out, hb + off + eb, sb);
+    return;
   }
   // ---- 9. commit: bond dimensions, site pointers, messages <- diag(S) (apply_gates.jl:105-119) ----
   bool layout_changed = false;
@@ -1139,6 +1192,8 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
   if (sb) memcpy(svals_out, hb + eb, sb);
 }
 
+static bool gate_optimistic() { const char* e = getenv("TNQS_GATE_OPTIMISTIC"); return !(e && e[0] == '0'); }
+
 static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_t* flips, const double* gates,
                              const tnqs_apply_opts& o, int32_t* ranks_out, double* err_out, double* svals_out) {
   if (n == 0) return;
@@ -1161,10 +1216,41 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
       if (i1 > i0 && bytes + need > budget) break;
       bytes += need; gcount += (size_t)d * d * d * d; ++i1;
     }
-    GateBatch gb; gb.c = c;
-    gb.stage1(i1 - i0, es + i0, flips ? flips + i0 : nullptr, (const double*)(g + goff), o, nullptr);
-    gb.stage2(nullptr, ranks_out ? ranks_out + i0 : nullptr, err_out ? err_out + i0 : nullptr,
-              svals_out ? svals_out + (size_t)i0 * c->chi_cap : nullptr);
+    const int nb = i1 - i0;
+    // saturated bonds (chi = maxdim on every edge of the chunk): the steady state of a truncated evolution, where a gate keeps its
+    // bond dimension - run the chunk optimistically (one synchronisation, GateBatch::optimistic) and redo what did not hold
+    bool optimistic = gate_optimistic() && o.maxdim > 0 && o.maxdim <= c->chi_cap;
+    for (int i = i0; i < i1 && optimistic; ++i) optimistic = c->chi[es[i]] == o.maxdim;
+    std::vector<int> failed;
+    {
+      GateBatch gb; gb.c = c; gb.optimistic = optimistic;
+      gb.stage1(nb, es + i0, flips ? flips + i0 : nullptr, (const double*)(g + goff), o, nullptr);
+      gb.stage2(nullptr, ranks_out ? ranks_out + i0 : nullptr, err_out ? err_out + i0 : nullptr,
+                svals_out ? svals_out + (size_t)i0 * c->chi_cap : nullptr);
+      failed.swap(gb.failed);
+    }
+    if (!failed.empty()) {                     // rank below the old bond dimension or an ill-conditioned QR: those gates again, conventionally
+      c->release_temps();
+      const int nf = (int)failed.size();
+      std::vector<int> fe(nf), ff(nf), fr(nf); std::vector<double> ferr(nf), fsv((size_t)nf * c->chi_cap); std::vector<cplx> fg;
+      size_t off = goff;
+      std::vector<size_t> goffs(nb);
+      for (int i = 0; i < nb; ++i) { goffs[i] = off; int d = c->d[c->esrc[es[i0 + i]]]; off += (size_t)d * d * d * d; }
+      for (int k = 0; k < nf; ++k) {
+        const int i = failed[k], d = c->d[c->esrc[es[i0 + i]]];
+        fe[k] = es[i0 + i]; ff[k] = flips ? flips[i0 + i] : 0;
+        fg.insert(fg.end(), g + goffs[i], g + goffs[i] + (size_t)d * d * d * d);
+      }
+      GateBatch gb; gb.c = c;
+      gb.stage1(nf, fe.data(), ff.data(), (const double*)fg.data(), o, nullptr);
+      gb.stage2(nullptr, fr.data(), ferr.data(), fsv.data());
+      for (int k = 0; k < nf; ++k) {
+        const int i = i0 + failed[k];
+        if (ranks_out) ranks_out[i] = fr[k];
+        if (err_out) err_out[i] = ferr[k];
+        if (svals_out) memcpy(svals_out + (size_t)i * c->chi_cap, fsv.data() + (size_t)k * c->chi_cap, c->chi_cap * sizeof(double));
+      }
+    }
     if (i1 < n) c->release_temps();
     goff += gcount; i0 = i1;
   }

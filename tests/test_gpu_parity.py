@@ -1128,3 +1128,31 @@ def test_config_c3_full_size_eagle(E):
             got = np.array(E.expect(psi_e, obs))
             assert np.max(np.abs(got - want)) < EXP_TOL, f"<Z> after step {step + 1}"
     assert psi_e.maxvirtualdim() == 32
+
+
+@pytest.mark.parametrize("cutoff", [0.2, 1e-10])
+def test_optimistic_gate_batches_fall_back_when_ranks_drop(E, cutoff):
+    # saturated bonds (chi = maxdim) run optimistically: the device commits a gate only if it kept its bond dimension.  A coarse
+    # cutoff makes every gate of the class truncate below chi, so all of them take the conventional second pass; the fine cutoff keeps
+    # the ranks at chi (all committed by the first pass).  Either way the result is the oracle's.
+    g = G.named_grid((4, 4))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=8, seed=67)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    grp = G.grid_edge_color(g)[0]
+    arrs = [gates.gate_array(("Rzz", [0, 1], 0.3 + 0.05 * i)) for i in range(len(grp))]
+    be, bo = gate_case(E, g, psi_o, grp, arrs, dict(maxdim=8, cutoff=cutoff, normalize_tensors=True), sweeps=3)
+    dims = be.psi.bond_dims()
+    assert (min(dims[e] for e in grp) < 8) == (cutoff == 0.2)
+    # a second class on the now ragged state (mixed optimistic / conventional chunks are decided per batch)
+    grp2 = G.grid_edge_color(g)[2]
+    bo2 = O.update(bo, maxiter=3)
+    be2 = E.update(be, maxiter=3)
+    dets = []
+    for e in grp2:
+        det = {}
+        O.apply_gate(bo2, arrs[0], [int(g.esrc[e]), int(g.edst[e])], maxdim=8, cutoff=1e-10, detail=det)
+        dets.append(det)
+    ranks, errs, sv = E.apply_2site_batch(be2, grp2, [arrs[0]] * len(grp2), apply_kwargs=dict(maxdim=8, cutoff=1e-10))
+    for i, det in enumerate(dets):
+        assert ranks[i] == det["rank"] and rel(sv[i, :ranks[i]], det["svals"]) < MSG_TOL
