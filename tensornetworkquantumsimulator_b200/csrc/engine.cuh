@@ -65,6 +65,8 @@ struct tnqs_ctx {
   long long prof_launches[TNQS_KC_COUNT] = {0};
   std::vector<void*> temp;                         // stream-ordered temporaries of the current call
   void* pending_gate = nullptr;
+  size_t budget_bytes = 0; int budget_calls = 0; long long budget_version = -1;      // scratch_budget() cache
+  std::vector<void*> gate_graphs;                  // GateGraph*: captured optimistic gate batches (tnqs_cuda.cu)
   void* bp_cache = nullptr;                        // BpPlanCache: last BP plan, reused while sites / bonds are unchanged
   long long state_version = 0;                     // bumped whenever a site pointer or a bond dimension changes                    // GateBatch between tnqs_apply_2site_begin and _end
 
@@ -113,6 +115,7 @@ struct tnqs_ctx {
       if (arena_off + bytes <= arena[arena_chunk].size) { void* p = arena[arena_chunk].base + arena_off; arena_off += bytes; return p; }
       ++arena_chunk; arena_off = 0;
     }
+    if (capturing) throw TnqsError(TNQS_ERR_OOM, "arena would have to grow during a graph capture");
     size_t sz = std::max(bytes, (size_t)256 << 20);
     ArenaChunk ch; ch.base = (char*)dalloc(sz); ch.size = sz;
     arena.push_back(ch); arena_chunk = arena.size() - 1; arena_off = bytes;
@@ -150,8 +153,20 @@ struct tnqs_ctx {
     if (cudaHostAlloc((void**)&hstage, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); hstage = nullptr; hstage_disabled = true; return; }
     hstage_size = bytes;
   }
+  // While a gate batch is being captured into a CUDA graph (GateGraph in tnqs_cuda.cu) every upload is staged in a pinned buffer
+  // that belongs to that graph: its memcpy nodes read the same bytes at every replay (the shared staging buffer is recycled at
+  // each synchronisation).  cap_last = where the latest upload was staged (the gate matrices are refreshed there before a replay).
+  char* cap_stage = nullptr; size_t cap_stage_size = 0, cap_stage_off = 0; char* cap_last = nullptr; bool capturing = false;
   void h2d(void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return;
+    if (capturing) {
+      const size_t need = (bytes + 255) / 256 * 256;
+      if (!cap_stage || cap_stage_off + need > cap_stage_size) throw TnqsError(TNQS_ERR_OOM, "capture staging buffer exhausted");
+      char* s = cap_stage + cap_stage_off; cap_stage_off += need; cap_last = s;
+      memcpy(s, src, bytes);
+      CU(cudaMemcpyAsync(dst, s, bytes, cudaMemcpyHostToDevice, stream));
+      return;
+    }
     StallProbe sp("upload");
     if (!hstage && !hstage_disabled) {
       const char* e = getenv("TNQS_NO_HSTAGE");

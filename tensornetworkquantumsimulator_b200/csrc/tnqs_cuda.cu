@@ -8,6 +8,7 @@ static thread_local std::string g_create_error;
 static void bp_cache_drop(tnqs_ctx* c);
 static void halo_release(tnqs_ctx* c);
 static void drop_pending_gate(tnqs_ctx* c);
+static void gate_graphs_drop(tnqs_ctx* c);
 
 #define API_BEGIN(ctx) if (!(ctx)) return TNQS_ERR_INVALID_ARG; try { CU(cudaSetDevice((ctx)->device));
 #define API_END(ctx) } catch (const TnqsError& e) { (ctx)->err = e.msg; (ctx)->release_temps(); return e.code; } \
@@ -83,11 +84,15 @@ static void reset_messages(tnqs_ctx* c) {
 
 static size_t scratch_budget(tnqs_ctx* c) {
   if (const char* e = getenv("TNQS_SCRATCH_MB")) { long mb = atol(e); if (mb > 0) return (size_t)mb << 20; }   // tests: force chunking
+  // cudaMemGetInfo takes driver locks and is not cheap on a busy host: the answer is kept for 64 calls (or until the state changes
+  // shape), which is as current as the quarter-of-free-memory rule needs
+  if (c->budget_calls > 0 && c->budget_version == c->state_version) { --c->budget_calls; return c->budget_bytes; }
   size_t fr = 0, tot = 0;
   cudaMemGetInfo(&fr, &tot);
   size_t b = fr / 4;
   const size_t cap = (size_t)16 << 30, floor_ = (size_t)64 << 20;
-  return std::max(floor_, std::min(b, cap));
+  c->budget_bytes = std::max(floor_, std::min(b, cap)); c->budget_calls = 64; c->budget_version = c->state_version;
+  return c->budget_bytes;
 }
 
 extern "C" int32_t tnqs_create(tnqs_ctx** out, int32_t nv, int32_t ne, const int32_t* esrc, const int32_t* edst,
@@ -155,6 +160,7 @@ extern "C" int32_t tnqs_destroy(tnqs_ctx* c) {
   c->collect_profile();
   drop_pending_gate(c);
   bp_cache_drop(c);
+  gate_graphs_drop(c);
   // bilinear forms: no handle may keep a pointer to this one (its cached BP plan holds our site pointers), nor we to another
   for (tnqs_ctx* u : c->bra_users) { cudaStreamSynchronize(u->stream); bp_cache_drop(u); u->bra = nullptr; ++u->state_version; }
   c->bra_users.clear();
@@ -683,6 +689,9 @@ struct GateBatch {
   // anything back, and the device commits a gate only if the assumptions held (k_gate_ok).  One synchronisation per batch; the
   // gates whose assumptions failed are left untouched and listed in `failed` for a second, conventional pass.
   bool optimistic = false; int* d_ok = nullptr; std::vector<int> failed;
+  bool defer_collect = false;            // graph capture: stage2 stops after the last enqueue, the caller collects after the launch
+  char* gates_staged = nullptr;          // where the gate matrices were staged for upload (refreshed before a graph replay)
+  void collect_optimistic(int32_t* ranks_out, double* err_out, double* svals_out);
   void householder_qr(const std::vector<int>& list);
   void resolve_chol_flags();
   void stage1(int n_, const int32_t* es_, const int32_t* flips, const double* gates, const tnqs_apply_opts& o_, const int32_t* remote);
@@ -1021,6 +1030,7 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
       svd_maxn = std::max(svd_maxn, mn);
     }
     c->h2d(d_gates, hg.data(), hg.size() * sizeof(cplx));
+    gates_staged = c->cap_last;
   }
   (void)any_global;
   if (!optimistic) resolve_chol_flags();        // the only host read between the stages; by now the device has (nearly) drained the QR kernels
@@ -1136,24 +1146,7 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
     std::vector<int> ks(es.begin(), es.end());
     int* dks = c->upload(ks);
     LAUNCH(c, TNQS_KC_MISC, k_msg_diag, n, 128, 0, c->msg_cur, c->slot, dks, d_sv, d_rank, cap, d_ok);
-    const size_t ob = n * sizeof(int), eb = err_out ? n * sizeof(double) : 0, sb = svals_out ? (size_t)n * cap * sizeof(double) : 0;
-    char* hb = (char*)c->hret_side(ob + sizeof(int) + eb + sb + 16);
-    CU(cudaMemcpyAsync(hb, d_ok, ob, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(hb + ob, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    const size_t off = (ob + sizeof(int) + 15) / 16 * 16;
-    if (eb) CU(cudaMemcpyAsync(hb + off, d_err, eb, cudaMemcpyDeviceToHost, c->stream));
-    if (sb) CU(cudaMemcpyAsync(hb + off + eb, d_sv, sb, cudaMemcpyDeviceToHost, c->stream));
-    c->sync();
-    st = *(int*)(hb + ob);
-    if (st) { int z = 0; c->h2d(c->d_status, &z, sizeof(int)); }
-    if (st & ST_NEG_EIG) throw TnqsError(TNQS_ERR_NEGATIVE_EIGENVALUE, "message eigenvalue < -10 eps in simple update");
-    if (st & ST_NO_CONV) throw TnqsError(TNQS_ERR_SVD_NO_CONVERGENCE, "Jacobi eigen/SVD iteration did not converge");
-    if (st & ST_RANK_CAP) throw TnqsError(TNQS_ERR_SHAPE, "kept rank exceeds chi_cap (raise chi_cap or set maxdim)");
-    const int* ok = (const int*)hb;
-    for (int i = 0; i < n; ++i) if (!ok[i]) failed.push_back(i);
-    if (ranks_out) for (int i = 0; i < n; ++i) ranks_out[i] = ranks[i];
-    if (eb) memcpy(err_out, hb + off, eb);
-    if (sb) memcpy(svals_out, hb + off + eb, sb);
+    if (!defer_collect) collect_optimistic(ranks_out, err_out, svals_out);
     return;
   }
   // ---- 9. commit: bond dimensions, site pointers, messages <- diag(S) (apply_gates.jl:105-119) ----
@@ -1192,6 +1185,73 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
   if (sb) memcpy(svals_out, hb + eb, sb);
 }
 
+// Results of an optimistic batch (after its kernels were enqueued, eagerly or by a graph launch): which gates committed, truncation
+// errors, singular values - one staged copy, one synchronisation.
+static void collect_optimistic_results(tnqs_ctx* c, int n, int cap, const int* es, const int* d_ok, const double* d_err, const double* d_sv,
+                                       int32_t* ranks_out, double* err_out, double* svals_out, std::vector<int>& failed) {
+  const size_t ob = n * sizeof(int), eb = err_out ? n * sizeof(double) : 0, sb = svals_out ? (size_t)n * cap * sizeof(double) : 0;
+  char* hb = (char*)c->hret_side(ob + sizeof(int) + eb + sb + 16);
+  CU(cudaMemcpyAsync(hb, d_ok, ob, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(hb + ob, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  const size_t off = (ob + sizeof(int) + 15) / 16 * 16;
+  if (eb) CU(cudaMemcpyAsync(hb + off, d_err, eb, cudaMemcpyDeviceToHost, c->stream));
+  if (sb) CU(cudaMemcpyAsync(hb + off + eb, d_sv, sb, cudaMemcpyDeviceToHost, c->stream));
+  c->sync();
+  const int st = *(int*)(hb + ob);
+  if (st) { int z = 0; c->h2d(c->d_status, &z, sizeof(int)); }
+  if (st & ST_NEG_EIG) throw TnqsError(TNQS_ERR_NEGATIVE_EIGENVALUE, "message eigenvalue < -10 eps in simple update");
+  if (st & ST_NO_CONV) throw TnqsError(TNQS_ERR_SVD_NO_CONVERGENCE, "Jacobi eigen/SVD iteration did not converge");
+  if (st & ST_RANK_CAP) throw TnqsError(TNQS_ERR_SHAPE, "kept rank exceeds chi_cap (raise chi_cap or set maxdim)");
+  const int* ok = (const int*)hb;
+  for (int i = 0; i < n; ++i) if (!ok[i]) failed.push_back(i);
+  if (ranks_out) for (int i = 0; i < n; ++i) ranks_out[i] = c->chi[es[i]];
+  if (eb) memcpy(err_out, hb + off, eb);
+  if (sb) memcpy(svals_out, hb + off + eb, sb);
+}
+void GateBatch::collect_optimistic(int32_t* ranks_out, double* err_out, double* svals_out) {
+  collect_optimistic_results(c, n, cap, es.data(), d_ok, d_err, d_sv, ranks_out, err_out, svals_out, failed);
+}
+
+// A captured optimistic batch.  In the steady state of a truncated evolution a colour class is the same launch sequence over the
+// same addresses at every layer (site tensors rewritten in place, temporaries from the same positions of the bump arena, bond
+// dimensions unchanged), so after it has run once eagerly with every gate committed it is captured - descriptor uploads included,
+// from a pinned buffer the graph owns - and replayed: one launch and one read-back per class instead of ~25 launches and ~20
+// uploads, and nothing for a preempted host thread to stall between them.  Only the gate matrices are refreshed before a replay.
+struct GateGraph {
+  std::vector<int> es, fl; tnqs_apply_opts o; long long version = -1; int n = 0, cap = 0;
+  cudaGraphExec_t exec = nullptr; char* stage = nullptr; size_t stage_size = 0; char* gates_staged = nullptr; size_t gates_bytes = 0;
+  int* d_ok = nullptr; double* d_err = nullptr; double* d_sv = nullptr; long long nlaunch = 0; int seen_ok = 0; bool no_graph = false;
+};
+static void gate_graph_free(GateGraph* gg) {
+  if (gg->exec) cudaGraphExecDestroy(gg->exec);
+  if (gg->stage) cudaFreeHost(gg->stage);
+  delete gg;
+}
+static void gate_graphs_drop(tnqs_ctx* c) { for (void* p : c->gate_graphs) gate_graph_free((GateGraph*)p); c->gate_graphs.clear(); }
+static bool same_opts(const tnqs_apply_opts& a, const tnqs_apply_opts& b) {
+  return a.maxdim == b.maxdim && a.normalize_tensors == b.normalize_tensors && memcmp(&a.cutoff, &b.cutoff, sizeof(double)) == 0;
+}
+static GateGraph* gate_graph_find(tnqs_ctx* c, int n, const int32_t* es, const int32_t* fl, const tnqs_apply_opts& o) {
+  GateGraph* hit = nullptr;
+  for (size_t i = 0; i < c->gate_graphs.size();) {
+    GateGraph* gg = (GateGraph*)c->gate_graphs[i];
+    if (gg->version != c->state_version) { gate_graph_free(gg); c->gate_graphs.erase(c->gate_graphs.begin() + i); continue; }      // a shape or an address changed
+    if (!hit && gg->n == n && same_opts(gg->o, o) && memcmp(gg->es.data(), es, n * sizeof(int)) == 0) {
+      bool same = true;
+      for (int k = 0; k < n && same; ++k) same = gg->fl[k] == (fl ? fl[k] : 0);
+      if (same) hit = gg;
+    }
+    ++i;
+  }
+  return hit;
+}
+static bool gate_graphs_enabled(tnqs_ctx* c) {
+  if (c->profiling || graphs_disabled()) return false;
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("TNQS_GATE_GRAPH"); const char* d = getenv("TNQS_DEBUG"); off = ((e && e[0] == '0') || (d && d[0] == '1')) ? 1 : 0; }
+  return off == 0;
+}
+
 static bool gate_optimistic() { const char* e = getenv("TNQS_GATE_OPTIMISTIC"); return !(e && e[0] == '0'); }
 
 static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_t* flips, const double* gates,
@@ -1222,12 +1282,66 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
     bool optimistic = gate_optimistic() && o.maxdim > 0 && o.maxdim <= c->chi_cap;
     for (int i = i0; i < i1 && optimistic; ++i) optimistic = c->chi[es[i]] == o.maxdim;
     std::vector<int> failed;
-    {
+    int32_t* r_out = ranks_out ? ranks_out + i0 : nullptr; double* e_out = err_out ? err_out + i0 : nullptr;
+    double* s_out = svals_out ? svals_out + (size_t)i0 * c->chi_cap : nullptr;
+    const int32_t* fl0 = flips ? flips + i0 : nullptr;
+    GateGraph* gg = (optimistic && gate_graphs_enabled(c)) ? gate_graph_find(c, nb, es + i0, fl0, o) : nullptr;
+    bool done = false;
+    if (gg && gg->exec) {                                  // replay
+      memcpy(gg->gates_staged, g + goff, gg->gates_bytes);
+      CU(cudaGraphLaunch(gg->exec, c->stream));
+      c->launches += gg->nlaunch;
+      collect_optimistic_results(c, nb, gg->cap, es + i0, gg->d_ok, gg->d_err, gg->d_sv, r_out, e_out, s_out, failed);
+      done = true;
+    } else if (gg && gg->seen_ok >= 1 && !gg->no_graph) {  // ran eagerly with every gate committed: capture it now
+      const long long l0 = c->launches;
+      if (!gg->stage) { gg->stage_size = (size_t)16 << 20; if (cudaHostAlloc((void**)&gg->stage, gg->stage_size, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); gg->stage = nullptr; gg->no_graph = true; } }
+      if (gg->stage) {
+        cudaGraph_t graph = nullptr;
+        GateBatch gb; gb.c = c; gb.optimistic = true; gb.defer_collect = true;
+        c->cap_stage = gg->stage; c->cap_stage_size = gg->stage_size; c->cap_stage_off = 0; c->cap_last = nullptr;
+        bool ok_cap = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok_cap) {
+          c->capturing = true;
+          try { gb.stage1(nb, es + i0, fl0, (const double*)(g + goff), o, nullptr); gb.stage2(nullptr, nullptr, nullptr, nullptr); }
+          catch (const TnqsError&) { ok_cap = false; }
+          c->capturing = false;
+          if (cudaStreamEndCapture(c->stream, &graph) != cudaSuccess || !graph) ok_cap = false;
+        }
+        c->cap_stage = nullptr;
+        if (ok_cap && cudaGraphInstantiate(&gg->exec, graph, 0) != cudaSuccess) { gg->exec = nullptr; ok_cap = false; }
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (ok_cap && gb.gates_staged) {
+          gg->nlaunch = c->launches - l0; c->launches = l0;          // the capture pass launched nothing
+          gg->d_ok = gb.d_ok; gg->d_err = gb.d_err; gg->d_sv = gb.d_sv; gg->cap = gb.cap; gg->gates_staged = gb.gates_staged; gg->gates_bytes = gcount * sizeof(cplx);
+          CU(cudaGraphLaunch(gg->exec, c->stream));
+          c->launches += gg->nlaunch;
+          collect_optimistic_results(c, nb, gg->cap, es + i0, gg->d_ok, gg->d_err, gg->d_sv, r_out, e_out, s_out, failed);
+          done = true;
+        } else {
+          c->launches = l0;
+          if (gg->exec) { cudaGraphExecDestroy(gg->exec); gg->exec = nullptr; }
+          gg->no_graph = true;                                 // e.g. the arena would have had to grow: stay eager for this batch
+          c->release_temps();
+        }
+      }
+    }
+    if (!done) {
       GateBatch gb; gb.c = c; gb.optimistic = optimistic;
-      gb.stage1(nb, es + i0, flips ? flips + i0 : nullptr, (const double*)(g + goff), o, nullptr);
-      gb.stage2(nullptr, ranks_out ? ranks_out + i0 : nullptr, err_out ? err_out + i0 : nullptr,
-                svals_out ? svals_out + (size_t)i0 * c->chi_cap : nullptr);
+      gb.stage1(nb, es + i0, fl0, (const double*)(g + goff), o, nullptr);
+      gb.stage2(nullptr, r_out, e_out, s_out);
       failed.swap(gb.failed);
+      if (optimistic && gate_graphs_enabled(c) && failed.empty()) {
+        if (!gg) {
+          if (c->gate_graphs.size() >= 12) { gate_graph_free((GateGraph*)c->gate_graphs.front()); c->gate_graphs.erase(c->gate_graphs.begin()); }
+          gg = new GateGraph(); gg->es.assign(es + i0, es + i1); gg->fl.resize(nb);
+          for (int k = 0; k < nb; ++k) gg->fl[k] = fl0 ? fl0[k] : 0;
+          gg->o = o; gg->n = nb; gg->version = c->state_version;
+          c->gate_graphs.push_back(gg);
+        }
+        ++gg->seen_ok;
+      }
     }
     if (!failed.empty()) {                     // rank below the old bond dimension or an ill-conditioned QR: those gates again, conventionally
       c->release_temps();
