@@ -341,8 +341,10 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
   if (nseq == 0) return;
   const bool want_diff = o.tolerance >= 0;
   // dependency levels of the sequential (Gauss-Seidel) order; no message is read and written in the same level
-  std::vector<int> level(nseq, 0);
+  std::vector<int> level;
   int nlevels = 1;
+  auto compute_levels = [&]() {                    // only when the plan is (re)built: a cached plan already holds its schedule
+  level.assign(nseq, 0);
   if (o.mode == TNQS_BP_REFERENCE_ORDER) {
     std::vector<int> lastwrite(2 * c->ne, -1), lastread(2 * c->ne, -1);
     for (int i = 0; i < nseq; ++i) {
@@ -367,9 +369,10 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
       nlevels = std::max(nlevels, lvl + 1);
     }
   } else {
-    std::set<int> uniq(seq.begin(), seq.end());
-    REQUIRE((int)uniq.size() == nseq, TNQS_ERR_INVALID_ARG, "JACOBI mode needs each directed edge at most once");
+    std::vector<char> seen(2 * c->ne, 0);
+    for (int k : seq) { REQUIRE(!seen[k], TNQS_ERR_INVALID_ARG, "JACOBI mode needs each directed edge at most once"); seen[k] = 1; }
   }
+  };
   BpPlanCache* pc = (BpPlanCache*)c->bp_cache;
   const bool same_request = pc && pc->mode == o.mode && pc->normalize == o.normalize && pc->hermitize == o.hermitize &&
                             pc->want_diff == (int)want_diff && pc->seq == seq;
@@ -378,6 +381,7 @@ static void bp_update_impl(tnqs_ctx* c, const int32_t* seq_in, int nseq_in, cons
     // (re)build; when only site pointers / values changed the new plan lands in the old one's buffers and keeps its graph
     BpPlanCache* old = same_request ? pc : nullptr;
     if (pc && !old) { bp_cache_drop(c); pc = nullptr; }
+    compute_levels();
     BpPlanCache* nc = old ? old : new BpPlanCache();
     std::vector<void*> saved; saved.swap(c->temp);            // allocations made while building belong to the cache
     c->arena_bypass = true;
