@@ -1251,6 +1251,7 @@ static GateGraph* gate_graph_find(tnqs_ctx* c, int n, const int32_t* es, const i
 }
 static bool gate_graphs_enabled(tnqs_ctx* c) {
   if (c->profiling || graphs_disabled()) return false;
+  if (getenv("TNQS_GATE_GRAPH_OFF_FOR_TEST")) return false;          // read on every call (the other switches are latched at first use)
   static int off = -1;
   if (off < 0) { const char* e = getenv("TNQS_GATE_GRAPH"); const char* d = getenv("TNQS_DEBUG"); off = ((e && e[0] == '0') || (d && d[0] == '1')) ? 1 : 0; }
   return off == 0;
@@ -1292,6 +1293,8 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
     GateGraph* gg = (optimistic && gate_graphs_enabled(c)) ? gate_graph_find(c, nb, es + i0, fl0, o) : nullptr;
     bool done = false;
     if (gg && gg->exec) {                                  // replay
+      static const char* dbg = getenv("TNQS_DEBUG_QUEUE");
+      if (dbg) fprintf(stderr, "[tnqs] gate batch of %d: graph replay (%lld kernels)\n", nb, gg->nlaunch);
       memcpy(gg->gates_staged, g + goff, gg->gates_bytes);
       CU(cudaGraphLaunch(gg->exec, c->stream));
       c->launches += gg->nlaunch;

@@ -1156,3 +1156,44 @@ def test_optimistic_gate_batches_fall_back_when_ranks_drop(E, cutoff):
     ranks, errs, sv = E.apply_2site_batch(be2, grp2, [arrs[0]] * len(grp2), apply_kwargs=dict(maxdim=8, cutoff=1e-10))
     for i, det in enumerate(dets):
         assert ranks[i] == det["rank"] and rel(sv[i, :ranks[i]], det["svals"]) < MSG_TOL
+
+
+def test_graph_replayed_gate_classes_follow_the_oracle_over_layers(E):
+    # saturated bonds (random chi = 8 state, maxdim = 8): from the second layer on a colour class is captured into a CUDA graph and
+    # from the third on replayed with only the gate matrices refreshed.  Four layers with a different angle per layer (the refresh
+    # matters) against the oracle, layer by layer; then the same with the replay switched off must give bit-identical tensors.
+    g = G.named_grid((4, 4))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=8, seed=91)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    groups = G.grid_edge_color(g)
+    kw = dict(maxdim=8, cutoff=1e-12, normalize_tensors=True)
+
+    def layer(l):
+        out = [("Rx", [g.names[v]], 0.3 + 0.1 * l) for v in range(g.nv)]
+        for grp in groups:
+            out += [("Rzz", [g.names[int(g.esrc[e])], g.names[int(g.edst[e])]], 0.2 + 0.07 * l) for e in grp]
+        return out
+
+    def run(engine_state):
+        bo = O.update(O.BeliefPropagationCache(psi_o.copy()), **O.default_bp_update_kwargs(psi_o))
+        be = E.update(E.BeliefPropagationCache(engine_state, _share=True), inplace=True, **E.default_bp_update_kwargs(engine_state))
+        for l in range(4):
+            bo, errs_o = O.apply_gates(layer(l), bo, apply_kwargs=kw)
+            be, errs_e = E.apply_gates(layer(l), be, apply_kwargs=kw, inplace=True)
+            assert list(be.psi.bond_dims()) == list(bo.network.bond_dims()), f"layer {l}"
+            assert np.allclose(errs_e, errs_o, rtol=1e-6, atol=1e-13), f"layer {l}"
+            for v in (0, 5, 10, 15):
+                assert abs(E.expect(be, ("Z", [g.names[v]])) - O.expect(bo, ("Z", [g.names[v]]))) < EXP_TOL, f"layer {l}, vertex {v}"
+        return be
+
+    b1 = run(E.TensorNetworkState.from_arrays(g, psi_o.tensors, chi_cap=8))
+    assert b1.psi.maxvirtualdim() == 8
+    import os
+    os.environ["TNQS_GATE_GRAPH_OFF_FOR_TEST"] = "1"
+    try:
+        b2 = run(E.TensorNetworkState.from_arrays(g, psi_o.tensors, chi_cap=8))
+    finally:
+        os.environ.pop("TNQS_GATE_GRAPH_OFF_FOR_TEST")
+    for a, b in zip(b1.psi.tensors(), b2.psi.tensors()):
+        assert np.array_equal(a, b)
