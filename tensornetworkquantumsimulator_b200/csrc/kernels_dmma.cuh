@@ -624,8 +624,12 @@ inline size_t leg_smem_bytes(int n, int np) { return (size_t)(8 * leg_kk(n)) * l
 // current one multiplies.
 // A CTA fills the expanded matrix once and then walks `tpc` consecutive row tiles with it (the fill costs about as much as
 // one tile at n = 32).
-__global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __restrict__ descs, int tpc) {
+// CANON: the two-leg form described at ModeApplyDesc (row stride, composite contracted index, commit predicate); the plain
+// instantiation is the one every other caller uses and is compiled without any of it.
+template <bool CANON>
+__global__ void __launch_bounds__(256, 2) k_leg_dmma_t(const ModeApplyDesc* __restrict__ descs, int tpc) {
   const ModeApplyDesc d = descs[blockIdx.y];
+  if (CANON && d.commit && *d.commit == 0) return;
   const int G = leg_groups(d.np), LDB = leg_ldb(d.np);
   const int rows_per_cta = leg_rows_per_cta(d.np);
   const long long rows = (long long)d.L * d.R;
@@ -665,7 +669,7 @@ __global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __rest
     long long row = wrow0 + 8 * t + r;
     valid[t] = row < rows;
     long long rr = valid[t] ? row / d.L : 0, l = valid[t] ? row - rr * d.L : 0;
-    soff[t] = (int)(l + rr * d.in_sr);
+    soff[t] = (int)((CANON ? l * d.in_sl : l) + rr * d.in_sr);
   }
   double acc[4][4][2];
 #pragma unroll
@@ -676,7 +680,7 @@ __global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __rest
   auto load = [&](int set, int kk) {
     const int b = 4 * kk + q;
     const bool bok = b < n;
-    const cplx* in_b = d.in + (long long)b * d.in_sb;
+    const cplx* in_b = CANON ? d.in + (b % d.kd) + (long long)(b / d.kd) * d.in_sb : d.in + (long long)b * d.in_sb;
 #pragma unroll
     for (int t = 0; t < 4; ++t) a[set][t] = (valid[t] && bok) ? in_b[soff[t]] : cmake(0, 0);
   };
@@ -707,15 +711,18 @@ __global__ void __launch_bounds__(256, 2) k_leg_dmma(const ModeApplyDesc* __rest
     const ModeApplyDesc* dp = descs + blockIdx.y;
     const long long out_sr = dp->out_sr, out_sb = dp->out_sb;
     const long long row = wrow0 + 8 * t + r, rr = row / d.L, l = row - rr * d.L;
-    cplx* o = dp->out + l + rr * out_sr;
+    cplx* o = dp->out + (CANON ? l * dp->out_sl : l) + rr * out_sr;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = 16 * grp + 4 * j + q;
-      if (c < np) o[(long long)c * out_sb] = cmake(acc[t][j][0], acc[t][j][1]);
+      if (c < np) o[CANON ? (c % d.kd) + (long long)(c / d.kd) * out_sb : (long long)c * out_sb] = cmake(acc[t][j][0], acc[t][j][1]);
     }
   }
   }   // tiles
 }
+
+#define k_leg_dmma k_leg_dmma_t<false>
+#define k_leg_canon_dmma k_leg_dmma_t<true>
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_close_leg_dmma: tensor-core version of k_mode_close for n, np <= 64:  G[b, b'] = sum_rows A[row, b] conj(B[row, b']).

@@ -12,6 +12,10 @@ struct ModeApplyDesc {
   long long in_sb, in_sr, out_sb, out_sr;   // strides (complex elements) of the b and r indices; l stride = 1
   int ldm;                         // leading dimension of m
   int flags;                       // bit0: use conj(m); bit1: use m^T (element (b,c) = m[c + b*ldm])
+  // k_leg_dmma<true> only (a product over TWO legs of a tensor in its canonical layout, e.g. (site index, gate bond)): the row
+  // index l has stride sl instead of 1, and the contracted / produced index k = k0 + kd * k1 sits at k0 + k1 * sb
+  long long in_sl = 1, out_sl = 1; int kd = 1;
+  const int* commit = nullptr;     // optimistic gate batches: nothing is written unless *commit != 0
 };
 
 #define MA_BM 64

@@ -79,9 +79,10 @@ __global__ void __launch_bounds__(1024) k_norm2(const Norm2Desc* __restrict__ de
 // ---- x *= factor (complex); factor = f(*scalar) ----------------------------------------------------------------
 // mode 0: 1/sqrt(norm2[0]) (Frobenius normalisation, simple_update.jl:63-65)
 // mode 1: rescale_vertices!: s / sqrt(vn), vn = scalar[0] + i scalar[1], s = sign(vn) if real else 1 (bpcache.jl:87-106)
-struct ScaleDesc { cplx* x; long long n; const double* scalar; int mode; };
+struct ScaleDesc { cplx* x; long long n; const double* scalar; int mode; const int* commit = nullptr; };     // commit: see PermDesc
 __global__ void __launch_bounds__(256) k_scale(const ScaleDesc* __restrict__ descs) {
   const ScaleDesc d = descs[blockIdx.y];
+  if (d.commit && *d.commit == 0) return;
   cplx f;
   if (d.mode == 0) { double n2 = d.scalar[0]; f = cmake(n2 > 0.0 ? 1.0 / sqrt(n2) : 1.0, 0.0); }
   else {

@@ -131,6 +131,7 @@ struct EighDesc {
   double cutoff;                  // mode 0: f(lambda) = 0 if lambda == 0 or |lambda| < cutoff
   double shift;                   // mode 1: lambda <- lambda + shift, no cutoff (symmetric_gauge.jl:14-15)
   int mode;
+  int* cutflag = nullptr;         // mode 0: set to 1 when an eigenvalue fell under the cutoff (then sqrt(M) M^(-1/2) is a projector, not 1)
 };
 
 // dynamic shared memory: W[n*n] V[n*n] complex, lam[n] fr[n] fi[n] doubles
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(1024) k_eigh_sqrt(const EighDesc* __restrict__
       if (d.mode == 0) {
         if (!(s == 0.0 || fabs(s) < d.cutoff)) {
           if (s < 0) atomicOr(status, ST_NEG_EIG); else { f = sqrt(s); g = 1.0 / f; }
-        }
+        } else if (d.cutflag) atomicOr(d.cutflag, 1);
       } else {
         double l = s + d.shift;
         if (l < 0) atomicOr(status, ST_NEG_EIG); else { f = sqrt(l); g = 1.0 / f; }
@@ -453,4 +454,33 @@ __global__ void __launch_bounds__(256) k_small_matmul(const SmallMatmulDesc* __r
     }
     d.c[i + (size_t)j * d.ldc] = acc;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_tri_solve: W = R^-1 B for an upper-triangular R (n x n, ld = ldr) and n x m right-hand sides (ld = ldb), by back substitution in
+// shared memory; one CTA per item, a thread per column of B.  Used by the optimistic gate path: T' = psi (R^-1 R') replaces
+// Q' R' when the incoming messages are of full rank (tnqs_cuda.cu, GateBatch::stage2).  dynamic shared memory: n * n + n * m complex.
+// ---------------------------------------------------------------------------------------------------------------
+struct TriSolveDesc { const cplx* r; int ldr; const cplx* b; int ldb; cplx* w; int ldw; int n, m; };
+__global__ void __launch_bounds__(256) k_tri_solve(const TriSolveDesc* __restrict__ descs) {
+  const TriSolveDesc d = descs[blockIdx.x];
+  extern __shared__ cplx tsm[];
+  cplx* R = tsm;                       // n x n
+  cplx* X = tsm + (size_t)d.n * d.n;   // n x m
+  const int n = d.n, m = d.m;
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) R[idx] = d.r[(idx % n) + (size_t)(idx / n) * d.ldr];
+  for (int idx = threadIdx.x; idx < n * m; idx += blockDim.x) X[idx] = d.b[(idx % n) + (size_t)(idx / n) * d.ldb];
+  __syncthreads();
+  for (int c = threadIdx.x; c < m; c += blockDim.x) {
+    cplx* x = X + (size_t)c * n;
+    for (int i = n - 1; i >= 0; --i) {
+      cplx s = x[i];
+      for (int k = i + 1; k < n; ++k) s = csub(s, cmul(R[i + (size_t)k * n], x[k]));
+      const cplx rii = R[i + (size_t)i * n];
+      const double den = rii.x * rii.x + rii.y * rii.y;
+      x[i] = cmake((s.x * rii.x + s.y * rii.y) / den, (s.y * rii.x - s.x * rii.y) / den);
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n * m; idx += blockDim.x) d.w[(idx % n) + (size_t)(idx / n) * d.ldw] = X[idx];
 }

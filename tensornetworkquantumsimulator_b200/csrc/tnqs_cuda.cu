@@ -9,6 +9,7 @@ static void bp_cache_drop(tnqs_ctx* c);
 static void halo_release(tnqs_ctx* c);
 static void drop_pending_gate(tnqs_ctx* c);
 static void gate_graphs_drop(tnqs_ctx* c);
+static bool gate_wpath();
 
 #define API_BEGIN(ctx) if (!(ctx)) return TNQS_ERR_INVALID_ARG; try { CU(cudaSetDevice((ctx)->device));
 #define API_END(ctx) } catch (const TnqsError& e) { (ctx)->err = e.msg; (ctx)->release_temps(); return e.code; } \
@@ -61,6 +62,8 @@ static void set_smem_attrs() {   // per device: called at every handle creation 
   cudaFuncSetAttribute(k_bp_sweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_close_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_leg_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_leg_canon_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_tri_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   // three 72 KB CTAs per SM need the largest shared-memory carve-out
   cudaFuncSetAttribute(k_absorb_slab<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -609,11 +612,11 @@ __global__ void k_msg_diag(cplx* slab, long long slot, const int* list, const do
 // Optimistic gate batches: gate i may commit (overwrite its two site tensors in place, reset its messages) iff its kept rank is the
 // one the host assumed, neither of its QR factorisations raised the CholeskyQR2 flag and no kernel of the batch reported an error.
 // flag_idx[2i], flag_idx[2i+1]: positions of the two sites in the flag array, or -1 (Householder path / remote half).
-__global__ void k_gate_ok(int n, const int* rank, const int* expect, const int* flags, const int* flag_idx, const int* status, int* ok) {
+__global__ void k_gate_ok(int n, const int* rank, const int* expect, const int* flags, const int* flag_idx, const int* cut, const int* status, int* ok) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int fa = flag_idx[2 * i], fb = flag_idx[2 * i + 1];
-  ok[i] = rank[i] == expect[i] && (fa < 0 || flags[fa] == 0) && (fb < 0 || flags[fb] == 0) && *status == 0;
+  ok[i] = rank[i] == expect[i] && (fa < 0 || flags[fa] == 0) && (fb < 0 || flags[fb] == 0) && (!cut || (cut[2 * i] == 0 && cut[2 * i + 1] == 0)) && *status == 0;
 }
 
 // Debug aid (TNQS_DEBUG=1): Frobenius norm^2 and finiteness of a device buffer, printed to stderr.
@@ -693,6 +696,11 @@ struct GateBatch {
   // anything back, and the device commits a gate only if the assumptions held (k_gate_ok).  One synchronisation per batch; the
   // gates whose assumptions failed are left untouched and listed in `failed` for a second, conventional pass.
   bool optimistic = false; int* d_ok = nullptr; std::vector<int> failed;
+  // W path (optimistic mode, square R): with messages of full rank sqrt(M) M^(-1/2) = 1, so T' = Q' R' = psi (R^-1 R') - the new site
+  // tensor is the OLD one times a small matrix over its (site, gate-bond) legs, computed in place in the canonical layout
+  // (k_leg_canon_dmma).  No inverse absorption, no Q R' product, no permute back; a message with a cut eigenvalue (k_eigh_sqrt's
+  // flag) fails the gate's commit predicate and sends it to the conventional second pass.
+  std::vector<char> wpath; int* d_jobcut = nullptr;
   bool defer_collect = false;            // graph capture: stage2 stops after the last enqueue, the caller collects after the launch
   char* gates_staged = nullptr;          // where the gate matrices were staged for upload (refreshed before a graph replay)
   void collect_optimistic(int32_t* ranks_out, double* err_out, double* svals_out);
@@ -709,6 +717,7 @@ void GateBatch::absorb_outer(bool inverse) {   // forward: on A (psi~); inverse:
   std::vector<SlabDesc> slab[2];                 // [0]: N = 8, [1]: N = 16
   int maxcols[2] = {0, 0};
   for (int j : LJ) {
+    if (inverse && !wpath.empty() && wpath[j]) continue;
     SiteJob& J = jobs[j];
     const int F = (int)J.outer.size();
     int N = F ? c->chi[c->inc[J.v][J.outer[0]]] : 0;
@@ -861,12 +870,14 @@ void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const d
   // ---- 1. sqrt / inverse sqrt of the incoming messages (src/utils.jl:18-26) ----
   std::vector<EighDesc> eg;
   int maxchi = 1;
+  d_jobcut = c->talloc<int>(NJ);
+  CU(cudaMemsetAsync(d_jobcut, 0, NJ * sizeof(int), c->stream));
   for (int jj : LJ) { SiteJob& J = jobs[jj];
     for (int j : J.outer) {
       int ee = c->inc[J.v][j], u = c->other(ee, J.v), x = c->chi[ee];
       EighDesc d; d.m = c->msg(c->dedge(u, ee)); d.n = x; d.ldm = x;
       d.root = c->talloc<cplx>((size_t)x * x); d.invroot = c->talloc<cplx>((size_t)x * x);
-      d.cutoff = 10 * TNQS_EPS; d.shift = 0; d.mode = 0;
+      d.cutoff = 10 * TNQS_EPS; d.shift = 0; d.mode = 0; d.cutflag = d_jobcut + jj;
       J.root.push_back(d.root); J.invroot.push_back(d.invroot);
       eg.push_back(d); maxchi = std::max(maxchi, x);
     } }
@@ -1060,7 +1071,11 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
     int* d_expect = c->upload(ranks); int* d_fidx = c->upload(fidx);
     d_ok = c->talloc<int>(n);
     int* no_flags = d_chol_flag ? d_chol_flag : c->d_status;                           // never read when every index is -1
-    LAUNCH(c, TNQS_KC_MISC, k_gate_ok, (n + 127) / 128, 128, 0, n, d_rank, d_expect, no_flags, d_fidx, c->d_status, d_ok);
+    wpath.assign(NJ, 0);
+    bool any_w = false;
+    if (gate_wpath() && !dmma_disabled())
+      for (int j : LJ) { wpath[j] = jobs[j].q == jobs[j].nc && jobs[j].nc <= 64; any_w = any_w || wpath[j]; }
+    LAUNCH(c, TNQS_KC_MISC, k_gate_ok, (n + 127) / 128, 128, 0, n, d_rank, d_expect, no_flags, d_fidx, any_w ? d_jobcut : (int*)nullptr, c->d_status, d_ok);
     for (int j = 0; j < NJ; ++j) ncols[j] = jobs[j].q;
     absorb_outer(true);
   } else {
@@ -1093,14 +1108,42 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
     for (int j : LJ) {
       SiteJob& J = jobs[j]; int r = ranks[j / 2];
       rfin[j] = (j & 1) ? r2n[j / 2] : r1n[j / 2];
-      if (!J.colfix) continue;
+      if (!J.colfix || (!wpath.empty() && wpath[j])) continue;
       SmallMatmulDesc x; x.a = J.colfix; x.b = rfin[j]; x.m = J.nc; x.k = J.q; x.n = J.d * r; x.lda = J.nc; x.ldb = J.q; x.ldc = J.nc; x.transA = 0;
       x.c = c->talloc<cplx>((size_t)J.nc * J.d * r);
       rfin[j] = x.c; sm.push_back(x);
     }
     if (!sm.empty()) { SmallMatmulDesc* dsm = c->upload(sm); LAUNCH(c, TNQS_KC_MISC, k_small_matmul, (unsigned)sm.size(), 256, 0, dsm); }
+    if (!wpath.empty()) {
+      std::vector<TriSolveDesc> ts; std::vector<ModeApplyDesc> mw; size_t tsmem = 0;
+      for (int j : LJ) {
+        if (!wpath[j]) continue;
+        SiteJob& J = jobs[j]; const int r = ranks[j / 2], v = J.v;
+        TriSolveDesc t; t.r = J.Rbuf; t.ldr = J.q; t.b = (j & 1) ? r2n[j / 2] : r1n[j / 2]; t.ldb = J.q; t.n = J.nc; t.m = J.d * r;
+        t.w = c->talloc<cplx>((size_t)J.nc * J.d * r); t.ldw = J.nc;
+        ts.push_back(t); tsmem = std::max(tsmem, ((size_t)t.n * t.n + (size_t)t.n * t.m) * sizeof(cplx));
+        long long Llo = 1, hi = 1;
+        for (int l = 0; l < (int)c->inc[v].size(); ++l) { const int x = c->chi[c->inc[v][l]]; if (l < J.jb) Llo *= x; else if (l > J.jb) hi *= x; }
+        ModeApplyDesc d; d.in = c->site[v]; d.out = c->site[v]; d.m = t.w; d.ldm = J.nc; d.flags = 0;
+        d.L = (int)Llo; d.R = (int)hi; d.n = J.nc; d.np = J.d * r; d.kd = J.d;
+        d.in_sl = J.d; d.in_sb = J.d * Llo; d.in_sr = (long long)J.d * Llo * J.chib;
+        d.out_sl = J.d; d.out_sb = J.d * Llo; d.out_sr = (long long)J.d * Llo * r;
+        d.commit = d_ok + j / 2;
+        mw.push_back(d);
+      }
+      if (!ts.empty()) {
+        REQUIRE(tsmem <= 160 * 1024, TNQS_ERR_UNSUPPORTED, "triangular solve does not fit shared memory");
+        TriSolveDesc* dts = c->upload(ts);
+        LAUNCH(c, TNQS_KC_MISC, k_tri_solve, (unsigned)ts.size(), 256, tsmem, dts);
+        ModeApplyDesc* dmw = c->upload(mw);
+        ApplyLaunch al = plan_apply_launch(mw.data(), mw.size());
+        REQUIRE(al.dmma, TNQS_ERR_UNSUPPORTED, "internal: the in-place two-leg product needs the tensor-core leg kernel");
+        LAUNCH(c, TNQS_KC_MODE_APPLY, k_leg_canon_dmma, al.grid, 256, al.smem, dmw, al.tpc);
+      }
+    }
     std::vector<ModeApplyDesc> ma; long long maxtiles = 1; int maxcol = 1;
     for (int j : LJ) {
+      if (!wpath.empty() && wpath[j]) continue;
       SiteJob& J = jobs[j]; int r = ranks[j / 2];
       Tm[j] = c->talloc<cplx>((size_t)J.Po * J.d * r);
       ma.emplace_back(); ModeApplyDesc& d = ma.back();
@@ -1115,13 +1158,20 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
   double* d_n2 = c->talloc<double>(NJ);
   if (o.normalize_tensors) {
     std::vector<Norm2Desc> nd;
-    for (int j : LJ) { Norm2Desc x; x.x = Tm[j]; x.n = jobs[j].Po * jobs[j].d * ranks[j / 2]; x.out = d_n2 + j; x.partial = nullptr; x.npartial = 0; nd.push_back(x); }
+    std::vector<ScaleDesc> sw;
+    for (int j : LJ) {
+      const bool w = !wpath.empty() && wpath[j];
+      Norm2Desc x; x.x = w ? c->site[jobs[j].v] : Tm[j]; x.n = jobs[j].Po * jobs[j].d * ranks[j / 2]; x.out = d_n2 + j; x.partial = nullptr; x.npartial = 0; nd.push_back(x);
+      if (w) { ScaleDesc sc; sc.x = c->site[jobs[j].v]; sc.n = x.n; sc.scalar = d_n2 + j; sc.mode = 0; sc.commit = d_ok + j / 2; sw.push_back(sc); }
+    }
     Norm2Desc* dnd = c->upload(nd);
     if (!nd.empty()) LAUNCH(c, TNQS_KC_MISC, k_norm2, (unsigned)nd.size(), 1024, 0, dnd);
+    if (!sw.empty()) { ScaleDesc* dsw = c->upload(sw); LAUNCH(c, TNQS_KC_MISC, k_scale, dim3(64, (unsigned)sw.size()), 256, 0, dsw); }
   }
   {
     long long maxtot2 = 1;
     for (int j : LJ) {
+      if (!wpath.empty() && wpath[j]) { newsite[j] = c->site[jobs[j].v]; continue; }
       SiteJob& J = jobs[j]; int r = ranks[j / 2];
       long long tot = J.Po * J.d * r;
       // same size as before (saturated bonds): the old tensor is dead by now, write over it and keep its address, so
@@ -1139,7 +1189,7 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
       }
       maxtot2 = std::max(maxtot2, tot);
     }
-    std::vector<PermDesc> lp; for (int j : LJ) lp.push_back(pd[j]);
+    std::vector<PermDesc> lp; for (int j : LJ) if (wpath.empty() || !wpath[j]) lp.push_back(pd[j]);
     PermDesc* dpd = c->upload(lp);
     long long maxPo = 1; for (int j : LJ) maxPo = std::max(maxPo, jobs[j].Po);
     unsigned gx = (unsigned)((maxPo + 255) / 256); (void)maxtot2;
@@ -1257,6 +1307,7 @@ static bool gate_graphs_enabled(tnqs_ctx* c) {
   return off == 0;
 }
 
+static bool gate_wpath() { const char* e = getenv("TNQS_GATE_WPATH"); return !(e && e[0] == '0'); }
 static bool gate_optimistic() { const char* e = getenv("TNQS_GATE_OPTIMISTIC"); return !(e && e[0] == '0'); }
 
 static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_t* flips, const double* gates,
