@@ -1197,3 +1197,33 @@ def test_graph_replayed_gate_classes_follow_the_oracle_over_layers(E):
         os.environ.pop("TNQS_GATE_GRAPH_OFF_FOR_TEST")
     for a, b in zip(b1.psi.tensors(), b2.psi.tensors()):
         assert np.array_equal(a, b)
+
+
+def test_optimistic_gates_with_rank_deficient_messages_take_the_conventional_pass(E):
+    # a chi = 2 state embedded in zero-padded chi = 4 tensors, maxdim = 4: bonds are "saturated", so the batch starts optimistically, but
+    # every message has two vanishing eigenvalues (sqrt(M) M^(-1/2) is a projector, not 1): k_eigh_sqrt's flag fails every commit
+    # predicate and the gates run conventionally.  Gauge-invariant results against the oracle on the same padded tensors.
+    g = G.named_grid((3, 3))
+    small = O.random_tensornetworkstate(g, bond_dimension=2, seed=19)
+    ts = []
+    for v, t in enumerate(small.tensors):
+        big = np.zeros((2,) + (4,) * g.degree(v), dtype=np.complex128)
+        big[tuple(slice(0, n) for n in t.shape)] = t / np.linalg.norm(t)
+        ts.append(big)
+    psi_o = O.TensorNetworkState(g, ts)
+    grp = G.grid_edge_color(g)[0]
+    arr = gates.gate_array(("Rxx", [0, 1], 0.7))
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=8)
+    be = E.update(to_engine(psi_o, chi_cap=4), maxiter=8)
+    dets = []
+    for e in grp:
+        det = {}
+        O.apply_gate(bo, arr, [int(g.esrc[e]), int(g.edst[e])], maxdim=4, cutoff=1e-12, detail=det)
+        dets.append(det)
+    ranks, errs, sv = E.apply_2site_batch(be, grp, [arr] * len(grp), apply_kwargs=dict(maxdim=4, cutoff=1e-12))
+    for i, det in enumerate(dets):
+        assert ranks[i] == det["rank"]
+        assert rel(sv[i, :ranks[i]], det["svals"]) < 1e-8
+    te = be.psi.tensors()
+    for e in grp:
+        assert rel(two_site(g, te, e), two_site(g, bo.network.tensors, e)) < 1e-7
