@@ -66,6 +66,7 @@ struct tnqs_ctx {
   std::vector<void*> temp;                         // stream-ordered temporaries of the current call
   void* pending_gate = nullptr;
   size_t budget_bytes = 0; int budget_calls = 0; long long budget_version = -1;      // scratch_budget() cache
+  char* gg_pool = nullptr; size_t gg_pool_size = 0, gg_pool_off = 0;               // pinned pool of the captured batches' upload stages
   std::vector<void*> gate_graphs;                  // GateGraph*: captured optimistic gate batches (tnqs_cuda.cu)
   void* bp_cache = nullptr;                        // BpPlanCache: last BP plan, reused while sites / bonds are unchanged
   long long state_version = 0;                     // bumped whenever a site pointer or a bond dimension changes                    // GateBatch between tnqs_apply_2site_begin and _end
@@ -183,7 +184,8 @@ struct tnqs_ctx {
     }
   }
   void hstage_destroy() { if (hstage) cudaFreeHost(hstage); hstage = nullptr; hstage_size = 0; hstage_off = 0; if (hret) cudaFreeHost(hret); hret = nullptr;
-                          if (hside) cudaFreeHost(hside); hside = nullptr; hside_size = 0; }
+                          if (hside) cudaFreeHost(hside); hside = nullptr; hside_size = 0;
+                          if (gg_pool) cudaFreeHost(gg_pool); gg_pool = nullptr; gg_pool_size = 0; gg_pool_off = 0; }
   // Second pinned return page, grown on demand: results that come back on the copy stream (gate ranks) or in one batch at the end
   // of a call (truncation errors, singular values).  Valid until the next request.
   char* hside = nullptr; size_t hside_size = 0;

@@ -1276,12 +1276,26 @@ struct GateGraph {
   cudaGraphExec_t exec = nullptr; char* stage = nullptr; size_t stage_size = 0; char* gates_staged = nullptr; size_t gates_bytes = 0;
   int* d_ok = nullptr; double* d_err = nullptr; double* d_sv = nullptr; long long nlaunch = 0; int seen_ok = 0; bool no_graph = false;
 };
+// The upload stages of all captured batches of a handle are slices of ONE pinned pool (page-locking memory costs tens of
+// milliseconds per call on these hosts): bump-allocated, rewound when the last graph of the handle is gone.
 static void gate_graph_free(GateGraph* gg) {
   if (gg->exec) cudaGraphExecDestroy(gg->exec);
-  if (gg->stage) cudaFreeHost(gg->stage);
   delete gg;
 }
-static void gate_graphs_drop(tnqs_ctx* c) { for (void* p : c->gate_graphs) gate_graph_free((GateGraph*)p); c->gate_graphs.clear(); }
+static void gate_graphs_drop(tnqs_ctx* c) {
+  for (void* p : c->gate_graphs) gate_graph_free((GateGraph*)p);
+  c->gate_graphs.clear(); c->gg_pool_off = 0;
+}
+static char* gate_graph_stage(tnqs_ctx* c, size_t bytes) {
+  if (!c->gg_pool) {
+    const size_t sz = (size_t)48 << 20;
+    if (cudaHostAlloc((void**)&c->gg_pool, sz, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); c->gg_pool = nullptr; return nullptr; }
+    c->gg_pool_size = sz; c->gg_pool_off = 0;
+  }
+  if (c->gg_pool_off + bytes > c->gg_pool_size) return nullptr;
+  char* p = c->gg_pool + c->gg_pool_off; c->gg_pool_off += bytes;
+  return p;
+}
 static bool same_opts(const tnqs_apply_opts& a, const tnqs_apply_opts& b) {
   return a.maxdim == b.maxdim && a.normalize_tensors == b.normalize_tensors && memcmp(&a.cutoff, &b.cutoff, sizeof(double)) == 0;
 }
@@ -1289,7 +1303,11 @@ static GateGraph* gate_graph_find(tnqs_ctx* c, int n, const int32_t* es, const i
   GateGraph* hit = nullptr;
   for (size_t i = 0; i < c->gate_graphs.size();) {
     GateGraph* gg = (GateGraph*)c->gate_graphs[i];
-    if (gg->version != c->state_version) { gate_graph_free(gg); c->gate_graphs.erase(c->gate_graphs.begin() + i); continue; }      // a shape or an address changed
+    if (gg->version != c->state_version) {                 // a shape or an address changed
+      gate_graph_free(gg); c->gate_graphs.erase(c->gate_graphs.begin() + i);
+      if (c->gate_graphs.empty()) c->gg_pool_off = 0;
+      continue;
+    }
     if (!hit && gg->n == n && same_opts(gg->o, o) && memcmp(gg->es.data(), es, n * sizeof(int)) == 0) {
       bool same = true;
       for (int k = 0; k < n && same; ++k) same = gg->fl[k] == (fl ? fl[k] : 0);
@@ -1353,7 +1371,12 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
       done = true;
     } else if (gg && gg->seen_ok >= 1 && !gg->no_graph) {  // ran eagerly with every gate committed: capture it now
       const long long l0 = c->launches;
-      if (!gg->stage) { gg->stage_size = (size_t)16 << 20; if (cudaHostAlloc((void**)&gg->stage, gg->stage_size, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); gg->stage = nullptr; gg->no_graph = true; } }
+      if (!gg->stage) {
+        // descriptor bytes of a batch: a few hundred per site job (measured 2.4 KB per gate at C2), rounded up generously
+        gg->stage_size = ((size_t)nb * 6144 + ((size_t)1 << 20) + 4095) / 4096 * 4096;
+        gg->stage = gate_graph_stage(c, gg->stage_size);
+        if (!gg->stage) gg->no_graph = true;
+      }
       if (gg->stage) {
         cudaGraph_t graph = nullptr;
         GateBatch gb; gb.c = c; gb.optimistic = true; gb.defer_collect = true;
@@ -1371,6 +1394,8 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
         if (ok_cap && gb.gates_staged) {
+          static const char* dbg = getenv("TNQS_DEBUG_QUEUE");
+          if (dbg) fprintf(stderr, "[tnqs] gate batch of %d captured: %zu of %zu staged bytes\n", nb, c->cap_stage_off, gg->stage_size);
           gg->nlaunch = c->launches - l0; c->launches = l0;          // the capture pass launched nothing
           gg->d_ok = gb.d_ok; gg->d_err = gb.d_err; gg->d_sv = gb.d_sv; gg->cap = gb.cap; gg->gates_staged = gb.gates_staged; gg->gates_bytes = gcount * sizeof(cplx);
           CU(cudaGraphLaunch(gg->exec, c->stream));
@@ -1392,7 +1417,7 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
       failed.swap(gb.failed);
       if (optimistic && gate_graphs_enabled(c) && failed.empty()) {
         if (!gg) {
-          if (c->gate_graphs.size() >= 12) { gate_graph_free((GateGraph*)c->gate_graphs.front()); c->gate_graphs.erase(c->gate_graphs.begin()); }
+          if (c->gate_graphs.size() >= 16) gate_graphs_drop(c);       // far more distinct batches than a layer has classes: start over
           gg = new GateGraph(); gg->es.assign(es + i0, es + i1); gg->fl.resize(nb);
           for (int k = 0; k < nb; ++k) gg->fl[k] = fl0 ? fl0[k] : 0;
           gg->o = o; gg->n = nb; gg->version = c->state_version;
