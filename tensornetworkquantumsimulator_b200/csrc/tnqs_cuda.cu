@@ -1275,7 +1275,13 @@ struct GateGraph {
   std::vector<int> es, fl; tnqs_apply_opts o; long long version = -1; int n = 0, cap = 0;
   cudaGraphExec_t exec = nullptr; char* stage = nullptr; size_t stage_size = 0; char* gates_staged = nullptr; size_t gates_bytes = 0;
   int* d_ok = nullptr; double* d_err = nullptr; double* d_sv = nullptr; long long nlaunch = 0; int seen_ok = 0; bool no_graph = false;
+  size_t arena_chunk0 = 0, arena_off0 = 0; char* arena_base0 = nullptr;      // where the bump arena stood when the batch was captured
 };
+// The temporaries of a captured batch are baked into it as addresses of the bump arena: a replay is only valid from the same arena
+// position (every entry point releases its temporaries before it returns, so this is the start of the arena in practice).
+static bool arena_at(const tnqs_ctx* c, const GateGraph* gg) {
+  return c->arena_chunk == gg->arena_chunk0 && c->arena_off == gg->arena_off0 && !c->arena.empty() && c->arena[0].base == gg->arena_base0;
+}
 // The upload stages of all captured batches of a handle are slices of ONE pinned pool (page-locking memory costs tens of
 // milliseconds per call on these hosts): bump-allocated, rewound when the last graph of the handle is gone.
 static void gate_graph_free(GateGraph* gg) {
@@ -1361,6 +1367,7 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
     const int32_t* fl0 = flips ? flips + i0 : nullptr;
     GateGraph* gg = (optimistic && gate_graphs_enabled(c)) ? gate_graph_find(c, nb, es + i0, fl0, o) : nullptr;
     bool done = false;
+    if (gg && gg->exec && !arena_at(c, gg)) gg = nullptr;   // (not from here: run it eagerly, leave the graph alone)
     if (gg && gg->exec) {                                  // replay
       static const char* dbg = getenv("TNQS_DEBUG_QUEUE");
       if (dbg) fprintf(stderr, "[tnqs] gate batch of %d: graph replay (%lld kernels)\n", nb, gg->nlaunch);
@@ -1381,11 +1388,12 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
         cudaGraph_t graph = nullptr;
         GateBatch gb; gb.c = c; gb.optimistic = true; gb.defer_collect = true;
         c->cap_stage = gg->stage; c->cap_stage_size = gg->stage_size; c->cap_stage_off = 0; c->cap_last = nullptr;
-        bool ok_cap = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        gg->arena_chunk0 = c->arena_chunk; gg->arena_off0 = c->arena_off; gg->arena_base0 = c->arena.empty() ? nullptr : c->arena[0].base;
+        bool ok_cap = gg->arena_base0 && cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         if (ok_cap) {
           c->capturing = true;
           try { gb.stage1(nb, es + i0, fl0, (const double*)(g + goff), o, nullptr); gb.stage2(nullptr, nullptr, nullptr, nullptr); }
-          catch (const TnqsError&) { ok_cap = false; }
+          catch (...) { ok_cap = false; }
           c->capturing = false;
           if (cudaStreamEndCapture(c->stream, &graph) != cudaSuccess || !graph) ok_cap = false;
         }
@@ -1416,6 +1424,7 @@ static void apply_2site_impl(tnqs_ctx* c, int n, const int32_t* es, const int32_
       gb.stage2(nullptr, r_out, e_out, s_out);
       failed.swap(gb.failed);
       if (optimistic && gate_graphs_enabled(c) && failed.empty()) {
+        if (!gg) gg = gate_graph_find(c, nb, es + i0, fl0, o);
         if (!gg) {
           if (c->gate_graphs.size() >= 16) gate_graphs_drop(c);       // far more distinct batches than a layer has classes: start over
           gg = new GateGraph(); gg->es.assign(es + i0, es + i1); gg->fl.resize(nb);
