@@ -1227,3 +1227,44 @@ def test_optimistic_gates_with_rank_deficient_messages_take_the_conventional_pas
     te = be.psi.tensors()
     for e in grp:
         assert rel(two_site(g, te, e), two_site(g, bo.network.tensors, e)) < 1e-7
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_random_circuits_on_random_states_follow_the_oracle(E, seed):
+    # randomised end-to-end check of every gate path at once (conventional, optimistic, optimistic + W, graph capture and replay, the
+    # fallbacks between them): a random lattice, ragged bond dimensions with some bonds already at maxdim, three layers of random
+    # one- and two-site gates with a cutoff that lets some ranks drop; bond dimensions exact, <Z> within 1e-8 after every layer
+    rs = np.random.default_rng(1000 + seed)
+    shapes = [G.named_grid((3, 3)), G.named_grid((4, 3)), G.named_hexagonal_lattice_graph(2, 1), G.named_grid((2, 2, 2)), G.named_comb_tree((3, 3)), G.named_grid((5, 2))]
+    g = shapes[seed % len(shapes)]
+    maxdim = int(rs.choice([4, 6, 8]))
+    dims = rs.integers(max(2, maxdim - 3), maxdim + 1, size=g.ne)
+    dims[rs.random(g.ne) < 0.5] = maxdim                                   # half of the bonds saturated
+    psi_o = ragged_state(g, dims, seed=seed)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    cutoff = float(rs.choice([1e-12, 1e-6, 1e-3]))
+    kw = dict(maxdim=maxdim, cutoff=cutoff, normalize_tensors=True)
+    groups = G.edge_color(g)
+    bo = O.update(O.BeliefPropagationCache(psi_o.copy()), **O.default_bp_update_kwargs(psi_o))
+    be = E.update(to_engine(psi_o, chi_cap=maxdim), inplace=True, **E.default_bp_update_kwargs(network_of(E, psi_o, maxdim)))
+    names = ["Rxx", "Ryy", "Rzz"]
+    for layer in range(3):
+        circ = [("Rx", [g.names[v]], float(rs.uniform(0, 1))) for v in range(g.nv)]
+        for grp in groups:
+            nm = names[int(rs.integers(3))]
+            th = float(rs.uniform(0.1, 0.6))
+            for e in grp:
+                a, b = int(g.esrc[e]), int(g.edst[e])
+                vs = [g.names[b], g.names[a]] if rs.random() < 0.3 else [g.names[a], g.names[b]]
+                circ.append((nm, vs, th))
+        bo, errs_o = O.apply_gates(circ, bo, apply_kwargs=kw)
+        be, errs_e = E.apply_gates(circ, be, apply_kwargs=kw, inplace=True)
+        assert list(be.psi.bond_dims()) == list(bo.network.bond_dims()), f"seed {seed} layer {layer}"
+        assert np.allclose(errs_e, errs_o, rtol=1e-5, atol=1e-12), f"seed {seed} layer {layer}"
+        for v in range(g.nv):
+            assert abs(E.expect(be, ("Z", [g.names[v]])) - O.expect(bo, ("Z", [g.names[v]]))) < EXP_TOL, f"seed {seed} layer {layer} vertex {v}"
+
+
+def network_of(E, psi_o, cap):
+    return E.TensorNetworkState.from_arrays(psi_o.g, psi_o.tensors, chi_cap=cap)
