@@ -661,6 +661,10 @@ __global__ void k_xchg_unpack(const XchgDesc* __restrict__ descs) {
 // needs only one site); stage2 = theta, gate, SVD + truncation, reabsorb, T' = Q R', normalise, commit.  Between the two
 // a vertex-partitioned run exchanges the R factors of gates that cross a cut (`remote`), so each side finishes its own
 // half with an identical, deterministic theta/SVD.  All temporaries live until stage2 returns.
+// Three ways through it (apply_2site_impl chooses per chunk): conventional (the host reads the CholeskyQR2 flags and the kept ranks,
+// then allocates and commits); optimistic (saturated bonds: nothing is read back until the end, the device commits per gate - and with
+// square R factors the W path replaces reabsorption, Q R' and the permute back by one in-place product); and the optimistic chain
+// replayed from a CUDA graph (GateGraph below).  Gates that fail the optimistic assumptions are redone conventionally.
 struct GateBatch {
   struct SiteJob {
     int v, e, jb, d, chib; long long Po; int nc, q; std::vector<int> outer;   // outer: bond leg indices ascending
