@@ -170,6 +170,21 @@ int32_t tnqs_expect_2site_nn(tnqs_ctx* ctx, int32_t n, const int32_t* e, const d
  * path i = path_v[path_off[i] .. path_off[i+1]) (consecutive vertices share an edge), O1 acts on its first vertex, O2 on
  * its last; ops and out as in tnqs_expect_2site_nn. */
 int32_t tnqs_expect_path(tnqs_ctx* ctx, int32_t n, const int32_t* path_off, const int32_t* path_v, const double* ops, double* out);
+/* replaces: weights(bpc, egs) / weight(bpc, eg) (src/MessagePassing/loopcorrection.jl:81-96), the terms of
+ * loopcorrected_partitionfunction (:3-16).  Subgraph i is induced by the edges sub_edges[sub_off[i] .. sub_off[i+1]) (no
+ * duplicates; it may be disconnected: the weight is then the product over its components).  weights[i] (cplx) = the
+ * contraction of the factors of its vertices with the messages that enter them along every other edge and, on each of its
+ * own edges, the antiprojector 1 - message(e) (x) message(reverse e) (:49-60).  The handle must hold the RESCALED cache
+ * (tnqs_rescale: edge and vertex scalars 1), as the reference's caller does (:8).  Evaluated as message updates with
+ * substituted messages over a spanning tree of the subgraph; cost grows as prod over its independent cycles of (chi^2 + 1):
+ * TNQS_ERR_UNSUPPORTED beyond 2^22 tree contractions per subgraph.  Not available on a partitioned handle. */
+int32_t tnqs_loop_weights(tnqs_ctx* ctx, int32_t nsub, const int32_t* sub_off, const int32_t* sub_edges, double* weights);
+/* replaces: the contraction inside loop_correlation (src/MessagePassing/beliefpropagationcache.jl:145-174).  walk_v =
+ * the len >= 3 distinct vertices of a closed walk v_0 -> v_1 -> .. -> v_{len-1} -> v_0; the bond of the last step is cut open.
+ * out = chi^2 x chi^2 cplx, column-major: column (b, b') = the environment that arrives at the open leg of v_{len-1} when the
+ * leg of v_0 carries the matrix unit |b)(b'| (ket index fastest in rows and columns).  loop_correlation is
+ * 1 - |lambda_1| / sum |lambda_i| of its eigenvalues (:175-178), which the caller takes on the host. */
+int32_t tnqs_loop_transfer(tnqs_ctx* ctx, int32_t len, const int32_t* walk_v, double* out);
 /* vertex_scalar (src/MessagePassing/abstractbeliefpropagationcache.jl:21-27) for all vertices, [nv] cplx;
  * edge_scalar (src/MessagePassing/beliefpropagationcache.jl:38-40) for all edges, [ne] cplx. */
 int32_t tnqs_vertex_scalars(tnqs_ctx* ctx, double* out);

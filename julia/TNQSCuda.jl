@@ -108,6 +108,10 @@ tnqs_expect_2site_nn(ctx, n, e, ops, out) =
 tnqs_expect_path(ctx, n, path_off, path_v, ops, out) =
     ccall((:tnqs_expect_path, LIB), Int32, (Ctx, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{ComplexF64}, Ptr{ComplexF64}),
           ctx, n, path_off, path_v, ops, out)
+tnqs_loop_weights(ctx, nsub, sub_off, sub_edges, weights) =
+    ccall((:tnqs_loop_weights, LIB), Int32, (Ctx, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{ComplexF64}), ctx, nsub, sub_off, sub_edges, weights)
+tnqs_loop_transfer(ctx, len, walk_v, out) =
+    ccall((:tnqs_loop_transfer, LIB), Int32, (Ctx, Int32, Ptr{Int32}, Ptr{ComplexF64}), ctx, len, walk_v, out)
 tnqs_vertex_scalars(ctx, out) = ccall((:tnqs_vertex_scalars, LIB), Int32, (Ctx, Ptr{ComplexF64}), ctx, out)
 tnqs_edge_scalars(ctx, out) = ccall((:tnqs_edge_scalars, LIB), Int32, (Ctx, Ptr{ComplexF64}), ctx, out)
 tnqs_rescale(ctx) = ccall((:tnqs_rescale, LIB), Int32, (Ctx,), ctx)
@@ -444,6 +448,41 @@ function Base.truncate(c::CudaBeliefPropagationCache; maxdim, cutoff = nothing, 
     seq = _edge_seq(c, forest_cover_edge_sequence(c.g))
     check(c.ctx, tnqs_truncate(c.ctx, length(groups), group_off, group_edges, a, seq, length(seq), b))
     return _refresh_binds!(c)
+end
+
+# ---- loop corrections (src/MessagePassing/loopcorrection.jl): the generalised loops come from NamedGraphs as in the reference
+# (:11-12), their weights from the device (one call), the series is summed here (:13-15)
+function loop_weights(c::CudaBeliefPropagationCache, egs)                      # weights(bpc, egs), loopcorrection.jl:81-96
+    undirected = Dict{Any, Int32}()
+    for (k, e) in enumerate(c.es)
+        undirected[(src(e), dst(e))] = Int32(k - 1); undirected[(dst(e), src(e))] = Int32(k - 1)
+    end
+    sub_off = Int32[0]; sub_edges = Int32[]
+    for eg in egs
+        append!(sub_edges, Int32[undirected[(src(e), dst(e))] for e in edges(eg)]); push!(sub_off, length(sub_edges))
+    end
+    ws = zeros(ComplexF64, length(egs))
+    check(c.ctx, tnqs_loop_weights(c.ctx, length(egs), sub_off, sub_edges, ws))
+    return ws
+end
+
+function TN.loopcorrected_partitionfunction(c::CudaBeliefPropagationCache, max_configuration_size::Integer)    # :3-16
+    zbp = partitionfunction(c)
+    egs = NamedGraphs.edgeinduced_subgraphs_no_leaves(c.g, max_configuration_size)
+    isempty(egs) && return zbp
+    return zbp * (1 + sum(loop_weights(rescale(c), egs)))
+end
+
+# loop_correlation (src/MessagePassing/beliefpropagationcache.jl:145-179): the transfer matrix of the closed walk comes from the
+# device, its eigenvalues are taken here
+function TN.loop_correlation(c::CudaBeliefPropagationCache, loop::Vector{<:NamedEdge}, target_e::NamedEdge)
+    is_tree(c.g) && return 0
+    walk = Int32[vertex_id(c, src(e)) for e in vcat(loop, [target_e])]
+    χ = Int(bond_dims(c)[directed_id(c, target_e) ÷ 2 + 1])
+    t = Matrix{ComplexF64}(undef, χ^2, χ^2)
+    check(c.ctx, tnqs_loop_transfer(c.ctx, length(walk), walk, t))
+    λs = reverse(sort(eigvals(t); by = abs))
+    return 1 - abs(λs[1]) / sum(abs.(λs))
 end
 
 function entanglement(c::CudaBeliefPropagationCache, e)                        # src/symmetric_gauge.jl:85-114

@@ -31,7 +31,8 @@ import numpy as np
 
 from tensornetworkquantumsimulator_b200 import gates as _gates
 from tensornetworkquantumsimulator_b200 import rng as _rng
-from tensornetworkquantumsimulator_b200.graphs import Graph, forest_cover_edge_sequence, edge_color, steiner_tree
+from tensornetworkquantumsimulator_b200.graphs import (Graph, forest_cover_edge_sequence, edge_color, steiner_tree,
+                                                       edgeinduced_subgraphs_no_leaves, cycle_walks)
 
 EPS = float(np.finfo(np.float64).eps)
 DEFAULT_BP_MAXITER = 25          # src/MessagePassing/beliefpropagationcache.jl:108
@@ -321,9 +322,14 @@ def rescale_messages(bpc: BeliefPropagationCache, edges: Optional[Sequence[int]]
 
 
 def rescale_vertices(bpc: BeliefPropagationCache, vertices: Optional[Sequence[int]] = None) -> None:
-    """In place; src/MessagePassing/beliefpropagationcache.jl:87-106 (TensorNetworkState branch)."""
+    """In place; src/MessagePassing/beliefpropagationcache.jl:87-106 (TensorNetworkState branch).  A bilinear form has no rule
+    there (the reference raises, :102-103): its ket layer is divided by the vertex scalar, which makes the scalar 1 - what the
+    TensorNetwork branch (:100-101) does up to its sign factor, and what the loop series needs."""
     for v in (range(bpc.g.nv) if vertices is None else vertices):
         vn = vertex_scalar(bpc, v)
+        if bpc.bra is not None:
+            bpc.network.tensors[v] = bpc.network.tensors[v] * (1.0 / complex(vn))
+            continue
         s = _csign(vn) if vn.imag == 0 else 1.0
         bpc.network.tensors[v] = bpc.network.tensors[v] * (s * (1.0 / np.sqrt(complex(vn))))
 
@@ -827,6 +833,157 @@ def contract_bp(g: Graph, tensors: Sequence[np.ndarray], maxiter: Optional[int] 
 def contract_exact(g: Graph, tensors: Sequence[np.ndarray]) -> complex:
     """Full contraction of a small single-layer network (independent ground truth)."""
     return complex(to_statevector(TensorNetworkState(g, [t[None, ...] for t in tensors]))[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# loop corrections (src/MessagePassing/loopcorrection.jl, loop_correlation(s): beliefpropagationcache.jl:144-197)
+# ---------------------------------------------------------------------------------------------
+def _contract_network(tensors: List[np.ndarray], labels: List[List[int]]) -> np.ndarray:
+    """Greedy pairwise contraction of a closed or open network: labels[i] names the axes of tensors[i]; a label that appears
+    twice is summed.  The pair with the smallest result goes first (the reference asks for a greedy sequence too:
+    loopcorrection.jl:88).  Returns the tensor over the labels that are left, in ascending label order."""
+    ts = [(np.asarray(t), list(l)) for t, l in zip(tensors, labels)]
+    while len(ts) > 1:
+        best = None
+        for i in range(len(ts)):
+            for j in range(i + 1, len(ts)):
+                shared = set(ts[i][1]) & set(ts[j][1])
+                if not shared and best is not None:
+                    continue
+                size = 1
+                for t, l in (ts[i], ts[j]):
+                    for ax, lab in enumerate(l):
+                        if lab not in shared:
+                            size *= t.shape[ax]
+                key = (0 if shared else 1, size)
+                if best is None or key < best[0]:
+                    best = (key, i, j, shared)
+        _, i, j, shared = best
+        (a, la), (b, lb) = ts[i], ts[j]
+        shared = sorted(shared)
+        out = np.tensordot(a, b, axes=([la.index(x) for x in shared], [lb.index(x) for x in shared]))
+        lout = [x for x in la if x not in shared] + [x for x in lb if x not in shared]
+        ts = [ts[k] for k in range(len(ts)) if k not in (i, j)] + [(out, lout)]
+    t, l = ts[0]
+    return np.transpose(t, np.argsort(l)) if l else t
+
+
+def loop_weight(bpc: BeliefPropagationCache, edges: Sequence[int]) -> complex:
+    """weight(bpc, eg) (loopcorrection.jl:81-91) for the subgraph induced by `edges`: the factors of its vertices, the messages
+    entering them along every edge that is not in the subgraph, and on every edge of the subgraph the antiprojector
+    delta - message(e) (x) message(reverse e) over the doubled (ket, bra) bond (loopcorrection.jl:49-60).  The cache is expected to
+    be rescaled (edge and vertex scalars 1)."""
+    g = bpc.g
+    es = sorted(set(int(e) for e in edges))
+    vs = sorted(set(int(x) for e in es for x in (g.esrc[e], g.edst[e])))
+    nlab = [0]
+
+    def fresh() -> int:
+        nlab[0] += 1
+        return nlab[0] - 1
+
+    ket_lab = {(v, e): fresh() for v in vs for e in g.incident[v]}
+    bra_lab = {(v, e): fresh() for v in vs for e in g.incident[v]}
+    site_lab = {v: fresh() for v in vs}
+    ts, ls = [], []
+    for v in vs:
+        ts.append(bpc.network.tensors[v]); ls.append([site_lab[v]] + [ket_lab[(v, e)] for e in g.incident[v]])
+        ts.append(bpc.bra_tensor(v).conj()); ls.append([site_lab[v]] + [bra_lab[(v, e)] for e in g.incident[v]])
+        for e in g.incident[v]:
+            if e not in es:
+                ts.append(message(bpc, g.dedge(g.other(e, v), v))); ls.append([ket_lab[(v, e)], bra_lab[(v, e)]])
+    for e in es:
+        a, b = int(g.esrc[e]), int(g.edst[e])
+        m_ab, m_ba = message(bpc, 2 * e), message(bpc, 2 * e + 1)          # a -> b enters b; b -> a enters a
+        n, nb = m_ab.shape
+        ap = np.einsum("ik,jl->ijkl", np.eye(n), np.eye(nb)) - np.einsum("ij,kl->ijkl", m_ab, m_ba)
+        ts.append(ap); ls.append([ket_lab[(b, e)], bra_lab[(b, e)], ket_lab[(a, e)], bra_lab[(a, e)]])
+    return complex(_contract_network(ts, ls))
+
+
+def loop_weights(bpc: BeliefPropagationCache, egs: Sequence[Sequence[int]]) -> np.ndarray:
+    """loopcorrection.jl:94-96."""
+    return np.array([loop_weight(bpc, eg) for eg in egs], dtype=np.complex128)
+
+
+def loopcorrected_partitionfunction(bpc: BeliefPropagationCache, max_configuration_size: int) -> complex:
+    """loopcorrection.jl:3-16: Z_bp * (1 + sum of the weights of every leafless edge-induced subgraph of at most
+    max_configuration_size edges), weights taken on the rescaled cache."""
+    zbp = partitionfunction(bpc)
+    bpc = rescale(bpc)
+    egs = edgeinduced_subgraphs_no_leaves(bpc.g, int(max_configuration_size))
+    if not egs:
+        return zbp
+    return zbp * (1 + complex(np.sum(loop_weights(bpc, egs))))
+
+
+def norm_sqr_loopcorrected(psi: TensorNetworkState, max_configuration_size: int, maxiter: Optional[int] = None,
+                           tolerance: Optional[float] = None) -> complex:
+    """norm_sqr(psi; alg = "loopcorrections", max_configuration_size) (src/norm_sqr.jl:56-76)."""
+    kw = default_bp_update_kwargs(psi)
+    bpc = update(BeliefPropagationCache(psi.copy()), maxiter=maxiter if maxiter is not None else kw["maxiter"],
+                 tolerance=tolerance if tolerance is not None else kw["tolerance"])
+    return loopcorrected_partitionfunction(bpc, max_configuration_size)
+
+
+def loop_transfer_matrix(bpc: BeliefPropagationCache, loop: Sequence[int], target: int) -> np.ndarray:
+    """The matrix whose spectrum loop_correlation looks at (beliefpropagationcache.jl:145-179): `loop` + [`target`] are the
+    directed edges (ids k = 2e + dir) of a closed walk v0 -> v1 -> .. -> v0 whose last step is `target`; the factors of its
+    vertices are contracted with every message that enters from outside, with the bond of `target` cut open at its source:
+    rows = the (ket, bra) pair the source keeps, columns = the pair on the far side (ket index fastest in both)."""
+    g = bpc.g
+    ks = [int(k) for k in loop] + [int(target)]
+    es = [k // 2 for k in ks]
+    vs = [g.dsrc(k) for k in ks]
+    if [g.ddst(k) for k in ks] != vs[1:] + vs[:1] or len(set(vs)) != len(vs):
+        raise ValueError("loop + target must be a simple closed walk")
+    nlab = [0]
+
+    def fresh() -> int:
+        nlab[0] += 1
+        return nlab[0] - 1
+
+    et = es[-1]
+    src = vs[-1]
+    chi, chib = message(bpc, target).shape
+    # open labels first so that they come out as the leading axes: (far ket, far bra, src ket, src bra)
+    far_k, far_b, src_k, src_b = fresh(), fresh(), fresh(), fresh()
+    bond_k = {e: fresh() for e in es[:-1]}
+    bond_b = {e: fresh() for e in es[:-1]}
+    ts, ls = [], []
+    for v in vs:
+        sl = fresh()
+        lk, lb = [sl], [sl]
+        for e in g.incident[v]:
+            if e == et:
+                lk.append(src_k if v == src else far_k); lb.append(src_b if v == src else far_b)
+            elif e in bond_k:
+                lk.append(bond_k[e]); lb.append(bond_b[e])
+            else:
+                a, b = fresh(), fresh()
+                lk.append(a); lb.append(b)
+                ts.append(message(bpc, g.dedge(g.other(e, v), v))); ls.append([a, b])
+        ts.append(bpc.network.tensors[v]); ls.append(lk)
+        ts.append(bpc.bra_tensor(v).conj()); ls.append(lb)
+    t = _contract_network(ts, ls)                       # axes (far ket, far bra, src ket, src bra)
+    t = np.transpose(t, (2, 3, 0, 1))
+    return t.reshape(chi * chib, chi * chib, order="F")
+
+
+def loop_correlation(bpc: BeliefPropagationCache, loop: Sequence[int], target: int) -> float:
+    """beliefpropagationcache.jl:145-179: 1 - |lambda_1| / sum |lambda_i| of the loop's transfer matrix; 0 on a tree."""
+    if bpc.g.is_tree():
+        return 0.0
+    lam = np.abs(np.linalg.eigvals(loop_transfer_matrix(bpc, loop, target)))
+    return float(1.0 - lam.max() / lam.sum())
+
+
+def loop_correlations(bpc: BeliefPropagationCache, smallest_loop_size: int) -> List[float]:
+    """beliefpropagationcache.jl:182-192: one value per simple cycle of at most `smallest_loop_size` edges."""
+    out = []
+    for loop, target in cycle_walks(bpc.g, smallest_loop_size):
+        out.append(loop_correlation(bpc, loop, target))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

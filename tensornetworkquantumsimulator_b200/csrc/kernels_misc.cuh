@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(1024) k_norm2(const Norm2Desc* __restrict__ de
 // ---- x *= factor (complex); factor = f(*scalar) ----------------------------------------------------------------
 // mode 0: 1/sqrt(norm2[0]) (Frobenius normalisation, simple_update.jl:63-65)
 // mode 1: rescale_vertices!: s / sqrt(vn), vn = scalar[0] + i scalar[1], s = sign(vn) if real else 1 (bpcache.jl:87-106)
+// mode 0: x / sqrt(scalar[0]) (real norm^2); 1: x * sign / sqrt(complex scalar) (rescale_vertices! of a state); 2: x / complex scalar
 struct ScaleDesc { cplx* x; long long n; const double* scalar; int mode; const int* commit = nullptr; };     // commit: see PermDesc
 __global__ void __launch_bounds__(256) k_scale(const ScaleDesc* __restrict__ descs) {
   const ScaleDesc d = descs[blockIdx.y];
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(256) k_scale(const ScaleDesc* __restrict__ des
     cplx sg = cmake(1, 0);
     if (im == 0.0) sg = cmake(re > 0 ? 1.0 : (re < 0 ? -1.0 : 0.0), 0.0);
     f = cmul(sg, inv);
+    if (d.mode == 2) { const double m2 = re * re + im * im; f = cmake(re / m2, -im / m2); }     // 1 / scalar
   }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += (long long)gridDim.x * blockDim.x)
     d.x[i] = cmul(d.x[i], f);
@@ -238,4 +240,26 @@ __global__ void __launch_bounds__(256) k_fill_random(cplx* x, long long n, unsig
     sincos(2.0 * 3.14159265358979323846 * u2, &s, &c);
     x[i] = cmake(r * c, r * s);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Loop corrections (loop_corrections.cuh).
+// k_antiproject: X <- X - mf * (mb | X) with (a | b) = sum_{i,j} a[i,j] b[i,j]: the antiprojector 1 - |m_e)(m_rev| of
+// src/MessagePassing/loopcorrection.jl:49-60 applied to an environment that crosses the edge (mf = the BP message travelling the
+// same way as X, mb = the one travelling against it).  One CTA (128 threads) per item; dense n x n blocks, nn = n * n.
+// ---------------------------------------------------------------------------------------------------------------
+struct AntiProjDesc { cplx* x; const cplx* mf; const cplx* mb; int nn; };
+__global__ void __launch_bounds__(128) k_antiproject(const AntiProjDesc* __restrict__ descs) {
+  const AntiProjDesc d = descs[blockIdx.x];
+  __shared__ double red[8];
+  double re = 0, im = 0;
+  for (int i = threadIdx.x; i < d.nn; i += blockDim.x) { const cplx p = cmul(d.mb[i], d.x[i]); re += p.x; im += p.y; }
+  re = block_sum(re, red); im = block_sum(im, red);
+  const cplx t = cmake(re, im);
+  for (int i = threadIdx.x; i < d.nn; i += blockDim.x) { const cplx p = cmul(t, d.mf[i]); d.x[i] = cmake(d.x[i].x - p.x, d.x[i].y - p.y); }
+}
+// the n x n identity into a zeroed buffer (rows of it are the chi x chi matrix units, n = chi^2)
+__global__ void k_unit_diagonal(cplx* u, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) u[i + i * n] = cmake(1, 0);
 }

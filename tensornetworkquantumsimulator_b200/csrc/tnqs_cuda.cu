@@ -1779,6 +1779,25 @@ extern "C" int32_t tnqs_expect_path(tnqs_ctx* c, int32_t n, const int32_t* path_
   API_END(c)
 }
 
+#include "loop_corrections.cuh"
+
+extern "C" int32_t tnqs_loop_weights(tnqs_ctx* c, int32_t nsub, const int32_t* sub_off, const int32_t* sub_edges, double* weights) {
+  API_BEGIN(c)
+  REQUIRE(nsub >= 0 && (nsub == 0 || (sub_off && sub_edges && weights)), TNQS_ERR_INVALID_ARG, "tnqs_loop_weights: null argument");
+  for (int i = 0; i < nsub; ++i) REQUIRE(sub_off[i + 1] >= sub_off[i], TNQS_ERR_INVALID_ARG, "tnqs_loop_weights: offsets must not decrease");
+  if (nsub > 0) loop_weights_impl(c, nsub, sub_off, sub_edges, weights);
+  c->release_temps();
+  API_END(c)
+}
+
+extern "C" int32_t tnqs_loop_transfer(tnqs_ctx* c, int32_t len, const int32_t* walk_v, double* out) {
+  API_BEGIN(c)
+  REQUIRE(walk_v && out, TNQS_ERR_INVALID_ARG, "tnqs_loop_transfer: null argument");
+  loop_transfer_impl(c, len, walk_v, out);
+  c->release_temps();
+  API_END(c)
+}
+
 static void vertex_scalars_impl(tnqs_ctx* c, cplx* d_vs /* [nv] device */) {
   std::vector<int> vs(c->nv);
   for (int v = 0; v < c->nv; ++v) vs[v] = v;
@@ -1820,6 +1839,9 @@ extern "C" int32_t tnqs_edge_scalars(tnqs_ctx* c, double* out) {
   API_END(c)
 }
 
+// With a bra attached (bilinear form) only the ket layer can be scaled: it is divided by the vertex scalar itself, the rule
+// rescale_vertices! applies to single-layer networks (beliefpropagationcache.jl:100-101; for a BilinearForm the reference has
+// no rule and raises, :102-103), so that every vertex scalar becomes 1 as the loop series needs.
 extern "C" int32_t tnqs_rescale(tnqs_ctx* c) {
   API_BEGIN(c)
   if (c->ne) LAUNCH(c, TNQS_KC_MISC, k_rescale_messages, c->ne, 256, 0, c->msg_cur, c->slot, c->d_chi);
@@ -1827,7 +1849,7 @@ extern "C" int32_t tnqs_rescale(tnqs_ctx* c) {
   vertex_scalars_impl(c, d_vs);
   std::vector<ScaleDesc> sd(c->nv);
   long long maxn = 1;
-  for (int v = 0; v < c->nv; ++v) { sd[v].x = c->site[v]; sd[v].n = c->site_n[v]; sd[v].scalar = (const double*)(d_vs + v); sd[v].mode = 1; maxn = std::max(maxn, c->site_n[v]); }
+  for (int v = 0; v < c->nv; ++v) { sd[v].x = c->site[v]; sd[v].n = c->site_n[v]; sd[v].scalar = (const double*)(d_vs + v); sd[v].mode = c->bra ? 2 : 1; maxn = std::max(maxn, c->site_n[v]); }
   ScaleDesc* dsd = c->upload(sd);
   LAUNCH(c, TNQS_KC_MISC, k_scale, dim3((unsigned)std::min<long long>((maxn + 255) / 256, 1024), c->nv), 256, 0, dsd);
   c->sync();

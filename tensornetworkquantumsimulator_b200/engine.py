@@ -5,7 +5,9 @@ Same names, argument meaning and error behaviour as the Julia API it stands in f
 `BeliefPropagationCache`, `update`, `message(s)`, `partitionfunction`, `rescale`
 (src/MessagePassing/*.jl), `apply_gates` / `apply_circuit` (src/Apply/apply_gates.jl:13-133),
 `expect(...; alg="bp")` (src/expect.jl:53-136), `truncate` (src/truncate.jl:12-38,74-79),
-`symmetric_gauge`, `gauge_and_scale`, `entanglement` (src/symmetric_gauge.jl).
+`symmetric_gauge`, `gauge_and_scale`, `entanglement` (src/symmetric_gauge.jl),
+`loopcorrected_partitionfunction`, `norm_sqr` / `inner` with alg="loopcorrections" (src/MessagePassing/loopcorrection.jl,
+src/norm_sqr.jl:56-76, src/inner.jl:67-86), `loop_correlation(s)` (src/MessagePassing/beliefpropagationcache.jl:144-197).
 
 Non-mutating functions copy on entry and return new objects like the reference (`copy(bpc)`,
 apply_gates.jl:51, abstractbeliefpropagationcache.jl:206); pass `inplace=True` to skip the device copy.
@@ -22,7 +24,8 @@ import numpy as np
 
 from . import gates as _gates
 from . import lib as _lib
-from .graphs import Graph, edge_color as _edge_color, forest_cover_edge_sequence, steiner_tree as _steiner_tree, tree_schedule as _tree_schedule
+from .graphs import (Graph, edge_color as _edge_color, forest_cover_edge_sequence, steiner_tree as _steiner_tree, tree_schedule as _tree_schedule,
+                     edgeinduced_subgraphs_no_leaves as _subgraphs_no_leaves, cycle_walks as _cycle_walks)
 from .lib import ApplyOpts, BpOpts, TnqsError, check, i32, ptr_f64, ptr_i32, ptr_i64
 
 DEFAULT_BP_MAXITER = 25      # src/MessagePassing/beliefpropagationcache.jl:108
@@ -694,12 +697,17 @@ def bilinear_cache(psi: TensorNetworkState, phi: TensorNetworkState, delta_defau
     return bpc
 
 
-def inner(psi: TensorNetworkState, phi: TensorNetworkState, alg: str = "bp", cache_update_kwargs: Optional[dict] = None) -> complex:
-    """inner(psi, phi; alg = "bp") = <phi|psi> by BP on the bilinear form (src/inner.jl:82-86): exact on trees."""
-    if alg != "bp":
-        raise ValueError("Only alg='bp' is on the CUDA path")
+def inner(psi: TensorNetworkState, phi: TensorNetworkState, alg: str = "bp", cache_update_kwargs: Optional[dict] = None,
+          max_configuration_size: Optional[int] = None) -> complex:
+    """inner(psi, phi; alg = "bp" | "loopcorrections") = <phi|psi> by BP on the bilinear form (src/inner.jl:67-86): exact on trees;
+    with loop corrections the partition function is multiplied by 1 + the weights of the generalised loops of at most
+    max_configuration_size edges."""
+    if alg not in ("bp", "loopcorrections"):
+        raise ValueError("Only alg='bp' and alg='loopcorrections' are on the CUDA path")
     kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(psi)
     bpc = update(bilinear_cache(psi, phi, delta_default=True), inplace=True, **kw)
+    if alg == "loopcorrections":
+        return loopcorrected_partitionfunction(bpc, _need_size(max_configuration_size))
     return partitionfunction(bpc)
 
 
@@ -727,12 +735,84 @@ def contract(tensors: Sequence[np.ndarray], g: Graph, alg: str = "bp", bp_update
     return partitionfunction(bpc)
 
 
-def norm_sqr(x, alg: str = "bp", cache_update_kwargs: Optional[dict] = None) -> complex:
-    """BP norm (src/norm_sqr.jl:56-76): partition function of the updated cache."""
+def norm_sqr(x, alg: str = "bp", cache_update_kwargs: Optional[dict] = None, max_configuration_size: Optional[int] = None) -> complex:
+    """norm_sqr(x; alg = "bp" | "loopcorrections") (src/norm_sqr.jl:56-76): partition function of the updated cache, with loop
+    corrections up to max_configuration_size edges for the latter."""
+    if alg not in ("bp", "loopcorrections"):
+        raise ValueError("Only alg='bp' and alg='loopcorrections' are on the CUDA path")
     if isinstance(x, TensorNetworkState):
         kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(x)
         x = update(BeliefPropagationCache(x.copy(), _share=True), inplace=True, **kw)
+    if alg == "loopcorrections":
+        return loopcorrected_partitionfunction(x, _need_size(max_configuration_size))
     return partitionfunction(x)
+
+
+def norm(x, alg: str = "bp", **kwargs) -> complex:
+    """LinearAlgebra.norm(x; alg, ..) = sqrt(norm_sqr) (src/norm_sqr.jl:90-91)."""
+    return complex(np.sqrt(complex(norm_sqr(x, alg=alg, **kwargs))))
+
+
+def _need_size(max_configuration_size: Optional[int]) -> int:
+    if max_configuration_size is None:
+        raise ValueError("alg='loopcorrections' needs max_configuration_size")
+    return int(max_configuration_size)
+
+
+def loop_weights(bpc: BeliefPropagationCache, egs: Sequence[Sequence[int]]) -> np.ndarray:
+    """weights(bpc, egs) (src/MessagePassing/loopcorrection.jl:81-96): one complex number per edge-induced subgraph (tuples of
+    edge ids) of the RESCALED cache.  On the device each weight is a signed sum of tree contractions of BP message updates with
+    substituted messages (csrc/loop_corrections.cuh)."""
+    egs = [tuple(int(e) for e in eg) for eg in egs]
+    if not egs:
+        return np.zeros(0, dtype=np.complex128)
+    off = np.zeros(len(egs) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(eg) for eg in egs])
+    edges = np.array([e for eg in egs for e in eg], dtype=np.int32)
+    out = np.zeros(2 * len(egs), dtype=np.float64)
+    check(bpc.psi._h.ptr, _lib.load().tnqs_loop_weights(bpc.psi._h.ptr, len(egs), ptr_i32(off), ptr_i32(edges), ptr_f64(out)))
+    return out.view(np.complex128)
+
+
+def loopcorrected_partitionfunction(bpc: BeliefPropagationCache, max_configuration_size: int) -> complex:
+    """loopcorrected_partitionfunction(bp_cache, max_configuration_size) (src/MessagePassing/loopcorrection.jl:3-16):
+    Z_bp (1 + sum of the weights of every leafless edge-induced subgraph of at most that many edges), the weights taken on a
+    rescaled copy of the cache."""
+    zbp = partitionfunction(bpc)
+    egs = _subgraphs_no_leaves(bpc.g, int(max_configuration_size))
+    if not egs:
+        return zbp
+    ws = loop_weights(rescale(bpc), egs)
+    return zbp * (1 + complex(np.sum(ws)))
+
+
+def loop_correlation(bpc: BeliefPropagationCache, loop: Sequence[int], target_e: int) -> float:
+    """loop_correlation(bpc, loop, target_e) (src/MessagePassing/beliefpropagationcache.jl:145-179): `loop` + [target_e] are the
+    directed edge ids (k = 2e + dir) of a simple closed walk that target_e closes; 1 - |lambda_1| / sum |lambda_i| over the
+    spectrum of the walk's transfer matrix (contracted on the device; the eigenvalues of the chi^2 x chi^2 matrix are taken on the
+    host, as the reference does with LinearAlgebra.eigvals)."""
+    g = bpc.g
+    if g.is_tree():
+        return 0.0
+    ks = [int(k) for k in loop] + [int(target_e)]
+    vs = [g.dsrc(k) for k in ks]
+    if [g.ddst(k) for k in ks] != vs[1:] + vs[:1]:
+        raise ValueError("loop + [target_e] must be a closed walk")
+    walk = np.array(vs, dtype=np.int32)
+    n2 = int(bpc.psi.bond_dims()[ks[-1] // 2]) ** 2
+    out = np.zeros(2 * n2 * n2, dtype=np.float64)
+    check(bpc.psi._h.ptr, _lib.load().tnqs_loop_transfer(bpc.psi._h.ptr, len(vs), ptr_i32(walk), ptr_f64(out)))
+    lam = np.abs(np.linalg.eigvals(out.view(np.complex128).reshape(n2, n2, order="F")))
+    return float(1.0 - lam.max() / lam.sum())
+
+
+def loop_correlations(x, smallest_loop_size: int, bp_update_kwargs: Optional[dict] = None) -> List[float]:
+    """loop_correlations (beliefpropagationcache.jl:182-197): one value per simple cycle of at most smallest_loop_size edges; a
+    state is wrapped in an updated cache first."""
+    if isinstance(x, TensorNetworkState):
+        kw = bp_update_kwargs if bp_update_kwargs is not None else default_bp_update_kwargs(x)
+        x = update(BeliefPropagationCache(x.copy(), _share=True), inplace=True, **kw)
+    return [loop_correlation(x, loop, target) for loop, target in _cycle_walks(x.g, int(smallest_loop_size))]
 
 
 def rescale(bpc: BeliefPropagationCache, inplace: bool = False) -> BeliefPropagationCache:

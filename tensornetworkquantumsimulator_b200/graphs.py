@@ -134,7 +134,7 @@ def named_hexagonal_lattice_graph(m: int, n: int) -> Graph:
     row_edges = [((i, j), (i + 1, j)) for i in cols[:n] for j in rows if i % 2 == j % 2]
     nodes = {(i, j) for i in cols for j in rows}
     nodes.discard((0, M))
-    nodes.discard((n, M * ((n + 1) % 2)))
+    nodes.discard((n, M * (n % 2)))
     names = sorted(nodes)
     edges = [(a, b) for a, b in col_edges + row_edges if a in nodes and b in nodes]
     names = [(a + 1, b + 1) for a, b in names]
@@ -426,3 +426,113 @@ def _bipartition(g: Graph):
                 elif side[w] == side[u]:
                     return None
     return side
+
+
+# ---------------------------------------------------------------------------------------------
+# generalised loops (loop corrections)
+# ---------------------------------------------------------------------------------------------
+def simple_cycles_limited_length(g: Graph, max_length: int) -> List[Tuple[int, ...]]:
+    """Every simple cycle of g with at most `max_length` edges, each once, as the sorted tuple of its edge ids
+    (NamedGraphs.unique_simplecycles_limited_length, used by src/MessagePassing/beliefpropagationcache.jl:185-187).
+    Depth-limited DFS from the smallest vertex of the cycle."""
+    out = set()
+    for root in range(g.nv):
+        stack = [(root, (), (root,))]
+        while stack:
+            v, es, vs = stack.pop()
+            for e in g.incident[v]:
+                u = g.other(e, v)
+                if u == root and len(es) >= 2 and e not in es:
+                    out.add(tuple(sorted(es + (e,))))
+                elif u > root and u not in vs and len(es) + 1 < max_length:
+                    stack.append((u, es + (e,), vs + (u,)))
+    return sorted(out, key=lambda c: (len(c), c))
+
+
+def edgeinduced_subgraphs_no_leaves(g: Graph, max_number_of_edges: int) -> List[Tuple[int, ...]]:
+    """Every non-empty set of at most `max_number_of_edges` edges whose edge-induced subgraph has no vertex of degree one - the
+    "generalised loops" of the loop series (NamedGraphs.edgeinduced_subgraphs_no_leaves as called by
+    src/MessagePassing/loopcorrection.jl:11-12; upstream code is not vendored: this is the definition its name and its use state,
+    and the one that makes the series exact when every such subgraph is included - tests/test_loopcorrections.py).  Disconnected
+    subgraphs (vertex-disjoint unions of smaller ones) are part of it once the size allows two loops.  Sorted tuples of edge ids,
+    ordered by size, then lexicographically.
+
+    Connected ones: ESU enumeration of the connected vertex sets of the line graph, anchored at the smallest edge id, pruned when
+    the leaves of the partial set cannot all be cured with the edges that are left (one new edge cures at most two)."""
+    ne = g.ne
+    if max_number_of_edges < 3 or ne == 0:
+        return []
+    ends = [(int(a), int(b)) for a, b in zip(g.esrc.tolist(), g.edst.tolist())]
+    adj = [sorted(set(f for x in ends[e] for f in g.incident[x]) - {e}) for e in range(ne)]
+    found: List[Tuple[int, ...]] = []
+    deg = [0] * g.nv
+
+    def nleaves(sub):
+        return sum(1 for e in sub for x in ends[e] if deg[x] == 1)
+
+    def extend(sub: List[int], subset: set, ext: List[int], nbhood: set, anchor: int):
+        leaves = nleaves(sub)
+        if leaves == 0:
+            found.append(tuple(sorted(sub)))
+        if len(sub) == max_number_of_edges or len(sub) + (leaves + 1) // 2 > max_number_of_edges:
+            return
+        ext = list(ext)
+        while ext:
+            w = ext.pop()
+            # exclusive neighbours of w: beyond the anchor, not in the set, not adjacent to the set already
+            new = [u for u in adj[w] if u > anchor and u not in subset and u not in nbhood]
+            sub.append(w); subset.add(w)
+            for x in ends[w]:
+                deg[x] += 1
+            extend(sub, subset, ext + new, nbhood | set(new), anchor)
+            for x in ends[w]:
+                deg[x] -= 1
+            sub.pop(); subset.discard(w)
+
+    for a in range(ne):
+        for x in ends[a]:
+            deg[x] += 1
+        first = [u for u in adj[a] if u > a]
+        extend([a], {a}, first, set(first) | {a}, a)
+        for x in ends[a]:
+            deg[x] -= 1
+    connected = sorted(set(found), key=lambda c: (len(c), c))
+    # vertex-disjoint unions
+    vsets = [frozenset(x for e in c for x in ends[e]) for c in connected]
+    smallest = len(connected[0]) if connected else max_number_of_edges + 1
+    out = list(connected)
+    if 2 * smallest <= max_number_of_edges:
+        def combine(start: int, edges: Tuple[int, ...], verts: frozenset):
+            for j in range(start, len(connected)):
+                if len(edges) + len(connected[j]) > max_number_of_edges:
+                    break                      # `connected` is sorted by size
+                if verts & vsets[j]:
+                    continue
+                union = tuple(sorted(edges + connected[j]))
+                out.append(union)
+                combine(j + 1, union, verts | vsets[j])
+        for i in range(len(connected)):
+            combine(i + 1, connected[i], vsets[i])
+    return sorted(set(out), key=lambda c: (len(c), c))
+
+
+def cycle_walks(g: Graph, max_length: int) -> List[Tuple[List[int], int]]:
+    """Every simple cycle of at most `max_length` edges as a closed walk of directed edge ids k = 2e + dir: (all steps but the
+    last, the last step).  The walk starts at the smallest vertex of the cycle and leaves it along its smaller edge; the second
+    element is what loop_correlations hands to loop_correlation as the target (beliefpropagationcache.jl:185-190: the reverse of
+    the last edge of the cycle's path, i.e. the step that closes the walk, traversed towards the start)."""
+    out = []
+    for cyc in simple_cycles_limited_length(g, max_length):
+        cs = set(cyc)
+        start = min(int(x) for e in cyc for x in (g.esrc[e], g.edst[e]))
+        e0 = min(e for e in g.incident[start] if e in cs)
+        walk, v, e = [], start, e0
+        while True:
+            u = g.other(e, v)
+            walk.append(g.dedge(v, u))
+            if u == start:
+                break
+            e = next(f for f in g.incident[u] if f in cs and f != e)
+            v = u
+        out.append((walk[:-1], walk[-1]))
+    return out

@@ -22,7 +22,7 @@ SYMBOLS = [
     "tnqs_sync", "tnqs_num_vertices", "tnqs_num_edges", "tnqs_get_bond_dims", "tnqs_site_size", "tnqs_set_site",
     "tnqs_get_site", "tnqs_set_sites", "tnqs_get_sites", "tnqs_fill_random", "tnqs_set_message", "tnqs_get_message", "tnqs_reset_messages",
     "tnqs_bp_update", "tnqs_apply_1site", "tnqs_apply_2site", "tnqs_apply_2site_begin", "tnqs_apply_2site_end", "tnqs_apply_circuit", "tnqs_apply_circuit_fetch", "tnqs_rdm_1site",
-    "tnqs_expect_2site_nn", "tnqs_expect_path", "tnqs_vertex_scalars", "tnqs_edge_scalars", "tnqs_rescale", "tnqs_symmetric_gauge",
+    "tnqs_expect_2site_nn", "tnqs_expect_path", "tnqs_loop_weights", "tnqs_loop_transfer", "tnqs_vertex_scalars", "tnqs_edge_scalars", "tnqs_rescale", "tnqs_symmetric_gauge",
     "tnqs_truncate", "tnqs_message_slab", "tnqs_halo_pack", "tnqs_halo_unpack", "tnqs_set_partition", "tnqs_set_bra", "tnqs_halo_alloc", "tnqs_halo_peer", "tnqs_halo_route", "tnqs_halo_close",
     "tnqs_kernel_launches", "tnqs_bp_sweeps_total", "tnqs_bp_message_updates_total", "tnqs_profile_enable", "tnqs_profile_read", "tnqs_stream",
 ]
@@ -85,6 +85,8 @@ def load() -> C.CDLL:
     lib.tnqs_rdm_1site.argtypes = [p, i32, i32p, f64p]
     lib.tnqs_expect_2site_nn.argtypes = [p, i32, i32p, f64p, f64p]
     lib.tnqs_expect_path.argtypes = [p, i32, i32p, i32p, f64p, f64p]
+    lib.tnqs_loop_weights.argtypes = [p, i32, i32p, i32p, f64p]
+    lib.tnqs_loop_transfer.argtypes = [p, i32, i32p, f64p]
     lib.tnqs_vertex_scalars.argtypes = [p, f64p]; lib.tnqs_edge_scalars.argtypes = [p, f64p]
     lib.tnqs_rescale.argtypes = [p]
     lib.tnqs_symmetric_gauge.argtypes = [p, C.c_double]

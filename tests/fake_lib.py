@@ -184,6 +184,7 @@ class FakeLib:
         return 0
 
     def tnqs_rescale(self, h):
+        self.calls.append("tnqs_rescale")
         st = self._s(h)
         new = O.rescale(self._bpc(st))
         st.bpc.network.tensors, st.bpc.messages = new.network.tensors, new.messages
@@ -303,6 +304,26 @@ class FakeLib:
             num = O._region_contract(self._bpc(st), path, {path[0]: o1, path[-1]: o2})
             den = O._region_contract(self._bpc(st), path, {})
             res[4 * i:4 * i + 4] = [num.real, num.imag, den.real, den.imag]
+        return 0
+
+    def tnqs_loop_weights(self, h, nsub, sub_off, sub_edges, weights):
+        self.calls.append("tnqs_loop_weights")
+        st = self._s(h)
+        offs = _arr(sub_off, nsub + 1, np.int32)
+        es = _arr(sub_edges, int(offs[nsub]), np.int32)
+        res = _arr(weights, nsub, np.complex128)
+        for i in range(nsub):
+            res[i] = O.loop_weight(self._bpc(st), [int(e) for e in es[offs[i]:offs[i + 1]]])
+        return 0
+
+    def tnqs_loop_transfer(self, h, length, walk_v, out):
+        self.calls.append("tnqs_loop_transfer")
+        st = self._s(h)
+        g = st.g
+        vs = [int(x) for x in _arr(walk_v, length, np.int32)]
+        ks = [g.dedge(vs[i], vs[(i + 1) % length]) for i in range(length)]
+        m = O.loop_transfer_matrix(self._bpc(st), ks[:-1], ks[-1])
+        _arr(out, m.size, np.complex128)[:] = m.reshape(-1, order="F")
         return 0
 
     def tnqs_kernel_launches(self, h):

@@ -130,3 +130,132 @@ def test_single_layer_network_contraction():
         zo = O.contract_bp(g, ts, info=io, **kw)
         ze = E.contract(ts, g, bp_update_kwargs=kw, info=ie)
         assert abs(ze - zo) < 1e-9 * abs(zo) and ie["iters"] == io["iters"]
+
+
+# ---- loop corrections: src/MessagePassing/loopcorrection.jl, loop_correlation(s) -------------------
+def _engine_cache_from(bo):
+    from util import to_engine
+    return to_engine(bo.network, with_messages=bo.messages)
+
+
+@pytest.mark.parametrize("dims,chi,size", [((4, 4), 3, 7), ((3, 3), 2, 12), ((2, 4), 2, 10), ((3, 4), 4, 6)])
+def test_loop_weights_follow_the_oracle(dims, chi, size):
+    # weights(bpc, egs) (loopcorrection.jl:81-96) for every generalised loop up to `size` edges - plaquettes, longer cycles, theta
+    # graphs (two independent cycles: the (chi^2 + 1)^2 assignments of the two cut edges), disconnected pairs on the 2 x 4 ladder -
+    # on the SAME rescaled messages as the oracle's direct contraction with antiprojector tensors
+    from tensornetworkquantumsimulator_b200 import engine as E
+    g = G.named_grid(dims)
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=chi, seed=31)
+    bo = O.rescale(O.update(O.BeliefPropagationCache(psi_o.copy()), maxiter=30, tolerance=1e-12))
+    be = _engine_cache_from(bo)
+    egs = G.edgeinduced_subgraphs_no_leaves(g, size)
+    if size >= 7:
+        assert any(len(eg) - len({int(x) for e in eg for x in (g.esrc[e], g.edst[e])}) + 1 >= 2 for eg in egs)      # cyclomatic number >= 2 present
+    we = E.loop_weights(be, egs)
+    wo = O.loop_weights(bo, egs)
+    assert np.max(np.abs(we - wo)) < 1e-10 * max(1.0, np.max(np.abs(wo)))
+    # the full pipeline from the state: update, partition function, rescale on a copy, enumeration, weights, series
+    kw = dict(maxiter=40, tolerance=1e-12)
+    ze = E.norm_sqr(E.TensorNetworkState.from_arrays(g, psi_o.tensors), alg="loopcorrections", max_configuration_size=size, cache_update_kwargs=kw)
+    zo = O.norm_sqr_loopcorrected(psi_o, size, **kw)
+    assert abs(ze - zo) < 1e-9 * abs(zo)
+
+
+def test_full_loop_series_is_exact_on_the_device():
+    # Z_exact = Z_bp (1 + all weights) at the BP fixed point: the device path against the exact statevector norm, not the oracle
+    from tensornetworkquantumsimulator_b200 import engine as E
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=7)
+    sv = O.to_statevector(psi_o)
+    exact = complex(np.vdot(sv, sv))
+    psi = E.TensorNetworkState.from_arrays(g, psi_o.tensors)
+    kw = dict(maxiter=3000, tolerance=1e-16)
+    zbp = E.norm_sqr(psi, cache_update_kwargs=kw)
+    zlc = E.norm_sqr(psi, alg="loopcorrections", max_configuration_size=g.ne, cache_update_kwargs=kw)
+    assert abs(zbp - exact) > 1e-3 * abs(exact) and abs(zlc - exact) < 1e-8 * abs(exact)
+    assert abs(E.norm(psi, alg="loopcorrections", max_configuration_size=g.ne, cache_update_kwargs=kw) - np.sqrt(exact)) < 1e-8 * abs(exact)
+
+
+def test_loop_weights_on_other_shapes():
+    # ragged bond dimensions, a degree-3 lattice, d = 3 sites, the tensor-core fast path (chi = 8 plaquette: 65 tree contractions
+    # of 8 x 8 messages through k_absorb_slab / k_close_dmma), a bilinear form
+    from tensornetworkquantumsimulator_b200 import engine as E
+    from util import ragged_state, to_engine
+    cases = []
+    g = G.named_grid((3, 3))
+    cases.append((g, ragged_state(g, [2, 3, 2, 4, 3, 2, 3, 2, 4, 2, 3, 2], 41), 6))
+    h = G.named_hexagonal_lattice_graph(2, 1)
+    cases.append((h, O.random_tensornetworkstate(h, bond_dimension=3, seed=42), 11))
+    cases.append((g, O.random_tensornetworkstate(g, bond_dimension=2, seed=43, d=3), 7))
+    g2 = G.named_grid((3, 2))
+    cases.append((g2, O.random_tensornetworkstate(g2, bond_dimension=8, seed=44), 4))
+    for g, psi_o, size in cases:
+        bo = O.rescale(O.update(O.BeliefPropagationCache(psi_o.copy()), maxiter=30, tolerance=1e-12))
+        be = to_engine(bo.network, with_messages=bo.messages)
+        egs = G.edgeinduced_subgraphs_no_leaves(g, size)
+        assert egs
+        we, wo = E.loop_weights(be, egs), O.loop_weights(bo, egs)
+        assert np.max(np.abs(we - wo)) < 1e-10 * max(1.0, np.max(np.abs(wo))), (g.nv, size)
+    # <phi|psi> with loop corrections (src/inner.jl:67-86): exact when every loop is included
+    g = G.named_grid((2, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=11)
+    phi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=12)
+    for v in range(g.nv):
+        phi_o.tensors[v] = psi_o.tensors[v] + 0.2 * phi_o.tensors[v]
+    exact = complex(np.vdot(O.to_statevector(phi_o), O.to_statevector(psi_o)))
+    kw = dict(maxiter=3000, tolerance=1e-16)
+    ze = E.inner(E.TensorNetworkState.from_arrays(g, psi_o.tensors), E.TensorNetworkState.from_arrays(g, phi_o.tensors),
+                 alg="loopcorrections", max_configuration_size=g.ne, cache_update_kwargs=kw)
+    assert abs(ze - exact) < 1e-8 * abs(exact)
+
+
+def test_loop_weight_argument_errors():
+    from tensornetworkquantumsimulator_b200 import engine as E
+    from tensornetworkquantumsimulator_b200.lib import TnqsError
+    from util import to_engine
+    g = G.named_grid((3, 3))
+    be = to_engine(O.random_tensornetworkstate(g, bond_dimension=2, seed=1))
+    for bad in ([(0, 0, 1, 2)], [(99,)], [()]):
+        with pytest.raises(TnqsError):
+            E.loop_weights(be, bad)
+    # a subgraph with a leaf is a legal argument (the weight is simply small at the fixed point); a tree gives the product of
+    # antiprojected environments and needs no cut at all
+    bo = O.rescale(O.update(O.BeliefPropagationCache(O.random_tensornetworkstate(g, bond_dimension=2, seed=1)), maxiter=50, tolerance=1e-14))
+    be = to_engine(bo.network, with_messages=bo.messages)
+    odd = [(0, 1), (0, 1, 2, 3, 4)]
+    assert np.max(np.abs(E.loop_weights(be, odd) - O.loop_weights(bo, odd))) < 1e-10
+    # chi = 16 theta graph: (16^2 + 1)^2 root contractions is allowed, three independent cycles at chi = 16 are refused
+    g4 = G.named_grid((3, 3))
+    big = to_engine(O.random_tensornetworkstate(g4, bond_dimension=16, seed=2))
+    full = tuple(range(g4.ne))                                          # 12 edges, 9 vertices: 4 independent cycles
+    with pytest.raises(TnqsError):
+        E.loop_weights(big, [full])
+
+
+def test_loop_correlations_follow_the_oracle():
+    # loop_correlation(s) (beliefpropagationcache.jl:144-197): transfer matrix of every plaquette from the device, entry by entry
+    # against the oracle's direct contraction, then the spectra
+    from tensornetworkquantumsimulator_b200 import engine as E
+    g = G.named_grid((3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=51)
+    bo = O.update(O.BeliefPropagationCache(psi_o.copy()), maxiter=30, tolerance=1e-12)
+    be = _engine_cache_from(bo)
+    import ctypes as C
+    from tensornetworkquantumsimulator_b200 import lib as L
+    for loop, target in G.cycle_walks(g, 4):
+        mo = O.loop_transfer_matrix(bo, loop, target)
+        walk = np.array([g.dsrc(k) for k in loop + [target]], dtype=np.int32)
+        out = np.zeros(2 * mo.size, dtype=np.float64)
+        L.check(be.psi._h.ptr, L.load().tnqs_loop_transfer(be.psi._h.ptr, len(walk), L.ptr_i32(walk), L.ptr_f64(out)))
+        me = out.view(np.complex128).reshape(mo.shape, order="F")
+        assert np.max(np.abs(me - mo)) < 1e-10 * np.max(np.abs(mo))
+    ce, co = E.loop_correlations(be, 4), O.loop_correlations(bo, 4)
+    assert len(ce) == 4 and np.allclose(ce, co, atol=1e-10)
+    # from a state: wrapped in an updated cache first (:194-196)
+    kw = dict(maxiter=200, tolerance=1e-14)
+    c2 = E.loop_correlations(E.TensorNetworkState.from_arrays(g, psi_o.tensors), 4, bp_update_kwargs=kw)
+    assert np.allclose(c2, O.loop_correlations(O.update(O.BeliefPropagationCache(psi_o.copy()), **kw), 4), atol=1e-9)
+    ring = G.named_grid((6, 1), periodic=True)
+    pr = O.random_tensornetworkstate(ring, bond_dimension=4, seed=52)
+    br = O.update(O.BeliefPropagationCache(pr.copy()), maxiter=50, tolerance=1e-13)
+    assert np.allclose(E.loop_correlations(_engine_cache_from(br), 6), O.loop_correlations(br, 6), atol=1e-10)

@@ -104,3 +104,19 @@ def test_steiner_tree_properties():
     assert len(es) == 8                                                  # a shortest path for two terminals
     with pytest.raises(ValueError):
         G.steiner_tree(g, [3, 3])
+
+
+def test_hexagonal_lattice_is_the_networkx_generator():
+    # NamedGraphs.named_hexagonal_lattice_graph follows networkx.hexagonal_lattice_graph (vertex names shifted to 1-based): same
+    # vertices, same edges, no dangling corner; heavy_hexagonal_lattice(5, 5) of examples/heavyhexIsing_dynamics.jl:9 then has the
+    # 164 vertices / 188 edges SURVEY section 8d quotes
+    nx = pytest.importorskip("networkx")
+    for m, n in ((1, 1), (2, 1), (1, 2), (2, 2), (2, 3), (3, 3), (4, 4)):
+        h = nx.hexagonal_lattice_graph(m, n)
+        g = G.named_hexagonal_lattice_graph(m, n)
+        want = sorted(tuple(sorted(((a[0] + 1, a[1] + 1), (b[0] + 1, b[1] + 1)))) for a, b in h.edges())
+        got = sorted(tuple(sorted((g.names[s], g.names[t]))) for s, t in zip(g.esrc.tolist(), g.edst.tolist()))
+        assert got == want and g.nv == h.number_of_nodes()
+        assert min(g.degree(v) for v in range(g.nv)) == 2
+    hh = G.heavy_hexagonal_lattice(5, 5)
+    assert (hh.nv, hh.ne) == (164, 188)
