@@ -411,7 +411,8 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
       mem[L][i] = cm;
       size_t bytes = align_up(cm.buf_elems * sizeof(cplx), 256) * cm.nbuf;
       const bool otherN = fN[i] && curN && fN[i] != curN;
-      if (!cur.empty() && (cur_bytes + bytes > scratch_budget_bytes || otherN)) { subsets[L].push_back(cur); cur.clear(); cur_bytes = 0; curN = 0; }
+      // a sub-level is also cut at 65535 chains: the item index of every batched launch is blockIdx.y
+      if (!cur.empty() && (cur_bytes + bytes > scratch_budget_bytes || otherN || cur.size() >= 65535)) { subsets[L].push_back(cur); cur.clear(); cur_bytes = 0; curN = 0; }
       cur.push_back(i); cur_bytes += bytes;
       if (fN[i]) curN = fN[i];
       max_scratch = std::max(max_scratch, cur_bytes);

@@ -259,3 +259,20 @@ def test_loop_correlations_follow_the_oracle():
     pr = O.random_tensornetworkstate(ring, bond_dimension=4, seed=52)
     br = O.update(O.BeliefPropagationCache(pr.copy()), maxiter=50, tolerance=1e-13)
     assert np.allclose(E.loop_correlations(_engine_cache_from(br), 6), O.loop_correlations(br, 6), atol=1e-10)
+
+
+def test_loop_weights_with_more_chains_than_one_launch_indexes():
+    # 16 x 16 at chi = 4, first-order series (1065 generalised loops): the root level alone holds 225 * 17 + 420 * 17 + 420 * 289
+    # chains, more than blockIdx.y can index - build_plan cuts the level into sub-levels
+    from tensornetworkquantumsimulator_b200 import engine as E
+    g = G.named_grid((16, 16))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=4, seed=61)
+    bo = O.rescale(O.update(O.BeliefPropagationCache(psi_o.copy()), maxiter=6, tolerance=None))
+    be = _engine_cache_from(bo)
+    egs = G.edgeinduced_subgraphs_no_leaves(g, 7)
+    assert len(egs) == 225 + 420 + 420
+    we = E.loop_weights(be, egs)
+    pick = list(range(0, len(egs), 7))
+    wo = O.loop_weights(bo, [egs[i] for i in pick])
+    assert np.max(np.abs(we[pick] - wo)) < 1e-10 * max(1.0, np.max(np.abs(wo)))
+    assert np.all(np.isfinite(we.view(np.float64)))
