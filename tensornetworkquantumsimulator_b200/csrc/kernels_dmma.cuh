@@ -812,8 +812,8 @@ __global__ void __launch_bounds__(256, 2) k_close_leg_dmma(const ModeCloseDesc* 
 // ---------------------------------------------------------------------------------------------------------------
 // k_gram_dmma: Gram matrix of a tall column-major matrix, G[b, b'] = sum_rows A[row, b] conj(A[row, b']) (n <= 64), the
 // CholeskyQR2 step.  Same formulation as the BP closing (complex rows, 16-byte operand loads, K order permuted so that a
-// K-group = 4 consecutive rows = 64 contiguous bytes of a column, three groups in flight per warp).  A warp owns a
-// 16 x 16 complex quadrant of G; the 8 warps are quadrants x K-slices, several passes when n > 32.  Fixed-order
+// K-group = 4 consecutive rows = 64 contiguous bytes of a column, three groups in flight per warp).  The CTA walks the
+// 16 x 16 complex quadrants of the upper triangle of G; the 8 warps are K-slices of the quadrant in hand.  Fixed-order
 // reductions; partials in the layout k_close_reduce consumes.  Descriptor: ModeCloseDesc with a == b, R == 1
 // (rows = L contiguous, a_sb = column stride).  grid: (max nsplit, items); block 256; dynamic shared memory 8 * 512 doubles.
 // ---------------------------------------------------------------------------------------------------------------
@@ -825,18 +825,19 @@ __global__ void __launch_bounds__(256, 2) k_gram_dmma(const ModeCloseDesc* __res
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = lane >> 2, q = lane & 3, pp = r & 1;
   const int n = d.n;
-  const int qm = (n + 15) / 16, nquad = qm * qm;
-  const int qpp = nquad < 8 ? (nquad == 1 ? 1 : (nquad <= 4 ? 4 : 8)) : 8;      // quadrants per pass: 1, 4 or 8
-  const int npass = (nquad + qpp - 1) / qpp;
-  const int nslice = 8 / qpp;
+  // G is Hermitian: only the 16 x 16 quadrants on and above the diagonal are accumulated (3 of 4 at n = 32), one after the other,
+  // each with the rows of the CTA dealt over all 8 warps; the quadrants below the diagonal are filled in by conjugation
+  const int qm = (n + 15) / 16, ntri = qm * (qm + 1) / 2;
+  constexpr int nslice = 8;
   const long long r_begin = (long long)blockIdx.x * d.rows_per_split;
   const long long r_end = min((long long)d.L, r_begin + d.rows_per_split);
   const long long g_begin = r_begin / 4, g_end = (r_end + 3) / 4;               // rows_per_split is a multiple of 4
   cplx* out = d.partial + (size_t)blockIdx.x * n * n;
-  for (int pass = 0; pass < npass; ++pass) {
-    const int quad = pass * qpp + warp % qpp, slice = warp / qpp;
-    const bool live = quad < nquad;
-    const int mq = quad % qm, nq = quad / qm;
+  for (int pass = 0; pass < ntri; ++pass) {
+    int nq = 0, mq = pass;
+    while (mq > nq) { mq -= nq + 1; ++nq; }                                      // upper triangle, column by column
+    const int slice = warp;
+    const bool live = true;
     double acc[2][4][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -892,18 +893,20 @@ __global__ void __launch_bounds__(256, 2) k_gram_dmma(const ModeCloseDesc* __res
         mine[row + 16 * (col + 1)] = acc[mt][nt][1];
       }
     __syncthreads();
-    for (int idx = tid; idx < n * n; idx += blockDim.x) {
-      const int bb = idx % n, bp = idx / n;
-      const int qd = (bb >> 4) + qm * (bp >> 4);
-      if (qd / qpp != pass) continue;
-      const int lb = bb & 15, lbp = bp & 15;
-      double re = 0, im = 0;
-      for (int sl = 0; sl < nslice; ++sl) {
-        const double* P = red + (size_t)(qd % qpp + qpp * sl) * 512;
-        re += P[lb + 16 * (2 * lbp)];
-        im += P[lb + 16 * (2 * lbp + 1)];
+    {
+      const int lb = tid & 15, lbp = tid >> 4;                 // 256 threads = the 16 x 16 entries of the quadrant
+      const int bb = 16 * mq + lb, bp = 16 * nq + lbp;
+      if (bb < n && bp < n) {
+        double re = 0, im = 0;
+#pragma unroll
+        for (int sl = 0; sl < nslice; ++sl) {
+          const double* P = red + (size_t)sl * 512;
+          re += P[lb + 16 * (2 * lbp)];
+          im += P[lb + 16 * (2 * lbp + 1)];
+        }
+        out[bb + (size_t)bp * n] = cmake(re, im);
+        if (mq != nq) out[bp + (size_t)bb * n] = cmake(re, -im);
       }
-      out[idx] = cmake(re, im);
     }
     __syncthreads();
   }
