@@ -260,8 +260,10 @@ class Stepper:
                 if item[0] == "refresh":
                     self.sched.append(item)
                 elif item[0] == "gates1":
-                    ids = item[1]
-                    self.sched.append(("gates1", [self.layer[i][1][0] for i in ids], [self.layer[i][0] for i in ids]))
+                    ids, folds = item[1], item[2]
+                    # consecutive one-site gates of a vertex (Rx, Rz) are one gate, as in tnqs_apply_circuit
+                    arrs = [E.fold_gates(self.layer[i][0], [self.layer[k][0] for k in f]) for i, f in zip(ids, folds)]
+                    self.sched.append(("gates1", [self.layer[i][1][0] for i in ids], arrs, len(ids) + sum(len(f) for f in folds)))
                 else:
                     ids = item[1]
                     es = [g.edge_of[(self.layer[i][1][0], self.layer[i][1][1])] for i in ids]
@@ -272,7 +274,7 @@ class Stepper:
                 self.bp()
             elif item[0] == "gates1":
                 _, ms = self._timed(lambda: E.apply_1site_batch(self.bpc, item[1], item[2]))
-                self.other_ms += ms; self.gates1 += len(item[1])
+                self.other_ms += ms; self.gates1 += item[3]
             else:
                 _, ms = self._timed(lambda: E.apply_2site_batch(self.bpc, item[1], item[2], flip=item[3], apply_kwargs=self.kw))
                 self.gate_ms += ms; self.gates2 += len(item[1])
@@ -294,6 +296,7 @@ def run_distributed(args, torch, dist, rank, world, local):
     lg = P.build_local_graph(gg, owner, rank)
     dt, hx, hz, J = 0.25, 1.0, 0.8, 0.5
     rx = gates.gate_array(("Rx", [0], 2 * hx * dt)); rz = gates.gate_array(("Rz", [0], 2 * hz * dt)); rzz = gates.gate_array(("Rzz", [0, 1], 2 * J * dt))
+    rzrx = E.fold_gates(rx, [rz])
     psi = E.random_tensornetworkstate(lg.g, bond_dimension=chi, seed=1 + rank, device=local)
     bpc = E.BeliefPropagationCache(psi, _share=True)
     ow = lib.i32(lg.owner_local)
@@ -333,7 +336,8 @@ def run_distributed(args, torch, dist, rank, world, local):
         stats["msg"] += info["iters"] * info["messages_per_sweep"]; stats["sweeps"] += info["iters"]; stats["halo"] += info["halo_bytes"]
 
     def step():
-        _, dt = dev_timed(lambda: (E.apply_1site_batch(bpc, owned_v, [rx] * len(owned_v)), E.apply_1site_batch(bpc, owned_v, [rz] * len(owned_v))))
+        # Rx then Rz on a vertex = one gate, their product, as tnqs_apply_circuit applies them (engine.fold_gates)
+        _, dt = dev_timed(lambda: E.apply_1site_batch(bpc, owned_v, [rzrx] * len(owned_v)))
         stats["other_s"] += dt
         for grp, batch in zip(groups, batches):
             bp()

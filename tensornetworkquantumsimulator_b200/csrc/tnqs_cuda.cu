@@ -1516,12 +1516,23 @@ static void apply_circuit_impl(tnqs_ctx* c, int32_t ngates, const int32_t* gate_
   const cplx* gd = (const cplx*)gate_data;
   std::vector<char> affected(c->nv, 0), inbatch(c->nv, 0);
   std::vector<int> batch;          // gate indices of the pending batch (all 1-site or all 2-site, vertex-disjoint)
+  // Consecutive one-site gates on a vertex (the Rx and Rz of a Trotter layer) are multiplied on the host and applied as one gate:
+  // one pass over the tensor and one normalisation instead of one per gate.  With normalize_tensors the intermediate norms are
+  // scalars that the last normalisation removes, so only rounding changes.  folded[j] = product for batch[j].
+  std::vector<std::vector<cplx>> folded;
+  std::vector<int> pos1(c->nv, -1);
   int batch_arity = 0, nrefresh = 0;
   auto flush = [&]() {
     if (batch.empty()) return;
     if (batch_arity == 1) {
       std::vector<int> vs; std::vector<cplx> g;
-      for (int i : batch) { int v = gate_v[2 * i], d = c->d[v]; vs.push_back(v); g.insert(g.end(), gd + gate_off[i], gd + gate_off[i] + d * d); }
+      for (size_t j = 0; j < batch.size(); ++j) {
+        const int i = batch[j], v = gate_v[2 * i], d = c->d[v];
+        vs.push_back(v); pos1[v] = -1;
+        if (j < folded.size() && !folded[j].empty()) g.insert(g.end(), folded[j].begin(), folded[j].end());
+        else g.insert(g.end(), gd + gate_off[i], gd + gate_off[i] + d * d);
+      }
+      folded.clear();
       apply_1site_impl(c, (int)vs.size(), vs.data(), (const double*)g.data(), aopts->normalize_tensors);
     } else {
       std::vector<int> es, fl; std::vector<cplx> g; std::vector<double> err(batch.size());
@@ -1553,9 +1564,24 @@ static void apply_circuit_impl(tnqs_ctx* c, int32_t ngates, const int32_t* gate_
     if (truncerr) truncerr[i] = 0.0;
     bool need = update_cache && arity == 2 && (affected[v1] || affected[v2]);        // apply_gates.jl:64
     if (need) { flush(); refresh(); std::fill(affected.begin(), affected.end(), 0); }
+    if (arity == 1 && !batch.empty() && batch_arity == 1 && pos1[v1] >= 0) {
+      // o[s', s] <- g_i[s', t] * o[t, s]
+      const int j = pos1[v1], d = c->d[v1];
+      folded.resize(batch.size());
+      if (folded[j].empty()) folded[j].assign(gd + gate_off[batch[j]], gd + gate_off[batch[j]] + d * d);
+      const cplx* gi = gd + gate_off[i];
+      std::vector<cplx> prod((size_t)d * d, cmake(0, 0));
+      for (int s2 = 0; s2 < d; ++s2) for (int t = 0; t < d; ++t) for (int s1 = 0; s1 < d; ++s1) {
+        const cplx a = gi[s1 + d * t], b = folded[j][t + d * s2];
+        prod[s1 + d * s2].x += a.x * b.x - a.y * b.y; prod[s1 + d * s2].y += a.x * b.y + a.y * b.x;
+      }
+      folded[j].swap(prod);
+      continue;
+    }
     bool conflict = !batch.empty() && (arity != batch_arity || inbatch[v1] || (v2 >= 0 && inbatch[v2]));
     if (conflict) flush();
     batch_arity = arity; batch.push_back(i);
+    if (arity == 1) pos1[v1] = (int)batch.size() - 1;
     inbatch[v1] = 1; affected[v1] = 1;                                                // apply_gates.jl:84
     if (v2 >= 0) { inbatch[v2] = 1; affected[v2] = 1; }
   }

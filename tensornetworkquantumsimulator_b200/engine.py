@@ -381,33 +381,60 @@ def circuit_schedule(g: Graph, circuit: Sequence[tuple], update_cache: bool = Tr
     """The batches and BP refreshes `apply_gates` / tnqs_apply_circuit execute for an ordered gate list, by the reference's
     rule (src/Apply/apply_gates.jl:56-89): a refresh before a 2-site gate that touches a vertex touched since the last
     refresh (1-site gates mark vertices too), consecutive independent gates of equal arity form one batch, final refresh.
-    Returns [("refresh",) | ("gates1", [gate indices]) | ("gates2", [gate indices])].  Runs are defined by the rule, not by
-    colour: gates of a new colour class that precede its first overlapping gate are applied before the refresh."""
+    Returns [("refresh",) | ("gates1", [gate indices], folds) | ("gates2", [gate indices])].  Runs are defined by the rule, not by
+    colour: gates of a new colour class that precede its first overlapping gate are applied before the refresh.  Consecutive
+    one-site gates on a vertex are applied as ONE gate, their product (`fold_gates`): folds[j] lists the later gates multiplied
+    onto the j-th gate of the batch, in program order (empty for most)."""
     verts = []
     for gate in circuit:
         v = gate[1] if isinstance(gate[1], list) else [gate[1]]
         verts.append([_vid(g, x) for x in v])
     out: List[tuple] = []
     affected, inbatch, batch, arity_b = set(), set(), [], 0
+    folds, pos1 = [], {}
 
     def flush():
-        nonlocal batch, inbatch
+        nonlocal batch, inbatch, folds, pos1
         if batch:
-            out.append(("gates1" if arity_b == 1 else "gates2", batch))
-        batch, inbatch = [], set()
+            out.append(("gates1", batch, folds) if arity_b == 1 else ("gates2", batch))
+        batch, inbatch, folds, pos1 = [], set(), [], {}
 
     for i, vs in enumerate(verts):
         arity = len(vs)
         if update_cache and arity == 2 and any(v in affected for v in vs):
             flush(); out.append(("refresh",)); affected = set()
+        if arity == 1 and batch and arity_b == 1 and vs[0] in pos1:
+            folds[pos1[vs[0]]].append(i)
+            continue
         if batch and (arity != arity_b or any(v in inbatch for v in vs)):
             flush()
         arity_b = arity
         batch.append(i); inbatch |= set(vs); affected |= set(vs)
+        if arity == 1:
+            folds.append([]); pos1[vs[0]] = len(batch) - 1
     flush()
     if update_cache:
         out.append(("refresh",))
     return out
+
+
+def fold_gates(first: np.ndarray, later: Sequence[np.ndarray]) -> np.ndarray:
+    """Product of consecutive one-site gates on a vertex, later ... first, as tnqs_apply_circuit forms it before applying them in
+    one pass: the same scalar operations in the same order (o[s', s] <- sum_t g[s', t] o[t, s], t ascending), so that a schedule
+    executed call by call reproduces apply_gates bit for bit."""
+    o = np.array(first, dtype=np.complex128)
+    d = o.shape[0]
+    for g in later:
+        g = np.asarray(g, dtype=np.complex128)
+        new = np.zeros((d, d), dtype=np.complex128)
+        for s2 in range(d):
+            for t in range(d):
+                for s1 in range(d):
+                    a, b = complex(g[s1, t]), complex(o[t, s2])
+                    p = complex(a.real * b.real - a.imag * b.imag, a.real * b.imag + a.imag * b.real)
+                    new[s1, s2] = complex(new[s1, s2].real + p.real, new[s1, s2].imag + p.imag)
+        o = new
+    return o
 
 
 def _pack_gate_arrays(gates: Sequence[np.ndarray]) -> np.ndarray:

@@ -524,11 +524,12 @@ def test_bench_phase_sequence_equals_apply_gates(E):
         if item[0] == "refresh":
             E.update(b, edge_sequence=seq, inplace=True, **bp_kw)
         elif item[0] == "gates1":
-            E.apply_1site_batch(b, [layer[i][1][0] for i in item[1]], [layer[i][0] for i in item[1]])
+            E.apply_1site_batch(b, [layer[i][1][0] for i in item[1]], [E.fold_gates(layer[i][0], [layer[k][0] for k in f]) for i, f in zip(item[1], item[2])])
         else:
             es = [g.edge_of[(layer[i][1][0], layer[i][1][1])] for i in item[1]]
             E.apply_2site_batch(b, es, [layer[i][0] for i in item[1]], flip=[0 if int(g.esrc[e]) == layer[i][1][0] else 1 for e, i in zip(es, item[1])], apply_kwargs=kw)
     assert info["refreshes"] == 5 == sum(1 for it in sched if it[0] == "refresh")
+    assert [(len(it[1]), sum(len(f) for f in it[2])) for it in sched if it[0] == "gates1"] == [(g.nv, g.nv)]      # Rz folded onto Rx: one pass
     # runs are defined by the rule, not by colour: the first gates of the third class precede its refresh
     assert [len(it[1]) for it in sched if it[0] == "gates2"] != [len(grp) for grp in groups]
     assert list(a.psi.bond_dims()) == list(b.psi.bond_dims())

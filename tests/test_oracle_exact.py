@@ -205,8 +205,20 @@ def test_circuit_schedule_follows_the_reference_rule():
         psi0 = O.tensornetworkstate(lambda v: "↑", g)
         O.apply_gates(layer * 2, O.BeliefPropagationCache(psi0), apply_kwargs=dict(maxdim=2, cutoff=1e-10), info=info)
         assert sum(1 for it in sched if it[0] == "refresh") == info["refreshes"]
-        ids = [i for it in sched if it[0] != "refresh" for i in it[1]]
-        assert ids == list(range(len(layer) * 2))                       # program order is preserved
+        # every gate exactly once; program order is preserved per vertex (one-site gates folded onto an earlier one of the same
+        # vertex and batch keep their order inside the fold)
+        ids = [i for it in sched if it[0] != "refresh" for i in it[1]] + [k for it in sched if it[0] == "gates1" for f in it[2] for k in f]
+        assert sorted(ids) == list(range(len(layer) * 2))
+        last = {}
+        for it in sched:
+            if it[0] == "refresh":
+                continue
+            groups_ = [[i] + (it[2][j] if it[0] == "gates1" else []) for j, i in enumerate(it[1])]
+            for grp in groups_:
+                assert grp == sorted(grp)
+                for x in (layer * 2)[grp[0]][1]:
+                    assert last.get(g.v(x), -1) < grp[0]
+                    last[g.v(x)] = grp[-1]
         for it in sched:
             if it[0] == "gates2":                                        # a batch is vertex-disjoint
                 vs = [g.v(x) for i in it[1] for x in (layer * 2)[i][1]]
