@@ -276,3 +276,23 @@ def test_loop_weights_with_more_chains_than_one_launch_indexes():
     wo = O.loop_weights(bo, [egs[i] for i in pick])
     assert np.max(np.abs(we[pick] - wo)) < 1e-10 * max(1.0, np.max(np.abs(wo)))
     assert np.all(np.isfinite(we.view(np.float64)))
+
+
+def test_full_loop_series_on_k4_and_the_cube_on_the_device():
+    # triangles and vertices of loop degree 3 (K4), degree-3 vertices with five independent cycles (2 x 2 x 2 cube: up to 5^5 signed
+    # tree contractions for one subgraph): weights against the oracle and the whole series against the exact norm
+    from tensornetworkquantumsimulator_b200 import engine as E
+    from util import to_engine
+    k4 = G._from_named_edges(list(range(4)), [(a, b) for a in range(4) for b in range(a + 1, 4)])
+    for g, seed in ((k4, 3), (G.named_grid((2, 2, 2)), 4)):
+        psi_o = O.random_tensornetworkstate(g, bond_dimension=2, seed=seed)
+        bo = O.update(O.BeliefPropagationCache(psi_o.copy()), maxiter=5000, tolerance=1e-16)
+        egs = G.edgeinduced_subgraphs_no_leaves(g, g.ne)
+        br = O.rescale(bo)
+        we = E.loop_weights(to_engine(br.network, with_messages=br.messages), egs)
+        wo = O.loop_weights(br, egs)
+        assert np.max(np.abs(we - wo)) < 1e-10 * max(1.0, np.max(np.abs(wo)))
+        sv = O.to_statevector(psi_o)
+        exact = complex(np.vdot(sv, sv))
+        ze = E.loopcorrected_partitionfunction(to_engine(bo.network, with_messages=bo.messages), g.ne)
+        assert abs(ze - exact) < 1e-8 * abs(exact)

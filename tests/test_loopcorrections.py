@@ -72,6 +72,24 @@ def test_full_loop_series_is_exact(dims, chi, seed):
     assert abs(zbp - exact) > 1e-3 * abs(exact)                         # BP alone is visibly off: the corrections carry the difference
 
 
+def _k4():
+    return G._from_named_edges(list(range(4)), [(a, b) for a in range(4) for b in range(a + 1, 4)])
+
+
+@pytest.mark.parametrize("which", ["k4", "cube"])
+def test_full_loop_series_is_exact_with_triangles_and_high_degree(which):
+    # K4 (triangles, every vertex of loop degree 3 in the largest subgraphs) and the 2 x 2 x 2 cube (five independent cycles):
+    # enumeration against brute force and the series against the exact norm
+    g = _k4() if which == "k4" else G.named_grid((2, 2, 2))
+    egs = G.edgeinduced_subgraphs_no_leaves(g, g.ne)
+    assert egs == sorted(_brute_force_no_leaves(g, g.ne), key=lambda c: (len(c), c))
+    psi = O.random_tensornetworkstate(g, bond_dimension=2, seed=3 if which == "k4" else 4)
+    bpc = O.update(O.BeliefPropagationCache(psi.copy()), maxiter=5000, tolerance=1e-16)
+    sv = O.to_statevector(psi)
+    exact = complex(np.vdot(sv, sv))
+    assert abs(O.loopcorrected_partitionfunction(bpc, g.ne) - exact) < 1e-8 * abs(exact)
+
+
 def test_bilinear_and_single_layer_series_are_exact():
     # inner(psi, phi; alg = "loopcorrections") (src/inner.jl:67-86): the same weights on the messages of the bilinear form
     g = G.named_grid((2, 3))
