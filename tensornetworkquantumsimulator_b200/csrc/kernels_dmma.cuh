@@ -61,6 +61,9 @@ constexpr int SLAB_CTAS = 3;
 #ifndef TNQS_QUEUE_THREADS
 #define TNQS_QUEUE_THREADS 256
 #endif
+#ifndef TNQS_3M
+#define TNQS_3M 1              // leg absorptions of the slab kernels: 3M complex products (see absorb_phase)
+#endif
 constexpr int QUEUE_THREADS = TNQS_QUEUE_THREADS;
 constexpr int QUEUE_CTAS = 2;
 
@@ -76,6 +79,27 @@ __device__ __forceinline__ void absorb_phase(const SlabDesc& d, const cplx* __re
   constexpr int O1 = P == 0 ? 1 : 0, O2 = P == 2 ? 1 : 2;              // the other slab legs, fastest first
   constexpr long long XST[3] = {1, N, (long long)N * N};                // intermediate strides
   const int r = lane >> 2, q = lane & 3;
+#if TNQS_3M
+  // 3M complex product (three real GEMMs instead of four: T1 = A_r M_r, T2 = A_i M_i, T3 = (A_r + A_i)(M_r + M_i);
+  // C_r = T1 - T2, C_i = T3 - T1 - T2): 6 instead of 8 DMMAs per row tile and k-group.  A real n-tile holds 8 complex columns;
+  // fragment column n stands for the complex column 4 (2 nt' + (n & 1)) + (n >> 1), so that a lane ends up with the columns
+  // 4 nt + q it stores in the four-product form, and every shared- and global-memory access pattern stays what it was.
+  constexpr int NT3 = N / 8;
+  double br[KK][NT3], bi[KK][NT3], bs[KK][NT3];
+  {
+    const cplx* m = msm;
+    const bool conj_m = d.flags & 1, trans_m = d.flags & 2;
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk)
+#pragma unroll
+      for (int nt = 0; nt < NT3; ++nt) {
+        const int b = 4 * kk + q, c = 4 * (2 * nt + (r & 1)) + (r >> 1);
+        cplx v = trans_m ? m[c + N * b] : m[b + N * c];
+        if (conj_m) v.y = -v.y;
+        br[kk][nt] = v.x; bi[kk][nt] = v.y; bs[kk][nt] = v.x + v.y;
+      }
+  }
+#else
   // B fragments of [[Re m, Im m], [-Im m, Re m]], kept in registers for the whole phase
   double bf[2 * KK][NT];
   {
@@ -93,6 +117,7 @@ __device__ __forceinline__ void absorb_phase(const SlabDesc& d, const cplx* __re
         bf[2 * kk + 1][nt] = pp ? v.x : -v.y;       // row (b, im): -Im m to the real column, Re m to the imaginary one
       }
   }
+#endif
   constexpr int ntiles = (F == 3 ? N * N : N) / 8;
   const int fq = slab_f(q);
   cplx a[KK];
@@ -118,6 +143,29 @@ __device__ __forceinline__ void absorb_phase(const SlabDesc& d, const cplx* __re
     const bool more = tn < ntiles;
     const long long son = more ? src_off(8 * tn + r) : 0;
     double acc[NT][2];
+#if TNQS_3M
+    double t1[NT3][2], t2[NT3][2], t3[NT3][2];
+#pragma unroll
+    for (int nt = 0; nt < NT3; ++nt) { t1[nt][0] = t1[nt][1] = t2[nt][0] = t2[nt][1] = t3[nt][0] = t3[nt][1] = 0.0; }
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) {
+      const double ax = a[kk].x, ay = a[kk].y, as = ax + ay;
+#pragma unroll
+      for (int nt = 0; nt < NT3; ++nt) dmma884(t1[nt][0], t1[nt][1], ax, br[kk][nt]);
+#pragma unroll
+      for (int nt = 0; nt < NT3; ++nt) dmma884(t2[nt][0], t2[nt][1], ay, bi[kk][nt]);
+#pragma unroll
+      for (int nt = 0; nt < NT3; ++nt) dmma884(t3[nt][0], t3[nt][1], as, bs[kk][nt]);
+      if (more) a[kk] = src[son + kk * kstride];
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT3; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        acc[2 * nt + j][0] = t1[nt][j] - t2[nt][j];
+        acc[2 * nt + j][1] = t3[nt][j] - t1[nt][j] - t2[nt][j];
+      }
+#else
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = 0.0; acc[nt][1] = 0.0; }
 #pragma unroll
@@ -128,6 +176,7 @@ __device__ __forceinline__ void absorb_phase(const SlabDesc& d, const cplx* __re
       for (int nt = 0; nt < NT; ++nt) dmma884(acc[nt][0], acc[nt][1], a[kk].y, bf[2 * kk + 1][nt]);
       if (more) a[kk] = src[son + kk * kstride];
     }
+#endif
     const int rho = 8 * ti + r, o1 = rho % N, o2 = rho / N;
     if (to_global) {
       cplx* dst = gdst + (long long)o1 * XST[O1] + (F == 3 ? (long long)o2 * XST[O2] : 0) + (long long)q * XST[P];
