@@ -64,6 +64,9 @@ constexpr int SLAB_CTAS = 3;
 #ifndef TNQS_3M
 #define TNQS_3M 1              // leg absorptions of the slab kernels: 3M complex products (see absorb_phase)
 #endif
+#ifndef TNQS_3M_CLOSE
+#define TNQS_3M_CLOSE (TNQS_CLOSE_QUAD)     // the closing contraction likewise (needs the quad K-groups)
+#endif
 constexpr int QUEUE_THREADS = TNQS_QUEUE_THREADS;
 constexpr int QUEUE_CTAS = 2;
 
@@ -296,6 +299,70 @@ __device__ __forceinline__ bool close_dmma_item(const CloseDmmaDesc& d, int sub,
   const cplx* tl = d.t + s + (long long)ih * d.g[0] + (long long)(r >> 1) * d.gw;     // + 4 nt * gw + toff0
 #endif
   const long long g2 = d.F == 3 ? d.g[2] : 0;
+#if TNQS_3M_CLOSE
+  // 3M form of M[w, w'] = sum_K X[K, w] conj(T[K, w']):  T1 = X_r T_r, T2 = X_i T_i, T3 = (X_r + X_i)(T_r - T_i);
+  // Re M = T1 + T2, Im M = T3 - T1 + T2.  A real n-tile is 8 values of w' (fragment column n = w' - 8 nt'): 12 instead of 16
+  // DMMAs per K-group, and every element of T is loaded by one lane instead of two.
+  constexpr int NT3 = N / 8;
+  const cplx* tl3 = d.t + (long long)q * d.g[0] + (long long)r * d.gw;                  // + s + 8 nt' * gw + toff0
+  cplx a[NSET][MT], b[NSET][NT3];
+  auto load = [&](int set, long long g) {
+    if (g < g_end) {
+      const int sg = (int)(g & 1), j = (int)((g >> 1) % (N / 4));
+      const long long rest = (g >> 1) / (N / 4);
+      const int i2 = (int)(rest % N), i3 = (int)(rest / N);
+      const long long sigma0 = (long long)sg * NF + 4 * j + (long long)N * i2 + (long long)N * N * i3;
+      const long long toff0 = sg + 4 * j * d.g[0] + i2 * d.g[1] + i3 * g2;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) a[set][mt] = __ldcg(xl + (long long)(8 * mt + r) * 2 * NF + sigma0);
+#pragma unroll
+      for (int nt = 0; nt < NT3; ++nt) b[set][nt] = tl3[toff0 + (long long)8 * nt * d.gw];
+    } else {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) a[set][mt] = cmake(0, 0);
+#pragma unroll
+      for (int nt = 0; nt < NT3; ++nt) b[set][nt] = cmake(0, 0);
+    }
+  };
+  double t1[MT][NT3][2], t2[MT][NT3][2], t3[MT][NT3][2];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT3; ++j) { t1[i][j][0] = t1[i][j][1] = t2[i][j][0] = t2[i][j][1] = t3[i][j][0] = t3[i][j][1] = 0.0; }
+  long long g = g_begin + warp;
+#pragma unroll
+  for (int u = 0; u < NSET; ++u) load(u, g + nw * u);
+  for (; g < g_end; g += nw * NSET) {
+#pragma unroll
+    for (int u = 0; u < NSET; ++u) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT3; ++nt) dmma884(t1[mt][nt][0], t1[mt][nt][1], a[u][mt].x, b[u][nt].x);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT3; ++nt) dmma884(t2[mt][nt][0], t2[mt][nt][1], a[u][mt].y, b[u][nt].y);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT3; ++nt) dmma884(t3[mt][nt][0], t3[mt][nt][1], a[u][mt].x + a[u][mt].y, b[u][nt].x - b[u][nt].y);
+      load(u, g + nw * (u + NSET));
+    }
+  }
+  constexpr int LD = N;
+  double* mine = red + (size_t)warp * 2 * N * N;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT3; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int row = 8 * mt + r, wp = 8 * nt + 2 * q + j;
+        mine[row + LD * (2 * wp)] = t1[mt][nt][j] + t2[mt][nt][j];
+        mine[row + LD * (2 * wp + 1)] = t3[mt][nt][j] - t1[mt][nt][j] + t2[mt][nt][j];
+      }
+#else
   cplx a[NSET][MT], b[NSET][NT];
   auto load = [&](int set, long long g) {
     if (g < g_end) {
@@ -361,6 +428,7 @@ __device__ __forceinline__ bool close_dmma_item(const CloseDmmaDesc& d, int sub,
       mine[row + LD * col] = acc[mt][nt][0];
       mine[row + LD * (col + 1)] = acc[mt][nt][1];
     }
+#endif
   __syncthreads();
   cplx* out = d.partial + (size_t)sub * N * N;
   for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
