@@ -955,6 +955,65 @@ __global__ void __launch_bounds__(256, 2) k_gram_dmma(const ModeCloseDesc* __res
     while (mq > nq) { mq -= nq + 1; ++nq; }                                      // upper triangle, column by column
     const int slice = warp;
     const bool live = true;
+#if TNQS_3M
+    // 3M form, as in the BP closing: T1 = X_r T_r, T2 = X_i T_i, T3 = (X_r + X_i)(T_r - T_i); Re G = T1 + T2, Im G = T3 - T1 + T2
+    // with X = the columns b of the quadrant's row block and T = the columns b' of its column block (8 per real n-tile)
+    double t1[2][2][2], t2[2][2][2], t3[2][2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { t1[i][j][0] = t1[i][j][1] = t2[i][j][0] = t2[i][j][1] = t3[i][j][0] = t3[i][j][1] = 0.0; }
+    if (live) {
+      // columns beyond n read a valid column; their rows / columns of G are never stored
+      const int sb = (int)d.a_sb;                                  // the matrix has fewer than 2^31 elements
+      const int acol0 = min(16 * mq + r, n - 1) * sb + q, acol1 = min(16 * mq + 8 + r, n - 1) * sb + q;
+      const int bcol0 = min(16 * nq + r, n - 1) * sb + q, bcol1 = min(16 * nq + 8 + r, n - 1) * sb + q;
+      cplx a[NSET][2], b[NSET][2];
+      auto load = [&](int set, long long g) {
+        const long long row = 4 * g;
+        if (g < g_end && row + q < r_end) {
+          const cplx* p = d.a + row;
+          a[set][0] = p[acol0]; a[set][1] = p[acol1];
+          b[set][0] = p[bcol0]; b[set][1] = p[bcol1];
+        } else {
+          a[set][0] = a[set][1] = cmake(0, 0);
+          b[set][0] = b[set][1] = cmake(0, 0);
+        }
+      };
+      long long g = g_begin + slice;
+#pragma unroll
+      for (int u = 0; u < NSET; ++u) load(u, g + (long long)nslice * u);
+      for (; g < g_end; g += (long long)nslice * NSET) {
+#pragma unroll
+        for (int u = 0; u < NSET; ++u) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) dmma884(t1[mt][nt][0], t1[mt][nt][1], a[u][mt].x, b[u][nt].x);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) dmma884(t2[mt][nt][0], t2[mt][nt][1], a[u][mt].y, b[u][nt].y);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) dmma884(t3[mt][nt][0], t3[mt][nt][1], a[u][mt].x + a[u][mt].y, b[u][nt].x - b[u][nt].y);
+          load(u, g + (long long)nslice * (u + NSET));
+        }
+      }
+    }
+    double* mine = red + (size_t)warp * 512;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int row = 8 * mt + r, lbp = 8 * nt + 2 * q + j;
+          mine[row + 16 * (2 * lbp)] = t1[mt][nt][j] + t2[mt][nt][j];
+          mine[row + 16 * (2 * lbp + 1)] = t3[mt][nt][j] - t1[mt][nt][j] + t2[mt][nt][j];
+        }
+#else
     double acc[2][4][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -1009,6 +1068,7 @@ __global__ void __launch_bounds__(256, 2) k_gram_dmma(const ModeCloseDesc* __res
         mine[row + 16 * col] = acc[mt][nt][0];
         mine[row + 16 * (col + 1)] = acc[mt][nt][1];
       }
+#endif
     __syncthreads();
     {
       const int lb = tid & 15, lbp = tid >> 4;                 // 256 threads = the 16 x 16 entries of the quadrant
