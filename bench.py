@@ -522,9 +522,11 @@ def run_engine(args):
         "roofline": {"bound": "tensor", "kernel": "k_bp_sweep<16> (one persistent launch per BP sweep: DMMA leg absorptions, closings and message epilogues of all 3968 updates)" if one_launch_per_sweep
                      else "k_absorb_slab<16> (fused BP leg absorption, DMMA)", "achieved": apply_tf, "peak": pk["fp64_tflops_sustained"],
                      "unit": "TFLOP/s", "frac": (apply_tf / pk["fp64_tflops_sustained"]) if apply_tf else None,
-                     "traffic": (22.75e9 if one_launch_per_sweep else 206.0e6),
-                     "traffic_detail": ({"dram_bytes_read": 14.06e9, "dram_bytes_written": 8.69e9, "algorithmic_bytes_per_launch": float(sum(16.0 * 2 * chi ** g.degree(g.dsrc(int(k))) for k in seq)),
-                                         "note": "one launch = one sweep of 3968 updates (ncu --set full, profiles/r02a_bp_kernels_ncu_full_raw.csv); algorithmic = every site tensor read once per update; the rest is the "
+                     "flop_count": "algorithmic: 8 flops per complex multiply-add of the reference's contraction (SURVEY 8d); the kernels form a complex "
+                                   "product from three real DMMA products (3M), i.e. execute 3/4 of the multiplications that count stands for",
+                     "traffic": (20.63e9 if one_launch_per_sweep else 206.0e6),
+                     "traffic_detail": ({"dram_bytes_read": 11.98e9, "dram_bytes_written": 8.64e9, "algorithmic_bytes_per_launch": float(sum(16.0 * 2 * chi ** g.degree(g.dsrc(int(k))) for k in seq)),
+                                         "note": "one launch = one sweep of 3968 updates (ncu --set full, profiles/r02g_bp_sweep_ncu_full_raw.csv); algorithmic = every site tensor read once per update; the rest is the "
                                                  "slab-major intermediate X (written once, read once by the closing) and the closing's second read of the site tensor, partly served by L2 (hit rate 40 %)"}
                                         if one_launch_per_sweep else {"dram_bytes_per_launch": 206.0e6, "algorithmic_bytes_per_launch": 260.0e6, "launch": "62 messages x 32 slabs (profiles/r01_final_dmma_ncu_full_raw.csv)"}),
                      "peak_source": pk["source"], "launches_profiled": int(ln[0]), "avg_launch_ms": ms[0] / max(1, ln[0]),
