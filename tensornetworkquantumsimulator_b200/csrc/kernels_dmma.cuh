@@ -68,7 +68,10 @@ constexpr int SLAB_CTAS = 3;
 #define TNQS_3M_CLOSE (TNQS_CLOSE_QUAD)     // the closing contraction likewise (needs the quad K-groups)
 #endif
 constexpr int QUEUE_THREADS = TNQS_QUEUE_THREADS;
-constexpr int QUEUE_CTAS = 2;
+#ifndef TNQS_QUEUE_CTAS
+#define TNQS_QUEUE_CTAS 2
+#endif
+constexpr int QUEUE_CTAS = TNQS_QUEUE_CTAS;
 
 // One absorption phase P of F.  K ordering: lane (r, q) loads the whole complex element b = 4kk + q of its row (one
 // 16-byte load) and feeds its real part to k-step 2kk and its imaginary part to k-step 2kk+1; the B fragments are built
