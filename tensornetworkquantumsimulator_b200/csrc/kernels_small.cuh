@@ -189,6 +189,77 @@ __global__ void __launch_bounds__(1024) k_eigh_sqrt(const EighDesc* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Householder QR of an h x nc block (h >= nc) held in shared memory, overwritten by its explicit thin Q (zgeqr2 + zung2r
+// arithmetic, R is not kept).  Every thread of the CTA must call; tau: nc complex, scal: 1 complex of shared memory.
+__device__ void house_q_inplace(cplx* A, int h, int nc, cplx* tau, cplx* scal) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int j = 0; j < nc; ++j) {
+    cplx* col = A + (size_t)j * h;
+    if (warp == 0) {                                      // zlarfg
+      double xn2 = 0;
+      for (int r = j + 1 + lane; r < h; r += 32) xn2 += cabs2(col[r]);
+      xn2 = warp_sum(xn2);
+      if (lane == 0) {
+        cplx alpha = col[j];
+        if (xn2 == 0.0 && alpha.y == 0.0) { tau[j] = cmake(0, 0); scal[0] = cmake(0, 0); }
+        else {
+          double beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xn2), alpha.x);
+          tau[j] = cmake((beta - alpha.x) / beta, -alpha.y / beta);
+          double dr = alpha.x - beta, di = alpha.y, den = dr * dr + di * di;
+          scal[0] = cmake(dr / den, -di / den);
+          col[j] = cmake(beta, 0);
+        }
+      }
+    }
+    __syncthreads();
+    {
+      cplx sc = scal[0];
+      for (int r = j + 1 + tid; r < h; r += blockDim.x) col[r] = cmul(col[r], sc);
+    }
+    __syncthreads();
+    cplx tj = tau[j];
+    if (tj.x != 0.0 || tj.y != 0.0) {                     // H(j)^H = I - conj(tau) v v^H on the trailing columns
+      for (int c = j + 1 + warp; c < nc; c += nwarps) {
+        cplx* cc = A + (size_t)c * h;
+        cplx w = cmake(0, 0);
+        for (int r = j + 1 + lane; r < h; r += 32) cfma_ca(w, col[r], cc[r]);
+        w.x = warp_sum(w.x); w.y = warp_sum(w.y);
+        w = cadd(w, cc[j]);                                // v_j = 1
+        cplx f = cmul(cconj(tj), w);
+        if (lane == 0) cc[j] = csub(cc[j], f);
+        for (int r = j + 1 + lane; r < h; r += 32) cc[r] = csub(cc[r], cmul(f, col[r]));
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = nc - 1; i >= 0; --i) {                      // explicit Q (zung2r)
+    cplx* col = A + (size_t)i * h;
+    cplx ti = tau[i];
+    if (ti.x != 0.0 || ti.y != 0.0) {
+      for (int c = i + 1 + warp; c < nc; c += nwarps) {
+        cplx* cc = A + (size_t)c * h;
+        cplx w = cmake(0, 0);
+        for (int r = i + 1 + lane; r < h; r += 32) cfma_ca(w, col[r], cc[r]);
+        w.x = warp_sum(w.x); w.y = warp_sum(w.y);
+        w = cadd(w, cc[i]);
+        cplx f = cmul(ti, w);
+        if (lane == 0) cc[i] = csub(cc[i], f);
+        for (int r = i + 1 + lane; r < h; r += 32) cc[r] = csub(cc[r], cmul(f, col[r]));
+      }
+    }
+    __syncthreads();
+    for (int r = tid; r < h; r += blockDim.x) {
+      cplx v;
+      if (r < i) v = cmake(0, 0);
+      else if (r == i) v = cmake(1.0 - ti.x, -ti.y);
+      else v = cmul(cmake(-ti.x, -ti.y), col[r]);
+      col[r] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 struct QrDesc {
   cplx* a; long long lda; int h, nc;     // block: h rows x nc columns, column-major
   cplx* rout; int ldr;                   // R: min(h,nc) x nc, zeros below the diagonal
@@ -330,6 +401,13 @@ struct SvdDesc {
   int* rank; double* truncerr;
   cplx* msg_a; cplx* msg_b;              // message slots receiving diag(S) (rank x rank), may be null
   int maxdim; double cutoff; int has_cutoff; int normalize; int cap; int mindim;
+  // Row-space reduction (optional, gate path): theta' = R1 (gate) R2 has rank <= r_o * chi with r_o the operator-Schmidt rank of
+  // the gate over the (site 1 | site 2) cut - 2 for Rzz, Rxx, CZ, CNOT.  When that is at most n / 2 the kernel iterates
+  // W = theta' conj(Q) (m x r_o chi) instead of theta' (m x n), Q = an orthonormal basis of the span of the vectors
+  // sum_s2 B_k[s2', s2] R2[q2, s2, b] that contains every row of theta' (B_k = a basis of the row space of the gate as a
+  // d^2 x d^2 matrix, found on the device so that a replayed graph may carry other gate angles).  Same singular values and left
+  // vectors as theta'; the right factor comes from theta'^H W_j as before.  rs_gate == null: off.
+  const cplx* rs_gate = nullptr; const cplx* rs_r2 = nullptr; int rs_q2 = 0, rs_ld2 = 0, rs_d = 0, rs_chi = 0;
 };
 
 // dynamic shared memory: W (mm x nn) if work == null, then sigma[nn] doubles, perm[nn] ints.
@@ -341,18 +419,82 @@ __global__ void __launch_bounds__(512, 2) k_svd_trunc(const SvdDesc* __restrict_
   extern __shared__ cplx ssm[];
   const int m = d.m, n = d.n;
   const bool swapped = m < n;
-  const int mm = swapped ? n : m, nn = swapped ? m : n;
+  const int mm = swapped ? n : m;
+  int nn = swapped ? m : n;
   cplx* W = d.work ? d.work : ssm;
   double* sigma = (double*)((char*)ssm + smem_wv_bytes);
-  int* perm = (int*)(sigma + nn);
   __shared__ int sh_rank;
   __shared__ double sh_norm, sh_fro2;
-  for (int idx = threadIdx.x; idx < mm * nn; idx += blockDim.x) {
-    int r = idx % mm, c = idx / mm;
-    cplx v;
-    if (!swapped) v = d.theta[r + (size_t)c * m];
-    else v = cconj(d.theta[c + (size_t)r * m]);        // W = theta'^H
-    W[idx] = v;
+  // ---- row-space reduction (see SvdDesc) ----
+  __shared__ cplx rs_rows[256], rs_basis[256];
+  __shared__ int rs_ro;
+  bool reduced = false;
+  if (d.rs_gate && !swapped && !d.work) {
+    const int dd = d.rs_d, d2 = dd * dd;
+    // rows e1 = (s1', s1), columns e2 = (s2', s2) of the gate o[s1', s2', s1, s2]
+    for (int idx = threadIdx.x; idx < d2 * d2; idx += blockDim.x) {
+      const int e1 = idx / d2, e2 = idx - e1 * d2;
+      const int s1p = e1 % dd, s1 = e1 / dd, s2p = e2 % dd, s2 = e2 / dd;
+      rs_rows[idx] = d.rs_gate[s1p + dd * (s2p + dd * (s1 + dd * s2))];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                     // pivoted modified Gram-Schmidt over at most 16 rows of 16 entries
+      double nrm[16], maxn2 = 0;
+      for (int e = 0; e < d2; ++e) { double s = 0; for (int k = 0; k < d2; ++k) s += cabs2(rs_rows[e * d2 + k]); nrm[e] = s; maxn2 = fmax(maxn2, s); }
+      int ro = 0;
+      for (int it = 0; it < d2; ++it) {
+        int best = 0; double bn = -1;
+        for (int e = 0; e < d2; ++e) if (nrm[e] > bn) { bn = nrm[e]; best = e; }
+        if (!(bn > 1e-26 * maxn2) || bn <= 0.0) break;
+        const double inv = 1.0 / sqrt(bn);
+        for (int k = 0; k < d2; ++k) rs_basis[ro * d2 + k] = cscale(rs_rows[best * d2 + k], inv);
+        for (int e = 0; e < d2; ++e) {
+          if (e == best) { nrm[e] = -1; continue; }
+          if (nrm[e] < 0) continue;
+          cplx p = cmake(0, 0);                 // <basis, row_e>
+          for (int k = 0; k < d2; ++k) cfma_ca(p, rs_basis[ro * d2 + k], rs_rows[e * d2 + k]);
+          double s = 0;
+          for (int k = 0; k < d2; ++k) { rs_rows[e * d2 + k] = csub(rs_rows[e * d2 + k], cmul(p, rs_basis[ro * d2 + k])); s += cabs2(rs_rows[e * d2 + k]); }
+          nrm[e] = s;
+        }
+        ++ro;
+      }
+      rs_ro = ro;
+    }
+    __syncthreads();
+    const int ro = rs_ro, rho = ro * d.rs_chi;
+    reduced = ro > 0 && 2 * rho <= n && (d.has_cutoff || (d.maxdim > 0 && d.maxdim <= rho)) && d.mindim <= rho;      // uniform over the CTA
+    if (reduced) {
+      cplx* Q = ssm;                             // n x rho, then W = m x rho behind it: (n + m) rho <= m n
+      W = ssm + (size_t)n * rho;
+      cplx* tau = (cplx*)sigma;                  // rho complex + 1: inside the sigma / perm area, free until the iteration is over
+      for (int idx = threadIdx.x; idx < n * rho; idx += blockDim.x) {
+        const int row = idx % n, col = idx / n;
+        const int cq = row % d.rs_q2, s2p = row / d.rs_q2, k = col % ro, b = col / ro;
+        cplx v = cmake(0, 0);
+        for (int s2 = 0; s2 < dd; ++s2) cfma(v, rs_basis[k * d2 + s2p + dd * s2], d.rs_r2[cq + (size_t)(s2 + dd * b) * d.rs_ld2]);
+        Q[idx] = v;
+      }
+      __syncthreads();
+      house_q_inplace(Q, n, rho, tau, tau + rho);
+      for (int idx = threadIdx.x; idx < m * rho; idx += blockDim.x) {
+        const int i = idx % m, j = idx / m;
+        cplx v = cmake(0, 0);
+        for (int cc = 0; cc < n; ++cc) cfma_cb(v, d.theta[i + (size_t)cc * m], Q[cc + (size_t)j * n]);      // theta' conj(Q)
+        W[idx] = v;
+      }
+      nn = rho;
+    }
+  }
+  int* perm = (int*)(sigma + nn);
+  if (!reduced) {
+    for (int idx = threadIdx.x; idx < mm * nn; idx += blockDim.x) {
+      int r = idx % mm, c = idx / mm;
+      cplx v;
+      if (!swapped) v = d.theta[r + (size_t)c * m];
+      else v = cconj(d.theta[c + (size_t)r * m]);        // W = theta'^H
+      W[idx] = v;
+    }
   }
   __syncthreads();
   int sweeps = jacobi_columns(W, mm, mm, nullptr, 0, 0, nn);

@@ -10,6 +10,8 @@ static void halo_release(tnqs_ctx* c);
 static void drop_pending_gate(tnqs_ctx* c);
 static void gate_graphs_drop(tnqs_ctx* c);
 static bool gate_wpath();
+// TNQS_SVD_ROWSPACE=0: the Jacobi SVD of a gate always iterates the full theta' (no row-space reduction, see SvdDesc)
+static bool svd_rowspace() { const char* e = getenv("TNQS_SVD_ROWSPACE"); return !(e && e[0] == '0'); }
 
 #define API_BEGIN(ctx) if (!(ctx)) return TNQS_ERR_INVALID_ARG; try { CU(cudaSetDevice((ctx)->device));
 #define API_END(ctx) } catch (const TnqsError& e) { (ctx)->err = e.msg; (ctx)->release_temps(); return e.code; } \
@@ -1042,6 +1044,7 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
       s.svals = d_sv + (size_t)i * cap; s.rank = d_rank + i; s.truncerr = d_err + i; s.msg_a = nullptr; s.msg_b = nullptr;
       s.maxdim = o.maxdim; s.has_cutoff = !std::isnan(o.cutoff); s.cutoff = s.has_cutoff ? o.cutoff : 0.0;
       s.normalize = o.normalize_tensors; s.cap = cap; s.mindim = 1;
+      if (svd_rowspace()) { s.rs_gate = t.gate; s.rs_r2 = B.Rbuf; s.rs_q2 = B.q; s.rs_ld2 = B.q; s.rs_d = d; s.rs_chi = A.chib; }
       int mm = std::max(m, nn), mn = std::min(m, nn);
       size_t wv = (size_t)mm * mn * sizeof(cplx);                      // only W = theta' V is iterated (kernels_small.cuh)
       if (wv + mn * 12 + 64 <= 100 * 1024) { s.work = nullptr; svd_smem_wv = std::max(svd_smem_wv, wv); }
