@@ -1269,3 +1269,69 @@ def test_random_circuits_on_random_states_follow_the_oracle(E, seed):
 
 def network_of(E, psi_o, cap):
     return E.TensorNetworkState.from_arrays(psi_o.g, psi_o.tensors, chi_cap=cap)
+
+
+def _gate_of_operator_rank(rs, d, r):
+    """A d^2 x d^2 two-site gate o[s1', s2', s1, s2] = sum_k A_k[s1', s1] B_k[s2', s2] with r generic terms (operator-Schmidt rank r)."""
+    o = np.zeros((d, d, d, d), dtype=np.complex128)
+    for _ in range(r):
+        a = rs.normal(size=(d, d)) + 1j * rs.normal(size=(d, d))
+        b = rs.normal(size=(d, d)) + 1j * rs.normal(size=(d, d))
+        o += np.einsum("ab,cd->acbd", a, b)
+    return o / np.linalg.norm(o) * d
+
+
+@pytest.mark.parametrize("kw", [dict(maxdim=4, cutoff=1e-10, normalize_tensors=True),
+                                dict(maxdim=8, cutoff=1e-12, normalize_tensors=False),
+                                dict(maxdim=None, cutoff=None, normalize_tensors=True),     # no cutoff: the noise ranks of the full theta' are the answer
+                                dict(maxdim=3, cutoff=None, normalize_tensors=True)])
+def test_two_site_gates_of_every_operator_rank(E, kw):
+    # the Jacobi SVD of a gate runs on the row space of theta' when (operator-Schmidt rank of the gate) x chi <= half its columns
+    # (SvdDesc in kernels_small.cuh): ranks 1 and 2 take that path at chi = 4 (theta' 16 x 16 -> 16 x 4 / 16 x 8), ranks 3 and 4 and
+    # every request that would have to report noise ranks take the full one - all against the oracle's LAPACK SVD of theta'
+    g = G.named_grid((4, 4))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=4, seed=71)
+    rs = np.random.default_rng(7)
+    named = [gates.gate_array(("Rzz", [0, 1], 0.37)), gates.gate_array(("Rxx", [0, 1], 1.1)), gates.gate_array(("CNOT", [0, 1])),
+             gates.gate_array(("Rzz", [0, 1], 0.0)), gates.gate_array(("SWAP", [0, 1]))]
+    for gi, grp in enumerate(G.grid_edge_color(g)[:2]):
+        arrs = []
+        for i, e in enumerate(grp):
+            arrs.append(named[(i + gi) % len(named)] if i % 2 else _gate_of_operator_rank(rs, 2, 1 + (i // 2 + gi) % 4))
+        gate_case(E, g, psi_o, grp, arrs, kw, flip=[(i // 2) % 2 for i in range(len(grp))])
+
+
+def test_two_site_gates_of_low_operator_rank_on_qutrits_and_ragged_bonds(E):
+    # d = 3 (a 9 x 9 operator matrix), ragged bonds (theta' not square: the reduction needs m >= n, the other gates run in full)
+    g = G.named_grid((3, 3))
+    rs = np.random.default_rng(8)
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=3, seed=72, d=3)
+    grp = G.grid_edge_color(g)[0]
+    arrs = [_gate_of_operator_rank(rs, 3, 1 + i % 3) for i in range(len(grp))]
+    gate_case(E, g, psi_o, grp, arrs, dict(maxdim=3, cutoff=1e-10, normalize_tensors=True))
+    psi_r = ragged_state(g, [2, 4, 3, 2, 4, 2, 3, 4, 2, 3, 4, 2], 73)
+    for grp in G.grid_edge_color(g)[:2]:
+        arrs = [_gate_of_operator_rank(rs, 2, 1 + i % 2) for i in range(len(grp))]
+        gate_case(E, g, psi_r, grp, arrs, dict(maxdim=4, cutoff=1e-10, normalize_tensors=True), flip=[i % 2 for i in range(len(grp))])
+
+
+def test_row_space_reduction_agrees_with_the_full_svd(E, monkeypatch):
+    # same batch with and without the reduction: ranks equal, singular values to 1e-12, two-site tensors to 1e-10
+    g = G.named_grid((3, 4))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=16, seed=74)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    grp = G.grid_edge_color(g)[0]
+    arrs = [gates.gate_array(("Rzz", [0, 1], 0.1 + 0.2 * i)) for i in range(len(grp))]
+    kw = dict(maxdim=16, cutoff=1e-10, normalize_tensors=True)
+    out = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TNQS_SVD_ROWSPACE", flag)
+        be = E.update(to_engine(psi_o, chi_cap=16), maxiter=4)
+        ranks, errs, sv = E.apply_2site_batch(be, grp, arrs, apply_kwargs=kw)
+        out.append((ranks, errs, sv, be.psi.tensors()))
+    (r1, e1, s1, t1), (r0, e0, s0, t0) = out
+    assert list(r1) == list(r0) and np.allclose(e1, e0, rtol=1e-8, atol=1e-18)
+    assert rel(s1, s0) < 1e-12
+    for e in grp:
+        assert rel(two_site(g, t1, e), two_site(g, t0, e)) < 1e-10
