@@ -940,6 +940,7 @@ __global__ void __launch_bounds__(256, 2) k_close_leg_dmma(const ModeCloseDesc* 
 __global__ void __launch_bounds__(256, 2) k_gram_dmma(const ModeCloseDesc* __restrict__ descs) {
   const ModeCloseDesc d = descs[blockIdx.y];
   if ((int)blockIdx.x >= d.nsplit) return;
+  if (d.need && *d.need == 0) return;
   extern __shared__ double red[];
   constexpr int NSET = 3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1100,10 +1101,16 @@ __global__ void __launch_bounds__(256, 2) k_gram_dmma(const ModeCloseDesc* __res
 // is too ill-conditioned for CholeskyQR2 and the caller falls back to Householder TSQR.
 // One CTA (64 threads) per matrix; dynamic shared memory: 2 * n * n complex.
 // ---------------------------------------------------------------------------------------------------------------
-struct CholDesc { const cplx* g; int n; cplx* rinv; cplx* rtot; int first; int* flag; double tol; };
+// Adaptive second pass: the first pass bounds the 2-norm condition number of its factor from above,
+//   kappa_2(R) <= sqrt(|R|_1 |R|_inf |R^-1|_1 |R^-1|_inf),
+// and clears *need_out when kappa^2 eps is far below the accuracy asked of the factor (bound <= 32: 1024 eps = 2.3e-13) - one pass of
+// CholeskyQR is then as good as two.  The second-pass kernels of that matrix return at once (need_in, ModeCloseDesc::need, the commit
+// word of the leg kernel).  Only used where nothing but R is needed afterwards (the W path of the optimistic gate batches).
+struct CholDesc { const cplx* g; int n; cplx* rinv; cplx* rtot; int first; int* flag; double tol; int* need_out = nullptr; const int* need_in = nullptr; };
 
 __global__ void __launch_bounds__(64) k_chol_inv(const CholDesc* __restrict__ descs) {
   const CholDesc d = descs[blockIdx.x];
+  if (d.need_in && *d.need_in == 0) return;
   extern __shared__ cplx csm[];
   const int n = d.n, tid = threadIdx.x;
   cplx* R = csm;                   // upper triangular factor, column-major n x n
@@ -1164,4 +1171,23 @@ __global__ void __launch_bounds__(64) k_chol_inv(const CholDesc* __restrict__ de
     }
   }
   if (tid == 0 && bad) *d.flag = 1;
+  if (d.need_out) {
+    __shared__ double nrm[4][64];
+    __syncthreads();
+    for (int c = tid; c < n; c += blockDim.x) {
+      double rc = 0, rr = 0, xc = 0, xr = 0;
+      for (int i = 0; i < n; ++i) {
+        rc += sqrt(cabs2(R[i + (size_t)c * n])); rr += sqrt(cabs2(R[c + (size_t)i * n]));
+        xc += sqrt(cabs2(csm[(size_t)n * n + i + (size_t)c * n])); xr += sqrt(cabs2(csm[(size_t)n * n + c + (size_t)i * n]));
+      }
+      nrm[0][c] = rc; nrm[1][c] = rr; nrm[2][c] = xc; nrm[3][c] = xr;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double m[4] = {0, 0, 0, 0};
+      for (int k = 0; k < 4; ++k) for (int c = 0; c < n; ++c) m[k] = fmax(m[k], nrm[k][c]);
+      const double bound = sqrt(m[0] * m[1] * m[2] * m[3]);
+      *d.need_out = (!bad && bound <= 32.0) ? 0 : 1;
+    }
+  }
 }

@@ -96,6 +96,7 @@ struct ModeCloseDesc {
   int L, R, n, np;
   long long a_sb, a_sr, b_sb, b_sr;
   int nsplit; long long rows_per_split;
+  const int* need = nullptr;        // k_gram_dmma only: the item is skipped when *need == 0 (adaptive second pass of CholeskyQR2)
 };
 
 #define MC_SMEM 2048      // complex elements of shared staging (32 KB)

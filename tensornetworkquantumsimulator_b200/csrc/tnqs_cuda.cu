@@ -11,6 +11,8 @@ static void drop_pending_gate(tnqs_ctx* c);
 static void gate_graphs_drop(tnqs_ctx* c);
 static bool gate_wpath();
 // TNQS_SVD_ROWSPACE=0: the Jacobi SVD of a gate always iterates the full theta' (no row-space reduction, see SvdDesc)
+// TNQS_CHOL_ADAPTIVE=0: CholeskyQR2 always runs both passes
+static bool chol_adaptive() { const char* e = getenv("TNQS_CHOL_ADAPTIVE"); return !(e && e[0] == '0'); }
 static bool svd_rowspace() { const char* e = getenv("TNQS_SVD_ROWSPACE"); return !(e && e[0] == '0'); }
 
 #define API_BEGIN(ctx) if (!(ctx)) return TNQS_ERR_INVALID_ARG; try { CU(cudaSetDevice((ctx)->device));
@@ -950,6 +952,15 @@ void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const d
         Qb[i] = c->talloc<cplx>((size_t)J.Po * J.nc); G[i] = c->talloc<cplx>((size_t)J.nc * J.nc);
         Rinv[i] = c->talloc<cplx>((size_t)J.nc * J.nc); part[i] = c->talloc<cplx>((size_t)nsplit * J.nc * J.nc);
       }
+      // W path (optimistic batches, square R): nothing but R is used afterwards, so a matrix whose first factor is provably
+      // well-conditioned skips its second pass on the device (CholDesc in kernels_dmma.cuh)
+      int* d_need = nullptr;
+      std::vector<char> adaptive(nj, 0);
+      if (optimistic && chol_adaptive() && gate_wpath() && !dmma_disabled()) {
+        bool any = false;
+        for (int i = 0; i < nj; ++i) { const SiteJob& J = jobs[chol_list[i]]; adaptive[i] = J.q == J.nc && J.nc <= 64; any = any || adaptive[i]; }
+        if (any) { d_need = c->talloc<int>(nj); CU(cudaMemsetAsync(d_need, 1, nj * sizeof(int), c->stream)); }
+      }
       for (int pass = 0; pass < 2; ++pass) {
         std::vector<ModeCloseDesc> mc(nj); std::vector<CloseReduceDesc> rd(nj); std::vector<CholDesc> cd(nj); std::vector<ModeApplyDesc> ma(nj);
         size_t maxnn = 1; int maxn = 1;
@@ -964,9 +975,11 @@ void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const d
           r.partial = part[i]; r.nsplit = ns; r.n = J.nc; r.np = J.nc; r.dst = G[i]; r.prev = nullptr; r.diff = nullptr; r.mode = 0; r.normalize = 0; r.hermitize = 0;
           CholDesc& k = cd[i];
           k.g = G[i]; k.n = J.nc; k.rinv = Rinv[i]; k.rtot = J.Rbuf; k.first = pass == 0; k.flag = d_flag + i; k.tol = 1e-11;
+          if (d_need && adaptive[i]) { if (pass == 0) k.need_out = d_need + i; else { k.need_in = d_need + i; m.need = d_need + i; } }
           ModeApplyDesc& a = ma[i];
           a.in = src; a.out = Qb[i]; a.m = Rinv[i]; a.L = (int)J.Po; a.n = J.nc; a.np = J.nc; a.R = 1;
           a.in_sb = J.Po; a.in_sr = 0; a.out_sb = J.Po; a.out_sr = 0; a.ldm = J.nc; a.flags = 0;
+          if (d_need && adaptive[i]) a.commit = d_need + i;               // Q1 feeds the second Gram matrix only
           maxnn = std::max(maxnn, (size_t)J.nc * J.nc); maxn = std::max(maxn, J.nc);
         }
         ModeCloseDesc* dmc = c->upload(mc);
@@ -975,7 +988,14 @@ void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const d
         LAUNCH(c, TNQS_KC_QR, k_close_reduce, nj, 256, maxnn * sizeof(cplx), drd);
         CholDesc* dcd = c->upload(cd);
         LAUNCH(c, TNQS_KC_QR, k_chol_inv, nj, 64, 2 * (size_t)maxn * maxn * sizeof(cplx), dcd);
-        if (pass == 0) launch_mode_apply(c, TNQS_KC_QR, ma);        // Q1 = A R1^-1; the second factor R2^-1 stays pending (colfix)
+        if (pass == 0) {                                            // Q1 = A R1^-1; the second factor R2^-1 stays pending (colfix)
+          if (d_need) {                                             // the two-leg instantiation honours the commit word
+            ModeApplyDesc* dma = c->upload(ma);
+            ApplyLaunch al = plan_apply_launch(ma.data(), ma.size());
+            REQUIRE(al.dmma, TNQS_ERR_UNSUPPORTED, "adaptive CholeskyQR2 needs the tensor-core leg kernel");
+            LAUNCH(c, TNQS_KC_QR, k_leg_canon_dmma, al.grid, 256, al.smem, dma, al.tpc);
+          } else launch_mode_apply(c, TNQS_KC_QR, ma);
+        }
       }
       for (int i = 0; i < nj; ++i) { jobs[chol_list[i]].Q = Qb[i]; jobs[chol_list[i]].colfix = Rinv[i]; }
       d_chol_flag = d_flag; chol_pending = true;

@@ -1335,3 +1335,36 @@ def test_row_space_reduction_agrees_with_the_full_svd(E, monkeypatch):
     assert rel(s1, s0) < 1e-12
     for e in grp:
         assert rel(two_site(g, t1, e), two_site(g, t0, e)) < 1e-10
+
+
+def test_adaptive_second_cholesky_pass(E, monkeypatch):
+    # CholeskyQR2 of the optimistic W path drops its second pass for matrices whose first factor is provably well-conditioned
+    # (bound on kappa_2 <= 32): same ranks, singular values and two-site tensors as the two-pass run for a random (well-conditioned)
+    # state, and an ill-conditioned state (site tensors with a graded leg) keeps the second pass and stays on the oracle
+    g = G.named_grid((3, 4))
+    grp = G.grid_edge_color(g)[0]
+    arrs = [gates.gate_array(("Rzz", [0, 1], 0.1 + 0.2 * i)) for i in range(len(grp))]
+    kw = dict(maxdim=16, cutoff=1e-10, normalize_tensors=True)
+    for graded in (False, True):
+        psi_o = O.random_tensornetworkstate(g, bond_dimension=16, seed=75)
+        for v in range(g.nv):
+            if graded:                                         # columns of the matricised tensor spread over two and a half decades
+                scale = np.logspace(0, -2.5, 16)
+                shape = [1] * psi_o.tensors[v].ndim
+                shape[1] = 16
+                psi_o.tensors[v] = psi_o.tensors[v] * scale.reshape(shape)
+            psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+        out = []
+        for flag in ("1", "0"):
+            monkeypatch.setenv("TNQS_CHOL_ADAPTIVE", flag)
+            be = E.update(to_engine(psi_o, chi_cap=16), maxiter=4)
+            n0 = be.psi.kernel_launches()
+            ranks, errs, sv = E.apply_2site_batch(be, grp, arrs, apply_kwargs=kw)
+            out.append((ranks, errs, sv, be.psi.tensors(), be.psi.kernel_launches() - n0))
+        (r1, e1, s1, t1, l1), (r0, e0, s0, t0, l0) = out
+        assert list(r1) == list(r0)
+        assert rel(s1, s0) < 1e-11
+        for e in grp:
+            assert rel(two_site(g, t1, e), two_site(g, t0, e)) < 1e-9
+        monkeypatch.setenv("TNQS_CHOL_ADAPTIVE", "1")
+        gate_case(E, g, psi_o, grp, arrs, kw, sweeps=4)
