@@ -753,7 +753,11 @@ __global__ void __launch_bounds__(256, 2) k_leg_dmma_t(const ModeApplyDesc* __re
   const int G = leg_groups(d.np), LDB = leg_ldb(d.np);
   const int rows_per_cta = leg_rows_per_cta(d.np);
   const long long rows = (long long)d.L * d.R;
-  if ((long long)blockIdx.x * tpc * rows_per_cta >= rows) return;
+  if ((long long)blockIdx.x * tpc * rows_per_cta >= rows) {
+    if (CANON && d.norm2_partial && threadIdx.x == 0) d.norm2_partial[blockIdx.x] = 0.0;
+    return;
+  }
+  double nrm2 = 0.0;
   extern __shared__ double Bs[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = lane >> 2, q = lane & 3;
@@ -835,10 +839,18 @@ __global__ void __launch_bounds__(256, 2) k_leg_dmma_t(const ModeApplyDesc* __re
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = 16 * grp + 4 * j + q;
-      if (c < np) o[CANON ? (c % d.kd) + (long long)(c / d.kd) * out_sb : (long long)c * out_sb] = cmake(acc[t][j][0], acc[t][j][1]);
+      if (c < np) {
+        o[CANON ? (c % d.kd) + (long long)(c / d.kd) * out_sb : (long long)c * out_sb] = cmake(acc[t][j][0], acc[t][j][1]);
+        if (CANON) nrm2 += acc[t][j][0] * acc[t][j][0] + acc[t][j][1] * acc[t][j][1];
+      }
     }
   }
   }   // tiles
+  if (CANON && d.norm2_partial) {
+    __shared__ double nred[8];
+    nrm2 = block_sum(nrm2, nred);
+    if (threadIdx.x == 0) d.norm2_partial[blockIdx.x] = nrm2;
+  }
 }
 
 #define k_leg_dmma k_leg_dmma_t<false>

@@ -16,6 +16,7 @@ struct ModeApplyDesc {
   // index l has stride sl instead of 1, and the contracted / produced index k = k0 + kd * k1 sits at k0 + k1 * sb
   long long in_sl = 1, out_sl = 1; int kd = 1;
   const int* commit = nullptr;     // optimistic gate batches: nothing is written unless *commit != 0
+  double* norm2_partial = nullptr; // k_leg_dmma<true> only: CTA x of the item leaves the sum of |out|^2 over its row tiles in [x] (fixed order)
 };
 
 #define MA_BM 64

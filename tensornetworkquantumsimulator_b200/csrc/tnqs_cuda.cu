@@ -1128,6 +1128,7 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
   if (st & ST_RANK_CAP) throw TnqsError(TNQS_ERR_SHAPE, "kept rank exceeds chi_cap (raise chi_cap or set maxdim)");
   // ---- 8. T' = Q R' (simple_update.jl:57), normalise, back to the canonical layout ----
   std::vector<cplx*> Tm(NJ), newsite(NJ);
+  std::vector<double*> w_partial(NJ, nullptr); int w_npartial = 0;      // per-CTA |T'|^2 of the in-place W products
   {
     // pending column factors of CholeskyQR2: R'' = R2^-1 R' (one small product per site instead of a pass over Q)
     std::vector<cplx*> rfin(NJ, nullptr);
@@ -1162,9 +1163,15 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
         REQUIRE(tsmem <= 160 * 1024, TNQS_ERR_UNSUPPORTED, "triangular solve does not fit shared memory");
         TriSolveDesc* dts = c->upload(ts);
         LAUNCH(c, TNQS_KC_MISC, k_tri_solve, (unsigned)ts.size(), 256, tsmem, dts);
-        ModeApplyDesc* dmw = c->upload(mw);
         ApplyLaunch al = plan_apply_launch(mw.data(), mw.size());
         REQUIRE(al.dmma, TNQS_ERR_UNSUPPORTED, "internal: the in-place two-leg product needs the tensor-core leg kernel");
+        if (o.normalize_tensors) {                    // the kernel leaves |T'|^2 per CTA: no separate pass over the tensor for the norm
+          w_npartial = (int)al.grid.x;
+          double* part = c->talloc<double>((size_t)w_npartial * mw.size());
+          size_t k = 0;
+          for (int j : LJ) if (wpath[j]) { w_partial[j] = part + k * w_npartial; mw[k].norm2_partial = w_partial[j]; ++k; }
+        }
+        ModeApplyDesc* dmw = c->upload(mw);
         LAUNCH(c, TNQS_KC_MODE_APPLY, k_leg_canon_dmma, al.grid, 256, al.smem, dmw, al.tpc);
       }
     }
@@ -1188,7 +1195,9 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
     std::vector<ScaleDesc> sw;
     for (int j : LJ) {
       const bool w = !wpath.empty() && wpath[j];
-      Norm2Desc x; x.x = w ? c->site[jobs[j].v] : Tm[j]; x.n = jobs[j].Po * jobs[j].d * ranks[j / 2]; x.out = d_n2 + j; x.partial = nullptr; x.npartial = 0; nd.push_back(x);
+      Norm2Desc x; x.x = w ? c->site[jobs[j].v] : Tm[j]; x.n = jobs[j].Po * jobs[j].d * ranks[j / 2]; x.out = d_n2 + j; x.partial = nullptr; x.npartial = 0;
+      if (w && w_partial[j]) { x.partial = w_partial[j]; x.npartial = w_npartial; }
+      nd.push_back(x);
       if (w) { ScaleDesc sc; sc.x = c->site[jobs[j].v]; sc.n = x.n; sc.scalar = d_n2 + j; sc.mode = 0; sc.commit = d_ok + j / 2; sw.push_back(sc); }
     }
     Norm2Desc* dnd = c->upload(nd);
