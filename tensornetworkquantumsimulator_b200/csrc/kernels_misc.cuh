@@ -50,6 +50,26 @@ __global__ void __launch_bounds__(256) k_gate1(const Gate1Desc* __restrict__ des
   __syncthreads();
   double acc = 0;
   const int d = g.d;
+  if (d == 2) {                                  // qubits: everything in registers, two fibres in flight per thread
+    const cplx o00 = o[0], o10 = o[1], o01 = o[2], o11 = o[3];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; r + stride < g.rest; r += 2 * stride) {
+      const cplx a0 = g.in[2 * r], a1 = g.in[2 * r + 1], b0 = g.in[2 * (r + stride)], b1 = g.in[2 * (r + stride) + 1];
+      cplx y0 = cmake(0, 0), y1 = cmake(0, 0), z0 = cmake(0, 0), z1 = cmake(0, 0);
+      cfma(y0, o00, a0); cfma(y0, o01, a1); cfma(y1, o10, a0); cfma(y1, o11, a1);
+      cfma(z0, o00, b0); cfma(z0, o01, b1); cfma(z1, o10, b0); cfma(z1, o11, b1);
+      acc += cabs2(y0); acc += cabs2(y1); acc += cabs2(z0); acc += cabs2(z1);
+      g.out[2 * r] = y0; g.out[2 * r + 1] = y1; g.out[2 * (r + stride)] = z0; g.out[2 * (r + stride) + 1] = z1;
+    }
+    for (; r < g.rest; r += stride) {
+      const cplx a0 = g.in[2 * r], a1 = g.in[2 * r + 1];
+      cplx y0 = cmake(0, 0), y1 = cmake(0, 0);
+      cfma(y0, o00, a0); cfma(y0, o01, a1); cfma(y1, o10, a0); cfma(y1, o11, a1);
+      acc += cabs2(y0); acc += cabs2(y1);
+      g.out[2 * r] = y0; g.out[2 * r + 1] = y1;
+    }
+  } else
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < g.rest; r += (long long)gridDim.x * blockDim.x) {
     cplx x[4], y[4];
     for (int s = 0; s < d; ++s) x[s] = g.in[r * d + s];
