@@ -514,6 +514,8 @@ def run_engine(args):
         "config": bench_config(nx, ny, chi, 1),
         "gates": {"metric": "two_site_gate_applications_per_sec", "value": gate_value, "unit": "gates/s",
                   "gflop_per_gate_nominal": gflops / 1e9, "achieved_tflops": gate_value * gflops / 1e12,
+                  "flop_count": "nominal count of the reference's algorithm (SURVEY 8d: explicit Q, inverse absorption, full Golub-Reinsch SVD of theta'); "
+                                "the engine executes less of it (R only, T' = psi R^-1 R', SVD on the row space of theta', 3M products)",
                   "frac_of_fp64_peak": gate_value * gflops / 1e12 / pk["fp64_tflops_sustained"]},
         "bp": {"sweeps_per_step": bp_sweeps / args.steps, "gflop_per_message": sweep_flops / len(seq) / 1e9, "achieved_tflops": bp_tf,
                "jacobi_mode_messages_per_s": jacobi_value, "jacobi_mode_frac_of_fp64_peak": jacobi_value * sweep_flops / len(seq) / 1e12 / pk["fp64_tflops_sustained"],
