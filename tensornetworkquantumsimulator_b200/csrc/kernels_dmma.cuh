@@ -887,6 +887,67 @@ __global__ void __launch_bounds__(256, 2) k_close_leg_dmma(const ModeCloseDesc* 
     const int quad = pass * qpp + warp % qpp, slice = warp / qpp;
     const bool live = quad < nquad && warp < qpp * nslice;
     const int mq = quad % qm, nq = quad / qm;
+#if TNQS_3M_CLOSE
+    // 3M form (as close_dmma_item): lanes load whole complex elements (16 bytes, each element by one lane), 12 DMMAs per four rows
+    double t1[2][2][2], t2[2][2][2], t3[2][2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { t1[i][j][0] = t1[i][j][1] = t2[i][j][0] = t2[i][j][1] = t3[i][j][0] = t3[i][j][1] = 0.0; }
+    if (live) {
+      for (long long k0 = r_begin + 4 * slice; k0 < r_end; k0 += 4 * nslice) {
+        const long long row = k0 + q;
+        const bool ok = row < r_end;
+        long long rr = ok ? row / d.L : 0, l = ok ? row - rr * d.L : 0;
+        const long long aoff = l + rr * d.a_sr, boff = l + rr * d.b_sr;
+        cplx a[2], b[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int ba = 16 * mq + 8 * t + r, bb = 16 * nq + 8 * t + r;
+          a[t] = (ok && ba < n) ? d.a[aoff + (long long)ba * d.a_sb] : cmake(0, 0);
+          b[t] = (ok && bb < np) ? d.b[boff + (long long)bb * d.b_sb] : cmake(0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) dmma884(t1[i][j][0], t1[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) dmma884(t2[i][j][0], t2[i][j][1], a[i].y, b[j].y);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) dmma884(t3[i][j][0], t3[i][j][1], a[i].x + a[i].y, b[j].x - b[j].y);
+      }
+    }
+    // this warp's 16 x 16 complex quadrant -> shared memory, then a fixed-order sum over the K-slices
+    double* mine = red + (size_t)warp * 1024;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int lb = 8 * i + r, lbp = 8 * j + 2 * q + e;
+          mine[lb + 16 * (2 * lbp)] = t1[i][j][e] + t2[i][j][e];
+          mine[lb + 16 * (2 * lbp + 1)] = t3[i][j][e] - t1[i][j][e] + t2[i][j][e];
+        }
+    __syncthreads();
+    for (int idx = tid; idx < n * np; idx += blockDim.x) {
+      const int b = idx % n, bp = idx / n;
+      const int qd = (b >> 4) + qm * (bp >> 4);
+      if (qd / qpp != pass) continue;
+      const int lb = b & 15, lbp = bp & 15;
+      double re = 0, im = 0;
+      for (int sl = 0; sl < nslice; ++sl) {
+        const double* P = red + (size_t)(qd % qpp + qpp * sl) * 1024;
+        re += P[lb + 16 * (2 * lbp)];
+        im += P[lb + 16 * (2 * lbp + 1)];
+      }
+      out[idx] = cmake(re, im);
+    }
+#else
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -937,6 +998,7 @@ __global__ void __launch_bounds__(256, 2) k_close_leg_dmma(const ModeCloseDesc* 
       }
       out[idx] = cmake(rr + ii, ir - ri);
     }
+#endif
     __syncthreads();
   }
 }
