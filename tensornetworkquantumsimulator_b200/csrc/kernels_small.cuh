@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(512, 2) k_svd_trunc(const SvdDesc* __restrict_
   __shared__ cplx rs_rows[256], rs_basis[256];
   __shared__ int rs_ro;
   bool reduced = false;
-  if (d.rs_gate && !swapped && !d.work) {
+  if (d.rs_gate && !swapped) {
     const int dd = d.rs_d, d2 = dd * dd;
     // rows e1 = (s1', s1), columns e2 = (s2', s2) of the gate o[s1', s2', s1, s2]
     for (int idx = threadIdx.x; idx < d2 * d2; idx += blockDim.x) {
@@ -464,9 +464,13 @@ __global__ void __launch_bounds__(512, 2) k_svd_trunc(const SvdDesc* __restrict_
     __syncthreads();
     const int ro = rs_ro, rho = ro * d.rs_chi;
     reduced = ro > 0 && 2 * rho <= n && (d.has_cutoff || (d.maxdim > 0 && d.maxdim <= rho)) && d.mindim <= rho;      // uniform over the CTA
+    // theta' too large for shared memory (d.work != null): the reduced matrix may still fit - Q is built in shared memory, W goes to
+    // the global work buffer first and moves into shared memory once Q is dead (the host sized the buffer for the rank of the gates
+    // it saw; another rank at a graph replay falls back to the full iteration in global memory)
+    if (d.work && (size_t)m * rho * sizeof(cplx) > smem_wv_bytes) reduced = false;
     if (reduced) {
       cplx* Q = ssm;                             // n x rho, then W = m x rho behind it: (n + m) rho <= m n
-      W = ssm + (size_t)n * rho;
+      W = d.work ? d.work : ssm + (size_t)n * rho;
       cplx* tau = (cplx*)sigma;                  // rho complex + 1: inside the sigma / perm area, free until the iteration is over
       for (int idx = threadIdx.x; idx < n * rho; idx += blockDim.x) {
         const int row = idx % n, col = idx / n;
@@ -482,6 +486,11 @@ __global__ void __launch_bounds__(512, 2) k_svd_trunc(const SvdDesc* __restrict_
         cplx v = cmake(0, 0);
         for (int cc = 0; cc < n; ++cc) cfma_cb(v, d.theta[i + (size_t)cc * m], Q[cc + (size_t)j * n]);      // theta' conj(Q)
         W[idx] = v;
+      }
+      if (d.work) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < m * rho; idx += blockDim.x) ssm[idx] = d.work[idx];
+        W = ssm;
       }
       nn = rho;
     }

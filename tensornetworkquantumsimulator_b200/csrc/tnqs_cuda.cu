@@ -13,6 +13,40 @@ static bool gate_wpath();
 // TNQS_SVD_ROWSPACE=0: the Jacobi SVD of a gate always iterates the full theta' (no row-space reduction, see SvdDesc)
 // TNQS_CHOL_ADAPTIVE=0: CholeskyQR2 always runs both passes
 static bool chol_adaptive() { const char* e = getenv("TNQS_CHOL_ADAPTIVE"); return !(e && e[0] == '0'); }
+// Operator-Schmidt rank of a two-site gate o[s1', s2', s1, s2] over the (site 1 | site 2) cut: the same pivoted Gram-Schmidt and
+// threshold as k_svd_trunc (which decides for itself; the host only needs the number to size shared memory)
+static int gate_operator_rank(const cplx* g, int d) {
+  const int d2 = d * d;
+  std::vector<cplx> rows((size_t)d2 * d2), basis((size_t)d2);
+  for (int e1 = 0; e1 < d2; ++e1) for (int e2 = 0; e2 < d2; ++e2) {
+    const int s1p = e1 % d, s1 = e1 / d, s2p = e2 % d, s2 = e2 / d;
+    rows[(size_t)e1 * d2 + e2] = g[s1p + d * (s2p + d * (s1 + d * s2))];
+  }
+  std::vector<double> nrm(d2); double maxn2 = 0;
+  for (int e = 0; e < d2; ++e) { double s = 0; for (int k = 0; k < d2; ++k) { const cplx x = rows[(size_t)e * d2 + k]; s += x.x * x.x + x.y * x.y; } nrm[e] = s; maxn2 = std::max(maxn2, s); }
+  int ro = 0;
+  for (int it = 0; it < d2; ++it) {
+    int best = 0; double bn = -1;
+    for (int e = 0; e < d2; ++e) if (nrm[e] > bn) { bn = nrm[e]; best = e; }
+    if (!(bn > 1e-26 * maxn2) || bn <= 0.0) break;
+    const double inv = 1.0 / std::sqrt(bn);
+    for (int k = 0; k < d2; ++k) { const cplx x = rows[(size_t)best * d2 + k]; basis[k] = cmake(x.x * inv, x.y * inv); }
+    for (int e = 0; e < d2; ++e) {
+      if (e == best) { nrm[e] = -1; continue; }
+      if (nrm[e] < 0) continue;
+      double pr = 0, pi = 0;
+      for (int k = 0; k < d2; ++k) { const cplx b = basis[k], x = rows[(size_t)e * d2 + k]; pr += b.x * x.x + b.y * x.y; pi += b.x * x.y - b.y * x.x; }
+      double s = 0;
+      for (int k = 0; k < d2; ++k) {
+        cplx& x = rows[(size_t)e * d2 + k]; const cplx b = basis[k];
+        x.x -= pr * b.x - pi * b.y; x.y -= pr * b.y + pi * b.x; s += x.x * x.x + x.y * x.y;
+      }
+      nrm[e] = s;
+    }
+    ++ro;
+  }
+  return ro;
+}
 static bool svd_rowspace() { const char* e = getenv("TNQS_SVD_ROWSPACE"); return !(e && e[0] == '0'); }
 
 #define API_BEGIN(ctx) if (!(ctx)) return TNQS_ERR_INVALID_ARG; try { CU(cudaSetDevice((ctx)->device));
@@ -1044,7 +1078,7 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
   d_rank = c->talloc<int>(n); d_err = c->talloc<double>(n); d_sv = c->talloc<double>((size_t)n * cap);
   cplx* d_gates = c->talloc<cplx>((size_t)n * 256);
   std::vector<cplx*> r1n(n), r2n(n);
-  size_t svd_smem_wv = 0; int svd_maxn = 2; bool any_global = false;
+  size_t svd_smem_wv = 0; int svd_maxn = 2; bool any_global = false; int last_ro = 0, last_d = 0; const cplx* last_g = nullptr;
   {
     size_t goff = 0; std::vector<cplx> hg;
     for (int i = 0; i < n; ++i) {
@@ -1068,7 +1102,15 @@ void GateBatch::stage2(const cplx* xrecv, int32_t* ranks_out, double* err_out, d
       int mm = std::max(m, nn), mn = std::min(m, nn);
       size_t wv = (size_t)mm * mn * sizeof(cplx);                      // only W = theta' V is iterated (kernels_small.cuh)
       if (wv + mn * 12 + 64 <= 100 * 1024) { s.work = nullptr; svd_smem_wv = std::max(svd_smem_wv, wv); }
-      else { s.work = c->talloc<cplx>(wv / sizeof(cplx)); any_global = true; }
+      else {
+        s.work = c->talloc<cplx>(wv / sizeof(cplx)); any_global = true;
+        if (s.rs_gate && m >= nn) {              // the row-space matrix of theta' may fit shared memory although theta' does not
+          if (!last_g || last_d != d || memcmp(g, last_g, (size_t)d4 * sizeof(cplx)) != 0) { last_ro = gate_operator_rank(g, d); last_g = g; last_d = d; }
+          const size_t rho = (size_t)last_ro * A.chib, need = (size_t)m * rho * sizeof(cplx);
+          if (2 * rho <= (size_t)nn && (s.has_cutoff || (s.maxdim > 0 && (size_t)s.maxdim <= rho)) && need + mn * 12 + 64 <= 190 * 1024)
+            svd_smem_wv = std::max(svd_smem_wv, need);
+        }
+      }
       svd_maxn = std::max(svd_maxn, mn);
     }
     c->h2d(d_gates, hg.data(), hg.size() * sizeof(cplx));

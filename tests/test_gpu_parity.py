@@ -1368,3 +1368,25 @@ def test_adaptive_second_cholesky_pass(E, monkeypatch):
             assert rel(two_site(g, t1, e), two_site(g, t0, e)) < 1e-9
         monkeypatch.setenv("TNQS_CHOL_ADAPTIVE", "1")
         gate_case(E, g, psi_o, grp, arrs, kw, sweeps=4)
+
+
+@pytest.mark.parametrize("shape,chi", [((3, 2), 32), ((3, 3), 24)])
+def test_low_rank_gates_at_large_bond(E, shape, chi):
+    # theta' (128 x 128 at chi = 32) does not fit shared memory, its row-space matrix (128 x 64 for an Rzz) does: the Jacobi
+    # iteration then runs in shared memory on W = theta' conj(Q) staged through the global work buffer; mixed with full-rank gates
+    # (global iteration on theta') in one batch
+    g = G.named_grid(shape)
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=chi, seed=84)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    rs = np.random.default_rng(5)
+    for gi, grp in enumerate(G.grid_edge_color(g)[:2]):
+        arrs = []
+        for i, e in enumerate(grp):
+            if (i + gi) % 3 == 2:
+                h = rs.normal(size=(4, 4)) + 1j * rs.normal(size=(4, 4))
+                u, _ = np.linalg.qr(h)
+                arrs.append(u.reshape(2, 2, 2, 2))
+            else:
+                arrs.append(gates.gate_array((("Rzz", "Rxx")[i % 2], [0, 1], 0.3 + 0.1 * i)))
+        gate_case(E, g, psi_o, grp, arrs, dict(maxdim=chi, cutoff=1e-10, normalize_tensors=True), sweeps=2, flip=[i % 2 for i in range(len(grp))])
