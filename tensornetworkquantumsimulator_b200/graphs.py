@@ -467,24 +467,37 @@ def edgeinduced_subgraphs_no_leaves(g: Graph, max_number_of_edges: int) -> List[
     found: List[Tuple[int, ...]] = []
     deg = [0] * g.nv
 
-    def nleaves(sub):
-        return sum(1 for e in sub for x in ends[e] if deg[x] == 1)
-
-    def extend(sub: List[int], subset: set, ext: List[int], nbhood: set, anchor: int):
-        leaves = nleaves(sub)
+    def extend(sub: List[int], subset: set, ext: List[int], nbhood: set, anchor: int, leaves: int):
         if leaves == 0:
             found.append(tuple(sorted(sub)))
-        if len(sub) == max_number_of_edges or len(sub) + (leaves + 1) // 2 > max_number_of_edges:
+        room = max_number_of_edges - len(sub)
+        if room == 0 or (leaves + 1) // 2 > room:
             return
+        if leaves > room:
+            # every leaf needs a new edge at it, and one edge serves two leaves only if it joins them: with p such edges
+            # available at most min(p, leaves // 2) edges do double duty
+            p = 0
+            for e in sub:
+                for x in ends[e]:
+                    if deg[x] == 1:
+                        for f in g.incident[x]:
+                            if f not in subset:
+                                y = ends[f][0] if ends[f][1] == x else ends[f][1]
+                                if deg[y] == 1:
+                                    p += 1
+            if leaves - min(p // 2, leaves // 2) > room:
+                return
         ext = list(ext)
         while ext:
             w = ext.pop()
             # exclusive neighbours of w: beyond the anchor, not in the set, not adjacent to the set already
             new = [u for u in adj[w] if u > anchor and u not in subset and u not in nbhood]
             sub.append(w); subset.add(w)
-            for x in ends[w]:
+            lv = leaves
+            for x in ends[w]:                       # a vertex of degree 0 becomes a leaf, a leaf stops being one
+                lv += 1 if deg[x] == 0 else (-1 if deg[x] == 1 else 0)
                 deg[x] += 1
-            extend(sub, subset, ext + new, nbhood | set(new), anchor)
+            extend(sub, subset, ext + new, nbhood | set(new), anchor, lv)
             for x in ends[w]:
                 deg[x] -= 1
             sub.pop(); subset.discard(w)
@@ -493,7 +506,7 @@ def edgeinduced_subgraphs_no_leaves(g: Graph, max_number_of_edges: int) -> List[
         for x in ends[a]:
             deg[x] += 1
         first = [u for u in adj[a] if u > a]
-        extend([a], {a}, first, set(first) | {a}, a)
+        extend([a], {a}, first, set(first) | {a}, a, 2)
         for x in ends[a]:
             deg[x] -= 1
     connected = sorted(set(found), key=lambda c: (len(c), c))
