@@ -16,6 +16,7 @@
 #include "kernels_small.cuh"
 #include "kernels_misc.cuh"
 #include "kernels_dmma.cuh"
+#include "kernels_deep.cuh"
 
 struct TnqsError {
   int code; std::string msg;
@@ -307,6 +308,7 @@ static ApplyLaunch plan_apply_launch(const ModeApplyDesc* d, size_t count) {
 struct SubLevel {
   LaunchRec slab{0, 0, dim3(), 0}, dclose{0, 0, dim3(), 0};   // DMMA fast path (kernels_dmma.cuh)
   LaunchRec fused{0, 0, dim3(), 0};                            // the same chains as one persistent launch (k_bp_level): queue items
+  LaunchRec deep{0, 0, dim3(), 0};                             // degree-5 / degree-6 chains at N = 8 (kernels_deep.cuh): k_deep_absorb + k_deep_close
   int fastN = 0, close_cap = 16;                               // close_cap: split cap of the fast chains (selects the closing CTA size)
   LaunchRec gate1{0, 0, dim3(), 0};
   std::vector<LaunchRec> steps;
@@ -319,6 +321,7 @@ struct Plan {
   Gate1Desc* d_gate1 = nullptr; ModeApplyDesc* d_apply = nullptr; ModeCloseDesc* d_close = nullptr;
   CloseReduceDesc* d_reduce = nullptr; int* d_commit = nullptr;
   SlabDesc* d_slab = nullptr; CloseDmmaDesc* d_dclose = nullptr; int* d_ticket = nullptr;
+  DeepDesc* d_deep = nullptr;
   int2* d_items = nullptr; int* d_qctr = nullptr; int* d_slab_done = nullptr;       // k_bp_level / k_bp_sweep queue, its counters, per-chain slab counters
   // whole-sweep persistent launch (k_bp_sweep): every chain of every level in one data-flow queue
   bool sweep = false; int sweepN = 0, sweep_items = 0; dim3 sweep_grid; size_t sweep_smem = 0;
@@ -328,7 +331,7 @@ struct Plan {
   // storage: a rebuilt plan of the same shape reuses the buffers of its predecessor, so device addresses (and a CUDA graph
   // captured over them) stay valid when only the site pointers inside the descriptors changed
   cplx* scratch = nullptr; size_t scratch_elems = 0; cplx* partial = nullptr; size_t partial_elems = 0;
-  size_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // descriptor counts: gate1, apply, close, reduce, commit, slab, dclose, queue items
+  size_t cnt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};    // descriptor counts: gate1, apply, close, reduce, commit, slab, dclose, queue items, deep
   int nlaunch = 0;                   // kernel launches per run
   double flops = 0;                  // executed flops per run of the plan (8 per complex MAC)
 };
@@ -353,6 +356,28 @@ static int fast_path_N(const tnqs_ctx* c, const Chain& ch) {
     ++expect_leg;
   }
   return N;
+}
+
+// Deep path eligibility (kernels_deep.cuh): BP-type chain on a vertex of degree 5 or 6 with site dimension 2 and every leg of
+// dimension 8, plain 8 x 8 matrices on all other legs in leg order.  Returns the extent of the fifth absorbed leg (8, or 1 when there
+// are four) or 0.  TNQS_DEEP=0 sends these chains down the generic leg-by-leg path.
+static bool deep_disabled() {
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("TNQS_DEEP"); disabled = (e && e[0] == '0') ? 1 : 0; }
+  return disabled == 1;
+}
+static int deep_path_E4(const tnqs_ctx* c, const Chain& ch) {
+  if (dmma_disabled() || deep_disabled() || ch.op || ch.close_leg < 0) return 0;
+  const int v = ch.v, z = (int)c->inc[v].size(), F = (int)ch.absorb.size();
+  if (c->d[v] != 2 || F != z - 1 || F < 4 || F > 5) return 0;
+  for (int e : c->inc[v]) if (c->chi[e] != 8) return 0;
+  int expect_leg = 0;
+  for (const Absorb& ab : ch.absorb) {
+    if (expect_leg == ch.close_leg) ++expect_leg;
+    if (ab.leg != expect_leg || ab.flags != 0 || ab.ldm != 8) return 0;
+    ++expect_leg;
+  }
+  return F == 5 ? 8 : 1;
 }
 
 // Build a plan for `levels` (vector of vector of chains).  All device buffers are temporaries of the current call.
@@ -385,7 +410,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
   std::vector<Gate1Desc> g1; std::vector<ModeApplyDesc> ma; std::vector<ModeCloseDesc> mc;
   std::vector<CloseReduceDesc> rd; std::vector<int> commit;
-  std::vector<SlabDesc> sd; std::vector<CloseDmmaDesc> dc;
+  std::vector<SlabDesc> sd; std::vector<CloseDmmaDesc> dc; std::vector<DeepDesc> dd;
   std::vector<CloseReduceDesc> frd;            // epilogues of the fast-path chains, in the order of `dc`
   // pass 1: scratch requirement per chain, sub-level split, global scratch sizing
   struct ChainMem { size_t buf_elems; int nbuf; int nsplit; size_t partial_elems; };
@@ -407,7 +432,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
       const Chain& ch = chains[i];
       int nsteps = (ch.op ? 1 : 0) + (int)ch.absorb.size();
       ChainMem cm; cm.buf_elems = (size_t)c->site_n[ch.v]; cm.nbuf = std::min(nsteps, 2); cm.nsplit = 1; cm.partial_elems = 0;
-      if (fN[i]) cm.nbuf = 1;
+      if (fN[i] || deep_path_E4(c, ch)) cm.nbuf = 1;
       mem[L][i] = cm;
       size_t bytes = align_up(cm.buf_elems * sizeof(cplx), 256) * cm.nbuf;
       const bool otherN = fN[i] && curN && fN[i] != curN;
@@ -428,6 +453,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         long long rows = c->site_n[ch.v] / n;
         int ns = (int)std::min<long long>(ch.split_cap, std::max<long long>(1, rows / (ch.split_rows ? ch.split_rows : split_rows())));
         mem[L][i].nsplit = std::max(1, ns);
+        if (deep_path_E4(c, ch)) mem[L][i].nsplit = 2 * 8 * 8;          // one partial per CTA of k_deep_close
         mem[L][i].partial_elems = (size_t)mem[L][i].nsplit * n * n;
         part += mem[L][i].partial_elems;
       }
@@ -527,6 +553,27 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
           }
         }
       }
+      // deep path: degree-5 / degree-6 chains at N = 8
+      sl.deep.off = dd.size();
+      for (size_t j = 0; j < sub.size(); ++j) {
+        const Chain& ch = chains[sub[j]];
+        const int E4 = deep_path_E4(c, ch);
+        if (!E4) continue;
+        fast[j] = 2;
+        const int v = ch.v, F = (int)ch.absorb.size();
+        DeepDesc a; a.t = c->site[v]; a.bt = c->bra_site(v); a.x = buf0[j]; a.partial = partial + fast_poff[j]; a.E4 = E4;
+        long long stride = 2; int ai = 0;
+        for (int l = 0; l < (int)c->inc[v].size(); ++l) {
+          if (l == ch.close_leg) a.gw = stride;
+          else { a.g[ai] = stride; a.m[ai] = ch.absorb[ai].mat; ++ai; }
+          stride *= 8;
+        }
+        for (; ai < 5; ++ai) { a.g[ai] = 0; a.m[ai] = nullptr; }
+        dd.push_back(a);
+        plan.flops += 8.0 * (double)c->site_n[v] * 8 * (F + 1);
+      }
+      sl.deep.count = (int)(dd.size() - sl.deep.off);
+      sl.deep.grid = dim3(2 * 8 * 8, std::max(1, sl.deep.count), 1);
       // one-site operators
       sl.gate1.off = g1.size();
       long long maxrest = 0;
@@ -599,7 +646,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
         if (ch.commit_k >= 0 && !level_staged) r.dst = c->msg(ch.commit_k);
         r.mode = ch.bp_mode; r.normalize = ch.normalize; r.hermitize = ch.hermitize;
         r.dst2 = ch.dst2; r.dst2_pstride = ch.dst2_pstride; r.parity = ch.parity;
-        if (fast[j]) frd.push_back(r); else rd.push_back(r);
+        if (fast[j] == 1) frd.push_back(r); else rd.push_back(r);
         maxnn = std::max(maxnn, (size_t)n * n);
         REQUIRE(n <= 64, TNQS_ERR_UNSUPPORTED, "closing extent > 64 is not supported");
       }
@@ -616,10 +663,11 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
   // fast-path epilogues live behind the generic reduce descriptors in one array; tickets: one int per fast chain
   const size_t nrd_generic = rd.size();
   rd.insert(rd.end(), frd.begin(), frd.end());
-  const size_t cnt[8] = {g1.size(), ma.size(), mc.size(), rd.size(), commit.size(), sd.size(), dc.size(), items.size()};
+  const size_t cnt[9] = {g1.size(), ma.size(), mc.size(), rd.size(), commit.size(), sd.size(), dc.size(), items.size(), dd.size()};
   bool same = reuse_mem;
-  for (int i = 0; i < 8 && same; ++i) same = cnt[i] == reuse->cnt[i];
-  for (int i = 0; i < 8; ++i) plan.cnt[i] = cnt[i];
+  for (int i = 0; i < 9 && same; ++i) same = cnt[i] == reuse->cnt[i];
+  for (int i = 0; i < 9; ++i) plan.cnt[i] = cnt[i];
+  plan.d_deep = upload_into(c, same ? reuse->d_deep : nullptr, dd);
   plan.d_gate1 = upload_into(c, same ? reuse->d_gate1 : nullptr, g1); plan.d_apply = upload_into(c, same ? reuse->d_apply : nullptr, ma);
   plan.d_close = upload_into(c, same ? reuse->d_close : nullptr, mc); plan.d_reduce = upload_into(c, same ? reuse->d_reduce : nullptr, rd);
   plan.d_commit = upload_into(c, same ? reuse->d_commit : nullptr, commit);
@@ -636,7 +684,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
     CU(cudaMemsetAsync(plan.d_slab_done, 0, (sd.size() + 1) * sizeof(int), c->stream));
   }
   for (const LevelPlan& lp : plan.levels) {
-    for (const SubLevel& sl : lp.subs) plan.nlaunch += (sl.slab.count ? (sl.fused.count ? 1 : 2) : 0) + (sl.gate1.count ? 1 : 0) + (int)sl.steps.size() + (sl.close.count ? 1 : 0) + (sl.reduce.count ? 1 : 0);
+    for (const SubLevel& sl : lp.subs) plan.nlaunch += (sl.slab.count ? (sl.fused.count ? 1 : 2) : 0) + (sl.deep.count ? 2 : 0) + (sl.gate1.count ? 1 : 0) + (int)sl.steps.size() + (sl.close.count ? 1 : 0) + (sl.reduce.count ? 1 : 0);
     plan.nlaunch += lp.commit_count ? 1 : 0;
   }
   return plan;
@@ -842,13 +890,13 @@ static bool same_launches(const Plan& a, const Plan& b) {
                       a.sweep_commit == b.sweep_commit && a.d_items == b.d_items && a.d_qctr == b.d_qctr && a.d_slab == b.d_slab && a.d_dclose == b.d_dclose &&
                       a.d_chains == b.d_chains && a.d_slab_done == b.d_slab_done && a.d_chain_done == b.d_chain_done && a.d_commit == b.d_commit;
   if (a.levels.size() != b.levels.size() || a.d_slab != b.d_slab || a.d_items != b.d_items || a.d_qctr != b.d_qctr || a.d_slab_done != b.d_slab_done || a.d_apply != b.d_apply || a.d_close != b.d_close ||
-      a.d_reduce != b.d_reduce || a.d_dclose != b.d_dclose || a.d_gate1 != b.d_gate1 || a.d_commit != b.d_commit) return false;
+      a.d_reduce != b.d_reduce || a.d_dclose != b.d_dclose || a.d_gate1 != b.d_gate1 || a.d_commit != b.d_commit || a.d_deep != b.d_deep) return false;
   for (size_t L = 0; L < a.levels.size(); ++L) {
     const LevelPlan &x = a.levels[L], &y = b.levels[L];
     if (x.subs.size() != y.subs.size() || x.commit_off != y.commit_off || x.commit_count != y.commit_count) return false;
     for (size_t i = 0; i < x.subs.size(); ++i) {
       const SubLevel &p = x.subs[i], &q = y.subs[i];
-      if (p.fastN != q.fastN || p.close_cap != q.close_cap || p.steps.size() != q.steps.size() || !same_rec(p.slab, q.slab) || !same_rec(p.dclose, q.dclose) || !same_rec(p.fused, q.fused) ||
+      if (p.fastN != q.fastN || p.close_cap != q.close_cap || p.steps.size() != q.steps.size() || !same_rec(p.slab, q.slab) || !same_rec(p.dclose, q.dclose) || !same_rec(p.fused, q.fused) || !same_rec(p.deep, q.deep) ||
           !same_rec(p.gate1, q.gate1) || !same_rec(p.close, q.close) || !same_rec(p.reduce, q.reduce)) return false;
       for (size_t j = 0; j < p.steps.size(); ++j) if (!same_rec(p.steps[j], q.steps[j])) return false;
     }
@@ -902,6 +950,10 @@ static void run_plan(tnqs_ctx* c, const Plan& p) {
           LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<8>, sl.slab.grid, SLAB_THREADS, sl.slab.smem, p.d_slab + sl.slab.off);
           LAUNCH(c, TNQS_KC_MODE_CLOSE, k_close_dmma<8>, sl.dclose.grid, close_threads(sl.close_cap), sl.dclose.smem, p.d_dclose + sl.dclose.off);
         }
+      }
+      if (sl.deep.count) {
+        LAUNCH(c, TNQS_KC_MODE_APPLY, k_deep_absorb<8>, sl.deep.grid, DeepCfg<8>::THREADS, DeepCfg<8>::SMEM_A, p.d_deep + sl.deep.off);
+        LAUNCH(c, TNQS_KC_MODE_CLOSE, k_deep_close<8>, sl.deep.grid, DeepCfg<8>::THREADS, DeepCfg<8>::SMEM_B, p.d_deep + sl.deep.off);
       }
       if (sl.gate1.count) LAUNCH(c, TNQS_KC_MISC, k_gate1, sl.gate1.grid, 256, 0, p.d_gate1 + sl.gate1.off);
       for (const LaunchRec& lr : sl.steps) {

@@ -1,0 +1,196 @@
+// FP64 tensor-core (DMMA.8x8x4) path of the BP message update on HIGH-COORDINATION vertices: uniform bond dimension N = 8,
+// site dimension 2, 4 or 5 absorbed legs (degree 5 and 6: the faces and the interior of the 8x8x8 cubic lattice, BASELINE
+// config C4, examples/3dIsing_dynamics.jl).  There the site tensor (8 MiB at degree 6) is 64x larger than anything a CTA can
+// hold and one leg absorption has an arithmetic intensity of 2 flop/B, so a chain of 5 separate leg passes + a closing pass
+// (96 MiB of traffic per message) is HBM-bound at a fifth of the FP64 peak.  Two kernels bring that down to 32 MiB:
+//
+//   k_deep_absorb : one CTA per (s, p4, w) block of 8^4 elements: the first three absorbed legs p0, p1, p2 go through shared
+//                   memory back to back (the slab machinery of k_absorb_slab, batched over the eight values of p3); the result
+//                   is written tile-major, XA[(s, p1', p2')][w][p4][p3][p0'], in full 128-byte runs.
+//   k_deep_close  : one CTA per (s, p1', p2') tile (contiguous 64 KB of XA): absorbs p3 on the way into shared memory and p4 in
+//                   place, then closes G[w, w'] += sum_{p0', p3', p4'} X[p0', p3', p4', w] conj(B[s, p0', p1', p2', p3', p4', w'])
+//                   with the X operand in shared memory and the bra operand streamed from global memory as DMMA fragments:
+//                   the fully absorbed tensor never exists in memory.  Each CTA leaves one N x N partial; k_close_reduce sums
+//                   the 2 N^2 partials of a message in a fixed order and runs the message epilogue.
+// (updated_message, src/MessagePassing/abstractbeliefpropagationcache.jl:144-166; same contraction, another association order.)
+// Complex products are 3M (three real DMMA products), with the fragment-column permutation of absorb_phase (kernels_dmma.cuh).
+#pragma once
+#include "kernels_dmma.cuh"
+
+struct DeepDesc {
+  const cplx* t;          // site tensor (ket), canonical layout T[s, l0 .. l_{z-1}]
+  const cplx* bt;         // bra site tensor of the closing (the ket itself for a norm network), same layout
+  cplx* x;                // tile-major intermediate, 2 N^(F+1) complex
+  cplx* partial;          // 2 N^2 partial results of N x N complex (column-major, M[w + N w'])
+  const cplx* m[5];       // messages of the absorbed legs p0 .. p4, in absorption order (N x N, ld = N)
+  long long g[5];         // canonical strides (complex elements) of p0 .. p4 (g[4] = 0 with four absorbed legs)
+  long long gw;           // canonical stride of the outgoing leg
+  int E4;                 // extent of p4: N (five absorbed legs) or 1 (four)
+};
+
+template <int N> struct DeepCfg {
+  static constexpr int SLAB = N * N * N * N;                                           // one (s, p4, w) block / one tile at E4 = N
+  static constexpr size_t SMEM_A = (size_t)(SLAB + 3 * N * N) * sizeof(cplx);
+  static constexpr int SB = N * N * N + 1;                                             // sub-slab stride of k_deep_close (see there)
+  static constexpr size_t SMEM_B = (size_t)(N * SB + 2 * N * N + 4 * N * N) * sizeof(cplx);
+  static constexpr int THREADS = 128;
+};
+
+// One absorption  out[row, c] = sum_b in[row, b] m[b, c]  over `ntiles` tiles of 8 rows, 3M form.  src(row, b) / dst(row, c) give the
+// addresses; a lane (r, q) loads the elements b = 4 kk + q of row 8 ti + r and stores the columns c = 4 nt + q of the same row, so a
+// phase may run in place when a row's inputs and outputs are the same set of addresses.  The next tile's elements are requested while
+// the current tile multiplies.
+template <int N, class Src, class Dst>
+__device__ __forceinline__ void deep_phase(const cplx* __restrict__ msm, int ntiles, Src src, Dst dst, int lane, int warp, int nwarps) {
+  constexpr int KK = N / 4, NT = N / 4, NT3 = N / 8;
+  const int r = lane >> 2, q = lane & 3;
+  double br[KK][NT3], bi[KK][NT3], bs[KK][NT3];
+#pragma unroll
+  for (int kk = 0; kk < KK; ++kk)
+#pragma unroll
+    for (int nt = 0; nt < NT3; ++nt) {
+      const int b = 4 * kk + q, c = 4 * (2 * nt + (r & 1)) + (r >> 1);
+      const cplx v = msm[b + N * c];
+      br[kk][nt] = v.x; bi[kk][nt] = v.y; bs[kk][nt] = v.x + v.y;
+    }
+  cplx a[KK];
+  int ti = warp;
+  if (ti < ntiles) {
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) a[kk] = *src(8 * ti + r, 4 * kk + q);
+  }
+  for (; ti < ntiles; ti += nwarps) {
+    const int tn = ti + nwarps;
+    const bool more = tn < ntiles;
+    double t1[NT3][2], t2[NT3][2], t3[NT3][2];
+#pragma unroll
+    for (int nt = 0; nt < NT3; ++nt) { t1[nt][0] = t1[nt][1] = t2[nt][0] = t2[nt][1] = t3[nt][0] = t3[nt][1] = 0.0; }
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) {
+      const double ax = a[kk].x, ay = a[kk].y, as = ax + ay;
+#pragma unroll
+      for (int nt = 0; nt < NT3; ++nt) dmma884(t1[nt][0], t1[nt][1], ax, br[kk][nt]);
+#pragma unroll
+      for (int nt = 0; nt < NT3; ++nt) dmma884(t2[nt][0], t2[nt][1], ay, bi[kk][nt]);
+#pragma unroll
+      for (int nt = 0; nt < NT3; ++nt) dmma884(t3[nt][0], t3[nt][1], as, bs[kk][nt]);
+      if (more) a[kk] = *src(8 * tn + r, 4 * kk + q);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT3; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        *dst(8 * ti + r, 4 * (2 * nt + j) + q) = cmake(t1[nt][j] - t2[nt][j], t3[nt][j] - t1[nt][j] - t2[nt][j]);
+  }
+}
+
+// grid: (2 N N, items); block 128; dynamic shared memory DeepCfg<N>::SMEM_A.  CTA x = s + 2 (p4 + E4 w).
+// Shared-memory slab: element (i0, i1, i2, i3) at (i0 ^ f(i1) ^ f(i2)) + N i1 + N^2 i2 + N^3 i3 (the swizzle of k_absorb_slab inside every
+// sub-slab i3 = p3; a quarter-warp never leaves its sub-slab).
+template <int N>
+__global__ void __launch_bounds__(DeepCfg<N>::THREADS, 3) k_deep_absorb(const DeepDesc* __restrict__ descs) {
+  const DeepDesc d = descs[blockIdx.y];
+  const int E4 = d.E4;
+  if ((int)blockIdx.x >= 2 * E4 * N) return;
+  extern __shared__ cplx dsm[];
+  cplx* const sm = dsm;
+  cplx* const msm = dsm + DeepCfg<N>::SLAB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int s = blockIdx.x & 1, rest = blockIdx.x >> 1, p4 = rest % E4, w = rest / E4;
+  for (int idx = threadIdx.x; idx < 3 * N * N; idx += blockDim.x) msm[idx] = __ldg(d.m[idx / (N * N)] + idx % (N * N));
+  __syncthreads();
+  const cplx* const gsrc = d.t + s + (long long)p4 * d.g[4] + (long long)w * d.gw;
+  const long long g0 = d.g[0], g1 = d.g[1], g2 = d.g[2], g3 = d.g[3];
+  auto at = [sm](int i0, int i1, int i2, int i3) -> cplx* { return sm + ((i0 ^ slab_f(i1) ^ slab_f(i2)) + N * i1 + N * N * i2 + N * N * N * i3); };
+  constexpr int NTILES = N * N * N / 8;
+  // p0: rows (p1, p2, p3) straight from global memory -> (i0 = p0', i1 = p1, i2 = p2, i3 = p3)
+  deep_phase<N>(msm, NTILES,
+                [=](int rho, int b) -> const cplx* { return gsrc + (rho % N) * g1 + ((rho / N) % N) * g2 + (rho / (N * N)) * g3 + b * g0; },
+                [=](int rho, int c) -> cplx* { return at(c, rho % N, (rho / N) % N, rho / (N * N)); }, lane, warp, nwarps);
+  __syncthreads();
+  // p1 in place: rows (i0, i2, i3)
+  deep_phase<N>(msm + N * N, NTILES,
+                [=](int rho, int b) -> const cplx* { return at(rho % N, b, (rho / N) % N, rho / (N * N)); },
+                [=](int rho, int c) -> cplx* { return at(rho % N, c, (rho / N) % N, rho / (N * N)); }, lane, warp, nwarps);
+  __syncthreads();
+  // p2: rows (i0 = p0', i1 = p1', i3 = p3) -> XA[(s, p1', p2')][w][p4][p3][p0']
+  const long long TS = (long long)N * N * N * E4;
+  cplx* const gdst = d.x + (long long)N * N * s * TS + (long long)N * N * p4 + (long long)N * N * E4 * w;
+  deep_phase<N>(msm + 2 * N * N, NTILES,
+                [=](int rho, int b) -> const cplx* { return at(rho % N, (rho / N) % N, b, rho / (N * N)); },
+                [=](int rho, int c) -> cplx* { return gdst + ((rho / N) % N + N * c) * TS + rho % N + N * (rho / (N * N)); }, lane, warp, nwarps);
+}
+
+// grid: (2 N N, items); block 128; dynamic shared memory DeepCfg<N>::SMEM_B.  CTA y = p1' + N p2' + N^2 s.
+// Shared-memory slab: element (i0 = p3', i1 = p0', i2 = p4, i3 = w) at (i0 ^ f(i1) ^ f(i2)) + N i1 + N^2 i2 + SB i3 with SB = N^3 + 1: the
+// closing reads 16-byte X elements for 2 values of w x 4 consecutive p0' per quarter-warp - the swizzle spreads the four p0' over the
+// even 16-byte bank groups and the odd sub-slab stride puts the second w on the odd ones.
+template <int N>
+__global__ void __launch_bounds__(DeepCfg<N>::THREADS, 3) k_deep_close(const DeepDesc* __restrict__ descs) {
+  const DeepDesc d = descs[blockIdx.y];
+  const int E4 = d.E4;
+  constexpr int SB = DeepCfg<N>::SB;
+  extern __shared__ cplx dsm[];
+  cplx* const sm = dsm;
+  cplx* const msm = dsm + N * SB;
+  cplx* const red = msm + 2 * N * N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int r = lane >> 2, q = lane & 3;
+  const int y = blockIdx.x, p1 = y % N, p2 = (y / N) % N, s = y / (N * N);
+  for (int idx = threadIdx.x; idx < (E4 == N ? 2 : 1) * N * N; idx += blockDim.x) msm[idx] = __ldg(d.m[3 + idx / (N * N)] + idx % (N * N));
+  __syncthreads();
+  const long long TS = (long long)N * N * N * E4;
+  const cplx* const xt = d.x + (long long)y * TS;
+  auto at = [sm](int i0, int i1, int i2, int i3) -> cplx* { return sm + ((i0 ^ slab_f(i1) ^ slab_f(i2)) + N * i1 + N * N * i2 + SB * i3); };
+  // p3: rows (p0', p4, w) straight from the tile [w][p4][p3][p0']
+  deep_phase<N>(msm, N * E4 * N / 8,
+                [=](int rho, int b) -> const cplx* { return xt + rho % N + N * b + N * N * (rho / N); },
+                [=](int rho, int c) -> cplx* { return at(c, rho % N, (rho / N) % E4, rho / (N * E4)); }, lane, warp, nwarps);
+  __syncthreads();
+  if (E4 == N) {
+    // p4 in place: rows (i0, i1, i3)
+    deep_phase<N>(msm + N * N, N * N * N / 8,
+                  [=](int rho, int b) -> const cplx* { return at(rho % N, (rho / N) % N, b, rho / (N * N)); },
+                  [=](int rho, int c) -> cplx* { return at(rho % N, (rho / N) % N, c, rho / (N * N)); }, lane, warp, nwarps);
+    __syncthreads();
+  }
+  // closing: G[w, w'] = sum_K X[K, w] conj(B[K, w']), K = (p0', p3', p4').  A k-step = four consecutive p0' at one (p3', p4'); lane (r, q)
+  // feeds X[.., w = r] as the A fragment and B[.., w' = r] as the B fragment, and owns G[r][2q], G[r][2q + 1].
+  // X conj(B) in 3M form: T1 = X_r B_r, T2 = X_i B_i, T3 = (X_r + X_i)(B_r - B_i); Re = T1 + T2, Im = T3 - T1 + T2.
+  const cplx* const bt = d.bt + s + (long long)p1 * d.g[1] + (long long)p2 * d.g[2] + (long long)r * d.gw;
+  const long long g0 = d.g[0], g3 = d.g[3], g4 = d.g[4];
+  constexpr int H = N / 4, U = 4;
+  const int steps = H * N * E4;                      // multiples of 4 per warp: 16 E4 steps over 4 warps
+  double t1[2] = {0, 0}, t2[2] = {0, 0}, t3[2] = {0, 0};
+  auto bra = [=](int st) -> const cplx* { const int i1 = 4 * (st % H) + q, i0 = (st / H) % N, i2 = st / (H * N); return bt + i1 * g0 + i0 * g3 + i2 * g4; };
+  auto ket = [=](int st) -> const cplx* { const int i1 = 4 * (st % H) + q, i0 = (st / H) % N, i2 = st / (H * N); return at(i0, i1, i2, r); };
+  cplx bcur[U], bnext[U];
+  int st = warp;
+#pragma unroll
+  for (int u = 0; u < U; ++u) bcur[u] = st + u * nwarps < steps ? __ldg(bra(st + u * nwarps)) : cmake(0, 0);
+  for (; st < steps; st += U * nwarps) {
+    const int sn = st + U * nwarps;
+#pragma unroll
+    for (int u = 0; u < U; ++u) bnext[u] = sn + u * nwarps < steps ? __ldg(bra(sn + u * nwarps)) : cmake(0, 0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (st + u * nwarps < steps) {                 // warp-uniform
+        const cplx xv = *ket(st + u * nwarps), bv = bcur[u];
+        dmma884(t1[0], t1[1], xv.x, bv.x);
+        dmma884(t2[0], t2[1], xv.y, bv.y);
+        dmma884(t3[0], t3[1], xv.x + xv.y, bv.x - bv.y);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) bcur[u] = bnext[u];
+  }
+  // fixed-order sum over the four warps, one partial per CTA
+#pragma unroll
+  for (int j = 0; j < 2; ++j) red[warp * N * N + r + N * (2 * q + j)] = cmake(t1[j] + t2[j], t3[j] - t1[j] + t2[j]);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
+    cplx acc = red[idx];
+    for (int wv = 1; wv < nwarps; ++wv) acc = cadd(acc, red[wv * N * N + idx]);
+    d.partial[(size_t)y * N * N + idx] = acc;
+  }
+}

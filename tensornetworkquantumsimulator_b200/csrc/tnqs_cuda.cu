@@ -105,6 +105,10 @@ static void set_smem_attrs() {   // per device: called at every handle creation 
   // three 72 KB CTAs per SM need the largest shared-memory carve-out
   cudaFuncSetAttribute(k_absorb_slab<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_deep_absorb<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_deep_close<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_deep_absorb<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_deep_close<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 static void alloc_site(tnqs_ctx* c, int v) {

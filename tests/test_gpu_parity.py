@@ -1057,6 +1057,48 @@ def test_bp_regions_of_bond_dimension_8_and_16_in_one_sweep(E, mode):
     check_messages(E, be, bo)
 
 
+@pytest.mark.parametrize("mode", ["jacobi", "reference"])
+def test_bp_high_coordination_vertices_chi8(E, mode):
+    # 3x3x3 cubic lattice at chi = 8 (the C4 geometry in small): corners / edges of degree 3 / 4 on the slab kernels, faces and the
+    # centre of degree 5 / 6 on the deep path (kernels_deep.cuh: three legs through shared memory, the last one or two fused with the
+    # closing).  Two sweeps against the oracle; the same sweeps with TNQS_DEEP=0 (leg-by-leg generic kernels) are covered by
+    # test_deep_path_agrees_with_the_generic_kernels.
+    g = G.named_grid((3, 3, 3))
+    assert sorted(set(g.degree(v) for v in range(g.nv))) == [3, 4, 5, 6]
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=8, seed=29)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    if mode == "jacobi":
+        bo = O.BeliefPropagationCache(psi_o)
+        for _ in range(2):
+            bo.messages = {k: O.updated_message(bo, k) for k in range(2 * g.ne)}
+        be = E.update(to_engine(psi_o, chi_cap=8), maxiter=2, edge_sequence=np.arange(2 * g.ne), mode="jacobi")
+    else:
+        seq = G.forest_cover_edge_sequence(g)
+        bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=2, edge_sequence=seq)
+        be = E.update(to_engine(psi_o, chi_cap=8), maxiter=2, edge_sequence=seq)
+    check_messages(E, be, bo)
+    # <Z> at the centre (degree 6) and on a face (degree 5) after convergence
+    seq = G.forest_cover_edge_sequence(g)
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=30, tolerance=1e-12, edge_sequence=seq)
+    be = E.update(to_engine(psi_o, chi_cap=8), maxiter=30, tolerance=1e-12, edge_sequence=seq)
+    for name in [(2, 2, 2), (2, 2, 1)]:
+        assert abs(E.expect(be, ("Z", [name])) - O.expect(bo, ("Z", [name]))) < EXP_TOL
+
+
+def test_deep_path_with_a_bra_layer(E):
+    # <phi|psi> on the 3x3x3 lattice: the closing of the deep path contracts against the bra's site tensors
+    g = G.named_grid((3, 3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=8, seed=31)
+    phi_o = O.random_tensornetworkstate(g, bond_dimension=8, seed=32)
+    seq = G.forest_cover_edge_sequence(g)
+    psi = E.TensorNetworkState.from_arrays(g, psi_o.tensors, chi_cap=8)
+    phi = E.TensorNetworkState.from_arrays(g, phi_o.tensors, chi_cap=8)
+    bn = E.update(E.bilinear_cache(psi, phi), maxiter=2, edge_sequence=seq, inplace=True)
+    bo = O.update(O.BeliefPropagationCache(psi_o.copy(), {}, phi_o), maxiter=2, edge_sequence=seq)
+    check_messages(E, bn, bo)
+
+
 def test_bilinear_form_outlives_its_cache_and_checks_shapes(E):
     # the bra pointer lives in the ket's device handle: dropping the cache object (or the bra) must not leave it dangling, and a
     # gate that changes the ket's bond dimensions while a bra is attached must be refused by the next BP update
