@@ -28,21 +28,37 @@ struct DeepDesc {
   int E4;                 // extent of p4: N (five absorbed legs) or 1 (four)
 };
 
+#ifndef TNQS_DEEP_THREADS
+#define TNQS_DEEP_THREADS 256
+#endif
+#ifndef TNQS_DEEP_CTAS
+#define TNQS_DEEP_CTAS 3
+#endif
+#ifndef TNQS_DEEP_DEPTH
+#define TNQS_DEEP_DEPTH 2      // row tiles in flight per warp in the phases that read global memory
+#endif
+#ifndef TNQS_DEEP_DEPTH_SMEM
+#define TNQS_DEEP_DEPTH_SMEM 1 // likewise in the phases that run inside shared memory
+#endif
+#ifndef TNQS_DEEP_ABLATE
+#define TNQS_DEEP_ABLATE 0     // experiments only (wrong results): 1 absorb: no global stores, 2 absorb: no in-place phases, 4 close: no closing loop,
+#endif                         // 8 close: no absorption phases, 16 absorb: no global loads
+constexpr int DEEP_THREADS = TNQS_DEEP_THREADS, DEEP_CTAS = TNQS_DEEP_CTAS;
 template <int N> struct DeepCfg {
   static constexpr int SLAB = N * N * N * N;                                           // one (s, p4, w) block / one tile at E4 = N
   static constexpr size_t SMEM_A = (size_t)(SLAB + 3 * N * N) * sizeof(cplx);
   static constexpr int SB = N * N * N + 1;                                             // sub-slab stride of k_deep_close (see there)
-  static constexpr size_t SMEM_B = (size_t)(N * SB + 2 * N * N + 4 * N * N) * sizeof(cplx);
-  static constexpr int THREADS = 128;
+  static constexpr size_t SMEM_B = (size_t)(N * SB + 2 * N * N) * sizeof(cplx);       // the cross-warp reduction reuses the slab
+  static constexpr int THREADS = DEEP_THREADS;
 };
 
 // One absorption  out[row, c] = sum_b in[row, b] m[b, c]  over `ntiles` tiles of 8 rows, 3M form.  src(row, b) / dst(row, c) give the
 // addresses; a lane (r, q) loads the elements b = 4 kk + q of row 8 ti + r and stores the columns c = 4 nt + q of the same row, so a
 // phase may run in place when a row's inputs and outputs are the same set of addresses.  The next tile's elements are requested while
 // the current tile multiplies.
-template <int N, class Src, class Dst>
-__device__ __forceinline__ void deep_phase(const cplx* __restrict__ msm, int ntiles, Src src, Dst dst, int lane, int warp, int nwarps) {
-  constexpr int KK = N / 4, NT = N / 4, NT3 = N / 8;
+template <int N, int D, class Src, class Dst>
+__device__ __forceinline__ void deep_phase(const cplx* __restrict__ msm, int first, int count, Src src, Dst dst, int lane) {
+  constexpr int KK = N / 4, NT3 = N / 8;
   const int r = lane >> 2, q = lane & 3;
   double br[KK][NT3], bi[KK][NT3], bs[KK][NT3];
 #pragma unroll
@@ -53,122 +69,143 @@ __device__ __forceinline__ void deep_phase(const cplx* __restrict__ msm, int nti
       const cplx v = msm[b + N * c];
       br[kk][nt] = v.x; bi[kk][nt] = v.y; bs[kk][nt] = v.x + v.y;
     }
-  cplx a[KK];
-  int ti = warp;
-  if (ti < ntiles) {
+  // tiles first .. first + count - 1, D of them in flight: a[j] holds tile base + j and is refilled with tile base + j + D as soon as
+  // it is consumed
+  const int last = first + count;
+  cplx a[D][KK];
 #pragma unroll
-    for (int kk = 0; kk < KK; ++kk) a[kk] = *src(8 * ti + r, 4 * kk + q);
-  }
-  for (; ti < ntiles; ti += nwarps) {
-    const int tn = ti + nwarps;
-    const bool more = tn < ntiles;
-    double t1[NT3][2], t2[NT3][2], t3[NT3][2];
+  for (int j = 0; j < D; ++j) {
+    if (first + j < last) {
 #pragma unroll
-    for (int nt = 0; nt < NT3; ++nt) { t1[nt][0] = t1[nt][1] = t2[nt][0] = t2[nt][1] = t3[nt][0] = t3[nt][1] = 0.0; }
-#pragma unroll
-    for (int kk = 0; kk < KK; ++kk) {
-      const double ax = a[kk].x, ay = a[kk].y, as = ax + ay;
-#pragma unroll
-      for (int nt = 0; nt < NT3; ++nt) dmma884(t1[nt][0], t1[nt][1], ax, br[kk][nt]);
-#pragma unroll
-      for (int nt = 0; nt < NT3; ++nt) dmma884(t2[nt][0], t2[nt][1], ay, bi[kk][nt]);
-#pragma unroll
-      for (int nt = 0; nt < NT3; ++nt) dmma884(t3[nt][0], t3[nt][1], as, bs[kk][nt]);
-      if (more) a[kk] = *src(8 * tn + r, 4 * kk + q);
+      for (int kk = 0; kk < KK; ++kk) a[j][kk] = *src(8 * (first + j) + r, 4 * kk + q);
     }
+  }
+  for (int base = first; base < last; base += D) {
 #pragma unroll
-    for (int nt = 0; nt < NT3; ++nt)
+    for (int j = 0; j < D; ++j) {
+      const int ti = base + j;
+      if (ti >= last) break;                         // warp-uniform
+      const int tn = ti + D;
+      const bool more = tn < last;
+      double t1[NT3][2], t2[NT3][2], t3[NT3][2];
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
-        *dst(8 * ti + r, 4 * (2 * nt + j) + q) = cmake(t1[nt][j] - t2[nt][j], t3[nt][j] - t1[nt][j] - t2[nt][j]);
+      for (int nt = 0; nt < NT3; ++nt) { t1[nt][0] = t1[nt][1] = t2[nt][0] = t2[nt][1] = t3[nt][0] = t3[nt][1] = 0.0; }
+#pragma unroll
+      for (int kk = 0; kk < KK; ++kk) {
+        const double ax = a[j][kk].x, ay = a[j][kk].y, as = ax + ay;
+#pragma unroll
+        for (int nt = 0; nt < NT3; ++nt) dmma884(t1[nt][0], t1[nt][1], ax, br[kk][nt]);
+#pragma unroll
+        for (int nt = 0; nt < NT3; ++nt) dmma884(t2[nt][0], t2[nt][1], ay, bi[kk][nt]);
+#pragma unroll
+        for (int nt = 0; nt < NT3; ++nt) dmma884(t3[nt][0], t3[nt][1], as, bs[kk][nt]);
+        if (more) a[j][kk] = *src(8 * tn + r, 4 * kk + q);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT3; ++nt)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+          *dst(8 * ti + r, 4 * (2 * nt + jj) + q) = cmake(t1[nt][jj] - t2[nt][jj], t3[nt][jj] - t1[nt][jj] - t2[nt][jj]);
+    }
   }
 }
 
-// grid: (2 N N, items); block 128; dynamic shared memory DeepCfg<N>::SMEM_A.  CTA x = s + 2 (p4 + E4 w).
+// grid: (2 N N, items); block 32 N threads; dynamic shared memory DeepCfg<N>::SMEM_A.  CTA x = s + 2 (p4 + E4 w).
 // Shared-memory slab: element (i0, i1, i2, i3) at (i0 ^ f(i1) ^ f(i2)) + N i1 + N^2 i2 + N^3 i3 (the swizzle of k_absorb_slab inside every
-// sub-slab i3 = p3; a quarter-warp never leaves its sub-slab).
+// sub-slab i3 = p3).  No phase mixes different p3, so WARP p3 OWNS SUB-SLAB p3 through all three phases: after the messages are staged
+// there is no CTA-wide barrier, and the warps of an SM drift apart - the global loads of one overlap the tensor-core phases of another.
 template <int N>
-__global__ void __launch_bounds__(DeepCfg<N>::THREADS, 3) k_deep_absorb(const DeepDesc* __restrict__ descs) {
-  const DeepDesc d = descs[blockIdx.y];
+__global__ void __launch_bounds__(DEEP_THREADS, DEEP_CTAS) k_deep_absorb(const DeepDesc* __restrict__ descs) {
+  static_assert(DEEP_THREADS == 32 * N, "one warp per sub-slab");
+  const DeepDesc& d = descs[blockIdx.y];
   const int E4 = d.E4;
   if ((int)blockIdx.x >= 2 * E4 * N) return;
   extern __shared__ cplx dsm[];
   cplx* const sm = dsm;
   cplx* const msm = dsm + DeepCfg<N>::SLAB;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int s = blockIdx.x & 1, rest = blockIdx.x >> 1, p4 = rest % E4, w = rest / E4;
-  for (int idx = threadIdx.x; idx < 3 * N * N; idx += blockDim.x) msm[idx] = __ldg(d.m[idx / (N * N)] + idx % (N * N));
-  __syncthreads();
-  const cplx* const gsrc = d.t + s + (long long)p4 * d.g[4] + (long long)w * d.gw;
-  const long long g0 = d.g[0], g1 = d.g[1], g2 = d.g[2], g3 = d.g[3];
-  auto at = [sm](int i0, int i1, int i2, int i3) -> cplx* { return sm + ((i0 ^ slab_f(i1) ^ slab_f(i2)) + N * i1 + N * N * i2 + N * N * N * i3); };
-  constexpr int NTILES = N * N * N / 8;
-  // p0: rows (p1, p2, p3) straight from global memory -> (i0 = p0', i1 = p1, i2 = p2, i3 = p3)
-  deep_phase<N>(msm, NTILES,
-                [=](int rho, int b) -> const cplx* { return gsrc + (rho % N) * g1 + ((rho / N) % N) * g2 + (rho / (N * N)) * g3 + b * g0; },
-                [=](int rho, int c) -> cplx* { return at(c, rho % N, (rho / N) % N, rho / (N * N)); }, lane, warp, nwarps);
-  __syncthreads();
-  // p1 in place: rows (i0, i2, i3)
-  deep_phase<N>(msm + N * N, NTILES,
-                [=](int rho, int b) -> const cplx* { return at(rho % N, b, (rho / N) % N, rho / (N * N)); },
-                [=](int rho, int c) -> cplx* { return at(rho % N, c, (rho / N) % N, rho / (N * N)); }, lane, warp, nwarps);
-  __syncthreads();
-  // p2: rows (i0 = p0', i1 = p1', i3 = p3) -> XA[(s, p1', p2')][w][p4][p3][p0']
+  {
+    const cplx *m0 = d.m[0], *m1 = d.m[1], *m2 = d.m[2];
+    for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) { msm[idx] = __ldg(m0 + idx); msm[N * N + idx] = __ldg(m1 + idx); msm[2 * N * N + idx] = __ldg(m2 + idx); }
+  }
+  const cplx* const gsrc = d.t + s + (long long)p4 * d.g[4] + (long long)w * d.gw + (long long)warp * d.g[3];
+  const long long g0 = d.g[0], g1 = d.g[1], g2 = d.g[2];
   const long long TS = (long long)N * N * N * E4;
-  cplx* const gdst = d.x + (long long)N * N * s * TS + (long long)N * N * p4 + (long long)N * N * E4 * w;
-  deep_phase<N>(msm + 2 * N * N, NTILES,
-                [=](int rho, int b) -> const cplx* { return at(rho % N, (rho / N) % N, b, rho / (N * N)); },
-                [=](int rho, int c) -> cplx* { return gdst + ((rho / N) % N + N * c) * TS + rho % N + N * (rho / (N * N)); }, lane, warp, nwarps);
+  cplx* const gdst = d.x + (long long)N * N * s * TS + (long long)N * N * p4 + (long long)N * N * E4 * w + N * warp;
+  cplx* const sub = sm + N * N * N * warp;
+  auto at = [sub](int i0, int i1, int i2) -> cplx* { return sub + ((i0 ^ slab_f(i1) ^ slab_f(i2)) + N * i1 + N * N * i2); };
+  constexpr int NTILES = N * N / 8;                  // per warp: rows (o1, o2) of its sub-slab
+  __syncthreads();
+  // p0: rows (p1, p2) straight from global memory -> (i0 = p0', i1 = p1, i2 = p2)
+  deep_phase<N, TNQS_DEEP_DEPTH>(msm, 0, NTILES,
+                [=](int rho, int b) -> const cplx* { if (TNQS_DEEP_ABLATE & 16) return msm + (rho + b) % (3 * N * N); return gsrc + (rho % N) * g1 + (rho / N) * g2 + b * g0; },
+                [=](int rho, int c) -> cplx* { return at(c, rho % N, rho / N); }, lane);
+  __syncwarp();
+  // p1 in place: rows (i0, i2)
+  if (!(TNQS_DEEP_ABLATE & 2)) deep_phase<N, TNQS_DEEP_DEPTH_SMEM>(msm + N * N, 0, NTILES,
+                [=](int rho, int b) -> const cplx* { return at(rho % N, b, rho / N); },
+                [=](int rho, int c) -> cplx* { return at(rho % N, c, rho / N); }, lane);
+  __syncwarp();
+  // p2: rows (i0 = p0', i1 = p1') -> XA[(s, p1', p2')][w][p4][p3][p0']
+  deep_phase<N, TNQS_DEEP_DEPTH_SMEM>(msm + 2 * N * N, 0, NTILES,
+                [=](int rho, int b) -> const cplx* { return at(rho % N, rho / N, b); },
+                [=](int rho, int c) -> cplx* { if (TNQS_DEEP_ABLATE & 1) return at(rho % N, rho / N, c); return gdst + (rho / N + N * c) * TS + rho % N; }, lane);
 }
 
-// grid: (2 N N, items); block 128; dynamic shared memory DeepCfg<N>::SMEM_B.  CTA y = p1' + N p2' + N^2 s.
+// grid: (2 N N, items); block DEEP_THREADS; dynamic shared memory DeepCfg<N>::SMEM_B.  CTA y = p1' + N p2' + N^2 s.
 // Shared-memory slab: element (i0 = p3', i1 = p0', i2 = p4, i3 = w) at (i0 ^ f(i1) ^ f(i2)) + N i1 + N^2 i2 + SB i3 with SB = N^3 + 1: the
 // closing reads 16-byte X elements for 2 values of w x 4 consecutive p0' per quarter-warp - the swizzle spreads the four p0' over the
 // even 16-byte bank groups and the odd sub-slab stride puts the second w on the odd ones.
 template <int N>
-__global__ void __launch_bounds__(DeepCfg<N>::THREADS, 3) k_deep_close(const DeepDesc* __restrict__ descs) {
-  const DeepDesc d = descs[blockIdx.y];
+__global__ void __launch_bounds__(DEEP_THREADS, DEEP_CTAS) k_deep_close(const DeepDesc* __restrict__ descs) {
+  static_assert(DEEP_THREADS == 32 * N, "one warp per sub-slab");
+  const DeepDesc& d = descs[blockIdx.y];
   const int E4 = d.E4;
   constexpr int SB = DeepCfg<N>::SB;
   extern __shared__ cplx dsm[];
   cplx* const sm = dsm;
   cplx* const msm = dsm + N * SB;
-  cplx* const red = msm + 2 * N * N;
+  cplx* const red = dsm;                             // after the closing loop: nwarps x N^2 complex on top of the slab
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int r = lane >> 2, q = lane & 3;
   const int y = blockIdx.x, p1 = y % N, p2 = (y / N) % N, s = y / (N * N);
-  for (int idx = threadIdx.x; idx < (E4 == N ? 2 : 1) * N * N; idx += blockDim.x) msm[idx] = __ldg(d.m[3 + idx / (N * N)] + idx % (N * N));
-  __syncthreads();
-  const long long TS = (long long)N * N * N * E4;
-  const cplx* const xt = d.x + (long long)y * TS;
-  auto at = [sm](int i0, int i1, int i2, int i3) -> cplx* { return sm + ((i0 ^ slab_f(i1) ^ slab_f(i2)) + N * i1 + N * N * i2 + SB * i3); };
-  // p3: rows (p0', p4, w) straight from the tile [w][p4][p3][p0']
-  deep_phase<N>(msm, N * E4 * N / 8,
-                [=](int rho, int b) -> const cplx* { return xt + rho % N + N * b + N * N * (rho / N); },
-                [=](int rho, int c) -> cplx* { return at(c, rho % N, (rho / N) % E4, rho / (N * E4)); }, lane, warp, nwarps);
-  __syncthreads();
-  if (E4 == N) {
-    // p4 in place: rows (i0, i1, i3)
-    deep_phase<N>(msm + N * N, N * N * N / 8,
-                  [=](int rho, int b) -> const cplx* { return at(rho % N, (rho / N) % N, b, rho / (N * N)); },
-                  [=](int rho, int c) -> cplx* { return at(rho % N, (rho / N) % N, c, rho / (N * N)); }, lane, warp, nwarps);
-    __syncthreads();
+  {
+    const cplx *m3 = d.m[3], *m4 = d.m[4];
+    for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) { msm[idx] = __ldg(m3 + idx); if (E4 == N) msm[N * N + idx] = __ldg(m4 + idx); }
   }
-  // closing: G[w, w'] = sum_K X[K, w] conj(B[K, w']), K = (p0', p3', p4').  A k-step = four consecutive p0' at one (p3', p4'); lane (r, q)
-  // feeds X[.., w = r] as the A fragment and B[.., w' = r] as the B fragment, and owns G[r][2q], G[r][2q + 1].
-  // X conj(B) in 3M form: T1 = X_r B_r, T2 = X_i B_i, T3 = (X_r + X_i)(B_r - B_i); Re = T1 + T2, Im = T3 - T1 + T2.
+  const long long TS = (long long)N * N * N * E4;
+  const cplx* const xt = d.x + (long long)y * TS + (long long)N * N * E4 * warp;       // warp w owns sub-slab i3 = w through both absorptions
+  // closing operands: descriptor scalars and the first bra elements are requested before the absorption phases
   const cplx* const bt = d.bt + s + (long long)p1 * d.g[1] + (long long)p2 * d.g[2] + (long long)r * d.gw;
   const long long g0 = d.g[0], g3 = d.g[3], g4 = d.g[4];
   constexpr int H = N / 4, U = 4;
-  const int steps = H * N * E4;                      // multiples of 4 per warp: 16 E4 steps over 4 warps
-  double t1[2] = {0, 0}, t2[2] = {0, 0}, t3[2] = {0, 0};
+  const int steps = H * N * E4;
   auto bra = [=](int st) -> const cplx* { const int i1 = 4 * (st % H) + q, i0 = (st / H) % N, i2 = st / (H * N); return bt + i1 * g0 + i0 * g3 + i2 * g4; };
-  auto ket = [=](int st) -> const cplx* { const int i1 = 4 * (st % H) + q, i0 = (st / H) % N, i2 = st / (H * N); return at(i0, i1, i2, r); };
   cplx bcur[U], bnext[U];
-  int st = warp;
 #pragma unroll
-  for (int u = 0; u < U; ++u) bcur[u] = st + u * nwarps < steps ? __ldg(bra(st + u * nwarps)) : cmake(0, 0);
-  for (; st < steps; st += U * nwarps) {
+  for (int u = 0; u < U; ++u) bcur[u] = warp + u * nwarps < steps ? __ldg(bra(warp + u * nwarps)) : cmake(0, 0);
+  auto at = [sm](int i0, int i1, int i2, int i3) -> cplx* { return sm + ((i0 ^ slab_f(i1) ^ slab_f(i2)) + N * i1 + N * N * i2 + SB * i3); };
+  __syncthreads();
+  // p3: rows (p0', p4) straight from the tile [w][p4][p3][p0']
+  if (!(TNQS_DEEP_ABLATE & 8)) deep_phase<N, TNQS_DEEP_DEPTH>(msm, 0, E4,
+                [=](int rho, int b) -> const cplx* { return xt + rho % N + N * b + N * N * (rho / N); },
+                [=](int rho, int c) -> cplx* { return at(c, rho % N, rho / N, warp); }, lane);
+  __syncwarp();
+  if (E4 == N && !(TNQS_DEEP_ABLATE & 8)) {
+    // p4 in place: rows (i0, i1)
+    deep_phase<N, TNQS_DEEP_DEPTH_SMEM>(msm + N * N, 0, N * N / 8,
+                  [=](int rho, int b) -> const cplx* { return at(rho % N, rho / N, b, warp); },
+                  [=](int rho, int c) -> cplx* { return at(rho % N, rho / N, c, warp); }, lane);
+  }
+  __syncthreads();
+  // closing: G[w, w'] = sum_K X[K, w] conj(B[K, w']), K = (p0', p3', p4').  A k-step = four consecutive p0' at one (p3', p4'); lane (r, q)
+  // feeds X[.., w = r] as the A fragment and B[.., w' = r] as the B fragment, and owns G[r][2q], G[r][2q + 1].
+  // X conj(B) in 3M form: T1 = X_r B_r, T2 = X_i B_i, T3 = (X_r + X_i)(B_r - B_i); Re = T1 + T2, Im = T3 - T1 + T2.
+  double t1[2] = {0, 0}, t2[2] = {0, 0}, t3[2] = {0, 0};
+  auto ket = [=](int st) -> const cplx* { const int i1 = 4 * (st % H) + q, i0 = (st / H) % N, i2 = st / (H * N); return at(i0, i1, i2, r); };
+  int st = warp;
+  for (; st < ((TNQS_DEEP_ABLATE & 4) ? 0 : steps); st += U * nwarps) {
     const int sn = st + U * nwarps;
 #pragma unroll
     for (int u = 0; u < U; ++u) bnext[u] = sn + u * nwarps < steps ? __ldg(bra(sn + u * nwarps)) : cmake(0, 0);
@@ -184,7 +221,8 @@ __global__ void __launch_bounds__(DeepCfg<N>::THREADS, 3) k_deep_close(const Dee
 #pragma unroll
     for (int u = 0; u < U; ++u) bcur[u] = bnext[u];
   }
-  // fixed-order sum over the four warps, one partial per CTA
+  // fixed-order sum over the warps, one partial per CTA
+  __syncthreads();                                   // every warp has read its last X element: the slab becomes the reduction buffer
 #pragma unroll
   for (int j = 0; j < 2; ++j) red[warp * N * N + r + N * (2 * q + j)] = cmake(t1[j] + t2[j], t3[j] - t1[j] + t2[j]);
   __syncthreads();

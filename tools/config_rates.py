@@ -39,6 +39,7 @@ def timed(L, h, fn):
     ms = (C.c_double * 8)(); ln = (C.c_int64 * 8)()
     L.tnqs_profile_read(h, ms, ln, 1); L.tnqs_profile_enable(h, 0)
     t0 = time.perf_counter(); fn(); L.tnqs_sync(h)
+    timed.classes = {k: round(ms[i], 3) for i, k in enumerate(lib.KERNEL_CLASSES) if ln[i]}
     return sum(ms), int(sum(ln)), 1e3 * (time.perf_counter() - t0)
 
 
@@ -60,7 +61,7 @@ def run(name):
         out[mode] = {"ms_per_sweep_device": round(dev / SWEEPS, 4), "ms_per_sweep_wall": round(wall / SWEEPS, 4), "launches_per_sweep": launches // SWEEPS,
                      "messages_per_s": round(2 * g.ne * SWEEPS / (wall * 1e-3)), "tflops": round(fl.sum() * SWEEPS / (wall * 1e-3) / 1e12, 3),
                      "frac_of_peak": round(fl.sum() * SWEEPS / (wall * 1e-3) / 1e12 / peak, 4),
-                     "frac_of_peak_device_time": round(fl.sum() * SWEEPS / (t * 1e-3) / 1e12 / peak, 4)}
+                     "frac_of_peak_device_time": round(fl.sum() * SWEEPS / (t * 1e-3) / 1e12 / peak, 4), "class_ms": dict(timed.classes)}
     rzz = gates.gate_array(("Rzz", [0, 1], 0.25))
     akw = dict(maxdim=chi, cutoff=1e-10, normalize_tensors=True)
     n_g = 0; f_g = 0.0; dev_g = 0.0; wall_g = 0.0; per = []
@@ -69,7 +70,7 @@ def run(name):
         dev, launches, wall = timed(L, h, lambda: E.apply_2site_batch(bpc, grp, [rzz] * len(grp), apply_kwargs=akw))
         f = sum(bench.gate_flops(g, e, chi) for e in grp)
         n_g += len(grp); f_g += f; dev_g += dev; wall_g += wall
-        per.append({"gates": len(grp), "ms_device": round(dev, 3), "ms_wall": round(wall, 3), "launches": launches})
+        per.append({"gates": len(grp), "ms_device": round(dev, 3), "ms_wall": round(wall, 3), "launches": launches, "class_ms": dict(timed.classes)})
     out["two_site_gates"] = {"classes": per, "gates_per_s": round(n_g / (wall_g * 1e-3)), "nominal_tflops": round(f_g / (wall_g * 1e-3) / 1e12, 3),
                              "frac_of_peak_nominal": round(f_g / (wall_g * 1e-3) / 1e12 / peak, 4), "bond_dims_after": sorted(set(int(x) for x in psi.bond_dims()))}
     print(json.dumps(out), flush=True)
