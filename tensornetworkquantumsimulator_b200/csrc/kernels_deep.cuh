@@ -232,3 +232,83 @@ __global__ void __launch_bounds__(DEEP_THREADS, DEEP_CTAS) k_deep_close(const De
     d.partial[(size_t)y * N * N + idx] = acc;
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_slab_batch: the warp-owned sub-slab machinery of k_deep_absorb with free input and output strides, for the gate path on
+// high-coordination vertices (simple_update.jl:35-36: psi~ = psi x sqrt(M_k) over 4 or 5 outer legs of dimension 8).  A warp takes a
+// sub-slab (i0, i1, i2) of N^3 elements from `in`, multiplies the legs that carry a matrix (leg 0 on the way into shared memory, leg 1
+// in place, leg 2 on the way out; a leg without a matrix is copied) and stores it to `out`; warp = a fourth index i3, CTA = up to three
+// more.  Two launches absorb five legs with 2 x (read + write) of the tensor instead of 5 x, and the first one reads the canonical
+// site tensor and writes the matricised layout, so the separate permute pass goes as well.  in == out is allowed when both stride
+// sets are equal (a warp reads its whole sub-slab before it writes).
+// ---------------------------------------------------------------------------------------------------------------
+struct BatchSlabDesc {
+  const cplx* in; cplx* out;
+  const cplx* m[3];            // N x N (ld = N) per slab leg, or null
+  long long gi[7], go[7];      // strides (complex elements) of i0, i1, i2, i3 (warp), and of the three digits of the CTA index
+  int n3;                      // extent of i3 (<= N)
+  int nc[3];                   // extents of the CTA digits
+  int flags;                   // bit0: conj(m), bit1: m^T (as k_mode_apply)
+};
+
+// grid: (max CTAs per item, items); block 32 N threads; dynamic shared memory DeepCfg<N>::SMEM_A
+template <int N>
+__global__ void __launch_bounds__(DEEP_THREADS, DEEP_CTAS) k_slab_batch(const BatchSlabDesc* __restrict__ descs) {
+  static_assert(DEEP_THREADS == 32 * N, "one warp per sub-slab");
+  const BatchSlabDesc& d = descs[blockIdx.y];
+  const int nc0 = d.nc[0], nc1 = d.nc[1], nc2 = d.nc[2];
+  if ((int)blockIdx.x >= nc0 * nc1 * nc2) return;
+  extern __shared__ cplx dsm[];
+  cplx* const msm = dsm + DeepCfg<N>::SLAB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const cplx *m0 = d.m[0], *m1 = d.m[1], *m2 = d.m[2];
+  {
+    const bool conj_m = d.flags & 1, trans_m = d.flags & 2;
+    for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
+      const int from = trans_m ? idx / N + N * (idx % N) : idx;
+      cplx v;
+      if (m0) { v = __ldg(m0 + from); if (conj_m) v.y = -v.y; msm[idx] = v; }
+      if (m1) { v = __ldg(m1 + from); if (conj_m) v.y = -v.y; msm[N * N + idx] = v; }
+      if (m2) { v = __ldg(m2 + from); if (conj_m) v.y = -v.y; msm[2 * N * N + idx] = v; }
+    }
+  }
+  const int x = blockIdx.x, c0 = x % nc0, c1 = (x / nc0) % nc1, c2 = x / (nc0 * nc1);
+  const cplx* const src = d.in + warp * d.gi[3] + c0 * d.gi[4] + c1 * d.gi[5] + c2 * d.gi[6];
+  cplx* const dst = d.out + warp * d.go[3] + c0 * d.go[4] + c1 * d.go[5] + c2 * d.go[6];
+  const long long gi0 = d.gi[0], gi1 = d.gi[1], gi2 = d.gi[2], go0 = d.go[0], go1 = d.go[1], go2 = d.go[2];
+  const int n3 = d.n3;
+  cplx* const sub = dsm + N * N * N * warp;
+  auto at = [sub](int i0, int i1, int i2) -> cplx* { return sub + ((i0 ^ slab_f(i1) ^ slab_f(i2)) + N * i1 + N * N * i2); };
+  constexpr int NTILES = N * N / 8;
+  __syncthreads();
+  if (warp >= n3) return;
+  if (m0) {
+    deep_phase<N, TNQS_DEEP_DEPTH>(msm, 0, NTILES,
+                  [=](int rho, int b) -> const cplx* { return src + (rho % N) * gi1 + (rho / N) * gi2 + b * gi0; },
+                  [=](int rho, int c) -> cplx* { return at(c, rho % N, rho / N); }, lane);
+  } else {
+    // plain copy: lane = (i0, two bits of i1); N^3 / 32 elements per lane, all requested before the first one is stored
+    constexpr int PER = N * N * N / 32;
+    cplx tmp[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { const int e = lane + 32 * k; tmp[k] = src[(e % N) * gi0 + ((e / N) % N) * gi1 + (e / (N * N)) * gi2]; }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { const int e = lane + 32 * k; *at(e % N, (e / N) % N, e / (N * N)) = tmp[k]; }
+  }
+  __syncwarp();
+  if (m1) {
+    deep_phase<N, TNQS_DEEP_DEPTH_SMEM>(msm + N * N, 0, NTILES,
+                  [=](int rho, int b) -> const cplx* { return at(rho % N, b, rho / N); },
+                  [=](int rho, int c) -> cplx* { return at(rho % N, c, rho / N); }, lane);
+    __syncwarp();
+  }
+  if (m2) {
+    deep_phase<N, TNQS_DEEP_DEPTH_SMEM>(msm + 2 * N * N, 0, NTILES,
+                  [=](int rho, int b) -> const cplx* { return at(rho % N, rho / N, b); },
+                  [=](int rho, int c) -> cplx* { return dst + (rho % N) * go0 + (rho / N) * go1 + c * go2; }, lane);
+  } else {
+    constexpr int PER = N * N * N / 32;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { const int e = lane + 32 * k; dst[(e % N) * go0 + ((e / N) % N) * go1 + (e / (N * N)) * go2] = *at(e % N, (e / N) % N, e / (N * N)); }
+  }
+}

@@ -107,6 +107,8 @@ static void set_smem_attrs() {   // per device: called at every handle creation 
   cudaFuncSetAttribute(k_chol_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   cudaFuncSetAttribute(k_deep_absorb<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_deep_close<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_slab_batch<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_slab_batch<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_deep_absorb<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_deep_close<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
@@ -733,6 +735,13 @@ struct GateBatch {
     for (int l : J.outer) if (c->chi[c->inc[J.v][l]] != N) return false;
     return true;
   }
+  bool deep_ok(int j) const {           // 4 or 5 outer legs of dimension 8 on a qubit site: two k_slab_batch passes (kernels_deep.cuh)
+    const SiteJob& J = jobs[j];
+    const int F = (int)J.outer.size();
+    if (dmma_disabled() || deep_disabled() || J.d != 2 || (F != 4 && F != 5)) return false;
+    for (int l : J.outer) if (c->chi[c->inc[J.v][l]] != 8) return false;
+    return true;
+  }
   // CholeskyQR2 runs optimistically for every tall matrix; its per-matrix flags (a pivot below the tolerance) are read as late as
   // possible - after the host has built the next stage's descriptors, while the device finishes the QR kernels - and the flagged
   // matrices are then redone by Householder TSQR
@@ -759,7 +768,7 @@ struct GateBatch {
 void GateBatch::absorb_outer(bool inverse) {   // forward: on A (psi~); inverse: on the Q factor
   // Fast path: every outer leg of the same dimension N in {8, 16}, 2 or 3 of them: each column of the matricised tensor
   // is a contiguous N^F slab, so the fused slab kernel absorbs all the legs in one pass, in place (k_absorb_slab).
-  std::vector<int> generic;
+  std::vector<int> generic, deep;
   std::vector<SlabDesc> slab[2];                 // [0]: N = 8, [1]: N = 16
   int maxcols[2] = {0, 0};
   for (int j : LJ) {
@@ -768,6 +777,7 @@ void GateBatch::absorb_outer(bool inverse) {   // forward: on A (psi~); inverse:
     const int F = (int)J.outer.size();
     int N = F ? c->chi[c->inc[J.v][J.outer[0]]] : 0;
     const bool ok = slab_ok(j) && ncols[j] >= 1;
+    if (!ok && !inverse && from_site[j] && deep_ok(j)) { deep.push_back(j); continue; }
     if (!ok) { if (F) generic.push_back(j); continue; }
     cplx* buf = inverse ? J.Q : J.A;
     SlabDesc d; d.t = buf; d.x = buf; d.F = F;
@@ -789,6 +799,45 @@ void GateBatch::absorb_outer(bool inverse) {   // forward: on A (psi~); inverse:
     size_t smem = N == 16 ? SlabCfg<16>::SMEM : SlabCfg<8>::SMEM;
     if (w) LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<16>, grid, SLAB_THREADS, smem, dsd);
     else LAUNCH(c, TNQS_KC_MODE_APPLY, k_absorb_slab<8>, grid, SLAB_THREADS, smem, dsd);
+  }
+  if (!deep.empty()) {
+    // 4 or 5 outer legs of dimension 8: legs 1-3 from the canonical site tensor into the matrix layout (warp = o4, CTA = (o5, s, b)),
+    // then legs 4 (and 5) in place (F = 5: slab (o1, o4, o5), warp = o2, CTA = (o3, column); F = 4: slab (o1, o2, o4), warp = o3,
+    // CTA = column)
+    std::vector<BatchSlabDesc> p1, p2; int g1 = 1, g2 = 1;
+    for (int j : deep) {
+      const SiteJob& J = jobs[j]; const PermDesc& p = pd[j];
+      const int F = (int)J.outer.size();
+      BatchSlabDesc a; a.in = c->site[J.v]; a.out = J.A; a.flags = 0; a.n3 = 8;
+      const long long mst[5] = {1, 8, 64, 512, 4096};
+      for (int i = 0; i < 3; ++i) { a.m[i] = J.root[i]; a.gi[i] = p.ostride[i]; a.go[i] = mst[i]; }
+      a.gi[3] = p.ostride[3]; a.go[3] = mst[3];
+      a.nc[0] = F == 5 ? 8 : 1; a.gi[4] = F == 5 ? p.ostride[4] : 0; a.go[4] = mst[4];
+      a.nc[1] = 2; a.gi[5] = 1; a.go[5] = J.Po;
+      a.nc[2] = J.chib; a.gi[6] = p.bstride; a.go[6] = 2 * J.Po;
+      p1.push_back(a); g1 = std::max(g1, a.nc[0] * a.nc[1] * a.nc[2]);
+      BatchSlabDesc b; b.in = J.A; b.out = J.A; b.flags = 0; b.n3 = 8;
+      if (F == 5) {
+        const long long st[3] = {1, 512, 4096};
+        b.m[0] = nullptr; b.m[1] = J.root[3]; b.m[2] = J.root[4];
+        for (int i = 0; i < 3; ++i) b.gi[i] = b.go[i] = st[i];
+        b.gi[3] = b.go[3] = 8;
+        b.nc[0] = 8; b.gi[4] = b.go[4] = 64;
+        b.nc[1] = ncols[j]; b.gi[5] = b.go[5] = J.Po;
+      } else {
+        const long long st[3] = {1, 8, 512};
+        b.m[0] = nullptr; b.m[1] = nullptr; b.m[2] = J.root[3];
+        for (int i = 0; i < 3; ++i) b.gi[i] = b.go[i] = st[i];
+        b.gi[3] = b.go[3] = 64;
+        b.nc[0] = ncols[j]; b.gi[4] = b.go[4] = J.Po;
+        b.nc[1] = 1; b.gi[5] = b.go[5] = 0;
+      }
+      b.nc[2] = 1; b.gi[6] = b.go[6] = 0;
+      p2.push_back(b); g2 = std::max(g2, b.nc[0] * b.nc[1] * b.nc[2]);
+    }
+    BatchSlabDesc* d1 = c->upload(p1); BatchSlabDesc* d2 = c->upload(p2);
+    LAUNCH(c, TNQS_KC_MODE_APPLY, k_slab_batch<8>, dim3((unsigned)g1, (unsigned)p1.size(), 1), DeepCfg<8>::THREADS, DeepCfg<8>::SMEM_A, d1);
+    LAUNCH(c, TNQS_KC_MODE_APPLY, k_slab_batch<8>, dim3((unsigned)g2, (unsigned)p2.size(), 1), DeepCfg<8>::THREADS, DeepCfg<8>::SMEM_A, d2);
   }
   size_t maxouter = 0;
   for (int jj : generic) { SiteJob& J = jobs[jj]; maxouter = std::max(maxouter, J.outer.size()); }
@@ -955,7 +1004,7 @@ void GateBatch::stage1(int n_, const int32_t* es_, const int32_t* flips, const d
   {
     // sites whose outer legs go through the fused slab kernel are matricised by that kernel (it reads the canonical layout)
     std::vector<PermDesc> lp;
-    for (int j : LJ) { if (jobs[j].d == 2 && slab_ok(j)) from_site[j] = 1; else lp.push_back(pd[j]); }
+    for (int j : LJ) { if (jobs[j].d == 2 && (slab_ok(j) || deep_ok(j))) from_site[j] = 1; else lp.push_back(pd[j]); }
     PermDesc* dpd = c->upload(lp);
     long long maxPo = 1; for (int j : LJ) maxPo = std::max(maxPo, jobs[j].Po);
     unsigned gx = (unsigned)((maxPo + 255) / 256); (void)maxtot;

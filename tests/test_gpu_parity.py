@@ -1086,6 +1086,60 @@ def test_bp_high_coordination_vertices_chi8(E, mode):
         assert abs(E.expect(be, ("Z", [name])) - O.expect(bo, ("Z", [name]))) < EXP_TOL
 
 
+def _projected_two_site(g, tensors, e, seed):
+    # gauge-invariant probe of the two-site tensor of edge e that never forms it: every other leg of both sites is contracted with a
+    # fixed random vector, the shared bond is summed - a d x d matrix
+    out = []
+    for v in (int(g.esrc[e]), int(g.edst[e])):
+        t = tensors[v]
+        keep = 1 + g.leg(v, e)
+        for ax in range(t.ndim - 1, 0, -1):
+            if ax == keep:
+                continue
+            rs = np.random.default_rng(seed + 17 * ax + 1000 * v)
+            vec = rs.normal(size=t.shape[ax]) + 1j * rs.normal(size=t.shape[ax])
+            t = np.tensordot(t, vec, axes=([ax], [0]))
+        out.append(t)                                   # [s, bond]
+    return out[0] @ out[1].T
+
+
+@pytest.mark.parametrize("kw", [dict(maxdim=8, cutoff=1e-10, normalize_tensors=True), dict(maxdim=6, cutoff=None, normalize_tensors=True)])
+def test_two_site_gates_on_high_coordination_vertices(E, kw):
+    # 3x3x3 lattice at chi = 8: gates on centre-face (degree 6 / 5), face-edge (5 / 4) and edge-corner (4 / 3) bonds.  Sites with 4 or 5
+    # outer legs take their sqrt(M) absorptions through k_slab_batch (two passes, the first one reading the canonical site tensor);
+    # the 8 MiB centre tensor makes the full two-site tensor too large to compare, so the gauge-invariant probe above stands in
+    g = G.named_grid((3, 3, 3))
+    psi_o = O.random_tensornetworkstate(g, bond_dimension=8, seed=37)
+    for v in range(g.nv):
+        psi_o.tensors[v] /= np.linalg.norm(psi_o.tensors[v])
+    edges = [g.edge_of[(g.v(a), g.v(b))] for a, b in [((2, 2, 2), (2, 2, 3)), ((1, 2, 2), (1, 2, 3)), ((3, 3, 1), (3, 3, 2))]]
+    degs = [sorted((g.degree(int(g.esrc[e])), g.degree(int(g.edst[e])))) for e in edges]
+    assert degs == [[5, 6], [4, 5], [3, 4]]
+    rs = np.random.default_rng(5)
+    arrs = []
+    for _ in edges:
+        u, _r = np.linalg.qr(rs.normal(size=(4, 4)) + 1j * rs.normal(size=(4, 4)))
+        arrs.append(u.reshape(2, 2, 2, 2))
+    seq = G.forest_cover_edge_sequence(g)
+    bo = O.update(O.BeliefPropagationCache(psi_o), maxiter=4, edge_sequence=seq)
+    be = E.update(to_engine(psi_o, chi_cap=16), maxiter=4, edge_sequence=seq)
+    dets = []
+    for i, e in enumerate(edges):
+        det = {}
+        O.apply_gate(bo, arrs[i], [int(g.esrc[e]), int(g.edst[e])], detail=det, **kw)
+        dets.append(det)
+    ranks, errs, sv = E.apply_2site_batch(be, edges, arrs, apply_kwargs=kw)
+    te = be.psi.tensors()
+    for i, e in enumerate(edges):
+        assert ranks[i] == dets[i]["rank"]
+        assert rel(sv[i, :ranks[i]], dets[i]["svals"]) < MSG_TOL
+        assert errs[i] == pytest.approx(dets[i]["truncerr"], rel=1e-8, abs=1e-16)
+        for k in (2 * e, 2 * e + 1):
+            assert rel(E.message(be, k), O.message(bo, k)) < MSG_TOL
+        assert rel(_projected_two_site(g, te, e, 3), _projected_two_site(g, bo.network.tensors, e, 3)) < 1e-9
+    assert list(be.psi.bond_dims()) == list(bo.network.bond_dims())
+
+
 def test_deep_path_with_a_bra_layer(E):
     # <phi|psi> on the 3x3x3 lattice: the closing of the deep path contracts against the bra's site tensors
     g = G.named_grid((3, 3, 3))
