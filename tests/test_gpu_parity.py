@@ -890,8 +890,9 @@ def test_set_get_sites_batched_round_trip(E):
         psi.set_sites([1], [ts[4]])                          # wrong element count
 
 
-@pytest.mark.parametrize("shape,chi,world", [((4, 6), 3, 2), ((4, 6), 8, 2), ((3, 8), 4, 4)])
+@pytest.mark.parametrize("shape,chi,world", [((4, 6), 3, 2), ((4, 6), 8, 2), ((3, 8), 4, 4), ((3, 4, 3), 8, 2)])
 def test_partitioned_bp_peer_memory_halo_matches_single_handle(E, shape, chi, world):
+    # (the 3 x 4 x 3 case at chi = 8 puts a degree-6 vertex and its degree-5 neighbours on either side of the cut: deep path + halo)
     # `world` "ranks" inside one process (one host thread per handle, all on cuda:0): each handle's BP kernels store their
     # boundary messages straight into the neighbours' receive buffers, every sweep ends with the device-side barrier /
     # all-reduce, and a whole refresh (fixed sweeps, then run to tolerance) is one call per rank - no host-side exchange
