@@ -315,17 +315,26 @@ def run_distributed(args, torch, dist, rank, world, local):
     stats = {"bp_s": 0.0, "gate_s": 0.0, "other_s": 0.0, "msg": 0, "gates2": 0, "sweeps": 0, "halo": 0}
 
     estream = torch.cuda.ExternalStream(lib.load().tnqs_stream(psi._h.ptr))
+    # TNQS_BENCH_TRACE=1: every rank prints, for each timed call of its last step, (host start in ms since the step began, host ms
+    # inside the call, device ms) - inter-rank skew and host stalls show up here
+    trace = [] if os.environ.get("TNQS_BENCH_TRACE") == "1" else None
+    trace_t0 = [time.perf_counter()]
 
     def dev_timed(fn):
         """Device time of fn: CUDA events on the engine's stream and on torch's current stream (NCCL), after a full
         synchronisation; the later end event counts."""
         torch.cuda.synchronize()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        w0 = time.perf_counter()
         e0.record(estream)
         r = fn()
+        w1 = time.perf_counter()
         e1.record(estream); e2.record(torch.cuda.current_stream())
         torch.cuda.synchronize()
-        return r, 1e-3 * max(e0.elapsed_time(e1), e0.elapsed_time(e2))
+        dt = 1e-3 * max(e0.elapsed_time(e1), e0.elapsed_time(e2))
+        if trace is not None:
+            trace.append((round(1e3 * (w0 - trace_t0[0]), 2), round(1e3 * (w1 - w0), 2), round(1e3 * dt, 2)))
+        return r, dt
 
     def bp():
         info = {}
@@ -336,6 +345,8 @@ def run_distributed(args, torch, dist, rank, world, local):
         stats["msg"] += info["iters"] * info["messages_per_sweep"]; stats["sweeps"] += info["iters"]; stats["halo"] += info["halo_bytes"]
 
     def step():
+        if trace is not None:
+            trace.clear(); trace_t0[0] = time.perf_counter()
         # Rx then Rz on a vertex = one gate, their product, as tnqs_apply_circuit applies them (engine.fold_gates)
         _, dt = dev_timed(lambda: E.apply_1site_batch(bpc, owned_v, [rzrx] * len(owned_v)))
         stats["other_s"] += dt
@@ -366,6 +377,8 @@ def run_distributed(args, torch, dist, rank, world, local):
     dist.barrier()
     total_ms = ev0.elapsed_time(ev1)
     gc.enable()
+    if trace is not None:
+        print(f"[trace rank {rank}] (start, host, device) ms per call of the last step: {trace}", file=sys.stderr, flush=True)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([total_ms, stats["bp_s"], stats["gate_s"], stats["other_s"], float(stats["msg"]), float(stats["gates2"]), float(stats["sweeps"]),
                       float(stats["halo"]), float(psi.kernel_launches() - launches0)], dtype=torch.float64, device=dev)

@@ -215,7 +215,10 @@ def update_distributed(lgraph: LocalGraph, comp: LocalCompute, dist, slot: int, 
     (send/recv), one all-reduce.  p2p_bytes = result of halo_setup_p2p: the whole refresh is one C-ABI call (one graph launch
     per rank; boundary stores, barrier, all-reduce and convergence test on the device)."""
     g = lgraph.g
-    seq = np.array([k for k in range(2 * g.ne) if lgraph.owned[g.dsrc(k)]], dtype=np.int32)
+    seq = getattr(lgraph, "_owned_seq", None)           # directed edges leaving an owned vertex, ascending: built once per local graph
+    if seq is None:
+        seq = np.array([k for k in range(2 * g.ne) if lgraph.owned[g.dsrc(k)]], dtype=np.int32)
+        lgraph._owned_seq = seq
     iters, mean, halo_bytes = 0, float("nan"), 0
     if p2p_bytes is not None:
         iters, mean = comp.refresh(seq, maxiter, tolerance)

@@ -48,6 +48,22 @@ for it in range(4):
     comp.refresh(seq, 10, None)                      # one call = one graph launch: 10 sweeps incl. boundary stores, barrier, commit
     torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) / 10)
 if rank == 0: print("peer-memory halo, device-driven refresh, ms per sweep:", [round(1e3 * x, 3) for x in ts], flush=True)
+# short refreshes as the bench issues them (1-2 sweeps, convergence test on): fixed cost per call, then the bench's own sequence
+# gate class -> refresh without a barrier in between, wall clock per rank
+ts2 = []
+for it in range(6):
+    sync(); t0 = time.perf_counter()
+    comp.refresh(seq, 2, None)
+    torch.cuda.synchronize(); ts2.append(time.perf_counter() - t0)
+print(f"rank {rank}: 2-sweep refresh, ms per call:", [round(1e3 * x, 2) for x in ts2], flush=True)
+for cls in range(4):
+    sync(); t0 = time.perf_counter()
+    P.apply_class_distributed(E, bpc, gg, lg, owner, rank, groups[cls], rzz, kw, dist, torch, dev, batch=batches[cls])
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    info = {}
+    P.update_distributed(lg, comp, dist, slot, torch, dev, maxiter=25, tolerance=1e-8, info=info, p2p_bytes=p2p)
+    torch.cuda.synchronize(); t2 = time.perf_counter()
+    print(f"rank {rank}: class {cls}: gates {1e3 * (t1 - t0):.2f} ms, refresh {1e3 * (t2 - t1):.2f} ms ({info['iters']} sweeps)", flush=True)
 it_, mean_ = comp.refresh(seq, 25, 1e-8)
 if rank == 0: print("refresh to 1e-8:", it_, "sweeps, global mean diff", mean_, flush=True)
 g2 = [gate_class() for _ in range(4)]
