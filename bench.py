@@ -400,7 +400,7 @@ def run_distributed(args, torch, dist, rank, world, local):
         "gates": {"metric": "two_site_gate_applications_per_sec", "value": gates2 / gate_s, "unit": "gates/s"},
         "bp": {"sweeps_per_step": mx[6].item() / args.steps, "approx_tflops": msg / bp_s * fm / 1e12, "halo_bytes_per_step": halo / args.steps},
         "phase_ms_per_step": {"bp": 1e3 * bp_s / args.steps, "two_site_gates": 1e3 * gate_s / args.steps, "one_site": 1e3 * other_s / args.steps},
-        "roofline": {"bound": "tensor", "kernel": (f"k_absorb_slab<{chi}> + k_close_dmma<{chi}> (the two launches of a JACOBI sweep)" if chi in (8, 16) else "k_leg_dmma x 3 + k_close_leg_dmma (generic tensor-core leg / closing kernels of a JACOBI sweep, chunked levels)") + " incl. the device-side barrier; whole BP phases, per GPU",
+        "roofline": {"bound": "tensor", "kernel": (f"k_absorb_slab<{chi}> + k_close_dmma<{chi}> (the two launches of a JACOBI sweep)" if chi in (8, 16) else "k_leg_dmma + k_close_leg_dmma (generic tensor-core leg / closing kernels of a JACOBI sweep, chunked levels; the four updates leaving a vertex share their absorptions: 8 leg passes instead of the 12 the algorithmic flop count stands for)") + " incl. the device-side barrier; whole BP phases, per GPU",
                      "achieved": msg / bp_s * fm / 1e12 / world, "peak": pk["fp64_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": msg / bp_s * fm / 1e12 / world / pk["fp64_tflops_sustained"], "traffic": None, "peak_source": pk["source"],
                      "note": "per-GPU rate over the BP phases (max over ranks, so the skew between ranks at the first sweep barrier is inside); single-kernel counters: profiles/README.md"},

@@ -380,6 +380,29 @@ static int deep_path_E4(const tnqs_ctx* c, const Chain& ch) {
   return F == 5 ? 8 : 1;
 }
 
+// Shared absorptions (generic leg-by-leg chains): the z message updates that leave one vertex in the same level absorb the same
+// messages into the same site tensor, each leaving out a different leg.  Degree 4: T x m0 x m1 and T x m2 x m3 are formed once and
+// serve two updates each - 8 leg passes instead of 12; degree 3: T x m0 and T x m1 serve three - 5 instead of 6 (the association
+// order changes, results agree to rounding; oracle twin: jacobi_sweep(shared=True)).  Eligible: a BP-type chain without operator whose
+// absorb list is every other leg in ascending order with plain matrices.  TNQS_BP_SHARE=0 switches it off.
+static bool share_disabled() {
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("TNQS_BP_SHARE"); disabled = (e && e[0] == '0') ? 1 : 0; }
+  return disabled == 1;
+}
+static bool share_candidate(const tnqs_ctx* c, const Chain& ch) {
+  if (share_disabled() || ch.op || ch.close_leg < 0) return false;
+  const int v = ch.v, z = (int)c->inc[v].size(), F = (int)ch.absorb.size();
+  if (F != z - 1 || (z != 3 && z != 4)) return false;
+  int expect_leg = 0;
+  for (const Absorb& ab : ch.absorb) {
+    if (expect_leg == ch.close_leg) ++expect_leg;
+    if (ab.leg != expect_leg || ab.flags != 0 || ab.ldm != c->chi[c->inc[v][ab.leg]]) return false;
+    ++expect_leg;
+  }
+  return true;
+}
+
 // Build a plan for `levels` (vector of vector of chains).  All device buffers are temporaries of the current call.
 template <typename T> static T* upload_into(tnqs_ctx* c, T* reuse, const std::vector<T>& v) {
   if (!reuse) return c->upload(v);
@@ -426,7 +449,11 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
     // (a region still at 8 next to one at 16 under a cutoff-driven truncation) therefore cost one more launch pair, not an error.
     std::vector<int> order(chains.size()), fN(chains.size());
     for (size_t i = 0; i < chains.size(); ++i) { order[i] = (int)i; fN[i] = fast_path_N(c, chains[i]); }
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return fN[a] < fN[b]; });
+    // generic chains are taken vertex by vertex, so that the updates leaving one vertex land in one sub-level (shared absorptions)
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      if (fN[a] != fN[b]) return fN[a] < fN[b];
+      return fN[a] == 0 && chains[a].v < chains[b].v;
+    });
     int curN = 0;
     for (int i : order) {
       const Chain& ch = chains[i];
@@ -587,13 +614,77 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
       }
       sl.gate1.count = (int)(g1.size() - sl.gate1.off);
       sl.gate1.grid = dim3((unsigned)std::min<long long>(std::max<long long>(1, (maxrest + 255) / 256), 1024), sl.gate1.count, 1);
+      // shared absorptions: groups of generic chains that are all the updates leaving one vertex
+      std::vector<char> shared(sub.size(), 0);
+      {
+        auto make_apply = [&](int v, int leg, const cplx* in, cplx* out, const cplx* mat) {
+          ModeApplyDesc d;
+          long long Lp = c->d[v];
+          for (int i = 0; i < leg; ++i) Lp *= c->chi[c->inc[v][i]];
+          const int n = c->chi[c->inc[v][leg]];
+          const long long R = c->site_n[v] / (Lp * n);
+          d.in = in; d.out = out; d.m = mat;
+          d.L = (int)Lp; d.n = n; d.np = n; d.R = (int)R;
+          d.in_sb = Lp; d.in_sr = Lp * n; d.out_sb = Lp; d.out_sr = Lp * n; d.ldm = n; d.flags = 0;
+          plan.flops += 8.0 * (double)c->site_n[v] * n;
+          return d;
+        };
+        std::vector<ModeApplyDesc> round[3];
+        size_t j0 = 0;
+        while (j0 < sub.size()) {
+          const int v = chains[sub[j0]].v;
+          size_t j1 = j0;
+          while (j1 < sub.size() && chains[sub[j1]].v == v) ++j1;
+          const int z = (int)c->inc[v].size();
+          bool ok = (int)(j1 - j0) == z && (z == 3 || z == 4);
+          std::vector<int> by_leg(z > 0 ? z : 1, -1);           // chain (index into sub) that closes on leg l
+          std::vector<const cplx*> mat(z > 0 ? z : 1, nullptr);
+          for (size_t j = j0; ok && j < j1; ++j) {
+            const Chain& ch = chains[sub[j]];
+            ok = !fast[j] && share_candidate(c, ch) && mem[L][sub[j]].nbuf == 2 && by_leg[ch.close_leg] < 0;
+            if (!ok) break;
+            by_leg[ch.close_leg] = (int)j;
+            for (const Absorb& ab : ch.absorb) {
+              if (mat[ab.leg] && mat[ab.leg] != ab.mat) ok = false;
+              mat[ab.leg] = ab.mat;
+            }
+          }
+          if (ok) {
+            const cplx* T = c->site[v];
+            auto X = [&](int l) { return buf0[by_leg[l]]; };
+            if (z == 4) {
+              cplx* A01 = buf1[by_leg[0]]; cplx* A23 = buf1[by_leg[1]];
+              round[0].push_back(make_apply(v, 0, T, A01, mat[0])); round[0].push_back(make_apply(v, 2, T, A23, mat[2]));
+              round[1].push_back(make_apply(v, 1, A01, A01, mat[1])); round[1].push_back(make_apply(v, 3, A23, A23, mat[3]));
+              round[2].push_back(make_apply(v, 2, A01, X(3), mat[2])); round[2].push_back(make_apply(v, 3, A01, X(2), mat[3]));
+              round[2].push_back(make_apply(v, 0, A23, X(1), mat[0])); round[2].push_back(make_apply(v, 1, A23, X(0), mat[1]));
+            } else {
+              cplx* P = buf1[by_leg[0]]; cplx* Q = buf1[by_leg[1]];
+              round[0].push_back(make_apply(v, 0, T, P, mat[0])); round[0].push_back(make_apply(v, 1, T, Q, mat[1]));
+              round[1].push_back(make_apply(v, 1, P, X(2), mat[1])); round[1].push_back(make_apply(v, 2, P, X(1), mat[2]));
+              round[1].push_back(make_apply(v, 2, Q, X(0), mat[2]));
+            }
+            for (size_t j = j0; j < j1; ++j) { shared[j] = 1; curp[j] = buf0[j]; }
+          }
+          j0 = j1;
+        }
+        for (int r = 0; r < 3; ++r) {
+          if (round[r].empty()) continue;
+          LaunchRec lr; lr.off = ma.size(); lr.smem = 0;
+          ma.insert(ma.end(), round[r].begin(), round[r].end());
+          lr.count = (int)round[r].size();
+          ApplyLaunch al = plan_apply_launch(ma.data() + lr.off, lr.count);
+          lr.grid = al.grid; lr.dmma = al.dmma; lr.smem = al.smem; lr.tpc = al.tpc;
+          sl.steps.push_back(lr);
+        }
+      }
       // absorption steps
       for (int s = 0; s < maxsteps; ++s) {
         LaunchRec lr; lr.off = ma.size(); lr.smem = 0;
         long long maxtiles = 1; int maxcol = 1;
         for (size_t j = 0; j < sub.size(); ++j) {
           const Chain& ch = chains[sub[j]];
-          if (fast[j] || s >= (int)ch.absorb.size()) continue;
+          if (fast[j] || shared[j] || s >= (int)ch.absorb.size()) continue;
           const Absorb& ab = ch.absorb[s];
           int v = ch.v;
           ModeApplyDesc d;
