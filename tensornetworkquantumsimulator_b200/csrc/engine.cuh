@@ -308,7 +308,8 @@ static ApplyLaunch plan_apply_launch(const ModeApplyDesc* d, size_t count) {
 struct SubLevel {
   LaunchRec slab{0, 0, dim3(), 0}, dclose{0, 0, dim3(), 0};   // DMMA fast path (kernels_dmma.cuh)
   LaunchRec fused{0, 0, dim3(), 0};                            // the same chains as one persistent launch (k_bp_level): queue items
-  LaunchRec deep{0, 0, dim3(), 0};                             // degree-5 / degree-6 chains at N = 8 (kernels_deep.cuh): k_deep_absorb + k_deep_close
+  LaunchRec deep{0, 0, dim3(), 0};                             // degree-5 / degree-6 chains at N = 8 (kernels_deep.cuh): k_deep_close, one item per message
+  LaunchRec deepA{0, 0, dim3(), 0};                            // k_deep_absorb: one item per message, or two per degree-6 vertex whose six updates share them
   int fastN = 0, close_cap = 16;                               // close_cap: split cap of the fast chains (selects the closing CTA size)
   LaunchRec gate1{0, 0, dim3(), 0};
   std::vector<LaunchRec> steps;
@@ -321,7 +322,7 @@ struct Plan {
   Gate1Desc* d_gate1 = nullptr; ModeApplyDesc* d_apply = nullptr; ModeCloseDesc* d_close = nullptr;
   CloseReduceDesc* d_reduce = nullptr; int* d_commit = nullptr;
   SlabDesc* d_slab = nullptr; CloseDmmaDesc* d_dclose = nullptr; int* d_ticket = nullptr;
-  DeepDesc* d_deep = nullptr;
+  DeepDesc* d_deep = nullptr; DeepDesc* d_deepA = nullptr;
   int2* d_items = nullptr; int* d_qctr = nullptr; int* d_slab_done = nullptr;       // k_bp_level / k_bp_sweep queue, its counters, per-chain slab counters
   // whole-sweep persistent launch (k_bp_sweep): every chain of every level in one data-flow queue
   bool sweep = false; int sweepN = 0, sweep_items = 0; dim3 sweep_grid; size_t sweep_smem = 0;
@@ -331,7 +332,7 @@ struct Plan {
   // storage: a rebuilt plan of the same shape reuses the buffers of its predecessor, so device addresses (and a CUDA graph
   // captured over them) stay valid when only the site pointers inside the descriptors changed
   cplx* scratch = nullptr; size_t scratch_elems = 0; cplx* partial = nullptr; size_t partial_elems = 0;
-  size_t cnt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};    // descriptor counts: gate1, apply, close, reduce, commit, slab, dclose, queue items, deep
+  size_t cnt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // descriptor counts: gate1, apply, close, reduce, commit, slab, dclose, queue items, deep, deepA
   int nlaunch = 0;                   // kernel launches per run
   double flops = 0;                  // executed flops per run of the plan (8 per complex MAC)
 };
@@ -433,7 +434,7 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
   std::vector<Gate1Desc> g1; std::vector<ModeApplyDesc> ma; std::vector<ModeCloseDesc> mc;
   std::vector<CloseReduceDesc> rd; std::vector<int> commit;
-  std::vector<SlabDesc> sd; std::vector<CloseDmmaDesc> dc; std::vector<DeepDesc> dd;
+  std::vector<SlabDesc> sd; std::vector<CloseDmmaDesc> dc; std::vector<DeepDesc> dd, da;
   std::vector<CloseReduceDesc> frd;            // epilogues of the fast-path chains, in the order of `dc`
   // pass 1: scratch requirement per chain, sub-level split, global scratch sizing
   struct ChainMem { size_t buf_elems; int nbuf; int nsplit; size_t partial_elems; };
@@ -580,27 +581,78 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
           }
         }
       }
-      // deep path: degree-5 / degree-6 chains at N = 8
-      sl.deep.off = dd.size();
-      for (size_t j = 0; j < sub.size(); ++j) {
-        const Chain& ch = chains[sub[j]];
-        const int E4 = deep_path_E4(c, ch);
-        if (!E4) continue;
-        fast[j] = 2;
-        const int v = ch.v, F = (int)ch.absorb.size();
-        DeepDesc a; a.t = c->site[v]; a.bt = c->bra_site(v); a.x = buf0[j]; a.partial = partial + fast_poff[j]; a.E4 = E4;
-        long long stride = 2; int ai = 0;
-        for (int l = 0; l < (int)c->inc[v].size(); ++l) {
-          if (l == ch.close_leg) a.gw = stride;
-          else { a.g[ai] = stride; a.m[ai] = ch.absorb[ai].mat; ++ai; }
-          stride *= 8;
+      // deep path: degree-5 / degree-6 chains at N = 8.  The six updates leaving a degree-6 vertex in one sub-level share their
+      // three-leg products: T x m0 x m1 x m2 serves the updates on legs 3, 4, 5 and T x m3 x m4 x m5 those on legs 0, 1, 2 - two
+      // k_deep_absorb items per vertex instead of six; the tile keeps the three open legs in ascending order and every update reads
+      // it with its own strides (DeepDesc::xs).
+      sl.deep.off = dd.size(); sl.deepA.off = da.size();
+      {
+        auto leg_stride = [](int l) { long long st = 2; for (int i = 0; i < l; ++i) st *= 8; return st; };
+        size_t j0 = 0;
+        while (j0 < sub.size()) {
+          const int v = chains[sub[j0]].v;
+          size_t j1 = j0;
+          while (j1 < sub.size() && chains[sub[j1]].v == v) ++j1;
+          const int z = (int)c->inc[v].size();
+          // whole group eligible for sharing?
+          bool group = !share_disabled() && z == 6 && (int)(j1 - j0) == 6;
+          int by_leg[6] = {-1, -1, -1, -1, -1, -1}; const cplx* mat[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+          for (size_t j = j0; group && j < j1; ++j) {
+            const Chain& ch = chains[sub[j]];
+            group = deep_path_E4(c, ch) == 8 && by_leg[ch.close_leg] < 0;
+            if (!group) break;
+            by_leg[ch.close_leg] = (int)j;
+            for (const Absorb& ab : ch.absorb) { if (mat[ab.leg] && mat[ab.leg] != ab.mat) group = false; mat[ab.leg] = ab.mat; }
+          }
+          if (group) {
+            for (int half = 0; half < 2; ++half) {
+              const int s0 = half ? 3 : 0, u0 = half ? 0 : 3;            // slab legs s0 .. s0 + 2, open legs u0 .. u0 + 2
+              DeepDesc a; a.t = c->site[v]; a.bt = c->bra_site(v); a.x = buf0[by_leg[u0]]; a.partial = nullptr; a.E4 = 8;
+              for (int i = 0; i < 3; ++i) { a.g[i] = leg_stride(s0 + i); a.m[i] = mat[s0 + i]; }
+              a.g[3] = leg_stride(u0); a.g[4] = leg_stride(u0 + 1); a.gw = leg_stride(u0 + 2);
+              a.m[3] = a.m[4] = nullptr; a.xs[0] = 8; a.xs[1] = 64; a.xs[2] = 512;
+              da.push_back(a);
+              for (int o = 0; o < 3; ++o) {                                 // the update that leaves on open leg u0 + o
+                const int j = by_leg[u0 + o];
+                const int q3 = o == 0 ? 1 : 0, q4 = o == 2 ? 1 : 2;         // the other two open legs, ascending
+                DeepDesc b = a; b.partial = partial + fast_poff[j];
+                b.g[3] = leg_stride(u0 + q3); b.g[4] = leg_stride(u0 + q4); b.gw = leg_stride(u0 + o);
+                b.m[3] = mat[u0 + q3]; b.m[4] = mat[u0 + q4];
+                const int tile_stride[3] = {8, 64, 512};                    // open legs in ascending order behind p0'
+                b.xs[0] = tile_stride[q3]; b.xs[1] = tile_stride[q4]; b.xs[2] = tile_stride[o];
+                dd.push_back(b); fast[j] = 2;
+                plan.flops += 8.0 * (double)c->site_n[v] * 8 * 6;
+              }
+            }
+            // dd must follow the chain order of the sub-level for the reduce descriptors?  No: reduce descriptors address the partials
+            // through fast_poff[j], which the B items above carry themselves.
+          } else {
+            for (size_t j = j0; j < j1; ++j) {
+              const Chain& ch = chains[sub[j]];
+              const int E4 = deep_path_E4(c, ch);
+              if (!E4) continue;
+              fast[j] = 2;
+              const int F = (int)ch.absorb.size();
+              DeepDesc a; a.t = c->site[v]; a.bt = c->bra_site(v); a.x = buf0[j]; a.partial = partial + fast_poff[j]; a.E4 = E4;
+              long long stride = 2; int ai = 0;
+              for (int l = 0; l < z; ++l) {
+                if (l == ch.close_leg) a.gw = stride;
+                else { a.g[ai] = stride; a.m[ai] = ch.absorb[ai].mat; ++ai; }
+                stride *= 8;
+              }
+              for (; ai < 5; ++ai) { a.g[ai] = 0; a.m[ai] = nullptr; }
+              a.xs[0] = 8; a.xs[1] = 64; a.xs[2] = 64 * E4;
+              dd.push_back(a); da.push_back(a);
+              plan.flops += 8.0 * (double)c->site_n[v] * 8 * (F + 1);
+            }
+          }
+          j0 = j1;
         }
-        for (; ai < 5; ++ai) { a.g[ai] = 0; a.m[ai] = nullptr; }
-        dd.push_back(a);
-        plan.flops += 8.0 * (double)c->site_n[v] * 8 * (F + 1);
       }
       sl.deep.count = (int)(dd.size() - sl.deep.off);
       sl.deep.grid = dim3(2 * 8 * 8, std::max(1, sl.deep.count), 1);
+      sl.deepA.count = (int)(da.size() - sl.deepA.off);
+      sl.deepA.grid = dim3(2 * 8 * 8, std::max(1, sl.deepA.count), 1);
       // one-site operators
       sl.gate1.off = g1.size();
       long long maxrest = 0;
@@ -754,11 +806,12 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
   // fast-path epilogues live behind the generic reduce descriptors in one array; tickets: one int per fast chain
   const size_t nrd_generic = rd.size();
   rd.insert(rd.end(), frd.begin(), frd.end());
-  const size_t cnt[9] = {g1.size(), ma.size(), mc.size(), rd.size(), commit.size(), sd.size(), dc.size(), items.size(), dd.size()};
+  const size_t cnt[10] = {g1.size(), ma.size(), mc.size(), rd.size(), commit.size(), sd.size(), dc.size(), items.size(), dd.size(), da.size()};
   bool same = reuse_mem;
-  for (int i = 0; i < 9 && same; ++i) same = cnt[i] == reuse->cnt[i];
-  for (int i = 0; i < 9; ++i) plan.cnt[i] = cnt[i];
+  for (int i = 0; i < 10 && same; ++i) same = cnt[i] == reuse->cnt[i];
+  for (int i = 0; i < 10; ++i) plan.cnt[i] = cnt[i];
   plan.d_deep = upload_into(c, same ? reuse->d_deep : nullptr, dd);
+  plan.d_deepA = upload_into(c, same ? reuse->d_deepA : nullptr, da);
   plan.d_gate1 = upload_into(c, same ? reuse->d_gate1 : nullptr, g1); plan.d_apply = upload_into(c, same ? reuse->d_apply : nullptr, ma);
   plan.d_close = upload_into(c, same ? reuse->d_close : nullptr, mc); plan.d_reduce = upload_into(c, same ? reuse->d_reduce : nullptr, rd);
   plan.d_commit = upload_into(c, same ? reuse->d_commit : nullptr, commit);
@@ -981,13 +1034,13 @@ static bool same_launches(const Plan& a, const Plan& b) {
                       a.sweep_commit == b.sweep_commit && a.d_items == b.d_items && a.d_qctr == b.d_qctr && a.d_slab == b.d_slab && a.d_dclose == b.d_dclose &&
                       a.d_chains == b.d_chains && a.d_slab_done == b.d_slab_done && a.d_chain_done == b.d_chain_done && a.d_commit == b.d_commit;
   if (a.levels.size() != b.levels.size() || a.d_slab != b.d_slab || a.d_items != b.d_items || a.d_qctr != b.d_qctr || a.d_slab_done != b.d_slab_done || a.d_apply != b.d_apply || a.d_close != b.d_close ||
-      a.d_reduce != b.d_reduce || a.d_dclose != b.d_dclose || a.d_gate1 != b.d_gate1 || a.d_commit != b.d_commit || a.d_deep != b.d_deep) return false;
+      a.d_reduce != b.d_reduce || a.d_dclose != b.d_dclose || a.d_gate1 != b.d_gate1 || a.d_commit != b.d_commit || a.d_deep != b.d_deep || a.d_deepA != b.d_deepA) return false;
   for (size_t L = 0; L < a.levels.size(); ++L) {
     const LevelPlan &x = a.levels[L], &y = b.levels[L];
     if (x.subs.size() != y.subs.size() || x.commit_off != y.commit_off || x.commit_count != y.commit_count) return false;
     for (size_t i = 0; i < x.subs.size(); ++i) {
       const SubLevel &p = x.subs[i], &q = y.subs[i];
-      if (p.fastN != q.fastN || p.close_cap != q.close_cap || p.steps.size() != q.steps.size() || !same_rec(p.slab, q.slab) || !same_rec(p.dclose, q.dclose) || !same_rec(p.fused, q.fused) || !same_rec(p.deep, q.deep) ||
+      if (p.fastN != q.fastN || p.close_cap != q.close_cap || p.steps.size() != q.steps.size() || !same_rec(p.slab, q.slab) || !same_rec(p.dclose, q.dclose) || !same_rec(p.fused, q.fused) || !same_rec(p.deep, q.deep) || !same_rec(p.deepA, q.deepA) ||
           !same_rec(p.gate1, q.gate1) || !same_rec(p.close, q.close) || !same_rec(p.reduce, q.reduce)) return false;
       for (size_t j = 0; j < p.steps.size(); ++j) if (!same_rec(p.steps[j], q.steps[j])) return false;
     }
@@ -1043,7 +1096,7 @@ static void run_plan(tnqs_ctx* c, const Plan& p) {
         }
       }
       if (sl.deep.count) {
-        LAUNCH(c, TNQS_KC_MODE_APPLY, k_deep_absorb<8>, sl.deep.grid, DeepCfg<8>::THREADS, DeepCfg<8>::SMEM_A, p.d_deep + sl.deep.off);
+        LAUNCH(c, TNQS_KC_MODE_APPLY, k_deep_absorb<8>, sl.deepA.grid, DeepCfg<8>::THREADS, DeepCfg<8>::SMEM_A, p.d_deepA + sl.deepA.off);
         LAUNCH(c, TNQS_KC_MODE_CLOSE, k_deep_close<8>, sl.deep.grid, DeepCfg<8>::THREADS, DeepCfg<8>::SMEM_B, p.d_deep + sl.deep.off);
       }
       if (sl.gate1.count) LAUNCH(c, TNQS_KC_MISC, k_gate1, sl.gate1.grid, 256, 0, p.d_gate1 + sl.gate1.off);

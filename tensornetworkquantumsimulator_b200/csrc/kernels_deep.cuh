@@ -26,6 +26,8 @@ struct DeepDesc {
   long long g[5];         // canonical strides (complex elements) of p0 .. p4 (g[4] = 0 with four absorbed legs)
   long long gw;           // canonical stride of the outgoing leg
   int E4;                 // extent of p4: N (five absorbed legs) or 1 (four)
+  int xs[3];              // k_deep_close: strides of p3, p4 and w inside a tile (N, N^2, N^2 E4 for a tile of its own; a tile shared by the
+                          // three updates of a degree-6 vertex keeps its open legs in ascending order and each update permutes them)
 };
 
 #ifndef TNQS_DEEP_THREADS
@@ -175,7 +177,8 @@ __global__ void __launch_bounds__(DEEP_THREADS, DEEP_CTAS) k_deep_close(const De
     for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) { msm[idx] = __ldg(m3 + idx); if (E4 == N) msm[N * N + idx] = __ldg(m4 + idx); }
   }
   const long long TS = (long long)N * N * N * E4;
-  const cplx* const xt = d.x + (long long)y * TS + (long long)N * N * E4 * warp;       // warp w owns sub-slab i3 = w through both absorptions
+  const int xs3 = d.xs[0], xs4 = d.xs[1];
+  const cplx* const xt = d.x + (long long)y * TS + (long long)d.xs[2] * warp;          // warp w owns sub-slab i3 = w through both absorptions
   // closing operands: descriptor scalars and the first bra elements are requested before the absorption phases
   const cplx* const bt = d.bt + s + (long long)p1 * d.g[1] + (long long)p2 * d.g[2] + (long long)r * d.gw;
   const long long g0 = d.g[0], g3 = d.g[3], g4 = d.g[4];
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(DEEP_THREADS, DEEP_CTAS) k_deep_close(const De
   __syncthreads();
   // p3: rows (p0', p4) straight from the tile [w][p4][p3][p0']
   if (!(TNQS_DEEP_ABLATE & 8)) deep_phase<N, TNQS_DEEP_DEPTH>(msm, 0, E4,
-                [=](int rho, int b) -> const cplx* { return xt + rho % N + N * b + N * N * (rho / N); },
+                [=](int rho, int b) -> const cplx* { return xt + rho % N + xs3 * b + xs4 * (rho / N); },
                 [=](int rho, int c) -> cplx* { return at(c, rho % N, rho / N, warp); }, lane);
   __syncwarp();
   if (E4 == N && !(TNQS_DEEP_ABLATE & 8)) {
