@@ -5,13 +5,18 @@
 // (96 MiB of traffic per message) is HBM-bound at a fifth of the FP64 peak.  Two kernels bring that down to 32 MiB:
 //
 //   k_deep_absorb : one CTA per (s, p4, w) block of 8^4 elements: the first three absorbed legs p0, p1, p2 go through shared
-//                   memory back to back (the slab machinery of k_absorb_slab, batched over the eight values of p3); the result
-//                   is written tile-major, XA[(s, p1', p2')][w][p4][p3][p0'], in full 128-byte runs.
+//                   memory back to back (the slab machinery of k_absorb_slab; warp p3 owns sub-slab p3 through all three phases,
+//                   so there is no CTA-wide barrier between them); the result is written tile-major,
+//                   XA[(s, p1', p2')][w][p4][p3][p0'], in full 128-byte runs.
 //   k_deep_close  : one CTA per (s, p1', p2') tile (contiguous 64 KB of XA): absorbs p3 on the way into shared memory and p4 in
 //                   place, then closes G[w, w'] += sum_{p0', p3', p4'} X[p0', p3', p4', w] conj(B[s, p0', p1', p2', p3', p4', w'])
 //                   with the X operand in shared memory and the bra operand streamed from global memory as DMMA fragments:
 //                   the fully absorbed tensor never exists in memory.  Each CTA leaves one N x N partial; k_close_reduce sums
 //                   the 2 N^2 partials of a message in a fixed order and runs the message epilogue.
+//                   In a JACOBI sweep the six updates that leave a degree-6 vertex share two k_deep_absorb items (legs 0-2 for the
+//                   updates on legs 3-5 and vice versa): the tile then keeps its three open legs in ascending order and every
+//                   update reads it with its own strides (DeepDesc::xs; engine.cuh build_plan).
+//   k_slab_batch  : the same warp-owned sub-slab with free strides, for sqrt(M) absorptions of the gate path (at the end of this file).
 // (updated_message, src/MessagePassing/abstractbeliefpropagationcache.jl:144-166; same contraction, another association order.)
 // Complex products are 3M (three real DMMA products), with the fragment-column permutation of absorb_phase (kernels_dmma.cuh).
 #pragma once
