@@ -554,6 +554,14 @@ def test_chunked_levels_and_gate_batches(E, monkeypatch):
     bj.messages = {k: O.updated_message(bj, k) for k in range(2 * g.ne)}
     ej = E.update(to_engine(psi_o, chi_cap=8), maxiter=1, edge_sequence=np.arange(2 * g.ne), mode="jacobi")
     check_messages(E, ej, bj)
+    # generic (leg-by-leg) chains under the same budget: 40 KB of scratch per chain at chi = 5, so the JACOBI level is cut into
+    # sub-levels and the cuts fall inside the group of updates of one vertex - those fall back from shared to separate absorptions
+    psi5 = O.random_tensornetworkstate(g, bond_dimension=5, seed=72)
+    b5 = O.BeliefPropagationCache(psi5)
+    for _ in range(2):
+        b5.messages = {k: O.updated_message(b5, k) for k in range(2 * g.ne)}
+    e5 = E.update(to_engine(psi5, chi_cap=5), maxiter=2, edge_sequence=np.arange(2 * g.ne), mode="jacobi")
+    check_messages(E, e5, b5)
     grp = G.grid_edge_color(g)[2]
     arr = gates.gate_array(("Rxx", [0, 1], 0.6))
     dets = []
