@@ -1160,6 +1160,12 @@ def test_deep_path_with_a_bra_layer(E):
     bn = E.update(E.bilinear_cache(psi, phi), maxiter=2, edge_sequence=seq, inplace=True)
     bo = O.update(O.BeliefPropagationCache(psi_o.copy(), {}, phi_o), maxiter=2, edge_sequence=seq)
     check_messages(E, bn, bo)
+    # JACOBI order: the six updates of the centre vertex share their three-leg products of the KET, each closes against the bra
+    bj = O.BeliefPropagationCache(psi_o.copy(), {}, phi_o)
+    for _ in range(2):
+        bj.messages = {k: O.updated_message(bj, k) for k in range(2 * g.ne)}
+    ej = E.update(E.bilinear_cache(psi, phi), maxiter=2, edge_sequence=np.arange(2 * g.ne), mode="jacobi", inplace=True)
+    check_messages(E, ej, bj)
 
 
 def test_bilinear_form_outlives_its_cache_and_checks_shapes(E):
