@@ -450,10 +450,13 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
     // (a region still at 8 next to one at 16 under a cutoff-driven truncation) therefore cost one more launch pair, not an error.
     std::vector<int> order(chains.size()), fN(chains.size());
     for (size_t i = 0; i < chains.size(); ++i) { order[i] = (int)i; fN[i] = fast_path_N(c, chains[i]); }
-    // generic chains are taken vertex by vertex, so that the updates leaving one vertex land in one sub-level (shared absorptions)
+    // chains are taken vertex by vertex: the updates leaving one vertex land in one sub-level (shared absorptions of the generic
+    // chains) and next to each other in the batched launches (they read the same site tensor: L2).  TNQS_BP_VSORT=0: generic only.
+    static int vsort = -1;
+    if (vsort < 0) { const char* e = getenv("TNQS_BP_VSORT"); vsort = (e && e[0] == '0') ? 0 : 1; }
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
       if (fN[a] != fN[b]) return fN[a] < fN[b];
-      return fN[a] == 0 && chains[a].v < chains[b].v;
+      return (fN[a] == 0 || vsort) && chains[a].v < chains[b].v;
     });
     int curN = 0;
     for (int i : order) {
