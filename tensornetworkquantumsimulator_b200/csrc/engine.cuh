@@ -598,16 +598,55 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
           while (j1 < sub.size() && chains[sub[j1]].v == v) ++j1;
           const int z = (int)c->inc[v].size();
           // whole group eligible for sharing?
-          bool group = !share_disabled() && z == 6 && (int)(j1 - j0) == 6;
+          bool group = !share_disabled() && (z == 6 || z == 5) && (int)(j1 - j0) == z;
           int by_leg[6] = {-1, -1, -1, -1, -1, -1}; const cplx* mat[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
           for (size_t j = j0; group && j < j1; ++j) {
             const Chain& ch = chains[sub[j]];
-            group = deep_path_E4(c, ch) == 8 && by_leg[ch.close_leg] < 0;
+            group = deep_path_E4(c, ch) == (z == 6 ? 8 : 1) && by_leg[ch.close_leg] < 0;
             if (!group) break;
             by_leg[ch.close_leg] = (int)j;
             for (const Absorb& ab : ch.absorb) { if (mat[ab.leg] && mat[ab.leg] != ab.mat) group = false; mat[ab.leg] = ab.mat; }
           }
-          if (group) {
+          // the per-message item pair of one chain (its own three-leg product)
+          auto single = [&](size_t j) {
+            const Chain& ch = chains[sub[j]];
+            const int E4 = deep_path_E4(c, ch);
+            if (!E4) return;
+            fast[j] = 2;
+            const int F = (int)ch.absorb.size();
+            DeepDesc a; a.t = c->site[v]; a.bt = c->bra_site(v); a.x = buf0[j]; a.partial = partial + fast_poff[j]; a.E4 = E4;
+            long long stride = 2; int ai = 0;
+            for (int l = 0; l < z; ++l) {
+              if (l == ch.close_leg) a.gw = stride;
+              else { a.g[ai] = stride; a.m[ai] = ch.absorb[ai].mat; ++ai; }
+              stride *= 8;
+            }
+            for (; ai < 5; ++ai) { a.g[ai] = 0; a.m[ai] = nullptr; }
+            a.xs[0] = 8; a.xs[1] = 64; a.xs[2] = 64 * E4;
+            dd.push_back(a); da.push_back(a);
+            plan.flops += 8.0 * (double)c->site_n[v] * 8 * (F + 1);
+          };
+          if (group && z == 5) {
+            // degree 5: T x m0 x m1 x m2 serves the updates on legs 3 and 4, T x m2 x m3 x m4 those on legs 0 and 1 (tile
+            // [open leg 2][open leg 1][p0']); the update on leg 2 keeps its own product - three k_deep_absorb items instead of five
+            for (int half = 0; half < 2; ++half) {
+              const int s0 = half ? 2 : 0, u0 = half ? 0 : 3;
+              DeepDesc a; a.t = c->site[v]; a.bt = c->bra_site(v); a.x = buf0[by_leg[u0]]; a.partial = nullptr; a.E4 = 1;
+              for (int i = 0; i < 3; ++i) { a.g[i] = leg_stride(s0 + i); a.m[i] = mat[s0 + i]; }
+              a.g[3] = leg_stride(u0); a.g[4] = 0; a.gw = leg_stride(u0 + 1);
+              a.m[3] = a.m[4] = nullptr; a.xs[0] = 8; a.xs[1] = 64; a.xs[2] = 64;
+              da.push_back(a);
+              for (int o = 0; o < 2; ++o) {                                 // the update that leaves on open leg u0 + o absorbs the other one
+                const int j = by_leg[u0 + o], other = u0 + 1 - o;
+                DeepDesc b = a; b.partial = partial + fast_poff[j];
+                b.g[3] = leg_stride(other); b.gw = leg_stride(u0 + o); b.m[3] = mat[other];
+                b.xs[0] = o == 0 ? 64 : 8; b.xs[1] = 64; b.xs[2] = o == 0 ? 8 : 64;
+                dd.push_back(b); fast[j] = 2;
+                plan.flops += 8.0 * (double)c->site_n[v] * 8 * 5;
+              }
+            }
+            single((size_t)by_leg[2]);
+          } else if (group) {
             for (int half = 0; half < 2; ++half) {
               const int s0 = half ? 3 : 0, u0 = half ? 0 : 3;            // slab legs s0 .. s0 + 2, open legs u0 .. u0 + 2
               DeepDesc a; a.t = c->site[v]; a.bt = c->bra_site(v); a.x = buf0[by_leg[u0]]; a.partial = nullptr; a.E4 = 8;
@@ -627,27 +666,9 @@ static Plan build_plan(tnqs_ctx* c, const std::vector<std::vector<Chain>>& level
                 plan.flops += 8.0 * (double)c->site_n[v] * 8 * 6;
               }
             }
-            // dd must follow the chain order of the sub-level for the reduce descriptors?  No: reduce descriptors address the partials
-            // through fast_poff[j], which the B items above carry themselves.
+            // (the items need not follow the chain order of the sub-level: every one carries the partial buffer of its chain)
           } else {
-            for (size_t j = j0; j < j1; ++j) {
-              const Chain& ch = chains[sub[j]];
-              const int E4 = deep_path_E4(c, ch);
-              if (!E4) continue;
-              fast[j] = 2;
-              const int F = (int)ch.absorb.size();
-              DeepDesc a; a.t = c->site[v]; a.bt = c->bra_site(v); a.x = buf0[j]; a.partial = partial + fast_poff[j]; a.E4 = E4;
-              long long stride = 2; int ai = 0;
-              for (int l = 0; l < z; ++l) {
-                if (l == ch.close_leg) a.gw = stride;
-                else { a.g[ai] = stride; a.m[ai] = ch.absorb[ai].mat; ++ai; }
-                stride *= 8;
-              }
-              for (; ai < 5; ++ai) { a.g[ai] = 0; a.m[ai] = nullptr; }
-              a.xs[0] = 8; a.xs[1] = 64; a.xs[2] = 64 * E4;
-              dd.push_back(a); da.push_back(a);
-              plan.flops += 8.0 * (double)c->site_n[v] * 8 * (F + 1);
-            }
+            for (size_t j = j0; j < j1; ++j) single(j);
           }
           j0 = j1;
         }
