@@ -120,3 +120,41 @@ def test_hexagonal_lattice_is_the_networkx_generator():
         assert min(g.degree(v) for v in range(g.nv)) == 2
     hh = G.heavy_hexagonal_lattice(5, 5)
     assert (hh.nv, hh.ne) == (164, 188)
+
+
+def _dependency_levels(g, seq):
+    """Levels of a sequential (Gauss-Seidel) sweep as the engine builds them: an update is placed strictly after
+    the last write of every message it reads (RAW), after the last read of the message it writes (WAR) and after its last write (WAW)."""
+    into = {}
+    for k in range(2 * g.ne):
+        into.setdefault(g.ddst(k), []).append(k)
+    last_write = np.full(2 * g.ne, -1)
+    last_read = np.full(2 * g.ne, -1)
+    level = {}
+    for k in (int(x) for x in seq):
+        ins = [m for m in into[g.dsrc(k)] if m != (k ^ 1)]
+        lv = max([0] + [last_write[m] + 1 for m in ins] + [last_read[k] + 1, last_write[k] + 1])
+        level[k] = lv
+        for m in ins:
+            last_read[m] = max(last_read[m], lv)
+        last_write[k] = lv
+    return level
+
+
+@pytest.mark.parametrize("dims", [(16, 16), (8, 8, 8)])
+def test_reference_order_never_updates_two_messages_of_an_interior_vertex_in_one_level(dims):
+    # why the shared partial products of the JACOBI sweeps (DESIGN.md sections 4 and 6) have no counterpart in the reference's order:
+    # in the forest-cover sequence of an open grid the updates that leave one interior vertex always sit in different dependency
+    # levels, i.e. some message they read changes in between
+    g = G.named_grid(dims)
+    level = _dependency_levels(g, G.forest_cover_edge_sequence(g))
+    assert len(level) == 2 * g.ne
+    zmax = 2 * len(dims)
+    seen = set()
+    for k, lv in level.items():
+        v = g.dsrc(k)
+        if g.degree(v) == zmax:
+            assert (v, lv) not in seen
+            seen.add((v, lv))
+    # levels are what makes the order parallel at all: far fewer levels than messages
+    assert max(level.values()) + 1 < g.ne // 4
